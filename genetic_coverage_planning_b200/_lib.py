@@ -1,0 +1,82 @@
+"""ctypes binding of libgcp.so (include/gcp.h).  No fallback: if the CUDA library is
+missing or does not load, importing the engine raises."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgcp.so")
+
+GCP_ABI_VERSION = 1
+GCP_MAX_AGENTS = 32
+INVALID_EDGE = 0xFFFFFFFF
+
+
+class GcpParams(C.Structure):
+    _fields_ = [("num_agents", C.c_int32), ("max_dna_len", C.c_int32),
+                ("solo_sep_thresh", C.c_int32), ("min_solo_lcs", C.c_int32),
+                ("min_comb_lcs", C.c_int32), ("reserved0", C.c_int32),
+                ("flight_time_scale", C.c_double), ("coverage_blend", C.c_double),
+                ("one_minus_blend", C.c_double)]
+
+
+class GcpMapConsts(C.Structure):
+    _fields_ = [("height", C.c_int32), ("width", C.c_int32), ("nbx", C.c_int32),
+                ("nby", C.c_int32), ("mask_size", C.c_int64), ("gsum_mask", C.c_int64),
+                ("map_size", C.c_int64), ("num_occluded", C.c_double)]
+
+
+class GcpEvalOut(C.Structure):
+    _fields_ = [("obj", C.c_void_p), ("neg_cov", C.c_void_p), ("dist", C.c_void_p),
+                ("turn", C.c_void_p), ("cov", C.c_void_p), ("lc_mat", C.c_void_p),
+                ("flags", C.c_void_p)]
+
+
+# name -> (restype, argtypes); must list every symbol include/gcp.h declares
+_vp, _u32, _u64, _i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+SIGNATURES = {
+    "gcp_abi_version": (C.c_int, []),
+    "gcp_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "gcp_destroy": (None, [_vp]),
+    "gcp_last_error": (C.c_char_p, [_vp]),
+    "gcp_upload_graph": (C.c_int, [_vp, _u32, _u32, _vp, _vp, _vp, _vp]),
+    "gcp_upload_edges": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _u64, _vp, _u64]),
+    "gcp_upload_map": (C.c_int, [_vp, C.POINTER(GcpMapConsts), _vp, _vp, _vp, _vp, _u64]),
+    "gcp_set_params": (C.c_int, [_vp, C.POINTER(GcpParams)]),
+    "gcp_eval_scratch_bytes": (C.c_size_t, [_vp, _u32]),
+    "gcp_eval": (C.c_int, [_vp, _vp, _u32, C.POINTER(GcpEvalOut), _vp, C.c_size_t, _vp]),
+    "gcp_path_costs": (C.c_int, [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "gcp_coverage": (C.c_int, [_vp, _vp, _u32, _vp, _vp, _vp]),
+    "gcp_loop_closures": (C.c_int, [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gcp_eval_host": (C.c_int, [_vp, _vp, _u32, _vp, _vp]),
+    "gcp_rank_scratch_bytes": (C.c_size_t, [_vp, _u32]),
+    "gcp_maximin": (C.c_int, [_vp, _vp, _u32, C.c_double, _u32, _u32, _vp, _vp, _vp,
+                              C.c_size_t, _vp]),
+    "gcp_arena_order": (C.c_int, [_vp, _vp, _u32, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "gcp_launch_count": (C.c_uint64, [_vp]),
+    "gcp_set_timing": (C.c_int, [_vp, C.c_int]),
+    "gcp_stage_ms": (C.c_float, [_vp, C.c_int]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libgcp.so and bind every entry point.  Raises if the library is absent:
+    build it with `python -m genetic_coverage_planning_b200.build`."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libgcp.so not built (%s); run `python -m "
+                          "genetic_coverage_planning_b200.build` - there is no CPU fallback"
+                          % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    if lib.gcp_abi_version() != GCP_ABI_VERSION:
+        raise ImportError("libgcp.so ABI %d != binding %d" % (lib.gcp_abi_version(),
+                                                              GCP_ABI_VERSION))
+    _lib = lib
+    return lib

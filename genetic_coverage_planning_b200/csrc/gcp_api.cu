@@ -1,0 +1,319 @@
+// C ABI (include/gcp.h): context, table upload, stage dispatch.  Host code only.
+#include "gcp_common.cuh"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+size_t rank_scratch_bytes(gcp_ctx* ctx, uint32_t n);
+
+static std::string g_create_err;
+
+int gcp_fail(gcp_ctx* ctx, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_err = buf;
+    return code;
+}
+
+extern "C" {
+
+int gcp_abi_version(void) { return GCP_ABI_VERSION; }
+
+const char* gcp_last_error(gcp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int gcp_create(gcp_ctx** out, int device)
+{
+    if (!out) return gcp_fail(nullptr, -1, "gcp_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return gcp_fail(nullptr, -2, "gcp_create: no CUDA device (%s); this engine has no CPU path",
+                        cudaGetErrorString(e));
+    if (device < 0 || device >= n) return gcp_fail(nullptr, -1, "gcp_create: bad device %d", device);
+    gcp_ctx* c = new (std::nothrow) gcp_ctx();
+    if (!c) return gcp_fail(nullptr, -4, "out of host memory");
+    c->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) {
+        delete c;
+        return gcp_fail(nullptr, -2, "cudaSetDevice: %s", cudaGetErrorString(e));
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    c->num_sms = prop.multiProcessorCount;
+    c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    for (int s = 0; s < GCP_NUM_STAGES; ++s) {
+        cudaEventCreate(&c->ev_beg[s]);
+        cudaEventCreate(&c->ev_end[s]);
+    }
+    *out = c;
+    return 0;
+}
+
+void gcp_destroy(gcp_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (int i = 0; i < c->n_owned; ++i) cudaFree(c->owned[i]);
+    if (c->stage_dev) cudaFree(c->stage_dev);
+    for (int s = 0; s < 2; ++s) if (c->hstream[s]) cudaStreamDestroy(c->hstream[s]);
+    for (int s = 0; s < GCP_NUM_STAGES; ++s) { cudaEventDestroy(c->ev_beg[s]); cudaEventDestroy(c->ev_end[s]); }
+    delete c;
+}
+
+} // extern "C"
+
+template <typename T>
+static int upload(gcp_ctx* c, const T** dst, const void* src, size_t count)
+{
+    void* p = nullptr;
+    const size_t bytes = (count ? count : 1) * sizeof(T);
+    GCP_CUDA(c, cudaMalloc(&p, bytes));
+    if (c->n_owned >= 32) return gcp_fail(c, -4, "too many table uploads (upload each table once)");
+    c->owned[c->n_owned++] = p;
+    if (count) GCP_CUDA(c, cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = reinterpret_cast<const T*>(p);
+    return 0;
+}
+
+extern "C" {
+
+int gcp_upload_graph(gcp_ctx* c, uint32_t N, uint32_t E, const uint32_t* row_ptr,
+                     const uint32_t* col, const int32_t* xy, const uint8_t* xover)
+{
+    if (!c) return -1;
+    if (c->have_graph) return gcp_fail(c, -1, "graph already uploaded (create a new ctx)");
+    if (N == 0 || N >= (1u << 24)) return gcp_fail(c, -1, "need 0 < N < 2^24 waypoints, got %u", N);
+    if (row_ptr[N] != E) return gcp_fail(c, -1, "row_ptr[N]=%u != E=%u", row_ptr[N], E);
+    GCP_CUDA(c, cudaSetDevice(c->device));
+    int r;
+    if ((r = upload(c, &c->t.row_ptr, row_ptr, (size_t)N + 1))) return r;
+    if ((r = upload(c, &c->t.col, col, E))) return r;
+    if ((r = upload(c, &c->t.xy, xy, (size_t)N))) return r;           // int2 = 2 x int32
+    if ((r = upload(c, &c->t.xover, xover, N))) return r;
+    c->t.N = N; c->t.E = E;
+    c->have_graph = true;
+    return 0;
+}
+
+int gcp_upload_edges(gcp_ctx* c, const double* edge_cost, const double* edge_theta,
+                     const uint32_t* sub_ptr, const uint32_t* sub_block,
+                     const uint32_t* sub_payload, uint64_t n_sub, const uint64_t* tile_data,
+                     uint64_t n_quarters)
+{
+    if (!c) return -1;
+    if (!c->have_graph) return gcp_fail(c, -1, "upload the graph first");
+    if (c->have_edges) return gcp_fail(c, -1, "edges already uploaded");
+    const size_t EN = (size_t)c->t.E + c->t.N;
+    if (sub_ptr[EN] != n_sub) return gcp_fail(c, -1, "sub_ptr[E+N] != n_sub");
+    if (n_quarters >= (1ull << 28)) return gcp_fail(c, -1, "footprint store too large");
+    GCP_CUDA(c, cudaSetDevice(c->device));
+    int r;
+    if ((r = upload(c, &c->t.edge_cost, edge_cost, EN))) return r;     // double2
+    if ((r = upload(c, &c->t.edge_theta, edge_theta, c->t.E))) return r;
+    if ((r = upload(c, &c->t.sub_ptr, sub_ptr, EN + 1))) return r;
+    if ((r = upload(c, &c->t.sub_block, sub_block, n_sub))) return r;
+    if ((r = upload(c, &c->t.sub_payload, sub_payload, n_sub))) return r;
+    if ((r = upload(c, &c->t.tile, tile_data, (size_t)n_quarters * 8))) return r;   // uint4
+    c->n_sub = n_sub; c->n_quarters = n_quarters;
+    c->have_edges = true;
+    return 0;
+}
+
+int gcp_upload_map(gcp_ctx* c, const gcp_map_consts* mc, const uint64_t* blk_mask0,
+                   const uint64_t* blk_free0, const uint32_t* gray_ptr, const uint32_t* gray_ent,
+                   uint64_t n_gray)
+{
+    if (!c || !mc) return -1;
+    if (c->have_map) return gcp_fail(c, -1, "map already uploaded");
+    const size_t nb = (size_t)mc->nbx * mc->nby;
+    if (nb == 0 || nb >= (1u << 28)) return gcp_fail(c, -1, "bad block grid %d x %d", mc->nbx, mc->nby);
+    if (gray_ptr[nb] != n_gray) return gcp_fail(c, -1, "gray_ptr[nb] != n_gray");
+    GCP_CUDA(c, cudaSetDevice(c->device));
+    int r;
+    if ((r = upload(c, &c->t.blk_mask0, blk_mask0, nb * 32))) return r;    // uint4
+    if ((r = upload(c, &c->t.blk_free0, blk_free0, nb * 32))) return r;
+    if ((r = upload(c, &c->t.gray_ptr, gray_ptr, nb + 1))) return r;
+    if ((r = upload(c, &c->t.gray_ent, gray_ent, n_gray))) return r;
+    c->t.n_blocks = (uint32_t)nb;
+    c->mc = *mc;
+    c->n_gray = n_gray;
+    c->have_map = true;
+    return 0;
+}
+
+int gcp_set_params(gcp_ctx* c, const gcp_params* p)
+{
+    if (!c || !p) return -1;
+    if (p->num_agents < 1 || p->num_agents > GCP_MAX_AGENTS)
+        return gcp_fail(c, -1, "num_agents must be in [1,%d]", GCP_MAX_AGENTS);
+    if (p->max_dna_len < 2) return gcp_fail(c, -1, "max_dna_len must be >= 2");
+    if ((int64_t)p->num_agents * p->max_dna_len > 65535)
+        return gcp_fail(c, -1, "num_agents*max_dna_len must be <= 65535");
+    c->p = *p;
+    c->have_params = true;
+    return 0;
+}
+
+static int ready(gcp_ctx* c)
+{
+    if (!c) return -1;
+    if (!(c->have_graph && c->have_edges && c->have_map && c->have_params))
+        return gcp_fail(c, -1, "tables/params not uploaded (graph=%d edges=%d map=%d params=%d)",
+                        c->have_graph, c->have_edges, c->have_map, c->have_params);
+    return 0;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t gcp_eval_scratch_bytes(gcp_ctx* c, uint32_t P)
+{
+    if (!c || !c->have_params) return 0;
+    const size_t A = c->p.num_agents, L = c->p.max_dna_len;
+    return align256(P * A * L * 4) + 2 * align256(P * A * 8) + align256((size_t)P * 32) +
+           align256((size_t)P * 4) + 256;
+}
+
+int gcp_path_costs(gcp_ctx* c, const int32_t* dna, uint32_t P, uint32_t* edge_ids, double* dist,
+                   double* turn, uint8_t* flags, void* stream)
+{
+    int r = ready(c); if (r) return r;
+    return launch_path_costs(c, dna, P, edge_ids, dist, turn, flags, (cudaStream_t)stream);
+}
+
+int gcp_coverage(gcp_ctx* c, const uint32_t* edge_ids, uint32_t P, uint32_t* cov, uint8_t* flags,
+                 void* stream)
+{
+    int r = ready(c); if (r) return r;
+    return launch_coverage(c, edge_ids, P, cov, flags, (cudaStream_t)stream);
+}
+
+int gcp_loop_closures(gcp_ctx* c, const int32_t* dna, uint32_t P, const double* dist,
+                      const double* turn, const uint32_t* cov, int32_t* lc, double* obj,
+                      double* neg_cov, uint8_t* flags, void* stream)
+{
+    int r = ready(c); if (r) return r;
+    return launch_loop_closures(c, dna, P, dist, turn, cov, lc, obj, neg_cov, flags,
+                                (cudaStream_t)stream);
+}
+
+int gcp_eval(gcp_ctx* c, const int32_t* dna, uint32_t P, const gcp_eval_out* out, void* scratch,
+             size_t scratch_bytes, void* stream)
+{
+    int r = ready(c); if (r) return r;
+    if (!out) return gcp_fail(c, -1, "gcp_eval: out is NULL");
+    if (P == 0) return 0;
+    if (scratch_bytes < gcp_eval_scratch_bytes(c, P) || !scratch)
+        return gcp_fail(c, -1, "gcp_eval: scratch too small (%zu < %zu)", scratch_bytes,
+                        gcp_eval_scratch_bytes(c, P));
+    const size_t A = c->p.num_agents, L = c->p.max_dna_len;
+    char* s = reinterpret_cast<char*>(scratch);
+    uint32_t* edge_ids = reinterpret_cast<uint32_t*>(s); s += align256(P * A * L * 4);
+    double* dist = reinterpret_cast<double*>(s);         s += align256(P * A * 8);
+    double* turn = reinterpret_cast<double*>(s);         s += align256(P * A * 8);
+    uint32_t* cov = reinterpret_cast<uint32_t*>(s);      s += align256((size_t)P * 32);
+    uint8_t* flags = reinterpret_cast<uint8_t*>(s);
+    if (out->dist) dist = out->dist;
+    if (out->turn) turn = out->turn;
+    if (out->cov) cov = out->cov;
+    if (out->flags) flags = out->flags;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((r = launch_path_costs(c, dna, P, edge_ids, dist, turn, flags, st))) return r;
+    if ((r = launch_coverage(c, edge_ids, P, cov, flags, st))) return r;
+    if ((r = launch_loop_closures(c, dna, P, dist, turn, cov, out->lc_mat, out->obj, out->neg_cov,
+                                  flags, st))) return r;
+    return 0;
+}
+
+int gcp_eval_host(gcp_ctx* c, const int32_t* dna_host, uint32_t P, double* obj_host,
+                  uint8_t* flags_host)
+{
+    int r = ready(c); if (r) return r;
+    if (P == 0) return 0;
+    GCP_CUDA(c, cudaSetDevice(c->device));
+    const size_t A = c->p.num_agents, L = c->p.max_dna_len;
+    // chunk so that copy-in, kernels and copy-out of neighbouring chunks overlap
+    uint32_t chunk = 8192;
+    if (chunk > P) chunk = P;
+    const size_t dna_b = align256((size_t)chunk * A * L * 4);
+    const size_t scr_b = align256(gcp_eval_scratch_bytes(c, chunk));
+    const size_t obj_b = align256((size_t)chunk * 16);
+    const size_t flg_b = align256((size_t)chunk * 4);
+    const size_t per = dna_b + scr_b + obj_b + flg_b;
+    if (c->stage_bytes < 2 * per) {
+        if (c->stage_dev) cudaFree(c->stage_dev);
+        c->stage_dev = nullptr; c->stage_bytes = 0;
+        GCP_CUDA(c, cudaMalloc(&c->stage_dev, 2 * per));
+        c->stage_bytes = 2 * per;
+    }
+    for (int s = 0; s < 2; ++s)
+        if (!c->hstream[s]) GCP_CUDA(c, cudaStreamCreateWithFlags(&c->hstream[s], cudaStreamNonBlocking));
+    int k = 0;
+    for (uint32_t o0 = 0; o0 < P; o0 += chunk, ++k) {
+        const uint32_t n = (P - o0 < chunk) ? (P - o0) : chunk;
+        cudaStream_t st = c->hstream[k & 1];
+        char* base = reinterpret_cast<char*>(c->stage_dev) + (size_t)(k & 1) * per;
+        int32_t* d_dna = reinterpret_cast<int32_t*>(base);
+        void* d_scr = base + dna_b;
+        double* d_obj = reinterpret_cast<double*>(base + dna_b + scr_b);
+        uint8_t* d_flg = reinterpret_cast<uint8_t*>(base + dna_b + scr_b + obj_b);
+        GCP_CUDA(c, cudaMemcpyAsync(d_dna, dna_host + (size_t)o0 * A * L, (size_t)n * A * L * 4,
+                                    cudaMemcpyHostToDevice, st));
+        gcp_eval_out out;
+        memset(&out, 0, sizeof(out));
+        out.obj = d_obj;
+        out.flags = d_flg;
+        if ((r = gcp_eval(c, d_dna, n, &out, d_scr, scr_b, st))) return r;
+        if (obj_host)
+            GCP_CUDA(c, cudaMemcpyAsync(obj_host + (size_t)o0 * 2, d_obj, (size_t)n * 16,
+                                        cudaMemcpyDeviceToHost, st));
+        if (flags_host)
+            GCP_CUDA(c, cudaMemcpyAsync(flags_host + (size_t)o0 * 4, d_flg, (size_t)n * 4,
+                                        cudaMemcpyDeviceToHost, st));
+    }
+    GCP_CUDA(c, cudaStreamSynchronize(c->hstream[0]));
+    GCP_CUDA(c, cudaStreamSynchronize(c->hstream[1]));
+    return 0;
+}
+
+size_t gcp_rank_scratch_bytes(gcp_ctx* c, uint32_t n) { return c ? rank_scratch_bytes(c, n) : 0; }
+
+int gcp_maximin(gcp_ctx* c, const double* obj, uint32_t n, double constr, uint32_t r0, uint32_t r1,
+                double* obj_sc, double* fit, void* scratch, size_t sb, void* stream)
+{
+    if (!c) return -1;
+    return launch_maximin(c, obj, n, constr, r0, r1, obj_sc, fit, scratch, sb, (cudaStream_t)stream);
+}
+
+int gcp_arena_order(gcp_ctx* c, const double* fit, uint32_t n, int32_t* order, uint8_t* nondom,
+                    void* scratch, size_t sb, void* stream)
+{
+    if (!c) return -1;
+    return launch_arena_order(c, fit, n, order, nondom, scratch, sb, (cudaStream_t)stream);
+}
+
+uint64_t gcp_launch_count(gcp_ctx* c) { return c ? c->launches : 0; }
+
+int gcp_set_timing(gcp_ctx* c, int enabled)
+{
+    if (!c) return -1;
+    c->timing = enabled ? 1 : 0;
+    if (!enabled) for (int s = 0; s < GCP_NUM_STAGES; ++s) c->ev_valid[s] = false;
+    return 0;
+}
+
+float gcp_stage_ms(gcp_ctx* c, int stage)
+{
+    if (!c || stage < 0 || stage >= GCP_NUM_STAGES || !c->ev_valid[stage]) return -1.0f;
+    if (cudaEventSynchronize(c->ev_end[stage]) != cudaSuccess) return -1.0f;
+    float ms = -1.0f;
+    if (cudaEventElapsedTime(&ms, c->ev_beg[stage], c->ev_end[stage]) != cudaSuccess) return -1.0f;
+    return ms;
+}
+
+} // extern "C"

@@ -1,0 +1,87 @@
+// Shared declarations of the B200 fitness engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "../../include/gcp.h"
+
+#define GCP_NUM_STAGES 8
+
+// Device-side view of the static lookup tables (uploaded once, read-only afterwards).
+struct GcpTables {
+    // graph (pathmaker.py:157-173)
+    uint32_t N, E;
+    const uint32_t* row_ptr;   // [N+1]
+    const uint32_t* col;       // [E]
+    const int2*     xy;        // [N] (row, col)
+    const uint8_t*  xover;     // [N]
+    // edges (mappy.py:274-328): ids [0,E) real, [E,E+N) null edge of node id-E
+    const double2*  edge_cost; // {dist, turn}
+    const double*   edge_theta;
+    const uint32_t* sub_ptr;   // [E+N+1]
+    const uint32_t* sub_block; // [S]
+    const uint32_t* sub_payload; // [S] (offset128<<4)|qmask
+    const uint4*    tile;      // quarters: 8 x uint4 = 16 rows of 64 px
+    // map planes, block-major: 32 x uint4 per block (lane l = rows 2l, 2l+1)
+    uint32_t n_blocks;
+    const uint4*    blk_mask0; // buffer_mask & (g==0)
+    const uint4*    blk_free0; // (g==0)
+    const uint32_t* gray_ptr;  // [n_blocks+1]
+    const uint32_t* gray_ent;  // pos(12) | (255-g)<<12 | in_mask<<20
+};
+
+struct gcp_ctx {
+    int device = -1;
+    std::string err;
+    GcpTables t{};
+    gcp_map_consts mc{};
+    gcp_params p{};
+    bool have_graph = false, have_edges = false, have_map = false, have_params = false;
+    uint64_t n_sub = 0, n_quarters = 0, n_gray = 0;
+    uint64_t launches = 0;
+    int max_smem_optin = 0;
+    int num_sms = 0;
+    // owned device allocations
+    void* owned[32] = {};
+    int n_owned = 0;
+    // timing
+    int timing = 0;
+    cudaEvent_t ev_beg[GCP_NUM_STAGES] = {}, ev_end[GCP_NUM_STAGES] = {};
+    bool ev_valid[GCP_NUM_STAGES] = {};
+    // host-eval staging (gcp_eval_host)
+    void* stage_dev = nullptr; size_t stage_bytes = 0;
+    cudaStream_t hstream[2] = {};
+    // coverage kernel tuning (0 = auto)
+    int cov_threads = 0, cov_table = 0, cov_maxpairs = 0;
+};
+
+int gcp_fail(gcp_ctx* ctx, int code, const char* fmt, ...);
+#define GCP_CUDA(ctx, call)                                                        \
+    do { cudaError_t e__ = (call);                                                 \
+         if (e__ != cudaSuccess)                                                   \
+             return gcp_fail(ctx, -2, "%s failed: %s (%s:%d)", #call,             \
+                             cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
+
+struct StageTimer {
+    gcp_ctx* c; int s; cudaStream_t st;
+    StageTimer(gcp_ctx* ctx, int stage, cudaStream_t stream) : c(ctx), s(stage), st(stream) {
+        if (c->timing) cudaEventRecord(c->ev_beg[s], st);
+    }
+    ~StageTimer() {
+        if (c->timing) { cudaEventRecord(c->ev_end[s], st); c->ev_valid[s] = true; }
+    }
+};
+
+// kernel launchers (defined in the .cu files)
+int launch_path_costs(gcp_ctx*, const int32_t* dna, uint32_t P, uint32_t* edge_ids,
+                      double* dist, double* turn, uint8_t* flags, cudaStream_t);
+int launch_coverage(gcp_ctx*, const uint32_t* edge_ids, uint32_t P, uint32_t* cov,
+                    uint8_t* flags, cudaStream_t);
+int launch_loop_closures(gcp_ctx*, const int32_t* dna, uint32_t P, const double* dist,
+                         const double* turn, const uint32_t* cov, int32_t* lc, double* obj,
+                         double* neg_cov, uint8_t* flags, cudaStream_t);
+int launch_maximin(gcp_ctx*, const double* obj, uint32_t n, double constr, uint32_t r0,
+                   uint32_t r1, double* obj_sc, double* fit, void* scratch, size_t sb,
+                   cudaStream_t);
+int launch_arena_order(gcp_ctx*, const double* fit, uint32_t n, int32_t* order,
+                       uint8_t* nondom, void* scratch, size_t sb, cudaStream_t);

@@ -1,0 +1,217 @@
+"""FitnessEngine: the device side of `Organism.calcObj` / `GeneticalGorithm.rackNstack`
+for whole populations.  PyTorch is used only to own device buffers and streams; all
+compute is in libgcp.so (hand-written sm_100a kernels) behind the C ABI of include/gcp.h.
+
+Reference call sites replaced (file:line into /root/reference/src):
+  geneticalgorithm.py:177-201  Organism.calcObj           -> FitnessEngine.evaluate
+  geneticalgorithm.py:86-123   GeneticalGorithm.rackNstack -> FitnessEngine.maximin
+  geneticalgorithm.py:78-84    GeneticalGorithm.arena      -> FitnessEngine.arena_order
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import GcpEvalOut, GcpMapConsts, GcpParams
+
+
+class GcpError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    """Host pointer of a C-contiguous numpy array (kept alive by the caller)."""
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class EvalResult(object):
+    """Device tensors produced by one evaluate() call."""
+    __slots__ = ("obj", "neg_cov", "dist", "turn", "cov", "lc_mat", "flags")
+
+    def feasible(self):
+        return self.flags[:, 0]
+
+    def traversable(self):
+        return self.flags[:, 1]
+
+    def n_components(self):
+        return self.flags[:, 2]
+
+    def error(self):
+        return self.flags[:, 3]
+
+
+class FitnessEngine(object):
+    def __init__(self, packed, org_params, num_agents=None, device=0):
+        """packed: packing.PackedWorld; org_params: the reference's org_params dict
+        (pather_driver.py:179-191).  Raises if CUDA or libgcp.so is unavailable."""
+        if not torch.cuda.is_available():
+            raise GcpError("FitnessEngine needs a CUDA device: there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device)
+        self.pw = packed
+        ctx = C.c_void_p()
+        rc = self.lib.gcp_create(C.byref(ctx), int(device))
+        if rc != 0:
+            raise GcpError("gcp_create: %s" % self.lib.gcp_last_error(None).decode())
+        self.ctx = ctx
+        pw = packed
+        self._keep = []
+
+        def arr(a, dt):
+            a = np.ascontiguousarray(a, dtype=dt)
+            self._keep.append(a)
+            return a
+        self._check(self.lib.gcp_upload_graph(
+            ctx, pw.N, pw.E, _ptr(arr(pw.row_ptr, np.uint32)), _ptr(arr(pw.col, np.uint32)),
+            _ptr(arr(pw.xy, np.int32)), _ptr(arr(pw.xover_cand, np.uint8))))
+        self._check(self.lib.gcp_upload_edges(
+            ctx, _ptr(arr(pw.edge_cost, np.float64)), _ptr(arr(pw.edge_theta, np.float64)),
+            _ptr(arr(pw.sub_ptr, np.uint32)), _ptr(arr(pw.sub_block, np.uint32)),
+            _ptr(arr(pw.sub_payload, np.uint32)), len(pw.sub_block),
+            _ptr(arr(pw.tile_data, np.uint64)), pw.n_quarters))
+        mc = GcpMapConsts(pw.H, pw.W, pw.nbx, pw.nby, pw.mask_size, pw.gsum_mask, pw.map_size,
+                          pw.num_occluded)
+        self._check(self.lib.gcp_upload_map(
+            ctx, C.byref(mc), _ptr(arr(pw.blk_mask0, np.uint64)),
+            _ptr(arr(pw.blk_free0, np.uint64)), _ptr(arr(pw.gray_ptr, np.uint32)),
+            _ptr(arr(pw.gray_ent, np.uint32)), len(pw.gray_ent)))
+        self._keep = []
+        self.A = int(num_agents if num_agents is not None else len(org_params['start_idx']))
+        self.L = int(org_params['max_dna_len'])
+        self.set_params(org_params)
+        self._scratch = None
+        self._rank_scratch = None
+
+    # ------------------------------------------------------------------
+    def set_params(self, org_params, solo_sep_thresh=None, blend=None):
+        pw = self.pw
+        blend = pw.blend if blend is None else float(blend)
+        p = GcpParams(self.A, self.L,
+                      int(pw.solo_sep_thresh if solo_sep_thresh is None else solo_sep_thresh),
+                      int(org_params['min_solo_lcs']), int(org_params['min_comb_lcs']), 0,
+                      float(org_params['flight_time_scale']), blend, 1 - blend)
+        self._check(self.lib.gcp_set_params(self.ctx, C.byref(p)))
+        self.org_params = dict(org_params)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise GcpError("libgcp error %d: %s" % (rc, self.lib.gcp_last_error(self.ctx).decode()))
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.gcp_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _get_scratch(self, P):
+        need = self.lib.gcp_eval_scratch_bytes(self.ctx, P)
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._scratch
+
+    # ------------------------------------------------------------------
+    def to_device_dna(self, dna):
+        """Accepts numpy / torch int arrays [P,A,L]; returns contiguous int32 on device."""
+        if isinstance(dna, np.ndarray):
+            dna = torch.from_numpy(np.ascontiguousarray(dna, dtype=np.int32))
+        dna = dna.to(device=self.device, dtype=torch.int32).contiguous()
+        if dna.dim() != 3 or dna.shape[1] != self.A or dna.shape[2] != self.L:
+            raise ValueError("dna must be [P,%d,%d], got %s" % (self.A, self.L, tuple(dna.shape)))
+        return dna
+
+    def evaluate(self, dna, detail=True):
+        """Organism.calcObj for every organism.  dna: [P,A,L] int32 device tensor (or
+        anything to_device_dna accepts).  Returns EvalResult of device tensors."""
+        dna = self.to_device_dna(dna)
+        P = dna.shape[0]
+        dev, A = self.device, self.A
+        res = EvalResult()
+        res.obj = torch.empty((P, 2), dtype=torch.float64, device=dev)
+        res.flags = torch.zeros((P, 4), dtype=torch.uint8, device=dev)
+        out = GcpEvalOut()
+        out.obj = res.obj.data_ptr()
+        out.flags = res.flags.data_ptr()
+        if detail:
+            res.neg_cov = torch.empty(P, dtype=torch.float64, device=dev)
+            res.dist = torch.empty((P, A), dtype=torch.float64, device=dev)
+            res.turn = torch.empty((P, A), dtype=torch.float64, device=dev)
+            res.cov = torch.empty((P, 8), dtype=torch.int32, device=dev)
+            res.lc_mat = torch.empty((P, A, A), dtype=torch.int32, device=dev)
+            out.neg_cov, out.dist, out.turn = res.neg_cov.data_ptr(), res.dist.data_ptr(), res.turn.data_ptr()
+            out.cov, out.lc_mat = res.cov.data_ptr(), res.lc_mat.data_ptr()
+        else:
+            res.neg_cov = res.dist = res.turn = res.cov = res.lc_mat = None
+        scratch = self._get_scratch(P)
+        self._check(self.lib.gcp_eval(self.ctx, C.c_void_p(dna.data_ptr()), P, C.byref(out),
+                                      C.c_void_p(scratch.data_ptr()), scratch.numel(),
+                                      self._stream()))
+        return res
+
+    def evaluate_host(self, dna_host, obj_host=None, flags_host=None):
+        """End-to-end call with HOST buffers (the reference-facing shape of the path):
+        dna_host int32 [P,A,L] (pinned torch tensor or numpy); returns (obj, flags) on host."""
+        if isinstance(dna_host, np.ndarray):
+            dna_host = torch.from_numpy(np.ascontiguousarray(dna_host, dtype=np.int32))
+        assert dna_host.dtype == torch.int32 and dna_host.is_contiguous() and not dna_host.is_cuda
+        P = dna_host.shape[0]
+        if obj_host is None:
+            obj_host = torch.empty((P, 2), dtype=torch.float64).pin_memory()
+        if flags_host is None:
+            flags_host = torch.empty((P, 4), dtype=torch.uint8).pin_memory()
+        self._check(self.lib.gcp_eval_host(self.ctx, C.c_void_p(dna_host.data_ptr()), P,
+                                           C.c_void_p(obj_host.data_ptr()),
+                                           C.c_void_p(flags_host.data_ptr())))
+        return obj_host, flags_host
+
+    # ------------------------------------------------------------------
+    def _get_rank_scratch(self, n):
+        need = self.lib.gcp_rank_scratch_bytes(self.ctx, n)
+        if self._rank_scratch is None or self._rank_scratch.numel() < need:
+            self._rank_scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._rank_scratch
+
+    def maximin(self, obj, coverage_constr, row_range=None, return_scaled=False):
+        """GeneticalGorithm.rackNstack: obj [n,2] float64 device tensor -> fit [n]."""
+        obj = obj.to(device=self.device, dtype=torch.float64).contiguous()
+        n = obj.shape[0]
+        r0, r1 = (0, n) if row_range is None else row_range
+        fit = torch.empty(n, dtype=torch.float64, device=self.device)
+        sc = torch.empty((n, 2), dtype=torch.float64, device=self.device) if return_scaled else None
+        s = self._get_rank_scratch(n)
+        self._check(self.lib.gcp_maximin(
+            self.ctx, C.c_void_p(obj.data_ptr()), n, float(coverage_constr), r0, r1,
+            C.c_void_p(sc.data_ptr()) if sc is not None else None, C.c_void_p(fit.data_ptr()),
+            C.c_void_p(s.data_ptr()), s.numel(), self._stream()))
+        return (fit, sc) if return_scaled else fit
+
+    def arena_order(self, fit):
+        """got.sortBy canonical order: stable ascending by (fit, index)."""
+        fit = fit.to(device=self.device, dtype=torch.float64).contiguous()
+        n = fit.shape[0]
+        order = torch.empty(n, dtype=torch.int32, device=self.device)
+        nondom = torch.empty(n, dtype=torch.uint8, device=self.device)
+        s = self._get_rank_scratch(n)
+        self._check(self.lib.gcp_arena_order(
+            self.ctx, C.c_void_p(fit.data_ptr()), n, C.c_void_p(order.data_ptr()),
+            C.c_void_p(nondom.data_ptr()), C.c_void_p(s.data_ptr()), s.numel(), self._stream()))
+        return order, nondom
+
+    # ------------------------------------------------------------------
+    def launch_count(self):
+        return int(self.lib.gcp_launch_count(self.ctx))
+
+    def set_timing(self, on):
+        self.lib.gcp_set_timing(self.ctx, 1 if on else 0)
+
+    def stage_ms(self, stage):
+        return float(self.lib.gcp_stage_ms(self.ctx, stage))

@@ -1,0 +1,151 @@
+/*
+ * gcp.h - C ABI of the B200 fitness engine for genetic_coverage_planning.
+ *
+ * The reference has no FFI layer: its seam is the Python class API
+ * (geneticalgorithm.py / mappy.py).  Each entry point below names the reference
+ * function(s) it replaces (file:line into /root/reference/src); the Python facade in
+ * genetic_coverage_planning_b200/ binds them with ctypes.
+ *
+ * Conventions
+ *   - C linkage, POD arguments, no C++/torch types.
+ *   - every function returns 0 on success, <0 on error; gcp_last_error(ctx) gives the
+ *     text (owned by ctx, valid until the next call on that ctx).
+ *   - "dev" pointers are CUDA device pointers owned by the caller (e.g.
+ *     torch.Tensor.data_ptr()); "host" pointers are plain host memory.
+ *   - work is enqueued on the caller's stream (void* = cudaStream_t, NULL = default
+ *     stream); no hidden synchronisation except in the *_host convenience calls and
+ *     the gcp_upload_* calls, which are synchronous.
+ *   - the static lookup tables (uploaded once) live in device memory owned by ctx.
+ *   - one host thread per ctx at a time; one ctx per GPU.
+ *   - there is NO CPU fallback: without a CUDA device gcp_create fails.
+ */
+#ifndef GCP_H
+#define GCP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCP_ABI_VERSION 1
+#define GCP_MAX_AGENTS 32
+#define GCP_INVALID_EDGE 0xFFFFFFFFu
+
+typedef struct gcp_ctx gcp_ctx;
+
+/* Scalar parameters of the path.  Sources: pather_driver.py:161-200 dicts. */
+typedef struct gcp_params {
+    int32_t num_agents;        /* A  <= GCP_MAX_AGENTS         gen_params['num_agents']   */
+    int32_t max_dna_len;       /* L                             org_params['max_dna_len']  */
+    int32_t solo_sep_thresh;   /* mappy.py:413                  map_params['solo_sep_thresh'] */
+    int32_t min_solo_lcs;      /* geneticalgorithm.py:198       org_params['min_solo_lcs'] */
+    int32_t min_comb_lcs;      /* geneticalgorithm.py:199       org_params['min_comb_lcs'] */
+    int32_t reserved0;
+    double  flight_time_scale; /* geneticalgorithm.py:196       org_params['flight_time_scale'] */
+    double  coverage_blend;    /* mappy.py:364                  map_params['coverage_blend'] */
+    double  one_minus_blend;   /* (1 - blend) as the host language evaluates it */
+} gcp_params;
+
+/* Constants of the map planes (computed by the host packer with the reference's own
+ * numpy/cv2 expressions: mappy.py:25,36-39,337). */
+typedef struct gcp_map_consts {
+    int32_t  height, width;    /* pixels */
+    int32_t  nbx, nby;         /* 64x64 blocks per row / column */
+    int64_t  mask_size;        /* draw_map[buffer_mask].size          mappy.py:361 */
+    int64_t  gsum_mask;        /* sum over buffer_mask of gray level g (0..255) */
+    int64_t  map_size;         /* draw_map.size                        mappy.py:358 */
+    double   num_occluded;     /* np.sum(img)                          mappy.py:25  */
+} gcp_map_consts;
+
+/* Per-organism outputs of gcp_eval; any pointer may be NULL (that output is skipped). */
+typedef struct gcp_eval_out {
+    double*   obj;        /* dev [P][2]   Organism.calcObj -> [-coverage | 0, travel_cost]  geneticalgorithm.py:177-201 */
+    double*   neg_cov;    /* dev [P]      -coverage before the feasibility zeroing          mappy.py:364-370 */
+    double*   dist;       /* dev [P][A]   travel_cost per agent                             mappy.py:351 */
+    double*   turn;       /* dev [P][A]   turning_cost per agent                            mappy.py:352 */
+    uint32_t* cov;        /* dev [P][8]   {n_mask0, n_free0, wg_mask, wg_all, n_cov_mask, n_cov_all, 0, 0} pixel counts */
+    int32_t*  lc_mat;     /* dev [P][A][A] Mappy.getLoopClosures                            mappy.py:386-437 */
+    uint8_t*  flags;      /* dev [P][4]   {feasible, traversable, n_components, error}      geneticalgorithm.py:188-200 */
+} gcp_eval_out;
+
+/* ---- life cycle ---------------------------------------------------------------- */
+int         gcp_abi_version(void);
+int         gcp_create(gcp_ctx** out, int device);
+void        gcp_destroy(gcp_ctx* ctx);
+const char* gcp_last_error(gcp_ctx* ctx);   /* ctx may be NULL: error of a failed gcp_create */
+
+/* ---- one-time table upload (synchronous; host pointers) ---------------------------
+ * Replaces: PathMaker._graph/_XY/_crossover_cand (pathmaker.py:157-173) and
+ * Mappy._traverse_frustum/_angles/_dists (mappy.py:274-328) as seen by the hot path. */
+int gcp_upload_graph(gcp_ctx* ctx, uint32_t n_nodes, uint32_t n_edges,
+                     const uint32_t* row_ptr /*[N+1]*/, const uint32_t* col /*[E]*/,
+                     const int32_t* xy /*[N][2] (row,col)*/, const uint8_t* xover_cand /*[N]*/);
+int gcp_upload_edges(gcp_ctx* ctx,
+                     const double* edge_cost   /*[E+N][2] {dist, turn}; ids >= E are null edges*/,
+                     const double* edge_theta  /*[E] heading, radians*/,
+                     const uint32_t* sub_ptr   /*[E+N+1]*/,
+                     const uint32_t* sub_block /*[S] block id of each sub-tile*/,
+                     const uint32_t* sub_payload /*[S] (offset128<<4)|qmask*/,
+                     uint64_t n_sub,
+                     const uint64_t* tile_data /*[n_quarters][16] rows of 64 px*/,
+                     uint64_t n_quarters);
+int gcp_upload_map(gcp_ctx* ctx, const gcp_map_consts* consts,
+                   const uint64_t* blk_mask0 /*[nb][64]*/, const uint64_t* blk_free0 /*[nb][64]*/,
+                   const uint32_t* gray_ptr /*[nb+1]*/, const uint32_t* gray_ent /*[G]*/,
+                   uint64_t n_gray);
+int gcp_set_params(gcp_ctx* ctx, const gcp_params* p);
+
+/* ---- evaluation: Organism.calcObj for P organisms ---------------------------------
+ * Replaces: `for o in organisms: o.calcObj()` = Mappy.getCoverage (mappy.py:330-370)
+ * + Mappy.getLoopClosures (mappy.py:386-437) + constraints (geneticalgorithm.py:177-201).
+ * dna: dev int32 [P][A][L], -1 padded (Organism._dna, geneticalgorithm.py:335-344). */
+size_t gcp_eval_scratch_bytes(gcp_ctx* ctx, uint32_t n_org);
+int    gcp_eval(gcp_ctx* ctx, const int32_t* dna_dev, uint32_t n_org,
+                const gcp_eval_out* out, void* scratch_dev, size_t scratch_bytes,
+                void* stream);
+/* Individual stages (same buffers; used by tests / profiling). edge_ids: dev u32 [P][A][L]. */
+int gcp_path_costs(gcp_ctx* ctx, const int32_t* dna_dev, uint32_t n_org, uint32_t* edge_ids_dev,
+                   double* dist_dev, double* turn_dev, uint8_t* flags_dev, void* stream);
+int gcp_coverage(gcp_ctx* ctx, const uint32_t* edge_ids_dev, uint32_t n_org,
+                 uint32_t* cov_dev, uint8_t* flags_dev, void* stream);
+int gcp_loop_closures(gcp_ctx* ctx, const int32_t* dna_dev, uint32_t n_org,
+                      const double* dist_dev, const double* turn_dev, const uint32_t* cov_dev,
+                      int32_t* lc_mat_dev, double* obj_dev, double* neg_cov_dev,
+                      uint8_t* flags_dev, void* stream);
+
+/* Host-buffer convenience (the end-to-end path): copies dna H2D in chunks, evaluates,
+ * copies obj [P][2] and flags [P][4] back; synchronous.  Pinned host memory is used as
+ * is; pageable memory works but is slower. */
+int gcp_eval_host(gcp_ctx* ctx, const int32_t* dna_host, uint32_t n_org,
+                  double* obj_host, uint8_t* flags_host);
+
+/* ---- ranking: GeneticalGorithm.rackNstack + arena ordering -------------------------
+ * Replaces geneticalgorithm.py:86-123 (maximin fitness) and gori_tools.py:232-236
+ * (argsort; canonical stable order by (fit, index)).
+ * coverage_constr = (1-alpha)*c0 + alpha*cf evaluated by the host (geneticalgorithm.py:98-100).
+ * Rows [row_begin, row_end) of fit are computed (multi-GPU row sharding); pass 0, n.
+ * obj: dev [n][2]; obj_sc (optional): dev [n][2]; fit: dev [n]. */
+size_t gcp_rank_scratch_bytes(gcp_ctx* ctx, uint32_t n);
+int gcp_maximin(gcp_ctx* ctx, const double* obj_dev, uint32_t n, double coverage_constr,
+                uint32_t row_begin, uint32_t row_end, double* obj_sc_dev, double* fit_dev,
+                void* scratch_dev, size_t scratch_bytes, void* stream);
+/* order[k] = index of the k-th best (ascending fit, ties by index); nondom[i] = fit[i] < 0. */
+int gcp_arena_order(gcp_ctx* ctx, const double* fit_dev, uint32_t n, int32_t* order_dev,
+                    uint8_t* nondom_dev, void* scratch_dev, size_t scratch_bytes, void* stream);
+
+/* ---- introspection ---------------------------------------------------------------- */
+/* kernel launch counter since gcp_create (for bench.py's gpu_launches). */
+uint64_t gcp_launch_count(gcp_ctx* ctx);
+/* time of the most recent call of each stage measured with CUDA events on the launch
+ * stream; only recorded while enabled (adds two event records per stage). */
+int gcp_set_timing(gcp_ctx* ctx, int enabled);
+/* stage: 0 path_costs, 1 coverage, 2 loop_closures, 3 maximin, 4 arena_order, 5 select_vary.
+ * Synchronises on the stage's end event. Returns milliseconds, <0 if not recorded. */
+float gcp_stage_ms(gcp_ctx* ctx, int stage);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCP_H */

@@ -1,0 +1,183 @@
+"""GPU parity: CUDA path (through the C ABI) vs golden vectors of the unmodified
+reference and vs the oracle on seeded inputs.  Integer outputs bit-exact; float costs
+bit-exact (tolerance 0); -coverage within 1e-12 on the gray reference maps and
+bit-exact on binary maps (SURVEY.md section 8a parity rules)."""
+import os
+
+import numpy as np
+import pytest
+
+import fitness_oracle as fo
+from world import World
+
+pytestmark = pytest.mark.gpu
+
+COV_TOL_GRAY = 1e-12
+
+
+def _engine(world, org_params=None, num_agents=None):
+    from genetic_coverage_planning_b200 import packing
+    from genetic_coverage_planning_b200.engine import FitnessEngine
+    pw = packing.pack_world(world.img, world.xy, world.row_ptr, world.col, world.edge_poly,
+                            world.edge_theta, world.edge_dist, world.map_params)
+    op = org_params or world.org_params
+    return FitnessEngine(pw, op, num_agents=num_agents)
+
+
+@pytest.fixture(scope="module")
+def eng_big(world_big):
+    return _engine(world_big)
+
+
+def _check_against_golden(eng, z, exact_cov=False):
+    dna = z['dna'].astype(np.int32)
+    r = eng.evaluate(dna)
+    dist, turn = r.dist.cpu().numpy(), r.turn.cpu().numpy()
+    assert np.array_equal(dist, z['dist']), "per-agent travel distance not bit-exact"
+    assert np.array_equal(turn, z['turn']), "per-agent turning cost not bit-exact"
+    cov = r.cov.cpu().numpy()
+    assert np.array_equal(cov[:, 5], z['n_painted'])
+    assert np.array_equal(cov[:, 4], z['n_painted_mask'])
+    assert np.array_equal(r.lc_mat.cpu().numpy(), z['lc'].astype(np.int32))
+    flags = r.flags.cpu().numpy()
+    assert np.array_equal(flags[:, 2], z['ncomp'])
+    assert not flags[:, 3].any()
+    obj = r.obj.cpu().numpy()
+    assert np.array_equal(obj[:, 1], z['obj'][:, 1]), "travel cost objective not bit-exact"
+    neg = r.neg_cov.cpu().numpy()
+    if exact_cov:
+        assert np.array_equal(neg, z['neg_cov'])
+        assert np.array_equal(obj[:, 0], z['obj'][:, 0])
+    else:
+        assert np.max(np.abs(neg - z['neg_cov'])) <= COV_TOL_GRAY
+        assert np.max(np.abs(obj[:, 0] - z['obj'][:, 0])) <= COV_TOL_GRAY
+    # feasibility: the reference zeroes coverage exactly when infeasible
+    infeasible_ref = (z['obj'][:, 0] == 0) & (z['neg_cov'] != 0)
+    assert np.array_equal(flags[:, 0] == 0, infeasible_ref | ((flags[:, 0] == 0) & (z['neg_cov'] == 0)))
+
+
+def test_eval_golden_big(eng_big, golden_dir):
+    _check_against_golden(eng_big, np.load(os.path.join(golden_dir, "eval_big.npz")))
+
+
+def test_edge_cases_golden(eng_big, golden_dir):
+    _check_against_golden(eng_big, np.load(os.path.join(golden_dir, "edge_big.npz")))
+
+
+def test_eval_golden_small(world_small, golden_dir):
+    eng = _engine(world_small)
+    _check_against_golden(eng, np.load(os.path.join(golden_dir, "eval_small.npz")))
+
+
+def test_blend_golden(golden_dir):
+    w = World.load_npz(os.path.join(golden_dir, "world_big.npz"))
+    w.map_params['coverage_blend'] = 0.1
+    eng = _engine(w)
+    _check_against_golden(eng, np.load(os.path.join(golden_dir, "eval_big_blend01.npz")))
+
+
+@pytest.mark.parametrize("A", [1, 3])
+def test_agent_counts_golden(golden_dir, A):
+    z = np.load(os.path.join(golden_dir, "eval_big_A%d.npz" % A))
+    w = World.load_npz(os.path.join(golden_dir, "world_big.npz"))
+    w.map_params['solo_sep_thresh'] = int(z['solo_sep_thresh'])
+    op = dict(w.org_params)
+    op.update(min_solo_lcs=int(z['min_solo_lcs']), min_comb_lcs=int(z['min_comb_lcs']),
+              max_dna_len=int(z['max_dna_len']), start_idx=w.org_params['start_idx'][:A])
+    eng = _engine(w, op, num_agents=A)
+    _check_against_golden(eng, z)
+
+
+def _random_dna(world, P, A, L, seed, p_nonedge=0.02):
+    """Random walks on the graph with ragged lengths, a few teleports (non-edges),
+    some full-length rows, some empty rows."""
+    rng = np.random.RandomState(seed)
+    deg = np.diff(world.row_ptr)
+    dna = -np.ones((P, A, L), dtype=np.int32)
+    for p in range(P):
+        for a in range(A):
+            n = int(rng.choice([0, 1, 2, L, rng.randint(3, L + 1)], p=[.02, .02, .02, .1, .84]))
+            if n == 0:
+                continue
+            w = int(rng.randint(world.N))
+            for i in range(n):
+                dna[p, a, i] = w
+                if rng.rand() < p_nonedge or deg[w] == 0:
+                    w = int(rng.randint(world.N))
+                else:
+                    w = int(world.col[world.row_ptr[w] + rng.randint(deg[w])])
+    return dna
+
+
+def test_eval_vs_oracle_random(eng_big, world_big):
+    A, L = eng_big.A, eng_big.L
+    dna = _random_dna(world_big, 96, A, L, seed=5)
+    r = eng_big.evaluate(dna)
+    dist, turn, cov = r.dist.cpu().numpy(), r.turn.cpu().numpy(), r.cov.cpu().numpy()
+    lc, obj, flags = r.lc_mat.cpu().numpy(), r.obj.cpu().numpy(), r.flags.cpu().numpy()
+    neg = r.neg_cov.cpu().numpy()
+    for k in range(len(dna)):
+        d = dna[k].astype(int)
+        c, dd, tt, cnt = fo.get_coverage(world_big, d, return_counts=True)
+        assert np.array_equal(dd, dist[k]) and np.array_equal(tt, turn[k]), k
+        assert cnt['n_cov_all'] == cov[k, 5] and cnt['n_cov_mask'] == cov[k, 4], k
+        assert abs(c - neg[k]) <= COV_TOL_GRAY
+        det = fo.calc_obj(world_big, d, detail=True)
+        assert np.array_equal(det['lc_mat'].astype(np.int32), lc[k]), k
+        assert det['n_components'] == flags[k, 2] and det['feasible'] == flags[k, 0], k
+        assert det['obj'][1] == obj[k, 1]
+        assert abs(det['obj'][0] - obj[k, 0]) <= COV_TOL_GRAY
+        assert fo.traversable(world_big, d) == flags[k, 1], k
+
+
+def test_shard_equivalence_and_host_path(eng_big, golden_dir):
+    import torch
+    z = np.load(os.path.join(golden_dir, "eval_big.npz"))
+    dna = np.concatenate([z['dna'].astype(np.int32)] * 3)
+    full = eng_big.evaluate(dna)
+    parts = [eng_big.evaluate(dna[s:s + 50]) for s in range(0, len(dna), 50)]
+    for name in ("obj", "dist", "turn", "cov", "lc_mat", "flags"):
+        a = getattr(full, name).cpu().numpy()
+        b = np.concatenate([getattr(p, name).cpu().numpy() for p in parts])
+        assert np.array_equal(a, b), name
+    obj_h, flags_h = eng_big.evaluate_host(torch.from_numpy(dna).pin_memory())
+    assert np.array_equal(obj_h.numpy(), full.obj.cpu().numpy())
+    assert np.array_equal(flags_h.numpy(), full.flags.cpu().numpy())
+
+
+def test_maximin_and_order_golden(eng_big, golden_dir):
+    import torch
+    import ref_shim
+    z = np.load(os.path.join(golden_dir, "rank.npz"))
+    _, _, _, gp = ref_shim.driver_params(6)
+    for gen in (0, 17, 80, 200):
+        constr = fo.coverage_constraint(gen, gp)
+        fit, sc = eng_big.maximin(torch.from_numpy(z['objs']), constr, return_scaled=True)
+        assert np.array_equal(sc.cpu().numpy(), z['sc_gen%d' % gen])
+        assert np.array_equal(fit.cpu().numpy(), z['fit_gen%d' % gen])
+        order, nondom = eng_big.arena_order(fit)
+        assert np.array_equal(order.cpu().numpy(), z['order_gen%d' % gen])
+        assert np.array_equal(nondom.cpu().numpy() == 1, z['fit_gen%d' % gen] < 0)
+    fit = eng_big.maximin(torch.from_numpy(z['syn_objs']), fo.coverage_constraint(40, gp))
+    assert np.array_equal(fit.cpu().numpy(), z['syn_fit_gen40'])
+
+
+def test_maximin_vs_oracle_large_with_ties(eng_big):
+    import torch
+    import ref_shim
+    _, _, _, gp = ref_shim.driver_params(6)
+    rs = np.random.RandomState(2)
+    n = 5000
+    objs = np.stack([-rs.randint(0, 300, n) / 300.0, rs.rand(n) * 3 + 0.5], 1)
+    objs[rs.rand(n) < 0.5, 0] = 0.0                      # infeasible organisms tie (F15)
+    objs[100:140] = objs[200:240]                        # exact duplicates
+    for gen in (0, 50):
+        constr = fo.coverage_constraint(gen, gp)
+        want = fo.rack_n_stack(objs, gen, gp)
+        fit = eng_big.maximin(torch.from_numpy(objs), constr)
+        assert np.array_equal(fit.cpu().numpy(), want)
+        order, _ = eng_big.arena_order(fit)
+        assert np.array_equal(order.cpu().numpy(), fo.arena_order(want))
+        # row-sharded evaluation (multi-GPU layout) gives the same rows
+        part = eng_big.maximin(torch.from_numpy(objs), constr, row_range=(1234, 3456))
+        assert np.array_equal(part.cpu().numpy()[1234:3456], want[1234:3456])
