@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""Benchmark of the fitness hot path (BASELINE.json metric: organisms evaluated/sec at
+population 65,536, 6 agents, synthetic 4096^2 map = config C3).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...   # CPU restatement of the
+        reference's own loop (oracle port, all host cores) on bounded samples
+
+A "step" = one evaluation pass (Organism.calcObj for every organism: path costs +
+coverage union + loop closures/constraints/objectives) over one population of P
+organisms per GPU, DNA already resident in HBM.  Weak scaling: every rank evaluates its
+own P organisms of a global population of N*P, tables replicated, no data-path collective
+(organisms are independent).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "organisms_evaluated_per_s"
+UNIT = "organisms/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=os.environ.get("GCP_BENCH_CONFIG", "C3"))
+    ap.add_argument("--pop", type=int, default=0, help="override organisms per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=48)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip e2e / per-kernel / ranking legs")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def known_traffic(workload):
+    """dram bytes per launch of the coverage kernel from the committed ncu --set full
+    capture (profiles/roofline_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(",") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for k, n in enumerate(names):
+                    if r[3 + k].strip().lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)),
+                       reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def build_setup(cfg_name, pop_override, rank, world_size, barrier):
+    from genetic_coverage_planning_b200 import synth, worlds
+    cfg = dict(worlds.CONFIGS[cfg_name])
+    if pop_override:
+        cfg['pop'] = pop_override
+    if rank == 0:
+        w, pw = worlds.build_synth_world(cfg['size'], seed=0, verbose=True)
+    barrier()
+    if rank != 0:
+        w, pw = worlds.build_synth_world(cfg['size'], seed=0)
+    starts = synth.spread_starts(w.xy, cfg['agents'], cfg['size'])
+    op = worlds.org_params_for(cfg, starts)
+    return cfg, w, pw, op, starts
+
+
+def oracle_world(w, op):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from world import World
+    return World(w.img, w.xy, w.row_ptr, w.col, w.edge_poly, w.edge_theta, w.edge_dist,
+                 w.map_params, op, name="synth")
+
+
+_OW = None
+
+
+def _cpu_eval_slice(dnas):
+    import fitness_oracle as fo
+    return [fo.calc_obj(_OW, d.astype(int)) for d in dnas]
+
+
+def cpu_port_rate(w, op, dna_sample, procs):
+    """organisms/s of the oracle port (restatement of the reference loop) on `procs`
+    host processes.  Returns (rate, seconds)."""
+    global _OW
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fitness_oracle as fo
+    _OW = oracle_world(w, op)
+    _OW.safety_img  # build once, shared with forked workers
+    _OW.edge_id(0, 0)
+    if procs <= 1:
+        t0 = time.time()
+        for d in dna_sample:
+            fo.calc_obj(_OW, d.astype(int))
+        dt = time.time() - t0
+        return len(dna_sample) / dt, dt
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    chunks = [c for c in np.array_split(dna_sample, procs) if len(c)]
+    with ctx.Pool(len(chunks)) as pool:
+        pool.map(_cpu_eval_slice, [c[:1] for c in chunks])        # warm the workers
+        t0 = time.time()
+        pool.map(_cpu_eval_slice, chunks)
+        dt = time.time() - t0
+    return len(dna_sample) / dt, dt
+
+
+def run_reference(args):
+    rank, world_size, _ = dist_env()
+    if rank != 0:
+        return 0
+    from genetic_coverage_planning_b200 import synth, worlds
+    cfg, w, pw, op, starts = build_setup(args.config, args.pop, 0, 1, lambda: None)
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    per_step = max(procs * 2, 16)
+    n = per_step * (args.steps + args.warmup)
+    dna = synth.random_walk_population(w.xy, w.row_ptr, w.col, starts, n, cfg['walk'], cfg['L'],
+                                       seed=1)
+    rates, secs = [], []
+    for s in range(args.steps + args.warmup):
+        r, dt = cpu_port_rate(w, op, dna[s * per_step:(s + 1) * per_step], procs)
+        if s >= args.warmup:
+            rates.append(r)
+            secs.append(dt)
+    value = per_step * len(secs) / sum(secs)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * sum(secs) / len(secs), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64 bitsets + f64 costs",
+        "data": "synthetic",
+        "config": {"workload": "%s: synthetic %d^2 binary map, N=%d waypoints, E=%d edges, "
+                               "%d agents x %d genes" % (args.config, cfg['size'], w.N, w.E,
+                                                         cfg['agents'], cfg['L']),
+                   "sample_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
+                         "sample": "%d organisms per step, Organism.calcObj restated in numpy/cv2 "
+                                   "(oracle/fitness_oracle.py), %d forked processes" %
+                                   (per_step, procs)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank, world_size, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    distributed = world_size > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+
+    from genetic_coverage_planning_b200 import synth, worlds
+    from genetic_coverage_planning_b200.engine import FitnessEngine
+
+    cfg, w, pw, op, starts = build_setup(args.config, args.pop, rank, world_size, barrier)
+    P, A, L = cfg['pop'], cfg['agents'], cfg['L']
+    eng = FitnessEngine(pw, op, num_agents=A, device=local)
+    t0 = time.time()
+    dna = synth.random_walk_population_torch(w.xy, w.row_ptr, w.col, starts, P, cfg['walk'], L,
+                                             seed=1 + rank, device=dev)
+    torch.cuda.synchronize()
+    if rank == 0:
+        print("[bench] population %d x %d x %d generated in %.1fs" % (P, A, L, time.time() - t0),
+              file=sys.stderr, flush=True)
+    S_mean = float(worlds.executed_steps(dna[:4096].cpu().numpy()).mean())
+    B_org = S_mean * 544 + A * L * 4 + 64
+
+    # ---------------- timed region: K evaluation steps ----------------
+    for _ in range(max(args.warmup, 3)):
+        res = eng.evaluate(dna, detail=False)
+    torch.cuda.synchronize()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        res = eng.evaluate(dna, detail=False)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    launches = eng.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    if distributed:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world_size * P / (ms_per_step / 1000.0)
+
+    extras = {}
+    roofline = None
+    e2e = None
+    cpu_baseline = None
+    if not args.no_extras:
+        # ---------------- per-kernel timing (CUDA events on the launch stream) ----------
+        edge_ids, d_dist, d_turn, flags = eng.path_costs(dna)
+        cov, _ = eng.coverage(edge_ids)
+        torch.cuda.synchronize()
+
+        def time_stage(fn, reps):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        reps = max(args.steps, 5)
+        ms_k2 = time_stage(lambda: eng.coverage(edge_ids, cov, flags), reps)
+        ms_k1 = time_stage(lambda: eng.lib.gcp_path_costs(
+            eng.ctx, dna.data_ptr(), P, edge_ids.data_ptr(), d_dist.data_ptr(), d_turn.data_ptr(),
+            flags.data_ptr(), eng._stream()), reps)
+        ms_k3 = time_stage(lambda: eng.loop_closures(dna, d_dist, d_turn, cov, flags), reps)
+        peak, peak_src = measured_peak()
+        achieved = B_org * P / (ms_k2 * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_coverage (bitset union + popcount)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": known_traffic(args.config), "peak_source": peak_src,
+                    "algorithmic_bytes_per_organism": B_org, "organisms_per_launch": P,
+                    "ms_per_launch": ms_k2,
+                    "kernel_ms": {"path_costs": ms_k1, "coverage": ms_k2, "loop_closures": ms_k3},
+                    "eval_frac_of_peak": (B_org * P / (ms_per_step * 1e-3) / 1e9) / peak}
+        # ---------------- ranking leg: maximin + arena order over 2P gladiators ---------
+        obj2 = torch.cat([res.obj, res.obj.flip(0) * 1.0001])
+        constr = -0.3
+        ms_mm = time_stage(lambda: eng.maximin(obj2, constr), 3)
+        fit = eng.maximin(obj2, constr)
+        ms_ord = time_stage(lambda: eng.arena_order(fit), 3)
+        extras["ranking"] = {"n_gladiators": 2 * P, "maximin_ms": ms_mm, "arena_order_ms": ms_ord,
+                             "fp64_gflops": 4.0 * (2 * P) * (2 * P - 1) / (ms_mm * 1e-3) / 1e9}
+        # ---------------- end to end: host DNA in, host objectives out ------------------
+        dna_h = dna.cpu().pin_memory()
+        obj_h = torch.empty((P, 2), dtype=torch.float64).pin_memory()
+        flg_h = torch.empty((P, 4), dtype=torch.uint8).pin_memory()
+        for _ in range(2):
+            eng.evaluate_host(dna_h, obj_h, flg_h)
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(3, min(args.steps, 10))
+        for _ in range(n_e2e):
+            eng.evaluate_host(dna_h, obj_h, flg_h)
+        dt = (time.perf_counter() - t0) / n_e2e
+        if distributed:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        assert torch.equal(obj_h, res.obj.cpu()), "host path result differs from device path"
+        e2e = {"value": world_size * P / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(P * A * L * 4), "d2h_bytes_per_step": int(P * 20),
+               "ms_per_step": dt * 1e3,
+               "api": "FitnessEngine.evaluate_host -> gcp_eval_host (pinned host buffers, "
+                      "chunked H2D / kernels / D2H on two streams)"}
+        # ---------------- CPU baseline (rank 0, N=1 only) --------------------------------
+        if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
+            sample = dna[:args.cpu_sample].cpu().numpy()
+            rate, secs = cpu_port_rate(w, op, sample, 1)
+            cpu_baseline = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+                            "sample": "first %d organisms of the same population, "
+                                      "Organism.calcObj restated in numpy/cv2 (oracle/"
+                                      "fitness_oracle.py), single thread like the reference, "
+                                      "%.1fs" % (len(sample), secs),
+                            "host_cores_available": os.cpu_count()}
+            # parity spot check of the timed population against the oracle
+            import fitness_oracle as fo
+            ow = oracle_world(w, op)
+            full = eng.evaluate(dna[:4])
+            for k in range(4):
+                det = fo.calc_obj(ow, sample[k].astype(int), detail=True)
+                o = full.obj[k].cpu().numpy()
+                assert det['obj'][0] == o[0] and det['obj'][1] == o[1], "bench parity check failed"
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 bitsets + f64 costs", "data": "synthetic",
+            "config": {"workload": "%s: synthetic %d^2 binary map, N=%d waypoints, E=%d edges, "
+                                   "%d agents x %d genes (walks of %d steps), population %d per GPU"
+                                   % (args.config, cfg['size'], w.N, w.E, A, L, cfg['walk'], P),
+                       "organisms_per_gpu": P, "global_population": P * world_size,
+                       "mean_executed_steps_per_organism": S_mean,
+                       "l2": "per-step inputs (dna + edge ids, %.0f MB) exceed the 126 MB L2; no "
+                             "flush; the %.0f MB footprint store is reused inside a launch"
+                             % (2 * P * A * L * 4 / 1e6, pw.n_quarters * 128 / 1e6),
+                       "parallelism": "population sharded, tables replicated, no collective"},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if roofline:
+            line["roofline"] = roofline
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        if e2e:
+            line["e2e"] = e2e
+        line.update(extras)
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -173,6 +173,46 @@ class FitnessEngine(object):
                                            C.c_void_p(flags_host.data_ptr())))
         return obj_host, flags_host
 
+    # ---- individual stages (tests / profiling) ------------------------------
+    def path_costs(self, dna):
+        dna = self.to_device_dna(dna)
+        P, dev = dna.shape[0], self.device
+        edge_ids = torch.empty((P, self.A, self.L), dtype=torch.int32, device=dev)
+        dist = torch.empty((P, self.A), dtype=torch.float64, device=dev)
+        turn = torch.empty((P, self.A), dtype=torch.float64, device=dev)
+        flags = torch.zeros((P, 4), dtype=torch.uint8, device=dev)
+        self._check(self.lib.gcp_path_costs(
+            self.ctx, C.c_void_p(dna.data_ptr()), P, C.c_void_p(edge_ids.data_ptr()),
+            C.c_void_p(dist.data_ptr()), C.c_void_p(turn.data_ptr()),
+            C.c_void_p(flags.data_ptr()), self._stream()))
+        return edge_ids, dist, turn, flags
+
+    def coverage(self, edge_ids, cov=None, flags=None):
+        P = edge_ids.shape[0]
+        if cov is None:
+            cov = torch.empty((P, 8), dtype=torch.int32, device=self.device)
+        if flags is None:
+            flags = torch.zeros((P, 4), dtype=torch.uint8, device=self.device)
+        self._check(self.lib.gcp_coverage(
+            self.ctx, C.c_void_p(edge_ids.data_ptr()), P, C.c_void_p(cov.data_ptr()),
+            C.c_void_p(flags.data_ptr()), self._stream()))
+        return cov, flags
+
+    def loop_closures(self, dna, dist, turn, cov, flags=None):
+        dna = self.to_device_dna(dna)
+        P, dev, A = dna.shape[0], self.device, self.A
+        lc = torch.empty((P, A, A), dtype=torch.int32, device=dev)
+        obj = torch.empty((P, 2), dtype=torch.float64, device=dev)
+        neg = torch.empty(P, dtype=torch.float64, device=dev)
+        if flags is None:
+            flags = torch.zeros((P, 4), dtype=torch.uint8, device=dev)
+        self._check(self.lib.gcp_loop_closures(
+            self.ctx, C.c_void_p(dna.data_ptr()), P, C.c_void_p(dist.data_ptr()),
+            C.c_void_p(turn.data_ptr()), C.c_void_p(cov.data_ptr()), C.c_void_p(lc.data_ptr()),
+            C.c_void_p(obj.data_ptr()), C.c_void_p(neg.data_ptr()), C.c_void_p(flags.data_ptr()),
+            self._stream()))
+        return lc, obj, neg, flags
+
     # ------------------------------------------------------------------
     def _get_rank_scratch(self, n):
         need = self.lib.gcp_rank_scratch_bytes(self.ctx, n)
