@@ -40,11 +40,13 @@ SIGNATURES = {
     "gcp_last_error": (C.c_char_p, [_vp]),
     "gcp_upload_graph": (C.c_int, [_vp, _u32, _u32, _vp, _vp, _vp, _vp]),
     "gcp_upload_edges": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _u64, _vp, _u64]),
+    "gcp_upload_masked_footprints": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _vp, _u64]),
     "gcp_upload_map": (C.c_int, [_vp, C.POINTER(GcpMapConsts), _vp, _vp, _vp, _vp, _u64]),
     "gcp_set_params": (C.c_int, [_vp, C.POINTER(GcpParams)]),
     "gcp_eval_scratch_bytes": (C.c_size_t, [_vp, _u32]),
     "gcp_eval": (C.c_int, [_vp, _vp, _u32, C.POINTER(GcpEvalOut), _vp, C.c_size_t, _vp]),
-    "gcp_path_costs": (C.c_int, [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "gcp_path_costs": (C.c_int, [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gcp_coverage_masked": (C.c_int, [_vp, _vp, _u32, _vp, _vp, _vp]),
     "gcp_coverage": (C.c_int, [_vp, _vp, _u32, _vp, _vp, _vp]),
     "gcp_loop_closures": (C.c_int, [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gcp_eval_host": (C.c_int, [_vp, _vp, _u32, _vp, _vp]),

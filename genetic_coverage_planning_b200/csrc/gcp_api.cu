@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 
 size_t rank_scratch_bytes(gcp_ctx* ctx, uint32_t n);
 
@@ -116,12 +117,50 @@ int gcp_upload_edges(gcp_ctx* c, const double* edge_cost, const double* edge_the
     int r;
     if ((r = upload(c, &c->t.edge_cost, edge_cost, EN))) return r;     // double2
     if ((r = upload(c, &c->t.edge_theta, edge_theta, c->t.E))) return r;
-    if ((r = upload(c, &c->t.sub_ptr, sub_ptr, EN + 1))) return r;
-    if ((r = upload(c, &c->t.sub_block, sub_block, n_sub))) return r;
-    if ((r = upload(c, &c->t.sub_payload, sub_payload, n_sub))) return r;
+    {   // device layout: one u32 per edge (first | count<<28) and one uint2 per sub-tile
+        if (n_sub >= (1ull << 28)) return gcp_fail(c, -1, "too many sub-tiles");
+        std::vector<uint32_t> info(EN);
+        for (size_t e = 0; e < EN; ++e) {
+            const uint32_t n = sub_ptr[e + 1] - sub_ptr[e];
+            if (n > 15) return gcp_fail(c, -1, "edge %zu has %u sub-tiles (max 15)", e, n);
+            info[e] = sub_ptr[e] | (n << 28);
+        }
+        std::vector<uint2> desc(n_sub);
+        for (size_t k = 0; k < n_sub; ++k) desc[k] = make_uint2(sub_block[k], sub_payload[k]);
+        if ((r = upload(c, &c->t.sub_info, info.data(), EN))) return r;
+        if ((r = upload(c, &c->t.sub_desc, desc.data(), n_sub))) return r;
+    }
     if ((r = upload(c, &c->t.tile, tile_data, (size_t)n_quarters * 8))) return r;   // uint4
     c->n_sub = n_sub; c->n_quarters = n_quarters;
     c->have_edges = true;
+    return 0;
+}
+
+int gcp_upload_masked_footprints(gcp_ctx* c, const uint32_t* sub_ptr, const uint32_t* sub_block,
+                                 const uint32_t* sub_payload, uint64_t n_sub,
+                                 const uint64_t* tile_data, uint64_t n_quarters)
+{
+    if (!c) return -1;
+    if (!c->have_graph) return gcp_fail(c, -1, "upload the graph first");
+    if (c->have_masked) return gcp_fail(c, -1, "masked footprints already uploaded");
+    const size_t EN = (size_t)c->t.E + c->t.N;
+    if (sub_ptr[EN] != n_sub) return gcp_fail(c, -1, "masked sub_ptr[E+N] != n_sub");
+    if (n_quarters >= (1ull << 27) || n_sub >= (1ull << 28))
+        return gcp_fail(c, -1, "masked footprint store too large");
+    GCP_CUDA(c, cudaSetDevice(c->device));
+    std::vector<uint32_t> info(EN);
+    for (size_t e = 0; e < EN; ++e) {
+        const uint32_t n = sub_ptr[e + 1] - sub_ptr[e];
+        if (n > 15) return gcp_fail(c, -1, "edge %zu has %u masked sub-tiles (max 15)", e, n);
+        info[e] = sub_ptr[e] | (n << 28);
+    }
+    std::vector<uint2> desc(n_sub);
+    for (size_t k = 0; k < n_sub; ++k) desc[k] = make_uint2(sub_block[k], sub_payload[k]);
+    int r;
+    if ((r = upload(c, &c->t.m_sub_info, info.data(), EN))) return r;
+    if ((r = upload(c, &c->t.m_sub_desc, desc.data(), n_sub))) return r;
+    if ((r = upload(c, &c->t.m_tile, tile_data, (size_t)n_quarters * 8))) return r;
+    c->have_masked = true;
     return 0;
 }
 
@@ -175,21 +214,30 @@ size_t gcp_eval_scratch_bytes(gcp_ctx* c, uint32_t P)
 {
     if (!c || !c->have_params) return 0;
     const size_t A = c->p.num_agents, L = c->p.max_dna_len;
-    return align256(P * A * L * 4) + 2 * align256(P * A * 8) + align256((size_t)P * 32) +
+    return 2 * align256(P * A * L * 4) + 2 * align256(P * A * 8) + align256((size_t)P * 32) +
            align256((size_t)P * 4) + 256;
 }
 
-int gcp_path_costs(gcp_ctx* c, const int32_t* dna, uint32_t P, uint32_t* edge_ids, double* dist,
-                   double* turn, uint8_t* flags, void* stream)
+int gcp_path_costs(gcp_ctx* c, const int32_t* dna, uint32_t P, uint32_t* edge_ids,
+                   uint32_t* step_info, double* dist, double* turn, uint8_t* flags, void* stream)
 {
     int r = ready(c); if (r) return r;
-    return launch_path_costs(c, dna, P, edge_ids, dist, turn, flags, (cudaStream_t)stream);
+    return launch_path_costs(c, dna, P, edge_ids, step_info, dist, turn, flags,
+                             (cudaStream_t)stream);
+}
+
+int gcp_coverage_masked(gcp_ctx* c, const uint32_t* step_info, uint32_t P, uint32_t* cov,
+                        uint8_t* flags, void* stream)
+{
+    int r = ready(c); if (r) return r;
+    return launch_coverage_masked(c, step_info, P, cov, flags, (cudaStream_t)stream);
 }
 
 int gcp_coverage(gcp_ctx* c, const uint32_t* edge_ids, uint32_t P, uint32_t* cov, uint8_t* flags,
                  void* stream)
 {
     int r = ready(c); if (r) return r;
+    c->cov_detail = 1;
     return launch_coverage(c, edge_ids, P, cov, flags, (cudaStream_t)stream);
 }
 
@@ -214,6 +262,7 @@ int gcp_eval(gcp_ctx* c, const int32_t* dna, uint32_t P, const gcp_eval_out* out
     const size_t A = c->p.num_agents, L = c->p.max_dna_len;
     char* s = reinterpret_cast<char*>(scratch);
     uint32_t* edge_ids = reinterpret_cast<uint32_t*>(s); s += align256(P * A * L * 4);
+    uint32_t* step_info = reinterpret_cast<uint32_t*>(s); s += align256(P * A * L * 4);
     double* dist = reinterpret_cast<double*>(s);         s += align256(P * A * 8);
     double* turn = reinterpret_cast<double*>(s);         s += align256(P * A * 8);
     uint32_t* cov = reinterpret_cast<uint32_t*>(s);      s += align256((size_t)P * 32);
@@ -223,8 +272,17 @@ int gcp_eval(gcp_ctx* c, const int32_t* dna, uint32_t P, const gcp_eval_out* out
     if (out->cov) cov = out->cov;
     if (out->flags) flags = out->flags;
     cudaStream_t st = (cudaStream_t)stream;
-    if ((r = launch_path_costs(c, dna, P, edge_ids, dist, turn, flags, st))) return r;
-    if ((r = launch_coverage(c, edge_ids, P, cov, flags, st))) return r;
+    // objectives-only fast path: binary map, wall coverage only -> pre-masked footprint store
+    const bool fast = c->have_masked && c->n_gray == 0 && c->p.coverage_blend == 1.0 &&
+                      !out->cov && !c->force_general;
+    if ((r = launch_path_costs(c, dna, P, edge_ids, fast ? step_info : nullptr, dist, turn,
+                               flags, st))) return r;
+    if (fast) {
+        if ((r = launch_coverage_masked(c, step_info, P, cov, flags, st))) return r;
+    } else {
+        c->cov_detail = out->cov ? 1 : 0;   // objectives-only mode skips unused pixel counters
+        if ((r = launch_coverage(c, edge_ids, P, cov, flags, st))) return r;
+    }
     if ((r = launch_loop_closures(c, dna, P, dist, turn, cov, out->lc_mat, out->obj, out->neg_cov,
                                   flags, st))) return r;
     return 0;

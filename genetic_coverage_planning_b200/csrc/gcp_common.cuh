@@ -18,10 +18,13 @@ struct GcpTables {
     // edges (mappy.py:274-328): ids [0,E) real, [E,E+N) null edge of node id-E
     const double2*  edge_cost; // {dist, turn}
     const double*   edge_theta;
-    const uint32_t* sub_ptr;   // [E+N+1]
-    const uint32_t* sub_block; // [S]
-    const uint32_t* sub_payload; // [S] (offset128<<4)|qmask
+    const uint32_t* sub_info;  // [E+N] first sub-tile (28 bits) | count << 28
+    const uint2*    sub_desc;  // [S] {block id, (offset128<<4)|qmask}
     const uint4*    tile;      // quarters: 8 x uint4 = 16 rows of 64 px
+    // second store: footprints pre-ANDed with buffer_mask (optional)
+    const uint32_t* m_sub_info;
+    const uint2*    m_sub_desc;
+    const uint4*    m_tile;
     // map planes, block-major: 32 x uint4 per block (lane l = rows 2l, 2l+1)
     uint32_t n_blocks;
     const uint4*    blk_mask0; // buffer_mask & (g==0)
@@ -37,6 +40,7 @@ struct gcp_ctx {
     gcp_map_consts mc{};
     gcp_params p{};
     bool have_graph = false, have_edges = false, have_map = false, have_params = false;
+    bool have_masked = false;
     uint64_t n_sub = 0, n_quarters = 0, n_gray = 0;
     uint64_t launches = 0;
     int max_smem_optin = 0;
@@ -52,7 +56,9 @@ struct gcp_ctx {
     void* stage_dev = nullptr; size_t stage_bytes = 0;
     cudaStream_t hstream[2] = {};
     // coverage kernel tuning (0 = auto)
-    int cov_threads = 0, cov_table = 0, cov_maxpairs = 0;
+    int cov_table = 0, cov_maxpairs = 0;
+    int force_general = 0;   // testing: never take the pre-masked fast path
+    int cov_detail = 1;      // 1: all six counters; 0: only what the objectives need
 };
 
 int gcp_fail(gcp_ctx* ctx, int code, const char* fmt, ...);
@@ -74,7 +80,10 @@ struct StageTimer {
 
 // kernel launchers (defined in the .cu files)
 int launch_path_costs(gcp_ctx*, const int32_t* dna, uint32_t P, uint32_t* edge_ids,
-                      double* dist, double* turn, uint8_t* flags, cudaStream_t);
+                      uint32_t* step_info, double* dist, double* turn, uint8_t* flags,
+                      cudaStream_t);
+int launch_coverage_masked(gcp_ctx*, const uint32_t* step_info, uint32_t P, uint32_t* cov,
+                           uint8_t* flags, cudaStream_t);
 int launch_coverage(gcp_ctx*, const uint32_t* edge_ids, uint32_t P, uint32_t* cov,
                     uint8_t* flags, cudaStream_t);
 int launch_loop_closures(gcp_ctx*, const int32_t* dna, uint32_t P, const double* dist,

@@ -23,8 +23,8 @@ constexpr int K1_STAGE_ELEMS = 2048;   // double2 entries (32 KB)
 
 __global__ void __launch_bounds__(K1_THREADS)
 k_path_costs(const int32_t* __restrict__ dna, uint32_t P, GcpTables t, int A, int L,
-             uint32_t* __restrict__ edge_ids, double* __restrict__ dist,
-             double* __restrict__ turn, uint8_t* __restrict__ flags)
+             uint32_t* __restrict__ edge_ids, uint32_t* __restrict__ step_info,
+             double* __restrict__ dist, double* __restrict__ turn, uint8_t* __restrict__ flags)
 {
     __shared__ int s_first_neg[GCP_MAX_AGENTS];
     __shared__ int s_bad;       // bit0: non-traversable step, bit1: gene out of range
@@ -75,6 +75,9 @@ k_path_costs(const int32_t* __restrict__ dna, uint32_t P, GcpTables t, int A, in
                 }
             }
             edge_ids[(size_t)org * AL + a * L + i] = e;
+            if (step_info)
+                step_info[(size_t)org * AL + a * L + i] =
+                    (e != GCP_INVALID_EDGE) ? __ldg(t.m_sub_info + e) : 0u;
             s_stage[ii * A + a] = c;
         }
         __syncthreads();
@@ -98,12 +101,15 @@ k_path_costs(const int32_t* __restrict__ dna, uint32_t P, GcpTables t, int A, in
 }
 
 int launch_path_costs(gcp_ctx* ctx, const int32_t* dna, uint32_t P, uint32_t* edge_ids,
-                      double* dist, double* turn, uint8_t* flags, cudaStream_t st)
+                      uint32_t* step_info, double* dist, double* turn, uint8_t* flags,
+                      cudaStream_t st)
 {
     if (P == 0) return 0;
+    if (step_info && !ctx->have_masked)
+        return gcp_fail(ctx, -1, "step_info requested but no masked footprint store uploaded");
     StageTimer tm(ctx, 0, st);
-    k_path_costs<<<P, K1_THREADS, 0, st>>>(dna, P, ctx->t, ctx->p.num_agents,
-                                           ctx->p.max_dna_len, edge_ids, dist, turn, flags);
+    k_path_costs<<<P, K1_THREADS, 0, st>>>(dna, P, ctx->t, ctx->p.num_agents, ctx->p.max_dna_len,
+                                           edge_ids, step_info, dist, turn, flags);
     ctx->launches++;
     GCP_CUDA(ctx, cudaGetLastError());
     return 0;
@@ -114,26 +120,27 @@ int launch_path_costs(gcp_ctx* ctx, const int32_t* dna, uint32_t P, uint32_t* ed
 //     map planes.  One CTA per organism.
 //
 //   phase 1 (thread per step): each step's edge contributes 1..4 sub-tiles, each aligned
-//     to one 64x64 map block.  Sub-tiles are grouped by block with an open-addressing
-//     hash table in shared memory (key = block id) and per-block linked lists (one
-//     atomicExch per sub-tile).
+//     to one 64x64 map block.  Sub-tiles are bucketed by block: an open-addressing hash
+//     table in shared memory maps block id -> slot, one shared atomicAdd per sub-tile
+//     returns its rank inside the slot; a CTA-wide exclusive scan of the slot counts then
+//     turns (slot, rank) into a position, i.e. a counting sort with one atomic per item.
 //   phase 2 (warp per block, "owner computes"): the warp holds the block's 64 rows in
-//     registers (lane l = rows 2l,2l+1 = one uint4), walks the list, ORs 128-bit
-//     coalesced loads of the stored quarters, then popcounts against the mask planes.
+//     registers (lane l = rows 2l,2l+1 = one uint4), reads its bucket 32 payloads at a
+//     time, broadcasts them by shuffle and ORs 128-bit coalesced loads of the stored
+//     quarters (4 loads in flight per lane), then popcounts against the mask planes.
 //     No shared-memory bitmap, no zeroing pass, no bitmap atomics.
 //   If the table or pair store overflows (very long genomes), the organism is redone in
-//   R = 2,4,8.. spatial partitions of the blocks; results are exact in every case.
+//   R = 2,4,8.. hash partitions of the blocks; results are exact in every case.
 // ============================================================================
 __device__ __forceinline__ uint32_t hash_block(uint32_t b) { return b * 2654435761u; }
 __device__ __forceinline__ uint32_t part_block(uint32_t b) { return (b * 0x85ebca6bu) >> 12; }
 
-__device__ __forceinline__ uint4 ld_quarter(const uint4* __restrict__ tile, uint32_t p, int lane)
+__device__ __forceinline__ uint4 ld_quarter(const uint4* __restrict__ tile, uint32_t p,
+                                            uint32_t q, uint32_t below, uint32_t l7)
 {
-    const uint32_t qm = p & 15u;
-    const int q = lane >> 3;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if ((qm >> q) & 1u) {
-        const size_t idx = ((size_t)(p >> 4) + __popc(qm & ((1u << q) - 1u))) * 8 + (lane & 7);
+    if ((p >> q) & 1u) {
+        const uint32_t idx = (((p >> 4) + __popc(p & below)) << 3) | l7;
         v = __ldg(tile + idx);
     }
     return v;
@@ -152,22 +159,25 @@ __device__ __forceinline__ void or128(uint4& a, uint4 b)
     a.x |= b.x; a.y |= b.y; a.z |= b.z; a.w |= b.w;
 }
 
-constexpr uint32_t K2_NIL = 0xFFFFu;
-
-template <int THREADS>
+// NEED_FREE: also count against the (g==0) plane (internal coverage, blend < 1 or detail)
+// NEED_ALL : also count every painted pixel (detail output n_cov_all)
+// HAS_GRAY : the map has pixels with 0 < g < 255
+template <int THREADS, bool NEED_FREE, bool NEED_ALL, bool HAS_GRAY>
 __global__ void __launch_bounds__(THREADS)
 k_coverage(const uint32_t* __restrict__ edge_ids, uint32_t P, GcpTables t, int AL,
-           int T /*pow2*/, int MAXP /*<=65535*/, uint32_t* __restrict__ cov,
-           uint8_t* __restrict__ flags)
+           int T /*pow2, multiple of THREADS*/, int MAXP /*<=65535*/, uint32_t R0,
+           uint32_t* __restrict__ cov, uint8_t* __restrict__ flags)
 {
     constexpr int NW = THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem[];
     uint4*    s_scr  = reinterpret_cast<uint4*>(smem);                  // [NW][32] gray scratch
-    uint32_t* s_keys = reinterpret_cast<uint32_t*>(s_scr + NW * 32);    // [T] block id + 1
-    uint32_t* s_head = s_keys + T;                                       // [T] first pair | NIL
-    uint32_t* s_pay  = s_head + T;                                       // [MAXP]
-    uint16_t* s_next = reinterpret_cast<uint16_t*>(s_pay + MAXP);        // [MAXP]
-    __shared__ uint32_t s_npairs, s_overflow;
+    uint32_t* s_keys = reinterpret_cast<uint32_t*>(s_scr + (HAS_GRAY ? NW * 32 : 0)); // [T] block+1
+    uint32_t* s_cnt  = s_keys + T;                                       // [T] count -> base
+    uint32_t* s_pay  = s_cnt + T;                                        // [MAXP] payload
+    uint32_t* s_sr   = s_pay + MAXP;                                     // [MAXP] slot<<16 | rank
+    uint16_t* s_sort = reinterpret_cast<uint16_t*>(s_sr + MAXP);         // [MAXP] pair index
+    __shared__ uint32_t s_npairs, s_overflow, s_group;
+    __shared__ uint32_t s_wsum[NW];
     __shared__ uint32_t s_tot[6];
 
     const uint32_t org = blockIdx.x;
@@ -175,8 +185,9 @@ k_coverage(const uint32_t* __restrict__ edge_ids, uint32_t P, GcpTables t, int A
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t* eids = edge_ids + (size_t)org * AL;
     const int logT = 31 - __clz(T);
+    const uint32_t q = 0u + (lane >> 3), below = (1u << q) - 1u, l7 = lane & 7;
 
-    uint32_t R = 1;
+    uint32_t R = R0;
     bool failed = false;
     uint32_t n_mask0, n_free0, wg_mask, wg_all, n_gmask, n_all;
 
@@ -185,22 +196,26 @@ k_coverage(const uint32_t* __restrict__ edge_ids, uint32_t P, GcpTables t, int A
         bool overflow = false;
         for (uint32_t r = 0; r < R && !overflow; ++r) {
             // ---- clear table ----
-            for (int i = tid; i < T; i += THREADS) { s_keys[i] = 0; s_head[i] = K2_NIL; }
-            if (tid == 0) { s_npairs = 0; s_overflow = 0; }
+            for (int i = tid; i < T; i += THREADS) { s_keys[i] = 0; s_cnt[i] = 0; }
+            if (tid == 0) { s_npairs = 0; s_overflow = 0; s_group = 0; }
             __syncthreads();
-            // ---- phase 1: group sub-tiles by block ----
+            // ---- phase 1: slot + rank for every sub-tile ----
             for (int s0 = warp * 32; s0 < AL; s0 += THREADS) {
                 const int s = s0 + lane;
                 uint32_t lo = 0, hi = 0;
                 if (s < AL) {
                     const uint32_t e = eids[s];
-                    if (e != GCP_INVALID_EDGE) { lo = t.sub_ptr[e]; hi = t.sub_ptr[e + 1]; }
+                    if (e != GCP_INVALID_EDGE) {
+                        const uint32_t info = __ldg(t.sub_info + e);
+                        lo = info & 0x0FFFFFFFu;
+                        hi = lo + (info >> 28);
+                    }
                 }
                 uint32_t mine = hi - lo;
                 if (R > 1) {
                     mine = 0;
                     for (uint32_t k = lo; k < hi; ++k)
-                        mine += ((part_block(t.sub_block[k]) & (R - 1)) == r);
+                        mine += ((part_block(__ldg(t.sub_desc + k).x) & (R - 1)) == r);
                 }
                 // warp-aggregated allocation of pair slots
                 uint32_t incl = mine;
@@ -220,7 +235,8 @@ k_coverage(const uint32_t* __restrict__ edge_ids, uint32_t P, GcpTables t, int A
                 }
                 uint32_t idx = base + incl - mine;
                 for (uint32_t k = lo; k < hi; ++k) {
-                    const uint32_t blk = t.sub_block[k];
+                    const uint2 dsc = __ldg(t.sub_desc + k);
+                    const uint32_t blk = dsc.x;
                     if (R > 1 && (part_block(blk) & (R - 1)) != r) continue;
                     const uint32_t key = blk + 1;
                     uint32_t h = hash_block(blk) >> (32 - logT);
@@ -236,56 +252,102 @@ k_coverage(const uint32_t* __restrict__ edge_ids, uint32_t P, GcpTables t, int A
                         if (++probes >= T) { s_overflow = 1; break; }
                     }
                     if (probes >= T) break;
-                    s_pay[idx] = t.sub_payload[k];
-                    s_next[idx] = (uint16_t)atomicExch(&s_head[h], idx);
+                    const uint32_t rank = atomicAdd(&s_cnt[h], 1u);
+                    s_pay[idx] = dsc.y;
+                    s_sr[idx] = (h << 16) | rank;
                     ++idx;
                 }
             }
             __syncthreads();
             overflow = (s_overflow != 0);      // table or pair store full: more partitions
             if (overflow) { __syncthreads(); break; }
-            // ---- phase 2: owner warps ----
-            for (int g0 = warp * 32; g0 < T; g0 += THREADS) {
-                const uint32_t hd = s_head[g0 + lane];
-                uint32_t m = __ballot_sync(FULL, hd != K2_NIL);
+            const uint32_t npairs = s_npairs;
+            // ---- exclusive scan of the slot counts (T entries, T/THREADS per thread) ----
+            {
+                const int per = T / THREADS;
+                uint32_t loc = 0;
+                for (int k = 0; k < per; ++k) loc += s_cnt[tid * per + k];
+                uint32_t inc = loc;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t v = __shfl_up_sync(FULL, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                if (lane == 31) s_wsum[warp] = inc;
+                __syncthreads();
+                uint32_t woff = 0;
+                for (int w2 = 0; w2 < warp; ++w2) woff += s_wsum[w2];
+                uint32_t run = woff + inc - loc;
+                for (int k = 0; k < per; ++k) {
+                    const uint32_t c = s_cnt[tid * per + k];
+                    // keep the count in the high half: cnt[slot] = count<<16 | base
+                    s_cnt[tid * per + k] = (c << 16) | run;
+                    run += c;
+                }
+            }
+            __syncthreads();
+            // ---- place: sorted position = base[slot] + rank ----
+            for (uint32_t i = tid; i < npairs; i += THREADS) {
+                const uint32_t sr = s_sr[i];
+                s_sort[(s_cnt[sr >> 16] & 0xFFFFu) + (sr & 0xFFFFu)] = (uint16_t)i;
+            }
+            __syncthreads();
+            // ---- phase 2: owner warps, groups of 32 slots handed out dynamically ----
+            for (;;) {
+                uint32_t g = 0;
+                if (lane == 0) g = atomicAdd(&s_group, 1u);
+                g = __shfl_sync(FULL, g, 0);
+                if (g * 32 >= (uint32_t)T) break;
+                const uint32_t cb = s_cnt[g * 32 + lane];
+                const uint32_t ky = s_keys[g * 32 + lane];
+                uint32_t m = __ballot_sync(FULL, (cb >> 16) != 0);
                 while (m) {
                     const int b = __ffs(m) - 1;
                     m &= m - 1;
-                    uint32_t i = __shfl_sync(FULL, hd, b);
-                    const uint32_t blk = s_keys[g0 + b] - 1;
-                    uint4 acc = make_uint4(0, 0, 0, 0);
-                    while (i != K2_NIL) {
-                        uint32_t p0, p1 = 0, p2 = 0, p3 = 0;
-                        p0 = s_pay[i]; i = s_next[i];
-                        if (i != K2_NIL) { p1 = s_pay[i]; i = s_next[i]; }
-                        if (i != K2_NIL) { p2 = s_pay[i]; i = s_next[i]; }
-                        if (i != K2_NIL) { p3 = s_pay[i]; i = s_next[i]; }
-                        const uint4 v0 = ld_quarter(t.tile, p0, lane);
-                        const uint4 v1 = ld_quarter(t.tile, p1, lane);
-                        const uint4 v2 = ld_quarter(t.tile, p2, lane);
-                        const uint4 v3 = ld_quarter(t.tile, p3, lane);
-                        or128(acc, v0); or128(acc, v1); or128(acc, v2); or128(acc, v3);
-                    }
+                    const uint32_t cbb = __shfl_sync(FULL, cb, b);
+                    const uint32_t blk = __shfl_sync(FULL, ky, b) - 1;
+                    const uint32_t cnt = cbb >> 16, base = cbb & 0xFFFFu;
                     const uint4 mk = __ldg(t.blk_mask0 + (size_t)blk * 32 + lane);
-                    const uint4 fr = __ldg(t.blk_free0 + (size_t)blk * 32 + lane);
-                    n_all   += popc128(acc);
-                    n_mask0 += popc128(and128(acc, mk));
-                    n_free0 += popc128(and128(acc, fr));
-                    const uint32_t ga = t.gray_ptr[blk], gb = t.gray_ptr[blk + 1];
-                    if (gb > ga) {                     // gray pixels (0 < g < 255), SURVEY F6
-                        s_scr[warp * 32 + lane] = acc;
-                        __syncwarp();
-                        const uint64_t* rows = reinterpret_cast<const uint64_t*>(s_scr + warp * 32);
-                        for (uint32_t g = ga + lane; g < gb; g += 32) {
-                            const uint32_t ent = t.gray_ent[g];
-                            const uint32_t pos = ent & 4095u;
-                            if ((rows[pos >> 6] >> (pos & 63u)) & 1ull) {
-                                const uint32_t w = (ent >> 12) & 255u;
-                                wg_all += w;
-                                if ((ent >> 20) & 1u) { wg_mask += w; n_gmask += 1; }
-                            }
+                    uint4 fr = make_uint4(0, 0, 0, 0);
+                    if (NEED_FREE) fr = __ldg(t.blk_free0 + (size_t)blk * 32 + lane);
+                    uint4 acc = make_uint4(0, 0, 0, 0);
+                    for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
+                        uint32_t my = 0;
+                        if (c0 + lane < cnt) my = s_pay[s_sort[base + c0 + lane]];
+                        const uint32_t nn = min(32u, cnt - c0);
+                        for (uint32_t k = 0; k < nn; k += 4) {
+                            const uint32_t p0 = __shfl_sync(FULL, my, k);
+                            const uint32_t p1 = __shfl_sync(FULL, my, k + 1);
+                            const uint32_t p2 = __shfl_sync(FULL, my, k + 2);
+                            const uint32_t p3 = __shfl_sync(FULL, my, k + 3);
+                            const uint4 v0 = ld_quarter(t.tile, p0, q, below, l7);
+                            const uint4 v1 = ld_quarter(t.tile, p1, q, below, l7);
+                            const uint4 v2 = ld_quarter(t.tile, p2, q, below, l7);
+                            const uint4 v3 = ld_quarter(t.tile, p3, q, below, l7);
+                            or128(acc, v0); or128(acc, v1); or128(acc, v2); or128(acc, v3);
                         }
-                        __syncwarp();
+                    }
+                    n_mask0 += popc128(and128(acc, mk));
+                    if (NEED_FREE) n_free0 += popc128(and128(acc, fr));
+                    if (NEED_ALL) n_all += popc128(acc);
+                    if (HAS_GRAY) {
+                        const uint32_t ga = t.gray_ptr[blk], gb = t.gray_ptr[blk + 1];
+                        if (gb > ga) {                 // gray pixels (0 < g < 255), SURVEY F6
+                            s_scr[warp * 32 + lane] = acc;
+                            __syncwarp();
+                            const uint64_t* rows =
+                                reinterpret_cast<const uint64_t*>(s_scr + warp * 32);
+                            for (uint32_t gi = ga + lane; gi < gb; gi += 32) {
+                                const uint32_t ent = t.gray_ent[gi];
+                                const uint32_t pos = ent & 4095u;
+                                if ((rows[pos >> 6] >> (pos & 63u)) & 1ull) {
+                                    const uint32_t w = (ent >> 12) & 255u;
+                                    wg_all += w;
+                                    if ((ent >> 20) & 1u) { wg_mask += w; n_gmask += 1; }
+                                }
+                            }
+                            __syncwarp();
+                        }
                     }
                 }
             }
@@ -312,10 +374,25 @@ k_coverage(const uint32_t* __restrict__ edge_ids, uint32_t P, GcpTables t, int A
     if (tid == 0 && failed && flags) flags[(size_t)org * 4 + 3] |= 2;
 }
 
-static size_t cov_smem_bytes(int threads, int T, int MAXP)
+constexpr int K2_THREADS = 256;
+
+static size_t cov_smem_bytes(bool gray, int T, int MAXP)
 {
-    return (size_t)(threads / 32) * 32 * 16 + (size_t)T * 8 + (size_t)MAXP * 4 +
+    return (gray ? (size_t)(K2_THREADS / 32) * 32 * 16 : 0) + (size_t)T * 8 + (size_t)MAXP * 8 +
            (size_t)((MAXP * 2 + 15) / 16) * 16;
+}
+
+template <bool F, bool A, bool G>
+static int launch_cov_variant(gcp_ctx* ctx, const uint32_t* edge_ids, uint32_t P, int AL, int T,
+                              int maxp, size_t smem, uint32_t* cov, uint8_t* flags, cudaStream_t st)
+{
+    GCP_CUDA(ctx, cudaFuncSetAttribute(k_coverage<K2_THREADS, F, A, G>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint32_t R0 = 1;                      // expected ~2.2 sub-tiles per step
+    while ((size_t)R0 * maxp < (size_t)AL * 5 / 2 && R0 < 4096) R0 <<= 1;
+    k_coverage<K2_THREADS, F, A, G><<<P, K2_THREADS, smem, st>>>(edge_ids, P, ctx->t, AL, T, maxp,
+                                                                R0, cov, flags);
+    return 0;
 }
 
 int launch_coverage(gcp_ctx* ctx, const uint32_t* edge_ids, uint32_t P, uint32_t* cov,
@@ -323,28 +400,294 @@ int launch_coverage(gcp_ctx* ctx, const uint32_t* edge_ids, uint32_t P, uint32_t
 {
     if (P == 0) return 0;
     const int AL = ctx->p.num_agents * ctx->p.max_dna_len;
-    // pair store sized for ~3 sub-tiles per step, table for a quarter of that
-    int maxp = ctx->cov_maxpairs;
-    if (maxp <= 0) {
-        maxp = 1024;
-        while (maxp < 3 * AL && maxp < 16384) maxp <<= 1;
-    }
-    if (maxp > 65534) maxp = 65534;
+    // pair store sized for 3 sub-tiles per step (average is ~2), table for a third of that
+    int maxp = ctx->cov_maxpairs > 0 ? ctx->cov_maxpairs : 3 * AL;
+    if (maxp < 256) maxp = 256;
+    if (maxp > 32768) maxp = 32768;
     int T = ctx->cov_table;
-    if (T <= 0) { T = 256; while (T < maxp / 4) T <<= 1; }
-    constexpr int THREADS = 256;
-    const size_t smem = cov_smem_bytes(THREADS, T, maxp);
+    if (T <= 0) { T = K2_THREADS; while (T < maxp / 3) T <<= 1; }
+    if (T > 32768) T = 32768;
+    const bool gray = ctx->n_gray > 0;
+    const bool need_free = ctx->cov_detail || ctx->p.coverage_blend != 1.0;
+    const bool need_all = ctx->cov_detail != 0;
+    const size_t smem = cov_smem_bytes(gray, T, maxp);
     if (smem > (size_t)ctx->max_smem_optin)
         return gcp_fail(ctx, -3, "coverage kernel needs %zu B shared memory", smem);
-    static bool attr_set = false;
-    if (!attr_set || smem > 48 * 1024) {
-        GCP_CUDA(ctx, cudaFuncSetAttribute(k_coverage<THREADS>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem));
-        attr_set = true;
-    }
     StageTimer tm(ctx, 1, st);
-    k_coverage<THREADS><<<P, THREADS, smem, st>>>(edge_ids, P, ctx->t, AL, T, maxp, cov, flags);
+    int r;
+    if (gray)                     r = launch_cov_variant<true, true, true>(ctx, edge_ids, P, AL, T, maxp, smem, cov, flags, st);
+    else if (need_all)            r = launch_cov_variant<true, true, false>(ctx, edge_ids, P, AL, T, maxp, smem, cov, flags, st);
+    else if (need_free)           r = launch_cov_variant<true, false, false>(ctx, edge_ids, P, AL, T, maxp, smem, cov, flags, st);
+    else                          r = launch_cov_variant<false, false, false>(ctx, edge_ids, P, AL, T, maxp, smem, cov, flags, st);
+    if (r) return r;
+    ctx->launches++;
+    GCP_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+// ============================================================================
+// K2m  wall coverage from the PRE-MASKED footprint store (objectives-only fast path).
+//   Every stored sub-tile is footprint AND buffer_mask, so the wall-coverage pixel count is
+//   just popcount(union): no plane loads, fewer and emptier sub-tiles (the mask is a thin
+//   band along walls).  Same counting-sort bucketing as k_coverage, but phase 2 walks the
+//   flat sorted payload array: each warp owns a contiguous range snapped to bucket
+//   boundaries, keeps 4 independent 128-bit loads in flight per lane across bucket
+//   boundaries, and closes a bucket (popcount, clear) when it meets the "last" flag.
+//   sorted entry = payload << 1 | last   (payload = offset128 << 4 | qmask, offset < 2^27)
+// ============================================================================
+constexpr int K2M_THREADS = 256;
+constexpr int K2M_PPT = 12;               // pairs staged per thread (MAXP <= 12 * 256)
+
+__device__ __forceinline__ uint4 ld_quarter1(const uint4* __restrict__ tile, uint32_t p,
+                                             uint32_t q1, uint32_t below1, uint32_t l7)
+{
+    // p = payload << 1 | last  ->  qmask at bits [1,5), offset at bits [5,32)
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if ((p >> q1) & 1u) {
+        const uint32_t idx = (((p >> 5) + __popc(p & below1)) << 3) | l7;
+        v = __ldg(tile + idx);
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(K2M_THREADS, 6)
+k_coverage_masked(const uint32_t* __restrict__ step_info, uint32_t P,
+                  const uint2* __restrict__ sub_desc, const uint4* __restrict__ tile, int AL,
+                  int T /*pow2, multiple of THREADS*/, int MAXP /*<= PPT*THREADS*/, uint32_t R0,
+                  uint32_t* __restrict__ cov, uint8_t* __restrict__ flags)
+{
+    constexpr int THREADS = K2M_THREADS;
+    constexpr int NW = THREADS / 32;
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint32_t* s_keys = reinterpret_cast<uint32_t*>(smem);   // [T] block id + 1
+    uint32_t* s_cnt  = s_keys + T;                           // [T] count -> count<<16 | base
+    uint32_t* s_pay  = s_cnt + T;                            // [MAXP] payload, then sorted entries
+    uint32_t* s_sr   = s_pay + MAXP;                         // [MAXP] slot<<16 | rank
+    __shared__ uint32_t s_npairs, s_overflow;
+    __shared__ uint32_t s_wsum[NW];
+    __shared__ uint32_t s_total;
+
+    const uint32_t org = blockIdx.x;
+    if (org >= P) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t* info = step_info + (size_t)org * AL;
+    const int logT = 31 - __clz(T);
+    const uint32_t q1 = 1u + (lane >> 3), below1 = ((1u << q1) - 1u) & ~1u, l7 = lane & 7;
+
+    uint32_t R = R0;
+    bool failed = false;
+    uint32_t n_cov;
+
+    for (;;) {                                   // retry loop over partition count R
+        n_cov = 0;
+        bool overflow = false;
+        for (uint32_t r = 0; r < R && !overflow; ++r) {
+            for (int i = tid; i < T; i += THREADS) { s_keys[i] = 0; s_cnt[i] = 0; }
+            if (tid == 0) { s_npairs = 0; s_overflow = 0; }
+            __syncthreads();
+            // ---- phase 1: slot + rank for every sub-tile ----
+            for (int s0 = warp * 32; s0 < AL; s0 += THREADS) {
+                const int s = s0 + lane;
+                uint32_t lo = 0, n = 0;
+                if (s < AL) {
+                    const uint32_t inf = __ldg(info + s);
+                    lo = inf & 0x0FFFFFFFu;
+                    n = inf >> 28;
+                }
+                // fetch the first four descriptors together (one L2 round trip)
+                uint2 d[4];
+                #pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    d[k] = (k < (int)n) ? __ldg(sub_desc + lo + k) : make_uint2(0, 0);
+                uint32_t mine = n;
+                if (R > 1) {
+                    mine = 0;
+                    for (uint32_t k = 0; k < n; ++k) {
+                        const uint32_t blk = (k == 0) ? d[0].x : (k == 1) ? d[1].x : (k == 2) ? d[2].x
+                                           : (k == 3) ? d[3].x : __ldg(sub_desc + lo + k).x;
+                        mine += ((part_block(blk) & (R - 1)) == r);
+                    }
+                }
+                uint32_t incl = mine;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t v = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const uint32_t total = __shfl_sync(FULL, incl, 31);
+                if (total == 0) continue;
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&s_npairs, total);
+                base = __shfl_sync(FULL, base, 0);
+                if (base + total > (uint32_t)MAXP) {
+                    if (lane == 0) s_overflow = 1;
+                    continue;
+                }
+                uint32_t idx = base + incl - mine;
+                for (uint32_t k = 0; k < n; ++k) {
+                    uint2 dsc;
+                    if (k == 0) dsc = d[0]; else if (k == 1) dsc = d[1];
+                    else if (k == 2) dsc = d[2]; else if (k == 3) dsc = d[3];
+                    else dsc = __ldg(sub_desc + lo + k);
+                    const uint32_t blk = dsc.x;
+                    if (R > 1 && (part_block(blk) & (R - 1)) != r) continue;
+                    const uint32_t key = blk + 1;
+                    uint32_t h = hash_block(blk) >> (32 - logT);
+                    int probes = 0;
+                    for (;;) {
+                        const uint32_t cur = ((volatile uint32_t*)s_keys)[h];
+                        if (cur == key) break;
+                        if (cur == 0) {
+                            const uint32_t old = atomicCAS(&s_keys[h], 0u, key);
+                            if (old == 0 || old == key) break;
+                        }
+                        h = (h + 1) & (T - 1);
+                        if (++probes >= T) { s_overflow = 1; break; }
+                    }
+                    if (probes >= T) break;
+                    const uint32_t rank = atomicAdd(&s_cnt[h], 1u);
+                    s_pay[idx] = dsc.y;
+                    s_sr[idx] = (h << 16) | rank;
+                    ++idx;
+                }
+            }
+            __syncthreads();
+            overflow = (s_overflow != 0);
+            if (overflow) { __syncthreads(); break; }
+            const uint32_t npairs = s_npairs;
+            // ---- exclusive scan of the slot counts ----
+            {
+                const int per = T / THREADS;
+                uint32_t loc = 0;
+                for (int k = 0; k < per; ++k) loc += s_cnt[tid * per + k];
+                uint32_t inc = loc;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t v = __shfl_up_sync(FULL, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                if (lane == 31) s_wsum[warp] = inc;
+                __syncthreads();
+                uint32_t woff = 0;
+                for (int w2 = 0; w2 < warp; ++w2) woff += s_wsum[w2];
+                uint32_t run = woff + inc - loc;
+                for (int k = 0; k < per; ++k) {
+                    const uint32_t c = s_cnt[tid * per + k];
+                    s_cnt[tid * per + k] = (c << 16) | run;
+                    run += c;
+                }
+            }
+            __syncthreads();
+            // ---- place through registers so the sorted array can reuse s_pay ----
+            uint32_t ent[K2M_PPT], pos[K2M_PPT];
+            #pragma unroll
+            for (int k = 0; k < K2M_PPT; ++k) {
+                const uint32_t i = tid + k * THREADS;
+                pos[k] = 0xFFFFFFFFu;
+                if (i < npairs) {
+                    const uint32_t sr = s_sr[i];
+                    const uint32_t cb = s_cnt[sr >> 16];
+                    const uint32_t rank = sr & 0xFFFFu;
+                    pos[k] = (cb & 0xFFFFu) + rank;
+                    ent[k] = (s_pay[i] << 1) | (rank + 1 == (cb >> 16) ? 1u : 0u);
+                }
+            }
+            __syncthreads();
+            #pragma unroll
+            for (int k = 0; k < K2M_PPT; ++k)
+                if (pos[k] != 0xFFFFFFFFu) s_pay[pos[k]] = ent[k];
+            __syncthreads();
+            // ---- phase 2: each warp takes an equal share of the flat array, snapped to
+            //      bucket boundaries (a range starts right after a "last" entry) ----
+            uint32_t bounds[2];
+            #pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const uint32_t w = warp + e;
+                uint32_t b = (uint32_t)(((uint64_t)npairs * w) / NW);
+                if (w == 0) b = 0;
+                else if (w >= (uint32_t)NW) b = npairs;
+                else {
+                    // first position >= b whose predecessor is a "last" entry
+                    uint32_t c = b;
+                    for (;;) {
+                        const uint32_t pp = c + lane;       // predecessor index pp - 1
+                        const bool is_start = (pp >= npairs) ||
+                                              (pp == 0) || ((s_pay[pp - 1] & 1u) != 0);
+                        const uint32_t m = __ballot_sync(FULL, is_start);
+                        if (m) { c += __ffs(m) - 1; break; }
+                        c += 32;
+                    }
+                    b = min(c, npairs);
+                }
+                bounds[e] = b;
+            }
+            uint4 acc = make_uint4(0, 0, 0, 0);
+            for (uint32_t c0 = bounds[0]; c0 < bounds[1]; c0 += 32) {
+                uint32_t my = 0;
+                if (c0 + lane < bounds[1]) my = s_pay[c0 + lane];
+                const uint32_t nn = min(32u, bounds[1] - c0);
+                for (uint32_t k = 0; k < nn; k += 4) {
+                    const uint32_t p0 = __shfl_sync(FULL, my, k);
+                    const uint32_t p1 = __shfl_sync(FULL, my, k + 1);
+                    const uint32_t p2 = __shfl_sync(FULL, my, k + 2);
+                    const uint32_t p3 = __shfl_sync(FULL, my, k + 3);
+                    const uint4 v0 = ld_quarter1(tile, p0, q1, below1, l7);
+                    const uint4 v1 = ld_quarter1(tile, p1, q1, below1, l7);
+                    const uint4 v2 = ld_quarter1(tile, p2, q1, below1, l7);
+                    const uint4 v3 = ld_quarter1(tile, p3, q1, below1, l7);
+                    or128(acc, v0);
+                    if (p0 & 1u) { n_cov += popc128(acc); acc = make_uint4(0, 0, 0, 0); }
+                    or128(acc, v1);
+                    if (p1 & 1u) { n_cov += popc128(acc); acc = make_uint4(0, 0, 0, 0); }
+                    or128(acc, v2);
+                    if (p2 & 1u) { n_cov += popc128(acc); acc = make_uint4(0, 0, 0, 0); }
+                    or128(acc, v3);
+                    if (p3 & 1u) { n_cov += popc128(acc); acc = make_uint4(0, 0, 0, 0); }
+                }
+            }
+            __syncthreads();
+        }
+        if (!overflow) break;
+        R <<= 1;
+        if (R > 4096) { failed = true; break; }
+    }
+
+    if (tid == 0) s_total = 0;
+    __syncthreads();
+    uint32_t v = n_cov;
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    if (lane == 0 && v) atomicAdd(&s_total, v);
+    __syncthreads();
+    if (tid < 8) {
+        const uint32_t n = failed ? 0u : s_total;
+        cov[(size_t)org * 8 + tid] = (tid == 0 || tid == 4) ? n : 0u;
+    }
+    if (tid == 0 && failed && flags) flags[(size_t)org * 4 + 3] |= 2;
+}
+
+int launch_coverage_masked(gcp_ctx* ctx, const uint32_t* step_info, uint32_t P, uint32_t* cov,
+                           uint8_t* flags, cudaStream_t st)
+{
+    if (P == 0) return 0;
+    if (!ctx->have_masked) return gcp_fail(ctx, -1, "masked footprint store not uploaded");
+    const int AL = ctx->p.num_agents * ctx->p.max_dna_len;
+    int maxp = ctx->cov_maxpairs > 0 ? ctx->cov_maxpairs : 2 * AL;
+    if (maxp < 256) maxp = 256;
+    if (maxp > K2M_PPT * K2M_THREADS) maxp = K2M_PPT * K2M_THREADS;
+    int T = ctx->cov_table;
+    if (T <= 0) { T = K2M_THREADS; while (T < maxp / 5) T <<= 1; }
+    if (T > 32768) T = 32768;
+    const size_t smem = (size_t)T * 8 + (size_t)maxp * 8;
+    if (smem > (size_t)ctx->max_smem_optin)
+        return gcp_fail(ctx, -3, "masked coverage kernel needs %zu B shared memory", smem);
+    GCP_CUDA(ctx, cudaFuncSetAttribute(k_coverage_masked,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    StageTimer tm(ctx, 1, st);
+    uint32_t R0 = 1;                      // expected ~1.1 masked sub-tiles per step
+    while ((size_t)R0 * maxp < (size_t)AL + AL / 2 && R0 < 4096) R0 <<= 1;
+    k_coverage_masked<<<P, K2M_THREADS, smem, st>>>(step_info, P, ctx->t.m_sub_desc, ctx->t.m_tile,
+                                                    AL, T, maxp, R0, cov, flags);
     ctx->launches++;
     GCP_CUDA(ctx, cudaGetLastError());
     return 0;

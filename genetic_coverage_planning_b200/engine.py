@@ -71,6 +71,12 @@ class FitnessEngine(object):
             _ptr(arr(pw.sub_ptr, np.uint32)), _ptr(arr(pw.sub_block, np.uint32)),
             _ptr(arr(pw.sub_payload, np.uint32)), len(pw.sub_block),
             _ptr(arr(pw.tile_data, np.uint64)), pw.n_quarters))
+        self.has_masked = hasattr(pw, "m_sub_ptr")
+        if self.has_masked:
+            self._check(self.lib.gcp_upload_masked_footprints(
+                ctx, _ptr(arr(pw.m_sub_ptr, np.uint32)), _ptr(arr(pw.m_sub_block, np.uint32)),
+                _ptr(arr(pw.m_sub_payload, np.uint32)), len(pw.m_sub_block),
+                _ptr(arr(pw.m_tile_data, np.uint64)), pw.m_n_quarters))
         mc = GcpMapConsts(pw.H, pw.W, pw.nbx, pw.nby, pw.mask_size, pw.gsum_mask, pw.map_size,
                           pw.num_occluded)
         self._check(self.lib.gcp_upload_map(
@@ -174,18 +180,34 @@ class FitnessEngine(object):
         return obj_host, flags_host
 
     # ---- individual stages (tests / profiling) ------------------------------
-    def path_costs(self, dna):
+    def path_costs(self, dna, with_step_info=False):
         dna = self.to_device_dna(dna)
         P, dev = dna.shape[0], self.device
         edge_ids = torch.empty((P, self.A, self.L), dtype=torch.int32, device=dev)
+        step_info = (torch.empty((P, self.A, self.L), dtype=torch.int32, device=dev)
+                     if with_step_info else None)
         dist = torch.empty((P, self.A), dtype=torch.float64, device=dev)
         turn = torch.empty((P, self.A), dtype=torch.float64, device=dev)
         flags = torch.zeros((P, 4), dtype=torch.uint8, device=dev)
         self._check(self.lib.gcp_path_costs(
             self.ctx, C.c_void_p(dna.data_ptr()), P, C.c_void_p(edge_ids.data_ptr()),
+            C.c_void_p(step_info.data_ptr()) if with_step_info else None,
             C.c_void_p(dist.data_ptr()), C.c_void_p(turn.data_ptr()),
             C.c_void_p(flags.data_ptr()), self._stream()))
+        if with_step_info:
+            return edge_ids, step_info, dist, turn, flags
         return edge_ids, dist, turn, flags
+
+    def coverage_masked(self, step_info, cov=None, flags=None):
+        P = step_info.shape[0]
+        if cov is None:
+            cov = torch.empty((P, 8), dtype=torch.int32, device=self.device)
+        if flags is None:
+            flags = torch.zeros((P, 4), dtype=torch.uint8, device=self.device)
+        self._check(self.lib.gcp_coverage_masked(
+            self.ctx, C.c_void_p(step_info.data_ptr()), P, C.c_void_p(cov.data_ptr()),
+            C.c_void_p(flags.data_ptr()), self._stream()))
+        return cov, flags
 
     def coverage(self, edge_ids, cov=None, flags=None):
         P = edge_ids.shape[0]

@@ -120,6 +120,7 @@ def pack_world(img, xy, row_ptr, col, edge_poly, edge_theta, edge_dist, map_para
     zero_g = g_u8 == 0
     gray = np.logical_and(g_u8 > 0, g_u8 < 255)
     pw.blk_mask0 = _blockify(np.logical_and(mask, zero_g), nby, nbx)
+    blk_mask_all = _blockify(mask, nby, nbx)            # host only: pre-masked footprint store
     pw.blk_free0 = _blockify(zero_g, nby, nbx)
     gy, gx = np.nonzero(gray)
     gb = (gy // BLK) * nbx + (gx // BLK)
@@ -155,6 +156,10 @@ def pack_world(img, xy, row_ptr, col, edge_poly, edge_theta, edge_dist, map_para
     sub_ptr = np.zeros(E + N + 1, dtype=np.int64)
     sub_block, sub_payload, chunks = [], [], []
     off128 = 0
+    # second store: footprint AND buffer_mask (wall-coverage fast path; union and AND commute)
+    m_sub_ptr = np.zeros(E + N + 1, dtype=np.int64)
+    m_sub_block, m_sub_payload, m_chunks = [], [], []
+    m_off128 = 0
     n_pix = np.zeros(E + N, dtype=np.int32)
     it = range(E + N)
     if progress:
@@ -179,6 +184,7 @@ def pack_world(img, xy, row_ptr, col, edge_poly, edge_theta, edge_dist, map_para
             canvas[max(y_hi, 0):, :] = 0
         rows = _rows_to_u64(canvas.reshape(kb * BLK, kb, BLK))     # [kb*64, kb]
         n_sub = 0
+        m_n_sub = 0
         for j in range(kb):
             for i in range(kb):
                 blk = rows[j * BLK:(j + 1) * BLK, i]
@@ -191,8 +197,18 @@ def pack_world(img, xy, row_ptr, col, edge_poly, edge_theta, edge_dist, map_para
                 chunks.append(blk.reshape(4, 16)[q_any].reshape(-1).copy())
                 off128 += int(q_any.sum())
                 n_sub += 1
+                mblk = blk & blk_mask_all[(by0 + j) * nbx + (bx0 + i)]
+                if mblk.any():
+                    mq = mblk.reshape(4, 16).any(axis=1)
+                    mqm = int(mq[0]) | int(mq[1]) << 1 | int(mq[2]) << 2 | int(mq[3]) << 3
+                    m_sub_block.append((by0 + j) * nbx + (bx0 + i))
+                    m_sub_payload.append((m_off128 << 4) | mqm)
+                    m_chunks.append(mblk.reshape(4, 16)[mq].reshape(-1).copy())
+                    m_off128 += int(mq.sum())
+                    m_n_sub += 1
         n_pix[e] = int(canvas.sum())
         sub_ptr[e + 1] = sub_ptr[e] + n_sub
+        m_sub_ptr[e + 1] = m_sub_ptr[e] + m_n_sub
     if off128 >= (1 << 28):
         raise ValueError("footprint store exceeds 2^28 quarters (32 GiB)")
     pw.sub_ptr = sub_ptr.astype(np.uint32)
@@ -202,6 +218,13 @@ def pack_world(img, xy, row_ptr, col, edge_poly, edge_theta, edge_dist, map_para
     pw.n_quarters = off128
     pw.edge_pixels = n_pix
     pw.max_sub_per_edge = int(np.diff(sub_ptr).max()) if E + N else 0
+    if m_off128 >= (1 << 27):
+        raise ValueError("masked footprint store exceeds 2^27 quarters")
+    pw.m_sub_ptr = m_sub_ptr.astype(np.uint32)
+    pw.m_sub_block = np.array(m_sub_block, dtype=np.uint32)
+    pw.m_sub_payload = np.array(m_sub_payload, dtype=np.uint32)
+    pw.m_tile_data = (np.concatenate(m_chunks) if m_chunks else np.zeros(0, dtype='<u8')).astype('<u8')
+    pw.m_n_quarters = m_off128
     return pw
 
 

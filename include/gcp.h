@@ -91,6 +91,14 @@ int gcp_upload_edges(gcp_ctx* ctx,
                      uint64_t n_sub,
                      const uint64_t* tile_data /*[n_quarters][16] rows of 64 px*/,
                      uint64_t n_quarters);
+/* Optional second footprint store: every sub-tile ANDed with buffer_mask (mappy.py:337).
+ * Union and AND commute, so popcount(union of masked tiles) == the reference's
+ * wall-coverage pixel count (mappy.py:361).  Enables the objectives-only fast kernel
+ * (binary map, coverage_blend == 1).  Same layout as the arguments of gcp_upload_edges;
+ * offsets must be < 2^27. */
+int gcp_upload_masked_footprints(gcp_ctx* ctx, const uint32_t* sub_ptr /*[E+N+1]*/,
+                                 const uint32_t* sub_block, const uint32_t* sub_payload,
+                                 uint64_t n_sub, const uint64_t* tile_data, uint64_t n_quarters);
 int gcp_upload_map(gcp_ctx* ctx, const gcp_map_consts* consts,
                    const uint64_t* blk_mask0 /*[nb][64]*/, const uint64_t* blk_free0 /*[nb][64]*/,
                    const uint32_t* gray_ptr /*[nb+1]*/, const uint32_t* gray_ent /*[G]*/,
@@ -105,11 +113,17 @@ size_t gcp_eval_scratch_bytes(gcp_ctx* ctx, uint32_t n_org);
 int    gcp_eval(gcp_ctx* ctx, const int32_t* dna_dev, uint32_t n_org,
                 const gcp_eval_out* out, void* scratch_dev, size_t scratch_bytes,
                 void* stream);
-/* Individual stages (same buffers; used by tests / profiling). edge_ids: dev u32 [P][A][L]. */
+/* Individual stages (same buffers; used by tests / profiling). edge_ids: dev u32 [P][A][L];
+ * step_info (optional, needs the masked store): dev u32 [P][A][L], per step the masked
+ * sub-tile range of its edge (first | count<<28), 0 where no step is executed. */
 int gcp_path_costs(gcp_ctx* ctx, const int32_t* dna_dev, uint32_t n_org, uint32_t* edge_ids_dev,
-                   double* dist_dev, double* turn_dev, uint8_t* flags_dev, void* stream);
+                   uint32_t* step_info_dev, double* dist_dev, double* turn_dev,
+                   uint8_t* flags_dev, void* stream);
 int gcp_coverage(gcp_ctx* ctx, const uint32_t* edge_ids_dev, uint32_t n_org,
                  uint32_t* cov_dev, uint8_t* flags_dev, void* stream);
+/* objectives-only wall coverage from the masked store: cov[P][8] = {n,0,0,0,n,0,0,0}. */
+int gcp_coverage_masked(gcp_ctx* ctx, const uint32_t* step_info_dev, uint32_t n_org,
+                        uint32_t* cov_dev, uint8_t* flags_dev, void* stream);
 int gcp_loop_closures(gcp_ctx* ctx, const int32_t* dna_dev, uint32_t n_org,
                       const double* dist_dev, const double* turn_dev, const uint32_t* cov_dev,
                       int32_t* lc_mat_dev, double* obj_dev, double* neg_cov_dev,

@@ -13,8 +13,10 @@ $CMD > $OUT/plain_${TAG}.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 200 --csv \
     --log-file $OUT/launches_${TAG}.csv $CMD > $OUT/ncu_launches_${TAG}.log 2>&1
 echo "launch list rc=$?"
+for K in ${KERNELS:-k_coverage_masked}; do
 $CMD > $OUT/plain2_${TAG}.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_coverage -s 3 -c 1 \
-    -o $OUT/prof_cov_${TAG} -f $CMD > $OUT/ncu_full_${TAG}.log 2>&1
-echo "full capture rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:$K -s 3 -c 1 \
+    -o $OUT/prof_${K}_${TAG} -f $CMD > $OUT/ncu_full_${K}_${TAG}.log 2>&1
+echo "full capture $K rc=$?"
+done
 ls -la $OUT

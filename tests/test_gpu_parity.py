@@ -181,3 +181,90 @@ def test_maximin_vs_oracle_large_with_ties(eng_big):
         # row-sharded evaluation (multi-GPU layout) gives the same rows
         part = eng_big.maximin(torch.from_numpy(objs), constr, row_range=(1234, 3456))
         assert np.array_equal(part.cpu().numpy()[1234:3456], want[1234:3456])
+
+
+# ---------------------------------------------------------------------------------------
+# binary synthetic world: -coverage must be BIT-exact, and the objectives-only fast path
+# (pre-masked footprint store) must agree with the general kernel and the oracle.
+# ---------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def synth_setup():
+    from genetic_coverage_planning_b200 import packing, synth, worlds
+    from genetic_coverage_planning_b200.engine import FitnessEngine
+    sw = synth.make_world(1024, seed=5)
+    pw = packing.pack_world(sw.img, sw.xy, sw.row_ptr, sw.col, sw.edge_poly, sw.edge_theta,
+                            sw.edge_dist, sw.map_params)
+    starts = synth.spread_starts(sw.xy, 6, 1024)
+    op = worlds.org_params_for(dict(L=200), starts)
+    ow = World(sw.img, sw.xy, sw.row_ptr, sw.col, sw.edge_poly, sw.edge_theta, sw.edge_dist,
+               sw.map_params, op, name="synth1024")
+    eng = FitnessEngine(pw, op, num_agents=6)
+    return sw, pw, ow, op, eng, starts
+
+
+def test_binary_world_bit_exact_and_fast_path(synth_setup):
+    from genetic_coverage_planning_b200 import synth
+    sw, pw, ow, op, eng, starts = synth_setup
+    assert pw.is_binary and eng.has_masked
+    walks = synth.random_walk_population(sw.xy, sw.row_ptr, sw.col, starts, 40, 150, 200, seed=9)
+    dna = np.concatenate([walks, _random_dna(ow, 40, 6, 200, seed=10)]).astype(np.int32)
+    full = eng.evaluate(dna, detail=True)        # general kernel, all counters
+    fast = eng.evaluate(dna, detail=False)       # pre-masked fast kernel
+    assert np.array_equal(full.obj.cpu().numpy(), fast.obj.cpu().numpy())
+    assert np.array_equal(full.flags.cpu().numpy(), fast.flags.cpu().numpy())
+    obj, neg = full.obj.cpu().numpy(), full.neg_cov.cpu().numpy()
+    cov = full.cov.cpu().numpy()
+    for k in range(len(dna)):
+        d = dna[k].astype(int)
+        c, dd, tt, cnt = fo.get_coverage(ow, d, return_counts=True)
+        assert c == neg[k], "binary map: -coverage must be bit-exact"
+        assert cnt['n_cov_all'] == cov[k, 5] and cnt['n_cov_mask'] == cov[k, 4]
+        o = fo.calc_obj(ow, d)
+        assert o[0] == obj[k, 0] and o[1] == obj[k, 1]
+    # stage API: masked kernel count == general kernel mask count
+    edge_ids, step_info, dist, turn, flags = eng.path_costs(dna, with_step_info=True)
+    cov_m, _ = eng.coverage_masked(step_info)
+    cov_g, _ = eng.coverage(edge_ids)
+    assert np.array_equal(cov_m.cpu().numpy()[:, 4], cov_g.cpu().numpy()[:, 4])
+
+
+def test_binary_world_blend(synth_setup):
+    """blend < 1 needs the internal-coverage counter: general kernel, still bit-exact."""
+    sw, pw, ow, op, eng, starts = synth_setup
+    from genetic_coverage_planning_b200 import synth
+    dna = synth.random_walk_population(sw.xy, sw.row_ptr, sw.col, starts, 12, 150, 200, seed=4)
+    try:
+        eng.set_params(op, blend=0.1)
+        ow.map_params['coverage_blend'] = 0.1
+        r = eng.evaluate(dna.astype(np.int32), detail=False)
+        obj = r.obj.cpu().numpy()
+        for k in range(len(dna)):
+            o = fo.calc_obj(ow, dna[k].astype(int))
+            assert o[0] == obj[k, 0] and o[1] == obj[k, 1]
+    finally:
+        eng.set_params(op, blend=1.0)
+        ow.map_params['coverage_blend'] = 1.0
+
+
+def test_long_genomes_partition_fallback(synth_setup):
+    """A*L far beyond the shared-memory pair store: the kernels must fall back to block
+    partitions and stay exact (C4-style long paths)."""
+    from genetic_coverage_planning_b200 import synth, worlds
+    from genetic_coverage_planning_b200.engine import FitnessEngine
+    sw, pw, ow, op, eng, starts = synth_setup
+    A, L = 12, 640
+    st = synth.spread_starts(sw.xy, A, 1024)
+    op2 = worlds.org_params_for(dict(L=L), st)
+    eng2 = FitnessEngine(pw, op2, num_agents=A)
+    dna = synth.random_walk_population(sw.xy, sw.row_ptr, sw.col, st, 6, 600, L, seed=11)
+    full = eng2.evaluate(dna.astype(np.int32), detail=True)
+    fast = eng2.evaluate(dna.astype(np.int32), detail=False)
+    assert np.array_equal(full.obj.cpu().numpy(), fast.obj.cpu().numpy())
+    assert not full.flags.cpu().numpy()[:, 3].any()
+    ow2 = World(sw.img, sw.xy, sw.row_ptr, sw.col, sw.edge_poly, sw.edge_theta, sw.edge_dist,
+                sw.map_params, op2, name="synth-long")
+    for k in range(3):
+        det = fo.calc_obj(ow2, dna[k].astype(int), detail=True)
+        assert det['obj'][0] == full.obj.cpu().numpy()[k, 0]
+        assert det['obj'][1] == full.obj.cpu().numpy()[k, 1]
+        assert np.array_equal(det['lc_mat'].astype(np.int32), full.lc_mat.cpu().numpy()[k])

@@ -1,0 +1,59 @@
+"""CPU: the windowed table builders reproduce the reference's tables; synthetic worlds are
+well formed."""
+import numpy as np
+import pytest
+
+from genetic_coverage_planning_b200 import synth, worlds
+
+
+def test_windowed_frustums_equal_reference_tables(world_big):
+    """All 1,618 edges of the reference's big map: polygons, headings and lengths from
+    the windowed CSR builder are identical to Mappy.computeFrustums' (golden world)."""
+    w = world_big
+    poly, theta, dist = synth.compute_frustums(w.img, w.xy, w.row_ptr, w.col, w.map_params)
+    assert np.array_equal(poly, w.edge_poly)
+    assert np.array_equal(theta, w.edge_theta)
+    assert np.array_equal(dist, w.edge_dist)
+
+
+def test_windowed_frustums_small_map(world_small):
+    w = world_small
+    poly, theta, dist = synth.compute_frustums(w.img, w.xy, w.row_ptr, w.col, w.map_params)
+    assert np.array_equal(poly, w.edge_poly)
+    assert np.array_equal(theta, w.edge_theta) and np.array_equal(dist, w.edge_dist)
+
+
+@pytest.fixture(scope="module")
+def synth_world():
+    return synth.make_world(768, seed=3)
+
+
+def test_synth_world_is_binary_and_connected(synth_world):
+    import scipy.sparse as sp
+    import scipy.sparse.csgraph as cg
+    w = synth_world
+    assert set(np.unique(w.img)) <= {0.0, 1.0}
+    assert w.N > 300 and w.E > w.N
+    g = sp.csr_matrix((np.ones(w.E), w.col, w.row_ptr), shape=(w.N, w.N))
+    nc, lab = cg.connected_components(g, directed=False)
+    assert np.bincount(lab).max() > 0.75 * w.N
+    assert (w.img[w.xy[:, 0], w.xy[:, 1]] == 0).all()          # waypoints on free pixels
+    # every edge within max_traverse_dist
+    src = np.repeat(np.arange(w.N), np.diff(w.row_ptr))
+    d = np.linalg.norm(w.xy[src] - w.xy[w.col], axis=1) * w.map_params['scale']
+    assert (d < w.path_params['max_traverse_dist']).all()
+
+
+def test_random_walks_follow_edges(synth_world):
+    w = synth_world
+    starts = synth.spread_starts(w.xy, 4, 768)
+    dna = synth.random_walk_population(w.xy, w.row_ptr, w.col, starts, 16, 60, 80, seed=2)
+    assert dna.shape == (16, 4, 80)
+    assert (dna[:, :, 0] == np.array(starts)[None, :]).all()
+    assert (dna[:, :, 61:] == -1).all() and (dna[:, :, :61] >= 0).all()
+    edges = set(zip(np.repeat(np.arange(w.N), np.diff(w.row_ptr)).tolist(), w.col.tolist()))
+    for row in dna.reshape(-1, 80):
+        v = row[row >= 0]
+        for a, b in zip(v[:-1], v[1:]):
+            assert (int(a), int(b)) in edges or a == b
+    assert np.array_equal(worlds.executed_steps(dna), np.full(16, 4 * 61))
