@@ -403,7 +403,7 @@ int launch_coverage(gcp_ctx* ctx, const uint32_t* edge_ids, uint32_t P, uint32_t
     // pair store sized for 3 sub-tiles per step (average is ~2), table for a third of that
     int maxp = ctx->cov_maxpairs > 0 ? ctx->cov_maxpairs : 3 * AL;
     if (maxp < 256) maxp = 256;
-    if (maxp > 32768) maxp = 32768;
+    if (maxp > 4096) maxp = 4096;          // longer genomes run in R0 block partitions
     int T = ctx->cov_table;
     if (T <= 0) { T = K2_THREADS; while (T < maxp / 3) T <<= 1; }
     if (T > 32768) T = 32768;
@@ -450,7 +450,7 @@ __device__ __forceinline__ uint4 ld_quarter1(const uint4* __restrict__ tile, uin
     return v;
 }
 
-__global__ void __launch_bounds__(K2M_THREADS, 6)
+__global__ void __launch_bounds__(K2M_THREADS, 5)
 k_coverage_masked(const uint32_t* __restrict__ step_info, uint32_t P,
                   const uint2* __restrict__ sub_desc, const uint4* __restrict__ tile, int AL,
                   int T /*pow2, multiple of THREADS*/, int MAXP /*<= PPT*THREADS*/, uint32_t R0,
@@ -621,28 +621,43 @@ k_coverage_masked(const uint32_t* __restrict__ step_info, uint32_t P,
                 }
                 bounds[e] = b;
             }
+            // acc = (acc & keep) | v : keep = 0 right after a bucket was closed (one LOP3 per
+            // word, no clearing); a bucket is closed by a warp-uniform branch on its last entry.
             uint4 acc = make_uint4(0, 0, 0, 0);
+            uint32_t keep = 0;
+            const uint4* tile_l = tile + l7;
+            uint32_t qq = q1, bl = below1;
+            // opaque copies: stop ptxas from re-deriving the lane constants inside the loop
+            asm volatile("" : "+l"(tile_l), "+r"(qq), "+r"(bl));
             for (uint32_t c0 = bounds[0]; c0 < bounds[1]; c0 += 32) {
                 uint32_t my = 0;
                 if (c0 + lane < bounds[1]) my = s_pay[c0 + lane];
+                const uint32_t lastm = __ballot_sync(FULL, my & 1u);     // warp-uniform
                 const uint32_t nn = min(32u, bounds[1] - c0);
                 for (uint32_t k = 0; k < nn; k += 4) {
-                    const uint32_t p0 = __shfl_sync(FULL, my, k);
-                    const uint32_t p1 = __shfl_sync(FULL, my, k + 1);
-                    const uint32_t p2 = __shfl_sync(FULL, my, k + 2);
-                    const uint32_t p3 = __shfl_sync(FULL, my, k + 3);
-                    const uint4 v0 = ld_quarter1(tile, p0, q1, below1, l7);
-                    const uint4 v1 = ld_quarter1(tile, p1, q1, below1, l7);
-                    const uint4 v2 = ld_quarter1(tile, p2, q1, below1, l7);
-                    const uint4 v3 = ld_quarter1(tile, p3, q1, below1, l7);
-                    or128(acc, v0);
-                    if (p0 & 1u) { n_cov += popc128(acc); acc = make_uint4(0, 0, 0, 0); }
-                    or128(acc, v1);
-                    if (p1 & 1u) { n_cov += popc128(acc); acc = make_uint4(0, 0, 0, 0); }
-                    or128(acc, v2);
-                    if (p2 & 1u) { n_cov += popc128(acc); acc = make_uint4(0, 0, 0, 0); }
-                    or128(acc, v3);
-                    if (p3 & 1u) { n_cov += popc128(acc); acc = make_uint4(0, 0, 0, 0); }
+                    uint32_t p[4];
+                    uint4 v[4];
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) p[j] = __shfl_sync(FULL, my, k + j);
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        v[j] = make_uint4(0, 0, 0, 0);
+                        if ((p[j] >> qq) & 1u)
+                            v[j] = __ldg(tile_l + ((((p[j] >> 5) + __popc(p[j] & bl))) << 3));
+                    }
+                    const uint32_t lm = (lastm >> k) & 15u;
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc.x = (acc.x & keep) | v[j].x;
+                        acc.y = (acc.y & keep) | v[j].y;
+                        acc.z = (acc.z & keep) | v[j].z;
+                        acc.w = (acc.w & keep) | v[j].w;
+                        keep = 0xFFFFFFFFu;
+                        if (lm & (1u << j)) {          // uniform: close the bucket
+                            n_cov += popc128(acc);
+                            keep = 0;
+                        }
+                    }
                 }
             }
             __syncthreads();
@@ -700,11 +715,14 @@ int launch_coverage_masked(gcp_ctx* ctx, const uint32_t* step_info, uint32_t P, 
 //   groups of equal keys, size > 1, none of whose positions is a path split (F10)
 //   one owner  -> lc[a][a] += 1 iff some consecutive (ascending) gap > thresh  :413
 //   >= 2 owners -> lc[x][y] += 1 for every owner pair x < y                    :417-424
-//   The (key, position) pairs are sorted as packed u64 (from:24 | to:24 | pos:16) with a
-//   shared-memory bitonic network, so groups are contiguous and positions ascend
-//   (= the stable-argsort canonical order).
+//   Most keys are unique, so instead of sorting everything the keys go through a
+//   shared-memory hash table (64-bit CAS); only members of groups with count >= 2 are
+//   linked per slot, and every member finds its successor (next larger position in the
+//   group) by walking its group's list - the "consecutive ascending gap" test of the
+//   stable-argsort canonical order without a sort.
 // ============================================================================
 constexpr int K3_THREADS = 256;
+constexpr uint32_t K3_NIL = 0xFFFFFFFFu;
 
 __device__ double np_sum_order(const double* a, int n)
 {
@@ -726,7 +744,7 @@ __device__ double np_sum_order(const double* a, int n)
 }
 
 __global__ void __launch_bounds__(K3_THREADS)
-k_loop_closures(const int32_t* __restrict__ dna, uint32_t P, int A, int L, int SNMAX,
+k_loop_closures(const int32_t* __restrict__ dna, uint32_t P, int A, int L, int T3 /*pow2*/,
                 gcp_params prm, gcp_map_consts mc,
                 const double* __restrict__ dist, const double* __restrict__ turn,
                 const uint32_t* __restrict__ cov,
@@ -734,9 +752,13 @@ k_loop_closures(const int32_t* __restrict__ dna, uint32_t P, int A, int L, int S
                 double* __restrict__ neg_cov_out, uint8_t* __restrict__ flags)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem);   // [SNMAX]
-    int32_t* s_seq = reinterpret_cast<int32_t*>(s_key + SNMAX);                 // [A*L]
-    uint8_t* s_own = reinterpret_cast<uint8_t*>(s_seq + A * L);                 // [A*L] owner | split<<7
+    // per slot: key (u64; after the count pass reused as {head, owners}), count|flags
+    unsigned long long* s_hkey = reinterpret_cast<unsigned long long*>(smem);     // [T3]
+    uint32_t* s_hcnt = reinterpret_cast<uint32_t*>(s_hkey + T3);                   // [T3]
+    int32_t*  s_seq  = reinterpret_cast<int32_t*>(s_hcnt + T3);                    // [A*L]
+    uint16_t* s_slot = reinterpret_cast<uint16_t*>(s_seq + A * L);                 // [A*L]
+    uint16_t* s_next = s_slot + A * L;                                             // [A*L]
+    uint8_t*  s_own  = reinterpret_cast<uint8_t*>(s_next + A * L);                 // [A*L]
     __shared__ int s_len[GCP_MAX_AGENTS], s_base[GCP_MAX_AGENTS + 1];
     __shared__ int s_lc[GCP_MAX_AGENTS * GCP_MAX_AGENTS];
 
@@ -747,6 +769,7 @@ k_loop_closures(const int32_t* __restrict__ dna, uint32_t P, int A, int L, int S
     const int32_t* d = dna + (size_t)org * A * L;
 
     for (int i = tid; i < A * A; i += K3_THREADS) s_lc[i] = 0;
+    for (int i = tid; i < T3; i += K3_THREADS) { s_hkey[i] = 0ull; s_hcnt[i] = 0u; }
     // ---- valid-gene counts per row ----
     for (int a = warp; a < A; a += NW) {
         int cnt = 0;
@@ -782,52 +805,60 @@ k_loop_closures(const int32_t* __restrict__ dna, uint32_t P, int A, int L, int S
         }
     }
     __syncthreads();
-    int SN = 2;
-    while (SN < n) SN <<= 1;
-    if (SN > SNMAX) SN = SNMAX;          // cannot happen: SNMAX >= A*L
-    for (int i = tid; i < SN; i += K3_THREADS) {
-        unsigned long long k = ~0ull;
-        if (i < n) {
-            const unsigned long long f = (uint32_t)s_seq[i] & 0xFFFFFFu;
-            const unsigned long long g = (uint32_t)s_seq[(i + 1 == n) ? 0 : i + 1] & 0xFFFFFFu;
-            k = (f << 40) | (g << 16) | (unsigned long long)i;
+    // ---- pass 1: hash every key, count group sizes ----
+    const int logT = 31 - __clz(T3);
+    for (int i = tid; i < n; i += K3_THREADS) {
+        const unsigned long long f = (uint32_t)s_seq[i] & 0xFFFFFFu;
+        const unsigned long long g = (uint32_t)s_seq[(i + 1 == n) ? 0 : i + 1] & 0xFFFFFFu;
+        const unsigned long long key = ((f << 24) | g) + 1ull;              // never 0
+        uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> (64 - logT));
+        for (;;) {
+            const unsigned long long cur = ((volatile unsigned long long*)s_hkey)[h];
+            if (cur == key) break;
+            if (cur == 0ull) {
+                const unsigned long long old = atomicCAS(&s_hkey[h], 0ull, key);
+                if (old == 0ull || old == key) break;
+            }
+            h = (h + 1) & (T3 - 1);                      // T3 > n: always terminates
         }
-        s_key[i] = k;
+        atomicAdd(&s_hcnt[h], 1u);
+        s_slot[i] = (uint16_t)h;
     }
     __syncthreads();
-    // ---- bitonic sort, ascending ----
-    for (int k = 2; k <= SN; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int tt = tid; tt < (SN >> 1); tt += K3_THREADS) {
-                const int i = ((tt & ~(j - 1)) << 1) | (tt & (j - 1));
-                const int l = i | j;
-                const unsigned long long x = s_key[i], y = s_key[l];
-                const bool asc = (i & k) == 0;
-                if ((x > y) == asc) { s_key[i] = y; s_key[l] = x; }
-            }
-            __syncthreads();
-        }
+    // ---- pass 2: slots with a duplicate group become {head = NIL, owners = 0} ----
+    for (int h = tid; h < T3; h += K3_THREADS)
+        if (s_hcnt[h] >= 2u) s_hkey[h] = (unsigned long long)K3_NIL;      // lo = head, hi = owners
+    __syncthreads();
+    uint32_t* s_w = reinterpret_cast<uint32_t*>(s_hkey);                  // [2*h] head, [2*h+1] owners
+    for (int i = tid; i < n; i += K3_THREADS) {
+        const uint32_t h = s_slot[i];
+        if ((s_hcnt[h] & 0xFFFFu) < 2u) continue;
+        const uint8_t o = s_own[i];
+        s_next[i] = (uint16_t)atomicExch(&s_w[2 * h], (uint32_t)i);       // NIL -> 0xFFFF
+        atomicOr(&s_w[2 * h + 1], 1u << (o & 31));
+        if (o & 0x80) atomicOr(&s_hcnt[h], 1u << 16);                     // group touches a split (F10)
     }
-    // ---- group analysis: the first element of each group walks it ----
+    __syncthreads();
+    // ---- pass 3: successor gap test (ascending consecutive positions) ----
     const int thresh = prm.solo_sep_thresh;
     for (int i = tid; i < n; i += K3_THREADS) {
-        const unsigned long long ki = s_key[i] >> 16;
-        if (i > 0 && (s_key[i - 1] >> 16) == ki) continue;
-        if (i + 1 >= n || (s_key[i + 1] >> 16) != ki) continue;          // size 1
-        uint32_t owners = 0;
-        bool split = false, gap = false;
-        int prev = -1;
-        for (int j = i; j < n && (s_key[j] >> 16) == ki; ++j) {
-            const int pos = (int)(s_key[j] & 0xFFFFu);
-            const uint8_t o = s_own[pos];
-            owners |= 1u << (o & 31);
-            split |= (o & 0x80) != 0;
-            if (prev >= 0 && pos - prev > thresh) gap = true;
-            prev = pos;
-        }
-        if (split) continue;                                             // F10
+        const uint32_t h = s_slot[i];
+        const uint32_t c = s_hcnt[h];
+        if ((c & 0xFFFFu) < 2u || (c & (1u << 16))) continue;
+        uint32_t succ = 0xFFFFFFFFu;
+        for (uint32_t j = s_w[2 * h]; j != 0xFFFFu && j != K3_NIL; j = s_next[j])
+            if (j > (uint32_t)i && j < succ) succ = j;
+        if (succ != 0xFFFFFFFFu && (int)(succ - (uint32_t)i) > thresh)
+            atomicOr(&s_hcnt[h], 1u << 17);
+    }
+    __syncthreads();
+    // ---- pass 4: one thread per duplicate group updates lc_mat ----
+    for (int h = tid; h < T3; h += K3_THREADS) {
+        const uint32_t c = s_hcnt[h];
+        if ((c & 0xFFFFu) < 2u || (c & (1u << 16))) continue;
+        const uint32_t owners = s_w[2 * h + 1];
         if (__popc(owners) == 1) {
-            if (gap) { const int a = __ffs(owners) - 1; atomicAdd(&s_lc[a * A + a], 1); }
+            if (c & (1u << 17)) { const int a = __ffs(owners) - 1; atomicAdd(&s_lc[a * A + a], 1); }
         } else {
             for (uint32_t mx = owners; mx; mx &= mx - 1) {
                 const int x = __ffs(mx) - 1;
@@ -903,15 +934,16 @@ int launch_loop_closures(gcp_ctx* ctx, const int32_t* dna, uint32_t P, const dou
 {
     if (P == 0) return 0;
     const int A = ctx->p.num_agents, L = ctx->p.max_dna_len;
-    int SNMAX = 2;
-    while (SNMAX < A * L) SNMAX <<= 1;
-    const size_t smem = (size_t)SNMAX * 8 + (size_t)A * L * 4 + (size_t)((A * L + 15) / 16) * 16;
+    int T3 = 256;
+    while (T3 * 5 < 7 * A * L) T3 <<= 1;      // > 1.4 * A*L slots: never full; ids fit 16 bits
+    if (T3 > 65536) return gcp_fail(ctx, -3, "loop-closure kernel: A*L too large");
+    const size_t smem = (size_t)T3 * 12 + (size_t)A * L * 9 + 16;
     if (smem > (size_t)ctx->max_smem_optin)
         return gcp_fail(ctx, -3, "loop-closure kernel needs %zu B shared memory (A*L too large)", smem);
     GCP_CUDA(ctx, cudaFuncSetAttribute(k_loop_closures,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     StageTimer tm(ctx, 2, st);
-    k_loop_closures<<<P, K3_THREADS, smem, st>>>(dna, P, A, L, SNMAX, ctx->p, ctx->mc, dist, turn,
+    k_loop_closures<<<P, K3_THREADS, smem, st>>>(dna, P, A, L, T3, ctx->p, ctx->mc, dist, turn,
                                                  cov, lc, obj, neg_cov, flags);
     ctx->launches++;
     GCP_CUDA(ctx, cudaGetLastError());
