@@ -744,7 +744,7 @@ __device__ double np_sum_order(const double* a, int n)
 }
 
 __global__ void __launch_bounds__(K3_THREADS)
-k_loop_closures(const int32_t* __restrict__ dna, uint32_t P, int A, int L, int T3 /*pow2*/,
+k_loop_closures(const int32_t* __restrict__ dna, uint32_t P, int A, int L, int T3 /*slots > A*L*/,
                 gcp_params prm, gcp_map_consts mc,
                 const double* __restrict__ dist, const double* __restrict__ turn,
                 const uint32_t* __restrict__ cov,
@@ -806,12 +806,12 @@ k_loop_closures(const int32_t* __restrict__ dna, uint32_t P, int A, int L, int T
     }
     __syncthreads();
     // ---- pass 1: hash every key, count group sizes ----
-    const int logT = 31 - __clz(T3);
     for (int i = tid; i < n; i += K3_THREADS) {
         const unsigned long long f = (uint32_t)s_seq[i] & 0xFFFFFFu;
         const unsigned long long g = (uint32_t)s_seq[(i + 1 == n) ? 0 : i + 1] & 0xFFFFFFu;
         const unsigned long long key = ((f << 24) | g) + 1ull;              // never 0
-        uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> (64 - logT));
+        // fast range reduction of the top 32 hash bits onto [0, T3)
+        uint32_t h = __umulhi((uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32), (uint32_t)T3);
         for (;;) {
             const unsigned long long cur = ((volatile unsigned long long*)s_hkey)[h];
             if (cur == key) break;
@@ -819,7 +819,7 @@ k_loop_closures(const int32_t* __restrict__ dna, uint32_t P, int A, int L, int T
                 const unsigned long long old = atomicCAS(&s_hkey[h], 0ull, key);
                 if (old == 0ull || old == key) break;
             }
-            h = (h + 1) & (T3 - 1);                      // T3 > n: always terminates
+            h = (h + 1 == (uint32_t)T3) ? 0u : h + 1;    // T3 > n: always terminates
         }
         atomicAdd(&s_hcnt[h], 1u);
         s_slot[i] = (uint16_t)h;
@@ -934,9 +934,8 @@ int launch_loop_closures(gcp_ctx* ctx, const int32_t* dna, uint32_t P, const dou
 {
     if (P == 0) return 0;
     const int A = ctx->p.num_agents, L = ctx->p.max_dna_len;
-    int T3 = 256;
-    while (T3 * 5 < 7 * A * L) T3 <<= 1;      // > 1.4 * A*L slots: never full; ids fit 16 bits
-    if (T3 > 65536) return gcp_fail(ctx, -3, "loop-closure kernel: A*L too large");
+    int T3 = (A * L * 3) / 2 + 64;            // load factor <= 2/3, never full; ids fit 16 bits
+    if (T3 > 65535) return gcp_fail(ctx, -3, "loop-closure kernel: A*L too large");
     const size_t smem = (size_t)T3 * 12 + (size_t)A * L * 9 + 16;
     if (smem > (size_t)ctx->max_smem_optin)
         return gcp_fail(ctx, -3, "loop-closure kernel needs %zu B shared memory (A*L too large)", smem);

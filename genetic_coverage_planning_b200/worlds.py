@@ -52,8 +52,9 @@ def build_synth_world(size, seed=0, use_cache=True, verbose=False):
     pw = packing.pack_world(w.img, w.xy, w.row_ptr, w.col, w.edge_poly, w.edge_theta,
                             w.edge_dist, w.map_params)
     if verbose:
+        import sys
         print("[worlds] size %d: N=%d E=%d world %.1fs pack %.1fs" %
-              (size, w.N, w.E, t1 - t0, time.time() - t1), flush=True)
+              (size, w.N, w.E, t1 - t0, time.time() - t1), file=sys.stderr, flush=True)
     if use_cache:
         tmp = path + ".%d.tmp" % os.getpid()
         with open(tmp, "wb") as f:
