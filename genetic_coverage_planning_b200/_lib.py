@@ -19,6 +19,15 @@ class GcpParams(C.Structure):
                 ("one_minus_blend", C.c_double)]
 
 
+class GcpVaryParams(C.Structure):
+    _fields_ = [("min_dna_len", C.c_int32), ("crossover_time_thresh", C.c_int32),
+                ("num_muterpolations", C.c_int32), ("muterpolation_srch_dist", C.c_int32),
+                ("path_memory", C.c_int32), ("reserved0", C.c_int32),
+                ("crossover_prob", C.c_double), ("mutation_prob", C.c_double),
+                ("muterpolate_prob", C.c_double), ("muterpolation_sub_prob", C.c_double),
+                ("log_scale_weight", C.c_double)]
+
+
 class GcpMapConsts(C.Structure):
     _fields_ = [("height", C.c_int32), ("width", C.c_int32), ("nbx", C.c_int32),
                 ("nby", C.c_int32), ("mask_size", C.c_int64), ("gsum_mask", C.c_int64),
@@ -54,6 +63,14 @@ SIGNATURES = {
     "gcp_maximin": (C.c_int, [_vp, _vp, _u32, C.c_double, _u32, _u32, _vp, _vp, _vp,
                               C.c_size_t, _vp]),
     "gcp_arena_order": (C.c_int, [_vp, _vp, _u32, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "gcp_set_vary_params": (C.c_int, [_vp, C.POINTER(GcpVaryParams)]),
+    "gcp_low_var_select": (C.c_int, [_vp, _vp, _u32, C.c_double, C.c_double, _vp, _vp, _vp]),
+    "gcp_crossover": (C.c_int, [_vp, _vp, _vp, _u32, _u64, _u32, _vp, _vp]),
+    "gcp_mutate": (C.c_int, [_vp, _vp, _u32, _u64, _u32, _u32, _vp]),
+    "gcp_select_vary": (C.c_int, [_vp, _vp, _vp, _u32, C.c_double, _u64, _u32, _vp, _vp,
+                                  C.c_size_t, _vp]),
+    "gcp_random_walks": (C.c_int, [_vp, _vp, _u32, _vp, C.c_int32, _u64, _u32, _vp]),
+    "gcp_gather_survivors": (C.c_int, [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gcp_launch_count": (C.c_uint64, [_vp]),
     "gcp_set_timing": (C.c_int, [_vp, C.c_int]),
     "gcp_stage_ms": (C.c_float, [_vp, C.c_int]),

@@ -355,6 +355,81 @@ int gcp_arena_order(gcp_ctx* c, const double* fit, uint32_t n, int32_t* order, u
     return launch_arena_order(c, fit, n, order, nondom, scratch, sb, (cudaStream_t)stream);
 }
 
+int gcp_set_vary_params(gcp_ctx* c, const gcp_vary_params* p)
+{
+    if (!c || !p) return -1;
+    if (p->num_muterpolations < 0 || p->num_muterpolations > 64)
+        return gcp_fail(c, -1, "num_muterpolations must be in [0,64]");
+    if (p->path_memory < 0 || p->path_memory > 16) return gcp_fail(c, -1, "path_memory must be in [0,16]");
+    if (!(p->log_scale_weight > 0)) return gcp_fail(c, -1, "log_scale_weight must be > 0");
+    c->vary = *p;
+    c->have_vary = true;
+    return 0;
+}
+
+static int vary_ready(gcp_ctx* c)
+{
+    int r = ready(c); if (r) return r;
+    if (!c->have_vary) return gcp_fail(c, -1, "gcp_set_vary_params not called");
+    return 0;
+}
+
+int gcp_low_var_select(gcp_ctx* c, const double* fit, uint32_t m, double gamma, double r0,
+                       double* scratch, int32_t* out, void* stream)
+{
+    if (!c) return -1;
+    return launch_low_var_select(c, fit, m, gamma, r0, scratch, out, (cudaStream_t)stream);
+}
+
+int gcp_crossover(gcp_ctx* c, const int32_t* parents, const int32_t* strong, uint32_t P,
+                  uint64_t seed, uint32_t gen, int32_t* children, void* stream)
+{
+    int r = vary_ready(c); if (r) return r;
+    return launch_crossover(c, parents, strong, P, seed, gen, children, (cudaStream_t)stream);
+}
+
+int gcp_mutate(gcp_ctx* c, int32_t* dna, uint32_t P, uint64_t seed, uint32_t gen, uint32_t salt,
+               void* stream)
+{
+    int r = vary_ready(c); if (r) return r;
+    return launch_mutate(c, dna, P, seed, gen, salt, (cudaStream_t)stream);
+}
+
+int gcp_select_vary(gcp_ctx* c, const int32_t* parents, const double* parent_fit, uint32_t P,
+                    double gamma, uint64_t seed, uint32_t gen, int32_t* children, void* scratch,
+                    size_t scratch_bytes, void* stream)
+{
+    int r = vary_ready(c); if (r) return r;
+    if (P == 0) return 0;
+    if (!scratch || scratch_bytes < (size_t)P * 16) return gcp_fail(c, -1, "select_vary: scratch too small");
+    double* cum = reinterpret_cast<double*>(scratch);
+    int32_t* strong = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(scratch) + (size_t)P * 8);
+    // the single U(0, 1/M) draw of lowVarSample (gori_tools.py:217), from the seed/generation
+    uint64_t z = seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(gen + 1));
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 27; z *= 0x94D049BB133111EBull; z ^= z >> 31;
+    const double r0 = ((double)(z >> 11) * (1.0 / 9007199254740992.0)) / (double)P;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((r = launch_low_var_select(c, parent_fit, P, gamma, r0, cum, strong, st))) return r;
+    if ((r = launch_crossover(c, parents, strong, P, seed, gen, children, st))) return r;
+    return launch_mutate(c, children, P, seed, gen, 0, st);
+}
+
+int gcp_random_walks(gcp_ctx* c, int32_t* dna, uint32_t P, const int32_t* start_idx, int32_t path_len,
+                     uint64_t seed, uint32_t batch, void* stream)
+{
+    int r = vary_ready(c); if (r) return r;
+    return launch_random_walks(c, dna, P, start_idx, path_len, seed, batch, (cudaStream_t)stream);
+}
+
+int gcp_gather_survivors(gcp_ctx* c, const int32_t* order, uint32_t P, const int32_t* par_dna,
+                         const int32_t* kid_dna, const double* glad_obj, const double* glad_fit,
+                         int32_t* out_dna, double* out_obj, double* out_fit, void* stream)
+{
+    int r = ready(c); if (r) return r;
+    return launch_gather_survivors(c, order, P, par_dna, kid_dna, glad_obj, glad_fit, out_dna,
+                                   out_obj, out_fit, (cudaStream_t)stream);
+}
+
 uint64_t gcp_launch_count(gcp_ctx* c) { return c ? c->launches : 0; }
 
 int gcp_set_timing(gcp_ctx* c, int enabled)

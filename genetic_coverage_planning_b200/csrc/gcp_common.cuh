@@ -39,6 +39,8 @@ struct gcp_ctx {
     GcpTables t{};
     gcp_map_consts mc{};
     gcp_params p{};
+    gcp_vary_params vary{};
+    bool have_vary = false;
     bool have_graph = false, have_edges = false, have_map = false, have_params = false;
     bool have_masked = false;
     uint64_t n_sub = 0, n_quarters = 0, n_gray = 0;
@@ -94,3 +96,15 @@ int launch_maximin(gcp_ctx*, const double* obj, uint32_t n, double constr, uint3
                    cudaStream_t);
 int launch_arena_order(gcp_ctx*, const double* fit, uint32_t n, int32_t* order,
                        uint8_t* nondom, void* scratch, size_t sb, cudaStream_t);
+
+int launch_low_var_select(gcp_ctx*, const double* fit, uint32_t M, double gamma, double r0,
+                          double* scratch, int32_t* out, cudaStream_t);
+int launch_crossover(gcp_ctx*, const int32_t* parents, const int32_t* strong, uint32_t P,
+                     uint64_t seed, uint32_t gen, int32_t* children, cudaStream_t);
+int launch_mutate(gcp_ctx*, int32_t* dna, uint32_t P, uint64_t seed, uint32_t gen, uint32_t salt,
+                  cudaStream_t);
+int launch_random_walks(gcp_ctx*, int32_t* dna, uint32_t P, const int32_t* start_idx_dev,
+                        int path_len, uint64_t seed, uint32_t batch, cudaStream_t);
+int launch_gather_survivors(gcp_ctx*, const int32_t* order, uint32_t P, const int32_t* par_dna,
+                            const int32_t* kid_dna, const double* glad_obj, const double* glad_fit,
+                            int32_t* out_dna, double* out_obj, double* out_fit, cudaStream_t);

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import GcpEvalOut, GcpMapConsts, GcpParams
+from ._lib import GcpEvalOut, GcpMapConsts, GcpParams, GcpVaryParams
 
 
 class GcpError(RuntimeError):
@@ -267,6 +267,82 @@ class FitnessEngine(object):
             self.ctx, C.c_void_p(fit.data_ptr()), n, C.c_void_p(order.data_ptr()),
             C.c_void_p(nondom.data_ptr()), C.c_void_p(s.data_ptr()), s.numel(), self._stream()))
         return order, nondom
+
+    # ---- selection + variation ------------------------------------------------
+    def set_vary_params(self, org_params, path_params=None):
+        """org_params / path_params dicts of pather_driver.py:173-191."""
+        pp = path_params or {}
+        v = GcpVaryParams(int(org_params['min_dna_len']), int(org_params['crossover_time_thresh']),
+                          int(org_params['num_muterpolations']),
+                          int(org_params['muterpolation_srch_dist']),
+                          int(pp.get('path_memory', 10)), 0,
+                          float(org_params['crossover_prob']), float(org_params['mutation_prob']),
+                          float(org_params['muterpolate_prob']),
+                          float(org_params['muterpolation_sub_prob']),
+                          float(pp.get('log_scale_weight', 0.7)))
+        self._check(self.lib.gcp_set_vary_params(self.ctx, C.byref(v)))
+
+    def low_var_select(self, fit, gamma, r0):
+        """got.lowVarSample -> indices of the resampled parents (device int32 [M])."""
+        fit = fit.to(device=self.device, dtype=torch.float64).contiguous()
+        M = fit.shape[0]
+        scratch = torch.empty(M, dtype=torch.float64, device=self.device)
+        out = torch.empty(M, dtype=torch.int32, device=self.device)
+        self._check(self.lib.gcp_low_var_select(
+            self.ctx, C.c_void_p(fit.data_ptr()), M, float(gamma), float(r0),
+            C.c_void_p(scratch.data_ptr()), C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def crossover(self, parents, strong, seed, gen):
+        parents = self.to_device_dna(parents)
+        strong = strong.to(device=self.device, dtype=torch.int32).contiguous()
+        P = strong.shape[0]
+        kids = torch.empty((P, self.A, self.L), dtype=torch.int32, device=self.device)
+        self._check(self.lib.gcp_crossover(
+            self.ctx, C.c_void_p(parents.data_ptr()), C.c_void_p(strong.data_ptr()), P,
+            int(seed), int(gen), C.c_void_p(kids.data_ptr()), self._stream()))
+        return kids
+
+    def mutate(self, dna, seed, gen, salt=0):
+        """In place on a device int32 [P,A,L] tensor: the Organism constructor's variation."""
+        assert dna.is_cuda and dna.dtype == torch.int32 and dna.is_contiguous()
+        self._check(self.lib.gcp_mutate(self.ctx, C.c_void_p(dna.data_ptr()), dna.shape[0],
+                                        int(seed), int(gen), int(salt), self._stream()))
+        return dna
+
+    def select_vary(self, parents, parent_fit, gamma, seed, gen):
+        """One generation's children: lowVarSample + crossover + constructor variation."""
+        parents = self.to_device_dna(parents)
+        parent_fit = parent_fit.to(device=self.device, dtype=torch.float64).contiguous()
+        P = parents.shape[0]
+        kids = torch.empty_like(parents)
+        scratch = torch.empty(P * 16, dtype=torch.uint8, device=self.device)
+        self._check(self.lib.gcp_select_vary(
+            self.ctx, C.c_void_p(parents.data_ptr()), C.c_void_p(parent_fit.data_ptr()), P,
+            float(gamma), int(seed), int(gen), C.c_void_p(kids.data_ptr()),
+            C.c_void_p(scratch.data_ptr()), scratch.numel(), self._stream()))
+        return kids
+
+    def random_walks(self, n_org, start_idx, path_len, seed, batch=0):
+        start = torch.as_tensor(np.asarray(start_idx, dtype=np.int32), device=self.device)
+        assert start.numel() == self.A
+        dna = torch.empty((n_org, self.A, self.L), dtype=torch.int32, device=self.device)
+        self._check(self.lib.gcp_random_walks(
+            self.ctx, C.c_void_p(dna.data_ptr()), n_org, C.c_void_p(start.data_ptr()),
+            int(path_len), int(seed), int(batch), self._stream()))
+        return dna
+
+    def gather_survivors(self, order, par_dna, kid_dna, glad_obj, glad_fit):
+        P = par_dna.shape[0]
+        out_dna = torch.empty_like(par_dna)
+        out_obj = torch.empty((P, 2), dtype=torch.float64, device=self.device)
+        out_fit = torch.empty(P, dtype=torch.float64, device=self.device)
+        self._check(self.lib.gcp_gather_survivors(
+            self.ctx, C.c_void_p(order.data_ptr()), P, C.c_void_p(par_dna.data_ptr()),
+            C.c_void_p(kid_dna.data_ptr()), C.c_void_p(glad_obj.data_ptr()),
+            C.c_void_p(glad_fit.data_ptr()), C.c_void_p(out_dna.data_ptr()),
+            C.c_void_p(out_obj.data_ptr()), C.c_void_p(out_fit.data_ptr()), self._stream()))
+        return out_dna, out_obj, out_fit
 
     # ------------------------------------------------------------------
     def launch_count(self):

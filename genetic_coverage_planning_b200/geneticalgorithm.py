@@ -1,0 +1,271 @@
+"""Drop-in for the reference's geneticalgorithm.py: same class names, constructor
+signatures, attributes and return values, with the population living on the GPU.
+
+    from genetic_coverage_planning_b200.geneticalgorithm import GeneticalGorithm, Organism
+    population = GeneticalGorithm(mappy, pather, gen_params)      # pather_driver.py:235
+    pareto_hist = population.runEvolution(100)                    # pather_driver.py:240
+
+`mappy` / `pather` are the reference's own Mappy / PathMaker objects (or anything with the
+same attributes: _img, _traverse_frustum/_angles/_dists, _graph, _XY, ...).  They are packed
+once (packing.pack_from_reference) and uploaded; after that each generation is a fixed
+sequence of kernels (select -> crossover -> mutate -> evaluate -> maximin -> order ->
+gather) with no host round trip except the per-generation objective list the reference
+also returns.
+
+Differences from the reference, all deliberate:
+  * random draws come from Philox streams keyed by (seed, generation, organism, agent),
+    not numpy's global MT19937: runs are reproducible for a seed but not draw-for-draw equal;
+  * survivors are ordered by the stable (fit, index) rule;
+  * parents are never deep-copied; `findCrossoverCand()` is not required to have been called.
+"""
+import copy
+
+import numpy as np
+import torch
+
+from . import packing
+from .engine import FitnessEngine
+
+_ENGINES = {}
+
+
+def _engine_for(mappy, pather, org_params, num_agents, device=0):
+    """One engine (packed tables + CUDA context) per (mappy, pather, A, L, device)."""
+    key = (id(mappy), id(pather), int(num_agents), int(org_params['max_dna_len']), int(device))
+    ent = _ENGINES.get(key)
+    if ent is None or ent[1] is not mappy or ent[2] is not pather:
+        pw = packing.pack_from_reference(mappy, pather)
+        eng = FitnessEngine(pw, org_params, num_agents=num_agents, device=device)
+        path_params = {'path_memory': getattr(pather, '_path_memory', 10),
+                       'log_scale_weight': getattr(pather, '_log_scale_weight', 0.7)}
+        eng.set_vary_params(org_params, path_params)
+        ent = (eng, mappy, pather)
+        _ENGINES[key] = ent
+    else:
+        ent[0].set_params(org_params)
+    return ent[0]
+
+
+def _pad_rows(dna_list, L):
+    d = -np.ones((len(dna_list), L), dtype=np.int32)
+    for a, row in enumerate(dna_list):
+        row = np.asarray(row, dtype=np.int64)
+        row = row[row != -1][:L]
+        d[a, :len(row)] = row
+    return d
+
+
+class Organism(object):
+    """geneticalgorithm.py:126-357.  Constructed from a list of per-agent waypoint arrays;
+    variation (mutation / muterpolate / U-turn pruning) and `calcObj` run on the GPU."""
+
+    def __init__(self, dna_list, mappy, pather, org_params, _precomputed=None, _seed=None):
+        self._max_dna_len = org_params['max_dna_len']
+        self._min_dna_len = org_params['min_dna_len']
+        self._xover_probability = org_params['crossover_prob']
+        self._time_thresh = org_params['crossover_time_thresh']
+        self._mutate_probability = org_params['mutation_prob']
+        self._muterpolate_probability = org_params['muterpolate_prob']
+        self._num_muterpolations = org_params['num_muterpolations']
+        self._srch_dist = org_params['muterpolation_srch_dist']
+        self._P_muterpolate_each = org_params['muterpolation_sub_prob']
+        self._min_solo_lcs = org_params['min_solo_lcs']
+        self._min_comb_lcs = org_params['min_comb_lcs']
+        self._ft_scale = org_params['flight_time_scale']
+        self._org_params = org_params
+        self._pather = pather
+        self._mappy = mappy
+        self._scale = getattr(mappy, '_scale', None)
+        self._narrowest_hall = getattr(mappy, '_hall_width', None)
+        self._safety_buffer = getattr(mappy, '_safety_buffer', None)
+        self._num_agents = len(dna_list)
+        self._obj_val_sc = [None, None]
+        if _precomputed is not None:                       # view of a device-side organism
+            self._dna = np.asarray(_precomputed[0]).astype(int)
+            self._obj_val = [float(_precomputed[1][0]), float(_precomputed[1][1])]
+            if len(_precomputed) > 2 and _precomputed[2] is not None:
+                self._obj_val_sc = [float(_precomputed[2][0]), float(_precomputed[2][1])]
+        else:
+            eng = _engine_for(mappy, pather, org_params, self._num_agents)
+            dna = torch.from_numpy(_pad_rows(dna_list, self._max_dna_len)[None]).to(eng.device)
+            seed = int(np.random.randint(0, 2 ** 31 - 1)) if _seed is None else int(_seed)
+            eng.mutate(dna, seed, 0, salt=7)               # constructor variation :158-168
+            self._dna = dna[0].cpu().numpy().astype(int)
+            self._obj_val = self.calcObj()
+        self._dna_list = [row[row != -1] for row in self._dna]
+        # reference quirk F12: _len_dna ends up as the padded length
+        self._len_dna = (np.ones(self._num_agents) * self._max_dna_len).astype(int)
+
+    def calcObj(self):
+        """geneticalgorithm.py:177-201 on the GPU."""
+        eng = _engine_for(self._mappy, self._pather, self._org_params, self._num_agents)
+        r = eng.evaluate(self._dna[None].astype(np.int32), detail=False)
+        o = r.obj[0].cpu().numpy()
+        return [float(o[0]), float(o[1])]
+
+    def crossover(self, mate):
+        """geneticalgorithm.py:211-249 -> [kid, kid]."""
+        eng = _engine_for(self._mappy, self._pather, self._org_params, self._num_agents)
+        parents = torch.from_numpy(np.stack([self._dna, mate._dna]).astype(np.int32)).to(eng.device)
+        strong = torch.tensor([0, 1], dtype=torch.int32, device=eng.device)
+        seed = int(np.random.randint(0, 2 ** 31 - 1))
+        kids = eng.crossover(parents, strong, seed, 0)
+        eng.mutate(kids, seed, 0, salt=0)
+        objs = eng.evaluate(kids, detail=False).obj.cpu().numpy()
+        kids = kids.cpu().numpy()
+        return [Organism([None] * self._num_agents, self._mappy, self._pather, self._org_params,
+                         _precomputed=(kids[k], objs[k])) for k in range(2)]
+
+
+class GeneticalGorithm(object):
+    """geneticalgorithm.py:15-123."""
+
+    def __init__(self, mappy, pather, gen_params, device=0, seed=None, initial_dna=None):
+        self._G_sz = gen_params['gen_size']
+        self._starting_path_len = gen_params['starting_path_len']
+        self._num_agents = gen_params['num_agents']
+        self._gamma = gen_params['gamma']
+        self._cov_constr_0 = -gen_params['coverage_constr_0']
+        self._cov_constr_f = -gen_params['coverage_constr_f']
+        self._cov_aging = gen_params['coverage_aging']
+        self._org_params = gen_params['org_params']
+        self._mappy, self._pather = mappy, pather
+        self._device = device
+        self._seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
+        self._gen_num = 0
+        self._views = None
+        if self._G_sz % 2:
+            raise ValueError("gen_size must be even (pather_driver.py:107)")
+        self._eng = _engine_for(mappy, pather, self._org_params, self._num_agents, device)
+        if initial_dna is not None:
+            self._dna = self._eng.to_device_dna(initial_dna).clone()
+            self._obj = self._eng.evaluate(self._dna, detail=False).obj
+        else:
+            self.firstGeneration(mappy, pather, self._org_params)
+        self._fit, self._obj_sc = self._eng.maximin(self._obj, self._coverage_constr(),
+                                                    return_scaled=True)
+
+    # -- reference: geneticalgorithm.py:37-53 ------------------------------------------
+    def firstGeneration(self, mappy, pather, org_params, max_batches=10000):
+        """Random paths + constructor variation + evaluation in batches, keeping the
+        candidates that meet the initial coverage constraint (:50), in generation order."""
+        eng, P = self._eng, self._G_sz
+        start = org_params['start_idx']
+        got_dna, got_obj, n = [], [], 0
+        batch_sz = int(min(max(2 * P, 256), 1 << 16))
+        for b in range(max_batches):
+            dna = eng.random_walks(batch_sz, start, self._starting_path_len, self._seed, batch=b)
+            eng.mutate(dna, self._seed, 0xFFFF0000 + b, salt=3)
+            obj = eng.evaluate(dna, detail=False).obj
+            ok = obj[:, 0] <= self._cov_constr_0
+            k = int(ok.sum().item())
+            if k:
+                got_dna.append(dna[ok])
+                got_obj.append(obj[ok])
+                n += k
+            if n >= P:
+                break
+        if n < P:
+            raise RuntimeError("firstGeneration: only %d of %d organisms met coverage >= %g"
+                               % (n, P, -self._cov_constr_0))
+        self._dna = torch.cat(got_dna)[:P].contiguous()
+        self._obj = torch.cat(got_obj)[:P].contiguous()
+
+    def _coverage_constr(self):
+        alpha = min(1, (self._gen_num / self._cov_aging))                    # :98
+        return (1 - alpha) * self._cov_constr_0 + alpha * self._cov_constr_f  # :99-100
+
+    # -- reference: geneticalgorithm.py:55-76 ------------------------------------------
+    def runEvolution(self, num_generations):
+        eng, P = self._eng, self._G_sz
+        hist_dev = []
+        for _ in range(num_generations):
+            kids = eng.select_vary(self._dna, self._fit, self._gamma, self._seed, self._gen_num)
+            kid_obj = eng.evaluate(kids, detail=False).obj
+            glad_obj = torch.cat([self._obj, kid_obj])                        # arena :72
+            fit, sc = eng.maximin(glad_obj, self._coverage_constr(), return_scaled=True)
+            order, _ = eng.arena_order(fit)
+            self._dna, self._obj, self._fit = eng.gather_survivors(order, self._dna, kids,
+                                                                   glad_obj, fit)
+            self._obj_sc = sc[order[:P].long()]
+            self._gen_num += 1
+            hist_dev.append(self._obj)
+        self._views = None
+        if not hist_dev:
+            return []
+        flat = torch.stack(hist_dev).cpu().numpy()                            # one D2H at the end
+        return [[[float(o[0]), float(o[1])] for o in gen] for gen in flat]
+
+    RunEvolution = runEvolution          # README.md:17 spells it this way
+
+    # -- reference: geneticalgorithm.py:78-123 -----------------------------------------
+    def rackNstack(self, gladiators):
+        """Maximin fitness of a list of Organism-likes; also fills their _obj_val_sc."""
+        objs = np.array([[float(g._obj_val[0]), float(g._obj_val[1])] for g in gladiators])
+        fit, sc = self._eng.maximin(torch.from_numpy(objs), self._coverage_constr(),
+                                    return_scaled=True)
+        sc = sc.cpu().numpy()
+        for g, s in zip(gladiators, sc):
+            g._obj_val_sc = [float(s[0]), float(s[1])]
+        return [float(f) for f in fit.cpu().numpy()]
+
+    def arena(self, gladiators):
+        fits = self.rackNstack(gladiators)
+        order, _ = self._eng.arena_order(torch.tensor(fits, dtype=torch.float64))
+        order = order.cpu().numpy()[:self._G_sz]
+        keep = [gladiators[i] for i in order]
+        self._dna = self._eng.to_device_dna(np.stack([g._dna for g in keep]).astype(np.int32))
+        self._obj = torch.tensor([[float(g._obj_val[0]), float(g._obj_val[1])] for g in keep],
+                                 dtype=torch.float64, device=self._eng.device)
+        self._fit = torch.tensor([fits[i] for i in order], dtype=torch.float64,
+                                 device=self._eng.device)
+        self._obj_sc = torch.tensor([g._obj_val_sc for g in keep], dtype=torch.float64,
+                                    device=self._eng.device)
+        self._views = None
+
+    # -- attributes the reference's plotting / export code reads -------------------------
+    @property
+    def _gen_parent(self):
+        """List of Organism views (gori_tools.py:23,248-250; pointselector.py:52), built on
+        first access after each change; no table copies."""
+        if self._views is None:
+            dna = self._dna.cpu().numpy()
+            obj = self._obj.cpu().numpy()
+            sc = self._obj_sc.cpu().numpy() if self._obj_sc is not None else [None] * len(dna)
+            self._views = [Organism([None] * self._num_agents, self._mappy, self._pather,
+                                    self._org_params, _precomputed=(dna[k], obj[k], sc[k]))
+                           for k in range(len(dna))]
+        return self._views
+
+    @property
+    def _gen_parent_fit(self):
+        return [float(f) for f in self._fit.cpu().numpy()]
+
+    # -- pickle (gori_tools.py:252-257): device state round-trips through numpy ----------
+    def __getstate__(self):
+        st = {k: v for k, v in self.__dict__.items() if k not in ('_eng', '_views', '_dna', '_obj',
+                                                                   '_fit', '_obj_sc')}
+        st['_dna_np'] = self._dna.cpu().numpy()
+        st['_obj_np'] = self._obj.cpu().numpy()
+        st['_fit_np'] = self._fit.cpu().numpy()
+        st['_obj_sc_np'] = self._obj_sc.cpu().numpy()
+        return st
+
+    def __setstate__(self, st):
+        st = dict(st)
+        dna, obj, fit, sc = (st.pop('_dna_np'), st.pop('_obj_np'), st.pop('_fit_np'),
+                             st.pop('_obj_sc_np'))
+        self.__dict__.update(st)
+        self._views = None
+        self._eng = _engine_for(self._mappy, self._pather, self._org_params, self._num_agents,
+                                self._device)
+        dev = self._eng.device
+        self._dna = torch.from_numpy(dna).to(dev)
+        self._obj = torch.from_numpy(obj).to(dev)
+        self._fit = torch.from_numpy(fit).to(dev)
+        self._obj_sc = torch.from_numpy(sc).to(dev)
+
+
+def getObjValsList(population):
+    """gori_tools.py:248-250 without materialising Organism views."""
+    return [[float(o[0]), float(o[1])] for o in population._obj.cpu().numpy()]

@@ -231,6 +231,13 @@ def pack_world(img, xy, row_ptr, col, edge_poly, edge_theta, edge_dist, map_para
 def pack_from_reference(mappy, pather, progress=False):
     """Build the packed world from live reference-API objects (Mappy, PathMaker)
     exactly as pather_driver.py:207-232 leaves them."""
+    mp = {'scale': mappy._scale, 'narrowest_hall': mappy._hall_width, 'rho': mappy._rho,
+          'solo_sep_thresh': mappy._solo_sep_thresh, 'coverage_blend': mappy._coverage_blend}
+    if hasattr(pather, '_csr'):
+        # CSR-backed objects (synthetic worlds: a dense N x N table cannot exist at 10^5 nodes)
+        row_ptr, col = pather._csr
+        return pack_world(mappy._img, pather._XY, row_ptr, col, mappy._edge_poly,
+                          mappy._edge_theta, mappy._edge_dist, mp, progress=progress)
     g = np.asarray(pather._graph)
     src, dst = np.nonzero(g == 1)
     N = g.shape[0]

@@ -349,3 +349,37 @@ def random_walk_population_torch(xy, row_ptr, col, starts, n_org, walk_len, max_
             cur = nxt
             dna[s:e, t + 1] = cur.to(torch.int32)
     return dna.reshape(n_org, A, max_dna_len)
+
+
+class CsrMappy(object):
+    """Mappy-shaped holder of a synthetic world's map-side tables (attribute names of the
+    reference's Mappy, mappy.py:14-64, plus per-edge CSR tables instead of dense N x N)."""
+
+    def __init__(self, world):
+        mp = world.map_params
+        self._img = world.img
+        self.shape = world.img.shape
+        self._scale = mp['scale']
+        self._hall_width = mp['narrowest_hall']
+        self._safety_buffer = self._hall_width / 2
+        self._rho = mp['rho']
+        self._solo_sep_thresh = mp['solo_sep_thresh']
+        self._coverage_blend = mp['coverage_blend']
+        self._all_waypoints = world.xy
+        self._edge_poly, self._edge_theta, self._edge_dist = (world.edge_poly, world.edge_theta,
+                                                              world.edge_dist)
+
+
+class CsrPather(object):
+    """PathMaker-shaped holder (pathmaker.py:15-24,157-173) with a CSR graph."""
+
+    def __init__(self, world):
+        self._XY = world.xy
+        self._csr = (world.row_ptr, world.col)
+        self._path_memory = world.path_params.get('path_memory', 10)
+        self._log_scale_weight = world.path_params.get('log_scale_weight', 0.7)
+        self._crossover_cand = (np.where(np.diff(world.row_ptr) > 2)[0],)
+
+    @property
+    def waypoint_locs(self):
+        return self._XY

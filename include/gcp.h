@@ -48,6 +48,21 @@ typedef struct gcp_params {
     double  one_minus_blend;   /* (1 - blend) as the host language evaluates it */
 } gcp_params;
 
+/* Variation parameters.  Sources: org_params / path_params of pather_driver.py:161-191. */
+typedef struct gcp_vary_params {
+    int32_t min_dna_len;              /* org_params['min_dna_len']              geneticalgorithm.py:205 */
+    int32_t crossover_time_thresh;    /* org_params['crossover_time_thresh']    :330 */
+    int32_t num_muterpolations;       /* org_params['num_muterpolations']       :275 (<= 64) */
+    int32_t muterpolation_srch_dist;  /* org_params['muterpolation_srch_dist']  :283 */
+    int32_t path_memory;              /* path_params['path_memory']             pathmaker.py:199 (<= 16) */
+    int32_t reserved0;
+    double  crossover_prob;           /* :217 */
+    double  mutation_prob;            /* :160 */
+    double  muterpolate_prob;         /* :164 */
+    double  muterpolation_sub_prob;   /* :285 */
+    double  log_scale_weight;         /* path_params['log_scale_weight']        pathmaker.py:182 */
+} gcp_vary_params;
+
 /* Constants of the map planes (computed by the host packer with the reference's own
  * numpy/cv2 expressions: mappy.py:25,36-39,337). */
 typedef struct gcp_map_consts {
@@ -149,13 +164,48 @@ int gcp_maximin(gcp_ctx* ctx, const double* obj_dev, uint32_t n, double coverage
 int gcp_arena_order(gcp_ctx* ctx, const double* fit_dev, uint32_t n, int32_t* order_dev,
                     uint8_t* nondom_dev, void* scratch_dev, size_t scratch_bytes, void* stream);
 
+/* ---- selection + variation (Philox streams keyed by seed / generation / organism / agent)
+ * Replaces got.lowVarSample (gori_tools.py:207-229), Organism.crossover + matchWaypt +
+ * padMinDNA (geneticalgorithm.py:203-249,311-333), the constructor's mutation / muterpolate /
+ * pruneUTurns / addTelomere (:156-175,251-357), PathMaker.makeMeAPath (pathmaker.py:188-213)
+ * and the arena truncation (geneticalgorithm.py:78-84). */
+int gcp_set_vary_params(gcp_ctx* ctx, const gcp_vary_params* p);
+/* out_idx[m] = index of the m-th resampled parent; r0 = the single U(0, 1/M) draw;
+ * scratch: dev double [M]. */
+int gcp_low_var_select(gcp_ctx* ctx, const double* fit_dev, uint32_t m, double gamma, double r0,
+                       double* scratch_dev, int32_t* out_idx_dev, void* stream);
+/* pair k = (strong[k], strong[k + P/2]) -> children 2k, 2k+1.  dna buffers: dev int32 [P][A][L]. */
+int gcp_crossover(gcp_ctx* ctx, const int32_t* parents_dna_dev, const int32_t* strong_idx_dev,
+                  uint32_t n_org, uint64_t seed, uint32_t generation, int32_t* children_dna_dev,
+                  void* stream);
+/* in place: mutation (prob), muterpolate (prob), pruneUTurns, addTelomere; `salt` separates
+ * independent uses within one generation. */
+int gcp_mutate(gcp_ctx* ctx, int32_t* dna_dev, uint32_t n_org, uint64_t seed, uint32_t generation,
+               uint32_t salt, void* stream);
+/* select + crossover + mutate in one call (the reference's child construction loop,
+ * geneticalgorithm.py:59-68).  scratch: dev, >= n_org * 16 bytes. */
+int gcp_select_vary(gcp_ctx* ctx, const int32_t* parents_dna_dev, const double* parent_fit_dev,
+                    uint32_t n_org, double gamma, uint64_t seed, uint32_t generation,
+                    int32_t* children_dna_dev, void* scratch_dev, size_t scratch_bytes, void* stream);
+/* heading-biased random walks of path_len steps from start_idx[a] (firstGeneration,
+ * geneticalgorithm.py:44-48).  start_idx_dev: dev int32 [A]. */
+int gcp_random_walks(gcp_ctx* ctx, int32_t* dna_dev, uint32_t n_org, const int32_t* start_idx_dev,
+                     int32_t path_len, uint64_t seed, uint32_t batch, void* stream);
+/* survivors k < P of the arena: out[k] = gladiator[order[k]], gladiators = parents ++ children;
+ * glad_obj [2P][2], glad_fit [2P]. */
+int gcp_gather_survivors(gcp_ctx* ctx, const int32_t* order_dev, uint32_t n_org,
+                         const int32_t* parents_dna_dev, const int32_t* children_dna_dev,
+                         const double* glad_obj_dev, const double* glad_fit_dev,
+                         int32_t* out_dna_dev, double* out_obj_dev, double* out_fit_dev, void* stream);
+
 /* ---- introspection ---------------------------------------------------------------- */
 /* kernel launch counter since gcp_create (for bench.py's gpu_launches). */
 uint64_t gcp_launch_count(gcp_ctx* ctx);
 /* time of the most recent call of each stage measured with CUDA events on the launch
  * stream; only recorded while enabled (adds two event records per stage). */
 int gcp_set_timing(gcp_ctx* ctx, int enabled);
-/* stage: 0 path_costs, 1 coverage, 2 loop_closures, 3 maximin, 4 arena_order, 5 select_vary.
+/* stage: 0 path_costs, 1 coverage, 2 loop_closures, 3 maximin, 4 arena_order, 5 select,
+ * 6 crossover, 7 mutate.
  * Synchronises on the stage's end event. Returns milliseconds, <0 if not recorded. */
 float gcp_stage_ms(gcp_ctx* ctx, int stage);
 

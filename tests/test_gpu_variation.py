@@ -1,0 +1,296 @@
+"""GPU: selection / variation kernels.  Deterministic parts are checked bit-exactly against
+golden vectors of the reference (pruneUTurns, lowVarSample); the random parts (Philox streams
+instead of numpy's MT19937) by the invariants and distributions SURVEY.md section 4 lists."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+import fitness_oracle as fo
+from world import World
+
+pytestmark = pytest.mark.gpu
+
+
+def _op(world, **kw):
+    op = dict(world.org_params)
+    op.update(kw)
+    return op
+
+
+def _engine(world, op):
+    from genetic_coverage_planning_b200 import packing
+    from genetic_coverage_planning_b200.engine import FitnessEngine
+    pw = packing.pack_world(world.img, world.xy, world.row_ptr, world.col, world.edge_poly,
+                            world.edge_theta, world.edge_dist, world.map_params)
+    eng = FitnessEngine(pw, op, num_agents=len(op['start_idx']))
+    eng.set_vary_params(op, {'path_memory': 10, 'log_scale_weight': 0.7})
+    return eng
+
+
+def _edges(world):
+    src = np.repeat(np.arange(world.N), np.diff(world.row_ptr))
+    return set(zip(src.tolist(), world.col.tolist()))
+
+
+def _valid(row):
+    row = np.asarray(row)
+    n = int((row != -1).sum())
+    assert (row[:n] != -1).all() and (row[n:] == -1).all(), "row must be a valid prefix + -1 padding"
+    return row[:n]
+
+
+def test_prune_uturns_golden(world_big, golden_dir):
+    import torch
+    z = np.load(os.path.join(golden_dir, "prune.npz"))
+    eng = _engine(world_big, _op(world_big, mutation_prob=0.0, muterpolate_prob=0.0))
+    dna = torch.from_numpy(z['before'].astype(np.int32)).cuda()
+    eng.mutate(dna, seed=1, gen=0)
+    assert np.array_equal(dna.cpu().numpy(), z['after'].astype(np.int32))
+
+
+def test_low_var_select_golden(world_big, golden_dir):
+    import torch
+    z = np.load(os.path.join(golden_dir, "rank.npz"))
+    eng = _engine(world_big, world_big.org_params)
+    fit = torch.from_numpy(z['fit_gen17'])
+    for r, idx in zip(z['lowvar_r'], z['lowvar_idx']):
+        got = eng.low_var_select(fit, float(z['gamma']), float(r)).cpu().numpy()
+        assert np.array_equal(got, idx)
+    # large population vs the oracle restatement
+    rs = np.random.RandomState(0)
+    fit = rs.randn(5000) * 0.3
+    got = eng.low_var_select(torch.from_numpy(fit), 0.5, 0.5 / 5000).cpu().numpy()
+    want = fo.low_var_sample_indices(fit, 0.5, 0.5 / 5000)
+    assert (got != want).mean() < 0.002 and np.abs(got - want).max() <= 1
+    assert (np.diff(got) >= 0).all()
+
+
+def _parents(world, eng, P, walk=150, seed=3):
+    from genetic_coverage_planning_b200 import synth
+    op = world.org_params
+    return synth.random_walk_population(world.xy, world.row_ptr, world.col, op['start_idx'], P,
+                                        walk, op['max_dna_len'], seed=seed).astype(np.int32)
+
+
+def test_crossover_invariants(world_big):
+    import torch
+    w = world_big
+    op = _op(w, crossover_prob=1.0)
+    eng = _engine(w, op)
+    P, A, L = 64, eng.A, eng.L
+    par = _parents(w, eng, P)
+    par[5, 2, 40:] = -1                              # a short row: child may need padMinDNA
+    strong = torch.arange(P, dtype=torch.int32)
+    kids = eng.crossover(par, strong, seed=11, gen=2).cpu().numpy()
+    kids2 = eng.crossover(par, strong, seed=11, gen=2).cpu().numpy()
+    assert np.array_equal(kids, kids2), "same seed/generation must reproduce"
+    assert not np.array_equal(kids, eng.crossover(par, strong, seed=12, gen=2).cpu().numpy())
+    cand = set(w.crossover_cand().tolist())
+    edges = _edges(w)
+    T, mn = op['crossover_time_thresh'], op['min_dna_len']
+    n_cross = 0
+    for k in range(P // 2):
+        for a in range(A):
+            pm, pd = _valid(par[k, a]), _valid(par[k + P // 2, a])
+            c1, c2 = _valid(kids[2 * k, a]), _valid(kids[2 * k + 1, a])
+            if np.array_equal(c1, pm) and np.array_equal(c2, pd):
+                continue                              # no candidate pair existed
+            n_cross += 1
+            # find the crossover point: c1 = pm[:i] + pd[j:], c2 = pd[:j] + pm[i:]
+            ok = False
+            for i in range(1, len(pm)):
+                if not np.array_equal(c1[:i], pm[:i]) or pm[i] not in cand:
+                    continue
+                for j in range(max(1, i - T + 1), min(len(pd), i + T)):
+                    if pd[j] != pm[i]:
+                        continue
+                    e1 = np.concatenate([pm[:i], pd[j:]])[:L]
+                    e2 = np.concatenate([pd[:j], pm[i:]])[:L]
+                    ok1 = np.array_equal(c1[:len(e1)], e1) and (len(e1) >= mn and len(c1) == len(e1)
+                                                                or len(e1) < mn and len(c1) == mn)
+                    ok2 = np.array_equal(c2[:len(e2)], e2) and (len(e2) >= mn and len(c2) == len(e2)
+                                                                or len(e2) < mn and len(c2) == mn)
+                    if ok1 and ok2:
+                        for c, e in ((c1, e1), (c2, e2)):     # padMinDNA tail walks on edges
+                            for x in range(len(e) - 1, len(c) - 1):
+                                assert (int(c[x]), int(c[x + 1])) in edges
+                        ok = True
+                        break
+                if ok:
+                    break
+            assert ok, (k, a)
+    assert n_cross > 0.5 * (P // 2) * A
+    # crossover_prob = 0: children are the parents, paired (k, k+P/2) -> (2k, 2k+1)
+    eng0 = _engine(w, _op(w, crossover_prob=0.0))
+    kids0 = eng0.crossover(par, strong, seed=1, gen=0).cpu().numpy()
+    assert np.array_equal(kids0[0::2], par[:P // 2]) and np.array_equal(kids0[1::2], par[P // 2:])
+
+
+def test_mutation_invariants(world_big):
+    import torch
+    w = world_big
+    eng = _engine(w, _op(w, mutation_prob=1.0, muterpolate_prob=0.0))
+    P, A, L = 96, eng.A, eng.L
+    par = _parents(w, eng, P, walk=120)
+    dna = torch.from_numpy(par.copy()).cuda()
+    eng.mutate(dna, seed=5, gen=1)
+    out = dna.cpu().numpy()
+    edges = _edges(w)
+    changed = 0
+    for p in range(P):
+        for a in range(A):
+            r0, r1 = _valid(par[p, a]), _valid(out[p, a])
+            assert r1[0] == r0[0] and 2 <= len(r1) <= L
+            changed += not np.array_equal(r0, r1)
+            for x in range(len(r1) - 1):           # walks stay on the graph
+                assert (int(r1[x]), int(r1[x + 1])) in edges
+            # no immediate u-turns survive pruneUTurns
+            assert not (r1[:-1] == r1[1:]).any()
+    assert changed > 0.9 * P * A
+    # mutation_prob = 0 and no u-turns in the input -> identity
+    eng0 = _engine(w, _op(w, mutation_prob=0.0, muterpolate_prob=0.0))
+    d0 = torch.from_numpy(out.copy()).cuda()
+    eng0.mutate(d0, seed=5, gen=1)
+    again = d0.cpu().numpy()
+    for p in range(P):
+        for a in range(A):
+            r = _valid(out[p, a])
+            if not ((r[:-2] == r[2:]).any()):
+                assert np.array_equal(again[p, a], out[p, a])
+
+
+def test_muterpolate_invariants(world_big):
+    import torch
+    w = world_big
+    eng = _engine(w, _op(w, mutation_prob=0.0, muterpolate_prob=1.0))
+    P, A = 64, eng.A
+    par = _parents(w, eng, P, walk=150, seed=8)
+    dna = torch.from_numpy(par.copy()).cuda()
+    eng.mutate(dna, seed=9, gen=4)
+    out = dna.cpu().numpy()
+    nbrs = {n: set(w.col[w.row_ptr[n]:w.row_ptr[n + 1]].tolist()) for n in range(w.N)}
+    shorter = 0
+    for p in range(P):
+        for a in range(A):
+            r0, r1 = _valid(par[p, a]), _valid(out[p, a])
+            assert r1[0] == r0[0] and len(r1) <= len(r0)
+            shorter += len(r1) < len(r0)
+            allowed = set(r0.tolist())
+            for g in r0:
+                allowed |= nbrs[int(g)]
+            assert set(r1.tolist()) <= allowed      # shortcut nodes are neighbours of old ones
+    assert shorter > 0.3 * P * A
+
+
+def test_random_walks_and_statistics(world_big):
+    from genetic_coverage_planning_b200 import synth
+    w = world_big
+    op = w.org_params
+    eng = _engine(w, op)
+    P, A, L = 256, eng.A, eng.L
+    dna = eng.random_walks(P, op['start_idx'], 150, seed=3).cpu().numpy()
+    assert np.array_equal(dna, eng.random_walks(P, op['start_idx'], 150, seed=3).cpu().numpy())
+    edges = _edges(w)
+    for p in range(0, P, 8):
+        for a in range(A):
+            r = _valid(dna[p, a])
+            assert len(r) == 151 and r[0] == op['start_idx'][a]
+            for x in range(150):
+                assert (int(r[x]), int(r[x + 1])) in edges
+    # same rule as the numpy restatement of makeMeAPath: compare simple statistics
+    ref = synth.random_walk_population(w.xy, w.row_ptr, w.col, op['start_idx'], P, 150, L, seed=1)
+
+    def stats(d):
+        uniq = np.mean([len(np.unique(r[r >= 0])) for r in d.reshape(-1, L)])
+        end = w.xy[d[:, :, 150]] - w.xy[d[:, :, 0]]
+        return uniq, np.sqrt((end ** 2).sum(-1)).mean()
+    u_dev, e_dev = stats(dna)
+    u_ref, e_ref = stats(ref)
+    assert abs(u_dev - u_ref) < 0.1 * u_ref, (u_dev, u_ref)
+    assert abs(e_dev - e_ref) < 0.15 * e_ref, (e_dev, e_ref)
+
+
+def test_generation_step_against_oracle(world_big):
+    """One full generation on the device, every deterministic stage re-derived by the oracle."""
+    import torch
+    import ref_shim
+    w = world_big
+    op = w.org_params
+    _, _, _, gp = ref_shim.driver_params(6)
+    eng = _engine(w, op)
+    P = 48
+    par = torch.from_numpy(_parents(w, eng, P)).cuda()
+    par_obj = eng.evaluate(par, detail=False).obj
+    constr = fo.coverage_constraint(0, gp)
+    par_fit = eng.maximin(par_obj, constr)
+    kids = eng.select_vary(par, par_fit, gp['gamma'], seed=77, gen=0)
+    kid_obj = eng.evaluate(kids, detail=False).obj
+    glad_obj = torch.cat([par_obj, kid_obj])
+    fit = eng.maximin(glad_obj, constr)
+    order, nondom = eng.arena_order(fit)
+    new_dna, new_obj, new_fit = eng.gather_survivors(order, par, kids, glad_obj, fit)
+    want_fit = fo.rack_n_stack(glad_obj.cpu().numpy(), 0, gp)
+    assert np.array_equal(fit.cpu().numpy(), want_fit)
+    want_order = fo.arena_order(want_fit)
+    assert np.array_equal(order.cpu().numpy(), want_order)
+    glad_dna = np.concatenate([par.cpu().numpy(), kids.cpu().numpy()])
+    assert np.array_equal(new_dna.cpu().numpy(), glad_dna[want_order[:P]])
+    assert np.array_equal(new_obj.cpu().numpy(), glad_obj.cpu().numpy()[want_order[:P]])
+    assert np.array_equal(new_fit.cpu().numpy(), want_fit[want_order[:P]])
+    for k in (0, 7, 23):                          # children objectives vs oracle
+        det = fo.calc_obj(w, kids[k].cpu().numpy().astype(int))
+        got = kid_obj[k].cpu().numpy()
+        assert det[1] == got[1] and abs(det[0] - got[0]) <= 1e-12
+
+
+def test_facade_drop_in(tmp_path):
+    """GeneticalGorithm / Organism facade on a small synthetic world (CSR-backed Mappy /
+    PathMaker stand-ins): constructor, runEvolution history, views, rackNstack, pickle."""
+    from genetic_coverage_planning_b200 import synth, worlds
+    from genetic_coverage_planning_b200.geneticalgorithm import GeneticalGorithm, Organism
+    sw = synth.make_world(768, seed=3)
+    mappy, pather = synth.CsrMappy(sw), synth.CsrPather(sw)
+    starts = synth.spread_starts(sw.xy, 3, 768)
+    op = worlds.org_params_for(dict(L=120), starts)
+    op.update(min_solo_lcs=0, min_comb_lcs=0)
+    gp = dict(worlds.GEN_PARAMS_6)
+    gp.update(gen_size=32, starting_path_len=80, num_agents=3, coverage_constr_0=0.0,
+              org_params=op)
+    pop = GeneticalGorithm(mappy, pather, gp, seed=5)
+    assert len(pop._gen_parent) == 32 and len(pop._gen_parent_fit) == 32
+    o0 = pop._gen_parent[0]
+    assert o0._dna.shape == (3, 120) and len(o0._obj_val) == 2 and o0._max_dna_len == 120
+    hist = pop.runEvolution(3)
+    assert len(hist) == 3 and len(hist[0]) == 32 and len(hist[0][0]) == 2
+    assert pop._gen_num == 3 and pop.RunEvolution.__func__ is pop.runEvolution.__func__
+    # parents' stored objectives equal a fresh oracle evaluation of their DNA
+    ow = World(sw.img, sw.xy, sw.row_ptr, sw.col, sw.edge_poly, sw.edge_theta, sw.edge_dist,
+               sw.map_params, op, name="facade")
+    for org in pop._gen_parent[:4]:
+        want = fo.calc_obj(ow, org._dna)
+        assert want[0] == org._obj_val[0] and want[1] == org._obj_val[1]
+    # fitnesses are non-decreasing (arena order) and rackNstack is the oracle's maximin
+    f = pop._gen_parent_fit
+    assert all(f[i] <= f[i + 1] for i in range(len(f) - 1))
+    fits = pop.rackNstack(pop._gen_parent)
+    want = fo.rack_n_stack(np.array([o._obj_val for o in pop._gen_parent]), pop._gen_num,
+                           dict(coverage_aging=gp['coverage_aging'],
+                                coverage_constr_0=gp['coverage_constr_0'],
+                                coverage_constr_f=gp['coverage_constr_f']))
+    assert np.array_equal(np.array(fits), want)
+    # single-organism API
+    kid_a, kid_b = pop._gen_parent[0].crossover(pop._gen_parent[1])
+    assert kid_a._dna.shape == (3, 120) and kid_a._dna[0, 0] == starts[0]
+    assert kid_a.calcObj() == kid_a._obj_val
+    org = Organism([r for r in pop._gen_parent[2]._dna_list], mappy, pather, op, _seed=1)
+    assert org._dna[1, 0] == starts[1]
+    # pickle round trip (gori_tools.savePopulation / loadPopulation)
+    fn = os.path.join(tmp_path, "pop.pkl")
+    pickle.dump(pop, open(fn, "wb"))
+    pop2 = pickle.load(open(fn, "rb"))
+    assert pop2._gen_num == 3
+    assert np.array_equal(pop2._gen_parent[5]._dna, pop._gen_parent[5]._dna)
+    h2 = pop2.runEvolution(1)
+    assert len(h2) == 1 and pop2._gen_num == 4
