@@ -240,6 +240,7 @@ def main():
     cfg, w, pw, op, starts = build_setup(args.config, args.pop, rank, world_size, barrier)
     P, A, L = cfg['pop'], cfg['agents'], cfg['L']
     eng = FitnessEngine(pw, op, num_agents=A, device=local)
+    eng.set_vary_params(op, w.path_params)
     t0 = time.time()
     dna = synth.random_walk_population_torch(w.xy, w.row_ptr, w.col, starts, P, cfg['walk'], L,
                                              seed=1 + rank, device=dev)
@@ -328,12 +329,67 @@ def main():
                     "eval_frac_of_peak": (B_org * P / (ms_per_step * 1e-3) / 1e9) / peak}
         # ---------------- ranking leg: maximin + arena order over 2P gladiators ---------
         obj2 = torch.cat([res.obj, res.obj.flip(0) * 1.0001])
-        constr = -0.3
+        constr = -worlds.GEN_PARAMS_6['coverage_constr_0']
         ms_mm = time_stage(lambda: eng.maximin(obj2, constr), 3)
         fit = eng.maximin(obj2, constr)
         ms_ord = time_stage(lambda: eng.arena_order(fit), 3)
         extras["ranking"] = {"n_gladiators": 2 * P, "maximin_ms": ms_mm, "arena_order_ms": ms_ord,
                              "fp64_gflops": 4.0 * (2 * P) * (2 * P - 1) / (ms_mm * 1e-3) / 1e9}
+        # ---------------- full generations on one GPU: select -> crossover -> mutate ->
+        # evaluate P children -> maximin over 2P -> order -> gather survivors ------------
+        gp = worlds.GEN_PARAMS_6
+        par_dna, par_obj = dna.clone(), res.obj.clone()
+        par_fit = eng.maximin(par_obj, constr)
+        n_gen = 5
+
+        def one_generation(g):
+            nonlocal par_dna, par_obj, par_fit
+            kids = eng.select_vary(par_dna, par_fit, gp['gamma'], 1234, g)
+            kid_obj = eng.evaluate(kids, detail=False).obj
+            glad_obj = torch.cat([par_obj, kid_obj])
+            alpha = min(1, g / gp['coverage_aging'])
+            c = (1 - alpha) * -gp['coverage_constr_0'] + alpha * -gp['coverage_constr_f']
+            gfit = eng.maximin(glad_obj, c)
+            order, _ = eng.arena_order(gfit)
+            par_dna, par_obj, par_fit = eng.gather_survivors(order, par_dna, kids, glad_obj, gfit)
+        one_generation(0)
+        torch.cuda.synchronize()
+        eng.set_timing(True)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for g in range(1, 1 + n_gen):
+            one_generation(g)
+        g1.record()
+        torch.cuda.synchronize()
+        ms_gen = g0.elapsed_time(g1) / n_gen
+        stage_names = ["path_costs", "coverage", "loop_closures", "maximin", "arena_order",
+                       "select", "crossover", "mutate"]
+        last = {n: eng.stage_ms(k) for k, n in enumerate(stage_names)}
+        eng.set_timing(False)
+        extras["generation"] = {"generations_per_s": 1000.0 / ms_gen, "ms_per_generation": ms_gen,
+                                "population": P, "gladiators": 2 * P, "generations_timed": n_gen,
+                                "includes": "lowVarSample + crossover + mutation/muterpolate/prune "
+                                            "+ evaluation of P children + maximin over 2P + stable "
+                                            "order + survivor gather; no host round trip",
+                                "last_generation_stage_ms": last,
+                                "mean_coverage_after": float((-par_obj[:, 0]).mean().item())}
+        if distributed:
+            from genetic_coverage_planning_b200.distributed import DistributedRanker
+            ranker = DistributedRanker(eng)
+            ranker.rank(res.obj, constr)
+            torch.cuda.synchronize()
+            barrier()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            ranker.rank(res.obj, constr)
+            r1.record()
+            torch.cuda.synchronize()
+            tms = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            extras["ranking_distributed"] = {
+                "n_gladiators": world_size * P, "ms": float(tms.item()),
+                "collective": "all-gather of objective records (16 B/organism) + all-gather of "
+                              "fits (8 B/organism) over NCCL; maximin rows sharded by rank"}
         # ---------------- end to end: host DNA in, host objectives out ------------------
         dna_h = dna.cpu().pin_memory()
         obj_h = torch.empty((P, 2), dtype=torch.float64).pin_memory()
