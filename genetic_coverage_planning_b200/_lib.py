@@ -71,6 +71,7 @@ SIGNATURES = {
                                   C.c_size_t, _vp]),
     "gcp_random_walks": (C.c_int, [_vp, _vp, _u32, _vp, C.c_int32, _u64, _u32, _vp]),
     "gcp_gather_survivors": (C.c_int, [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gcp_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     "gcp_launch_count": (C.c_uint64, [_vp]),
     "gcp_set_timing": (C.c_int, [_vp, C.c_int]),
     "gcp_stage_ms": (C.c_float, [_vp, C.c_int]),

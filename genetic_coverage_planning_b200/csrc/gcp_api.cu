@@ -430,6 +430,17 @@ int gcp_gather_survivors(gcp_ctx* c, const int32_t* order, uint32_t P, const int
                                    out_obj, out_fit, (cudaStream_t)stream);
 }
 
+int gcp_set_option(gcp_ctx* c, const char* name, int64_t value)
+{
+    if (!c || !name) return -1;
+    if (!strcmp(name, "rank_algo")) c->rank_algo = (int)value;
+    else if (!strcmp(name, "force_general")) c->force_general = (int)value;
+    else if (!strcmp(name, "cov_table")) c->cov_table = (int)value;
+    else if (!strcmp(name, "cov_maxpairs")) c->cov_maxpairs = (int)value;
+    else return gcp_fail(c, -1, "gcp_set_option: unknown option '%s'", name);
+    return 0;
+}
+
 uint64_t gcp_launch_count(gcp_ctx* c) { return c ? c->launches : 0; }
 
 int gcp_set_timing(gcp_ctx* c, int enabled)

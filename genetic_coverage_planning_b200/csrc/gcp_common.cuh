@@ -61,6 +61,7 @@ struct gcp_ctx {
     int cov_table = 0, cov_maxpairs = 0;
     int force_general = 0;   // testing: never take the pre-masked fast path
     int cov_detail = 1;      // 1: all six counters; 0: only what the objectives need
+    int rank_algo = 0;       // 0 auto, 1 O(N^2) dominance tiles, 2 sort-based (gcp_rank.cu)
 };
 
 int gcp_fail(gcp_ctx* ctx, int code, const char* fmt, ...);

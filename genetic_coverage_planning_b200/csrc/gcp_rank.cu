@@ -108,6 +108,20 @@ static void rank_grid(gcp_ctx* ctx, uint32_t rows, uint32_t n, uint32_t* itiles,
     *js = (n + per - 1) / per;
 }
 
+size_t sort_scratch_bytes(uint32_t n);
+int launch_maximin_sweep(gcp_ctx* ctx, const double2* sc, uint32_t n, uint32_t r0, uint32_t r1,
+                         double* fit, void* scratch, cudaStream_t st);
+int launch_arena_order_sort(gcp_ctx* ctx, const double* fit, uint32_t n, int32_t* order,
+                            uint8_t* nondom, void* scratch, cudaStream_t st);
+
+static inline size_t sc_bytes(uint32_t n) { return (((size_t)n * 16) + 255) & ~(size_t)255; }
+
+// rank_algo: 0 auto (sort-based for n >= 1024), 1 dominance-matrix tiles (O(N^2)), 2 sort-based
+static bool use_sort(gcp_ctx* ctx, uint32_t n)
+{
+    return ctx->rank_algo == 2 || (ctx->rank_algo == 0 && n >= 1024);
+}
+
 size_t rank_scratch_bytes(gcp_ctx* ctx, uint32_t n)
 {
     // sc [n] double2 | partial [256][n] worst case is too big: bound by the grid choice
@@ -117,7 +131,9 @@ size_t rank_scratch_bytes(gcp_ctx* ctx, uint32_t n)
     size_t b = (size_t)js * n * 8;             // maximin partials (also reused as u64 keys)
     if (b < (size_t)n * 8) b = (size_t)n * 8;
     size_t c = (size_t)n * 4;                  // ranks
-    return a + b + c + 1024;
+    size_t tiles = a + b + c + 1024;
+    size_t sorted = sc_bytes(n) + sort_scratch_bytes(n);
+    return tiles > sorted ? tiles : sorted;
 }
 
 int launch_maximin(gcp_ctx* ctx, const double* obj, uint32_t n, double constr, uint32_t r0,
@@ -131,6 +147,11 @@ int launch_maximin(gcp_ctx* ctx, const double* obj, uint32_t n, double constr, u
     double2* sc = reinterpret_cast<double2*>(scratch);
     double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + (size_t)n * 16);
     k_scale_obj<<<(n + 255) / 256, 256, 0, st>>>(obj, n, constr, sc, obj_sc);
+    if (use_sort(ctx, n)) {
+        ctx->launches++;
+        return launch_maximin_sweep(ctx, sc, n, r0, r1, fit,
+                                    reinterpret_cast<char*>(scratch) + sc_bytes(n), st);
+    }
     uint32_t itiles, js, per;
     const uint32_t rows = r1 - r0;
     rank_grid(ctx, rows, n, &itiles, &js, &per);
@@ -216,6 +237,9 @@ int launch_arena_order(gcp_ctx* ctx, const double* fit, uint32_t n, int32_t* ord
     if (n == 0) return 0;
     if (sb < rank_scratch_bytes(ctx, n)) return gcp_fail(ctx, -1, "arena_order: scratch too small");
     StageTimer tm(ctx, 4, st);
+    if (use_sort(ctx, n))
+        return launch_arena_order_sort(ctx, fit, n, order, nondom,
+                                       reinterpret_cast<char*>(scratch) + sc_bytes(n), st);
     unsigned long long* keys =
         reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(scratch) + (size_t)n * 16);
     uint32_t itiles, js, per;

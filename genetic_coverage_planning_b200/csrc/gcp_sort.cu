@@ -1,0 +1,395 @@
+// Sort-based ranking kernels (sm_100a):
+//   * stable LSD radix sort of (u64 key, u32 value) pairs           -> arena order, a-order
+//   * exact O(N log N) maximin fitness for two objectives            -> k_maximin_sweep
+//
+// Reference semantics (citations into /root/reference/src):
+//   geneticalgorithm.py:86-123  rackNstack: fit_i = max_{j!=i} min(sc0_i-sc0_j, sc1_i-sc1_j)
+//   gori_tools.py:232-236       sortBy -> argsort(fit), canonical stable order
+//
+// Why the sweep is bit-exact: fp64 subtraction is monotone in its
+// second operand, so with gladiators sorted by a = sc0 ascending, x_(k) = rn(a_i - a_(k))
+// is non-increasing in k and Y(k) = rn(b_i - min_{j<=k, j!=i} b_(j)) is non-decreasing;
+// max_j min(x_j, y_j) = max_{k != pos(i)} min(x_(k), Y(k)) and the maximum sits next to
+// the crossing, found by bisection.  Only differences of actual elements are evaluated.
+#include "gcp_common.cuh"
+#include <math_constants.h>
+
+#define FULL 0xffffffffu
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_NW = RS_THREADS / 32;
+constexpr int RS_ITEMS = 8;                          // keys per thread
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;       // 2048 keys per CTA
+constexpr int RS_BINS = 256;
+
+__device__ __forceinline__ unsigned long long f64_sort_key(double f)
+{
+    unsigned long long b = (unsigned long long)__double_as_longlong(f);
+    if (b == 0x8000000000000000ull) b = 0;                 // -0.0 == +0.0
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// keys[i] = order-preserving image of src[i*stride]; vals[i] = i
+__global__ void k_rs_make_keys(const double* __restrict__ src, uint32_t stride, uint32_t n,
+                               unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals,
+                               uint8_t* __restrict__ neg_flag /*optional: src < 0*/)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double f = src[(size_t)i * stride];
+    keys[i] = f64_sort_key(f);
+    vals[i] = i;
+    if (neg_flag) neg_flag[i] = f < 0.0 ? 1 : 0;
+}
+
+// Warp w of a CTA owns keys [tile0 + w*256, +256) in 8 rounds of 32 consecutive keys, so
+// (CTA, warp, round, lane) order == input order: ranks assigned in that order are stable.
+__global__ void __launch_bounds__(RS_THREADS)
+k_rs_hist(const unsigned long long* __restrict__ keys, uint32_t n, int shift,
+          uint32_t* __restrict__ hist /*[256][nblk]*/, uint32_t nblk)
+{
+    __shared__ uint32_t s_h[RS_BINS];
+    const int tid = threadIdx.x;
+    s_h[tid] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * RS_TILE;
+    #pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const uint32_t i = base + r * RS_THREADS + tid;
+        if (i < n) atomicAdd(&s_h[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)tid * nblk + blockIdx.x] = s_h[tid];
+}
+
+// exclusive scan of hist in (bin, block) order, one CTA
+__global__ void __launch_bounds__(1024)
+k_rs_scan(uint32_t* __restrict__ hist, uint32_t total)
+{
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_carry, s_tot;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t c0 = 0; c0 < total; c0 += 1024 * 4) {
+        uint32_t v[4], loc = 0;
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t i = c0 + tid * 4 + k;
+            v[k] = (i < total) ? hist[i] : 0u;
+            loc += v[k];
+        }
+        uint32_t inc = loc;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = s_w[lane];
+            uint32_t winc = w;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, winc, o);
+                if (lane >= o) winc += t;
+            }
+            s_w[lane] = winc - w;                       // exclusive warp offsets
+            if (lane == 31) s_tot = winc;
+        }
+        __syncthreads();
+        uint32_t run = s_carry + s_w[warp] + inc - loc;
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t i = c0 + tid * 4 + k;
+            if (i < total) hist[i] = run;
+            run += v[k];
+        }
+        __syncthreads();
+        if (tid == 0) s_carry += s_tot;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+k_rs_scatter(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals,
+             uint32_t n, int shift, const uint32_t* __restrict__ hist, uint32_t nblk,
+             unsigned long long* __restrict__ keys_out, uint32_t* __restrict__ vals_out)
+{
+    __shared__ uint32_t s_cnt[RS_NW][RS_BINS];          // per-warp digit counts -> bases
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < RS_NW * RS_BINS; i += RS_THREADS) (&s_cnt[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t wbase = blockIdx.x * RS_TILE + warp * (RS_ITEMS * 32);
+    unsigned long long k[RS_ITEMS];
+    uint32_t v[RS_ITEMS];
+    const uint32_t lt = (1u << lane) - 1u;
+    #pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const uint32_t i = wbase + r * 32 + lane;
+        const bool ok = i < n;
+        k[r] = ok ? keys[i] : ~0ull;
+        v[r] = ok ? vals[i] : 0u;
+        const uint32_t d = (uint32_t)(k[r] >> shift) & 255u;
+        const uint32_t act = __ballot_sync(FULL, ok);
+        if (ok) {
+            const uint32_t peers = __match_any_sync(act, d);
+            if ((peers & lt) == 0) s_cnt[warp][d] += __popc(peers);   // leader, warp-private row
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // digit `tid`: exclusive scan over the warps + global base of (digit, CTA)
+        uint32_t run = hist[(size_t)tid * nblk + blockIdx.x];
+        #pragma unroll
+        for (int w = 0; w < RS_NW; ++w) {
+            const uint32_t c = s_cnt[w][tid];
+            s_cnt[w][tid] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    #pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const uint32_t i = wbase + r * 32 + lane;
+        const bool ok = i < n;
+        const uint32_t d = (uint32_t)(k[r] >> shift) & 255u;
+        const uint32_t act = __ballot_sync(FULL, ok);
+        uint32_t peers = 0;
+        if (ok) {
+            peers = __match_any_sync(act, d);
+            const uint32_t pos = s_cnt[warp][d] + __popc(peers & lt);
+            keys_out[pos] = k[r];
+            vals_out[pos] = v[r];
+        }
+        __syncwarp();
+        if (ok && (peers & lt) == 0) s_cnt[warp][d] += __popc(peers);
+        __syncwarp();
+    }
+}
+
+static inline uint32_t rs_blocks(uint32_t n) { return (n + RS_TILE - 1) / RS_TILE; }
+
+// Sorts (keys, vals) in place (8 passes, ping-pong through the tmp buffers).
+static int radix_sort_pairs(gcp_ctx* ctx, unsigned long long* keys, uint32_t* vals, uint32_t n,
+                            unsigned long long* keys_tmp, uint32_t* vals_tmp, uint32_t* hist,
+                            cudaStream_t st)
+{
+    const uint32_t nblk = rs_blocks(n);
+    unsigned long long* kin = keys; unsigned long long* kout = keys_tmp;
+    uint32_t* vin = vals; uint32_t* vout = vals_tmp;
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = pass * 8;
+        k_rs_hist<<<nblk, RS_THREADS, 0, st>>>(kin, n, shift, hist, nblk);
+        k_rs_scan<<<1, 1024, 0, st>>>(hist, nblk * RS_BINS);
+        k_rs_scatter<<<nblk, RS_THREADS, 0, st>>>(kin, vin, n, shift, hist, nblk, kout, vout);
+        ctx->launches += 3;
+        unsigned long long* tk = kin; kin = kout; kout = tk;
+        uint32_t* tv = vin; vin = vout; vout = tv;
+    }
+    GCP_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// prefix (min1, argmin1 position, min2) of b along the a-sorted order; one CTA.
+//   rec[k] = {m1, m2}, arg[k] = sorted position of m1;  inv[perm[k]] = k; sa[k] = a[perm[k]]
+// ---------------------------------------------------------------------------------
+struct Min2 { double m1, m2; uint32_t i1; };
+
+__device__ __forceinline__ Min2 min2_combine(const Min2& L, const Min2& R)
+{
+    Min2 o;
+    if (L.m1 <= R.m1) { o.m1 = L.m1; o.i1 = L.i1; o.m2 = fmin(L.m2, R.m1); }
+    else              { o.m1 = R.m1; o.i1 = R.i1; o.m2 = fmin(L.m1, R.m2); }
+    return o;
+}
+
+__device__ __forceinline__ Min2 min2_shfl_up(const Min2& v, int o)
+{
+    Min2 r;
+    r.m1 = __shfl_up_sync(FULL, v.m1, o);
+    r.m2 = __shfl_up_sync(FULL, v.m2, o);
+    r.i1 = __shfl_up_sync(FULL, v.i1, o);
+    return r;
+}
+
+// sa[k] = a[perm[k]], sb[k] = b[perm[k]] (with -0.0 folded), inv[perm[k]] = k
+__global__ void k_gather_sorted(const double2* __restrict__ sc, const uint32_t* __restrict__ perm,
+                                uint32_t n, double* __restrict__ sa, double* __restrict__ sb,
+                                uint32_t* __restrict__ inv)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t p = perm[k];
+    const double2 s = sc[p];
+    sa[k] = s.x + 0.0;
+    sb[k] = s.y + 0.0;
+    inv[p] = k;
+}
+
+__global__ void __launch_bounds__(1024)
+k_prefix_min2(const double* __restrict__ sb, uint32_t n, double2* __restrict__ rec,
+              uint32_t* __restrict__ arg)
+{
+    __shared__ Min2 s_w[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t per = (n + 1023) / 1024;
+    const uint32_t b = min(n, tid * per), e = min(n, b + per);
+    Min2 loc; loc.m1 = CUDART_INF; loc.m2 = CUDART_INF; loc.i1 = 0xFFFFFFFFu;
+    #pragma unroll 8
+    for (uint32_t k = b; k < e; ++k) {
+        const double v = sb[k];
+        if (v < loc.m1) { loc.m2 = loc.m1; loc.m1 = v; loc.i1 = k; }
+        else if (v < loc.m2) loc.m2 = v;
+    }
+    Min2 inc = loc;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const Min2 t = min2_shfl_up(inc, o);
+        if (lane >= o) inc = min2_combine(t, inc);
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        Min2 w = s_w[lane];
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const Min2 t = min2_shfl_up(w, o);
+            if (lane >= o) w = min2_combine(t, w);
+        }
+        s_w[lane] = w;                                     // inclusive over warps
+    }
+    __syncthreads();
+    // exclusive prefix of this thread = (warps before) ++ (lanes before in this warp)
+    Min2 ex; ex.m1 = CUDART_INF; ex.m2 = CUDART_INF; ex.i1 = 0xFFFFFFFFu;
+    if (warp > 0) ex = s_w[warp - 1];
+    {
+        const Min2 prev = min2_shfl_up(inc, 1);
+        if (lane > 0) ex = min2_combine(ex, prev);
+    }
+    Min2 run = ex;
+    #pragma unroll 8
+    for (uint32_t k = b; k < e; ++k) {
+        const double v = sb[k];
+        if (v < run.m1) { run.m2 = run.m1; run.m1 = v; run.i1 = k; }
+        else if (v < run.m2) run.m2 = v;
+        rec[k] = make_double2(run.m1, run.m2);
+        arg[k] = run.i1;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_maximin_sweep(const double2* __restrict__ sc, uint32_t n, const double* __restrict__ sa,
+                const double2* __restrict__ rec, const uint32_t* __restrict__ arg,
+                const uint32_t* __restrict__ inv, uint32_t row_begin, uint32_t row_end,
+                double* __restrict__ fit)
+{
+    const uint32_t i = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= row_end) return;
+    const double2 me = sc[i];
+    const double a = me.x + 0.0, b = me.y + 0.0;
+    const uint32_t p = inv[i];
+    // largest k with x_(k) >= Y(k); -1 if none
+    int lo = -1, hi = (int)n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;                // hi >= 0 here, so the sum is >= 0
+        const double2 r = rec[mid];
+        const double pm = (arg[mid] == p) ? r.y : r.x;
+        const double x = __dsub_rn(a, sa[mid]);
+        const double y = __dsub_rn(b, pm);                 // b - inf = -inf for an empty prefix
+        if (x >= y) lo = mid; else hi = mid - 1;
+    }
+    double best = -CUDART_INF;
+    const int kl = (lo == (int)p) ? lo - 1 : lo;
+    const int kr = (lo + 1 == (int)p) ? lo + 2 : lo + 1;
+    #pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const int k = c ? kr : kl;
+        if (k >= 0 && k < (int)n) {
+            const double2 r = rec[k];
+            const double pm = (arg[k] == p) ? r.y : r.x;
+            const double x = __dsub_rn(a, sa[k]);
+            const double y = __dsub_rn(b, pm);
+            best = fmax(best, fmin(x, y));
+        }
+    }
+    fit[i] = best;
+}
+
+// ---------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t sort_scratch_bytes(uint32_t n)
+{
+    // keys x2, vals x2, hist, sa, sb, rec, arg, inv
+    return 2 * al256((size_t)n * 8) + 2 * al256((size_t)n * 4) +
+           al256((size_t)rs_blocks(n) * RS_BINS * 4) + 2 * al256((size_t)n * 8) +
+           al256((size_t)n * 16) + 2 * al256((size_t)n * 4) + 256;
+}
+
+struct SortScratch {
+    unsigned long long *keys, *keys_tmp;
+    uint32_t *vals, *vals_tmp, *hist, *arg, *inv;
+    double *sa, *sb;
+    double2* rec;
+};
+
+static SortScratch carve(void* base, uint32_t n)
+{
+    SortScratch s;
+    char* p = reinterpret_cast<char*>(base);
+    s.keys = reinterpret_cast<unsigned long long*>(p);      p += al256((size_t)n * 8);
+    s.keys_tmp = reinterpret_cast<unsigned long long*>(p);  p += al256((size_t)n * 8);
+    s.vals = reinterpret_cast<uint32_t*>(p);                p += al256((size_t)n * 4);
+    s.vals_tmp = reinterpret_cast<uint32_t*>(p);            p += al256((size_t)n * 4);
+    s.hist = reinterpret_cast<uint32_t*>(p);                p += al256((size_t)rs_blocks(n) * RS_BINS * 4);
+    s.sa = reinterpret_cast<double*>(p);                    p += al256((size_t)n * 8);
+    s.sb = reinterpret_cast<double*>(p);                    p += al256((size_t)n * 8);
+    s.rec = reinterpret_cast<double2*>(p);                  p += al256((size_t)n * 16);
+    s.arg = reinterpret_cast<uint32_t*>(p);                 p += al256((size_t)n * 4);
+    s.inv = reinterpret_cast<uint32_t*>(p);
+    return s;
+}
+
+// sc: dev double2 [n] (scaled objectives); fit rows [r0, r1) are written.
+int launch_maximin_sweep(gcp_ctx* ctx, const double2* sc, uint32_t n, uint32_t r0, uint32_t r1,
+                         double* fit, void* scratch, cudaStream_t st)
+{
+    SortScratch s = carve(scratch, n);
+    k_rs_make_keys<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const double*>(sc), 2, n,
+                                                    s.keys, s.vals, nullptr);
+    ctx->launches++;
+    int r = radix_sort_pairs(ctx, s.keys, s.vals, n, s.keys_tmp, s.vals_tmp, s.hist, st);
+    if (r) return r;
+    k_gather_sorted<<<(n + 255) / 256, 256, 0, st>>>(sc, s.vals, n, s.sa, s.sb, s.inv);
+    k_prefix_min2<<<1, 1024, 0, st>>>(s.sb, n, s.rec, s.arg);
+    const uint32_t rows = r1 - r0;
+    k_maximin_sweep<<<(rows + 255) / 256, 256, 0, st>>>(sc, n, s.sa, s.rec, s.arg, s.inv, r0, r1, fit);
+    ctx->launches += 3;
+    GCP_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+__global__ void k_copy_order(const uint32_t* __restrict__ vals, uint32_t n, int32_t* __restrict__ order)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) order[i] = (int32_t)vals[i];
+}
+
+int launch_arena_order_sort(gcp_ctx* ctx, const double* fit, uint32_t n, int32_t* order,
+                            uint8_t* nondom, void* scratch, cudaStream_t st)
+{
+    SortScratch s = carve(scratch, n);
+    k_rs_make_keys<<<(n + 255) / 256, 256, 0, st>>>(fit, 1, n, s.keys, s.vals, nondom);
+    ctx->launches++;
+    int r = radix_sort_pairs(ctx, s.keys, s.vals, n, s.keys_tmp, s.vals_tmp, s.hist, st);
+    if (r) return r;
+    k_copy_order<<<(n + 255) / 256, 256, 0, st>>>(s.vals, n, order);
+    ctx->launches++;
+    GCP_CUDA(ctx, cudaGetLastError());
+    return 0;
+}

@@ -345,6 +345,9 @@ class FitnessEngine(object):
         return out_dna, out_obj, out_fit
 
     # ------------------------------------------------------------------
+    def set_option(self, name, value):
+        self._check(self.lib.gcp_set_option(self.ctx, name.encode(), int(value)))
+
     def launch_count(self):
         return int(self.lib.gcp_launch_count(self.ctx))
 

@@ -198,6 +198,12 @@ int gcp_gather_survivors(gcp_ctx* ctx, const int32_t* order_dev, uint32_t n_org,
                          const double* glad_obj_dev, const double* glad_fit_dev,
                          int32_t* out_dna_dev, double* out_obj_dev, double* out_fit_dev, void* stream);
 
+/* ---- tuning / testing knobs (defaults are right for production) ---------------------
+ * "rank_algo": 0 auto, 1 O(N^2) dominance-matrix tiles, 2 sort-based O(N log N) (both exact);
+ * "force_general": never take the pre-masked coverage fast path; "cov_table", "cov_maxpairs":
+ * shared-memory sizing of the coverage kernels (0 = auto). */
+int gcp_set_option(gcp_ctx* ctx, const char* name, int64_t value);
+
 /* ---- introspection ---------------------------------------------------------------- */
 /* kernel launch counter since gcp_create (for bench.py's gpu_launches). */
 uint64_t gcp_launch_count(gcp_ctx* ctx);

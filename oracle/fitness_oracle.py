@@ -316,3 +316,58 @@ def low_var_sample_indices(fitnesses, pressure, r):
             c = c + w[i]
         out.append(i)
     return np.array(out)
+
+
+def rack_n_stack_sweep(objs, gen_num, gen_params):
+    """O(N log N) evaluation of the same maximin fitness for two objectives, used to pin the
+    algorithm of the CUDA kernel k_maximin_sweep on the CPU.
+
+    fit_i = max_{j != i} min(rn(a_i - a_j), rn(b_i - b_j)).  With gladiators sorted by a
+    ascending, x_(k) = rn(a_i - a_(k)) is non-increasing in k and
+    Y(k) = rn(b_i - min_{j <= k, j != i} b_(j)) is non-decreasing, and
+    max_j min(x_j, y_j) = max_{k != pos(i)} min(x_(k), Y(k)); the maximum sits next to the
+    crossing, found by bisection.  Only differences of actual elements are evaluated, so the
+    result is bit-identical to the double loop (geneticalgorithm.py:109-120)."""
+    sc = scaled_objectives(objs, gen_num, gen_params)
+    n = len(sc)
+    a, b = sc[:, 0] + 0.0, sc[:, 1] + 0.0          # +0.0 folds -0.0 into +0.0
+    perm = np.argsort(a, kind='stable')
+    sa, sb = a[perm], b[perm]
+    inv = np.empty(n, dtype=np.int64)
+    inv[perm] = np.arange(n)
+    # prefix (min1, argmin1, min2) of b along the sorted order; min2 excludes argmin1
+    m1 = np.empty(n); i1 = np.empty(n, dtype=np.int64); m2 = np.empty(n)
+    cm1, ci1, cm2 = np.inf, -1, np.inf
+    for k in range(n):
+        v = sb[k]
+        if v < cm1:
+            cm1, ci1, cm2 = v, k, cm1
+        elif v < cm2:
+            cm2 = v
+        m1[k], i1[k], m2[k] = cm1, ci1, cm2
+    fit = np.empty(n)
+    with np.errstate(invalid='ignore'):
+        for i in range(n):
+            p = inv[i]
+
+            def xy(k):
+                pm = m2[k] if i1[k] == p else m1[k]
+                return a[i] - sa[k], b[i] - pm          # b_i - inf = -inf for an empty prefix
+
+            lo, hi = -1, n - 1                          # largest k with x_(k) >= Y(k), or -1
+            while lo < hi:
+                mid = (lo + hi + 1) >> 1
+                x, y = xy(mid)
+                if x >= y:
+                    lo = mid
+                else:
+                    hi = mid - 1
+            best = -np.inf
+            kl = lo - 1 if lo == p else lo
+            kr = lo + 2 if lo + 1 == p else lo + 1
+            for k in (kl, kr):
+                if 0 <= k < n and k != p:
+                    x, y = xy(k)
+                    best = max(best, min(x, y))
+            fit[i] = best
+    return fit

@@ -145,42 +145,75 @@ def test_shard_equivalence_and_host_path(eng_big, golden_dir):
     assert np.array_equal(flags_h.numpy(), full.flags.cpu().numpy())
 
 
-def test_maximin_and_order_golden(eng_big, golden_dir):
+@pytest.mark.parametrize("algo", [1, 2])      # 1 = O(N^2) dominance tiles, 2 = sort-based sweep
+def test_maximin_and_order_golden(eng_big, golden_dir, algo):
     import torch
     import ref_shim
     z = np.load(os.path.join(golden_dir, "rank.npz"))
     _, _, _, gp = ref_shim.driver_params(6)
-    for gen in (0, 17, 80, 200):
-        constr = fo.coverage_constraint(gen, gp)
-        fit, sc = eng_big.maximin(torch.from_numpy(z['objs']), constr, return_scaled=True)
-        assert np.array_equal(sc.cpu().numpy(), z['sc_gen%d' % gen])
-        assert np.array_equal(fit.cpu().numpy(), z['fit_gen%d' % gen])
-        order, nondom = eng_big.arena_order(fit)
-        assert np.array_equal(order.cpu().numpy(), z['order_gen%d' % gen])
-        assert np.array_equal(nondom.cpu().numpy() == 1, z['fit_gen%d' % gen] < 0)
-    fit = eng_big.maximin(torch.from_numpy(z['syn_objs']), fo.coverage_constraint(40, gp))
-    assert np.array_equal(fit.cpu().numpy(), z['syn_fit_gen40'])
+    eng_big.set_option("rank_algo", algo)
+    try:
+        for gen in (0, 17, 80, 200):
+            constr = fo.coverage_constraint(gen, gp)
+            fit, sc = eng_big.maximin(torch.from_numpy(z['objs']), constr, return_scaled=True)
+            assert np.array_equal(sc.cpu().numpy(), z['sc_gen%d' % gen])
+            assert np.array_equal(fit.cpu().numpy(), z['fit_gen%d' % gen])
+            order, nondom = eng_big.arena_order(fit)
+            assert np.array_equal(order.cpu().numpy(), z['order_gen%d' % gen])
+            assert np.array_equal(nondom.cpu().numpy() == 1, z['fit_gen%d' % gen] < 0)
+        fit = eng_big.maximin(torch.from_numpy(z['syn_objs']), fo.coverage_constraint(40, gp))
+        assert np.array_equal(fit.cpu().numpy(), z['syn_fit_gen40'])
+    finally:
+        eng_big.set_option("rank_algo", 0)
 
 
-def test_maximin_vs_oracle_large_with_ties(eng_big):
+@pytest.mark.parametrize("algo", [0, 1, 2])
+@pytest.mark.parametrize("n", [2, 3, 257, 5000, 20011])
+def test_maximin_vs_oracle_large_with_ties(eng_big, algo, n):
     import torch
     import ref_shim
     _, _, _, gp = ref_shim.driver_params(6)
-    rs = np.random.RandomState(2)
-    n = 5000
+    rs = np.random.RandomState(2 + n)
     objs = np.stack([-rs.randint(0, 300, n) / 300.0, rs.rand(n) * 3 + 0.5], 1)
     objs[rs.rand(n) < 0.5, 0] = 0.0                      # infeasible organisms tie (F15)
-    objs[100:140] = objs[200:240]                        # exact duplicates
-    for gen in (0, 50):
-        constr = fo.coverage_constraint(gen, gp)
-        want = fo.rack_n_stack(objs, gen, gp)
-        fit = eng_big.maximin(torch.from_numpy(objs), constr)
-        assert np.array_equal(fit.cpu().numpy(), want)
-        order, _ = eng_big.arena_order(fit)
-        assert np.array_equal(order.cpu().numpy(), fo.arena_order(want))
-        # row-sharded evaluation (multi-GPU layout) gives the same rows
-        part = eng_big.maximin(torch.from_numpy(objs), constr, row_range=(1234, 3456))
-        assert np.array_equal(part.cpu().numpy()[1234:3456], want[1234:3456])
+    if n >= 5000:
+        objs[100:140] = objs[200:240]                    # exact duplicates
+        objs[300:400, 1] = objs[300, 1]                  # ties in the second objective
+    if n > 3:
+        objs[-1, 0] = -0.0                               # signed zero must not matter
+    eng_big.set_option("rank_algo", algo)
+    try:
+        for gen in (0, 50):
+            constr = fo.coverage_constraint(gen, gp)
+            want = fo.rack_n_stack(objs, gen, gp)
+            fit = eng_big.maximin(torch.from_numpy(objs), constr)
+            assert np.array_equal(fit.cpu().numpy(), want)
+            order, _ = eng_big.arena_order(fit)
+            assert np.array_equal(order.cpu().numpy(), fo.arena_order(want))
+            # row-sharded evaluation (multi-GPU layout) gives the same rows
+            lo, hi = n // 4, max(n // 4 + 1, (2 * n) // 3)
+            part = eng_big.maximin(torch.from_numpy(objs), constr, row_range=(lo, hi))
+            assert np.array_equal(part.cpu().numpy()[lo:hi], want[lo:hi])
+    finally:
+        eng_big.set_option("rank_algo", 0)
+
+
+def test_radix_order_is_stable_on_adversarial_keys(eng_big):
+    """arena order = stable sort by (fit, index): negative / positive / zero / huge / tiny fits,
+    long runs of equal keys, n not a multiple of the sort tile."""
+    import torch
+    rs = np.random.RandomState(11)
+    n = 70001
+    fit = np.concatenate([rs.randn(20000) * 1e-3, rs.randn(20000) * 1e6, np.zeros(5000),
+                          -np.zeros(5000), np.full(10000, -0.25), rs.randint(-3, 3, 10001) * 0.5])
+    assert len(fit) == n
+    rs.shuffle(fit)
+    for algo in (1, 2):
+        eng_big.set_option("rank_algo", algo)
+        order, nondom = eng_big.arena_order(torch.from_numpy(fit))
+        eng_big.set_option("rank_algo", 0)
+        assert np.array_equal(order.cpu().numpy(), np.argsort(fit, kind='stable'))
+        assert np.array_equal(nondom.cpu().numpy() == 1, fit < 0)
 
 
 # ---------------------------------------------------------------------------------------

@@ -76,3 +76,22 @@ def test_rank(golden_dir, world_big):
     assert np.array_equal(fo.rack_n_stack(z['syn_objs'], 40, gp), z['syn_fit_gen40'])
     for r, idx in zip(z['lowvar_r'], z['lowvar_idx']):
         assert np.array_equal(fo.low_var_sample_indices(z['fit_gen17'], float(z['gamma']), r), idx)
+
+
+def test_sweep_maximin_equals_double_loop(golden_dir):
+    """The O(N log N) restatement (pins the algorithm of k_maximin_sweep)
+    is bit-identical to the reference's double loop: golden fits, heavy ties, duplicates."""
+    z = _load(golden_dir, "rank.npz")
+    _, _, _, gp = __import__("ref_shim").driver_params(6)
+    for gen in (0, 17, 80, 200):
+        assert np.array_equal(fo.rack_n_stack_sweep(z['objs'], gen, gp), z['fit_gen%d' % gen])
+    assert np.array_equal(fo.rack_n_stack_sweep(z['syn_objs'], 40, gp), z['syn_fit_gen40'])
+    for seed, n in enumerate([2, 3, 17, 400, 1500]):
+        rs = np.random.RandomState(seed)
+        objs = np.stack([-rs.randint(0, 30, n) / 30.0, rs.randint(0, 50, n) / 7.0 + 0.5], 1)
+        objs[rs.rand(n) < 0.5, 0] = 0.0                      # infeasible organisms tie (F15)
+        if n > 300:
+            objs[100:140] = objs[200:240]                    # exact duplicates
+        for gen in (0, 50, 100):
+            assert np.array_equal(fo.rack_n_stack_sweep(objs, gen, gp),
+                                  fo.rack_n_stack(objs, gen, gp))
