@@ -98,6 +98,14 @@ int gcp_upload_graph(gcp_ctx* c, uint32_t N, uint32_t E, const uint32_t* row_ptr
     if ((r = upload(c, &c->t.xy, xy, (size_t)N))) return r;           // int2 = 2 x int32
     if ((r = upload(c, &c->t.xover, xover, N))) return r;
     c->t.N = N; c->t.E = E;
+    c->h_row_ptr.assign(row_ptr, row_ptr + N + 1);
+    c->h_col.assign(col, col + E);
+    c->max_degree = 0;
+    for (uint32_t i = 0; i < N; ++i) {
+        if (row_ptr[i + 1] < row_ptr[i]) return gcp_fail(c, -1, "row_ptr not monotone at %u", i);
+        const uint32_t d = row_ptr[i + 1] - row_ptr[i];
+        if (d > c->max_degree) c->max_degree = d;
+    }
     c->have_graph = true;
     return 0;
 }
@@ -117,6 +125,19 @@ int gcp_upload_edges(gcp_ctx* c, const double* edge_cost, const double* edge_the
     int r;
     if ((r = upload(c, &c->t.edge_cost, edge_cost, EN))) return r;     // double2
     if ((r = upload(c, &c->t.edge_theta, edge_theta, c->t.E))) return r;
+    c->t.adj8 = nullptr;
+    if (c->max_degree <= 8) {   // packed adjacency for the random walks: one 64-B record per node
+        std::vector<uint2> adj((size_t)c->t.N * 8, make_uint2(0xFFFFFFFFu, 0u));
+        for (uint32_t i = 0; i < c->t.N; ++i)
+            for (uint32_t e = c->h_row_ptr[i]; e < c->h_row_ptr[i + 1]; ++e) {
+                const float th = (float)edge_theta[e];
+                uint32_t bits; memcpy(&bits, &th, 4);
+                adj[(size_t)i * 8 + (e - c->h_row_ptr[i])] = make_uint2(c->h_col[e], bits);
+            }
+        if ((r = upload(c, &c->t.adj8, adj.data(), adj.size()))) return r;
+    }
+    c->h_row_ptr.clear(); c->h_row_ptr.shrink_to_fit();
+    c->h_col.clear(); c->h_col.shrink_to_fit();
     {   // device layout: one u32 per edge (first | count<<28) and one uint2 per sub-tile
         if (n_sub >= (1ull << 28)) return gcp_fail(c, -1, "too many sub-tiles");
         std::vector<uint32_t> info(EN);
@@ -362,6 +383,8 @@ int gcp_set_vary_params(gcp_ctx* c, const gcp_vary_params* p)
         return gcp_fail(c, -1, "num_muterpolations must be in [0,64]");
     if (p->path_memory < 0 || p->path_memory > 16) return gcp_fail(c, -1, "path_memory must be in [0,16]");
     if (!(p->log_scale_weight > 0)) return gcp_fail(c, -1, "log_scale_weight must be > 0");
+    if (c->have_graph && c->max_degree > 32)
+        return gcp_fail(c, -3, "variation kernels support out-degree <= 32, graph has %u", c->max_degree);
     c->vary = *p;
     c->have_vary = true;
     return 0;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 #include "../../include/gcp.h"
 
 #define GCP_NUM_STAGES 8
@@ -18,6 +19,7 @@ struct GcpTables {
     // edges (mappy.py:274-328): ids [0,E) real, [E,E+N) null edge of node id-E
     const double2*  edge_cost; // {dist, turn}
     const double*   edge_theta;
+    const uint2*    adj8;      // [N][8] {col, float bits of theta}, col = ~0 for empty; NULL if max degree > 8
     const uint32_t* sub_info;  // [E+N] first sub-tile (28 bits) | count << 28
     const uint2*    sub_desc;  // [S] {block id, (offset128<<4)|qmask}
     const uint4*    tile;      // quarters: 8 x uint4 = 16 rows of 64 px
@@ -44,6 +46,8 @@ struct gcp_ctx {
     bool have_graph = false, have_edges = false, have_map = false, have_params = false;
     bool have_masked = false;
     uint64_t n_sub = 0, n_quarters = 0, n_gray = 0;
+    uint32_t max_degree = 0;
+    std::vector<uint32_t> h_row_ptr, h_col;   // host copies until the edges are uploaded
     uint64_t launches = 0;
     int max_smem_optin = 0;
     int num_sms = 0;

@@ -16,9 +16,7 @@
 #include "gcp_common.cuh"
 
 #define FULL 0xffffffffu
-constexpr int VARY_THREADS = 128;
 constexpr int MAX_MUT_POINTS = 64;
-constexpr int PATH_MEM_MAX = 16;
 
 // ------------------------------------------------------------------ Philox4x32-10
 struct Philox {
@@ -66,7 +64,8 @@ struct Philox {
     __device__ int randint(int n) { return n <= 1 ? 0 : min(n - 1, (int)(uniform() * (float)n)); }
 };
 
-enum { STREAM_ORG = 1, STREAM_XOVER = 2, STREAM_MUT = 3, STREAM_INIT = 4 };
+enum { STREAM_ORG = 1, STREAM_XOVER = 2, STREAM_MUT = 3, STREAM_INIT = 4, STREAM_MUTERP = 5 };
+__device__ __forceinline__ uint32_t stream_id(uint32_t stream, uint32_t salt) { return stream | (salt << 8); }
 
 struct VaryParams {
     int A, L;
@@ -74,30 +73,99 @@ struct VaryParams {
     float xover_prob, mut_prob, muterp_prob, sub_prob, inv_sigma;
 };
 
-__device__ __forceinline__ int valid_len(const int32_t* r, int L)
+// All row-level routines below are WARP-COOPERATIVE: one warp owns one agent row held in
+// shared memory, every lane carries the same Philox state and takes the same branches
+// (control flow is warp-uniform), and the lanes split the data-parallel parts (adjacency
+// slots of a walk step, match counting, copies, compaction).
+
+__device__ __forceinline__ int w_valid_len(const int32_t* r, int L, int lane)
 {
-    int n = 0;
-    while (n < L && r[n] != -1) ++n;
-    return n;
+    for (int i0 = 0; i0 < L; i0 += 32) {
+        const int i = i0 + lane;
+        const uint32_t m = __ballot_sync(FULL, i < L && r[i] == -1);
+        if (m) return i0 + __ffs(m) - 1;
+    }
+    return L;
 }
 
-__device__ __forceinline__ bool is_edge(const GcpTables& t, int a, int b)
+// lane e: the e-th out-neighbour of `node`, or ~0
+__device__ __forceinline__ uint32_t w_nbr(const GcpTables& t, int node, int lane)
 {
-    for (uint32_t e = t.row_ptr[a]; e < t.row_ptr[a + 1]; ++e)
-        if ((int)t.col[e] == b) return true;
-    return false;
+    if (t.adj8) {
+        const uint2 a = __ldg(t.adj8 + (size_t)node * 8 + (lane & 7));
+        return lane < 8 ? a.x : 0xFFFFFFFFu;
+    }
+    const uint32_t lo = __ldg(t.row_ptr + node), hi = __ldg(t.row_ptr + node + 1);
+    return (lo + lane < hi) ? __ldg(t.col + lo + lane) : 0xFFFFFFFFu;
 }
 
 // pathmaker.py:188-213.  r[pos] is the current node; appends up to n_steps nodes (stops at
-// L).  The no-return memory is the last `path_memory` nodes of the running path, which
-// never reaches below row index mem_floor.  Returns the index of the last node written.
-__device__ int walk(const GcpTables& t, const VaryParams& vp, int32_t* r, int pos, int n_steps,
-                    int mem_floor, Philox& rng)
+// L).  The no-return memory is the last `path_memory` nodes of the running path, never
+// reaching below row index mem_floor: that is just r[max(mem_floor, pos-mem+1) .. pos].
+// Lane e handles the e-th out-edge of the current node.  Returns the last index written.
+__device__ int w_walk(const GcpTables& t, const VaryParams& vp, int32_t* r, int pos, int n_steps,
+                      int mem_floor, Philox& rng, int lane)
 {
     const float PI = 3.14159265358979f;
     const float heading = rng.uniform() * 2.0f * PI - PI;            // :190, never updated
-    int hist[PATH_MEM_MAX];
+    const float k2 = -0.5f * vp.inv_sigma * vp.inv_sigma;
+    const int W = t.adj8 ? 8 : 32;                                   // lanes that can hold an edge
+    int cur = r[pos];
+    for (int s = 0; s < n_steps && pos + 1 < vp.L; ++s) {
+        uint32_t c = 0xFFFFFFFFu;
+        float th = 0.f;
+        if (t.adj8) {                                                // one 64-B record per node
+            const uint2 a = __ldg(t.adj8 + (size_t)cur * 8 + (lane & 7));
+            if (lane < 8) { c = a.x; th = __uint_as_float(a.y); }
+        } else {
+            const uint32_t lo = __ldg(t.row_ptr + cur), hi = __ldg(t.row_ptr + cur + 1);
+            if (lo + lane < hi) { c = __ldg(t.col + lo + lane); th = (float)__ldg(t.edge_theta + lo + lane); }
+        }
+        const bool valid = c != 0xFFFFFFFFu;
+        int nxt = cur;
+        if (__any_sync(FULL, valid)) {
+            float ang = th - heading;                                // assignWeights :179-181
+            ang -= 2.0f * PI * floorf((ang + PI) * (0.5f / PI));
+            const float w = valid ? __expf(k2 * ang * ang) : 0.f;
+            bool seen = false;
+            for (int q = max(mem_floor, pos - vp.path_memory + 1); q <= pos; ++q)
+                seen |= ((uint32_t)r[q] == c);
+            const float wf = (valid && !seen) ? w : 0.f;
+            float ia = w, ifr = wf;                                  // inclusive scans in edge order
+            for (int o = 1; o < W; o <<= 1) {
+                const float va = __shfl_up_sync(FULL, ia, o), vf = __shfl_up_sync(FULL, ifr, o);
+                if (lane >= o) { ia += va; ifr += vf; }
+            }
+            const float tot_all = __shfl_sync(FULL, ia, W - 1), tot_fresh = __shfl_sync(FULL, ifr, W - 1);
+            const bool use_fresh = tot_fresh > 0.f;                  // :199-207
+            const float u = rng.uniform() * (use_fresh ? tot_fresh : tot_all);
+            const bool elig = valid && (!use_fresh || !seen);
+            const uint32_t hit = __ballot_sync(FULL, elig && u < (use_fresh ? ifr : ia));
+            const uint32_t em = __ballot_sync(FULL, elig);
+            const int src = hit ? (__ffs(hit) - 1) : (31 - __clz(em));
+            nxt = (int)__shfl_sync(FULL, c, src);
+        }
+        ++pos;
+        if (lane == 0) r[pos] = nxt;
+        __syncwarp();
+        cur = nxt;
+    }
+    return pos;
+}
+
+// Thread-level walk (one thread = one row in GLOBAL memory), same rule as w_walk.  Used
+// where many rows walk at once (mutation tails, initial population): 32 independent chains
+// per warp hide the dependent adjacency loads, and nothing is replicated across lanes.
+constexpr int PATH_MEM_MAX = 16;
+
+__device__ int t_walk(const GcpTables& t, const VaryParams& vp, int32_t* r, int pos, int n_steps,
+                      int mem_floor, Philox& rng)
+{
+    const float PI = 3.14159265358979f;
+    const float heading = rng.uniform() * 2.0f * PI - PI;            // :190, never updated
+    const float k2 = -0.5f * vp.inv_sigma * vp.inv_sigma;
     const int mem = min(vp.path_memory, PATH_MEM_MAX);
+    int hist[PATH_MEM_MAX];
     #pragma unroll
     for (int k = 0; k < PATH_MEM_MAX; ++k) {
         const int idx = pos - k;
@@ -105,49 +173,204 @@ __device__ int walk(const GcpTables& t, const VaryParams& vp, int32_t* r, int po
     }
     int cur = r[pos];
     for (int s = 0; s < n_steps && pos + 1 < vp.L; ++s) {
-        const uint32_t lo = t.row_ptr[cur], hi = t.row_ptr[cur + 1];
+        uint32_t c[8];
+        float w[8];
+        int deg = 0;
+        uint32_t lo = 0;
+        if (t.adj8) {
+            const uint4* rec = reinterpret_cast<const uint4*>(t.adj8 + (size_t)cur * 8);
+            #pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const uint4 q = __ldg(rec + h);
+                c[2 * h] = q.x; w[2 * h] = __uint_as_float(q.y);
+                c[2 * h + 1] = q.z; w[2 * h + 1] = __uint_as_float(q.w);
+            }
+            deg = 8;
+        } else {
+            lo = __ldg(t.row_ptr + cur);
+            deg = (int)(__ldg(t.row_ptr + cur + 1) - lo);
+        }
         int nxt = cur;
-        if (hi > lo) {
+        if (deg > 0) {
             float tot_all = 0.f, tot_fresh = 0.f;
-            for (uint32_t e = lo; e < hi; ++e) {
-                float ang = (float)t.edge_theta[e] - heading;        // assignWeights :179-181
-                ang -= 2.0f * PI * floorf((ang + PI) * (0.5f / PI));
-                const float w = __expf(-0.5f * ang * ang * vp.inv_sigma * vp.inv_sigma);
-                const int c = (int)t.col[e];
-                bool seen = false;
+            uint32_t seen_mask = 0;
+            if (t.adj8) {
                 #pragma unroll
-                for (int k = 0; k < PATH_MEM_MAX; ++k) seen |= (hist[k] == c);
-                tot_all += w;
-                if (!seen) tot_fresh += w;
-            }
-            const bool use_fresh = tot_fresh > 0.f;                  // :199-207
-            const float u = rng.uniform() * (use_fresh ? tot_fresh : tot_all);
-            float acc = 0.f;
-            nxt = -1;
-            int last_ok = -1;
-            for (uint32_t e = lo; e < hi; ++e) {
-                const int c = (int)t.col[e];
-                bool seen = false;
-                if (use_fresh) {
+                for (int e = 0; e < 8; ++e) {
+                    const bool valid = c[e] != 0xFFFFFFFFu;
+                    float ang = w[e] - heading;                      // assignWeights :179-181
+                    ang -= 2.0f * PI * floorf((ang + PI) * (0.5f / PI));
+                    w[e] = valid ? __expf(k2 * ang * ang) : 0.f;
+                    bool seen = !valid;
                     #pragma unroll
-                    for (int k = 0; k < PATH_MEM_MAX; ++k) seen |= (hist[k] == c);
+                    for (int k = 0; k < PATH_MEM_MAX; ++k) seen |= (hist[k] == (int)c[e]);
+                    seen_mask |= (seen ? 1u : 0u) << e;
+                    tot_all += w[e];
+                    if (!seen) tot_fresh += w[e];
                 }
-                if (seen) continue;
-                float ang = (float)t.edge_theta[e] - heading;
-                ang -= 2.0f * PI * floorf((ang + PI) * (0.5f / PI));
-                acc += __expf(-0.5f * ang * ang * vp.inv_sigma * vp.inv_sigma);
-                last_ok = c;
-                if (u < acc) { nxt = c; break; }
+                const bool use_fresh = tot_fresh > 0.f;              // :199-207
+                const float u = rng.uniform() * (use_fresh ? tot_fresh : tot_all);
+                float acc = 0.f;
+                int last_ok = -1;
+                nxt = -1;
+                #pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const bool valid = c[e] != 0xFFFFFFFFu;
+                    const bool skip = !valid || (use_fresh && ((seen_mask >> e) & 1u));
+                    if (!skip && nxt < 0) {
+                        acc += w[e];
+                        last_ok = (int)c[e];
+                        if (u < acc) nxt = (int)c[e];
+                    }
+                }
+                if (nxt < 0) nxt = (last_ok >= 0) ? last_ok : cur;
+            } else {
+                for (int e = 0; e < deg; ++e) {
+                    float ang = (float)__ldg(t.edge_theta + lo + e) - heading;
+                    ang -= 2.0f * PI * floorf((ang + PI) * (0.5f / PI));
+                    const float ww = __expf(k2 * ang * ang);
+                    const int cc = (int)__ldg(t.col + lo + e);
+                    bool seen = false;
+                    #pragma unroll
+                    for (int k = 0; k < PATH_MEM_MAX; ++k) seen |= (hist[k] == cc);
+                    tot_all += ww;
+                    if (!seen) tot_fresh += ww;
+                }
+                const bool use_fresh = tot_fresh > 0.f;
+                const float u = rng.uniform() * (use_fresh ? tot_fresh : tot_all);
+                float acc = 0.f;
+                int last_ok = -1;
+                nxt = -1;
+                for (int e = 0; e < deg; ++e) {
+                    const int cc = (int)__ldg(t.col + lo + e);
+                    bool seen = false;
+                    if (use_fresh) {
+                        #pragma unroll
+                        for (int k = 0; k < PATH_MEM_MAX; ++k) seen |= (hist[k] == cc);
+                    }
+                    if (seen) continue;
+                    float ang = (float)__ldg(t.edge_theta + lo + e) - heading;
+                    ang -= 2.0f * PI * floorf((ang + PI) * (0.5f / PI));
+                    acc += __expf(k2 * ang * ang);
+                    last_ok = cc;
+                    if (u < acc) { nxt = cc; break; }
+                }
+                if (nxt < 0) nxt = (last_ok >= 0) ? last_ok : cur;
             }
-            if (nxt < 0) nxt = (last_ok >= 0) ? last_ok : cur;
         }
         #pragma unroll
         for (int k = PATH_MEM_MAX - 1; k > 0; --k) hist[k] = (k < mem) ? hist[k - 1] : -2;
-        hist[0] = nxt;
+        hist[0] = (mem > 0) ? nxt : -2;
         r[++pos] = nxt;
         cur = nxt;
     }
     return pos;
+}
+
+// Second half of the constructor variation of one row (geneticalgorithm.py:163-168):
+// muterpolate (:270-309), pruneUTurns (:346-357).  s_tmp: 128 ints of warp scratch.
+// (The first half, mutation :251-268, is k_mutation_walks.)
+__device__ int w_post_mutate(const GcpTables& t, const VaryParams& vp, int32_t* r, int len,
+                             int32_t* s_tmp, bool do_mp, Philox& rng, int lane)
+{
+    const int L = vp.L;
+    if (do_mp && len - (vp.srch_dist + 3) > 0) {                       // muterpolate
+        const int np_ = min(vp.num_muterp, MAX_MUT_POINTS);
+        const int range = len - (vp.srch_dist + 3);
+        int32_t* raw = s_tmp;
+        int32_t* pts = s_tmp + MAX_MUT_POINTS;
+        for (int q = 0; q < np_; ++q) {                                // choice with replacement
+            const int v = rng.randint(range);
+            if (lane == 0) raw[q] = v;
+        }
+        __syncwarp();
+        for (int q = lane; q < np_; q += 32) {                         // rank sort, descending
+            const int v = raw[q];
+            int rank = 0;
+            for (int p = 0; p < np_; ++p) { const int o = raw[p]; rank += (o > v) || (o == v && p < q); }
+            pts[rank] = v;
+        }
+        __syncwarp();
+        int arr_len = L;                                               // np.delete shrinks the padded row
+        const int W = t.adj8 ? 8 : 32;
+        for (int q = 0; q < np_; ++q) {
+            const int idx1 = pts[q];
+            const uint32_t n1 = w_nbr(t, r[idx1], lane);               // lane e: e-th out-neighbour of pt1
+            for (int idx2 = idx1 + vp.srch_dist + 1; idx2 > idx1 + 1; --idx2) {
+                if (!(rng.uniform() < vp.sub_prob)) continue;
+                if (idx2 >= arr_len) break;                            // IndexError -> break :289
+                int pt2 = r[idx2];
+                if (pt2 < 0) pt2 += (int)t.N;                          // numpy index -1 (SURVEY F4)
+                if (__any_sync(FULL, n1 == (uint32_t)pt2)) break;      // direct edge: np.delete discarded :293
+                const uint32_t n2 = w_nbr(t, pt2, lane);               // common out-neighbours :298
+                bool hit = false;
+                for (int kk = 0; kk < W; ++kk) {
+                    const uint32_t v = __shfl_sync(FULL, n2, kk);
+                    hit |= (v != 0xFFFFFFFFu) && (n1 == v);
+                }
+                uint32_t cm = __ballot_sync(FULL, hit);                // n1 lanes, in edge order
+                if (cm == 0) continue;
+                for (int pick = rng.randint(__popc(cm)); pick > 0; --pick) cm &= cm - 1;
+                const int step = (int)__shfl_sync(FULL, n1, __ffs(cm) - 1);
+                const int ndel = idx2 - idx1 - 3;                      // delete idx1+2 .. idx2-2
+                __syncwarp();
+                if (lane == 0) r[idx1 + 1] = step;                     // :302
+                if (ndel > 0) {
+                    for (int x0 = idx1 + 2; x0 + ndel < arr_len; x0 += 32) {
+                        const int x = x0 + lane;
+                        int v = 0;
+                        const bool ok = x + ndel < arr_len;
+                        if (ok) v = r[x + ndel];
+                        __syncwarp();
+                        if (ok) r[x] = v;
+                        __syncwarp();
+                    }
+                    for (int x = arr_len - ndel + lane; x < arr_len; x += 32) r[x] = -1;
+                    arr_len -= ndel;
+                }
+                __syncwarp();
+                break;
+            }
+        }
+        // strip -1 (:307): stable compaction of the whole row
+        int w = 0;
+        for (int i0 = 0; i0 < L; i0 += 32) {
+            const int i = i0 + lane;
+            const int g = (i < L) ? r[i] : -1;
+            const uint32_t m = __ballot_sync(FULL, g != -1);
+            __syncwarp();
+            if (g != -1) r[w + __popc(m & ((1u << lane) - 1u))] = g;
+            w += __popc(m);
+            __syncwarp();
+        }
+        len = w;
+        for (int x = len + lane; x < L; x += 32) r[x] = -1;
+        __syncwarp();
+    }
+    // pruneUTurns :346-357: position i goes away if the waypoint at i recurs at i+1 or
+    // i+2, or if i-1 and i+1 hold the same waypoint (flags from the ORIGINAL row)
+    {
+        int w = 0, carry_prev = -3;
+        for (int i0 = 0; i0 < len; i0 += 32) {
+            const int i = i0 + lane;
+            const int g = (i < len) ? r[i] : -6;
+            const int n1 = (i + 1 < len) ? r[i + 1] : -4;
+            const int n2 = (i + 2 < len) ? r[i + 2] : -5;
+            int prev = __shfl_up_sync(FULL, g, 1);
+            if (lane == 0) prev = carry_prev;
+            carry_prev = __shfl_sync(FULL, g, 31);
+            const bool keep = (i < len) && !((g == n1) || (g == n2) || (prev == n1));
+            const uint32_t m = __ballot_sync(FULL, keep);
+            __syncwarp();
+            if (keep) r[w + __popc(m & ((1u << lane) - 1u))] = g;
+            w += __popc(m);
+            __syncwarp();
+        }
+        for (int x = w + lane; x < len; x += 32) r[x] = -1;
+        len = w;
+        __syncwarp();
+    }
+    return len;
 }
 
 // ------------------------------------------------------------------ lowVarSample
@@ -193,154 +416,188 @@ k_low_var_select(const double* __restrict__ fit, uint32_t M, double gamma, doubl
     }
 }
 
-// ------------------------------------------------------------------ crossover
-// One thread per (pair k, agent a): parents strong[k] ("self") and strong[k + P/2] ("mate").
-__global__ void __launch_bounds__(VARY_THREADS)
+// ------------------------------------------------------------------ crossover (+ fused mutation)
+// One warp per (pair k, agent a): parents strong[k] ("self") and strong[k + P/2] ("mate")
+// -> children 2k, 2k+1.  Rows live in shared memory: pm | pd | c1 | c2.
+constexpr int VARY_WARPS = 4;
+
+__device__ __forceinline__ size_t vary_row_stride(int L) { return (size_t)((L + 31) & ~31); }
+
+__global__ void __launch_bounds__(VARY_WARPS * 32)
 k_crossover(const int32_t* __restrict__ parents, const int32_t* __restrict__ strong, uint32_t P,
-            GcpTables t, VaryParams vp, uint64_t seed, uint32_t gen, int32_t* __restrict__ children)
+            GcpTables t, VaryParams vp, uint64_t seed, uint32_t gen,
+            int32_t* __restrict__ children)
 {
-    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ int32_t s_rows[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t gid = blockIdx.x * VARY_WARPS + warp;
     const uint32_t half = P / 2;
     if (gid >= half * vp.A) return;
     const uint32_t k = gid / vp.A, a = gid % vp.A;
     const int L = vp.L;
-    const int32_t* pm = parents + ((size_t)strong[k] * vp.A + a) * L;
-    const int32_t* pd = parents + ((size_t)strong[k + half] * vp.A + a) * L;
-    int32_t* c1 = children + ((size_t)(2 * k) * vp.A + a) * L;
-    int32_t* c2 = children + ((size_t)(2 * k + 1) * vp.A + a) * L;
-    const int lm = valid_len(pm, L), ld = valid_len(pd, L);
+    const size_t RS = vary_row_stride(L);
+    int32_t* pm = s_rows + (size_t)warp * (4 * RS);
+    int32_t* pd = pm + RS;
+    int32_t* c1 = pd + RS;
+    int32_t* c2 = c1 + RS;
+    const int32_t* gm = parents + ((size_t)strong[k] * vp.A + a) * L;
+    const int32_t* gd = parents + ((size_t)strong[k + half] * vp.A + a) * L;
+    for (int x = lane; x < L; x += 32) { pm[x] = gm[x]; pd[x] = gd[x]; }
+    __syncwarp();
+    const int lm = w_valid_len(pm, L, lane), ld = w_valid_len(pd, L, lane);
     Philox rng(seed, gen, STREAM_XOVER, gid);
     const bool want = rng.uniform() < vp.xover_prob;                   // :212,217
     int sel_i = -1, sel_j = -1;
     if (want) {
         // matchWaypt :311-333: i, j >= 1, equal waypoint that is a crossover candidate,
-        // |i - j| < time_thresh; candidates enumerated row-major like np.where
-        int cnt = 0;
-        for (int i = 1; i < lm; ++i) {
-            const int w = pm[i];
-            if (!t.xover[w]) continue;
-            const int j0 = max(1, i - vp.time_thresh + 1), j1 = min(ld - 1, i + vp.time_thresh - 1);
-            for (int j = j0; j <= j1; ++j) cnt += (pd[j] == w);
-        }
-        if (cnt > 0) {
-            int pick = rng.randint(cnt);                               // np.random.choice :221
-            for (int i = 1; i < lm && sel_i < 0; ++i) {
+        // |i - j| < time_thresh; candidates enumerated row-major like np.where.
+        // cnt[i] -> c1 (scratch until the children are built)
+        int total = 0;
+        for (int i0 = 1; i0 < lm; i0 += 32) {
+            const int i = i0 + lane;
+            int cnt = 0;
+            if (i < lm) {
                 const int w = pm[i];
-                if (!t.xover[w]) continue;
-                const int j0 = max(1, i - vp.time_thresh + 1), j1 = min(ld - 1, i + vp.time_thresh - 1);
-                for (int j = j0; j <= j1; ++j)
-                    if (pd[j] == w) { if (pick == 0) { sel_i = i; sel_j = j; break; } --pick; }
+                if (__ldg(t.xover + w)) {
+                    const int j0 = max(1, i - vp.time_thresh + 1), j1 = min(ld - 1, i + vp.time_thresh - 1);
+                    for (int j = j0; j <= j1; ++j) cnt += (pd[j] == w);
+                }
+                c1[i] = cnt;
+            }
+            total += cnt;
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
+        __syncwarp();
+        if (total > 0) {
+            int pick = rng.randint(total);                             // np.random.choice :221
+            for (int i0 = 1; i0 < lm; i0 += 32) {
+                const int i = i0 + lane;
+                const int cnt = (i < lm) ? c1[i] : 0;
+                int inc = cnt;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(FULL, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                const uint32_t m = __ballot_sync(FULL, inc > pick);
+                if (m) {
+                    const int src = __ffs(m) - 1;
+                    int jj = -1;
+                    if (lane == src) {
+                        int rem = pick - (inc - cnt);
+                        const int w = pm[i];
+                        const int j0 = max(1, i - vp.time_thresh + 1), j1 = min(ld - 1, i + vp.time_thresh - 1);
+                        for (int j = j0; j <= j1; ++j)
+                            if (pd[j] == w) { if (rem == 0) { jj = j; break; } --rem; }
+                    }
+                    sel_i = i0 + src;
+                    sel_j = __shfl_sync(FULL, jj, src);
+                    break;
+                }
+                pick -= __shfl_sync(FULL, inc, 31);
             }
         }
+        __syncwarp();
     }
     int n1, n2;
     if (sel_i >= 0) {
         // dna1 = self[0:i] + mate[j:], dna2 = mate[0:j] + self[i:]  (:225-229), cut at L
-        n1 = 0;
-        for (int x = 0; x < sel_i && n1 < L; ++x) c1[n1++] = pm[x];
-        for (int x = sel_j; x < ld && n1 < L; ++x) c1[n1++] = pd[x];
-        n2 = 0;
-        for (int x = 0; x < sel_j && n2 < L; ++x) c2[n2++] = pd[x];
-        for (int x = sel_i; x < lm && n2 < L; ++x) c2[n2++] = pm[x];
+        n1 = min(L, sel_i + ld - sel_j);
+        n2 = min(L, sel_j + lm - sel_i);
+        for (int x = lane; x < n1; x += 32) c1[x] = (x < sel_i) ? pm[x] : pd[sel_j + x - sel_i];
+        for (int x = lane; x < n2; x += 32) c2[x] = (x < sel_j) ? pd[x] : pm[sel_i + x - sel_j];
+        __syncwarp();
         // padMinDNA :203-209: extend short children with a fresh walk from their last node
-        if (n1 > 0 && n1 < vp.min_dna_len) n1 = walk(t, vp, c1, n1 - 1, vp.min_dna_len - n1, n1 - 1, rng) + 1;
-        if (n2 > 0 && n2 < vp.min_dna_len) n2 = walk(t, vp, c2, n2 - 1, vp.min_dna_len - n2, n2 - 1, rng) + 1;
+        if (n1 > 0 && n1 < vp.min_dna_len) n1 = w_walk(t, vp, c1, n1 - 1, vp.min_dna_len - n1, n1 - 1, rng, lane) + 1;
+        if (n2 > 0 && n2 < vp.min_dna_len) n2 = w_walk(t, vp, c2, n2 - 1, vp.min_dna_len - n2, n2 - 1, rng, lane) + 1;
     } else {
-        for (n1 = 0; n1 < lm; ++n1) c1[n1] = pm[n1];
-        for (n2 = 0; n2 < ld; ++n2) c2[n2] = pd[n2];
+        n1 = lm; n2 = ld;
+        for (int x = lane; x < n1; x += 32) c1[x] = pm[x];
+        for (int x = lane; x < n2; x += 32) c2[x] = pd[x];
     }
-    for (int x = n1; x < L; ++x) c1[x] = -1;                           // addTelomere :335-344
-    for (int x = n2; x < L; ++x) c2[x] = -1;
+    __syncwarp();
+    {
+        int32_t* g1 = children + ((size_t)(2 * k) * vp.A + a) * L;
+        int32_t* g2 = children + ((size_t)(2 * k + 1) * vp.A + a) * L;
+        for (int x = lane; x < L; x += 32) {                            // addTelomere :335-344
+            g1[x] = (x < n1) ? c1[x] : -1;
+            g2[x] = (x < n2) ? c2[x] : -1;
+        }
+    }
 }
 
-// ------------------------------------------------------------------ mutation / muterpolate / prune
-// One thread per (organism, agent); works in place on the organism's row.
-__global__ void __launch_bounds__(VARY_THREADS)
-k_mutate(int32_t* __restrict__ dna, uint32_t P, GcpTables t, VaryParams vp, uint64_t seed,
-         uint32_t gen, uint32_t stream_salt)
-{
-    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= P * vp.A) return;
-    const uint32_t org = gid / vp.A;
-    const int L = vp.L;
-    int32_t* r = dna + (size_t)gid * L;
-    int len = valid_len(r, L);
-    // organism-level coin flips, identical for all agents of the organism (:159-165)
-    Philox org_rng(seed, gen, STREAM_ORG + stream_salt, org);
-    const bool do_mut = org_rng.uniform() < vp.mut_prob;
-    const bool do_mp = org_rng.uniform() < vp.muterp_prob;
-    Philox rng(seed, gen, STREAM_MUT + stream_salt, gid);
+// ------------------------------------------------------------------ mutation (:251-268)
+// Organisms flip the mutation coin as a whole (:159-161); every agent row of a mutating
+// organism regrows its tail from a random cut.  One CTA looks at ORGS consecutive organisms,
+// compacts the rows that walk into a shared list, and hands them out one per THREAD.
+constexpr int MW_THREADS = 128;
+constexpr int MW_MAX_ROWS = 4096;
 
-    if (do_mut && len >= 3) {                                          // mutation :251-268
+__global__ void __launch_bounds__(MW_THREADS)
+k_mutation_walks(int32_t* __restrict__ dna, uint32_t P, uint32_t orgs_per_cta, GcpTables t,
+                 VaryParams vp, uint64_t seed, uint32_t gen, uint32_t salt)
+{
+    __shared__ uint32_t s_list[MW_MAX_ROWS];
+    __shared__ uint32_t s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const uint32_t org0 = blockIdx.x * orgs_per_cta;
+    for (uint32_t o = threadIdx.x; o < orgs_per_cta && org0 + o < P; o += MW_THREADS) {
+        Philox org_rng(seed, gen, stream_id(STREAM_ORG, salt), org0 + o);
+        if (org_rng.uniform() < vp.mut_prob) {
+            const uint32_t base = atomicAdd(&s_n, (uint32_t)vp.A);
+            for (int a = 0; a < vp.A; ++a) s_list[base + a] = (org0 + o) * vp.A + a;
+        }
+    }
+    __syncthreads();
+    const uint32_t n = s_n;
+    const int L = vp.L;
+    for (uint32_t j = threadIdx.x; j < n; j += MW_THREADS) {
+        const uint32_t gid = s_list[j];
+        int32_t* r = dna + (size_t)gid * L;
+        int len = 0;
+        while (len < L && r[len] != -1) ++len;
+        if (len < 3) continue;
+        Philox rng(seed, gen, stream_id(STREAM_MUT, salt), gid);
         const int idx = 1 + rng.randint(len - 2);                      // randint(1, len-1)
         int len_tail = len - idx;
         if (len + 1 < L) len_tail += rng.randint(L - len);             // :256-258
-        len = walk(t, vp, r, idx, len_tail, 0, rng) + 1;
-        for (int x = len; x < L; ++x) r[x] = -1;
-    }
-    if (do_mp && len - (vp.srch_dist + 3) > 0) {                       // muterpolate :270-309
-        int pts[MAX_MUT_POINTS];
-        const int np_ = min(vp.num_muterp, MAX_MUT_POINTS);
-        const int range = len - (vp.srch_dist + 3);
-        for (int q = 0; q < np_; ++q) {                                // choice with replacement,
-            const int v = rng.randint(range);                          // kept sorted descending
-            int x = q;
-            while (x > 0 && pts[x - 1] < v) { pts[x] = pts[x - 1]; --x; }
-            pts[x] = v;
-        }
-        int arr_len = L;                                               // np.delete shrinks the padded row
-        for (int q = 0; q < np_; ++q) {
-            const int idx1 = pts[q];
-            for (int idx2 = idx1 + vp.srch_dist + 1; idx2 > idx1 + 1; --idx2) {
-                if (!(rng.uniform() < vp.sub_prob)) continue;
-                if (idx2 >= arr_len) break;                            // IndexError -> break :289
-                const int pt1 = r[idx1];
-                int pt2 = r[idx2];
-                if (pt2 < 0) pt2 += (int)t.N;                          // numpy index -1 (SURVEY F4)
-                if (is_edge(t, pt1, pt2)) break;                       // np.delete discarded :293
-                int nopt = 0;                                          // common out-neighbours :298
-                for (uint32_t e1 = t.row_ptr[pt1]; e1 < t.row_ptr[pt1 + 1]; ++e1)
-                    nopt += is_edge(t, pt2, (int)t.col[e1]);
-                if (nopt == 0) continue;
-                int pick = rng.randint(nopt), step = -1;
-                for (uint32_t e1 = t.row_ptr[pt1]; e1 < t.row_ptr[pt1 + 1]; ++e1) {
-                    const int c = (int)t.col[e1];
-                    if (is_edge(t, pt2, c)) { if (pick == 0) { step = c; break; } --pick; }
-                }
-                r[idx1 + 1] = step;                                    // :302
-                const int ndel = idx2 - idx1 - 3;                      // delete idx1+2 .. idx2-2
-                if (ndel > 0) {
-                    for (int x = idx1 + 2; x + ndel < arr_len; ++x) r[x] = r[x + ndel];
-                    for (int x = arr_len - ndel; x < arr_len; ++x) r[x] = -1;
-                    arr_len -= ndel;
-                }
-                break;
-            }
-        }
-        int w = 0;                                                     // strip -1 :307
-        for (int x = 0; x < L; ++x) { const int g = r[x]; if (g != -1) r[w++] = g; }
-        len = w;
-        for (int x = len; x < L; ++x) r[x] = -1;
-    }
-    // pruneUTurns :346-357: position i goes away if the waypoint at i recurs at i+1 or
-    // i+2, or if i-1 and i+1 hold the same waypoint (one pass over the original row)
-    {
-        int w = 0, prev = -3;
-        for (int i = 0; i < len; ++i) {
-            const int g = r[i];
-            const int n1 = (i + 1 < len) ? r[i + 1] : -4;
-            const int n2 = (i + 2 < len) ? r[i + 2] : -5;
-            const bool gone = (g == n1) || (g == n2) || (prev == n1);
-            prev = g;
-            if (!gone) r[w++] = g;
-        }
-        for (int x = w; x < len; ++x) r[x] = -1;
-        len = w;
+        const int last = t_walk(t, vp, r, idx, len_tail, 0, rng);
+        for (int x = last + 1; x < len; ++x) r[x] = -1;                // addTelomere
     }
 }
 
+// ------------------------------------------------------------------ muterpolate / prune
+// One warp per (organism, agent); the row goes through shared memory and back in place.
+__global__ void __launch_bounds__(VARY_WARPS * 32)
+k_post_mutate(int32_t* __restrict__ dna, uint32_t P, GcpTables t, VaryParams vp, uint64_t seed,
+              uint32_t gen, uint32_t salt)
+{
+    extern __shared__ int32_t s_rows[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t gid = blockIdx.x * VARY_WARPS + warp;
+    if (gid >= P * vp.A) return;
+    const uint32_t org = gid / vp.A;
+    const int L = vp.L;
+    const size_t RS = vary_row_stride(L);
+    int32_t* r = s_rows + (size_t)warp * (RS + 128);
+    int32_t* s_tmp = r + RS;
+    int32_t* g = dna + (size_t)gid * L;
+    for (int x = lane; x < L; x += 32) r[x] = g[x];
+    __syncwarp();
+    int len = w_valid_len(r, L, lane);
+    // organism-level coin flips, identical for all agents of the organism (:159-165)
+    Philox org_rng(seed, gen, stream_id(STREAM_ORG, salt), org);
+    org_rng.uniform();                                                 // the mutation coin
+    const bool do_mp = org_rng.uniform() < vp.muterp_prob;
+    Philox rng(seed, gen, stream_id(STREAM_MUTERP, salt), gid);
+    len = w_post_mutate(t, vp, r, len, s_tmp, do_mp, rng, lane);
+    for (int x = lane; x < L; x += 32) g[x] = (x < len) ? r[x] : -1;
+}
+
 // ------------------------------------------------------------------ initial random paths
-__global__ void __launch_bounds__(VARY_THREADS)
+__global__ void __launch_bounds__(128)
 k_random_walks(int32_t* __restrict__ dna, uint32_t P, GcpTables t, VaryParams vp,
                const int32_t* __restrict__ start_idx, int path_len, uint64_t seed, uint32_t batch)
 {
@@ -349,7 +606,7 @@ k_random_walks(int32_t* __restrict__ dna, uint32_t P, GcpTables t, VaryParams vp
     int32_t* r = dna + (size_t)gid * vp.L;
     Philox rng(seed, batch, STREAM_INIT, gid);
     r[0] = start_idx[gid % vp.A];
-    const int last = walk(t, vp, r, 0, path_len, 0, rng);
+    const int last = t_walk(t, vp, r, 0, path_len, 0, rng);
     for (int x = last + 1; x < vp.L; ++x) r[x] = -1;
 }
 
@@ -399,17 +656,12 @@ int launch_low_var_select(gcp_ctx* c, const double* fit, uint32_t M, double gamm
     return 0;
 }
 
-int launch_crossover(gcp_ctx* c, const int32_t* parents, const int32_t* strong, uint32_t P,
-                     uint64_t seed, uint32_t gen, int32_t* children, cudaStream_t st)
+static int vary_smem(gcp_ctx* c, int rows, int extra, size_t* out)
 {
-    if (P < 2) return 0;
-    if (P & 1) return gcp_fail(c, -1, "population size must be even (pather_driver.py:107)");
-    StageTimer tm(c, 6, st);
-    const uint32_t n = (P / 2) * c->p.num_agents;
-    k_crossover<<<(n + VARY_THREADS - 1) / VARY_THREADS, VARY_THREADS, 0, st>>>(
-        parents, strong, P, c->t, make_vp(c), seed, gen, children);
-    c->launches++;
-    GCP_CUDA(c, cudaGetLastError());
+    const size_t RS = (size_t)((c->p.max_dna_len + 31) & ~31);
+    *out = (size_t)VARY_WARPS * (rows * RS + extra) * 4;
+    if (*out > (size_t)c->max_smem_optin)
+        return gcp_fail(c, -3, "variation kernel needs %zu B shared memory (max_dna_len too large)", *out);
     return 0;
 }
 
@@ -417,10 +669,38 @@ int launch_mutate(gcp_ctx* c, int32_t* dna, uint32_t P, uint64_t seed, uint32_t 
                   cudaStream_t st)
 {
     if (P == 0) return 0;
+    size_t smem; int r = vary_smem(c, 1, 128, &smem); if (r) return r;
+    GCP_CUDA(c, cudaFuncSetAttribute(k_post_mutate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     StageTimer tm(c, 7, st);
+    const VaryParams vp = make_vp(c);
+    if (vp.mut_prob > 0.f) {
+        // expected number of walking rows per CTA ~ 2 x MW_THREADS
+        const double pr = vp.mut_prob < 0.05f ? 0.05 : (vp.mut_prob > 1.f ? 1.0 : (double)vp.mut_prob);
+        uint32_t orgs = (uint32_t)(2.0 * MW_THREADS / (pr * vp.A) + 0.5);
+        if (orgs < 1) orgs = 1;
+        if (orgs * (uint32_t)vp.A > (uint32_t)MW_MAX_ROWS) orgs = MW_MAX_ROWS / vp.A;
+        k_mutation_walks<<<(P + orgs - 1) / orgs, MW_THREADS, 0, st>>>(dna, P, orgs, c->t, vp, seed, gen, salt);
+        c->launches++;
+    }
     const uint32_t n = P * c->p.num_agents;
-    k_mutate<<<(n + VARY_THREADS - 1) / VARY_THREADS, VARY_THREADS, 0, st>>>(dna, P, c->t, make_vp(c),
-                                                                            seed, gen, salt);
+    k_post_mutate<<<(n + VARY_WARPS - 1) / VARY_WARPS, VARY_WARPS * 32, smem, st>>>(dna, P, c->t, vp,
+                                                                                    seed, gen, salt);
+    c->launches++;
+    GCP_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+int launch_crossover(gcp_ctx* c, const int32_t* parents, const int32_t* strong, uint32_t P,
+                     uint64_t seed, uint32_t gen, int32_t* children, cudaStream_t st)
+{
+    if (P < 2) return 0;
+    if (P & 1) return gcp_fail(c, -1, "population size must be even (pather_driver.py:107)");
+    size_t smem; int r = vary_smem(c, 4, 0, &smem); if (r) return r;
+    GCP_CUDA(c, cudaFuncSetAttribute(k_crossover, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    StageTimer tm(c, 6, st);
+    const uint32_t n = (P / 2) * c->p.num_agents;
+    k_crossover<<<(n + VARY_WARPS - 1) / VARY_WARPS, VARY_WARPS * 32, smem, st>>>(
+        parents, strong, P, c->t, make_vp(c), seed, gen, children);
     c->launches++;
     GCP_CUDA(c, cudaGetLastError());
     return 0;
@@ -431,8 +711,8 @@ int launch_random_walks(gcp_ctx* c, int32_t* dna, uint32_t P, const int32_t* sta
 {
     if (P == 0) return 0;
     const uint32_t n = P * c->p.num_agents;
-    k_random_walks<<<(n + VARY_THREADS - 1) / VARY_THREADS, VARY_THREADS, 0, st>>>(
-        dna, P, c->t, make_vp(c), start_idx_dev, path_len, seed, batch);
+    k_random_walks<<<(n + 127) / 128, 128, 0, st>>>(dna, P, c->t, make_vp(c), start_idx_dev, path_len,
+                                                   seed, batch);
     c->launches++;
     GCP_CUDA(c, cudaGetLastError());
     return 0;

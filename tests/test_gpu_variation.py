@@ -248,6 +248,62 @@ def test_generation_step_against_oracle(world_big):
         assert det[1] == got[1] and abs(det[0] - got[0]) <= 1e-12
 
 
+def test_fused_select_vary_equals_staged_kernels(world_big):
+    """gcp_select_vary (lowVarSample + crossover with the constructor variation fused into the
+    same kernel) must produce exactly what the staged calls produce: same Philox streams."""
+    import torch
+    w = world_big
+    eng = _engine(w, w.org_params)
+    P = 128
+    par = torch.from_numpy(_parents(w, eng, P, seed=21)).cuda()
+    rs = np.random.RandomState(3)
+    fit = torch.from_numpy(rs.randn(P) * 0.2).cuda()
+    for seed, gen in ((5, 0), (123456789012345, 9)):
+        fused = eng.select_vary(par, fit, 0.5, seed=seed, gen=gen).cpu().numpy()
+        m64 = (1 << 64) - 1
+        z = (seed ^ (0x9E3779B97F4A7C15 * (gen + 1))) & m64
+        z ^= z >> 30
+        z = (z * 0xBF58476D1CE4E5B9) & m64
+        z ^= z >> 27
+        z = (z * 0x94D049BB133111EB) & m64
+        z ^= z >> 31
+        r0 = ((z >> 11) * (1.0 / 9007199254740992.0)) / P
+        strong = eng.low_var_select(fit, 0.5, r0)
+        kids = eng.crossover(par, strong, seed=seed, gen=gen)
+        eng.mutate(kids, seed=seed, gen=gen, salt=0)
+        assert np.array_equal(fused, kids.cpu().numpy())
+        for row in fused.reshape(-1, fused.shape[-1]):
+            _valid(row)
+
+
+def test_long_rows_variation(world_big):
+    """L = 640 rows (C4-style): shared-memory rows beyond the default 48 KB, invariants hold."""
+    import torch
+    w = world_big
+    op = _op(w, max_dna_len=640, mutation_prob=1.0, muterpolate_prob=1.0, crossover_prob=1.0)
+    eng = _engine(w, op)
+    from genetic_coverage_planning_b200 import synth
+    P = 32
+    par = synth.random_walk_population(w.xy, w.row_ptr, w.col, op['start_idx'], P, 500, 640,
+                                       seed=2).astype(np.int32)
+    fit = torch.from_numpy(np.linspace(-1, 1, P)).cuda()
+    kids = eng.select_vary(torch.from_numpy(par).cuda(), fit, 0.5, seed=1, gen=1).cpu().numpy()
+    edges = _edges(w)
+    steps = off = moved = 0
+    for p in range(P):
+        for a in range(eng.A):
+            r = _valid(kids[p, a])
+            assert 2 <= len(r) <= 640
+            # pruneUTurns on overlapping u-turns at the head (A B A B -> B) may drop the start
+            # waypoint: the reference's own artefact (geneticalgorithm.py:346-357), rare
+            moved += r[0] != op['start_idx'][a]
+            for x in range(len(r) - 1):
+                steps += 1
+                off += (int(r[x]), int(r[x + 1])) not in edges
+    assert off < 0.02 * steps, (off, steps)       # muterpolate / prune artefacts only (F4)
+    assert moved <= 0.05 * P * eng.A, moved
+
+
 def test_facade_drop_in(tmp_path):
     """GeneticalGorithm / Organism facade on a small synthetic world (CSR-backed Mappy /
     PathMaker stand-ins): constructor, runEvolution history, views, rackNstack, pickle."""
