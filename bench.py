@@ -241,6 +241,9 @@ def main():
     P, A, L = cfg['pop'], cfg['agents'], cfg['L']
     eng = FitnessEngine(pw, op, num_agents=A, device=local)
     eng.set_vary_params(op, w.path_params)
+    for kv in filter(None, os.environ.get("GCP_OPTS", "").split(",")):     # tuning experiments
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
     t0 = time.time()
     dna = synth.random_walk_population_torch(w.xy, w.row_ptr, w.col, starts, P, cfg['walk'], L,
                                              seed=1 + rank, device=dev)

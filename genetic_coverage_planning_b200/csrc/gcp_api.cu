@@ -181,6 +181,28 @@ int gcp_upload_masked_footprints(gcp_ctx* c, const uint32_t* sub_ptr, const uint
     if ((r = upload(c, &c->t.m_sub_info, info.data(), EN))) return r;
     if ((r = upload(c, &c->t.m_sub_desc, desc.data(), n_sub))) return r;
     if ((r = upload(c, &c->t.m_tile, tile_data, (size_t)n_quarters * 8))) return r;
+    {   // flat per-edge lists of QUARTER items for the fused kernel: {block<<2 | q, uint4 index}
+        std::vector<uint32_t> qinfo(EN);
+        std::vector<uint2> qdesc;
+        qdesc.reserve((size_t)n_sub * 2);
+        bool ok = true;
+        for (size_t e = 0; e < EN && ok; ++e) {
+            const size_t first = qdesc.size();
+            for (uint32_t k = sub_ptr[e]; k < sub_ptr[e + 1]; ++k) {
+                uint32_t off = sub_payload[k] >> 4;
+                for (uint32_t q = 0; q < 4; ++q)
+                    if ((sub_payload[k] >> q) & 1u) qdesc.push_back(make_uint2((sub_block[k] << 2) | q, (off++) << 3));
+            }
+            const size_t n = qdesc.size() - first;
+            if (n > 63 || first >= (1u << 26)) ok = false;
+            qinfo[e] = (uint32_t)first | ((uint32_t)n << 26);
+        }
+        c->t.m_q_info = nullptr; c->t.m_q_desc = nullptr;
+        if (ok) {
+            if ((r = upload(c, &c->t.m_q_info, qinfo.data(), EN))) return r;
+            if ((r = upload(c, &c->t.m_q_desc, qdesc.data(), qdesc.size()))) return r;
+        }
+    }
     c->have_masked = true;
     return 0;
 }
@@ -277,6 +299,11 @@ int gcp_eval(gcp_ctx* c, const int32_t* dna, uint32_t P, const gcp_eval_out* out
     int r = ready(c); if (r) return r;
     if (!out) return gcp_fail(c, -1, "gcp_eval: out is NULL");
     if (P == 0) return 0;
+    // objectives-only fast path: binary map, wall coverage only -> pre-masked footprint store
+    const bool fast = c->have_masked && c->n_gray == 0 && c->p.coverage_blend == 1.0 &&
+                      !out->cov && !c->force_general;
+    if (fast && c->fused_eval && c->t.m_q_info && eval_fused_fits(c))   // one kernel, no scratch (gcp_fused.cu)
+        return launch_eval_fused(c, dna, P, out, (cudaStream_t)stream);
     if (scratch_bytes < gcp_eval_scratch_bytes(c, P) || !scratch)
         return gcp_fail(c, -1, "gcp_eval: scratch too small (%zu < %zu)", scratch_bytes,
                         gcp_eval_scratch_bytes(c, P));
@@ -293,9 +320,6 @@ int gcp_eval(gcp_ctx* c, const int32_t* dna, uint32_t P, const gcp_eval_out* out
     if (out->cov) cov = out->cov;
     if (out->flags) flags = out->flags;
     cudaStream_t st = (cudaStream_t)stream;
-    // objectives-only fast path: binary map, wall coverage only -> pre-masked footprint store
-    const bool fast = c->have_masked && c->n_gray == 0 && c->p.coverage_blend == 1.0 &&
-                      !out->cov && !c->force_general;
     if ((r = launch_path_costs(c, dna, P, edge_ids, fast ? step_info : nullptr, dist, turn,
                                flags, st))) return r;
     if (fast) {
@@ -458,6 +482,7 @@ int gcp_set_option(gcp_ctx* c, const char* name, int64_t value)
     if (!c || !name) return -1;
     if (!strcmp(name, "rank_algo")) c->rank_algo = (int)value;
     else if (!strcmp(name, "force_general")) c->force_general = (int)value;
+    else if (!strcmp(name, "fused_eval")) c->fused_eval = (int)value;
     else if (!strcmp(name, "cov_table")) c->cov_table = (int)value;
     else if (!strcmp(name, "cov_maxpairs")) c->cov_maxpairs = (int)value;
     else return gcp_fail(c, -1, "gcp_set_option: unknown option '%s'", name);

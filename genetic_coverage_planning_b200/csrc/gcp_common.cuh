@@ -27,6 +27,8 @@ struct GcpTables {
     const uint32_t* m_sub_info;
     const uint2*    m_sub_desc;
     const uint4*    m_tile;
+    const uint32_t* m_q_info;  // [E+N] first quarter item (26 bits) | count << 26   (fused kernel)
+    const uint2*    m_q_desc;  // {block id << 2 | quarter index, uint4 index of the quarter in m_tile}
     // map planes, block-major: 32 x uint4 per block (lane l = rows 2l, 2l+1)
     uint32_t n_blocks;
     const uint4*    blk_mask0; // buffer_mask & (g==0)
@@ -65,6 +67,7 @@ struct gcp_ctx {
     int cov_table = 0, cov_maxpairs = 0;
     int force_general = 0;   // testing: never take the pre-masked fast path
     int cov_detail = 1;      // 1: all six counters; 0: only what the objectives need
+    int fused_eval = 1;      // 1: objectives-only fast path runs as ONE kernel (gcp_fused.cu)
     int rank_algo = 0;       // 0 auto, 1 O(N^2) dominance tiles, 2 sort-based (gcp_rank.cu)
 };
 
@@ -96,6 +99,9 @@ int launch_coverage(gcp_ctx*, const uint32_t* edge_ids, uint32_t P, uint32_t* co
 int launch_loop_closures(gcp_ctx*, const int32_t* dna, uint32_t P, const double* dist,
                          const double* turn, const uint32_t* cov, int32_t* lc, double* obj,
                          double* neg_cov, uint8_t* flags, cudaStream_t);
+int launch_eval_fused(gcp_ctx*, const int32_t* dna, uint32_t P, const gcp_eval_out* out,
+                      cudaStream_t);
+bool eval_fused_fits(gcp_ctx*);
 int launch_maximin(gcp_ctx*, const double* obj, uint32_t n, double constr, uint32_t r0,
                    uint32_t r1, double* obj_sc, double* fit, void* scratch, size_t sb,
                    cudaStream_t);

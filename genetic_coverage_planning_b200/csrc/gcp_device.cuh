@@ -1,0 +1,95 @@
+// Device helpers shared by the evaluation kernels (gcp_eval.cu, gcp_fused.cu).
+#pragma once
+#include "gcp_common.cuh"
+
+#define FULL 0xffffffffu
+
+__device__ __forceinline__ uint32_t hash_block(uint32_t b) { return b * 2654435761u; }
+__device__ __forceinline__ uint32_t part_block(uint32_t b) { return (b * 0x85ebca6bu) >> 12; }
+
+__device__ __forceinline__ int popc128(uint4 a)
+{
+    return __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w);
+}
+
+__device__ __forceinline__ double np_sum_order(const double* a, int n)
+{
+    // numpy pairwise_sum for n < 128 (verified against np.sum, tests/test_oracle_golden)
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; ++i) r = __dadd_rn(r, a[i]);
+        return r;
+    }
+    double r[8];
+    for (int k = 0; k < 8; ++k) r[k] = a[k];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8)
+        for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], a[i + k]);
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+    return res;
+}
+
+
+// Constraints + objectives of one organism (geneticalgorithm.py:177-201) from its loop-closure
+// matrix (shared memory, A x A), integer coverage counters cov[0..3] and per-agent cost sums.
+__device__ __forceinline__ void finish_objectives(const int* s_lc, int A, const gcp_params& prm,
+                                                  const gcp_map_consts& mc, const uint32_t* c,
+                                                  const double* dist, const double* turn,
+                                                  uint32_t org, double* __restrict__ obj,
+                                                  double* __restrict__ neg_cov_out,
+                                                  uint8_t* __restrict__ flags)
+{
+    bool solo_bad = false;
+    long long combo = 0;
+    uint32_t adj[GCP_MAX_AGENTS];
+    for (int a = 0; a < A; ++a) {
+        if (s_lc[a * A + a] < prm.min_solo_lcs) solo_bad = true;
+        uint32_t m = 0;
+        for (int b = 0; b < A; ++b) {
+            if (b == a) continue;
+            combo += s_lc[a * A + b];
+            if (s_lc[a * A + b] + s_lc[b * A + a] >= 1) m |= 1u << b;
+        }
+        adj[a] = m;
+    }
+    int ncomp = 0;
+    uint32_t seen = 0;
+    for (int a = 0; a < A; ++a) {
+        if ((seen >> a) & 1u) continue;
+        ++ncomp;
+        uint32_t fr = 1u << a;
+        while (fr) {
+            seen |= fr;
+            uint32_t nf = 0;
+            for (uint32_t m = fr; m; m &= m - 1) nf |= adj[__ffs(m) - 1];
+            fr = nf & ~seen;
+        }
+    }
+    const bool feasible = !(solo_bad || combo < (long long)prm.min_comb_lcs || ncomp > 1);
+
+    // coverage (mappy.py:358-364) from the integer pixel counts
+    const long long w_mask = 255ll * c[0] + c[2];
+    const long long w_all = 255ll * c[1] + c[3];
+    const double wall = __ddiv_rn(__ddiv_rn((double)(mc.gsum_mask + w_mask), 255.0),
+                                  (double)mc.mask_size);
+    const double sum_draw = __dadd_rn(mc.num_occluded, __ddiv_rn((double)w_all, 255.0));
+    const double internal = __ddiv_rn(__dsub_rn(sum_draw, mc.num_occluded),
+                                      __dsub_rn((double)mc.map_size, mc.num_occluded));
+    const double coverage = __dadd_rn(__dmul_rn(prm.coverage_blend, wall),
+                                      __dmul_rn(prm.one_minus_blend, internal));
+    const double neg_cov = -coverage;
+    const double td = np_sum_order(dist, A);
+    const double tc = np_sum_order(turn, A);
+    const double travel = __dmul_rn(__dadd_rn(td, tc), prm.flight_time_scale);
+    if (neg_cov_out) neg_cov_out[org] = neg_cov;
+    if (obj) {
+        obj[(size_t)org * 2 + 0] = feasible ? neg_cov : 0.0;
+        obj[(size_t)org * 2 + 1] = travel;
+    }
+    if (flags) {
+        flags[(size_t)org * 4 + 0] = feasible ? 1 : 0;
+        flags[(size_t)org * 4 + 2] = (uint8_t)ncomp;
+    }
+}

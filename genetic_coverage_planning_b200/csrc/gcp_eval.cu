@@ -7,8 +7,7 @@
 //   mappy.py:372-437   getLoopClosures  -> k_loop_closures
 //   geneticalgorithm.py:177-201 calcObj -> tail of k_loop_closures
 #include "gcp_common.cuh"
-
-#define FULL 0xffffffffu
+#include "gcp_device.cuh"
 
 // ============================================================================
 // K1  path costs: one CTA per organism.
@@ -132,8 +131,6 @@ int launch_path_costs(gcp_ctx* ctx, const int32_t* dna, uint32_t P, uint32_t* ed
 //   If the table or pair store overflows (very long genomes), the organism is redone in
 //   R = 2,4,8.. hash partitions of the blocks; results are exact in every case.
 // ============================================================================
-__device__ __forceinline__ uint32_t hash_block(uint32_t b) { return b * 2654435761u; }
-__device__ __forceinline__ uint32_t part_block(uint32_t b) { return (b * 0x85ebca6bu) >> 12; }
 
 __device__ __forceinline__ uint4 ld_quarter(const uint4* __restrict__ tile, uint32_t p,
                                             uint32_t q, uint32_t below, uint32_t l7)
@@ -146,10 +143,6 @@ __device__ __forceinline__ uint4 ld_quarter(const uint4* __restrict__ tile, uint
     return v;
 }
 
-__device__ __forceinline__ int popc128(uint4 a)
-{
-    return __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w);
-}
 __device__ __forceinline__ uint4 and128(uint4 a, uint4 b)
 {
     return make_uint4(a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w);
@@ -724,25 +717,6 @@ int launch_coverage_masked(gcp_ctx* ctx, const uint32_t* step_info, uint32_t P, 
 constexpr int K3_THREADS = 256;
 constexpr uint32_t K3_NIL = 0xFFFFFFFFu;
 
-__device__ double np_sum_order(const double* a, int n)
-{
-    // numpy pairwise_sum for n < 128 (verified against np.sum, tests/test_oracle_golden)
-    if (n < 8) {
-        double r = 0.0;
-        for (int i = 0; i < n; ++i) r = __dadd_rn(r, a[i]);
-        return r;
-    }
-    double r[8];
-    for (int k = 0; k < 8; ++k) r[k] = a[k];
-    int i = 8;
-    for (; i < n - (n % 8); i += 8)
-        for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], a[i + k]);
-    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-    for (; i < n; ++i) res = __dadd_rn(res, a[i]);
-    return res;
-}
-
 __global__ void __launch_bounds__(K3_THREADS)
 k_loop_closures(const int32_t* __restrict__ dna, uint32_t P, int A, int L, int T3 /*slots > A*L*/,
                 gcp_params prm, gcp_map_consts mc,
@@ -872,60 +846,9 @@ k_loop_closures(const int32_t* __restrict__ dna, uint32_t P, int A, int L, int T
         for (int i = tid; i < A * A; i += K3_THREADS) lc_out[(size_t)org * A * A + i] = s_lc[i];
 
     // ---- constraints + objectives (geneticalgorithm.py:177-201), one thread ----
-    if (tid == 0) {
-        bool solo_bad = false;
-        long long combo = 0;
-        uint32_t adj[GCP_MAX_AGENTS];
-        for (int a = 0; a < A; ++a) {
-            if (s_lc[a * A + a] < prm.min_solo_lcs) solo_bad = true;
-            uint32_t m = 0;
-            for (int b = 0; b < A; ++b) {
-                if (b == a) continue;
-                combo += s_lc[a * A + b];
-                if (s_lc[a * A + b] + s_lc[b * A + a] >= 1) m |= 1u << b;
-            }
-            adj[a] = m;
-        }
-        int ncomp = 0;
-        uint32_t seen = 0;
-        for (int a = 0; a < A; ++a) {
-            if ((seen >> a) & 1u) continue;
-            ++ncomp;
-            uint32_t fr = 1u << a;
-            while (fr) {
-                seen |= fr;
-                uint32_t nf = 0;
-                for (uint32_t m = fr; m; m &= m - 1) nf |= adj[__ffs(m) - 1];
-                fr = nf & ~seen;
-            }
-        }
-        const bool feasible = !(solo_bad || combo < (long long)prm.min_comb_lcs || ncomp > 1);
-
-        // coverage (mappy.py:358-364) from the integer pixel counts
-        const uint32_t* c = cov + (size_t)org * 8;
-        const long long w_mask = 255ll * c[0] + c[2];
-        const long long w_all = 255ll * c[1] + c[3];
-        const double wall = __ddiv_rn(__ddiv_rn((double)(mc.gsum_mask + w_mask), 255.0),
-                                      (double)mc.mask_size);
-        const double sum_draw = __dadd_rn(mc.num_occluded, __ddiv_rn((double)w_all, 255.0));
-        const double internal = __ddiv_rn(__dsub_rn(sum_draw, mc.num_occluded),
-                                          __dsub_rn((double)mc.map_size, mc.num_occluded));
-        const double coverage = __dadd_rn(__dmul_rn(prm.coverage_blend, wall),
-                                          __dmul_rn(prm.one_minus_blend, internal));
-        const double neg_cov = -coverage;
-        const double td = np_sum_order(dist + (size_t)org * A, A);
-        const double tc = np_sum_order(turn + (size_t)org * A, A);
-        const double travel = __dmul_rn(__dadd_rn(td, tc), prm.flight_time_scale);
-        if (neg_cov_out) neg_cov_out[org] = neg_cov;
-        if (obj) {
-            obj[(size_t)org * 2 + 0] = feasible ? neg_cov : 0.0;
-            obj[(size_t)org * 2 + 1] = travel;
-        }
-        if (flags) {
-            flags[(size_t)org * 4 + 0] = feasible ? 1 : 0;
-            flags[(size_t)org * 4 + 2] = (uint8_t)ncomp;
-        }
-    }
+    if (tid == 0)
+        finish_objectives(s_lc, A, prm, mc, cov + (size_t)org * 8, dist + (size_t)org * A,
+                          turn + (size_t)org * A, org, obj, neg_cov_out, flags);
 }
 
 int launch_loop_closures(gcp_ctx* ctx, const int32_t* dna, uint32_t P, const double* dist,

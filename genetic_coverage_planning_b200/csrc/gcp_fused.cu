@@ -1,0 +1,498 @@
+// Fused evaluation kernel (objectives-only fast path): Organism.calcObj for one organism per
+// CTA with the chromosome, its edge ids and its sub-tile ranges held in shared memory, so the
+// DNA is read from HBM exactly once and nothing intermediate is written back.
+//
+//   phase A  path costs        mappy.py:341-352   (k_path_costs restated on shared memory)
+//   phase B  wall coverage     mappy.py:353-364   (quarter-granular bucketing, see phase B)
+//   phase C  loop closures     mappy.py:372-437   (k_loop_closures)
+//   phase D  constraints + objectives  geneticalgorithm.py:177-201
+//
+// Preconditions (checked by the launcher): pre-masked footprint store uploaded, binary map,
+// coverage_blend == 1.  The staged kernels in gcp_eval.cu remain the general path (gray maps,
+// blend < 1, all six pixel counters) and the cross-check of this one (tests/test_gpu_parity.py).
+//
+#include "gcp_common.cuh"
+#include "gcp_device.cuh"
+
+constexpr int KF_THREADS = 256;
+constexpr int KF_NW = KF_THREADS / 32;
+constexpr int KF_PPT = 12;               // items (quarters) staged per thread: MAXP <= 12 * 256
+constexpr uint32_t KF_NIL = 0xFFFFFFFFu;
+
+struct FusedShape {
+    int A, L, AL;
+    uint32_t inv_L;      // ceil(2^32 / L): s / L == __umulhi(s, inv_L) for s < 2^16
+    int T, MAXP, T3;
+    uint32_t R0;
+    uint32_t off_info, off_x, off_cst, off_lc, off_cost;   // byte offsets into dynamic smem (off_cst relative to off_x)
+};
+
+__global__ void __launch_bounds__(KF_THREADS, 5)
+k_eval_fused(const int32_t* __restrict__ dna, uint32_t P, GcpTables t, FusedShape sh,
+             gcp_params prm, gcp_map_consts mc,
+             double* __restrict__ obj, double* __restrict__ neg_cov_out,
+             double* __restrict__ dist_out, double* __restrict__ turn_out,
+             int32_t* __restrict__ lc_out, uint8_t* __restrict__ flags)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    int32_t*  s_dna  = reinterpret_cast<int32_t*>(smem);                      // [AL]
+    uint32_t* s_info = reinterpret_cast<uint32_t*>(smem + sh.off_info);       // [AL] quarter-item range per step (C: slot/next)
+    unsigned char* s_x = smem + sh.off_x;                                     // B / C tables
+    double2*  s_cst  = reinterpret_cast<double2*>(smem + sh.off_x + sh.off_cst); // [AL] {dist, turn} per step (A only; aliases s_pay/s_sr)
+    int*      s_lc   = reinterpret_cast<int*>(smem + sh.off_lc);              // [A*A]
+    double*   s_cost = reinterpret_cast<double*>(smem + sh.off_cost);         // dist[A], turn[A]
+    __shared__ int s_first_neg[GCP_MAX_AGENTS], s_len[GCP_MAX_AGENTS], s_base[GCP_MAX_AGENTS + 1];
+    __shared__ int s_bad;
+    __shared__ uint32_t s_npairs, s_overflow, s_total, s_group;
+    __shared__ uint32_t s_wsum[KF_NW];
+    __shared__ uint32_t s_cov[4];
+
+    const uint32_t org = blockIdx.x;
+    if (org >= P) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int A = sh.A, L = sh.L, AL = sh.AL;
+
+    // ------------------------------------------------------------------ load the chromosome
+    {
+        const int32_t* d = dna + (size_t)org * AL;
+        if ((AL & 3) == 0) {
+            const int4* d4 = reinterpret_cast<const int4*>(d);
+            int4* s4 = reinterpret_cast<int4*>(s_dna);
+            for (int i = tid; i < (AL >> 2); i += KF_THREADS) s4[i] = __ldg(d4 + i);
+        } else {
+            for (int i = tid; i < AL; i += KF_THREADS) s_dna[i] = __ldg(d + i);
+        }
+        if (tid == 0) { s_bad = 0; s_total = 0; }
+        for (int i = tid; i < A * A; i += KF_THREADS) s_lc[i] = 0;
+    }
+    __syncthreads();
+    // first -1 per row (step rule mappy.py:343-345) and number of valid genes (:390)
+    for (int a = warp; a < A; a += KF_NW) {
+        int first = L, cnt = 0;
+        for (int i0 = 0; i0 < L; i0 += 32) {
+            const int i = i0 + lane;
+            const int g = (i < L) ? s_dna[a * L + i] : 0;
+            const uint32_t neg = __ballot_sync(FULL, (i < L) && g < 0);
+            if (neg && first == L) first = i0 + __ffs(neg) - 1;
+            cnt += __popc(__ballot_sync(FULL, (i < L) && g != -1));
+        }
+        if (lane == 0) { s_first_neg[a] = first; s_len[a] = cnt; }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ phase A1: edge lookup
+    {
+        int bad = 0;
+        for (int s = tid; s < AL; s += KF_THREADS) {
+            const int a = (int)__umulhi((uint32_t)s, sh.inv_L);
+            const int i = s - a * L;
+            const int g = s_dna[s];
+            if (g < -1 || (g >= 0 && (uint32_t)g >= t.N)) bad |= 2;
+            uint32_t e = GCP_INVALID_EDGE, info = 0;
+            double2 cst = make_double2(0.0, 0.0);
+            const int nsteps = min(s_first_neg[a], L - 1);
+            if (i < nsteps) {
+                const uint32_t w = (uint32_t)g;
+                int nx = s_dna[s + 1];
+                const bool sentinel = nx < 0;
+                if (nx < 0) nx += (int)t.N;                  // numpy wrap: -1 -> N-1
+                if (w < t.N && nx >= 0 && (uint32_t)nx < t.N) {
+                    const uint32_t lo = __ldg(t.row_ptr + w);
+                    e = t.E + w;                             // null edge unless found (F4)
+                    bool found = false;
+                    if (t.adj8) {
+                        const uint4* rec = reinterpret_cast<const uint4*>(t.adj8 + (size_t)w * 8);
+                        #pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const uint4 q = __ldg(rec + h);
+                            if (q.x == (uint32_t)nx && !found) { e = lo + 2 * h; found = true; }
+                            if (q.z == (uint32_t)nx && !found) { e = lo + 2 * h + 1; found = true; }
+                        }
+                    } else {
+                        const uint32_t hi = __ldg(t.row_ptr + w + 1);
+                        for (uint32_t q = lo; q < hi; ++q)
+                            if (__ldg(t.col + q) == (uint32_t)nx) { e = q; found = true; break; }
+                    }
+                    if (!found && !sentinel) bad |= 1;
+                    info = __ldg(t.m_q_info + e);
+                    cst = __ldg(t.edge_cost + e);
+                }
+            }
+            s_cst[s] = cst;
+            s_info[s] = info;
+        }
+        if (bad) atomicOr(&s_bad, bad);
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ phase B: wall coverage
+    // Items are QUARTERS (16 rows x 64 px = one 128-B line) of the visited edges' pre-masked
+    // sub-tiles.  B1 counting-sorts them by (map block, quarter index): an open-addressing hash
+    // table maps block id -> slot, one shared atomicAdd per item returns its rank inside
+    // (slot, quarter).  B2: a warp owns a block; its 8-lane group g streams the block's
+    // quarter-g list (lane = one uint4 = 2 rows), ORs into registers and popcounts once per
+    // block.  No lane idles on absent quarters, no bitmap in shared memory, no bitmap atomics.
+    const int T = sh.T, MAXP = sh.MAXP;
+    uint32_t* s_keys = reinterpret_cast<uint32_t*>(s_x);      // [T] block id + 1
+    uint32_t* s_cq   = s_keys + T;                             // [T][4] count -> count<<16 | base
+    uint32_t* s_pay  = s_cq + 4 * T;                           // [MAXP] uint4 index of the quarter, then sorted
+    uint32_t* s_sr   = s_pay + MAXP;                           // [MAXP] slot<<18 | q<<16 | rank
+    const int logT = 31 - __clz(T);
+    const uint32_t myq = lane >> 3, l7 = lane & 7;
+
+    uint32_t R = sh.R0;
+    bool failed = false;
+    bool first_pass = true;                  // uniform over the CTA
+    uint32_t n_cov;
+    for (;;) {                                   // retry loop over partition count R
+        n_cov = 0;
+        bool overflow = false;
+        for (uint32_t r = 0; r < R && !overflow; ++r) {
+            for (int i = tid; i < T; i += KF_THREADS) s_keys[i] = 0;
+            for (int i = tid; i < 4 * T; i += KF_THREADS) s_cq[i] = 0;
+            if (tid == 0) { s_npairs = 0; s_overflow = 0; s_group = 0; }
+            if (first_pass && warp == 0 && lane < A) {
+                // phase A2: sequential fp64 adds in step order per agent (mappy.py:351-352),
+                // bit-identical to the reference's `+=`; the per-step costs were staged by A1
+                const double2* ca = s_cst + lane * L;
+                const int nsteps = min(s_first_neg[lane], L - 1);
+                double acc_d = 0.0, acc_t = 0.0;
+                int i = 0;
+                for (; i + 8 <= nsteps; i += 8) {
+                    double2 c[8];
+                    #pragma unroll
+                    for (int k = 0; k < 8; ++k) c[k] = ca[i + k];
+                    #pragma unroll
+                    for (int k = 0; k < 8; ++k) { acc_d = __dadd_rn(acc_d, c[k].x); acc_t = __dadd_rn(acc_t, c[k].y); }
+                }
+                for (; i < nsteps; ++i) { acc_d = __dadd_rn(acc_d, ca[i].x); acc_t = __dadd_rn(acc_t, ca[i].y); }
+                s_cost[lane] = acc_d;
+                s_cost[A + lane] = acc_t;
+                if (dist_out) dist_out[(size_t)org * A + lane] = acc_d;
+                if (turn_out) turn_out[(size_t)org * A + lane] = acc_t;
+            }
+            first_pass = false;
+            __syncthreads();
+            // ---- B1: slot + rank for every quarter item ----
+            {
+                const int bw = warp, nbw = KF_NW;
+                for (int s0 = bw * 32; s0 < AL; s0 += nbw * 32) {
+                    const int s = s0 + lane;
+                    uint32_t lo = 0, n = 0;
+                    if (s < AL) {
+                        const uint32_t inf = s_info[s];
+                        lo = inf & 0x03FFFFFFu;
+                        n = inf >> 26;
+                    }
+                    uint2 d[4];                 // {block<<2 | q, uint4 index}: one L2 round trip
+                    #pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        d[k] = (k < (int)n) ? __ldg(t.m_q_desc + lo + k) : make_uint2(0, 0);
+                    uint32_t mine = n;
+                    if (R > 1) {
+                        mine = 0;
+                        for (uint32_t k = 0; k < n; ++k)
+                            mine += ((part_block(__ldg(t.m_q_desc + lo + k).x >> 2) & (R - 1)) == r);
+                    }
+                    uint32_t incl = mine;
+                    #pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        uint32_t v = __shfl_up_sync(FULL, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                    const uint32_t total = __shfl_sync(FULL, incl, 31);
+                    if (total == 0) continue;
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(&s_npairs, total);
+                    base = __shfl_sync(FULL, base, 0);
+                    if (base + total > (uint32_t)MAXP) {
+                        if (lane == 0) s_overflow = 1;
+                        continue;
+                    }
+                    uint32_t idx = base + incl - mine;
+                    uint32_t last_blk = KF_NIL, h = 0;
+                    auto put = [&](const uint2 dsc) {
+                        const uint32_t blk = dsc.x >> 2, q = dsc.x & 3u;
+                        if (R > 1 && (part_block(blk) & (R - 1)) != r) return;
+                        if (blk != last_blk) {          // quarters of one sub-tile share the slot
+                            const uint32_t key = blk + 1;
+                            h = hash_block(blk) >> (32 - logT);
+                            int probes = 0;
+                            for (;;) {
+                                const uint32_t cur = ((volatile uint32_t*)s_keys)[h];
+                                if (cur == key) break;
+                                if (cur == 0) {
+                                    const uint32_t old = atomicCAS(&s_keys[h], 0u, key);
+                                    if (old == 0 || old == key) break;
+                                }
+                                h = (h + 1) & (T - 1);
+                                if (++probes >= T) { s_overflow = 1; return; }
+                            }
+                            last_blk = blk;
+                        }
+                        const uint32_t rank = atomicAdd(&s_cq[4 * h + q], 1u);
+                        s_pay[idx] = dsc.y;
+                        s_sr[idx] = (h << 18) | (q << 16) | rank;
+                        ++idx;
+                    };
+                    #pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k < (int)n) put(d[k]);
+                    for (uint32_t k = 4; k < n; ++k) put(__ldg(t.m_q_desc + lo + k));
+                }
+            }
+            __syncthreads();
+            overflow = (s_overflow != 0);
+            if (overflow) { __syncthreads(); break; }
+            const uint32_t npairs = s_npairs;
+            // ---- exclusive scan of the (slot, quarter) counts ----
+            {
+                const int per = 4 * T / KF_THREADS;
+                uint32_t loc = 0;
+                for (int k = 0; k < per; ++k) loc += s_cq[tid * per + k];
+                uint32_t inc = loc;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t v = __shfl_up_sync(FULL, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                if (lane == 31) s_wsum[warp] = inc;
+                __syncthreads();
+                uint32_t woff = 0;
+                for (int w2 = 0; w2 < warp; ++w2) woff += s_wsum[w2];
+                uint32_t run = woff + inc - loc;
+                for (int k = 0; k < per; ++k) {
+                    const uint32_t c = s_cq[tid * per + k];
+                    s_cq[tid * per + k] = (c << 16) | run;
+                    run += c;
+                }
+            }
+            __syncthreads();
+            // ---- place through registers so the sorted array can reuse s_pay ----
+            uint32_t ent[KF_PPT], pos[KF_PPT];
+            #pragma unroll
+            for (int k = 0; k < KF_PPT; ++k) {
+                const uint32_t i = tid + k * KF_THREADS;
+                pos[k] = KF_NIL;
+                if (i < npairs) {
+                    const uint32_t sr = s_sr[i];
+                    pos[k] = (s_cq[sr >> 16] & 0xFFFFu) + (sr & 0xFFFFu);
+                    ent[k] = s_pay[i];
+                }
+            }
+            __syncthreads();
+            #pragma unroll
+            for (int k = 0; k < KF_PPT; ++k)
+                if (pos[k] != KF_NIL) s_pay[pos[k]] = ent[k];
+            __syncthreads();
+            // ---- B2: owner warps, groups of 32 slots handed out dynamically ----
+            for (;;) {
+                uint32_t g = 0;
+                if (lane == 0) g = atomicAdd(&s_group, 1u);
+                g = __shfl_sync(FULL, g, 0);
+                if (g * 32 >= (uint32_t)T) break;
+                const uint32_t used = __ballot_sync(FULL, s_keys[g * 32 + lane] != 0u);
+                for (uint32_t m = used; m; m &= m - 1) {
+                    const uint32_t slot = g * 32 + (__ffs(m) - 1);
+                    const uint32_t cb = s_cq[4 * slot + myq];            // my quarter's list
+                    const uint32_t cnt = cb >> 16;
+                    const uint32_t* pb = s_pay + (cb & 0xFFFFu);
+                    const uint32_t maxc = __reduce_max_sync(FULL, cnt);
+                    uint4 acc = make_uint4(0, 0, 0, 0);
+                    for (uint32_t k = 0; k < maxc; k += 2) {
+                        // reading past cnt only fetches a neighbour's entry (s_pay is padded)
+                        const uint32_t i0 = pb[k], i1 = pb[k + 1];
+                        if (k < cnt) {
+                            const uint4 v = __ldg(t.m_tile + (i0 + l7));
+                            acc.x |= v.x; acc.y |= v.y; acc.z |= v.z; acc.w |= v.w;
+                        }
+                        if (k + 1 < cnt) {
+                            const uint4 v = __ldg(t.m_tile + (i1 + l7));
+                            acc.x |= v.x; acc.y |= v.y; acc.z |= v.z; acc.w |= v.w;
+                        }
+                    }
+                    n_cov += popc128(acc);
+                }
+            }
+            __syncthreads();
+        }
+        if (!overflow) break;
+        R <<= 1;
+        if (R > 4096) { failed = true; break; }
+    }
+    {
+        uint32_t v = n_cov;
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        if (lane == 0 && v) atomicAdd(&s_total, v);
+    }
+    __syncthreads();      // B's tables are dead from here
+
+    // ------------------------------------------------------------------ phase C: loop closures
+    const int T3 = sh.T3;
+    unsigned long long* s_hkey = reinterpret_cast<unsigned long long*>(s_x);      // [T3]
+    uint32_t* s_hcnt = reinterpret_cast<uint32_t*>(s_hkey + T3);                   // [T3]
+    uint8_t*  s_own  = reinterpret_cast<uint8_t*>(s_hcnt + T3);                    // [AL]
+    int32_t*  s_seq  = reinterpret_cast<int32_t*>(s_x + (((size_t)T3 * 12 + AL + 15) & ~(size_t)15)); // [AL]
+    uint16_t* s_slot = reinterpret_cast<uint16_t*>(s_info);                        // [AL]
+    uint16_t* s_next = s_slot + AL;                                                // [AL]
+    for (int i = tid; i < T3; i += KF_THREADS) { s_hkey[i] = 0ull; s_hcnt[i] = 0u; }
+    if (tid == 0) {
+        int b = 0;
+        for (int a = 0; a < A; ++a) { s_base[a] = b; b += s_len[a]; }
+        s_base[A] = b;
+    }
+    __syncthreads();
+    const int n = s_base[A];
+    // compaction: seq[pos] = gene, own[pos] = agent | first-of-row(a>=1) << 7
+    for (int a = warp; a < A; a += KF_NW) {
+        int run = s_base[a];
+        for (int i0 = 0; i0 < L; i0 += 32) {
+            const int i = i0 + lane;
+            const int g = (i < L) ? s_dna[a * L + i] : -1;
+            const bool v = g != -1;
+            const uint32_t bal = __ballot_sync(FULL, v);
+            if (v) {
+                const int pos = run + __popc(bal & ((1u << lane) - 1u));
+                s_seq[pos] = g;
+                s_own[pos] = (uint8_t)(a | ((a >= 1 && pos == s_base[a]) ? 0x80 : 0));
+            }
+            run += __popc(bal);
+        }
+    }
+    __syncthreads();
+    // pass 1: hash every key, count group sizes
+    for (int i = tid; i < n; i += KF_THREADS) {
+        const unsigned long long f = (uint32_t)s_seq[i] & 0xFFFFFFu;
+        const unsigned long long g = (uint32_t)s_seq[(i + 1 == n) ? 0 : i + 1] & 0xFFFFFFu;
+        const unsigned long long key = ((f << 24) | g) + 1ull;              // never 0
+        uint32_t h = __umulhi((uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32), (uint32_t)T3);
+        for (;;) {
+            const unsigned long long cur = ((volatile unsigned long long*)s_hkey)[h];
+            if (cur == key) break;
+            if (cur == 0ull) {
+                const unsigned long long old = atomicCAS(&s_hkey[h], 0ull, key);
+                if (old == 0ull || old == key) break;
+            }
+            h = (h + 1 == (uint32_t)T3) ? 0u : h + 1;    // T3 > n: always terminates
+        }
+        atomicAdd(&s_hcnt[h], 1u);
+        s_slot[i] = (uint16_t)h;
+    }
+    __syncthreads();
+    // pass 2: slots with a duplicate group become {head = NIL, owners = 0}
+    for (int h = tid; h < T3; h += KF_THREADS)
+        if (s_hcnt[h] >= 2u) s_hkey[h] = (unsigned long long)KF_NIL;        // lo = head, hi = owners
+    __syncthreads();
+    uint32_t* s_w = reinterpret_cast<uint32_t*>(s_hkey);                    // [2*h] head, [2*h+1] owners
+    for (int i = tid; i < n; i += KF_THREADS) {
+        const uint32_t h = s_slot[i];
+        if ((s_hcnt[h] & 0xFFFFu) < 2u) continue;
+        const uint8_t o = s_own[i];
+        s_next[i] = (uint16_t)atomicExch(&s_w[2 * h], (uint32_t)i);         // NIL -> 0xFFFF
+        atomicOr(&s_w[2 * h + 1], 1u << (o & 31));
+        if (o & 0x80) atomicOr(&s_hcnt[h], 1u << 16);                       // group touches a split (F10)
+    }
+    __syncthreads();
+    // pass 3: successor gap test (ascending consecutive positions)
+    const int thresh = prm.solo_sep_thresh;
+    for (int i = tid; i < n; i += KF_THREADS) {
+        const uint32_t h = s_slot[i];
+        const uint32_t c = s_hcnt[h];
+        if ((c & 0xFFFFu) < 2u || (c & (1u << 16))) continue;
+        uint32_t succ = 0xFFFFFFFFu;
+        for (uint32_t j = s_w[2 * h]; j != 0xFFFFu && j != KF_NIL; j = s_next[j])
+            if (j > (uint32_t)i && j < succ) succ = j;
+        if (succ != 0xFFFFFFFFu && (int)(succ - (uint32_t)i) > thresh)
+            atomicOr(&s_hcnt[h], 1u << 17);
+    }
+    __syncthreads();
+    // pass 4: one thread per duplicate group updates lc_mat
+    for (int h = tid; h < T3; h += KF_THREADS) {
+        const uint32_t c = s_hcnt[h];
+        if ((c & 0xFFFFu) < 2u || (c & (1u << 16))) continue;
+        const uint32_t owners = s_w[2 * h + 1];
+        if (__popc(owners) == 1) {
+            if (c & (1u << 17)) { const int a = __ffs(owners) - 1; atomicAdd(&s_lc[a * A + a], 1); }
+        } else {
+            for (uint32_t mx = owners; mx; mx &= mx - 1) {
+                const int x = __ffs(mx) - 1;
+                for (uint32_t my = mx & (mx - 1); my; my &= my - 1)
+                    atomicAdd(&s_lc[x * A + (__ffs(my) - 1)], 1);
+            }
+        }
+    }
+    __syncthreads();
+    if (lc_out)
+        for (int i = tid; i < A * A; i += KF_THREADS) lc_out[(size_t)org * A * A + i] = s_lc[i];
+
+    // ------------------------------------------------------------------ phase D: objectives
+    if (tid == 0) {
+        s_cov[0] = failed ? 0u : s_total; s_cov[1] = 0; s_cov[2] = 0; s_cov[3] = 0;
+        finish_objectives(s_lc, A, prm, mc, s_cov, s_cost, s_cost + A, org, obj, neg_cov_out, flags);
+        if (flags) {
+            flags[(size_t)org * 4 + 1] = (s_bad & 1) ? 0 : 1;                       // traversable
+            flags[(size_t)org * 4 + 3] = (uint8_t)(((s_bad & 2) ? 1 : 0) | (failed ? 2 : 0));
+        }
+    }
+}
+
+static inline uint32_t al16(uint32_t x) { return (x + 15u) & ~15u; }
+
+static size_t fused_shape(gcp_ctx* ctx, FusedShape& sh);
+
+// does the fused kernel's shared-memory footprint fit this (A, L)?
+bool eval_fused_fits(gcp_ctx* ctx)
+{
+    FusedShape sh;
+    const size_t smem = fused_shape(ctx, sh);
+    return smem != 0 && smem <= (size_t)ctx->max_smem_optin;
+}
+
+static size_t fused_shape(gcp_ctx* ctx, FusedShape& sh)
+{
+    sh.A = ctx->p.num_agents; sh.L = ctx->p.max_dna_len; sh.AL = sh.A * sh.L;
+    sh.inv_L = (uint32_t)((0x100000000ull + (uint64_t)sh.L - 1) / (uint64_t)sh.L);
+    // expected ~1.4 masked sub-tiles x ~1.6 quarters per executed step
+    int maxp = ctx->cov_maxpairs > 0 ? ctx->cov_maxpairs : (9 * sh.AL) / 4;
+    if (maxp < 256) maxp = 256;
+    if (maxp > KF_PPT * KF_THREADS) maxp = KF_PPT * KF_THREADS;
+    maxp = (maxp + 7) & ~7;
+    int T = ctx->cov_table;
+    if (T <= 0) { T = KF_THREADS; while (T < sh.AL / 3) T <<= 1; }
+    if (T > 8192) T = 8192;
+    sh.T = T; sh.MAXP = maxp;
+    sh.T3 = (sh.AL * 3) / 2 + 64;
+    if (sh.T3 > 65535) return 0;
+    sh.R0 = 1;
+    while ((size_t)sh.R0 * maxp < (size_t)sh.AL * 2 && sh.R0 < 4096) sh.R0 <<= 1;
+    sh.off_cst = (uint32_t)T * 20;                                    // over s_pay / s_sr
+    const uint32_t cov_b = (uint32_t)T * 20 + (uint32_t)maxp * 8 + 16;  // + pad for B2's read-ahead
+    const uint32_t a_b = sh.off_cst + (uint32_t)sh.AL * 16;
+    const uint32_t lc_b = al16((uint32_t)sh.T3 * 12 + (uint32_t)sh.AL) + (uint32_t)sh.AL * 4;
+    uint32_t x_b = cov_b > lc_b ? cov_b : lc_b;
+    if (a_b > x_b) x_b = a_b;
+    sh.off_info = al16((uint32_t)sh.AL * 4);
+    sh.off_x = sh.off_info + al16((uint32_t)sh.AL * 4);
+    sh.off_lc = sh.off_x + al16(x_b);
+    sh.off_cost = sh.off_lc + al16((uint32_t)sh.A * sh.A * 4);
+    return sh.off_cost + (size_t)sh.A * 16;
+}
+
+int launch_eval_fused(gcp_ctx* ctx, const int32_t* dna, uint32_t P, const gcp_eval_out* out,
+                      cudaStream_t st)
+{
+    if (P == 0) return 0;
+    if (!ctx->have_masked) return gcp_fail(ctx, -1, "masked footprint store not uploaded");
+    FusedShape sh;
+    const size_t smem = fused_shape(ctx, sh);
+    if (smem == 0 || smem > (size_t)ctx->max_smem_optin)
+        return gcp_fail(ctx, -3, "fused eval kernel needs %zu B shared memory (A*L too large)", smem);
+    GCP_CUDA(ctx, cudaFuncSetAttribute(k_eval_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    StageTimer tm(ctx, 1, st);
+    k_eval_fused<<<P, KF_THREADS, smem, st>>>(dna, P, ctx->t, sh, ctx->p, ctx->mc, out->obj, out->neg_cov,
+                                              out->dist, out->turn, out->lc_mat, out->flags);
+    ctx->launches++;
+    GCP_CUDA(ctx, cudaGetLastError());
+    return 0;
+}

@@ -531,8 +531,8 @@ k_crossover(const int32_t* __restrict__ parents, const int32_t* __restrict__ str
 // Organisms flip the mutation coin as a whole (:159-161); every agent row of a mutating
 // organism regrows its tail from a random cut.  One CTA looks at ORGS consecutive organisms,
 // compacts the rows that walk into a shared list, and hands them out one per THREAD.
-constexpr int MW_THREADS = 128;
-constexpr int MW_MAX_ROWS = 4096;
+constexpr int MW_THREADS = 64;
+constexpr int MW_MAX_ROWS = 2048;
 
 __global__ void __launch_bounds__(MW_THREADS)
 k_mutation_walks(int32_t* __restrict__ dna, uint32_t P, uint32_t orgs_per_cta, GcpTables t,
@@ -674,9 +674,10 @@ int launch_mutate(gcp_ctx* c, int32_t* dna, uint32_t P, uint64_t seed, uint32_t 
     StageTimer tm(c, 7, st);
     const VaryParams vp = make_vp(c);
     if (vp.mut_prob > 0.f) {
-        // expected number of walking rows per CTA ~ 2 x MW_THREADS
+        // expected number of walking rows per CTA ~ 0.8 x MW_THREADS: one row per thread and
+        // many small CTAs, because the walks are dependent-load chains that need occupancy
         const double pr = vp.mut_prob < 0.05f ? 0.05 : (vp.mut_prob > 1.f ? 1.0 : (double)vp.mut_prob);
-        uint32_t orgs = (uint32_t)(2.0 * MW_THREADS / (pr * vp.A) + 0.5);
+        uint32_t orgs = (uint32_t)(0.8 * MW_THREADS / (pr * vp.A) + 0.5);
         if (orgs < 1) orgs = 1;
         if (orgs * (uint32_t)vp.A > (uint32_t)MW_MAX_ROWS) orgs = MW_MAX_ROWS / vp.A;
         k_mutation_walks<<<(P + orgs - 1) / orgs, MW_THREADS, 0, st>>>(dna, P, orgs, c->t, vp, seed, gen, salt);

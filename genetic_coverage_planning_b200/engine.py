@@ -135,9 +135,12 @@ class FitnessEngine(object):
             raise ValueError("dna must be [P,%d,%d], got %s" % (self.A, self.L, tuple(dna.shape)))
         return dna
 
-    def evaluate(self, dna, detail=True):
+    def evaluate(self, dna, detail=True, pixel_counts=True):
         """Organism.calcObj for every organism.  dna: [P,A,L] int32 device tensor (or
-        anything to_device_dna accepts).  Returns EvalResult of device tensors."""
+        anything to_device_dna accepts).  Returns EvalResult of device tensors.
+        detail: also per-agent costs, -coverage before the feasibility zeroing, loop-closure
+        matrix; pixel_counts (with detail): the six pixel counters, which selects the general
+        coverage kernel instead of the objectives-only fast path."""
         dna = self.to_device_dna(dna)
         P = dna.shape[0]
         dev, A = self.device, self.A
@@ -151,10 +154,13 @@ class FitnessEngine(object):
             res.neg_cov = torch.empty(P, dtype=torch.float64, device=dev)
             res.dist = torch.empty((P, A), dtype=torch.float64, device=dev)
             res.turn = torch.empty((P, A), dtype=torch.float64, device=dev)
-            res.cov = torch.empty((P, 8), dtype=torch.int32, device=dev)
             res.lc_mat = torch.empty((P, A, A), dtype=torch.int32, device=dev)
             out.neg_cov, out.dist, out.turn = res.neg_cov.data_ptr(), res.dist.data_ptr(), res.turn.data_ptr()
-            out.cov, out.lc_mat = res.cov.data_ptr(), res.lc_mat.data_ptr()
+            out.lc_mat = res.lc_mat.data_ptr()
+            res.cov = None
+            if pixel_counts:
+                res.cov = torch.empty((P, 8), dtype=torch.int32, device=dev)
+                out.cov = res.cov.data_ptr()
         else:
             res.neg_cov = res.dist = res.turn = res.cov = res.lc_mat = None
         scratch = self._get_scratch(P)

@@ -261,6 +261,36 @@ def test_binary_world_bit_exact_and_fast_path(synth_setup):
     assert np.array_equal(cov_m.cpu().numpy()[:, 4], cov_g.cpu().numpy()[:, 4])
 
 
+def test_fused_kernel_equals_staged_kernels(synth_setup):
+    """The one-kernel fast path (gcp_fused.cu) against the staged path_costs / coverage_masked /
+    loop_closures kernels and the general kernel: every output identical, ragged rows,
+    non-edges, empty rows and out-of-range genes included."""
+    from genetic_coverage_planning_b200 import synth
+    sw, pw, ow, op, eng, starts = synth_setup
+    walks = synth.random_walk_population(sw.xy, sw.row_ptr, sw.col, starts, 300, 150, 200, seed=19)
+    dna = np.concatenate([walks, _random_dna(ow, 212, 6, 200, seed=20)]).astype(np.int32)
+    dna[7, 2, 5] = sw.N + 3                          # out-of-range gene -> error flag, no crash
+    dna[9, 0, 3] = -7
+    fused = eng.evaluate(dna, detail=True, pixel_counts=False)
+    eng.set_option("fused_eval", 0)
+    try:
+        staged = eng.evaluate(dna, detail=True, pixel_counts=False)
+    finally:
+        eng.set_option("fused_eval", 1)
+    general = eng.evaluate(dna, detail=True, pixel_counts=True)
+    ok = np.ones(len(dna), dtype=bool)
+    ok[[7, 9]] = False
+    for name in ("obj", "neg_cov", "dist", "turn", "lc_mat", "flags"):
+        a, b, c = (getattr(r, name).cpu().numpy() for r in (fused, staged, general))
+        assert np.array_equal(a[ok], b[ok]), name
+        assert np.array_equal(a[ok], c[ok]), name
+    assert fused.flags.cpu().numpy()[7, 3] & 1 and fused.flags.cpu().numpy()[9, 3] & 1
+    for k in (0, 1, 300, 301, 400):
+        o = fo.calc_obj(ow, dna[k].astype(int))
+        got = fused.obj.cpu().numpy()[k]
+        assert o[0] == got[0] and o[1] == got[1]
+
+
 def test_binary_world_blend(synth_setup):
     """blend < 1 needs the internal-coverage counter: general kernel, still bit-exact."""
     sw, pw, ow, op, eng, starts = synth_setup
