@@ -316,20 +316,35 @@ def main():
         ms_k3 = time_stage(lambda: eng.loop_closures(dna, d_dist, d_turn, cov, flags), reps)
         peak, peak_src = measured_peak()
         ms_k2 = ms_k2m if fast else ms_k2g
-        achieved = B_org * P / (ms_k2 * 1e-3) / 1e9
-        roofline = {"bound": "hbm",
-                    "kernel": ("k_coverage_masked (bitset union + popcount, pre-masked footprint "
-                               "store; the coverage kernel of the timed step)") if fast else
-                              "k_coverage (bitset union + popcount against map planes)",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": known_traffic(args.config), "peak_source": peak_src,
-                    "algorithmic_bytes_per_organism": B_org, "organisms_per_launch": P,
-                    "ms_per_launch": ms_k2,
-                    "kernel_ms": {"path_costs": ms_k1, "coverage_masked": ms_k2m,
-                                  "coverage_general_all_counters": ms_k2g,
-                                  "loop_closures": ms_k3},
-                    "general_kernel_frac": (B_org * P / (ms_k2g * 1e-3) / 1e9) / peak,
-                    "eval_frac_of_peak": (B_org * P / (ms_per_step * 1e-3) / 1e9) / peak}
+        staged = {"path_costs": ms_k1, "coverage_masked": ms_k2m,
+                  "coverage_general_all_counters": ms_k2g, "loop_closures": ms_k3}
+        if fast:
+            # the timed step IS one kernel (k_eval_fused): its launch time = ms_per_step
+            achieved = B_org * P / (ms_per_step * 1e-3) / 1e9
+            roofline = {"bound": "hbm",
+                        "kernel": "k_eval_fused (path-cost gather + footprint bitset union/popcount + "
+                                  "loop closures + objectives, one CTA per organism; the only kernel of "
+                                  "the timed step)",
+                        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": known_traffic(args.config), "peak_source": peak_src,
+                        "algorithmic_bytes_per_organism": B_org, "organisms_per_launch": P,
+                        "ms_per_launch": ms_per_step,
+                        "note": "achieved = SURVEY 8d algorithmic bytes (one 512-B footprint tile + 32-B "
+                                "edge record per executed step + DNA + result) / launch time; the real "
+                                "DRAM traffic (`traffic`, ncu) is ~1% of that because the footprint store "
+                                "stays in L2 - the kernel is instruction-issue / latency bound",
+                        "staged_kernels_ms": staged,
+                        "staged_coverage_frac": (B_org * P / (ms_k2 * 1e-3) / 1e9) / peak,
+                        "general_kernel_frac": (B_org * P / (ms_k2g * 1e-3) / 1e9) / peak}
+        else:
+            achieved = B_org * P / (ms_k2 * 1e-3) / 1e9
+            roofline = {"bound": "hbm",
+                        "kernel": "k_coverage (bitset union + popcount against map planes)",
+                        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": known_traffic(args.config), "peak_source": peak_src,
+                        "algorithmic_bytes_per_organism": B_org, "organisms_per_launch": P,
+                        "ms_per_launch": ms_k2, "staged_kernels_ms": staged,
+                        "eval_frac_of_peak": (B_org * P / (ms_per_step * 1e-3) / 1e9) / peak}
         # ---------------- ranking leg: maximin + arena order over 2P gladiators ---------
         obj2 = torch.cat([res.obj, res.obj.flip(0) * 1.0001])
         constr = -worlds.GEN_PARAMS_6['coverage_constr_0']
@@ -365,8 +380,8 @@ def main():
         g1.record()
         torch.cuda.synchronize()
         ms_gen = g0.elapsed_time(g1) / n_gen
-        stage_names = ["path_costs", "coverage", "loop_closures", "maximin", "arena_order",
-                       "select", "crossover", "mutate"]
+        stage_names = ["path_costs", "eval_fused_or_coverage", "loop_closures", "maximin",
+                       "arena_order", "select", "crossover", "mutate"]
         last = {n: eng.stage_ms(k) for k, n in enumerate(stage_names)}
         eng.set_timing(False)
         extras["generation"] = {"generations_per_s": 1000.0 / ms_gen, "ms_per_generation": ms_gen,
@@ -394,27 +409,35 @@ def main():
                 "collective": "all-gather of objective records (16 B/organism) + all-gather of "
                               "fits (8 B/organism) over NCCL; maximin rows sharded by rank"}
         # ---------------- end to end: host DNA in, host objectives out ------------------
-        dna_h = dna.cpu().pin_memory()
-        obj_h = torch.empty((P, 2), dtype=torch.float64).pin_memory()
-        flg_h = torch.empty((P, 4), dtype=torch.uint8).pin_memory()
-        for _ in range(2):
-            eng.evaluate_host(dna_h, obj_h, flg_h)
-        barrier()
-        t0 = time.perf_counter()
-        n_e2e = max(3, min(args.steps, 10))
-        for _ in range(n_e2e):
-            eng.evaluate_host(dna_h, obj_h, flg_h)
-        dt = (time.perf_counter() - t0) / n_e2e
-        if distributed:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        assert torch.equal(obj_h, res.obj.cpu()), "host path result differs from device path"
+        def e2e_leg(dna_h):
+            obj_h = torch.empty((P, 2), dtype=torch.float64).pin_memory()
+            flg_h = torch.empty((P, 4), dtype=torch.uint8).pin_memory()
+            for _ in range(2):
+                eng.evaluate_host(dna_h, obj_h, flg_h)
+            barrier()
+            t0 = time.perf_counter()
+            n_e2e = max(3, min(args.steps, 10))
+            for _ in range(n_e2e):
+                eng.evaluate_host(dna_h, obj_h, flg_h)
+            dt = (time.perf_counter() - t0) / n_e2e
+            if distributed:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            assert torch.equal(obj_h, res.obj.cpu()), "host path result differs from device path"
+            return dt
+        use16 = fast and w.N <= 32767
+        dt32 = e2e_leg(dna.cpu().pin_memory())
+        dt = e2e_leg(dna.to(torch.int16).cpu().pin_memory()) if use16 else dt32
+        gsz = 2 if use16 else 4
         e2e = {"value": world_size * P / dt, "unit": UNIT,
-               "h2d_bytes_per_step": int(P * A * L * 4), "d2h_bytes_per_step": int(P * 20),
+               "h2d_bytes_per_step": int(P * A * L * gsz), "d2h_bytes_per_step": int(P * 20),
                "ms_per_step": dt * 1e3,
-               "api": "FitnessEngine.evaluate_host -> gcp_eval_host (pinned host buffers, "
-                      "chunked H2D / kernels / D2H on two streams)"}
+               "api": "FitnessEngine.evaluate_host -> gcp_eval_host%s (pinned host chromosomes in, "
+                      "objectives + flags out; chunked H2D / kernel / D2H on two streams)"
+                      % ("16, int16 genes" if use16 else ""),
+               "int32_genes": {"value": world_size * P / dt32, "ms_per_step": dt32 * 1e3,
+                               "h2d_bytes_per_step": int(P * A * L * 4)}}
         # ---------------- CPU baseline (rank 0, N=1 only) --------------------------------
         if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
             sample = dna[:args.cpu_sample].cpu().numpy()
@@ -445,9 +468,9 @@ def main():
                                    % (args.config, cfg['size'], w.N, w.E, A, L, cfg['walk'], P),
                        "organisms_per_gpu": P, "global_population": P * world_size,
                        "mean_executed_steps_per_organism": S_mean,
-                       "l2": "per-step inputs (dna + edge ids, %.0f MB) exceed the 126 MB L2; no "
-                             "flush; the %.0f MB footprint store is reused inside a launch"
-                             % (2 * P * A * L * 4 / 1e6, pw.n_quarters * 128 / 1e6),
+                       "l2": "per-step input (dna, %.0f MB) exceeds the 126 MB L2; no flush; the "
+                             "%.0f MB pre-masked footprint store is reused inside a launch"
+                             % (P * A * L * 4 / 1e6, pw.m_n_quarters * 128 / 1e6),
                        "parallelism": "population sharded, tables replicated, no collective"},
             "gpu_launches": int(launches), "clocks": clocks,
         }

@@ -303,7 +303,7 @@ int gcp_eval(gcp_ctx* c, const int32_t* dna, uint32_t P, const gcp_eval_out* out
     const bool fast = c->have_masked && c->n_gray == 0 && c->p.coverage_blend == 1.0 &&
                       !out->cov && !c->force_general;
     if (fast && c->fused_eval && c->t.m_q_info && eval_fused_fits(c))   // one kernel, no scratch (gcp_fused.cu)
-        return launch_eval_fused(c, dna, P, out, (cudaStream_t)stream);
+        return launch_eval_fused(c, dna, 0, P, out, (cudaStream_t)stream);
     if (scratch_bytes < gcp_eval_scratch_bytes(c, P) || !scratch)
         return gcp_fail(c, -1, "gcp_eval: scratch too small (%zu < %zu)", scratch_bytes,
                         gcp_eval_scratch_bytes(c, P));
@@ -333,18 +333,59 @@ int gcp_eval(gcp_ctx* c, const int32_t* dna, uint32_t P, const gcp_eval_out* out
     return 0;
 }
 
+static bool fast_path(gcp_ctx* c, const gcp_eval_out* out)
+{
+    return c->have_masked && c->n_gray == 0 && c->p.coverage_blend == 1.0 && !out->cov &&
+           !c->force_general && c->fused_eval && c->t.m_q_info && eval_fused_fits(c);
+}
+
+int gcp_eval16(gcp_ctx* c, const int16_t* dna, uint32_t P, const gcp_eval_out* out, void* stream)
+{
+    int r = ready(c); if (r) return r;
+    if (!out) return gcp_fail(c, -1, "gcp_eval16: out is NULL");
+    if (P == 0) return 0;
+    if (c->t.N > 32767) return gcp_fail(c, -1, "gcp_eval16: int16 genes need N <= 32767 waypoints (N=%u)", c->t.N);
+    if (!fast_path(c, out))
+        return gcp_fail(c, -1, "gcp_eval16: only the fused objectives path takes int16 genes "
+                               "(binary map, coverage_blend == 1, no pixel counters)");
+    return launch_eval_fused(c, dna, 1, P, out, (cudaStream_t)stream);
+}
+
+static int eval_host_impl(gcp_ctx* c, const void* dna_host, int gene16, uint32_t P, double* obj_host,
+                          uint8_t* flags_host);
+
 int gcp_eval_host(gcp_ctx* c, const int32_t* dna_host, uint32_t P, double* obj_host,
                   uint8_t* flags_host)
+{
+    return eval_host_impl(c, dna_host, 0, P, obj_host, flags_host);
+}
+
+int gcp_eval_host16(gcp_ctx* c, const int16_t* dna_host, uint32_t P, double* obj_host,
+                    uint8_t* flags_host)
+{
+    if (c && c->have_graph && c->t.N > 32767)
+        return gcp_fail(c, -1, "gcp_eval_host16: int16 genes need N <= 32767 waypoints");
+    return eval_host_impl(c, dna_host, 1, P, obj_host, flags_host);
+}
+
+static int eval_host_impl(gcp_ctx* c, const void* dna_host, int gene16, uint32_t P, double* obj_host,
+                          uint8_t* flags_host)
 {
     int r = ready(c); if (r) return r;
     if (P == 0) return 0;
     GCP_CUDA(c, cudaSetDevice(c->device));
     const size_t A = c->p.num_agents, L = c->p.max_dna_len;
     // chunk so that copy-in, kernels and copy-out of neighbouring chunks overlap
-    uint32_t chunk = 8192;
+    uint32_t chunk = 4096;
     if (chunk > P) chunk = P;
-    const size_t dna_b = align256((size_t)chunk * A * L * 4);
-    const size_t scr_b = align256(gcp_eval_scratch_bytes(c, chunk));
+    const size_t gsz = gene16 ? 2 : 4;
+    gcp_eval_out probe;
+    memset(&probe, 0, sizeof(probe));
+    const bool fused = fast_path(c, &probe);
+    if (gene16 && !fused)
+        return gcp_fail(c, -1, "gcp_eval_host16: only the fused objectives path takes int16 genes");
+    const size_t dna_b = align256((size_t)chunk * A * L * gsz);
+    const size_t scr_b = fused ? 256 : align256(gcp_eval_scratch_bytes(c, chunk));
     const size_t obj_b = align256((size_t)chunk * 16);
     const size_t flg_b = align256((size_t)chunk * 4);
     const size_t per = dna_b + scr_b + obj_b + flg_b;
@@ -361,17 +402,19 @@ int gcp_eval_host(gcp_ctx* c, const int32_t* dna_host, uint32_t P, double* obj_h
         const uint32_t n = (P - o0 < chunk) ? (P - o0) : chunk;
         cudaStream_t st = c->hstream[k & 1];
         char* base = reinterpret_cast<char*>(c->stage_dev) + (size_t)(k & 1) * per;
-        int32_t* d_dna = reinterpret_cast<int32_t*>(base);
+        void* d_dna = base;
         void* d_scr = base + dna_b;
         double* d_obj = reinterpret_cast<double*>(base + dna_b + scr_b);
         uint8_t* d_flg = reinterpret_cast<uint8_t*>(base + dna_b + scr_b + obj_b);
-        GCP_CUDA(c, cudaMemcpyAsync(d_dna, dna_host + (size_t)o0 * A * L, (size_t)n * A * L * 4,
-                                    cudaMemcpyHostToDevice, st));
+        GCP_CUDA(c, cudaMemcpyAsync(d_dna, reinterpret_cast<const char*>(dna_host) + (size_t)o0 * A * L * gsz,
+                                    (size_t)n * A * L * gsz, cudaMemcpyHostToDevice, st));
         gcp_eval_out out;
         memset(&out, 0, sizeof(out));
         out.obj = d_obj;
         out.flags = d_flg;
-        if ((r = gcp_eval(c, d_dna, n, &out, d_scr, scr_b, st))) return r;
+        if (gene16) r = gcp_eval16(c, reinterpret_cast<const int16_t*>(d_dna), n, &out, st);
+        else r = gcp_eval(c, reinterpret_cast<const int32_t*>(d_dna), n, &out, d_scr, scr_b, st);
+        if (r) return r;
         if (obj_host)
             GCP_CUDA(c, cudaMemcpyAsync(obj_host + (size_t)o0 * 2, d_obj, (size_t)n * 16,
                                         cudaMemcpyDeviceToHost, st));

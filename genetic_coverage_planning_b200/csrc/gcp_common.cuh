@@ -99,7 +99,7 @@ int launch_coverage(gcp_ctx*, const uint32_t* edge_ids, uint32_t P, uint32_t* co
 int launch_loop_closures(gcp_ctx*, const int32_t* dna, uint32_t P, const double* dist,
                          const double* turn, const uint32_t* cov, int32_t* lc, double* obj,
                          double* neg_cov, uint8_t* flags, cudaStream_t);
-int launch_eval_fused(gcp_ctx*, const int32_t* dna, uint32_t P, const gcp_eval_out* out,
+int launch_eval_fused(gcp_ctx*, const void* dna, int gene16, uint32_t P, const gcp_eval_out* out,
                       cudaStream_t);
 bool eval_fused_fits(gcp_ctx*);
 int launch_maximin(gcp_ctx*, const double* obj, uint32_t n, double constr, uint32_t r0,

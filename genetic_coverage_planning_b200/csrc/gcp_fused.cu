@@ -23,12 +23,13 @@ struct FusedShape {
     int A, L, AL;
     uint32_t inv_L;      // ceil(2^32 / L): s / L == __umulhi(s, inv_L) for s < 2^16
     int T, MAXP, T3;
+    int gene16;          // chromosome stored as int16 in global memory
     uint32_t R0;
     uint32_t off_info, off_x, off_cst, off_lc, off_cost;   // byte offsets into dynamic smem (off_cst relative to off_x)
 };
 
 __global__ void __launch_bounds__(KF_THREADS, 5)
-k_eval_fused(const int32_t* __restrict__ dna, uint32_t P, GcpTables t, FusedShape sh,
+k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape sh,
              gcp_params prm, gcp_map_consts mc,
              double* __restrict__ obj, double* __restrict__ neg_cov_out,
              double* __restrict__ dist_out, double* __restrict__ turn_out,
@@ -53,8 +54,27 @@ k_eval_fused(const int32_t* __restrict__ dna, uint32_t P, GcpTables t, FusedShap
     const int A = sh.A, L = sh.L, AL = sh.AL;
 
     // ------------------------------------------------------------------ load the chromosome
-    {
-        const int32_t* d = dna + (size_t)org * AL;
+    if (sh.gene16) {                       // int16 chromosome (N < 32768): half the bytes to move
+        const int16_t* d = reinterpret_cast<const int16_t*>(dna_v) + (size_t)org * AL;
+        if ((AL & 7) == 0) {
+            const int4* d8 = reinterpret_cast<const int4*>(d);
+            for (int i = tid; i < (AL >> 3); i += KF_THREADS) {
+                const int4 v = __ldg(d8 + i);
+                int4 lo, hi;
+                lo.x = (int)(short)(v.x & 0xFFFF); lo.y = v.x >> 16;
+                lo.z = (int)(short)(v.y & 0xFFFF); lo.w = v.y >> 16;
+                hi.x = (int)(short)(v.z & 0xFFFF); hi.y = v.z >> 16;
+                hi.z = (int)(short)(v.w & 0xFFFF); hi.w = v.w >> 16;
+                reinterpret_cast<int4*>(s_dna)[2 * i] = lo;
+                reinterpret_cast<int4*>(s_dna)[2 * i + 1] = hi;
+            }
+        } else {
+            for (int i = tid; i < AL; i += KF_THREADS) s_dna[i] = (int)__ldg(d + i);
+        }
+        if (tid == 0) { s_bad = 0; s_total = 0; }
+        for (int i = tid; i < A * A; i += KF_THREADS) s_lc[i] = 0;
+    } else {
+        const int32_t* d = reinterpret_cast<const int32_t*>(dna_v) + (size_t)org * AL;
         if ((AL & 3) == 0) {
             const int4* d4 = reinterpret_cast<const int4*>(d);
             int4* s4 = reinterpret_cast<int4*>(s_dna);
@@ -479,13 +499,14 @@ static size_t fused_shape(gcp_ctx* ctx, FusedShape& sh)
     return sh.off_cost + (size_t)sh.A * 16;
 }
 
-int launch_eval_fused(gcp_ctx* ctx, const int32_t* dna, uint32_t P, const gcp_eval_out* out,
+int launch_eval_fused(gcp_ctx* ctx, const void* dna, int gene16, uint32_t P, const gcp_eval_out* out,
                       cudaStream_t st)
 {
     if (P == 0) return 0;
     if (!ctx->have_masked) return gcp_fail(ctx, -1, "masked footprint store not uploaded");
     FusedShape sh;
     const size_t smem = fused_shape(ctx, sh);
+    sh.gene16 = gene16;
     if (smem == 0 || smem > (size_t)ctx->max_smem_optin)
         return gcp_fail(ctx, -3, "fused eval kernel needs %zu B shared memory (A*L too large)", smem);
     GCP_CUDA(ctx, cudaFuncSetAttribute(k_eval_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

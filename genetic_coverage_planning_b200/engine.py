@@ -174,16 +174,32 @@ class FitnessEngine(object):
         dna_host int32 [P,A,L] (pinned torch tensor or numpy); returns (obj, flags) on host."""
         if isinstance(dna_host, np.ndarray):
             dna_host = torch.from_numpy(np.ascontiguousarray(dna_host, dtype=np.int32))
-        assert dna_host.dtype == torch.int32 and dna_host.is_contiguous() and not dna_host.is_cuda
+        assert dna_host.dtype in (torch.int32, torch.int16) and dna_host.is_contiguous() \
+            and not dna_host.is_cuda
         P = dna_host.shape[0]
         if obj_host is None:
             obj_host = torch.empty((P, 2), dtype=torch.float64).pin_memory()
         if flags_host is None:
             flags_host = torch.empty((P, 4), dtype=torch.uint8).pin_memory()
-        self._check(self.lib.gcp_eval_host(self.ctx, C.c_void_p(dna_host.data_ptr()), P,
-                                           C.c_void_p(obj_host.data_ptr()),
-                                           C.c_void_p(flags_host.data_ptr())))
+        fn = self.lib.gcp_eval_host16 if dna_host.dtype == torch.int16 else self.lib.gcp_eval_host
+        self._check(fn(self.ctx, C.c_void_p(dna_host.data_ptr()), P,
+                       C.c_void_p(obj_host.data_ptr()), C.c_void_p(flags_host.data_ptr())))
         return obj_host, flags_host
+
+    def evaluate16(self, dna16):
+        """Objectives from an int16 device chromosome tensor [P,A,L] (N <= 32767): fused path only."""
+        assert dna16.is_cuda and dna16.dtype == torch.int16 and dna16.is_contiguous()
+        P = dna16.shape[0]
+        res = EvalResult()
+        res.obj = torch.empty((P, 2), dtype=torch.float64, device=self.device)
+        res.flags = torch.zeros((P, 4), dtype=torch.uint8, device=self.device)
+        res.neg_cov = res.dist = res.turn = res.cov = res.lc_mat = None
+        out = GcpEvalOut()
+        out.obj = res.obj.data_ptr()
+        out.flags = res.flags.data_ptr()
+        self._check(self.lib.gcp_eval16(self.ctx, C.c_void_p(dna16.data_ptr()), P, C.byref(out),
+                                        self._stream()))
+        return res
 
     # ---- individual stages (tests / profiling) ------------------------------
     def path_costs(self, dna, with_step_info=False):

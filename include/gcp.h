@@ -128,6 +128,11 @@ size_t gcp_eval_scratch_bytes(gcp_ctx* ctx, uint32_t n_org);
 int    gcp_eval(gcp_ctx* ctx, const int32_t* dna_dev, uint32_t n_org,
                 const gcp_eval_out* out, void* scratch_dev, size_t scratch_bytes,
                 void* stream);
+/* Same evaluation from int16 genes (dev int16 [P][A][L], -1 padded): halves the chromosome
+ * bytes moved over PCIe / HBM.  Needs N <= 32767 waypoints and the fused objectives-only path
+ * (pre-masked footprints uploaded, binary map, coverage_blend == 1, out->cov == NULL). */
+int    gcp_eval16(gcp_ctx* ctx, const int16_t* dna_dev, uint32_t n_org, const gcp_eval_out* out,
+                  void* stream);
 /* Individual stages (same buffers; used by tests / profiling). edge_ids: dev u32 [P][A][L];
  * step_info (optional, needs the masked store): dev u32 [P][A][L], per step the masked
  * sub-tile range of its edge (first | count<<28), 0 where no step is executed. */
@@ -149,6 +154,8 @@ int gcp_loop_closures(gcp_ctx* ctx, const int32_t* dna_dev, uint32_t n_org,
  * is; pageable memory works but is slower. */
 int gcp_eval_host(gcp_ctx* ctx, const int32_t* dna_host, uint32_t n_org,
                   double* obj_host, uint8_t* flags_host);
+int gcp_eval_host16(gcp_ctx* ctx, const int16_t* dna_host, uint32_t n_org,
+                    double* obj_host, uint8_t* flags_host);
 
 /* ---- ranking: GeneticalGorithm.rackNstack + arena ordering -------------------------
  * Replaces geneticalgorithm.py:86-123 (maximin fitness) and gori_tools.py:232-236

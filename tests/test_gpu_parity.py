@@ -291,6 +291,25 @@ def test_fused_kernel_equals_staged_kernels(synth_setup):
         assert o[0] == got[0] and o[1] == got[1]
 
 
+def test_int16_genes_equal_int32(synth_setup):
+    """gcp_eval16 / gcp_eval_host16 (half-width chromosomes) give the int32 results bit for bit."""
+    import torch
+    from genetic_coverage_planning_b200 import synth
+    sw, pw, ow, op, eng, starts = synth_setup
+    walks = synth.random_walk_population(sw.xy, sw.row_ptr, sw.col, starts, 5000, 150, 200, seed=23)
+    dna = np.concatenate([walks, _random_dna(ow, 121, 6, 200, seed=24)]).astype(np.int32)
+    want = eng.evaluate(dna, detail=False)
+    d16 = torch.from_numpy(dna.astype(np.int16))
+    got = eng.evaluate16(d16.cuda())
+    assert np.array_equal(got.obj.cpu().numpy(), want.obj.cpu().numpy())
+    assert np.array_equal(got.flags.cpu().numpy(), want.flags.cpu().numpy())
+    obj_h, flags_h = eng.evaluate_host(d16.pin_memory())
+    assert np.array_equal(obj_h.numpy(), want.obj.cpu().numpy())
+    assert np.array_equal(flags_h.numpy(), want.flags.cpu().numpy())
+    obj_h, flags_h = eng.evaluate_host(torch.from_numpy(dna).pin_memory())
+    assert np.array_equal(obj_h.numpy(), want.obj.cpu().numpy())
+
+
 def test_binary_world_blend(synth_setup):
     """blend < 1 needs the internal-coverage counter: general kernel, still bit-exact."""
     sw, pw, ow, op, eng, starts = synth_setup
