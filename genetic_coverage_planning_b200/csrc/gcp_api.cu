@@ -62,6 +62,7 @@ void gcp_destroy(gcp_ctx* c)
     cudaSetDevice(c->device);
     for (int i = 0; i < c->n_owned; ++i) cudaFree(c->owned[i]);
     if (c->stage_dev) cudaFree(c->stage_dev);
+    if (c->vary_scratch) cudaFree(c->vary_scratch);
     for (int s = 0; s < 2; ++s) if (c->hstream[s]) cudaStreamDestroy(c->hstream[s]);
     for (int s = 0; s < GCP_NUM_STAGES; ++s) { cudaEventDestroy(c->ev_beg[s]); cudaEventDestroy(c->ev_end[s]); }
     delete c;
@@ -491,9 +492,11 @@ int gcp_select_vary(gcp_ctx* c, const int32_t* parents, const double* parent_fit
 {
     int r = vary_ready(c); if (r) return r;
     if (P == 0) return 0;
-    if (!scratch || scratch_bytes < (size_t)P * 16) return gcp_fail(c, -1, "select_vary: scratch too small");
+    const size_t nt = ((size_t)P + 1023) / 1024;
+    if (!scratch || scratch_bytes < (size_t)P * 12 + nt * 16)
+        return gcp_fail(c, -1, "select_vary: scratch too small (need 12 * n_org + 16 * ceil(n_org / 1024) bytes)");
     double* cum = reinterpret_cast<double*>(scratch);
-    int32_t* strong = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(scratch) + (size_t)P * 8);
+    int32_t* strong = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(scratch) + ((size_t)P + 2 * nt) * 8);
     // the single U(0, 1/M) draw of lowVarSample (gori_tools.py:217), from the seed/generation
     uint64_t z = seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(gen + 1));
     z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 27; z *= 0x94D049BB133111EBull; z ^= z >> 31;

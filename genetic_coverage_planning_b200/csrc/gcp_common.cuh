@@ -62,6 +62,7 @@ struct gcp_ctx {
     bool ev_valid[GCP_NUM_STAGES] = {};
     // host-eval staging (gcp_eval_host)
     void* stage_dev = nullptr; size_t stage_bytes = 0;
+    void* vary_scratch = nullptr; size_t vary_scratch_bytes = 0;   // mutation row list (gcp_vary.cu)
     cudaStream_t hstream[2] = {};
     // coverage kernel tuning (0 = auto)
     int cov_table = 0, cov_maxpairs = 0;

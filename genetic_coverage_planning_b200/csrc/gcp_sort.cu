@@ -229,20 +229,38 @@ __global__ void k_gather_sorted(const double2* __restrict__ sc, const uint32_t* 
     inv[p] = k;
 }
 
-__global__ void __launch_bounds__(1024)
-k_prefix_min2(const double* __restrict__ sb, uint32_t n, double2* __restrict__ rec,
-              uint32_t* __restrict__ arg)
+// Block-wide inclusive scan of Min2 over 256 threads x 4 consecutive elements (1024 per CTA).
+// mode 0: write only the CTA total to partial[blockIdx.x]; mode 1: apply the exclusive prefix
+// of the preceding CTAs (prefix[blockIdx.x]) and write rec / arg.
+constexpr int PM_THREADS = 256;
+constexpr int PM_ITEMS = 4;
+constexpr int PM_TILE = PM_THREADS * PM_ITEMS;
+
+__device__ __forceinline__ Min2 min2_identity()
 {
-    __shared__ Min2 s_w[32];
+    Min2 m; m.m1 = CUDART_INF; m.m2 = CUDART_INF; m.i1 = 0xFFFFFFFFu;
+    return m;
+}
+__device__ __forceinline__ void min2_push(Min2& m, double v, uint32_t k)
+{
+    if (v < m.m1) { m.m2 = m.m1; m.m1 = v; m.i1 = k; }
+    else if (v < m.m2) m.m2 = v;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(PM_THREADS)
+k_prefix_min2(const double* __restrict__ sb, uint32_t n, Min2* __restrict__ partial,
+              const Min2* __restrict__ prefix, double2* __restrict__ rec, uint32_t* __restrict__ arg)
+{
+    __shared__ Min2 s_w[PM_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t per = (n + 1023) / 1024;
-    const uint32_t b = min(n, tid * per), e = min(n, b + per);
-    Min2 loc; loc.m1 = CUDART_INF; loc.m2 = CUDART_INF; loc.i1 = 0xFFFFFFFFu;
-    #pragma unroll 8
-    for (uint32_t k = b; k < e; ++k) {
-        const double v = sb[k];
-        if (v < loc.m1) { loc.m2 = loc.m1; loc.m1 = v; loc.i1 = k; }
-        else if (v < loc.m2) loc.m2 = v;
+    const uint32_t b = blockIdx.x * PM_TILE + tid * PM_ITEMS;
+    double v[PM_ITEMS];
+    Min2 loc = min2_identity();
+    #pragma unroll
+    for (int k = 0; k < PM_ITEMS; ++k) {
+        v[k] = (b + k < n) ? sb[b + k] : CUDART_INF;
+        if (b + k < n) min2_push(loc, v[k], b + k);
     }
     Min2 inc = loc;
     #pragma unroll
@@ -252,32 +270,56 @@ k_prefix_min2(const double* __restrict__ sb, uint32_t n, double2* __restrict__ r
     }
     if (lane == 31) s_w[warp] = inc;
     __syncthreads();
-    if (warp == 0) {
-        Min2 w = s_w[lane];
-        #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const Min2 t = min2_shfl_up(w, o);
-            if (lane >= o) w = min2_combine(t, w);
+    if (MODE == 0) {
+        if (tid == 0) {
+            Min2 tot = s_w[0];
+            for (int w = 1; w < PM_THREADS / 32; ++w) tot = min2_combine(tot, s_w[w]);
+            partial[blockIdx.x] = tot;
         }
-        s_w[lane] = w;                                     // inclusive over warps
+        return;
     }
-    __syncthreads();
-    // exclusive prefix of this thread = (warps before) ++ (lanes before in this warp)
-    Min2 ex; ex.m1 = CUDART_INF; ex.m2 = CUDART_INF; ex.i1 = 0xFFFFFFFFu;
-    if (warp > 0) ex = s_w[warp - 1];
+    Min2 ex = prefix[blockIdx.x];
+    for (int w = 0; w < warp; ++w) ex = min2_combine(ex, s_w[w]);
     {
         const Min2 prev = min2_shfl_up(inc, 1);
         if (lane > 0) ex = min2_combine(ex, prev);
     }
     Min2 run = ex;
-    #pragma unroll 8
-    for (uint32_t k = b; k < e; ++k) {
-        const double v = sb[k];
-        if (v < run.m1) { run.m2 = run.m1; run.m1 = v; run.i1 = k; }
-        else if (v < run.m2) run.m2 = v;
-        rec[k] = make_double2(run.m1, run.m2);
-        arg[k] = run.i1;
+    #pragma unroll
+    for (int k = 0; k < PM_ITEMS; ++k) {
+        if (b + k < n) {
+            min2_push(run, v[k], b + k);
+            rec[b + k] = make_double2(run.m1, run.m2);
+            arg[b + k] = run.i1;
+        }
     }
+}
+
+// exclusive scan of the CTA totals, one CTA (sequential per thread chunk + warp/block scan)
+__global__ void __launch_bounds__(1024)
+k_prefix_min2_partials(const Min2* __restrict__ partial, uint32_t nb, Min2* __restrict__ prefix)
+{
+    __shared__ Min2 s_w[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t per = (nb + 1023) / 1024;
+    const uint32_t b = min(nb, tid * per), e = min(nb, b + per);
+    Min2 loc = min2_identity();
+    for (uint32_t k = b; k < e; ++k) loc = min2_combine(loc, partial[k]);
+    Min2 inc = loc;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const Min2 t = min2_shfl_up(inc, o);
+        if (lane >= o) inc = min2_combine(t, inc);
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    Min2 ex = min2_identity();
+    for (int w = 0; w < warp; ++w) ex = min2_combine(ex, s_w[w]);
+    {
+        const Min2 prev = min2_shfl_up(inc, 1);
+        if (lane > 0) ex = min2_combine(ex, prev);
+    }
+    for (uint32_t k = b; k < e; ++k) { prefix[k] = ex; ex = min2_combine(ex, partial[k]); }
 }
 
 __global__ void __launch_bounds__(256)
@@ -328,7 +370,8 @@ size_t sort_scratch_bytes(uint32_t n)
     // keys x2, vals x2, hist, sa, sb, rec, arg, inv
     return 2 * al256((size_t)n * 8) + 2 * al256((size_t)n * 4) +
            al256((size_t)rs_blocks(n) * RS_BINS * 4) + 2 * al256((size_t)n * 8) +
-           al256((size_t)n * 16) + 2 * al256((size_t)n * 4) + 256;
+           al256((size_t)n * 16) + 2 * al256((size_t)n * 4) +
+           al256((size_t)2 * ((n + 1023) / 1024 + 1) * 24) + 256;
 }
 
 struct SortScratch {
@@ -336,6 +379,7 @@ struct SortScratch {
     uint32_t *vals, *vals_tmp, *hist, *arg, *inv;
     double *sa, *sb;
     double2* rec;
+    Min2* part;
 };
 
 static SortScratch carve(void* base, uint32_t n)
@@ -351,7 +395,8 @@ static SortScratch carve(void* base, uint32_t n)
     s.sb = reinterpret_cast<double*>(p);                    p += al256((size_t)n * 8);
     s.rec = reinterpret_cast<double2*>(p);                  p += al256((size_t)n * 16);
     s.arg = reinterpret_cast<uint32_t*>(p);                 p += al256((size_t)n * 4);
-    s.inv = reinterpret_cast<uint32_t*>(p);
+    s.inv = reinterpret_cast<uint32_t*>(p);                 p += al256((size_t)n * 4);
+    s.part = reinterpret_cast<Min2*>(p);
     return s;
 }
 
@@ -366,7 +411,13 @@ int launch_maximin_sweep(gcp_ctx* ctx, const double2* sc, uint32_t n, uint32_t r
     int r = radix_sort_pairs(ctx, s.keys, s.vals, n, s.keys_tmp, s.vals_tmp, s.hist, st);
     if (r) return r;
     k_gather_sorted<<<(n + 255) / 256, 256, 0, st>>>(sc, s.vals, n, s.sa, s.sb, s.inv);
-    k_prefix_min2<<<1, 1024, 0, st>>>(s.sb, n, s.rec, s.arg);
+    {
+        const uint32_t nb = (n + PM_TILE - 1) / PM_TILE;
+        k_prefix_min2<0><<<nb, PM_THREADS, 0, st>>>(s.sb, n, s.part, nullptr, nullptr, nullptr);
+        k_prefix_min2_partials<<<1, 1024, 0, st>>>(s.part, nb, s.part + nb);
+        k_prefix_min2<1><<<nb, PM_THREADS, 0, st>>>(s.sb, n, nullptr, s.part + nb, s.rec, s.arg);
+        ctx->launches += 2;
+    }
     const uint32_t rows = r1 - r0;
     k_maximin_sweep<<<(rows + 255) / 256, 256, 0, st>>>(sc, n, s.sa, s.rec, s.arg, s.inv, r0, r1, fit);
     ctx->launches += 3;

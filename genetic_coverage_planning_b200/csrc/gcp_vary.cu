@@ -375,45 +375,96 @@ __device__ int w_post_mutate(const GcpTables& t, const VaryParams& vp, int32_t* 
 
 // ------------------------------------------------------------------ lowVarSample
 // w_i = (1+gamma)^(-fit_i - max(-fit)); normalised; u_m = r + m/M; index = first i whose
-// inclusive cumulative weight reaches u_m.  One CTA (M <= a few 10^5).
-__global__ void __launch_bounds__(1024)
-k_low_var_select(const double* __restrict__ fit, uint32_t M, double gamma, double r0,
-                 double* __restrict__ cum /*scratch [M]*/, int32_t* __restrict__ out)
+// inclusive cumulative weight reaches u_m (gori_tools.py:207-229).  Four small grid-wide
+// kernels over tiles of 1024: max, weights + tile sums, cumulative weights, bisection.
+constexpr int LV_THREADS = 256;
+constexpr int LV_ITEMS = 4;
+constexpr int LV_TILE = LV_THREADS * LV_ITEMS;
+
+__device__ __forceinline__ double block_reduce(double v, bool is_max, double* s_red)
 {
-    __shared__ double s_red[32];
-    __shared__ double s_val;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // max(-fit)
-    double mx = -1.0e300;
-    for (uint32_t i = tid; i < M; i += 1024) mx = fmax(mx, -fit[i]);
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
-    if (lane == 0) s_red[warp] = mx;
-    __syncthreads();
-    if (tid == 0) { double m = s_red[0]; for (int w = 1; w < 32; ++w) m = fmax(m, s_red[w]); s_val = m; }
-    __syncthreads();
-    mx = s_val;
-    const double base = gamma + 1.0;
-    // contiguous chunk per thread -> in-order cumulative sum
-    const uint32_t per = (M + 1023) / 1024;
-    const uint32_t b = tid * per, e = min(M, b + per);
-    double loc = 0.0;
-    for (uint32_t i = b; i < e; ++i) { const double w = pow(base, -fit[i] - mx); cum[i] = w; loc += w; }
-    double inc = loc;
-    for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += v; }
-    __syncthreads();
-    if (lane == 31) s_red[warp] = inc;
-    __syncthreads();
-    double woff = 0.0, total = 0.0;
-    for (int w = 0; w < 32; ++w) { if (w < warp) woff += s_red[w]; total += s_red[w]; }
-    double run = woff + inc - loc;
-    for (uint32_t i = b; i < e; ++i) { run += cum[i]; cum[i] = run / total; }
-    __syncthreads();
-    for (uint32_t m = tid; m < M; m += 1024) {
-        const double u = r0 + (double)m / (double)M;
-        uint32_t lo = 0, hi = M - 1;                      // first i with cum[i] >= u
-        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (cum[mid] >= u) hi = mid; else lo = mid + 1; }
-        out[m] = (int32_t)lo;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double t = __shfl_xor_sync(FULL, v, o);
+        v = is_max ? fmax(v, t) : v + t;
     }
+    __syncthreads();
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    double r = s_red[0];
+    for (int w = 1; w < (int)blockDim.x / 32; ++w) r = is_max ? fmax(r, s_red[w]) : r + s_red[w];
+    return r;
+}
+
+__global__ void __launch_bounds__(LV_THREADS)
+k_lv_max(const double* __restrict__ fit, uint32_t M, double* __restrict__ tile_max)
+{
+    __shared__ double s_red[LV_THREADS / 32];
+    double mx = -1.0e300;
+    for (int k = 0; k < LV_ITEMS; ++k) {
+        const uint32_t i = blockIdx.x * LV_TILE + k * LV_THREADS + threadIdx.x;
+        if (i < M) mx = fmax(mx, -fit[i]);
+    }
+    mx = block_reduce(mx, true, s_red);
+    if (threadIdx.x == 0) tile_max[blockIdx.x] = mx;
+}
+
+__global__ void __launch_bounds__(LV_THREADS)
+k_lv_weights(const double* __restrict__ fit, uint32_t M, double gamma, uint32_t n_tiles,
+             const double* __restrict__ tile_max, double* __restrict__ cum, double* __restrict__ tile_sum)
+{
+    __shared__ double s_red[LV_THREADS / 32];
+    double mx = -1.0e300;
+    for (uint32_t k = threadIdx.x; k < n_tiles; k += LV_THREADS) mx = fmax(mx, tile_max[k]);
+    mx = block_reduce(mx, true, s_red);
+    const double base = gamma + 1.0;
+    const uint32_t b = blockIdx.x * LV_TILE + threadIdx.x * LV_ITEMS;
+    double loc = 0.0;
+    #pragma unroll
+    for (int k = 0; k < LV_ITEMS; ++k)
+        if (b + k < M) { const double w = pow(base, -fit[b + k] - mx); cum[b + k] = w; loc += w; }
+    loc = block_reduce(loc, false, s_red);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = loc;
+}
+
+__global__ void __launch_bounds__(LV_THREADS)
+k_lv_cumulate(uint32_t M, uint32_t n_tiles, const double* __restrict__ tile_sum, double* __restrict__ cum)
+{
+    __shared__ double s_red[LV_THREADS / 32];
+    __shared__ double s_w[LV_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double before = 0.0, all = 0.0;
+    for (uint32_t k = threadIdx.x; k < n_tiles; k += LV_THREADS) {
+        const double v = tile_sum[k];
+        all += v;
+        if (k < blockIdx.x) before += v;
+    }
+    before = block_reduce(before, false, s_red);
+    const double total = block_reduce(all, false, s_red);
+    const uint32_t b = blockIdx.x * LV_TILE + threadIdx.x * LV_ITEMS;
+    double w[LV_ITEMS], loc = 0.0;
+    #pragma unroll
+    for (int k = 0; k < LV_ITEMS; ++k) { w[k] = (b + k < M) ? cum[b + k] : 0.0; loc += w[k]; }
+    double inc = loc;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += v; }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    double run = before + inc - loc;
+    for (int w2 = 0; w2 < warp; ++w2) run += s_w[w2];
+    #pragma unroll
+    for (int k = 0; k < LV_ITEMS; ++k) { run += w[k]; if (b + k < M) cum[b + k] = run / total; }
+}
+
+__global__ void k_lv_search(const double* __restrict__ cum, uint32_t M, double r0, int32_t* __restrict__ out)
+{
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const double u = r0 + (double)m / (double)M;
+    uint32_t lo = 0, hi = M - 1;                          // first i with cum[i] >= u
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (cum[mid] >= u) hi = mid; else lo = mid + 1; }
+    out[m] = (int32_t)lo;
 }
 
 // ------------------------------------------------------------------ crossover (+ fused mutation)
@@ -529,43 +580,46 @@ k_crossover(const int32_t* __restrict__ parents, const int32_t* __restrict__ str
 
 // ------------------------------------------------------------------ mutation (:251-268)
 // Organisms flip the mutation coin as a whole (:159-161); every agent row of a mutating
-// organism regrows its tail from a random cut.  One CTA looks at ORGS consecutive organisms,
-// compacts the rows that walk into a shared list, and hands them out one per THREAD.
+// organism regrows its tail from a random cut.  k_mutation_list compacts the rows that walk
+// into a global list (order is irrelevant: every row owns its Philox stream), then
+// k_mutation_walks gives each listed row to one THREAD: 32 independent dependent-load
+// chains per warp, nothing replicated across lanes, no thread walks twice.
 constexpr int MW_THREADS = 64;
-constexpr int MW_MAX_ROWS = 2048;
+
+__global__ void k_mutation_list(uint32_t P, VaryParams vp, uint64_t seed, uint32_t gen, uint32_t salt,
+                                uint32_t* __restrict__ counter, uint32_t* __restrict__ list)
+{
+    const uint32_t org = blockIdx.x * blockDim.x + threadIdx.x;
+    if (org >= P) return;
+    Philox org_rng(seed, gen, stream_id(STREAM_ORG, salt), org);
+    if (org_rng.uniform() < vp.mut_prob) {
+        const uint32_t base = atomicAdd(counter, (uint32_t)vp.A);
+        for (int a = 0; a < vp.A; ++a) list[base + a] = org * vp.A + a;
+    }
+}
 
 __global__ void __launch_bounds__(MW_THREADS)
-k_mutation_walks(int32_t* __restrict__ dna, uint32_t P, uint32_t orgs_per_cta, GcpTables t,
-                 VaryParams vp, uint64_t seed, uint32_t gen, uint32_t salt)
+k_mutation_walks(int32_t* __restrict__ dna, GcpTables t, VaryParams vp, uint64_t seed, uint32_t gen,
+                 uint32_t salt, const uint32_t* __restrict__ counter, const uint32_t* __restrict__ list)
 {
-    __shared__ uint32_t s_list[MW_MAX_ROWS];
-    __shared__ uint32_t s_n;
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-    const uint32_t org0 = blockIdx.x * orgs_per_cta;
-    for (uint32_t o = threadIdx.x; o < orgs_per_cta && org0 + o < P; o += MW_THREADS) {
-        Philox org_rng(seed, gen, stream_id(STREAM_ORG, salt), org0 + o);
-        if (org_rng.uniform() < vp.mut_prob) {
-            const uint32_t base = atomicAdd(&s_n, (uint32_t)vp.A);
-            for (int a = 0; a < vp.A; ++a) s_list[base + a] = (org0 + o) * vp.A + a;
-        }
-    }
-    __syncthreads();
-    const uint32_t n = s_n;
+    const uint32_t j = blockIdx.x * MW_THREADS + threadIdx.x;
+    if (j >= *counter) return;
     const int L = vp.L;
-    for (uint32_t j = threadIdx.x; j < n; j += MW_THREADS) {
-        const uint32_t gid = s_list[j];
-        int32_t* r = dna + (size_t)gid * L;
-        int len = 0;
-        while (len < L && r[len] != -1) ++len;
-        if (len < 3) continue;
-        Philox rng(seed, gen, stream_id(STREAM_MUT, salt), gid);
-        const int idx = 1 + rng.randint(len - 2);                      // randint(1, len-1)
-        int len_tail = len - idx;
-        if (len + 1 < L) len_tail += rng.randint(L - len);             // :256-258
-        const int last = t_walk(t, vp, r, idx, len_tail, 0, rng);
-        for (int x = last + 1; x < len; ++x) r[x] = -1;                // addTelomere
+    const uint32_t gid = list[j];
+    int32_t* r = dna + (size_t)gid * L;
+    int len;
+    {   // rows are a valid prefix followed by -1 padding: first -1 by bisection
+        int lo = 0, hi = L;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (r[mid] == -1) hi = mid; else lo = mid + 1; }
+        len = lo;
     }
+    if (len < 3) return;
+    Philox rng(seed, gen, stream_id(STREAM_MUT, salt), gid);
+    const int idx = 1 + rng.randint(len - 2);                          // randint(1, len-1)
+    int len_tail = len - idx;
+    if (len + 1 < L) len_tail += rng.randint(L - len);                 // :256-258
+    const int last = t_walk(t, vp, r, idx, len_tail, 0, rng);
+    for (int x = last + 1; x < len; ++x) r[x] = -1;                    // addTelomere
 }
 
 // ------------------------------------------------------------------ muterpolate / prune
@@ -646,12 +700,20 @@ static VaryParams make_vp(gcp_ctx* c)
 }
 
 int launch_low_var_select(gcp_ctx* c, const double* fit, uint32_t M, double gamma, double r0,
-                          double* scratch, int32_t* out, cudaStream_t st)
+                          double* scratch /*dev double [M + 2 * ceil(M/1024)]*/, int32_t* out,
+                          cudaStream_t st)
 {
     if (M == 0) return 0;
     StageTimer tm(c, 5, st);
-    k_low_var_select<<<1, 1024, 0, st>>>(fit, M, gamma, r0, scratch, out);
-    c->launches++;
+    const uint32_t nt = (M + LV_TILE - 1) / LV_TILE;
+    double* cum = scratch;
+    double* tile_max = scratch + M;
+    double* tile_sum = tile_max + nt;
+    k_lv_max<<<nt, LV_THREADS, 0, st>>>(fit, M, tile_max);
+    k_lv_weights<<<nt, LV_THREADS, 0, st>>>(fit, M, gamma, nt, tile_max, cum, tile_sum);
+    k_lv_cumulate<<<nt, LV_THREADS, 0, st>>>(M, nt, tile_sum, cum);
+    k_lv_search<<<(M + 255) / 256, 256, 0, st>>>(cum, M, r0, out);
+    c->launches += 4;
     GCP_CUDA(c, cudaGetLastError());
     return 0;
 }
@@ -674,14 +736,21 @@ int launch_mutate(gcp_ctx* c, int32_t* dna, uint32_t P, uint64_t seed, uint32_t 
     StageTimer tm(c, 7, st);
     const VaryParams vp = make_vp(c);
     if (vp.mut_prob > 0.f) {
-        // expected number of walking rows per CTA ~ 0.8 x MW_THREADS: one row per thread and
-        // many small CTAs, because the walks are dependent-load chains that need occupancy
-        const double pr = vp.mut_prob < 0.05f ? 0.05 : (vp.mut_prob > 1.f ? 1.0 : (double)vp.mut_prob);
-        uint32_t orgs = (uint32_t)(0.8 * MW_THREADS / (pr * vp.A) + 0.5);
-        if (orgs < 1) orgs = 1;
-        if (orgs * (uint32_t)vp.A > (uint32_t)MW_MAX_ROWS) orgs = MW_MAX_ROWS / vp.A;
-        k_mutation_walks<<<(P + orgs - 1) / orgs, MW_THREADS, 0, st>>>(dna, P, orgs, c->t, vp, seed, gen, salt);
-        c->launches++;
+        const uint32_t n_rows = P * (uint32_t)vp.A;
+        const size_t need = 256 + (size_t)n_rows * 4;
+        if (c->vary_scratch_bytes < need) {
+            if (c->vary_scratch) cudaFree(c->vary_scratch);
+            c->vary_scratch = nullptr; c->vary_scratch_bytes = 0;
+            GCP_CUDA(c, cudaMalloc(&c->vary_scratch, need));
+            c->vary_scratch_bytes = need;
+        }
+        uint32_t* counter = reinterpret_cast<uint32_t*>(c->vary_scratch);
+        uint32_t* list = counter + 64;
+        GCP_CUDA(c, cudaMemsetAsync(counter, 0, 4, st));
+        k_mutation_list<<<(P + 255) / 256, 256, 0, st>>>(P, vp, seed, gen, salt, counter, list);
+        k_mutation_walks<<<(n_rows + MW_THREADS - 1) / MW_THREADS, MW_THREADS, 0, st>>>(
+            dna, c->t, vp, seed, gen, salt, counter, list);
+        c->launches += 2;
     }
     const uint32_t n = P * c->p.num_agents;
     k_post_mutate<<<(n + VARY_WARPS - 1) / VARY_WARPS, VARY_WARPS * 32, smem, st>>>(dna, P, c->t, vp,

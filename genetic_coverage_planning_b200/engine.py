@@ -308,7 +308,7 @@ class FitnessEngine(object):
         """got.lowVarSample -> indices of the resampled parents (device int32 [M])."""
         fit = fit.to(device=self.device, dtype=torch.float64).contiguous()
         M = fit.shape[0]
-        scratch = torch.empty(M, dtype=torch.float64, device=self.device)
+        scratch = torch.empty(M + 2 * ((M + 1023) // 1024), dtype=torch.float64, device=self.device)
         out = torch.empty(M, dtype=torch.int32, device=self.device)
         self._check(self.lib.gcp_low_var_select(
             self.ctx, C.c_void_p(fit.data_ptr()), M, float(gamma), float(r0),
@@ -338,7 +338,7 @@ class FitnessEngine(object):
         parent_fit = parent_fit.to(device=self.device, dtype=torch.float64).contiguous()
         P = parents.shape[0]
         kids = torch.empty_like(parents)
-        scratch = torch.empty(P * 16, dtype=torch.uint8, device=self.device)
+        scratch = torch.empty(P * 16 + 64, dtype=torch.uint8, device=self.device)
         self._check(self.lib.gcp_select_vary(
             self.ctx, C.c_void_p(parents.data_ptr()), C.c_void_p(parent_fit.data_ptr()), P,
             float(gamma), int(seed), int(gen), C.c_void_p(kids.data_ptr()),

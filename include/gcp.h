@@ -178,7 +178,7 @@ int gcp_arena_order(gcp_ctx* ctx, const double* fit_dev, uint32_t n, int32_t* or
  * and the arena truncation (geneticalgorithm.py:78-84). */
 int gcp_set_vary_params(gcp_ctx* ctx, const gcp_vary_params* p);
 /* out_idx[m] = index of the m-th resampled parent; r0 = the single U(0, 1/M) draw;
- * scratch: dev double [M]. */
+ * scratch: dev double [M + 2 * ceil(M / 1024)]. */
 int gcp_low_var_select(gcp_ctx* ctx, const double* fit_dev, uint32_t m, double gamma, double r0,
                        double* scratch_dev, int32_t* out_idx_dev, void* stream);
 /* pair k = (strong[k], strong[k + P/2]) -> children 2k, 2k+1.  dna buffers: dev int32 [P][A][L]. */
@@ -190,7 +190,8 @@ int gcp_crossover(gcp_ctx* ctx, const int32_t* parents_dna_dev, const int32_t* s
 int gcp_mutate(gcp_ctx* ctx, int32_t* dna_dev, uint32_t n_org, uint64_t seed, uint32_t generation,
                uint32_t salt, void* stream);
 /* select + crossover + mutate in one call (the reference's child construction loop,
- * geneticalgorithm.py:59-68).  scratch: dev, >= n_org * 16 bytes. */
+ * geneticalgorithm.py:59-68).  scratch: dev, >= 12 * n_org + 16 * ceil(n_org / 1024) bytes
+ * (n_org * 16 + 64 always suffices). */
 int gcp_select_vary(gcp_ctx* ctx, const int32_t* parents_dna_dev, const double* parent_fit_dev,
                     uint32_t n_org, double gamma, uint64_t seed, uint32_t generation,
                     int32_t* children_dna_dev, void* scratch_dev, size_t scratch_bytes, void* stream);
