@@ -14,9 +14,7 @@
 #include "gcp_common.cuh"
 #include "gcp_device.cuh"
 
-constexpr int KF_THREADS = 256;
-constexpr int KF_NW = KF_THREADS / 32;
-constexpr int KF_PPT = 12;               // items (quarters) staged per thread: MAXP <= 12 * 256
+constexpr int KF_PPT = 12;               // items (quarters) staged per thread: MAXP <= 12 * threads
 constexpr uint32_t KF_NIL = 0xFFFFFFFFu;
 
 struct FusedShape {
@@ -28,13 +26,16 @@ struct FusedShape {
     uint32_t off_info, off_x, off_cst, off_lc, off_cost;   // byte offsets into dynamic smem (off_cst relative to off_x)
 };
 
-__global__ void __launch_bounds__(KF_THREADS, 5)
+// KF_THREADS = 256 (5 CTAs / SM) for reference-sized genomes, 1024 (one CTA / SM) for long ones.
+template <int KF_THREADS>
+__global__ void __launch_bounds__(KF_THREADS, KF_THREADS == 256 ? 5 : 1)
 k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape sh,
              gcp_params prm, gcp_map_consts mc,
              double* __restrict__ obj, double* __restrict__ neg_cov_out,
              double* __restrict__ dist_out, double* __restrict__ turn_out,
              int32_t* __restrict__ lc_out, uint8_t* __restrict__ flags)
 {
+    constexpr int KF_NW = KF_THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem[];
     int32_t*  s_dna  = reinterpret_cast<int32_t*>(smem);                      // [AL]
     uint32_t* s_info = reinterpret_cast<uint32_t*>(smem + sh.off_info);       // [AL] quarter-item range per step (C: slot/next)
@@ -459,17 +460,31 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
 
 static inline uint32_t al16(uint32_t x) { return (x + 15u) & ~15u; }
 
-static size_t fused_shape(gcp_ctx* ctx, FusedShape& sh);
+static size_t fused_shape(gcp_ctx* ctx, FusedShape& sh, int threads);
+static int fused_threads(gcp_ctx* ctx, FusedShape& sh, size_t* smem);
 
 // does the fused kernel's shared-memory footprint fit this (A, L)?
 bool eval_fused_fits(gcp_ctx* ctx)
 {
     FusedShape sh;
-    const size_t smem = fused_shape(ctx, sh);
-    return smem != 0 && smem <= (size_t)ctx->max_smem_optin;
+    size_t smem;
+    return fused_threads(ctx, sh, &smem) != 0;
 }
 
-static size_t fused_shape(gcp_ctx* ctx, FusedShape& sh)
+// 256 threads when at least 3 CTAs fit an SM, else 1024 threads (one CTA per SM, 4x the item
+// store, so long genomes are not split into hash partitions); 0 if neither fits.
+static int fused_threads(gcp_ctx* ctx, FusedShape& sh, size_t* smem)
+{
+    *smem = fused_shape(ctx, sh, 256);
+    if (*smem != 0 && *smem * 3 + 3 * 1024 <= (size_t)ctx->max_smem_optin) return 256;
+    *smem = fused_shape(ctx, sh, 1024);
+    if (*smem != 0 && *smem <= (size_t)ctx->max_smem_optin) return 1024;
+    *smem = fused_shape(ctx, sh, 256);
+    if (*smem != 0 && *smem <= (size_t)ctx->max_smem_optin) return 256;
+    return 0;
+}
+
+static size_t fused_shape(gcp_ctx* ctx, FusedShape& sh, int KF_THREADS)
 {
     sh.A = ctx->p.num_agents; sh.L = ctx->p.max_dna_len; sh.AL = sh.A * sh.L;
     sh.inv_L = (uint32_t)((0x100000000ull + (uint64_t)sh.L - 1) / (uint64_t)sh.L);
@@ -505,14 +520,21 @@ int launch_eval_fused(gcp_ctx* ctx, const void* dna, int gene16, uint32_t P, con
     if (P == 0) return 0;
     if (!ctx->have_masked) return gcp_fail(ctx, -1, "masked footprint store not uploaded");
     FusedShape sh;
-    const size_t smem = fused_shape(ctx, sh);
+    size_t smem;
+    const int threads = fused_threads(ctx, sh, &smem);
     sh.gene16 = gene16;
-    if (smem == 0 || smem > (size_t)ctx->max_smem_optin)
+    if (threads == 0)
         return gcp_fail(ctx, -3, "fused eval kernel needs %zu B shared memory (A*L too large)", smem);
-    GCP_CUDA(ctx, cudaFuncSetAttribute(k_eval_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     StageTimer tm(ctx, 1, st);
-    k_eval_fused<<<P, KF_THREADS, smem, st>>>(dna, P, ctx->t, sh, ctx->p, ctx->mc, out->obj, out->neg_cov,
-                                              out->dist, out->turn, out->lc_mat, out->flags);
+    if (threads == 256) {
+        GCP_CUDA(ctx, cudaFuncSetAttribute(k_eval_fused<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_eval_fused<256><<<P, 256, smem, st>>>(dna, P, ctx->t, sh, ctx->p, ctx->mc, out->obj, out->neg_cov,
+                                                out->dist, out->turn, out->lc_mat, out->flags);
+    } else {
+        GCP_CUDA(ctx, cudaFuncSetAttribute(k_eval_fused<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_eval_fused<1024><<<P, 1024, smem, st>>>(dna, P, ctx->t, sh, ctx->p, ctx->mc, out->obj, out->neg_cov,
+                                                  out->dist, out->turn, out->lc_mat, out->flags);
+    }
     ctx->launches++;
     GCP_CUDA(ctx, cudaGetLastError());
     return 0;
