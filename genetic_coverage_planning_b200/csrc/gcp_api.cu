@@ -63,6 +63,7 @@ void gcp_destroy(gcp_ctx* c)
     for (int i = 0; i < c->n_owned; ++i) cudaFree(c->owned[i]);
     if (c->stage_dev) cudaFree(c->stage_dev);
     if (c->vary_scratch) cudaFree(c->vary_scratch);
+    if (c->lcb_scratch) cudaFree(c->lcb_scratch);
     for (int s = 0; s < 2; ++s) if (c->hstream[s]) cudaStreamDestroy(c->hstream[s]);
     for (int s = 0; s < GCP_NUM_STAGES; ++s) { cudaEventDestroy(c->ev_beg[s]); cudaEventDestroy(c->ev_end[s]); }
     delete c;
@@ -529,6 +530,7 @@ int gcp_set_option(gcp_ctx* c, const char* name, int64_t value)
     if (!strcmp(name, "rank_algo")) c->rank_algo = (int)value;
     else if (!strcmp(name, "force_general")) c->force_general = (int)value;
     else if (!strcmp(name, "fused_eval")) c->fused_eval = (int)value;
+    else if (!strcmp(name, "force_lc_big")) c->force_lc_big = (int)value;
     else if (!strcmp(name, "cov_table")) c->cov_table = (int)value;
     else if (!strcmp(name, "cov_maxpairs")) c->cov_maxpairs = (int)value;
     else return gcp_fail(c, -1, "gcp_set_option: unknown option '%s'", name);

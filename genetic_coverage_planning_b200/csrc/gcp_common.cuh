@@ -63,6 +63,8 @@ struct gcp_ctx {
     // host-eval staging (gcp_eval_host)
     void* stage_dev = nullptr; size_t stage_bytes = 0;
     void* vary_scratch = nullptr; size_t vary_scratch_bytes = 0;   // mutation row list (gcp_vary.cu)
+    void* lcb_scratch = nullptr; size_t lcb_scratch_bytes = 0;     // sort buffers (gcp_lcbig.cu)
+    int force_lc_big = 0;    // testing: always take the sort-based loop-closure path
     cudaStream_t hstream[2] = {};
     // coverage kernel tuning (0 = auto)
     int cov_table = 0, cov_maxpairs = 0;
@@ -103,6 +105,9 @@ int launch_loop_closures(gcp_ctx*, const int32_t* dna, uint32_t P, const double*
 int launch_eval_fused(gcp_ctx*, const void* dna, int gene16, uint32_t P, const gcp_eval_out* out,
                       cudaStream_t);
 bool eval_fused_fits(gcp_ctx*);
+int launch_loop_closures_big(gcp_ctx*, const int32_t* dna, uint32_t P, const double* dist,
+                             const double* turn, const uint32_t* cov, int32_t* lc, double* obj,
+                             double* neg_cov, uint8_t* flags, cudaStream_t);
 int launch_maximin(gcp_ctx*, const double* obj, uint32_t n, double constr, uint32_t r0,
                    uint32_t r1, double* obj_sc, double* fit, void* scratch, size_t sb,
                    cudaStream_t);

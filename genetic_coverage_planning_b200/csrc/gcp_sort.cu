@@ -62,21 +62,24 @@ k_rs_hist(const unsigned long long* __restrict__ keys, uint32_t n, int shift,
     hist[(size_t)tid * nblk + blockIdx.x] = s_h[tid];
 }
 
-// exclusive scan of hist in (bin, block) order, one CTA
+// Exclusive scan of hist in (bin, block) order in two steps: one CTA per bin scans its row
+// of nblk counts in place and records the row total at hist[256 * nblk + bin]; a 256-thread CTA
+// then turns the 256 totals into bin bases.
 __global__ void __launch_bounds__(1024)
-k_rs_scan(uint32_t* __restrict__ hist, uint32_t total)
+k_rs_scan_bins(uint32_t* __restrict__ hist, uint32_t nblk)
 {
     __shared__ uint32_t s_w[32];
     __shared__ uint32_t s_carry, s_tot;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t* row = hist + (size_t)blockIdx.x * nblk;
     if (tid == 0) s_carry = 0;
     __syncthreads();
-    for (uint32_t c0 = 0; c0 < total; c0 += 1024 * 4) {
+    for (uint32_t c0 = 0; c0 < nblk; c0 += 1024 * 4) {
         uint32_t v[4], loc = 0;
         #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint32_t i = c0 + tid * 4 + k;
-            v[k] = (i < total) ? hist[i] : 0u;
+            v[k] = (i < nblk) ? row[i] : 0u;
             loc += v[k];
         }
         uint32_t inc = loc;
@@ -103,13 +106,33 @@ k_rs_scan(uint32_t* __restrict__ hist, uint32_t total)
         #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint32_t i = c0 + tid * 4 + k;
-            if (i < total) hist[i] = run;
+            if (i < nblk) row[i] = run;
             run += v[k];
         }
         __syncthreads();
         if (tid == 0) s_carry += s_tot;
         __syncthreads();
     }
+    if (tid == 0) hist[(size_t)RS_BINS * nblk + blockIdx.x] = s_carry;
+}
+
+__global__ void __launch_bounds__(RS_BINS)
+k_rs_scan_totals(uint32_t* __restrict__ bin_total)
+{
+    __shared__ uint32_t s_w[RS_BINS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t v = bin_total[tid];
+    uint32_t inc = v;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    uint32_t off = 0;
+    for (int w = 0; w < warp; ++w) off += s_w[w];
+    bin_total[tid] = off + inc - v;
 }
 
 __global__ void __launch_bounds__(RS_THREADS)
@@ -141,7 +164,7 @@ k_rs_scatter(const unsigned long long* __restrict__ keys, const uint32_t* __rest
     }
     __syncthreads();
     {   // digit `tid`: exclusive scan over the warps + global base of (digit, CTA)
-        uint32_t run = hist[(size_t)tid * nblk + blockIdx.x];
+        uint32_t run = hist[(size_t)RS_BINS * nblk + tid] + hist[(size_t)tid * nblk + blockIdx.x];
         #pragma unroll
         for (int w = 0; w < RS_NW; ++w) {
             const uint32_t c = s_cnt[w][tid];
@@ -171,25 +194,42 @@ k_rs_scatter(const unsigned long long* __restrict__ keys, const uint32_t* __rest
 
 static inline uint32_t rs_blocks(uint32_t n) { return (n + RS_TILE - 1) / RS_TILE; }
 
-// Sorts (keys, vals) in place (8 passes, ping-pong through the tmp buffers).
-static int radix_sort_pairs(gcp_ctx* ctx, unsigned long long* keys, uint32_t* vals, uint32_t n,
-                            unsigned long long* keys_tmp, uint32_t* vals_tmp, uint32_t* hist,
-                            cudaStream_t st)
+// hist scratch: (256 * nblk + 256) u32
+size_t radix_hist_bytes(uint32_t n) { return ((size_t)rs_blocks(n) * RS_BINS + RS_BINS) * 4; }
+
+// Stable LSD radix sort of (keys, vals) on the low n_bits of the keys, ping-pong through the
+// tmp buffers; *out_keys / *out_vals say where the sorted data ends up.
+int radix_sort_pairs_bits(gcp_ctx* ctx, unsigned long long* keys, uint32_t* vals, uint32_t n,
+                          unsigned long long* keys_tmp, uint32_t* vals_tmp, uint32_t* hist,
+                          int n_bits, cudaStream_t st, unsigned long long** out_keys,
+                          uint32_t** out_vals)
 {
     const uint32_t nblk = rs_blocks(n);
     unsigned long long* kin = keys; unsigned long long* kout = keys_tmp;
     uint32_t* vin = vals; uint32_t* vout = vals_tmp;
-    for (int pass = 0; pass < 8; ++pass) {
+    const int passes = (n_bits + 7) / 8;
+    for (int pass = 0; pass < passes; ++pass) {
         const int shift = pass * 8;
         k_rs_hist<<<nblk, RS_THREADS, 0, st>>>(kin, n, shift, hist, nblk);
-        k_rs_scan<<<1, 1024, 0, st>>>(hist, nblk * RS_BINS);
+        k_rs_scan_bins<<<RS_BINS, 1024, 0, st>>>(hist, nblk);
+        k_rs_scan_totals<<<1, RS_BINS, 0, st>>>(hist + (size_t)RS_BINS * nblk);
         k_rs_scatter<<<nblk, RS_THREADS, 0, st>>>(kin, vin, n, shift, hist, nblk, kout, vout);
-        ctx->launches += 3;
+        ctx->launches += 4;
         unsigned long long* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;
     }
     GCP_CUDA(ctx, cudaGetLastError());
+    if (out_keys) *out_keys = kin;
+    if (out_vals) *out_vals = vin;
     return 0;
+}
+
+// Sorts (keys, vals) in place (8 passes: the data ends up in the original buffers).
+static int radix_sort_pairs(gcp_ctx* ctx, unsigned long long* keys, uint32_t* vals, uint32_t n,
+                            unsigned long long* keys_tmp, uint32_t* vals_tmp, uint32_t* hist,
+                            cudaStream_t st)
+{
+    return radix_sort_pairs_bits(ctx, keys, vals, n, keys_tmp, vals_tmp, hist, 64, st, nullptr, nullptr);
 }
 
 // ---------------------------------------------------------------------------------
@@ -369,7 +409,7 @@ size_t sort_scratch_bytes(uint32_t n)
 {
     // keys x2, vals x2, hist, sa, sb, rec, arg, inv
     return 2 * al256((size_t)n * 8) + 2 * al256((size_t)n * 4) +
-           al256((size_t)rs_blocks(n) * RS_BINS * 4) + 2 * al256((size_t)n * 8) +
+           al256(radix_hist_bytes(n)) + 2 * al256((size_t)n * 8) +
            al256((size_t)n * 16) + 2 * al256((size_t)n * 4) +
            al256((size_t)2 * ((n + 1023) / 1024 + 1) * 24) + 256;
 }
@@ -390,7 +430,7 @@ static SortScratch carve(void* base, uint32_t n)
     s.keys_tmp = reinterpret_cast<unsigned long long*>(p);  p += al256((size_t)n * 8);
     s.vals = reinterpret_cast<uint32_t*>(p);                p += al256((size_t)n * 4);
     s.vals_tmp = reinterpret_cast<uint32_t*>(p);            p += al256((size_t)n * 4);
-    s.hist = reinterpret_cast<uint32_t*>(p);                p += al256((size_t)rs_blocks(n) * RS_BINS * 4);
+    s.hist = reinterpret_cast<uint32_t*>(p);                p += al256(radix_hist_bytes(n));
     s.sa = reinterpret_cast<double*>(p);                    p += al256((size_t)n * 8);
     s.sb = reinterpret_cast<double*>(p);                    p += al256((size_t)n * 8);
     s.rec = reinterpret_cast<double2*>(p);                  p += al256((size_t)n * 16);

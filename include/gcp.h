@@ -208,7 +208,8 @@ int gcp_gather_survivors(gcp_ctx* ctx, const int32_t* order_dev, uint32_t n_org,
 
 /* ---- tuning / testing knobs (defaults are right for production) ---------------------
  * "rank_algo": 0 auto, 1 O(N^2) dominance-matrix tiles, 2 sort-based O(N log N) (both exact);
- * "force_general": never take the pre-masked coverage fast path; "cov_table", "cov_maxpairs":
+ * "force_general": never take the pre-masked coverage fast path; "fused_eval": 0 = staged kernels;
+ * "force_lc_big": sort-based loop closures even for short genomes; "cov_table", "cov_maxpairs":
  * shared-memory sizing of the coverage kernels (0 = auto). */
 int gcp_set_option(gcp_ctx* ctx, const char* name, int64_t value);
 

@@ -291,6 +291,47 @@ def test_fused_kernel_equals_staged_kernels(synth_setup):
         assert o[0] == got[0] and o[1] == got[1]
 
 
+def test_sort_based_loop_closures(eng_big, world_big, golden_dir):
+    """gcp_lcbig.cu (whole-population radix sort of edge keys, used when A*L outgrows shared
+    memory) against the golden vectors of the reference and the shared-memory kernel."""
+    z = np.load(os.path.join(golden_dir, "eval_big.npz"))
+    e = np.load(os.path.join(golden_dir, "edge_big.npz"))
+    dna = np.concatenate([z['dna'], e['dna'], _random_dna(world_big, 300, eng_big.A, eng_big.L, seed=31)]
+                         ).astype(np.int32)
+    want = eng_big.evaluate(dna)
+    eng_big.set_option("force_lc_big", 1)
+    try:
+        got = eng_big.evaluate(dna)
+    finally:
+        eng_big.set_option("force_lc_big", 0)
+    for name in ("obj", "neg_cov", "lc_mat", "flags"):
+        assert np.array_equal(getattr(got, name).cpu().numpy(), getattr(want, name).cpu().numpy()), name
+    n = len(z['dna'])
+    assert np.array_equal(got.lc_mat.cpu().numpy()[:n], z['lc'].astype(np.int32))
+
+
+def test_many_agents_long_rows(synth_setup):
+    """C4-style shape (16 agents x 640 genes = 10,240 genes per organism): staged kernels with
+    block partitions + sort-based loop closures, bit-exact against the oracle."""
+    from genetic_coverage_planning_b200 import synth, worlds
+    from genetic_coverage_planning_b200.engine import FitnessEngine
+    sw, pw, ow, op, eng, starts = synth_setup
+    A, L = 16, 640
+    st = synth.spread_starts(sw.xy, A, 1024)
+    op2 = worlds.org_params_for(dict(L=L), st)
+    eng2 = FitnessEngine(pw, op2, num_agents=A)
+    dna = synth.random_walk_population(sw.xy, sw.row_ptr, sw.col, st, 5, 520, L, seed=12).astype(np.int32)
+    r = eng2.evaluate(dna, detail=True, pixel_counts=False)
+    assert not r.flags.cpu().numpy()[:, 3].any()
+    ow2 = World(sw.img, sw.xy, sw.row_ptr, sw.col, sw.edge_poly, sw.edge_theta, sw.edge_dist,
+                sw.map_params, op2, name="synth-16x640")
+    for k in range(2):
+        det = fo.calc_obj(ow2, dna[k].astype(int), detail=True)
+        assert det['obj'][0] == r.obj.cpu().numpy()[k, 0]
+        assert det['obj'][1] == r.obj.cpu().numpy()[k, 1]
+        assert np.array_equal(det['lc_mat'].astype(np.int32), r.lc_mat.cpu().numpy()[k])
+
+
 def test_int16_genes_equal_int32(synth_setup):
     """gcp_eval16 / gcp_eval_host16 (half-width chromosomes) give the int32 results bit for bit."""
     import torch
