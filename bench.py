@@ -182,7 +182,7 @@ def run_reference(args):
     cfg, w, pw, op, starts = build_setup(args.config, args.pop, 0, 1, lambda: None)
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
-    per_step = max(procs * 2, 16)
+    per_step = max(procs * 6, 32)            # ~1-2 s of host work per step
     n = per_step * (args.steps + args.warmup)
     dna = synth.random_walk_population(w.xy, w.row_ptr, w.col, starts, n, cfg['walk'], cfg['L'],
                                        seed=1)

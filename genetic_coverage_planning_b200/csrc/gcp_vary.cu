@@ -56,6 +56,15 @@ struct Philox {
         return v;
     }
     __device__ float uniform() { return (float)(next() >> 8) * (1.0f / 16777216.0f); }   // [0,1)
+    // 16-bit coin: true with probability thr16 / 65536; two coins per 32-bit draw
+    uint32_t coin_bits = 0; int coin_have = 0;
+    __device__ bool coin(uint32_t thr16)
+    {
+        if (coin_have == 0) { coin_bits = next(); coin_have = 2; }
+        const uint32_t v = coin_bits & 0xFFFFu;
+        coin_bits >>= 16; --coin_have;
+        return v < thr16;
+    }
     __device__ double uniform64()
     {
         const uint64_t a = next(), b = next();
@@ -293,20 +302,30 @@ __device__ int w_post_mutate(const GcpTables& t, const VaryParams& vp, int32_t* 
         __syncwarp();
         int arr_len = L;                                               // np.delete shrinks the padded row
         const int W = t.adj8 ? 8 : 32;
+        const uint32_t sub_thr = (uint32_t)fminf(65536.f, fmaxf(0.f, vp.sub_prob * 65536.f + 0.5f));
         for (int q = 0; q < np_; ++q) {
             const int idx1 = pts[q];
             const uint32_t n1 = w_nbr(t, r[idx1], lane);               // lane e: e-th out-neighbour of pt1
             for (int idx2 = idx1 + vp.srch_dist + 1; idx2 > idx1 + 1; --idx2) {
-                if (!(rng.uniform() < vp.sub_prob)) continue;
+                if (!rng.coin(sub_thr)) continue;                       // do_it < P_muterpolate_each :285
                 if (idx2 >= arr_len) break;                            // IndexError -> break :289
                 int pt2 = r[idx2];
                 if (pt2 < 0) pt2 += (int)t.N;                          // numpy index -1
                 if (__any_sync(FULL, n1 == (uint32_t)pt2)) break;      // direct edge: np.delete discarded :293
-                const uint32_t n2 = w_nbr(t, pt2, lane);               // common out-neighbours :298
-                bool hit = false;
-                for (int kk = 0; kk < W; ++kk) {
-                    const uint32_t v = __shfl_sync(FULL, n2, kk);
-                    hit |= (v != 0xFFFFFFFFu) && (n1 == v);
+                bool hit = false;                                       // common out-neighbours :298
+                if (t.adj8) {
+                    // lanes 0..7 hold pt1's neighbours, lanes 8..15 pt2's: one MATCH finds the pairs
+                    const uint2 a2 = __ldg(t.adj8 + (size_t)pt2 * 8 + (lane & 7));
+                    uint32_t v = (lane < 8) ? n1 : (lane < 16 ? a2.x : 0xFFFFFFFFu);
+                    if (v == 0xFFFFFFFFu) v = 0xFFFFFF00u | (uint32_t)lane;    // never equal to anything
+                    const uint32_t peers = __match_any_sync(FULL, v);
+                    hit = (lane < 8) && (peers & 0xFF00u);
+                } else {
+                    const uint32_t n2 = w_nbr(t, pt2, lane);
+                    for (int kk = 0; kk < W; ++kk) {
+                        const uint32_t v = __shfl_sync(FULL, n2, kk);
+                        hit |= (v != 0xFFFFFFFFu) && (n1 == v);
+                    }
                 }
                 uint32_t cm = __ballot_sync(FULL, hit);                // n1 lanes, in edge order
                 if (cm == 0) continue;
