@@ -353,3 +353,57 @@ def test_facade_drop_in(tmp_path):
     assert np.array_equal(pop2._gen_parent[5]._dna, pop._gen_parent[5]._dna)
     h2 = pop2.runEvolution(1)
     assert len(h2) == 1 and pop2._gen_num == 4
+
+
+def test_evolution_matches_reference_statistics(world_small, golden_dir):
+    """BASELINE config C1 end to end: the drop-in GeneticalGorithm on the reference's own small map
+    (map_scaled.png + wilk_3 graph, 6 agents, pather_driver parameters) against per-generation
+    statistics of the UNMODIFIED reference's runEvolution (tests/golden/make_golden_evolution.py).
+    Random streams differ (Philox vs MT19937), so the comparison is statistical: means over
+    three seeds, tolerances a few times the reference's own seed-to-seed spread."""
+    import ref_shim
+    from genetic_coverage_planning_b200 import synth
+    from genetic_coverage_planning_b200.geneticalgorithm import GeneticalGorithm
+    z = np.load(os.path.join(golden_dir, "evolution_small.npz"))
+    ref = z['traj'].mean(axis=0)                      # [gen, stat]
+    n_gen, G = int(z['n_gen']), int(z['gen_size'])
+    w = world_small
+    w.path_params = {'path_memory': 10, 'log_scale_weight': 0.7}
+    mappy, pather = synth.CsrMappy(w), synth.CsrPather(w)
+    _, _, op, gp = ref_shim.driver_params(6)
+    op = dict(op)
+    op['start_idx'] = [int(x) for x in z['start_idx']]
+    gp = dict(gp)
+    gp.update(gen_size=G, coverage_constr_0=0.0, org_params=op,
+              starting_path_len=int(z['starting_path_len']))
+
+    def stats(pop):
+        obj = np.array([o._obj_val for o in pop._gen_parent], dtype=float)
+        lens = np.array([[(row != -1).sum() for row in o._dna] for o in pop._gen_parent])
+        return [(obj[:, 0] < 0).mean(), -obj[:, 0].min(), -obj[:, 0].mean(), obj[:, 1].mean(),
+                lens.mean()]
+    runs = []
+    for seed in (11, 12, 13):
+        pop = GeneticalGorithm(mappy, pather, gp, seed=seed)
+        traj = [stats(pop)]
+        for g in range(n_gen):
+            pop.runEvolution(1)
+            if g + 1 in (5, n_gen):
+                traj.append(stats(pop))
+        runs.append(traj)
+    got = np.array(runs).mean(axis=0)                 # rows: gen 0, gen 5, gen n_gen
+    FEAS, BEST, MEAN, COST, LEN = range(5)
+    # initial population: random walks + constructor variation (firstGeneration)
+    assert abs(got[0, FEAS] - ref[0, FEAS]) <= 0.2
+    assert got[0, BEST] >= 0.95
+    assert abs(got[0, LEN] - ref[0, LEN]) <= 0.08 * ref[0, LEN]
+    assert abs(got[0, COST] - ref[0, COST]) <= 0.10 * ref[0, COST]
+    # after 5 generations the constraint pressure has made the population feasible
+    assert got[1, FEAS] >= 0.9 and ref[5, FEAS] >= 0.9
+    assert got[1, MEAN] >= 0.9
+    # end of the run
+    assert got[2, FEAS] == 1.0
+    assert got[2, BEST] >= ref[n_gen, BEST] - 0.002
+    assert abs(got[2, MEAN] - ref[n_gen, MEAN]) <= 0.03
+    assert abs(got[2, COST] - ref[n_gen, COST]) <= 0.12 * ref[n_gen, COST]
+    assert abs(got[2, LEN] - ref[n_gen, LEN]) <= 0.12 * ref[n_gen, LEN]
