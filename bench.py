@@ -37,7 +37,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=os.environ.get("GCP_BENCH_CONFIG", "C3"))
     ap.add_argument("--pop", type=int, default=0, help="override organisms per GPU")
-    ap.add_argument("--cpu-sample", type=int, default=48)
+    ap.add_argument("--cpu-sample", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / per-kernel / ranking legs")
     return ap.parse_args()
