@@ -320,17 +320,18 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
                     const uint32_t* pb = s_pay + (cb & 0xFFFFu);
                     const uint32_t maxc = __reduce_max_sync(FULL, cnt);
                     uint4 acc = make_uint4(0, 0, 0, 0);
-                    for (uint32_t k = 0; k < maxc; k += 2) {
+                    for (uint32_t k = 0; k < maxc; k += 4) {
                         // reading past cnt only fetches a neighbour's entry (s_pay is padded)
-                        const uint32_t i0 = pb[k], i1 = pb[k + 1];
-                        if (k < cnt) {
-                            const uint4 v = __ldg(t.m_tile + (i0 + l7));
-                            acc.x |= v.x; acc.y |= v.y; acc.z |= v.z; acc.w |= v.w;
-                        }
-                        if (k + 1 < cnt) {
-                            const uint4 v = __ldg(t.m_tile + (i1 + l7));
-                            acc.x |= v.x; acc.y |= v.y; acc.z |= v.z; acc.w |= v.w;
-                        }
+                        const uint32_t i0 = pb[k], i1 = pb[k + 1], i2 = pb[k + 2], i3 = pb[k + 3];
+                        uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0, v3 = v0;
+                        if (k < cnt) v0 = __ldg(t.m_tile + (i0 + l7));
+                        if (k + 1 < cnt) v1 = __ldg(t.m_tile + (i1 + l7));
+                        if (k + 2 < cnt) v2 = __ldg(t.m_tile + (i2 + l7));
+                        if (k + 3 < cnt) v3 = __ldg(t.m_tile + (i3 + l7));
+                        acc.x |= (v0.x | v1.x) | (v2.x | v3.x);
+                        acc.y |= (v0.y | v1.y) | (v2.y | v3.y);
+                        acc.z |= (v0.z | v1.z) | (v2.z | v3.z);
+                        acc.w |= (v0.w | v1.w) | (v2.w | v3.w);
                     }
                     n_cov += popc128(acc);
                 }
@@ -502,7 +503,7 @@ static size_t fused_shape(gcp_ctx* ctx, FusedShape& sh, int KF_THREADS)
     sh.R0 = 1;
     while ((size_t)sh.R0 * maxp < (size_t)sh.AL * 2 && sh.R0 < 4096) sh.R0 <<= 1;
     sh.off_cst = (uint32_t)T * 20;                                    // over s_pay / s_sr
-    const uint32_t cov_b = (uint32_t)T * 20 + (uint32_t)maxp * 8 + 16;  // + pad for B2's read-ahead
+    const uint32_t cov_b = (uint32_t)T * 20 + (uint32_t)maxp * 8 + 32;  // + pad for B2's read-ahead
     const uint32_t a_b = sh.off_cst + (uint32_t)sh.AL * 16;
     const uint32_t lc_b = al16((uint32_t)sh.T3 * 12 + (uint32_t)sh.AL) + (uint32_t)sh.AL * 4;
     uint32_t x_b = cov_b > lc_b ? cov_b : lc_b;
