@@ -404,6 +404,32 @@ def main():
             torch.cuda.synchronize()
             tms = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
             dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            # full generations with the children sharded over the ranks (global population =
+            # world_size * P, parents replicated, children's DNA + objectives all-gathered)
+            from genetic_coverage_planning_b200.distributed import DistributedEvolution, _all_gather
+            ev = DistributedEvolution(eng, gp)
+            gd = _all_gather(dna)
+            go = _all_gather(res.obj)
+            gf = eng.maximin(go, constr)
+            gd, go, gf = ev.step(gd, go, gf, 4321, 0)
+            torch.cuda.synchronize()
+            barrier()
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            d0.record()
+            for g in range(1, 4):
+                gd, go, gf = ev.step(gd, go, gf, 4321, g)
+            d1.record()
+            torch.cuda.synchronize()
+            tg = torch.tensor([d0.elapsed_time(d1) / 3], dtype=torch.float64, device=dev)
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+            extras["generation_distributed"] = {
+                "global_population": world_size * P, "ms_per_generation": float(tg.item()),
+                "generations_per_s": 1000.0 / float(tg.item()),
+                "organisms_varied_and_evaluated_per_s": world_size * P / float(tg.item()) * 1e3,
+                "how": "children sharded by pair range, Philox keyed by global ids (bit-identical to "
+                       "one GPU), NCCL all-gather of children DNA (%d MB) + objective records, "
+                       "ranking and survivor gather replicated" % (world_size * P * A * L * 4 // 10**6)}
+            del gd, go, gf
             extras["ranking_distributed"] = {
                 "n_gladiators": world_size * P, "ms": float(tms.item()),
                 "collective": "all-gather of objective records (16 B/organism) + all-gather of "

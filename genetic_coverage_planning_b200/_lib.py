@@ -67,6 +67,7 @@ SIGNATURES = {
     "gcp_arena_order": (C.c_int, [_vp, _vp, _u32, _vp, _vp, _vp, C.c_size_t, _vp]),
     "gcp_set_vary_params": (C.c_int, [_vp, C.POINTER(GcpVaryParams)]),
     "gcp_low_var_select": (C.c_int, [_vp, _vp, _u32, C.c_double, C.c_double, _vp, _vp, _vp]),
+    "gcp_low_var_r0": (C.c_double, [_u64, _u32, _u32]),
     "gcp_crossover": (C.c_int, [_vp, _vp, _vp, _u32, _u64, _u32, _vp, _vp]),
     "gcp_mutate": (C.c_int, [_vp, _vp, _u32, _u64, _u32, _u32, _vp]),
     "gcp_select_vary": (C.c_int, [_vp, _vp, _vp, _u32, C.c_double, _u64, _u32, _vp, _vp,

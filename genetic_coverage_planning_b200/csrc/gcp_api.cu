@@ -487,6 +487,14 @@ int gcp_mutate(gcp_ctx* c, int32_t* dna, uint32_t P, uint64_t seed, uint32_t gen
     return launch_mutate(c, dna, P, seed, gen, salt, (cudaStream_t)stream);
 }
 
+double gcp_low_var_r0(uint64_t seed, uint32_t gen, uint32_t m)
+{
+    // the single U(0, 1/M) draw of lowVarSample (gori_tools.py:217), from the seed/generation
+    uint64_t z = seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(gen + 1));
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 27; z *= 0x94D049BB133111EBull; z ^= z >> 31;
+    return ((double)(z >> 11) * (1.0 / 9007199254740992.0)) / (double)(m ? m : 1);
+}
+
 int gcp_select_vary(gcp_ctx* c, const int32_t* parents, const double* parent_fit, uint32_t P,
                     double gamma, uint64_t seed, uint32_t gen, int32_t* children, void* scratch,
                     size_t scratch_bytes, void* stream)
@@ -498,10 +506,7 @@ int gcp_select_vary(gcp_ctx* c, const int32_t* parents, const double* parent_fit
         return gcp_fail(c, -1, "select_vary: scratch too small (need 12 * n_org + 16 * ceil(n_org / 1024) bytes)");
     double* cum = reinterpret_cast<double*>(scratch);
     int32_t* strong = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(scratch) + ((size_t)P + 2 * nt) * 8);
-    // the single U(0, 1/M) draw of lowVarSample (gori_tools.py:217), from the seed/generation
-    uint64_t z = seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(gen + 1));
-    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 27; z *= 0x94D049BB133111EBull; z ^= z >> 31;
-    const double r0 = ((double)(z >> 11) * (1.0 / 9007199254740992.0)) / (double)P;
+    const double r0 = gcp_low_var_r0(seed, gen, P);
     cudaStream_t st = (cudaStream_t)stream;
     if ((r = launch_low_var_select(c, parent_fit, P, gamma, r0, cum, strong, st))) return r;
     if ((r = launch_crossover(c, parents, strong, P, seed, gen, children, st))) return r;
@@ -531,6 +536,10 @@ int gcp_set_option(gcp_ctx* c, const char* name, int64_t value)
     else if (!strcmp(name, "force_general")) c->force_general = (int)value;
     else if (!strcmp(name, "fused_eval")) c->fused_eval = (int)value;
     else if (!strcmp(name, "force_lc_big")) c->force_lc_big = (int)value;
+    else if (!strcmp(name, "vary_org_offset")) {
+        if (value < 0 || (value & 1)) return gcp_fail(c, -1, "vary_org_offset must be even and >= 0");
+        c->vary_org_offset = (uint32_t)value;
+    }
     else if (!strcmp(name, "cov_table")) c->cov_table = (int)value;
     else if (!strcmp(name, "cov_maxpairs")) c->cov_maxpairs = (int)value;
     else return gcp_fail(c, -1, "gcp_set_option: unknown option '%s'", name);

@@ -64,6 +64,7 @@ struct gcp_ctx {
     void* stage_dev = nullptr; size_t stage_bytes = 0;
     void* vary_scratch = nullptr; size_t vary_scratch_bytes = 0;   // mutation row list (gcp_vary.cu)
     void* lcb_scratch = nullptr; size_t lcb_scratch_bytes = 0;     // sort buffers (gcp_lcbig.cu)
+    uint32_t vary_org_offset = 0;   // population shards: global id of local organism 0 (Philox keys)
     int force_lc_big = 0;    // testing: always take the sort-based loop-closure path
     cudaStream_t hstream[2] = {};
     // coverage kernel tuning (0 = auto)

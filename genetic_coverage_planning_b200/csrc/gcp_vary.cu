@@ -80,6 +80,7 @@ struct VaryParams {
     int A, L;
     int min_dna_len, time_thresh, num_muterp, srch_dist, path_memory;
     float xover_prob, mut_prob, muterp_prob, sub_prob, inv_sigma;
+    uint32_t org_off;    // global id of local organism 0 (population shards): Philox keys only
 };
 
 // All row-level routines below are WARP-COOPERATIVE: one warp owns one agent row held in
@@ -515,7 +516,7 @@ k_crossover(const int32_t* __restrict__ parents, const int32_t* __restrict__ str
     for (int x = lane; x < L; x += 32) { pm[x] = gm[x]; pd[x] = gd[x]; }
     __syncwarp();
     const int lm = w_valid_len(pm, L, lane), ld = w_valid_len(pd, L, lane);
-    Philox rng(seed, gen, STREAM_XOVER, gid);
+    Philox rng(seed, gen, STREAM_XOVER, gid + (vp.org_off / 2) * vp.A);   // global (pair, agent) id
     const bool want = rng.uniform() < vp.xover_prob;                   // :212,217
     int sel_i = -1, sel_j = -1;
     if (want) {
@@ -610,7 +611,7 @@ __global__ void k_mutation_list(uint32_t P, VaryParams vp, uint64_t seed, uint32
 {
     const uint32_t org = blockIdx.x * blockDim.x + threadIdx.x;
     if (org >= P) return;
-    Philox org_rng(seed, gen, stream_id(STREAM_ORG, salt), org);
+    Philox org_rng(seed, gen, stream_id(STREAM_ORG, salt), org + vp.org_off);
     if (org_rng.uniform() < vp.mut_prob) {
         const uint32_t base = atomicAdd(counter, (uint32_t)vp.A);
         for (int a = 0; a < vp.A; ++a) list[base + a] = org * vp.A + a;
@@ -633,7 +634,7 @@ k_mutation_walks(int32_t* __restrict__ dna, GcpTables t, VaryParams vp, uint64_t
         len = lo;
     }
     if (len < 3) return;
-    Philox rng(seed, gen, stream_id(STREAM_MUT, salt), gid);
+    Philox rng(seed, gen, stream_id(STREAM_MUT, salt), gid + vp.org_off * vp.A);
     const int idx = 1 + rng.randint(len - 2);                          // randint(1, len-1)
     int len_tail = len - idx;
     if (len + 1 < L) len_tail += rng.randint(L - len);                 // :256-258
@@ -661,10 +662,10 @@ k_post_mutate(int32_t* __restrict__ dna, uint32_t P, GcpTables t, VaryParams vp,
     __syncwarp();
     int len = w_valid_len(r, L, lane);
     // organism-level coin flips, identical for all agents of the organism (:159-165)
-    Philox org_rng(seed, gen, stream_id(STREAM_ORG, salt), org);
+    Philox org_rng(seed, gen, stream_id(STREAM_ORG, salt), org + vp.org_off);
     org_rng.uniform();                                                 // the mutation coin
     const bool do_mp = org_rng.uniform() < vp.muterp_prob;
-    Philox rng(seed, gen, stream_id(STREAM_MUTERP, salt), gid);
+    Philox rng(seed, gen, stream_id(STREAM_MUTERP, salt), gid + vp.org_off * vp.A);
     len = w_post_mutate(t, vp, r, len, s_tmp, do_mp, rng, lane);
     for (int x = lane; x < L; x += 32) g[x] = (x < len) ? r[x] : -1;
 }
@@ -715,6 +716,7 @@ static VaryParams make_vp(gcp_ctx* c)
     vp.xover_prob = (float)c->vary.crossover_prob; vp.mut_prob = (float)c->vary.mutation_prob;
     vp.muterp_prob = (float)c->vary.muterpolate_prob; vp.sub_prob = (float)c->vary.muterpolation_sub_prob;
     vp.inv_sigma = (float)(1.0 / c->vary.log_scale_weight);
+    vp.org_off = c->vary_org_offset;
     return vp;
 }
 

@@ -50,3 +50,70 @@ class DistributedRanker(object):
             fit = fit_full
         order, nondom = self.engine.arena_order(fit)
         return glad, fit, order, nondom
+
+
+def _all_gather(t, group=None):
+    """all_gather_into_tensor for device tensors: NCCL directly, other backends (gloo in the
+    single-GPU / CPU tests) through host memory."""
+    world = dist.get_world_size(group)
+    out = t.new_empty((world * t.shape[0],) + tuple(t.shape[1:]))
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+        return out
+    host = t.contiguous().cpu()
+    buf = host.new_empty(out.shape)
+    dist.all_gather_into_tensor(buf, host, group=group)
+    return buf.to(t.device)
+
+
+class DistributedEvolution(object):
+    """One generation of geneticalgorithm.py:55-76 with the CHILDREN sharded over the ranks.
+
+    Parents (DNA, objectives, fitness) are replicated.  Every rank resamples the same parents
+    (lowVarSample, tiny), builds and evaluates only its own contiguous range of child pairs, then
+    the children's DNA and objective records are all-gathered (NCCL over NVLink) and every rank
+    derives the identical maximin fitness, stable order and survivors.  Philox streams are keyed
+    by GLOBAL organism ids (`vary_org_offset`), so the result is bit-identical to the single-GPU
+    generation with the same seed, for any number of ranks."""
+
+    def __init__(self, engine, gen_params, group=None):
+        self.eng = engine
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank_id = dist.get_rank(group) if dist.is_initialized() else 0
+        self.gamma = gen_params['gamma']
+        self.c0 = -gen_params['coverage_constr_0']
+        self.cf = -gen_params['coverage_constr_f']
+        self.aging = gen_params['coverage_aging']
+
+    def constraint(self, gen):
+        alpha = min(1, gen / self.aging)                       # geneticalgorithm.py:98-100
+        return (1 - alpha) * self.c0 + alpha * self.cf
+
+    def step(self, par_dna, par_obj, par_fit, seed, gen):
+        """-> (new parents dna [P,A,L], obj [P,2], fit [P]) replicated on all ranks."""
+        eng, P = self.eng, par_dna.shape[0]
+        half = P // 2
+        if half % self.world:
+            raise ValueError("pairs (%d) must divide evenly over %d ranks" % (half, self.world))
+        m = half // self.world
+        k0 = self.rank_id * m
+        r0 = float(eng.lib.gcp_low_var_r0(int(seed), int(gen), P))
+        strong = eng.low_var_select(par_fit, self.gamma, r0)
+        local = torch.cat([strong[k0:k0 + m], strong[half + k0:half + k0 + m]]).contiguous()
+        eng.set_option("vary_org_offset", 2 * k0)
+        try:
+            kids = eng.crossover(par_dna, local, seed, gen)    # [2m, A, L]: children 2k0 .. 2(k0+m)-1
+            eng.mutate(kids, seed, gen, salt=0)
+        finally:
+            eng.set_option("vary_org_offset", 0)
+        kid_obj = eng.evaluate(kids, detail=False).obj
+        if self.world > 1:
+            kids_all = _all_gather(kids, self.group)
+            kid_obj = _all_gather(kid_obj, self.group)
+        else:
+            kids_all = kids
+        glad_obj = torch.cat([par_obj, kid_obj])
+        fit = eng.maximin(glad_obj, self.constraint(gen))
+        order, _ = eng.arena_order(fit)
+        return eng.gather_survivors(order, par_dna, kids_all, glad_obj, fit)

@@ -181,6 +181,8 @@ int gcp_set_vary_params(gcp_ctx* ctx, const gcp_vary_params* p);
  * scratch: dev double [M + 2 * ceil(M / 1024)]. */
 int gcp_low_var_select(gcp_ctx* ctx, const double* fit_dev, uint32_t m, double gamma, double r0,
                        double* scratch_dev, int32_t* out_idx_dev, void* stream);
+/* the r0 that gcp_select_vary derives from (seed, generation) for a population of m. */
+double gcp_low_var_r0(uint64_t seed, uint32_t generation, uint32_t m);
 /* pair k = (strong[k], strong[k + P/2]) -> children 2k, 2k+1.  dna buffers: dev int32 [P][A][L]. */
 int gcp_crossover(gcp_ctx* ctx, const int32_t* parents_dna_dev, const int32_t* strong_idx_dev,
                   uint32_t n_org, uint64_t seed, uint32_t generation, int32_t* children_dna_dev,
@@ -209,7 +211,8 @@ int gcp_gather_survivors(gcp_ctx* ctx, const int32_t* order_dev, uint32_t n_org,
 /* ---- tuning / testing knobs (defaults are right for production) ---------------------
  * "rank_algo": 0 auto, 1 O(N^2) dominance-matrix tiles, 2 sort-based O(N log N) (both exact);
  * "force_general": never take the pre-masked coverage fast path; "fused_eval": 0 = staged kernels;
- * "force_lc_big": sort-based loop closures even for short genomes; "cov_table", "cov_maxpairs":
+ * "force_lc_big": sort-based loop closures even for short genomes; "vary_org_offset": global id of
+ * local organism 0 when a rank varies only its shard of the children (keys of the Philox streams); "cov_table", "cov_maxpairs":
  * shared-memory sizing of the coverage kernels (0 = auto). */
 int gcp_set_option(gcp_ctx* ctx, const char* name, int64_t value);
 
