@@ -255,11 +255,13 @@ def main():
     B_org = S_mean * 544 + A * L * 4 + 64
 
     # ---------------- timed region: K evaluation steps ----------------
-    for _ in range(max(args.warmup, 3)):
+    # clocks are sampled (nvidia-smi, 100 ms period) from before the warm-up to the end of the
+    # timed region: same kernel, same load, enough samples even when K steps take < 100 ms
+    sampler = ClockSampler(local) if rank == 0 else None
+    for _ in range(max(args.warmup, 3) + 30):
         res = eng.evaluate(dna, detail=False)
     torch.cuda.synchronize()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()

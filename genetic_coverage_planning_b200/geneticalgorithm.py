@@ -176,18 +176,40 @@ class GeneticalGorithm(object):
         return (1 - alpha) * self._cov_constr_0 + alpha * self._cov_constr_f  # :99-100
 
     # -- reference: geneticalgorithm.py:55-76 ------------------------------------------
+    def _sharded(self):
+        """Under torch.distributed (one process per GPU, same seed on every rank) the children
+        of each generation are split over the ranks; the population stays replicated and the
+        result is bit-identical to a single-GPU run (distributed.DistributedEvolution)."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return None
+        if (self._G_sz // 2) % dist.get_world_size():
+            return None
+        from .distributed import DistributedEvolution
+        return DistributedEvolution(self._eng, {'gamma': self._gamma,
+                                                'coverage_constr_0': -self._cov_constr_0,
+                                                'coverage_constr_f': -self._cov_constr_f,
+                                                'coverage_aging': self._cov_aging})
+
     def runEvolution(self, num_generations):
         eng, P = self._eng, self._G_sz
         hist_dev = []
+        sharded = self._sharded()
         for _ in range(num_generations):
-            kids = eng.select_vary(self._dna, self._fit, self._gamma, self._seed, self._gen_num)
-            kid_obj = eng.evaluate(kids, detail=False).obj
-            glad_obj = torch.cat([self._obj, kid_obj])                        # arena :72
-            fit, sc = eng.maximin(glad_obj, self._coverage_constr(), return_scaled=True)
-            order, _ = eng.arena_order(fit)
-            self._dna, self._obj, self._fit = eng.gather_survivors(order, self._dna, kids,
-                                                                   glad_obj, fit)
-            self._obj_sc = sc[order[:P].long()]
+            if sharded is not None:
+                self._dna, self._obj, self._fit = sharded.step(self._dna, self._obj, self._fit,
+                                                               self._seed, self._gen_num)
+                _, sc = eng.maximin(self._obj, self._coverage_constr(), return_scaled=True)
+                self._obj_sc = sc
+            else:
+                kids = eng.select_vary(self._dna, self._fit, self._gamma, self._seed, self._gen_num)
+                kid_obj = eng.evaluate(kids, detail=False).obj
+                glad_obj = torch.cat([self._obj, kid_obj])                    # arena :72
+                fit, sc = eng.maximin(glad_obj, self._coverage_constr(), return_scaled=True)
+                order, _ = eng.arena_order(fit)
+                self._dna, self._obj, self._fit = eng.gather_survivors(order, self._dna, kids,
+                                                                       glad_obj, fit)
+                self._obj_sc = sc[order[:P].long()]
             self._gen_num += 1
             hist_dev.append(self._obj)
         self._views = None
