@@ -1,0 +1,17 @@
+import sys, torch
+sys.path.insert(0, "/root/repo")
+from genetic_coverage_planning_b200 import synth, worlds
+from genetic_coverage_planning_b200.engine import FitnessEngine
+w, pw = worlds.build_synth_world(4096, seed=0)
+for name in ("C4-16", "C4-32"):
+    cfg = worlds.CONFIGS[name]
+    A, L, P = cfg['agents'], cfg['L'], 4096
+    starts = synth.spread_starts(w.xy, A, 4096)
+    op = worlds.org_params_for(cfg, starts)
+    eng = FitnessEngine(pw, op, num_agents=A)
+    dna = synth.random_walk_population_torch(w.xy, w.row_ptr, w.col, starts, P, cfg['walk'], L, seed=1, device=eng.device)
+    for _ in range(2): eng.evaluate(dna, detail=False)
+    eng.set_timing(True)
+    eng.evaluate(dna, detail=False)
+    torch.cuda.synchronize()
+    print(name, "P", P, {n: round(eng.stage_ms(k), 3) for k, n in enumerate(["path", "cov", "lc"])})
