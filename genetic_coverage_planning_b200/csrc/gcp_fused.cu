@@ -7,8 +7,8 @@
 //   phase C  loop closures     mappy.py:372-437   (k_loop_closures)
 //   phase D  constraints + objectives  geneticalgorithm.py:177-201
 //
-// Preconditions (checked by the launcher): pre-masked footprint store uploaded, binary map,
-// coverage_blend == 1.  The staged kernels in gcp_eval.cu remain the general path (gray maps,
+// Preconditions (checked by the caller): pre-masked footprint store uploaded and
+// coverage_blend == 1 (wall coverage only); gray maps are handled (HAS_GRAY).  The staged kernels in gcp_eval.cu remain the general path (gray maps,
 // blend < 1, all six pixel counters) and the cross-check of this one (tests/test_gpu_parity.py).
 //
 #include "gcp_common.cuh"
@@ -27,7 +27,8 @@ struct FusedShape {
 };
 
 // KF_THREADS = 256 (5 CTAs / SM) for reference-sized genomes, 1024 (one CTA / SM) for long ones.
-template <int KF_THREADS>
+// HAS_GRAY: the map has pixels with 0 < g < 255: covered gray mask pixels weigh 255 - g.
+template <int KF_THREADS, bool HAS_GRAY>
 __global__ void __launch_bounds__(KF_THREADS, KF_THREADS == 256 ? 5 : 1)
 k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape sh,
              gcp_params prm, gcp_map_consts mc,
@@ -45,7 +46,7 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     double*   s_cost = reinterpret_cast<double*>(smem + sh.off_cost);         // dist[A], turn[A]
     __shared__ int s_first_neg[GCP_MAX_AGENTS], s_len[GCP_MAX_AGENTS], s_base[GCP_MAX_AGENTS + 1];
     __shared__ int s_bad;
-    __shared__ uint32_t s_npairs, s_overflow, s_total, s_group;
+    __shared__ uint32_t s_npairs, s_overflow, s_total, s_totalw, s_group;
     __shared__ uint32_t s_wsum[KF_NW];
     __shared__ uint32_t s_cov[4];
 
@@ -72,7 +73,7 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
         } else {
             for (int i = tid; i < AL; i += KF_THREADS) s_dna[i] = (int)__ldg(d + i);
         }
-        if (tid == 0) { s_bad = 0; s_total = 0; }
+        if (tid == 0) { s_bad = 0; s_total = 0; s_totalw = 0; }
         for (int i = tid; i < A * A; i += KF_THREADS) s_lc[i] = 0;
     } else {
         const int32_t* d = reinterpret_cast<const int32_t*>(dna_v) + (size_t)org * AL;
@@ -83,7 +84,7 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
         } else {
             for (int i = tid; i < AL; i += KF_THREADS) s_dna[i] = __ldg(d + i);
         }
-        if (tid == 0) { s_bad = 0; s_total = 0; }
+        if (tid == 0) { s_bad = 0; s_total = 0; s_totalw = 0; }
         for (int i = tid; i < A * A; i += KF_THREADS) s_lc[i] = 0;
     }
     __syncthreads();
@@ -164,9 +165,9 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     uint32_t R = sh.R0;
     bool failed = false;
     bool first_pass = true;                  // uniform over the CTA
-    uint32_t n_cov;
+    uint32_t n_cov, n_wg;                    // covered mask pixels with g == 0; sum of (255 - g) over covered gray ones
     for (;;) {                                   // retry loop over partition count R
-        n_cov = 0;
+        n_cov = 0; n_wg = 0;
         bool overflow = false;
         for (uint32_t r = 0; r < R && !overflow; ++r) {
             for (int i = tid; i < T; i += KF_THREADS) s_keys[i] = 0;
@@ -334,6 +335,25 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
                         acc.w |= (v0.w | v1.w) | (v2.w | v3.w);
                     }
                     n_cov += popc128(acc);
+                    if (HAS_GRAY) {
+                        // gray pixels of this block (CSR list {pos, 255 - g, in_mask}): lane i takes
+                        // entry i and fetches the row word that holds its pixel by shuffle
+                        const uint32_t blk = s_keys[slot] - 1u;
+                        const uint32_t ga = __ldg(t.gray_ptr + blk), gb = __ldg(t.gray_ptr + blk + 1);
+                        for (uint32_t g0 = ga; g0 < gb; g0 += 32) {
+                            const uint32_t gi = g0 + lane;
+                            const uint32_t ent = (gi < gb) ? __ldg(t.gray_ent + gi) : 0u;
+                            const uint32_t pos = ent & 4095u, row = pos >> 6, col = pos & 63u;
+                            const int src = (int)(((row >> 4) << 3) | ((row & 15u) >> 1));
+                            const uint32_t wx = __shfl_sync(FULL, acc.x, src), wy = __shfl_sync(FULL, acc.y, src);
+                            const uint32_t wz = __shfl_sync(FULL, acc.z, src), ww = __shfl_sync(FULL, acc.w, src);
+                            const uint32_t word = (row & 1u) ? ((col & 32u) ? ww : wz) : ((col & 32u) ? wy : wx);
+                            if (gi < gb && ((ent >> 20) & 1u) && ((word >> (col & 31u)) & 1u)) {
+                                n_wg += (ent >> 12) & 255u;    // weighs 255 - g ...
+                                n_cov -= 1u;                    // ... instead of a full pixel (wraps, summed mod 2^32)
+                            }
+                        }
+                    }
                 }
             }
             __syncthreads();
@@ -343,10 +363,11 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
         if (R > 4096) { failed = true; break; }
     }
     {
-        uint32_t v = n_cov;
+        uint32_t v = n_cov, vw = n_wg;
         #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(FULL, v, o); vw += __shfl_xor_sync(FULL, vw, o); }
         if (lane == 0 && v) atomicAdd(&s_total, v);
+        if (HAS_GRAY && lane == 0 && vw) atomicAdd(&s_totalw, vw);
     }
     __syncthreads();      // B's tables are dead from here
 
@@ -450,7 +471,7 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
 
     // ------------------------------------------------------------------ phase D: objectives
     if (tid == 0) {
-        s_cov[0] = failed ? 0u : s_total; s_cov[1] = 0; s_cov[2] = 0; s_cov[3] = 0;
+        s_cov[0] = failed ? 0u : s_total; s_cov[1] = 0; s_cov[2] = failed ? 0u : s_totalw; s_cov[3] = 0;
         finish_objectives(s_lc, A, prm, mc, s_cov, s_cost, s_cost + A, org, obj, neg_cov_out, flags);
         if (flags) {
             flags[(size_t)org * 4 + 1] = (s_bad & 1) ? 0 : 1;                       // traversable
@@ -527,15 +548,18 @@ int launch_eval_fused(gcp_ctx* ctx, const void* dna, int gene16, uint32_t P, con
     if (threads == 0)
         return gcp_fail(ctx, -3, "fused eval kernel needs %zu B shared memory (A*L too large)", smem);
     StageTimer tm(ctx, 1, st);
-    if (threads == 256) {
-        GCP_CUDA(ctx, cudaFuncSetAttribute(k_eval_fused<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_eval_fused<256><<<P, 256, smem, st>>>(dna, P, ctx->t, sh, ctx->p, ctx->mc, out->obj, out->neg_cov,
-                                                out->dist, out->turn, out->lc_mat, out->flags);
-    } else {
-        GCP_CUDA(ctx, cudaFuncSetAttribute(k_eval_fused<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_eval_fused<1024><<<P, 1024, smem, st>>>(dna, P, ctx->t, sh, ctx->p, ctx->mc, out->obj, out->neg_cov,
-                                                  out->dist, out->turn, out->lc_mat, out->flags);
-    }
+#define GCP_LAUNCH_FUSED(TH, GRAY)                                                                     \
+    do {                                                                                               \
+        GCP_CUDA(ctx, cudaFuncSetAttribute(k_eval_fused<TH, GRAY>,                                     \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        k_eval_fused<TH, GRAY><<<P, TH, smem, st>>>(dna, P, ctx->t, sh, ctx->p, ctx->mc, out->obj,    \
+                                                    out->neg_cov, out->dist, out->turn, out->lc_mat,   \
+                                                    out->flags);                                       \
+    } while (0)
+    const bool gray = ctx->n_gray > 0;
+    if (threads == 256) { if (gray) GCP_LAUNCH_FUSED(256, true); else GCP_LAUNCH_FUSED(256, false); }
+    else                { if (gray) GCP_LAUNCH_FUSED(1024, true); else GCP_LAUNCH_FUSED(1024, false); }
+#undef GCP_LAUNCH_FUSED
     ctx->launches++;
     GCP_CUDA(ctx, cudaGetLastError());
     return 0;

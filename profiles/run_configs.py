@@ -77,7 +77,7 @@ def run_c2(n_check):
         fo.calc_obj(w, dna[k].cpu().numpy().astype(int))
     cpu = 8 / (time.time() - t0)
     return {"config": "C2", "map": "big_map_scaled 662x462 (gray)", "N": pw.N, "E": pw.E, "A": 6, "L": 200,
-            "P": P, "eval_ms": ms, "organisms_per_s": P / ms * 1e3, "kernels": "general (gray map)",
+            "P": P, "eval_ms": ms, "organisms_per_s": P / ms * 1e3, "kernels": "k_eval_fused<256, HAS_GRAY> (objectives-only path; gray map)",
             "maximin_ms_2P": ms_mm, "arena_order_ms_2P": ms_ord, "rank_bit_exact_vs_oracle": rank_ok,
             "oracle_mismatches": check(eng, w, dna, n_check, tol=1e-12), "checked": n_check,
             "cpu_port_organisms_per_s_1core": cpu}

@@ -30,14 +30,23 @@ def eng_big(world_big):
 
 
 def _check_against_golden(eng, z, exact_cov=False):
+    """Both evaluation paths against the reference's vectors: the staged general kernels (all
+    pixel counters) and the objectives-only path (the fused kernel when coverage_blend == 1)."""
     dna = z['dna'].astype(np.int32)
-    r = eng.evaluate(dna)
+    _check_result(eng.evaluate(dna, detail=True, pixel_counts=False), z, exact_cov, counters=False)
+    _check_result(eng.evaluate(dna), z, exact_cov, counters=True)
+    obj_only = eng.evaluate(dna, detail=False)
+    assert np.max(np.abs(obj_only.obj.cpu().numpy() - z['obj'])) <= (0 if exact_cov else COV_TOL_GRAY)
+
+
+def _check_result(r, z, exact_cov, counters):
     dist, turn = r.dist.cpu().numpy(), r.turn.cpu().numpy()
     assert np.array_equal(dist, z['dist']), "per-agent travel distance not bit-exact"
     assert np.array_equal(turn, z['turn']), "per-agent turning cost not bit-exact"
-    cov = r.cov.cpu().numpy()
-    assert np.array_equal(cov[:, 5], z['n_painted'])
-    assert np.array_equal(cov[:, 4], z['n_painted_mask'])
+    if counters:
+        cov = r.cov.cpu().numpy()
+        assert np.array_equal(cov[:, 5], z['n_painted'])
+        assert np.array_equal(cov[:, 4], z['n_painted_mask'])
     assert np.array_equal(r.lc_mat.cpu().numpy(), z['lc'].astype(np.int32))
     flags = r.flags.cpu().numpy()
     assert np.array_equal(flags[:, 2], z['ncomp'])
