@@ -277,96 +277,9 @@ __device__ int t_walk(const GcpTables& t, const VaryParams& vp, int32_t* r, int 
     return pos;
 }
 
-// Second half of the constructor variation of one row (geneticalgorithm.py:163-168):
-// muterpolate (:270-309), pruneUTurns (:346-357).  s_tmp: 128 ints of warp scratch.
-// (The first half, mutation :251-268, is k_mutation_walks.)
-__device__ int w_post_mutate(const GcpTables& t, const VaryParams& vp, int32_t* r, int len,
-                             int32_t* s_tmp, bool do_mp, Philox& rng, int lane)
+// pruneUTurns (:346-357) of one row held in shared memory, warp-cooperative.
+__device__ int w_prune(int32_t* r, int len, int lane)
 {
-    const int L = vp.L;
-    if (do_mp && len - (vp.srch_dist + 3) > 0) {                       // muterpolate
-        const int np_ = min(vp.num_muterp, MAX_MUT_POINTS);
-        const int range = len - (vp.srch_dist + 3);
-        int32_t* raw = s_tmp;
-        int32_t* pts = s_tmp + MAX_MUT_POINTS;
-        for (int q = 0; q < np_; ++q) {                                // choice with replacement
-            const int v = rng.randint(range);
-            if (lane == 0) raw[q] = v;
-        }
-        __syncwarp();
-        for (int q = lane; q < np_; q += 32) {                         // rank sort, descending
-            const int v = raw[q];
-            int rank = 0;
-            for (int p = 0; p < np_; ++p) { const int o = raw[p]; rank += (o > v) || (o == v && p < q); }
-            pts[rank] = v;
-        }
-        __syncwarp();
-        int arr_len = L;                                               // np.delete shrinks the padded row
-        const int W = t.adj8 ? 8 : 32;
-        const uint32_t sub_thr = (uint32_t)fminf(65536.f, fmaxf(0.f, vp.sub_prob * 65536.f + 0.5f));
-        for (int q = 0; q < np_; ++q) {
-            const int idx1 = pts[q];
-            const uint32_t n1 = w_nbr(t, r[idx1], lane);               // lane e: e-th out-neighbour of pt1
-            for (int idx2 = idx1 + vp.srch_dist + 1; idx2 > idx1 + 1; --idx2) {
-                if (!rng.coin(sub_thr)) continue;                       // do_it < P_muterpolate_each :285
-                if (idx2 >= arr_len) break;                            // IndexError -> break :289
-                int pt2 = r[idx2];
-                if (pt2 < 0) pt2 += (int)t.N;                          // numpy index -1
-                if (__any_sync(FULL, n1 == (uint32_t)pt2)) break;      // direct edge: np.delete discarded :293
-                bool hit = false;                                       // common out-neighbours :298
-                if (t.adj8) {
-                    // lanes 0..7 hold pt1's neighbours, lanes 8..15 pt2's: one MATCH finds the pairs
-                    const uint2 a2 = __ldg(t.adj8 + (size_t)pt2 * 8 + (lane & 7));
-                    uint32_t v = (lane < 8) ? n1 : (lane < 16 ? a2.x : 0xFFFFFFFFu);
-                    if (v == 0xFFFFFFFFu) v = 0xFFFFFF00u | (uint32_t)lane;    // never equal to anything
-                    const uint32_t peers = __match_any_sync(FULL, v);
-                    hit = (lane < 8) && (peers & 0xFF00u);
-                } else {
-                    const uint32_t n2 = w_nbr(t, pt2, lane);
-                    for (int kk = 0; kk < W; ++kk) {
-                        const uint32_t v = __shfl_sync(FULL, n2, kk);
-                        hit |= (v != 0xFFFFFFFFu) && (n1 == v);
-                    }
-                }
-                uint32_t cm = __ballot_sync(FULL, hit);                // n1 lanes, in edge order
-                if (cm == 0) continue;
-                for (int pick = rng.randint(__popc(cm)); pick > 0; --pick) cm &= cm - 1;
-                const int step = (int)__shfl_sync(FULL, n1, __ffs(cm) - 1);
-                const int ndel = idx2 - idx1 - 3;                      // delete idx1+2 .. idx2-2
-                __syncwarp();
-                if (lane == 0) r[idx1 + 1] = step;                     // :302
-                if (ndel > 0) {
-                    for (int x0 = idx1 + 2; x0 + ndel < arr_len; x0 += 32) {
-                        const int x = x0 + lane;
-                        int v = 0;
-                        const bool ok = x + ndel < arr_len;
-                        if (ok) v = r[x + ndel];
-                        __syncwarp();
-                        if (ok) r[x] = v;
-                        __syncwarp();
-                    }
-                    for (int x = arr_len - ndel + lane; x < arr_len; x += 32) r[x] = -1;
-                    arr_len -= ndel;
-                }
-                __syncwarp();
-                break;
-            }
-        }
-        // strip -1 (:307): stable compaction of the whole row
-        int w = 0;
-        for (int i0 = 0; i0 < L; i0 += 32) {
-            const int i = i0 + lane;
-            const int g = (i < L) ? r[i] : -1;
-            const uint32_t m = __ballot_sync(FULL, g != -1);
-            __syncwarp();
-            if (g != -1) r[w + __popc(m & ((1u << lane) - 1u))] = g;
-            w += __popc(m);
-            __syncwarp();
-        }
-        len = w;
-        for (int x = len + lane; x < L; x += 32) r[x] = -1;
-        __syncwarp();
-    }
     // pruneUTurns :346-357: position i goes away if the waypoint at i recurs at i+1 or
     // i+2, or if i-1 and i+1 hold the same waypoint (flags from the ORIGINAL row)
     {
@@ -606,13 +519,15 @@ k_crossover(const int32_t* __restrict__ parents, const int32_t* __restrict__ str
 // chains per warp, nothing replicated across lanes, no thread walks twice.
 constexpr int MW_THREADS = 64;
 
+// which = 0: organisms whose mutation coin came up (:159-161); 1: muterpolate coin (:163-165)
 __global__ void k_mutation_list(uint32_t P, VaryParams vp, uint64_t seed, uint32_t gen, uint32_t salt,
-                                uint32_t* __restrict__ counter, uint32_t* __restrict__ list)
+                                int which, uint32_t* __restrict__ counter, uint32_t* __restrict__ list)
 {
     const uint32_t org = blockIdx.x * blockDim.x + threadIdx.x;
     if (org >= P) return;
     Philox org_rng(seed, gen, stream_id(STREAM_ORG, salt), org + vp.org_off);
-    if (org_rng.uniform() < vp.mut_prob) {
+    const float u0 = org_rng.uniform(), u1 = org_rng.uniform();
+    if (which == 0 ? (u0 < vp.mut_prob) : (u1 < vp.muterp_prob)) {
         const uint32_t base = atomicAdd(counter, (uint32_t)vp.A);
         for (int a = 0; a < vp.A; ++a) list[base + a] = org * vp.A + a;
     }
@@ -642,7 +557,117 @@ k_mutation_walks(int32_t* __restrict__ dna, GcpTables t, VaryParams vp, uint64_t
     for (int x = last + 1; x < len; ++x) r[x] = -1;                    // addTelomere
 }
 
-// ------------------------------------------------------------------ muterpolate / prune
+// ------------------------------------------------------------------ muterpolate (:270-309)
+// One THREAD per row of the organisms whose muterpolate coin came up (compacted list), the row
+// edited in place in global memory (it stays in L1).  num_muterpolations anchors, searched
+// back from idx1 + srch_dist + 1 to idx1 + 2, each tried with probability sub_prob: a direct
+// edge pt1 -> pt2 is a no-op (the reference discards its np.delete, :293), otherwise a random
+// common out-neighbour replaces idx1 + 1 and idx1 + 2 .. idx2 - 2 are deleted.
+__device__ __forceinline__ void t_nbrs(const GcpTables& t, int node, uint32_t* n)
+{
+    const uint4* rec = reinterpret_cast<const uint4*>(t.adj8 + (size_t)node * 8);
+    #pragma unroll
+    for (int h = 0; h < 4; ++h) { const uint4 q = __ldg(rec + h); n[2 * h] = q.x; n[2 * h + 1] = q.z; }
+}
+
+__device__ __forceinline__ bool t_is_edge_csr(const GcpTables& t, int a, int b)
+{
+    for (uint32_t e = __ldg(t.row_ptr + a); e < __ldg(t.row_ptr + a + 1); ++e)
+        if ((int)__ldg(t.col + e) == b) return true;
+    return false;
+}
+
+__global__ void __launch_bounds__(MW_THREADS)
+k_muterpolate_rows(int32_t* __restrict__ dna, GcpTables t, VaryParams vp, uint64_t seed, uint32_t gen,
+                   uint32_t salt, const uint32_t* __restrict__ counter, const uint32_t* __restrict__ list)
+{
+    const uint32_t j = blockIdx.x * MW_THREADS + threadIdx.x;
+    if (j >= *counter) return;
+    const int L = vp.L;
+    const uint32_t gid = list[j];
+    int32_t* r = dna + (size_t)gid * L;
+    int len;
+    {
+        int lo = 0, hi = L;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (r[mid] == -1) hi = mid; else lo = mid + 1; }
+        len = lo;
+    }
+    const int range = len - (vp.srch_dist + 3);
+    if (range <= 0) return;
+    Philox rng(seed, gen, stream_id(STREAM_MUTERP, salt), gid + vp.org_off * vp.A);
+    int pts[MAX_MUT_POINTS];
+    const int np_ = min(vp.num_muterp, MAX_MUT_POINTS);
+    for (int q = 0; q < np_; ++q) {                                    // choice with replacement,
+        const int v = rng.randint(range);                              // kept sorted descending
+        int x = q;
+        while (x > 0 && pts[x - 1] < v) { pts[x] = pts[x - 1]; --x; }
+        pts[x] = v;
+    }
+    const uint32_t sub_thr = (uint32_t)fminf(65536.f, fmaxf(0.f, vp.sub_prob * 65536.f + 0.5f));
+    int arr_len = L;                                                   // np.delete shrinks the padded row
+    bool changed = false;
+    for (int q = 0; q < np_; ++q) {
+        const int idx1 = pts[q];
+        const int pt1 = r[idx1];
+        uint32_t n1[8];
+        if (t.adj8) t_nbrs(t, pt1, n1);
+        for (int idx2 = idx1 + vp.srch_dist + 1; idx2 > idx1 + 1; --idx2) {
+            if (!rng.coin(sub_thr)) continue;                          // do_it < P_muterpolate_each :285
+            if (idx2 >= arr_len) break;                                // IndexError -> break :289
+            int pt2 = r[idx2];
+            if (pt2 < 0) pt2 += (int)t.N;                              // numpy index -1
+            int step = -1;
+            if (t.adj8) {
+                bool direct = false;
+                #pragma unroll
+                for (int e = 0; e < 8; ++e) direct |= (n1[e] == (uint32_t)pt2);
+                if (direct) break;                                     // np.delete discarded :293
+                uint32_t n2[8];
+                t_nbrs(t, pt2, n2);
+                uint32_t cm = 0;                                       // common out-neighbours :298
+                #pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    bool hit = false;
+                    #pragma unroll
+                    for (int f = 0; f < 8; ++f) hit |= (n1[e] == n2[f]);
+                    if (hit && n1[e] != 0xFFFFFFFFu) cm |= 1u << e;
+                }
+                if (cm == 0) continue;
+                for (int pick = rng.randint(__popc(cm)); pick > 0; --pick) cm &= cm - 1;
+                const int e = __ffs(cm) - 1;
+                #pragma unroll
+                for (int k = 0; k < 8; ++k) if (k == e) step = (int)n1[k];
+            } else {
+                if (t_is_edge_csr(t, pt1, pt2)) break;
+                int nopt = 0;
+                for (uint32_t e1 = __ldg(t.row_ptr + pt1); e1 < __ldg(t.row_ptr + pt1 + 1); ++e1)
+                    nopt += t_is_edge_csr(t, pt2, (int)__ldg(t.col + e1));
+                if (nopt == 0) continue;
+                int pick = rng.randint(nopt);
+                for (uint32_t e1 = __ldg(t.row_ptr + pt1); e1 < __ldg(t.row_ptr + pt1 + 1); ++e1) {
+                    const int c = (int)__ldg(t.col + e1);
+                    if (t_is_edge_csr(t, pt2, c)) { if (pick == 0) { step = c; break; } --pick; }
+                }
+            }
+            r[idx1 + 1] = step;                                        // :302
+            changed = true;
+            const int ndel = idx2 - idx1 - 3;                          // delete idx1+2 .. idx2-2
+            if (ndel > 0) {
+                for (int x = idx1 + 2; x + ndel < arr_len; ++x) r[x] = r[x + ndel];
+                for (int x = arr_len - ndel; x < arr_len; ++x) r[x] = -1;
+                arr_len -= ndel;
+            }
+            break;
+        }
+    }
+    if (changed) {                                                     // strip -1 (:307)
+        int w = 0;
+        for (int x = 0; x < L; ++x) { const int g = r[x]; if (g != -1) r[w++] = g; }
+        for (int x = w; x < L; ++x) r[x] = -1;
+    }
+}
+
+// ------------------------------------------------------------------ pruneUTurns (:346-357)
 // One warp per (organism, agent); the row goes through shared memory and back in place.
 __global__ void __launch_bounds__(VARY_WARPS * 32)
 k_post_mutate(int32_t* __restrict__ dna, uint32_t P, GcpTables t, VaryParams vp, uint64_t seed,
@@ -652,21 +677,14 @@ k_post_mutate(int32_t* __restrict__ dna, uint32_t P, GcpTables t, VaryParams vp,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t gid = blockIdx.x * VARY_WARPS + warp;
     if (gid >= P * vp.A) return;
-    const uint32_t org = gid / vp.A;
     const int L = vp.L;
     const size_t RS = vary_row_stride(L);
-    int32_t* r = s_rows + (size_t)warp * (RS + 128);
-    int32_t* s_tmp = r + RS;
+    int32_t* r = s_rows + (size_t)warp * RS;
     int32_t* g = dna + (size_t)gid * L;
     for (int x = lane; x < L; x += 32) r[x] = g[x];
     __syncwarp();
     int len = w_valid_len(r, L, lane);
-    // organism-level coin flips, identical for all agents of the organism (:159-165)
-    Philox org_rng(seed, gen, stream_id(STREAM_ORG, salt), org + vp.org_off);
-    org_rng.uniform();                                                 // the mutation coin
-    const bool do_mp = org_rng.uniform() < vp.muterp_prob;
-    Philox rng(seed, gen, stream_id(STREAM_MUTERP, salt), gid + vp.org_off * vp.A);
-    len = w_post_mutate(t, vp, r, len, s_tmp, do_mp, rng, lane);
+    len = w_prune(r, len, lane);
     for (int x = lane; x < L; x += 32) g[x] = (x < len) ? r[x] : -1;
 }
 
@@ -752,30 +770,37 @@ int launch_mutate(gcp_ctx* c, int32_t* dna, uint32_t P, uint64_t seed, uint32_t 
                   cudaStream_t st)
 {
     if (P == 0) return 0;
-    size_t smem; int r = vary_smem(c, 1, 128, &smem); if (r) return r;
+    size_t smem; int r = vary_smem(c, 1, 0, &smem); if (r) return r;
     GCP_CUDA(c, cudaFuncSetAttribute(k_post_mutate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     StageTimer tm(c, 7, st);
     const VaryParams vp = make_vp(c);
-    if (vp.mut_prob > 0.f) {
-        const uint32_t n_rows = P * (uint32_t)vp.A;
-        const size_t need = 256 + (size_t)n_rows * 4;
+    const uint32_t n_rows = P * (uint32_t)vp.A;
+    if (vp.mut_prob > 0.f || vp.muterp_prob > 0.f) {
+        const size_t need = 512 + (size_t)n_rows * 4;
         if (c->vary_scratch_bytes < need) {
             if (c->vary_scratch) cudaFree(c->vary_scratch);
             c->vary_scratch = nullptr; c->vary_scratch_bytes = 0;
             GCP_CUDA(c, cudaMalloc(&c->vary_scratch, need));
             c->vary_scratch_bytes = need;
         }
-        uint32_t* counter = reinterpret_cast<uint32_t*>(c->vary_scratch);
-        uint32_t* list = counter + 64;
+    }
+    uint32_t* counter = reinterpret_cast<uint32_t*>(c->vary_scratch);
+    uint32_t* list = counter + 128;
+    const uint32_t row_grid = (n_rows + MW_THREADS - 1) / MW_THREADS;
+    if (vp.mut_prob > 0.f) {                       // mutation (:159-161): tail regrowth walks
         GCP_CUDA(c, cudaMemsetAsync(counter, 0, 4, st));
-        k_mutation_list<<<(P + 255) / 256, 256, 0, st>>>(P, vp, seed, gen, salt, counter, list);
-        k_mutation_walks<<<(n_rows + MW_THREADS - 1) / MW_THREADS, MW_THREADS, 0, st>>>(
-            dna, c->t, vp, seed, gen, salt, counter, list);
+        k_mutation_list<<<(P + 255) / 256, 256, 0, st>>>(P, vp, seed, gen, salt, 0, counter, list);
+        k_mutation_walks<<<row_grid, MW_THREADS, 0, st>>>(dna, c->t, vp, seed, gen, salt, counter, list);
         c->launches += 2;
     }
-    const uint32_t n = P * c->p.num_agents;
-    k_post_mutate<<<(n + VARY_WARPS - 1) / VARY_WARPS, VARY_WARPS * 32, smem, st>>>(dna, P, c->t, vp,
-                                                                                    seed, gen, salt);
+    if (vp.muterp_prob > 0.f && vp.num_muterp > 0) {   // muterpolate (:163-165)
+        GCP_CUDA(c, cudaMemsetAsync(counter + 64, 0, 4, st));
+        k_mutation_list<<<(P + 255) / 256, 256, 0, st>>>(P, vp, seed, gen, salt, 1, counter + 64, list);
+        k_muterpolate_rows<<<row_grid, MW_THREADS, 0, st>>>(dna, c->t, vp, seed, gen, salt, counter + 64, list);
+        c->launches += 2;
+    }
+    k_post_mutate<<<(n_rows + VARY_WARPS - 1) / VARY_WARPS, VARY_WARPS * 32, smem, st>>>(dna, P, c->t, vp,
+                                                                                         seed, gen, salt);
     c->launches++;
     GCP_CUDA(c, cudaGetLastError());
     return 0;
