@@ -604,17 +604,21 @@ k_muterpolate_rows(int32_t* __restrict__ dna, GcpTables t, VaryParams vp, uint64
         pts[x] = v;
     }
     const uint32_t sub_thr = (uint32_t)fminf(65536.f, fmaxf(0.f, vp.sub_prob * 65536.f + 0.5f));
-    int arr_len = L;                                                   // np.delete shrinks the padded row
+    // np.delete shrinks the padded row; anchors come in descending order, so every deletion
+    // lies at or left of the previous one: a GAP BUFFER (logical index x lives at x below the gap,
+    // at x + gap_len above it) makes each deletion O(distance to the previous one) instead of
+    // shifting the whole tail.
+    int gap_lo = L, gap_len = 0;                                       // logical length = L - gap_len
     bool changed = false;
     for (int q = 0; q < np_; ++q) {
         const int idx1 = pts[q];
-        const int pt1 = r[idx1];
+        const int pt1 = r[idx1];                                       // idx1 + 1 < every gap position
         uint32_t n1[8];
         if (t.adj8) t_nbrs(t, pt1, n1);
         for (int idx2 = idx1 + vp.srch_dist + 1; idx2 > idx1 + 1; --idx2) {
             if (!rng.coin(sub_thr)) continue;                          // do_it < P_muterpolate_each :285
-            if (idx2 >= arr_len) break;                                // IndexError -> break :289
-            int pt2 = r[idx2];
+            if (idx2 >= L - gap_len) break;                            // IndexError -> break :289
+            int pt2 = r[idx2 < gap_lo ? idx2 : idx2 + gap_len];
             if (pt2 < 0) pt2 += (int)t.N;                              // numpy index -1
             int step = -1;
             if (t.adj8) {
@@ -653,16 +657,21 @@ k_muterpolate_rows(int32_t* __restrict__ dna, GcpTables t, VaryParams vp, uint64
             changed = true;
             const int ndel = idx2 - idx1 - 3;                          // delete idx1+2 .. idx2-2
             if (ndel > 0) {
-                for (int x = idx1 + 2; x + ndel < arr_len; ++x) r[x] = r[x + ndel];
-                for (int x = arr_len - ndel; x < arr_len; ++x) r[x] = -1;
-                arr_len -= ndel;
+                const int new_lo = idx1 + 2;                           // <= gap_lo always
+                for (int x = gap_lo - 1; x >= new_lo; --x) r[x + gap_len] = r[x];   // move the gap left
+                gap_lo = new_lo;
+                gap_len += ndel;
             }
             break;
         }
     }
-    if (changed) {                                                     // strip -1 (:307)
+    if (changed) {                                                     // close the gap, strip -1 (:307)
         int w = 0;
-        for (int x = 0; x < L; ++x) { const int g = r[x]; if (g != -1) r[w++] = g; }
+        for (int x = 0; x < L; ++x) {
+            if (x >= gap_lo && x < gap_lo + gap_len) continue;
+            const int g = r[x];
+            if (g != -1) r[w++] = g;
+        }
         for (int x = w; x < L; ++x) r[x] = -1;
     }
 }

@@ -15,7 +15,7 @@ $STEP > $OUT/plain_${TAG}.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 400 --csv \
     --log-file $OUT/launches_${TAG}.csv $STEP > $OUT/ncu_launches_${TAG}.log 2>&1
 echo "launch list rc=$?"
-for K in ${KERNELS:-k_coverage_masked}; do
+for K in ${KERNELS:-k_eval_fused}; do
 $FULL > $OUT/plain2_${TAG}.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:$K -s ${SKIP:-3} -c 1 \
     -o $OUT/prof_${K}_${TAG} -f $FULL > $OUT/ncu_full_${K}_${TAG}.log 2>&1
