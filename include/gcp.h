@@ -123,14 +123,20 @@ int gcp_set_params(gcp_ctx* ctx, const gcp_params* p);
 /* ---- evaluation: Organism.calcObj for P organisms ---------------------------------
  * Replaces: `for o in organisms: o.calcObj()` = Mappy.getCoverage (mappy.py:330-370)
  * + Mappy.getLoopClosures (mappy.py:386-437) + constraints (geneticalgorithm.py:177-201).
- * dna: dev int32 [P][A][L], -1 padded (Organism._dna, geneticalgorithm.py:335-344). */
+ * dna: dev int32 [P][A][L], -1 padded (Organism._dna, geneticalgorithm.py:335-344).
+ *
+ * Dispatch: with the pre-masked footprints uploaded, coverage_blend == 1 and out->cov == NULL the
+ * whole evaluation is ONE kernel (k_eval_fused: binary and gray maps, genomes up to ~7,000 genes;
+ * scratch may then be NULL).  Otherwise the staged kernels run (all six pixel counters, blend < 1,
+ * longer genomes; loop closures switch to a radix-sort formulation when A*L outgrows shared
+ * memory) and scratch_dev must hold gcp_eval_scratch_bytes(n_org) bytes.  Results are identical. */
 size_t gcp_eval_scratch_bytes(gcp_ctx* ctx, uint32_t n_org);
 int    gcp_eval(gcp_ctx* ctx, const int32_t* dna_dev, uint32_t n_org,
                 const gcp_eval_out* out, void* scratch_dev, size_t scratch_bytes,
                 void* stream);
 /* Same evaluation from int16 genes (dev int16 [P][A][L], -1 padded): halves the chromosome
  * bytes moved over PCIe / HBM.  Needs N <= 32767 waypoints and the fused objectives-only path
- * (pre-masked footprints uploaded, binary map, coverage_blend == 1, out->cov == NULL). */
+ * (pre-masked footprints uploaded, coverage_blend == 1, out->cov == NULL). */
 int    gcp_eval16(gcp_ctx* ctx, const int16_t* dna_dev, uint32_t n_org, const gcp_eval_out* out,
                   void* stream);
 /* Individual stages (same buffers; used by tests / profiling). edge_ids: dev u32 [P][A][L];
@@ -188,7 +194,8 @@ int gcp_crossover(gcp_ctx* ctx, const int32_t* parents_dna_dev, const int32_t* s
                   uint32_t n_org, uint64_t seed, uint32_t generation, int32_t* children_dna_dev,
                   void* stream);
 /* in place: mutation (prob), muterpolate (prob), pruneUTurns, addTelomere; `salt` separates
- * independent uses within one generation. */
+ * independent uses within one generation.  Rows must be a valid prefix followed by -1 padding
+ * (what every producer in this API and Organism.addTelomere emit). */
 int gcp_mutate(gcp_ctx* ctx, int32_t* dna_dev, uint32_t n_org, uint64_t seed, uint32_t generation,
                uint32_t salt, void* stream);
 /* select + crossover + mutate in one call (the reference's child construction loop,
@@ -212,8 +219,8 @@ int gcp_gather_survivors(gcp_ctx* ctx, const int32_t* order_dev, uint32_t n_org,
  * "rank_algo": 0 auto, 1 O(N^2) dominance-matrix tiles, 2 sort-based O(N log N) (both exact);
  * "force_general": never take the pre-masked coverage fast path; "fused_eval": 0 = staged kernels;
  * "force_lc_big": sort-based loop closures even for short genomes; "vary_org_offset": global id of
- * local organism 0 when a rank varies only its shard of the children (keys of the Philox streams); "cov_table", "cov_maxpairs":
- * shared-memory sizing of the coverage kernels (0 = auto). */
+ * local organism 0 when a rank varies only its shard of the children (keys of the Philox streams);
+ * "cov_table", "cov_maxpairs": shared-memory sizing of the coverage kernels (0 = auto). */
 int gcp_set_option(gcp_ctx* ctx, const char* name, int64_t value);
 
 /* ---- introspection ---------------------------------------------------------------- */
@@ -222,8 +229,8 @@ uint64_t gcp_launch_count(gcp_ctx* ctx);
 /* time of the most recent call of each stage measured with CUDA events on the launch
  * stream; only recorded while enabled (adds two event records per stage). */
 int gcp_set_timing(gcp_ctx* ctx, int enabled);
-/* stage: 0 path_costs, 1 coverage, 2 loop_closures, 3 maximin, 4 arena_order, 5 select,
- * 6 crossover, 7 mutate.
+/* stage: 0 path_costs, 1 coverage (or the whole fused evaluation), 2 loop_closures, 3 maximin,
+ * 4 arena_order, 5 select, 6 crossover, 7 mutate (walks + muterpolate + prune).
  * Synchronises on the stage's end event. Returns milliseconds, <0 if not recorded. */
 float gcp_stage_ms(gcp_ctx* ctx, int stage);
 
