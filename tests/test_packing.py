@@ -92,3 +92,23 @@ def test_layout_invariants(pw_big):
     # mask0 is a subset of free0; out-of-map bits are zero
     assert not (pw.blk_mask0 & ~pw.blk_free0).any()
     assert pw.gray_ptr[-1] == len(pw.gray_ent)
+
+
+def test_pack_from_live_reference_objects(world_small):
+    """The drop-in path: packing.pack_from_reference on the reference's own Mappy / PathMaker
+    objects (this container only) gives exactly the tables packed from the committed fixture."""
+    import ref_shim
+    if not ref_shim.available():
+        pytest.skip("needs /root/reference")
+    from genetic_coverage_planning_b200 import packing
+    m, p, _ = ref_shim.build_world("small", 6)
+    a = packing.pack_from_reference(m, p)
+    w = world_small
+    b = packing.pack_world(w.img, w.xy, w.row_ptr, w.col, w.edge_poly, w.edge_theta, w.edge_dist,
+                           w.map_params)
+    for name in ("row_ptr", "col", "xy", "xover_cand", "edge_cost", "edge_theta", "sub_ptr", "sub_block",
+                 "sub_payload", "tile_data", "m_sub_ptr", "m_sub_block", "m_sub_payload", "m_tile_data",
+                 "blk_mask0", "blk_free0", "gray_ptr", "gray_ent"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    assert (a.mask_size, a.gsum_mask, a.map_size, a.num_occluded) == \
+           (b.mask_size, b.gsum_mask, b.map_size, b.num_occluded)
