@@ -303,7 +303,10 @@ int gcp_eval(gcp_ctx* c, const int32_t* dna, uint32_t P, const gcp_eval_out* out
     if (P == 0) return 0;
     // objectives-only fast path: binary map, wall coverage only -> pre-masked footprint store
     const bool fast = c->have_masked && c->p.coverage_blend == 1.0 && !out->cov && !c->force_general;
-    const bool fast_staged = fast && c->n_gray == 0;     // k_coverage_masked has no gray weights
+    // staged objectives-only path: quarter-granular kernel (any map) when its tables exist, else
+    // the sub-tile kernel (binary maps only)
+    const bool fast_q = fast && c->t.m_q_info != nullptr;
+    const bool fast_staged = fast && (fast_q || c->n_gray == 0);
     if (fast && c->fused_eval && c->t.m_q_info && eval_fused_fits(c))   // one kernel, no scratch (gcp_fused.cu)
         return launch_eval_fused(c, dna, 0, P, out, (cudaStream_t)stream);
     if (scratch_bytes < gcp_eval_scratch_bytes(c, P) || !scratch)
@@ -323,8 +326,10 @@ int gcp_eval(gcp_ctx* c, const int32_t* dna, uint32_t P, const gcp_eval_out* out
     if (out->flags) flags = out->flags;
     cudaStream_t st = (cudaStream_t)stream;
     if ((r = launch_path_costs(c, dna, P, edge_ids, fast_staged ? step_info : nullptr, dist, turn,
-                               flags, st))) return r;
-    if (fast_staged) {
+                               flags, st, fast_q ? 1 : 0))) return r;
+    if (fast_q) {
+        if ((r = launch_coverage_quarters(c, step_info, P, cov, flags, st))) return r;
+    } else if (fast_staged) {
         if ((r = launch_coverage_masked(c, step_info, P, cov, flags, st))) return r;
     } else {
         c->cov_detail = out->cov ? 1 : 0;   // objectives-only mode skips unused pixel counters

@@ -95,7 +95,9 @@ struct StageTimer {
 // kernel launchers (defined in the .cu files)
 int launch_path_costs(gcp_ctx*, const int32_t* dna, uint32_t P, uint32_t* edge_ids,
                       uint32_t* step_info, double* dist, double* turn, uint8_t* flags,
-                      cudaStream_t);
+                      cudaStream_t, int quarter_info = 0);
+int launch_coverage_quarters(gcp_ctx*, const uint32_t* step_qinfo, uint32_t P, uint32_t* cov,
+                             uint8_t* flags, cudaStream_t);
 int launch_coverage_masked(gcp_ctx*, const uint32_t* step_info, uint32_t P, uint32_t* cov,
                            uint8_t* flags, cudaStream_t);
 int launch_coverage(gcp_ctx*, const uint32_t* edge_ids, uint32_t P, uint32_t* cov,

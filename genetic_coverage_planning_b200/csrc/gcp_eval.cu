@@ -23,6 +23,7 @@ constexpr int K1_STAGE_ELEMS = 2048;   // double2 entries (32 KB)
 __global__ void __launch_bounds__(K1_THREADS)
 k_path_costs(const int32_t* __restrict__ dna, uint32_t P, GcpTables t, int A, int L,
              uint32_t* __restrict__ edge_ids, uint32_t* __restrict__ step_info,
+             const uint32_t* __restrict__ info_table /*m_sub_info or m_q_info*/,
              double* __restrict__ dist, double* __restrict__ turn, uint8_t* __restrict__ flags)
 {
     __shared__ int s_first_neg[GCP_MAX_AGENTS];
@@ -76,7 +77,7 @@ k_path_costs(const int32_t* __restrict__ dna, uint32_t P, GcpTables t, int A, in
             edge_ids[(size_t)org * AL + a * L + i] = e;
             if (step_info)
                 step_info[(size_t)org * AL + a * L + i] =
-                    (e != GCP_INVALID_EDGE) ? __ldg(t.m_sub_info + e) : 0u;
+                    (e != GCP_INVALID_EDGE) ? __ldg(info_table + e) : 0u;
             s_stage[ii * A + a] = c;
         }
         __syncthreads();
@@ -101,14 +102,15 @@ k_path_costs(const int32_t* __restrict__ dna, uint32_t P, GcpTables t, int A, in
 
 int launch_path_costs(gcp_ctx* ctx, const int32_t* dna, uint32_t P, uint32_t* edge_ids,
                       uint32_t* step_info, double* dist, double* turn, uint8_t* flags,
-                      cudaStream_t st)
+                      cudaStream_t st, int quarter_info)
 {
     if (P == 0) return 0;
     if (step_info && !ctx->have_masked)
         return gcp_fail(ctx, -1, "step_info requested but no masked footprint store uploaded");
     StageTimer tm(ctx, 0, st);
     k_path_costs<<<P, K1_THREADS, 0, st>>>(dna, P, ctx->t, ctx->p.num_agents, ctx->p.max_dna_len,
-                                           edge_ids, step_info, dist, turn, flags);
+                                           edge_ids, step_info,
+                                           quarter_info ? ctx->t.m_q_info : ctx->t.m_sub_info, dist, turn, flags);
     ctx->launches++;
     GCP_CUDA(ctx, cudaGetLastError());
     return 0;

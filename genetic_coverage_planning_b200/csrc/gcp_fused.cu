@@ -26,135 +26,21 @@ struct FusedShape {
     uint32_t off_info, off_x, off_cst, off_lc, off_cost;   // byte offsets into dynamic smem (off_cst relative to off_x)
 };
 
-// KF_THREADS = 256 (5 CTAs / SM) for reference-sized genomes, 1024 (one CTA / SM) for long ones.
-// HAS_GRAY: the map has pixels with 0 < g < 255 (SURVEY F6): covered gray mask pixels weigh 255 - g.
+// ============================================================================
+// Wall coverage of one organism (CTA-wide): see "phase B" in the header comment of k_eval_fused.
+//   info[s], s < AL: quarter-item range of step s (first | count << 26), 0 = no step.
+//   n_cov: covered mask pixels with g == 0, n_wg: sum of (255 - g) over covered gray mask pixels
+//   (per-thread partial sums; the caller reduces them).  s_x: T*20 + MAXP*8 + 32 bytes.
+// ============================================================================
 template <int KF_THREADS, bool HAS_GRAY>
-__global__ void __launch_bounds__(KF_THREADS, KF_THREADS == 256 ? 5 : 1)
-k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape sh,
-             gcp_params prm, gcp_map_consts mc,
-             double* __restrict__ obj, double* __restrict__ neg_cov_out,
-             double* __restrict__ dist_out, double* __restrict__ turn_out,
-             int32_t* __restrict__ lc_out, uint8_t* __restrict__ flags)
+__device__ __forceinline__ void coverage_quarters(const uint32_t* info, int AL, const GcpTables& t,
+                                                  int T, int MAXP, uint32_t R0, unsigned char* s_x,
+                                                  uint32_t& n_cov, uint32_t& n_wg, bool& failed)
 {
     constexpr int KF_NW = KF_THREADS / 32;
-    extern __shared__ __align__(16) unsigned char smem[];
-    int32_t*  s_dna  = reinterpret_cast<int32_t*>(smem);                      // [AL]
-    uint32_t* s_info = reinterpret_cast<uint32_t*>(smem + sh.off_info);       // [AL] quarter-item range per step (C: slot/next)
-    unsigned char* s_x = smem + sh.off_x;                                     // B / C tables
-    double2*  s_cst  = reinterpret_cast<double2*>(smem + sh.off_x + sh.off_cst); // [AL] {dist, turn} per step (A only; aliases s_pay/s_sr)
-    int*      s_lc   = reinterpret_cast<int*>(smem + sh.off_lc);              // [A*A]
-    double*   s_cost = reinterpret_cast<double*>(smem + sh.off_cost);         // dist[A], turn[A]
-    __shared__ int s_first_neg[GCP_MAX_AGENTS], s_len[GCP_MAX_AGENTS], s_base[GCP_MAX_AGENTS + 1];
-    __shared__ int s_bad;
-    __shared__ uint32_t s_npairs, s_overflow, s_total, s_totalw, s_group;
+    __shared__ uint32_t s_npairs, s_overflow, s_group;
     __shared__ uint32_t s_wsum[KF_NW];
-    __shared__ uint32_t s_cov[4];
-
-    const uint32_t org = blockIdx.x;
-    if (org >= P) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int A = sh.A, L = sh.L, AL = sh.AL;
-
-    // ------------------------------------------------------------------ load the chromosome
-    if (sh.gene16) {                       // int16 chromosome (N < 32768): half the bytes to move
-        const int16_t* d = reinterpret_cast<const int16_t*>(dna_v) + (size_t)org * AL;
-        if ((AL & 7) == 0) {
-            const int4* d8 = reinterpret_cast<const int4*>(d);
-            for (int i = tid; i < (AL >> 3); i += KF_THREADS) {
-                const int4 v = __ldg(d8 + i);
-                int4 lo, hi;
-                lo.x = (int)(short)(v.x & 0xFFFF); lo.y = v.x >> 16;
-                lo.z = (int)(short)(v.y & 0xFFFF); lo.w = v.y >> 16;
-                hi.x = (int)(short)(v.z & 0xFFFF); hi.y = v.z >> 16;
-                hi.z = (int)(short)(v.w & 0xFFFF); hi.w = v.w >> 16;
-                reinterpret_cast<int4*>(s_dna)[2 * i] = lo;
-                reinterpret_cast<int4*>(s_dna)[2 * i + 1] = hi;
-            }
-        } else {
-            for (int i = tid; i < AL; i += KF_THREADS) s_dna[i] = (int)__ldg(d + i);
-        }
-        if (tid == 0) { s_bad = 0; s_total = 0; s_totalw = 0; }
-        for (int i = tid; i < A * A; i += KF_THREADS) s_lc[i] = 0;
-    } else {
-        const int32_t* d = reinterpret_cast<const int32_t*>(dna_v) + (size_t)org * AL;
-        if ((AL & 3) == 0) {
-            const int4* d4 = reinterpret_cast<const int4*>(d);
-            int4* s4 = reinterpret_cast<int4*>(s_dna);
-            for (int i = tid; i < (AL >> 2); i += KF_THREADS) s4[i] = __ldg(d4 + i);
-        } else {
-            for (int i = tid; i < AL; i += KF_THREADS) s_dna[i] = __ldg(d + i);
-        }
-        if (tid == 0) { s_bad = 0; s_total = 0; s_totalw = 0; }
-        for (int i = tid; i < A * A; i += KF_THREADS) s_lc[i] = 0;
-    }
-    __syncthreads();
-    // first -1 per row (step rule mappy.py:343-345) and number of valid genes (:390)
-    for (int a = warp; a < A; a += KF_NW) {
-        int first = L, cnt = 0;
-        for (int i0 = 0; i0 < L; i0 += 32) {
-            const int i = i0 + lane;
-            const int g = (i < L) ? s_dna[a * L + i] : 0;
-            const uint32_t neg = __ballot_sync(FULL, (i < L) && g < 0);
-            if (neg && first == L) first = i0 + __ffs(neg) - 1;
-            cnt += __popc(__ballot_sync(FULL, (i < L) && g != -1));
-        }
-        if (lane == 0) { s_first_neg[a] = first; s_len[a] = cnt; }
-    }
-    __syncthreads();
-
-    // ------------------------------------------------------------------ phase A1: edge lookup
-    {
-        int bad = 0;
-        for (int s = tid; s < AL; s += KF_THREADS) {
-            const int a = (int)__umulhi((uint32_t)s, sh.inv_L);
-            const int i = s - a * L;
-            const int g = s_dna[s];
-            if (g < -1 || (g >= 0 && (uint32_t)g >= t.N)) bad |= 2;
-            uint32_t e = GCP_INVALID_EDGE, info = 0;
-            double2 cst = make_double2(0.0, 0.0);
-            const int nsteps = min(s_first_neg[a], L - 1);
-            if (i < nsteps) {
-                const uint32_t w = (uint32_t)g;
-                int nx = s_dna[s + 1];
-                const bool sentinel = nx < 0;
-                if (nx < 0) nx += (int)t.N;                  // numpy wrap: -1 -> N-1 (SURVEY F3)
-                if (w < t.N && nx >= 0 && (uint32_t)nx < t.N) {
-                    const uint32_t lo = __ldg(t.row_ptr + w);
-                    e = t.E + w;                             // null edge unless found (F4)
-                    bool found = false;
-                    if (t.adj8) {
-                        const uint4* rec = reinterpret_cast<const uint4*>(t.adj8 + (size_t)w * 8);
-                        #pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            const uint4 q = __ldg(rec + h);
-                            if (q.x == (uint32_t)nx && !found) { e = lo + 2 * h; found = true; }
-                            if (q.z == (uint32_t)nx && !found) { e = lo + 2 * h + 1; found = true; }
-                        }
-                    } else {
-                        const uint32_t hi = __ldg(t.row_ptr + w + 1);
-                        for (uint32_t q = lo; q < hi; ++q)
-                            if (__ldg(t.col + q) == (uint32_t)nx) { e = q; found = true; break; }
-                    }
-                    if (!found && !sentinel) bad |= 1;
-                    info = __ldg(t.m_q_info + e);
-                    cst = __ldg(t.edge_cost + e);
-                }
-            }
-            s_cst[s] = cst;
-            s_info[s] = info;
-        }
-        if (bad) atomicOr(&s_bad, bad);
-    }
-    __syncthreads();
-
-    // ------------------------------------------------------------------ phase B: wall coverage
-    // Items are QUARTERS (16 rows x 64 px = one 128-B line) of the visited edges' pre-masked
-    // sub-tiles.  B1 counting-sorts them by (map block, quarter index): an open-addressing hash
-    // table maps block id -> slot, one shared atomicAdd per item returns its rank inside
-    // (slot, quarter).  B2: a warp owns a block; its 8-lane group g streams the block's
-    // quarter-g list (lane = one uint4 = 2 rows), ORs into registers and popcounts once per
-    // block.  No lane idles on absent quarters, no bitmap in shared memory, no bitmap atomics.
-    const int T = sh.T, MAXP = sh.MAXP;
     uint32_t* s_keys = reinterpret_cast<uint32_t*>(s_x);      // [T] block id + 1
     uint32_t* s_cq   = s_keys + T;                             // [T][4] count -> count<<16 | base
     uint32_t* s_pay  = s_cq + 4 * T;                           // [MAXP] uint4 index of the quarter, then sorted
@@ -162,10 +48,8 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     const int logT = 31 - __clz(T);
     const uint32_t myq = lane >> 3, l7 = lane & 7;
 
-    uint32_t R = sh.R0;
-    bool failed = false;
-    bool first_pass = true;                  // uniform over the CTA
-    uint32_t n_cov, n_wg;                    // covered mask pixels with g == 0; sum of (255 - g) over covered gray ones
+    uint32_t R = R0;
+    failed = false;
     for (;;) {                                   // retry loop over partition count R
         n_cov = 0; n_wg = 0;
         bool overflow = false;
@@ -173,27 +57,6 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
             for (int i = tid; i < T; i += KF_THREADS) s_keys[i] = 0;
             for (int i = tid; i < 4 * T; i += KF_THREADS) s_cq[i] = 0;
             if (tid == 0) { s_npairs = 0; s_overflow = 0; s_group = 0; }
-            if (first_pass && warp == 0 && lane < A) {
-                // phase A2: sequential fp64 adds in step order per agent (mappy.py:351-352),
-                // bit-identical to the reference's `+=`; the per-step costs were staged by A1
-                const double2* ca = s_cst + lane * L;
-                const int nsteps = min(s_first_neg[lane], L - 1);
-                double acc_d = 0.0, acc_t = 0.0;
-                int i = 0;
-                for (; i + 8 <= nsteps; i += 8) {
-                    double2 c[8];
-                    #pragma unroll
-                    for (int k = 0; k < 8; ++k) c[k] = ca[i + k];
-                    #pragma unroll
-                    for (int k = 0; k < 8; ++k) { acc_d = __dadd_rn(acc_d, c[k].x); acc_t = __dadd_rn(acc_t, c[k].y); }
-                }
-                for (; i < nsteps; ++i) { acc_d = __dadd_rn(acc_d, ca[i].x); acc_t = __dadd_rn(acc_t, ca[i].y); }
-                s_cost[lane] = acc_d;
-                s_cost[A + lane] = acc_t;
-                if (dist_out) dist_out[(size_t)org * A + lane] = acc_d;
-                if (turn_out) turn_out[(size_t)org * A + lane] = acc_t;
-            }
-            first_pass = false;
             __syncthreads();
             // ---- B1: slot + rank for every quarter item ----
             {
@@ -202,7 +65,7 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
                     const int s = s0 + lane;
                     uint32_t lo = 0, n = 0;
                     if (s < AL) {
-                        const uint32_t inf = s_info[s];
+                        const uint32_t inf = info[s];
                         lo = inf & 0x03FFFFFFu;
                         n = inf >> 26;
                     }
@@ -362,6 +225,159 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
         R <<= 1;
         if (R > 4096) { failed = true; break; }
     }
+}
+
+// KF_THREADS = 256 (5 CTAs / SM) for reference-sized genomes, 1024 (one CTA / SM) for long ones.
+// HAS_GRAY: the map has pixels with 0 < g < 255 (SURVEY F6): covered gray mask pixels weigh 255 - g.
+template <int KF_THREADS, bool HAS_GRAY>
+__global__ void __launch_bounds__(KF_THREADS, KF_THREADS == 256 ? 5 : 1)
+k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape sh,
+             gcp_params prm, gcp_map_consts mc,
+             double* __restrict__ obj, double* __restrict__ neg_cov_out,
+             double* __restrict__ dist_out, double* __restrict__ turn_out,
+             int32_t* __restrict__ lc_out, uint8_t* __restrict__ flags)
+{
+    constexpr int KF_NW = KF_THREADS / 32;
+    extern __shared__ __align__(16) unsigned char smem[];
+    int32_t*  s_dna  = reinterpret_cast<int32_t*>(smem);                      // [AL]
+    uint32_t* s_info = reinterpret_cast<uint32_t*>(smem + sh.off_info);       // [AL] quarter-item range per step (C: slot/next)
+    unsigned char* s_x = smem + sh.off_x;                                     // B / C tables
+    double2*  s_cst  = reinterpret_cast<double2*>(smem + sh.off_x + sh.off_cst); // [AL] {dist, turn} per step (A only; aliases s_pay/s_sr)
+    int*      s_lc   = reinterpret_cast<int*>(smem + sh.off_lc);              // [A*A]
+    double*   s_cost = reinterpret_cast<double*>(smem + sh.off_cost);         // dist[A], turn[A]
+    __shared__ int s_first_neg[GCP_MAX_AGENTS], s_len[GCP_MAX_AGENTS], s_base[GCP_MAX_AGENTS + 1];
+    __shared__ int s_bad;
+    __shared__ uint32_t s_total, s_totalw;
+    __shared__ uint32_t s_cov[4];
+
+    const uint32_t org = blockIdx.x;
+    if (org >= P) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int A = sh.A, L = sh.L, AL = sh.AL;
+
+    // ------------------------------------------------------------------ load the chromosome
+    if (sh.gene16) {                       // int16 chromosome (N < 32768): half the bytes to move
+        const int16_t* d = reinterpret_cast<const int16_t*>(dna_v) + (size_t)org * AL;
+        if ((AL & 7) == 0) {
+            const int4* d8 = reinterpret_cast<const int4*>(d);
+            for (int i = tid; i < (AL >> 3); i += KF_THREADS) {
+                const int4 v = __ldg(d8 + i);
+                int4 lo, hi;
+                lo.x = (int)(short)(v.x & 0xFFFF); lo.y = v.x >> 16;
+                lo.z = (int)(short)(v.y & 0xFFFF); lo.w = v.y >> 16;
+                hi.x = (int)(short)(v.z & 0xFFFF); hi.y = v.z >> 16;
+                hi.z = (int)(short)(v.w & 0xFFFF); hi.w = v.w >> 16;
+                reinterpret_cast<int4*>(s_dna)[2 * i] = lo;
+                reinterpret_cast<int4*>(s_dna)[2 * i + 1] = hi;
+            }
+        } else {
+            for (int i = tid; i < AL; i += KF_THREADS) s_dna[i] = (int)__ldg(d + i);
+        }
+        if (tid == 0) { s_bad = 0; s_total = 0; s_totalw = 0; }
+        for (int i = tid; i < A * A; i += KF_THREADS) s_lc[i] = 0;
+    } else {
+        const int32_t* d = reinterpret_cast<const int32_t*>(dna_v) + (size_t)org * AL;
+        if ((AL & 3) == 0) {
+            const int4* d4 = reinterpret_cast<const int4*>(d);
+            int4* s4 = reinterpret_cast<int4*>(s_dna);
+            for (int i = tid; i < (AL >> 2); i += KF_THREADS) s4[i] = __ldg(d4 + i);
+        } else {
+            for (int i = tid; i < AL; i += KF_THREADS) s_dna[i] = __ldg(d + i);
+        }
+        if (tid == 0) { s_bad = 0; s_total = 0; s_totalw = 0; }
+        for (int i = tid; i < A * A; i += KF_THREADS) s_lc[i] = 0;
+    }
+    __syncthreads();
+    // first -1 per row (step rule mappy.py:343-345) and number of valid genes (:390)
+    for (int a = warp; a < A; a += KF_NW) {
+        int first = L, cnt = 0;
+        for (int i0 = 0; i0 < L; i0 += 32) {
+            const int i = i0 + lane;
+            const int g = (i < L) ? s_dna[a * L + i] : 0;
+            const uint32_t neg = __ballot_sync(FULL, (i < L) && g < 0);
+            if (neg && first == L) first = i0 + __ffs(neg) - 1;
+            cnt += __popc(__ballot_sync(FULL, (i < L) && g != -1));
+        }
+        if (lane == 0) { s_first_neg[a] = first; s_len[a] = cnt; }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ phase A1: edge lookup
+    {
+        int bad = 0;
+        for (int s = tid; s < AL; s += KF_THREADS) {
+            const int a = (int)__umulhi((uint32_t)s, sh.inv_L);
+            const int i = s - a * L;
+            const int g = s_dna[s];
+            if (g < -1 || (g >= 0 && (uint32_t)g >= t.N)) bad |= 2;
+            uint32_t e = GCP_INVALID_EDGE, info = 0;
+            double2 cst = make_double2(0.0, 0.0);
+            const int nsteps = min(s_first_neg[a], L - 1);
+            if (i < nsteps) {
+                const uint32_t w = (uint32_t)g;
+                int nx = s_dna[s + 1];
+                const bool sentinel = nx < 0;
+                if (nx < 0) nx += (int)t.N;                  // numpy wrap: -1 -> N-1 (SURVEY F3)
+                if (w < t.N && nx >= 0 && (uint32_t)nx < t.N) {
+                    const uint32_t lo = __ldg(t.row_ptr + w);
+                    e = t.E + w;                             // null edge unless found (F4)
+                    bool found = false;
+                    if (t.adj8) {
+                        const uint4* rec = reinterpret_cast<const uint4*>(t.adj8 + (size_t)w * 8);
+                        #pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const uint4 q = __ldg(rec + h);
+                            if (q.x == (uint32_t)nx && !found) { e = lo + 2 * h; found = true; }
+                            if (q.z == (uint32_t)nx && !found) { e = lo + 2 * h + 1; found = true; }
+                        }
+                    } else {
+                        const uint32_t hi = __ldg(t.row_ptr + w + 1);
+                        for (uint32_t q = lo; q < hi; ++q)
+                            if (__ldg(t.col + q) == (uint32_t)nx) { e = q; found = true; break; }
+                    }
+                    if (!found && !sentinel) bad |= 1;
+                    info = __ldg(t.m_q_info + e);
+                    cst = __ldg(t.edge_cost + e);
+                }
+            }
+            s_cst[s] = cst;
+            s_info[s] = info;
+        }
+        if (bad) atomicOr(&s_bad, bad);
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ phase B: wall coverage
+    // Items are QUARTERS (16 rows x 64 px = one 128-B line) of the visited edges' pre-masked
+    // sub-tiles.  B1 counting-sorts them by (map block, quarter index): an open-addressing hash
+    // table maps block id -> slot, one shared atomicAdd per item returns its rank inside
+    // (slot, quarter).  B2: a warp owns a block; its 8-lane group g streams the block's
+    // quarter-g list (lane = one uint4 = 2 rows), ORs into registers and popcounts once per
+    // block.  No lane idles on absent quarters, no bitmap in shared memory, no bitmap atomics.
+    // phase A2 (lanes 0..A-1 of warp 0) runs while the other warps start clearing B's tables
+    if (warp == 0 && lane < A) {
+        // phase A2: sequential fp64 adds in step order per agent (mappy.py:351-352),
+        // bit-identical to the reference's `+=`; the per-step costs were staged by A1
+        const double2* ca = s_cst + lane * L;
+        const int nsteps = min(s_first_neg[lane], L - 1);
+        double acc_d = 0.0, acc_t = 0.0;
+        int i = 0;
+        for (; i + 8 <= nsteps; i += 8) {
+            double2 c[8];
+            #pragma unroll
+            for (int k = 0; k < 8; ++k) c[k] = ca[i + k];
+            #pragma unroll
+            for (int k = 0; k < 8; ++k) { acc_d = __dadd_rn(acc_d, c[k].x); acc_t = __dadd_rn(acc_t, c[k].y); }
+        }
+        for (; i < nsteps; ++i) { acc_d = __dadd_rn(acc_d, ca[i].x); acc_t = __dadd_rn(acc_t, ca[i].y); }
+        s_cost[lane] = acc_d;
+        s_cost[A + lane] = acc_t;
+        if (dist_out) dist_out[(size_t)org * A + lane] = acc_d;
+        if (turn_out) turn_out[(size_t)org * A + lane] = acc_t;
+    }
+    uint32_t n_cov, n_wg;
+    bool failed;
+    coverage_quarters<KF_THREADS, HAS_GRAY>(s_info, AL, t, sh.T, sh.MAXP, sh.R0, s_x, n_cov, n_wg, failed);
     {
         uint32_t v = n_cov, vw = n_wg;
         #pragma unroll
@@ -478,6 +494,74 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
             flags[(size_t)org * 4 + 3] = (uint8_t)(((s_bad & 2) ? 1 : 0) | (failed ? 2 : 0));
         }
     }
+}
+
+// ============================================================================
+// Stand-alone wall coverage for genomes that outgrow the fused kernel's shared memory (staged
+// path: k_path_costs -> k_cov_quarters -> loop closures).  step_qinfo: dev u32 [P][A*L], per
+// step the quarter-item range of its edge (GcpTables::m_q_info), 0 where no step is executed.
+// cov[P][8] = {n_mask0, 0, wg_mask, 0, n_mask0, 0, 0, 0}.
+// ============================================================================
+template <int KF_THREADS, bool HAS_GRAY>
+__global__ void __launch_bounds__(KF_THREADS, KF_THREADS == 256 ? 5 : 1)
+k_cov_quarters(const uint32_t* __restrict__ step_qinfo, uint32_t P, GcpTables t, int AL, int T, int MAXP,
+               uint32_t R0, uint32_t* __restrict__ cov, uint8_t* __restrict__ flags)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint32_t s_total, s_totalw;
+    const uint32_t org = blockIdx.x;
+    if (org >= P) return;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) { s_total = 0; s_totalw = 0; }
+    uint32_t n_cov, n_wg;
+    bool failed;
+    coverage_quarters<KF_THREADS, HAS_GRAY>(step_qinfo + (size_t)org * AL, AL, t, T, MAXP, R0, smem,
+                                            n_cov, n_wg, failed);
+    uint32_t v = n_cov, vw = n_wg;
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(FULL, v, o); vw += __shfl_xor_sync(FULL, vw, o); }
+    if (lane == 0 && v) atomicAdd(&s_total, v);
+    if (HAS_GRAY && lane == 0 && vw) atomicAdd(&s_totalw, vw);
+    __syncthreads();
+    if (tid < 8) {
+        const uint32_t n = failed ? 0u : s_total, w = failed ? 0u : s_totalw;
+        cov[(size_t)org * 8 + tid] = (tid == 0 || tid == 4) ? n : (tid == 2 ? w : 0u);
+    }
+    if (tid == 0 && failed && flags) flags[(size_t)org * 4 + 3] |= 2;
+}
+
+int launch_coverage_quarters(gcp_ctx* ctx, const uint32_t* step_qinfo, uint32_t P, uint32_t* cov,
+                             uint8_t* flags, cudaStream_t st)
+{
+    if (P == 0) return 0;
+    if (!ctx->have_masked || !ctx->t.m_q_info) return gcp_fail(ctx, -1, "quarter-item tables not uploaded");
+    const int AL = ctx->p.num_agents * ctx->p.max_dna_len;
+    const int threads = AL > 2048 ? 1024 : 256;
+    int maxp = ctx->cov_maxpairs > 0 ? ctx->cov_maxpairs : (9 * AL) / 4;
+    if (maxp < 256) maxp = 256;
+    if (maxp > KF_PPT * threads) maxp = KF_PPT * threads;
+    maxp = (maxp + 7) & ~7;
+    uint32_t R0 = 1;
+    while ((size_t)R0 * maxp < (size_t)AL * 2 && R0 < 4096) R0 <<= 1;
+    int T = ctx->cov_table;
+    if (T <= 0) { T = threads; while (T < (AL / 3) / (int)R0 && T < 4096) T <<= 1; }
+    const size_t smem = (size_t)T * 20 + (size_t)maxp * 8 + 32;
+    if (smem > (size_t)ctx->max_smem_optin)
+        return gcp_fail(ctx, -3, "coverage kernel needs %zu B shared memory", smem);
+    StageTimer tm(ctx, 1, st);
+    const bool gray = ctx->n_gray > 0;
+#define GCP_LAUNCH_COVQ(TH, GRAY)                                                                      \
+    do {                                                                                               \
+        GCP_CUDA(ctx, cudaFuncSetAttribute(k_cov_quarters<TH, GRAY>,                                   \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        k_cov_quarters<TH, GRAY><<<P, TH, smem, st>>>(step_qinfo, P, ctx->t, AL, T, maxp, R0, cov, flags); \
+    } while (0)
+    if (threads == 256) { if (gray) GCP_LAUNCH_COVQ(256, true); else GCP_LAUNCH_COVQ(256, false); }
+    else                { if (gray) GCP_LAUNCH_COVQ(1024, true); else GCP_LAUNCH_COVQ(1024, false); }
+#undef GCP_LAUNCH_COVQ
+    ctx->launches++;
+    GCP_CUDA(ctx, cudaGetLastError());
+    return 0;
 }
 
 static inline uint32_t al16(uint32_t x) { return (x + 15u) & ~15u; }
