@@ -174,6 +174,12 @@ def cpu_port_rate(w, op, dna_sample, procs):
     return len(dna_sample) / dt, dt
 
 
+def workload_string(name, cfg, w):
+    return ("%s: synthetic %d^2 binary map, N=%d waypoints, E=%d edges, %d agents x %d genes "
+            "(walks of %d steps), population %d per GPU"
+            % (name, cfg['size'], w.N, w.E, cfg['agents'], cfg['L'], cfg['walk'], cfg['pop']))
+
+
 def run_reference(args):
     rank, world_size, _ = dist_env()
     if rank != 0:
@@ -199,10 +205,11 @@ def run_reference(args):
         "ms_per_step": 1000.0 * sum(secs) / len(secs), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64 bitsets + f64 costs",
         "data": "synthetic",
-        "config": {"workload": "%s: synthetic %d^2 binary map, N=%d waypoints, E=%d edges, "
-                               "%d agents x %d genes" % (args.config, cfg['size'], w.N, w.E,
-                                                         cfg['agents'], cfg['L']),
-                   "sample_per_step": per_step},
+        "config": {"workload": workload_string(args.config, cfg, w),
+                   "organisms_per_gpu": cfg['pop'], "global_population": cfg['pop'] * args.gpus,
+                   "sample_per_step": per_step,
+                   "note": "CPU arm: every step evaluates a bounded sample of the same seeded "
+                           "population (the full 65,536 would take hours); rate = sample / time"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
                          "sample": "%d organisms per step, Organism.calcObj restated in numpy/cv2 "
                                    "(oracle/fitness_oracle.py), %d forked processes" %
@@ -491,9 +498,7 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64 bitsets + f64 costs", "data": "synthetic",
-            "config": {"workload": "%s: synthetic %d^2 binary map, N=%d waypoints, E=%d edges, "
-                                   "%d agents x %d genes (walks of %d steps), population %d per GPU"
-                                   % (args.config, cfg['size'], w.N, w.E, A, L, cfg['walk'], P),
+            "config": {"workload": workload_string(args.config, cfg, w),
                        "organisms_per_gpu": P, "global_population": P * world_size,
                        "mean_executed_steps_per_organism": S_mean,
                        "l2": "per-step input (dna, %.0f MB) exceeds the 126 MB L2; no flush; the "
