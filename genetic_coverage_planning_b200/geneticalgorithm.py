@@ -120,7 +120,7 @@ class Organism(object):
 class GeneticalGorithm(object):
     """geneticalgorithm.py:15-123."""
 
-    def __init__(self, mappy, pather, gen_params, device=0, seed=None, initial_dna=None):
+    def __init__(self, mappy, pather, gen_params, device=0, seed=None, initial_dna=None, gen_num=0):
         self._G_sz = gen_params['gen_size']
         self._starting_path_len = gen_params['starting_path_len']
         self._num_agents = gen_params['num_agents']
@@ -132,7 +132,7 @@ class GeneticalGorithm(object):
         self._mappy, self._pather = mappy, pather
         self._device = device
         self._seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
-        self._gen_num = 0
+        self._gen_num = int(gen_num)
         self._views = None
         if self._G_sz % 2:
             raise ValueError("gen_size must be even (pather_driver.py:107)")
@@ -144,6 +144,28 @@ class GeneticalGorithm(object):
             self.firstGeneration(mappy, pather, self._org_params)
         self._fit, self._obj_sc = self._eng.maximin(self._obj, self._coverage_constr(),
                                                     return_scaled=True)
+
+    @classmethod
+    def from_population(cls, population, gen_params=None, device=0, seed=None):
+        """Continue a population that was evolved (or unpickled, gori_tools.py:255-257) with the
+        REFERENCE's GeneticalGorithm - or anything that looks like one: `_gen_parent` (objects
+        with `_dna`, `_mappy`, `_pather`), `_gen_num`, and the scalar attributes of
+        geneticalgorithm.py:16-35.  The parents are re-evaluated on the GPU (their stored
+        objectives are not trusted), ranked, and evolution continues from `_gen_num`."""
+        first = population._gen_parent[0]
+        if gen_params is None:
+            gen_params = {'gen_size': population._G_sz,
+                          'starting_path_len': population._starting_path_len,
+                          'num_agents': population._num_agents, 'gamma': population._gamma,
+                          'coverage_constr_0': -population._cov_constr_0,
+                          'coverage_constr_f': -population._cov_constr_f,
+                          'coverage_aging': population._cov_aging,
+                          'org_params': population._org_params}
+        L = gen_params['org_params']['max_dna_len']
+        dna = np.stack([_pad_rows(list(o._dna), L) for o in population._gen_parent]).astype(np.int32)
+        pop = cls(first._mappy, first._pather, gen_params, device=device, seed=seed,
+                  initial_dna=dna, gen_num=int(getattr(population, '_gen_num', 0)))
+        return pop
 
     # -- reference: geneticalgorithm.py:37-53 ------------------------------------------
     def firstGeneration(self, mappy, pather, org_params, max_batches=10000):

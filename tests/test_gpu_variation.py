@@ -345,6 +345,24 @@ def test_facade_drop_in(tmp_path):
     assert kid_a.calcObj() == kid_a._obj_val
     org = Organism([r for r in pop._gen_parent[2]._dna_list], mappy, pather, op, _seed=1)
     assert org._dna[1, 0] == starts[1]
+    # migration: continue a population that came from the reference's classes (duck-typed here:
+    # plain objects carrying the attributes of geneticalgorithm.py:16-35 / :127-175)
+    class _Ref(object):
+        pass
+    old = _Ref()
+    for k in ("_G_sz", "_starting_path_len", "_num_agents", "_gamma", "_cov_constr_0",
+              "_cov_constr_f", "_cov_aging", "_org_params", "_gen_num"):
+        setattr(old, k, getattr(pop, k))
+    old._gen_parent = []
+    for o in pop._gen_parent:
+        r = _Ref()
+        r._dna, r._mappy, r._pather, r._obj_val = o._dna.copy(), mappy, pather, [0.0, 0.0]
+        old._gen_parent.append(r)
+    cont = GeneticalGorithm.from_population(old, seed=9)
+    assert cont._gen_num == pop._gen_num
+    assert [o._obj_val for o in cont._gen_parent] == [o._obj_val for o in pop._gen_parent]
+    assert cont._gen_parent_fit == cont.rackNstack(cont._gen_parent)       # re-ranked among themselves
+    assert len(cont.runEvolution(1)) == 1 and cont._gen_num == pop._gen_num + 1
     # pickle round trip (gori_tools.savePopulation / loadPopulation)
     fn = os.path.join(tmp_path, "pop.pkl")
     pickle.dump(pop, open(fn, "wb"))
