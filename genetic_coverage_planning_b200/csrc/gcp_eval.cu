@@ -433,18 +433,6 @@ int launch_coverage(gcp_ctx* ctx, const uint32_t* edge_ids, uint32_t P, uint32_t
 constexpr int K2M_THREADS = 256;
 constexpr int K2M_PPT = 12;               // pairs staged per thread (MAXP <= 12 * 256)
 
-__device__ __forceinline__ uint4 ld_quarter1(const uint4* __restrict__ tile, uint32_t p,
-                                             uint32_t q1, uint32_t below1, uint32_t l7)
-{
-    // p = payload << 1 | last  ->  qmask at bits [1,5), offset at bits [5,32)
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if ((p >> q1) & 1u) {
-        const uint32_t idx = (((p >> 5) + __popc(p & below1)) << 3) | l7;
-        v = __ldg(tile + idx);
-    }
-    return v;
-}
-
 __global__ void __launch_bounds__(K2M_THREADS, 5)
 k_coverage_masked(const uint32_t* __restrict__ step_info, uint32_t P,
                   const uint2* __restrict__ sub_desc, const uint4* __restrict__ tile, int AL,

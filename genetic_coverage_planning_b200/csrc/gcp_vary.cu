@@ -98,17 +98,6 @@ __device__ __forceinline__ int w_valid_len(const int32_t* r, int L, int lane)
     return L;
 }
 
-// lane e: the e-th out-neighbour of `node`, or ~0
-__device__ __forceinline__ uint32_t w_nbr(const GcpTables& t, int node, int lane)
-{
-    if (t.adj8) {
-        const uint2 a = __ldg(t.adj8 + (size_t)node * 8 + (lane & 7));
-        return lane < 8 ? a.x : 0xFFFFFFFFu;
-    }
-    const uint32_t lo = __ldg(t.row_ptr + node), hi = __ldg(t.row_ptr + node + 1);
-    return (lo + lane < hi) ? __ldg(t.col + lo + lane) : 0xFFFFFFFFu;
-}
-
 // pathmaker.py:188-213.  r[pos] is the current node; appends up to n_steps nodes (stops at
 // L).  The no-return memory is the last `path_memory` nodes of the running path, never
 // reaching below row index mem_floor: that is just r[max(mem_floor, pos-mem+1) .. pos].
