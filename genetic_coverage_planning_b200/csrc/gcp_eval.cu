@@ -849,7 +849,7 @@ int launch_loop_closures(gcp_ctx* ctx, const int32_t* dna, uint32_t P, const dou
     const int A = ctx->p.num_agents, L = ctx->p.max_dna_len;
     int T3 = (A * L * 3) / 2 + 64;            // load factor <= 2/3, never full; ids fit 16 bits
     const size_t smem = (size_t)T3 * 12 + (size_t)A * L * 9 + 16;
-    if (T3 > 65535 || smem > (size_t)ctx->max_smem_optin || ctx->force_lc_big)
+    if (T3 > 65535 || smem > (size_t)ctx->max_smem_optin || ctx->force_lc_big)   // 1: radix sort, 2: partitioned hash
         return launch_loop_closures_big(ctx, dna, P, dist, turn, cov, lc, obj, neg_cov, flags, st);
     GCP_CUDA(ctx, cudaFuncSetAttribute(k_loop_closures,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -134,6 +134,171 @@ k_lcb_finish(uint32_t P, int A, gcp_params prm, gcp_map_consts mc, const int32_t
                           turn + (size_t)org * A, org, obj, neg_cov_out, flags);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Hash-partitioned shared-memory variant (default for long genomes): one 1024-thread CTA per
+// organism.  The compacted gene sequence goes to global scratch (it stays in L2 for the CTA's
+// lifetime); the duplicate-edge hash table of k_loop_closures is kept, but only for the keys of
+// ONE of R hash partitions at a time, so that it fits shared memory for any A*L <= 65,535.  The
+// owner agent of a position is found from the row bases instead of a per-position array.
+// ---------------------------------------------------------------------------------------------
+constexpr int LP_THREADS = 1024;
+constexpr int LP_NW = LP_THREADS / 32;
+constexpr uint32_t LP_NIL = 0xFFFFFFFFu;
+
+template <typename SEQ>
+__device__ __forceinline__ unsigned long long lp_key(const SEQ* sq, int i, int n)
+{
+    const unsigned long long f = (uint32_t)sq[i] & 0xFFFFFFu;
+    const unsigned long long g = (uint32_t)sq[(i + 1 == n) ? 0 : i + 1] & 0xFFFFFFu;
+    return ((f << 24) | g) + 1ull;                                         // never 0
+}
+__device__ __forceinline__ uint32_t lp_hash(unsigned long long key) { return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32); }
+
+// SEQ16: node ids fit 16 bits -> the compacted sequence lives in shared memory (u16) instead of
+// global scratch (out-of-range genes are reported by k_path_costs; here they are truncated).
+template <bool SEQ16>
+__global__ void __launch_bounds__(LP_THREADS, 1)
+k_loop_closures_part(const int32_t* __restrict__ dna, uint32_t P, int A, int L, int T3 /*slots per partition*/,
+                     uint32_t R /*pow2 partitions*/, gcp_params prm, gcp_map_consts mc,
+                     int32_t* __restrict__ seq /*[P][A*L] scratch*/,
+                     const double* __restrict__ dist, const double* __restrict__ turn,
+                     const uint32_t* __restrict__ cov, int32_t* __restrict__ lc_out,
+                     double* __restrict__ obj, double* __restrict__ neg_cov_out, uint8_t* __restrict__ flags)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned long long* s_hkey = reinterpret_cast<unsigned long long*>(smem);       // [T3]
+    uint32_t* s_hcnt = reinterpret_cast<uint32_t*>(s_hkey + T3);                     // [T3] count | flags
+    uint32_t* s_head = s_hcnt + T3;                                                  // [T3] list head
+    uint32_t* s_ownm = s_head + T3;                                                  // [T3] owner mask
+    uint16_t* s_next = reinterpret_cast<uint16_t*>(s_ownm + T3);                     // [A*L]
+    int*      s_lc   = reinterpret_cast<int*>(s_next + ((A * L + 1) & ~1));          // [A*A]
+    uint16_t* s_seq16 = reinterpret_cast<uint16_t*>(s_lc + A * A);                   // [A*L] if SEQ16
+    __shared__ int s_len[GCP_MAX_AGENTS], s_base[GCP_MAX_AGENTS + 1];
+    __shared__ int s_fail;
+
+    const uint32_t org = blockIdx.x;
+    if (org >= P) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int AL = A * L;
+    const int32_t* d = dna + (size_t)org * AL;
+    int32_t* sq32 = SEQ16 ? nullptr : seq + (size_t)org * AL;
+
+    if (tid == 0) s_fail = 0;
+    for (int i = tid; i < A * A; i += LP_THREADS) s_lc[i] = 0;
+    for (int a = warp; a < A; a += LP_NW) {
+        int cnt = 0;
+        for (int i0 = 0; i0 < L; i0 += 32) {
+            const int i = i0 + lane;
+            cnt += __popc(__ballot_sync(FULL, (i < L) && (d[a * L + i] != -1)));
+        }
+        if (lane == 0) s_len[a] = cnt;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int b = 0;
+        for (int a = 0; a < A; ++a) { s_base[a] = b; b += s_len[a]; }
+        s_base[A] = b;
+    }
+    __syncthreads();
+    const int n = s_base[A];
+    for (int a = warp; a < A; a += LP_NW) {                      // compaction (row-major, mappy.py:390)
+        int run = s_base[a];
+        for (int i0 = 0; i0 < L; i0 += 32) {
+            const int i = i0 + lane;
+            const int g = (i < L) ? d[a * L + i] : -1;
+            const bool v = g != -1;
+            const uint32_t bal = __ballot_sync(FULL, v);
+            if (v) {
+                const int pos = run + __popc(bal & ((1u << lane) - 1u));
+                if (SEQ16) s_seq16[pos] = (uint16_t)g; else sq32[pos] = g;
+            }
+            run += __popc(bal);
+        }
+    }
+    __syncthreads();                                             // the CTA's own global writes are visible to it
+
+    const int thresh = prm.solo_sep_thresh;
+    for (uint32_t r = 0; r < R; ++r) {
+        for (int h = tid; h < T3; h += LP_THREADS) { s_hkey[h] = 0ull; s_hcnt[h] = 0u; s_head[h] = LP_NIL; s_ownm[h] = 0u; }
+        __syncthreads();
+        // pass 1: count the keys of this partition
+        for (int i = tid; i < n; i += LP_THREADS) {
+            const unsigned long long key = SEQ16 ? lp_key(s_seq16, i, n) : lp_key(sq32, i, n);
+            const uint32_t hv = lp_hash(key);
+            if ((hv & (R - 1)) != r) continue;
+            uint32_t h = __umulhi(hv, (uint32_t)T3);
+            int probes = 0;
+            for (;;) {
+                const unsigned long long cur = ((volatile unsigned long long*)s_hkey)[h];
+                if (cur == key) break;
+                if (cur == 0ull) {
+                    const unsigned long long old = atomicCAS(&s_hkey[h], 0ull, key);
+                    if (old == 0ull || old == key) break;
+                }
+                h = (h + 1 == (uint32_t)T3) ? 0u : h + 1;
+                if (++probes >= T3) { s_fail = 1; break; }       // partition far larger than expected
+            }
+            if (probes < T3) atomicAdd(&s_hcnt[h], 1u);
+        }
+        __syncthreads();
+        if (s_fail) break;                                       // uniform: reported through flags[3]
+        // pass 2: members of duplicate groups link themselves, record owner and split flag
+        for (int i = tid; i < n; i += LP_THREADS) {
+            const unsigned long long key = SEQ16 ? lp_key(s_seq16, i, n) : lp_key(sq32, i, n);
+            const uint32_t hv = lp_hash(key);
+            if ((hv & (R - 1)) != r) continue;
+            uint32_t h = __umulhi(hv, (uint32_t)T3);
+            while (s_hkey[h] != key) h = (h + 1 == (uint32_t)T3) ? 0u : h + 1;
+            if ((s_hcnt[h] & 0xFFFFu) < 2u) continue;
+            int a = 0;
+            while (a + 1 < A && i >= s_base[a + 1]) ++a;          // owner row of position i
+            while (s_len[a] == 0) ++a;                            // (rows of length 0 share a base)
+            s_next[i] = (uint16_t)atomicExch(&s_head[h], (uint32_t)i);      // NIL -> 0xFFFF
+            atomicOr(&s_ownm[h], 1u << a);
+            if (a >= 1 && i == s_base[a]) atomicOr(&s_hcnt[h], 1u << 16);   // touches a path split (F10)
+        }
+        __syncthreads();
+        // pass 3: successor gap test (ascending consecutive positions)
+        for (int i = tid; i < n; i += LP_THREADS) {
+            const unsigned long long key = SEQ16 ? lp_key(s_seq16, i, n) : lp_key(sq32, i, n);
+            const uint32_t hv = lp_hash(key);
+            if ((hv & (R - 1)) != r) continue;
+            uint32_t h = __umulhi(hv, (uint32_t)T3);
+            while (s_hkey[h] != key) h = (h + 1 == (uint32_t)T3) ? 0u : h + 1;
+            const uint32_t c = s_hcnt[h];
+            if ((c & 0xFFFFu) < 2u || (c & (1u << 16))) continue;
+            uint32_t succ = 0xFFFFFFFFu;
+            for (uint32_t j = s_head[h]; j != 0xFFFFu && j != LP_NIL; j = s_next[j])
+                if (j > (uint32_t)i && j < succ) succ = j;
+            if (succ != 0xFFFFFFFFu && (int)(succ - (uint32_t)i) > thresh) atomicOr(&s_hcnt[h], 1u << 17);
+        }
+        __syncthreads();
+        // pass 4: one thread per duplicate group updates lc_mat
+        for (int h = tid; h < T3; h += LP_THREADS) {
+            const uint32_t c = s_hcnt[h];
+            if ((c & 0xFFFFu) < 2u || (c & (1u << 16))) continue;
+            const uint32_t owners = s_ownm[h];
+            if (__popc(owners) == 1) {
+                if (c & (1u << 17)) { const int a = __ffs(owners) - 1; atomicAdd(&s_lc[a * A + a], 1); }
+            } else {
+                for (uint32_t mx = owners; mx; mx &= mx - 1) {
+                    const int x = __ffs(mx) - 1;
+                    for (uint32_t my = mx & (mx - 1); my; my &= my - 1)
+                        atomicAdd(&s_lc[x * A + (__ffs(my) - 1)], 1);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (lc_out)
+        for (int i = tid; i < A * A; i += LP_THREADS) lc_out[(size_t)org * A * A + i] = s_lc[i];
+    if (tid == 0) {
+        finish_objectives(s_lc, A, prm, mc, cov + (size_t)org * 8, dist + (size_t)org * A,
+                          turn + (size_t)org * A, org, obj, neg_cov_out, flags);
+        if (s_fail && flags) flags[(size_t)org * 4 + 3] |= 4;
+    }
+}
+
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static int bits_for(uint32_t x) { int b = 1; while (b < 32 && (1u << b) <= x) ++b; return b; }
@@ -145,6 +310,49 @@ int launch_loop_closures_big(gcp_ctx* ctx, const int32_t* dna, uint32_t P, const
     if (P == 0) return 0;
     const int A = ctx->p.num_agents, L = ctx->p.max_dna_len;
     const size_t AL = (size_t)A * L;
+    if (ctx->force_lc_big != 1) {
+        // hash-partitioned shared-memory kernel: pick the smallest R whose tables fit; keeping the
+        // sequence in shared memory (16-bit node ids) only when that does not cost a partition
+        auto pick = [&](bool s16, int* T3_out, size_t* smem_out) -> uint32_t {
+            const size_t fixed = ((AL + 1) & ~(size_t)1) * 2 * (s16 ? 2 : 1) + (size_t)A * A * 4 + 64;
+            for (uint32_t R = 1; R <= 64; R <<= 1) {
+                const int T3 = (int)((AL * 3) / (2 * R)) + 64 + (R > 1 ? (int)(AL / (4 * R)) : 0);   // slack: uneven partitions
+                const size_t smem = (size_t)T3 * 20 + fixed;
+                if (smem <= (size_t)ctx->max_smem_optin) { *T3_out = T3; *smem_out = smem; return R; }
+            }
+            return 0;
+        };
+        int T3a = 0, T3b = 0; size_t sma = 0, smb = 0;
+        const uint32_t Ra = ctx->t.N <= 65536 ? pick(true, &T3a, &sma) : 0;
+        const uint32_t Rb = pick(false, &T3b, &smb);
+        const bool seq16 = Ra != 0 && (Rb == 0 || Ra <= Rb);
+        const uint32_t R = seq16 ? Ra : Rb;
+        const int T3 = seq16 ? T3a : T3b;
+        const size_t smem = seq16 ? sma : smb;
+        if (R != 0) {
+            const size_t need = seq16 ? 256 : al256((size_t)P * AL * 4);
+            if (ctx->lcb_scratch_bytes < need) {
+                if (ctx->lcb_scratch) cudaFree(ctx->lcb_scratch);
+                ctx->lcb_scratch = nullptr; ctx->lcb_scratch_bytes = 0;
+                GCP_CUDA(ctx, cudaMalloc(&ctx->lcb_scratch, need));
+                ctx->lcb_scratch_bytes = need;
+            }
+            StageTimer tm(ctx, 2, st);
+            int32_t* seq = reinterpret_cast<int32_t*>(ctx->lcb_scratch);
+            if (seq16) {
+                GCP_CUDA(ctx, cudaFuncSetAttribute(k_loop_closures_part<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_loop_closures_part<true><<<P, LP_THREADS, smem, st>>>(dna, P, A, L, T3, R, ctx->p, ctx->mc, seq, dist,
+                                                                        turn, cov, lc_out, obj, neg_cov, flags);
+            } else {
+                GCP_CUDA(ctx, cudaFuncSetAttribute(k_loop_closures_part<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_loop_closures_part<false><<<P, LP_THREADS, smem, st>>>(dna, P, A, L, T3, R, ctx->p, ctx->mc, seq, dist,
+                                                                         turn, cov, lc_out, obj, neg_cov, flags);
+            }
+            ctx->launches++;
+            GCP_CUDA(ctx, cudaGetLastError());
+            return 0;
+        }
+    }
     const int nb = bits_for(ctx->t.N - 1);
     // chunk of organisms sorted at once: <= 16 Mi items, organism index must fit the key
     uint32_t chunk = (uint32_t)((16u << 20) / AL);

@@ -218,7 +218,7 @@ int gcp_gather_survivors(gcp_ctx* ctx, const int32_t* order_dev, uint32_t n_org,
 /* ---- tuning / testing knobs (defaults are right for production) ---------------------
  * "rank_algo": 0 auto, 1 O(N^2) dominance-matrix tiles, 2 sort-based O(N log N) (both exact);
  * "force_general": never take the pre-masked coverage fast path; "fused_eval": 0 = staged kernels;
- * "force_lc_big": sort-based loop closures even for short genomes; "vary_org_offset": global id of
+ * "force_lc_big": long-genome loop closures even for short genomes (1 radix sort, 2 partitioned hash); "vary_org_offset": global id of
  * local organism 0 when a rank varies only its shard of the children (keys of the Philox streams);
  * "cov_table", "cov_maxpairs": shared-memory sizing of the coverage kernels (0 = auto). */
 int gcp_set_option(gcp_ctx* ctx, const char* name, int64_t value);

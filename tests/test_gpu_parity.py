@@ -308,15 +308,16 @@ def test_sort_based_loop_closures(eng_big, world_big, golden_dir):
     dna = np.concatenate([z['dna'], e['dna'], _random_dna(world_big, 300, eng_big.A, eng_big.L, seed=31)]
                          ).astype(np.int32)
     want = eng_big.evaluate(dna)
-    eng_big.set_option("force_lc_big", 1)
-    try:
-        got = eng_big.evaluate(dna)
-    finally:
-        eng_big.set_option("force_lc_big", 0)
-    for name in ("obj", "neg_cov", "lc_mat", "flags"):
-        assert np.array_equal(getattr(got, name).cpu().numpy(), getattr(want, name).cpu().numpy()), name
     n = len(z['dna'])
-    assert np.array_equal(got.lc_mat.cpu().numpy()[:n], z['lc'].astype(np.int32))
+    for mode in (1, 2):                      # 1: radix sort of edge keys, 2: hash-partitioned shared memory
+        eng_big.set_option("force_lc_big", mode)
+        try:
+            got = eng_big.evaluate(dna)
+        finally:
+            eng_big.set_option("force_lc_big", 0)
+        for name in ("obj", "neg_cov", "lc_mat", "flags"):
+            assert np.array_equal(getattr(got, name).cpu().numpy(), getattr(want, name).cpu().numpy()), (mode, name)
+        assert np.array_equal(got.lc_mat.cpu().numpy()[:n], z['lc'].astype(np.int32))
 
 
 def test_many_agents_long_rows(synth_setup):
@@ -330,8 +331,13 @@ def test_many_agents_long_rows(synth_setup):
     op2 = worlds.org_params_for(dict(L=L), st)
     eng2 = FitnessEngine(pw, op2, num_agents=A)
     dna = synth.random_walk_population(sw.xy, sw.row_ptr, sw.col, st, 5, 520, L, seed=12).astype(np.int32)
-    r = eng2.evaluate(dna, detail=True, pixel_counts=False)
+    r = eng2.evaluate(dna, detail=True, pixel_counts=False)       # partitioned-hash loop closures
     assert not r.flags.cpu().numpy()[:, 3].any()
+    eng2.set_option("force_lc_big", 1)                            # radix-sort formulation
+    r1 = eng2.evaluate(dna, detail=True, pixel_counts=False)
+    eng2.set_option("force_lc_big", 0)
+    assert np.array_equal(r1.lc_mat.cpu().numpy(), r.lc_mat.cpu().numpy())
+    assert np.array_equal(r1.obj.cpu().numpy(), r.obj.cpu().numpy())
     ow2 = World(sw.img, sw.xy, sw.row_ptr, sw.col, sw.edge_poly, sw.edge_theta, sw.edge_dist,
                 sw.map_params, op2, name="synth-16x640")
     for k in range(2):
