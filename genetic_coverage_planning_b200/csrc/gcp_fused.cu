@@ -171,6 +171,10 @@ __device__ __forceinline__ void coverage_quarters(const uint32_t* info, int AL, 
                 if (pos[k] != KF_NIL) s_pay[pos[k]] = ent[k];
             __syncthreads();
             // ---- B2: owner warps, groups of 32 slots handed out dynamically ----
+            // per-lane tile base kept in registers: the opaque asm stops ptxas from re-deriving
+            // it (S2R tid + LDC of the table pointer) in front of every load
+            const uint4* tile_l = t.m_tile + l7;
+            asm volatile("" : "+l"(tile_l));
             for (;;) {
                 uint32_t g = 0;
                 if (lane == 0) g = atomicAdd(&s_group, 1u);
@@ -188,10 +192,10 @@ __device__ __forceinline__ void coverage_quarters(const uint32_t* info, int AL, 
                         // reading past cnt only fetches a neighbour's entry (s_pay is padded)
                         const uint32_t i0 = pb[k], i1 = pb[k + 1], i2 = pb[k + 2], i3 = pb[k + 3];
                         uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0, v3 = v0;
-                        if (k < cnt) v0 = __ldg(t.m_tile + (i0 + l7));
-                        if (k + 1 < cnt) v1 = __ldg(t.m_tile + (i1 + l7));
-                        if (k + 2 < cnt) v2 = __ldg(t.m_tile + (i2 + l7));
-                        if (k + 3 < cnt) v3 = __ldg(t.m_tile + (i3 + l7));
+                        if (k < cnt) v0 = __ldg(tile_l + i0);
+                        if (k + 1 < cnt) v1 = __ldg(tile_l + i1);
+                        if (k + 2 < cnt) v2 = __ldg(tile_l + i2);
+                        if (k + 3 < cnt) v3 = __ldg(tile_l + i3);
                         acc.x |= (v0.x | v1.x) | (v2.x | v3.x);
                         acc.y |= (v0.y | v1.y) | (v2.y | v3.y);
                         acc.z |= (v0.z | v1.z) | (v2.z | v3.z);
