@@ -231,9 +231,32 @@ __device__ __forceinline__ void coverage_quarters(const uint32_t* info, int AL, 
     }
 }
 
+// Compile-time copy of fused_shape() for A*L == SAL with 256 threads and default tuning: with the
+// shared-memory layout known at compile time the offsets fold into the LDS / STS / ATOMS
+// immediates instead of being rebuilt from kernel parameters in front of every access.
+constexpr uint32_t c_al16(uint32_t x) { return (x + 15u) & ~15u; }
+template <int SAL>
+struct StaticShape {
+    static constexpr int AL = SAL;
+    static constexpr int maxp0 = (9 * SAL) / 4 < 256 ? 256 : ((9 * SAL) / 4 > KF_PPT * 256 ? KF_PPT * 256 : (9 * SAL) / 4);
+    static constexpr int MAXP = (maxp0 + 7) & ~7;
+    static constexpr int T = SAL / 3 <= 256 ? 256 : SAL / 3 <= 512 ? 512 : SAL / 3 <= 1024 ? 1024 : SAL / 3 <= 2048 ? 2048 : SAL / 3 <= 4096 ? 4096 : 8192;
+    static constexpr int T3 = (SAL * 3) / 2 + 64;
+    static constexpr uint32_t R0 = (size_t)MAXP >= (size_t)SAL * 2 ? 1u : 0u;      // 0: not representable -> runtime shape
+    static constexpr uint32_t off_cst = (uint32_t)T * 20;
+    static constexpr uint32_t cov_b = (uint32_t)T * 20 + (uint32_t)MAXP * 8 + 32;
+    static constexpr uint32_t a_b = off_cst + (uint32_t)SAL * 16;
+    static constexpr uint32_t lc_b = c_al16((uint32_t)T3 * 12 + (uint32_t)SAL) + (uint32_t)SAL * 4;
+    static constexpr uint32_t x_b = cov_b > lc_b ? (cov_b > a_b ? cov_b : a_b) : (lc_b > a_b ? lc_b : a_b);
+    static constexpr uint32_t off_info = c_al16((uint32_t)SAL * 4);
+    static constexpr uint32_t off_x = off_info + c_al16((uint32_t)SAL * 4);
+    static constexpr uint32_t off_lc = off_x + c_al16(x_b);
+};
+
 // KF_THREADS = 256 (5 CTAs / SM) for reference-sized genomes, 1024 (one CTA / SM) for long ones.
 // HAS_GRAY: the map has pixels with 0 < g < 255: covered gray mask pixels weigh 255 - g.
-template <int KF_THREADS, bool HAS_GRAY>
+// SAL > 0: A*L == SAL and the shared-memory layout is StaticShape<SAL> (must equal fused_shape()).
+template <int KF_THREADS, bool HAS_GRAY, int SAL>
 __global__ void __launch_bounds__(KF_THREADS, KF_THREADS == 256 ? 5 : 1)
 k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape sh,
              gcp_params prm, gcp_map_consts mc,
@@ -244,10 +267,12 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     constexpr int KF_NW = KF_THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem[];
     int32_t*  s_dna  = reinterpret_cast<int32_t*>(smem);                      // [AL]
-    uint32_t* s_info = reinterpret_cast<uint32_t*>(smem + sh.off_info);       // [AL] quarter-item range per step (C: slot/next)
-    unsigned char* s_x = smem + sh.off_x;                                     // B / C tables
-    double2*  s_cst  = reinterpret_cast<double2*>(smem + sh.off_x + sh.off_cst); // [AL] {dist, turn} per step (A only; aliases s_pay/s_sr)
-    int*      s_lc   = reinterpret_cast<int*>(smem + sh.off_lc);              // [A*A]
+    constexpr bool ST = SAL > 0;
+    using SS = StaticShape<ST ? SAL : 1200>;
+    uint32_t* s_info = reinterpret_cast<uint32_t*>(smem + (ST ? SS::off_info : sh.off_info)); // [AL] quarter-item range per step (C: slot/next)
+    unsigned char* s_x = smem + (ST ? SS::off_x : sh.off_x);                  // B / C tables
+    double2*  s_cst  = reinterpret_cast<double2*>(s_x + (ST ? SS::off_cst : sh.off_cst)); // [AL] {dist, turn} per step (A only; aliases s_pay/s_sr)
+    int*      s_lc   = reinterpret_cast<int*>(smem + (ST ? SS::off_lc : sh.off_lc));       // [A*A]
     double*   s_cost = reinterpret_cast<double*>(smem + sh.off_cost);         // dist[A], turn[A]
     __shared__ int s_first_neg[GCP_MAX_AGENTS], s_len[GCP_MAX_AGENTS], s_base[GCP_MAX_AGENTS + 1];
     __shared__ int s_bad;
@@ -257,7 +282,7 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     const uint32_t org = blockIdx.x;
     if (org >= P) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int A = sh.A, L = sh.L, AL = sh.AL;
+    const int A = sh.A, L = sh.L, AL = ST ? SAL : sh.AL;
 
     // ------------------------------------------------------------------ load the chromosome
     if (sh.gene16) {                       // int16 chromosome (N < 32768): half the bytes to move
@@ -381,7 +406,8 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     }
     uint32_t n_cov, n_wg;
     bool failed;
-    coverage_quarters<KF_THREADS, HAS_GRAY>(s_info, AL, t, sh.T, sh.MAXP, sh.R0, s_x, n_cov, n_wg, failed);
+    coverage_quarters<KF_THREADS, HAS_GRAY>(s_info, AL, t, ST ? SS::T : sh.T, ST ? SS::MAXP : sh.MAXP,
+                                            ST ? 1u : sh.R0, s_x, n_cov, n_wg, failed);
     {
         uint32_t v = n_cov, vw = n_wg;
         #pragma unroll
@@ -392,7 +418,7 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     __syncthreads();      // B's tables are dead from here
 
     // ------------------------------------------------------------------ phase C: loop closures
-    const int T3 = sh.T3;
+    const int T3 = ST ? SS::T3 : sh.T3;
     unsigned long long* s_hkey = reinterpret_cast<unsigned long long*>(s_x);      // [T3]
     uint32_t* s_hcnt = reinterpret_cast<uint32_t*>(s_hkey + T3);                   // [T3]
     uint8_t*  s_own  = reinterpret_cast<uint8_t*>(s_hcnt + T3);                    // [AL]
@@ -636,17 +662,38 @@ int launch_eval_fused(gcp_ctx* ctx, const void* dna, int gene16, uint32_t P, con
     if (threads == 0)
         return gcp_fail(ctx, -3, "fused eval kernel needs %zu B shared memory (A*L too large)", smem);
     StageTimer tm(ctx, 1, st);
-#define GCP_LAUNCH_FUSED(TH, GRAY)                                                                     \
+#define GCP_LAUNCH_FUSED(TH, GRAY, SAL)                                                                \
     do {                                                                                               \
-        GCP_CUDA(ctx, cudaFuncSetAttribute(k_eval_fused<TH, GRAY>,                                     \
+        GCP_CUDA(ctx, cudaFuncSetAttribute(k_eval_fused<TH, GRAY, SAL>,                                \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-        k_eval_fused<TH, GRAY><<<P, TH, smem, st>>>(dna, P, ctx->t, sh, ctx->p, ctx->mc, out->obj,    \
-                                                    out->neg_cov, out->dist, out->turn, out->lc_mat,   \
-                                                    out->flags);                                       \
+        k_eval_fused<TH, GRAY, SAL><<<P, TH, smem, st>>>(dna, P, ctx->t, sh, ctx->p, ctx->mc, out->obj, \
+                                                         out->neg_cov, out->dist, out->turn,           \
+                                                         out->lc_mat, out->flags);                     \
     } while (0)
     const bool gray = ctx->n_gray > 0;
-    if (threads == 256) { if (gray) GCP_LAUNCH_FUSED(256, true); else GCP_LAUNCH_FUSED(256, false); }
-    else                { if (gray) GCP_LAUNCH_FUSED(1024, true); else GCP_LAUNCH_FUSED(1024, false); }
+    // the genome shapes of the reference's driver (pather_driver.py:122-158: max_dna_len 250 / 200 /
+    // 150 / 125 / 125 / 200 for 1..6 agents) get the compile-time layout
+#define GCP_TRY_STATIC(SAL)                                                                            \
+    if (!done && threads == 256 && sh.AL == SAL && StaticShape<SAL>::R0 == 1 && sh.R0 == 1 &&         \
+        sh.T == StaticShape<SAL>::T && sh.MAXP == StaticShape<SAL>::MAXP &&                           \
+        sh.T3 == StaticShape<SAL>::T3 && sh.off_info == StaticShape<SAL>::off_info &&                 \
+        sh.off_x == StaticShape<SAL>::off_x && sh.off_cst == StaticShape<SAL>::off_cst &&             \
+        sh.off_lc == StaticShape<SAL>::off_lc) {                                                       \
+        if (gray) GCP_LAUNCH_FUSED(256, true, SAL); else GCP_LAUNCH_FUSED(256, false, SAL);           \
+        done = true;                                                                                   \
+    }
+    bool done = false;
+    GCP_TRY_STATIC(1200)
+    GCP_TRY_STATIC(625)
+    GCP_TRY_STATIC(500)
+    GCP_TRY_STATIC(450)
+    GCP_TRY_STATIC(400)
+    GCP_TRY_STATIC(250)
+#undef GCP_TRY_STATIC
+    if (!done) {
+        if (threads == 256) { if (gray) GCP_LAUNCH_FUSED(256, true, 0); else GCP_LAUNCH_FUSED(256, false, 0); }
+        else                { if (gray) GCP_LAUNCH_FUSED(1024, true, 0); else GCP_LAUNCH_FUSED(1024, false, 0); }
+    }
 #undef GCP_LAUNCH_FUSED
     ctx->launches++;
     GCP_CUDA(ctx, cudaGetLastError());
