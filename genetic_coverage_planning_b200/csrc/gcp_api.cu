@@ -138,6 +138,16 @@ int gcp_upload_edges(gcp_ctx* c, const double* edge_cost, const double* edge_the
             }
         if ((r = upload(c, &c->t.adj8, adj.data(), adj.size()))) return r;
     }
+    c->t.adjc16 = nullptr;
+    if (c->max_degree <= 8 && c->t.N <= 65535) {   // edge lookup of the evaluation: 8 x u16 columns = one 16-B load
+        std::vector<uint16_t> a16((size_t)c->t.N * 8, (uint16_t)0xFFFF);
+        for (uint32_t i = 0; i < c->t.N; ++i)
+            for (uint32_t e = c->h_row_ptr[i]; e < c->h_row_ptr[i + 1]; ++e)
+                a16[(size_t)i * 8 + (e - c->h_row_ptr[i])] = (uint16_t)c->h_col[e];
+        const uint4* dev = nullptr;
+        if ((r = upload(c, &dev, a16.data(), a16.size() / 8))) return r;      // uint4 = 8 x u16
+        c->t.adjc16 = dev;
+    }
     c->h_row_ptr.clear(); c->h_row_ptr.shrink_to_fit();
     c->h_col.clear(); c->h_col.shrink_to_fit();
     {   // device layout: one u32 per edge (first | count<<28) and one uint2 per sub-tile
@@ -189,6 +199,7 @@ int gcp_upload_masked_footprints(gcp_ctx* c, const uint32_t* sub_ptr, const uint
         qdesc.reserve((size_t)n_sub * 2);
         bool ok = true;
         for (size_t e = 0; e < EN && ok; ++e) {
+            if (qdesc.size() & 1) qdesc.push_back(make_uint2(0u, 0u));   // lists start 16-B aligned: items are read in pairs
             const size_t first = qdesc.size();
             for (uint32_t k = sub_ptr[e]; k < sub_ptr[e + 1]; ++k) {
                 uint32_t off = sub_payload[k] >> 4;
@@ -202,6 +213,9 @@ int gcp_upload_masked_footprints(gcp_ctx* c, const uint32_t* sub_ptr, const uint
         c->t.m_q_info = nullptr; c->t.m_q_desc = nullptr;
         if (ok) {
             if ((r = upload(c, &c->t.m_q_info, qinfo.data(), EN))) return r;
+            qdesc.push_back(make_uint2(0u, 0u));                             // pair reads may touch one item past a list
+            qdesc.push_back(make_uint2(0u, 0u));
+            qdesc.push_back(make_uint2(0u, 0u));
             if ((r = upload(c, &c->t.m_q_desc, qdesc.data(), qdesc.size()))) return r;
         }
     }

@@ -19,6 +19,7 @@ struct GcpTables {
     // edges (mappy.py:274-328): ids [0,E) real, [E,E+N) null edge of node id-E
     const double2*  edge_cost; // {dist, turn}
     const double*   edge_theta;
+    const uint4*    adjc16;    // [N] 8 x u16 out-neighbour ids (0xFFFF = empty); NULL if N > 65535 or degree > 8
     const uint2*    adj8;      // [N][8] {col, float bits of theta}, col = ~0 for empty; NULL if max degree > 8
     const uint32_t* sub_info;  // [E+N] first sub-tile (28 bits) | count << 28
     const uint2*    sub_desc;  // [S] {block id, (offset128<<4)|qmask}

@@ -69,10 +69,15 @@ __device__ __forceinline__ void coverage_quarters(const uint32_t* info, int AL, 
                         lo = inf & 0x03FFFFFFu;
                         n = inf >> 26;
                     }
-                    uint2 d[4];                 // {block<<2 | q, uint4 index}: one L2 round trip
-                    #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        d[k] = (k < (int)n) ? __ldg(t.m_q_desc + lo + k) : make_uint2(0, 0);
+                    uint2 d[4];                 // {block<<2 | q, uint4 index}; lists are 16-B aligned: two pair loads
+                    {
+                        const uint4* dp = reinterpret_cast<const uint4*>(t.m_q_desc + lo);
+                        uint4 p0 = make_uint4(0, 0, 0, 0), p1 = p0;
+                        if (n > 0) p0 = __ldg(dp);
+                        if (n > 2) p1 = __ldg(dp + 1);
+                        d[0] = make_uint2(p0.x, p0.y); d[1] = make_uint2(p0.z, p0.w);
+                        d[2] = make_uint2(p1.x, p1.y); d[3] = make_uint2(p1.z, p1.w);
+                    }
                     uint32_t mine = n;
                     if (R > 1) {
                         mine = 0;
@@ -351,7 +356,16 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
                     const uint32_t lo = __ldg(t.row_ptr + w);
                     e = t.E + w;                             // null edge unless found (F4)
                     bool found = false;
-                    if (t.adj8) {
+                    if (t.adjc16) {                          // 8 x u16 columns in one 16-B load
+                        const uint4 q = __ldg(t.adjc16 + w);
+                        const uint32_t pat = (uint32_t)nx * 0x00010001u;
+                        const uint32_t m0 = __vcmpeq2(q.x, pat), m1 = __vcmpeq2(q.y, pat);
+                        const uint32_t m2 = __vcmpeq2(q.z, pat), m3 = __vcmpeq2(q.w, pat);
+                        // one bit per 16-bit lane, in slot order
+                        const uint32_t hit = ((m0 & 1u) | ((m0 >> 15) & 2u)) | (((m1 & 1u) | ((m1 >> 15) & 2u)) << 2) |
+                                             (((m2 & 1u) | ((m2 >> 15) & 2u)) << 4) | (((m3 & 1u) | ((m3 >> 15) & 2u)) << 6);
+                        if (hit) { e = lo + (uint32_t)(__ffs(hit) - 1); found = true; }
+                    } else if (t.adj8) {
                         const uint4* rec = reinterpret_cast<const uint4*>(t.adj8 + (size_t)w * 8);
                         #pragma unroll
                         for (int h = 0; h < 4; ++h) {
