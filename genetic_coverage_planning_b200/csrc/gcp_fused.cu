@@ -250,7 +250,7 @@ struct StaticShape {
     static constexpr uint32_t R0 = (size_t)MAXP >= (size_t)SAL * 2 ? 1u : 0u;      // 0: not representable -> runtime shape
     static constexpr uint32_t off_cst = (uint32_t)T * 20;
     static constexpr uint32_t cov_b = (uint32_t)T * 20 + (uint32_t)MAXP * 8 + 32;
-    static constexpr uint32_t a_b = off_cst + (uint32_t)SAL * 16;
+    static constexpr uint32_t a_b = off_cst + (uint32_t)SAL * 16 + GCP_MAX_AGENTS * 16;
     static constexpr uint32_t lc_b = c_al16((uint32_t)T3 * 12 + (uint32_t)SAL) + (uint32_t)SAL * 4;
     static constexpr uint32_t x_b = cov_b > lc_b ? (cov_b > a_b ? cov_b : a_b) : (lc_b > a_b ? lc_b : a_b);
     static constexpr uint32_t off_info = c_al16((uint32_t)SAL * 4);
@@ -383,7 +383,7 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
                     cst = __ldg(t.edge_cost + e);
                 }
             }
-            s_cst[s] = cst;
+            s_cst[s + a] = cst;                                   // row stride L + 1: see phase A2
             s_info[s] = info;
         }
         if (bad) atomicOr(&s_bad, bad);
@@ -401,7 +401,9 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     if (warp == 0 && lane < A) {
         // phase A2: sequential fp64 adds in step order per agent (mappy.py:351-352),
         // bit-identical to the reference's `+=`; the per-step costs were staged by A1
-        const double2* ca = s_cst + lane * L;
+        // rows are L + 1 entries apart: with a stride of L * 16 B (a multiple of 128 B for L = 200)
+        // the A lanes would all hit the same banks
+        const double2* ca = s_cst + lane * (L + 1);
         const int nsteps = min(s_first_neg[lane], L - 1);
         double acc_d = 0.0, acc_t = 0.0;
         int i = 0;
@@ -653,7 +655,7 @@ static size_t fused_shape(gcp_ctx* ctx, FusedShape& sh, int KF_THREADS)
     while ((size_t)sh.R0 * maxp < (size_t)sh.AL * 2 && sh.R0 < 4096) sh.R0 <<= 1;
     sh.off_cst = (uint32_t)T * 20;                                    // over s_pay / s_sr
     const uint32_t cov_b = (uint32_t)T * 20 + (uint32_t)maxp * 8 + 32;  // + pad for B2's read-ahead
-    const uint32_t a_b = sh.off_cst + (uint32_t)sh.AL * 16;
+    const uint32_t a_b = sh.off_cst + (uint32_t)sh.AL * 16 + GCP_MAX_AGENTS * 16;    // + one pad entry per row
     const uint32_t lc_b = al16((uint32_t)sh.T3 * 12 + (uint32_t)sh.AL) + (uint32_t)sh.AL * 4;
     uint32_t x_b = cov_b > lc_b ? cov_b : lc_b;
     if (a_b > x_b) x_b = a_b;
