@@ -347,6 +347,33 @@ def test_many_agents_long_rows(synth_setup):
         assert np.array_equal(det['lc_mat'].astype(np.int32), r.lc_mat.cpu().numpy()[k])
 
 
+def test_maximum_genome(synth_setup):
+    """The largest chromosome the ABI accepts (32 agents x 2,047 genes = 65,504 <= 65,535):
+    staged kernels, many hash partitions, bit-exact against the oracle."""
+    from genetic_coverage_planning_b200 import synth, worlds
+    from genetic_coverage_planning_b200.engine import FitnessEngine
+    sw, pw, ow, op, eng, starts = synth_setup
+    A, L = 32, 2047
+    st = synth.spread_starts(sw.xy, A, 1024)
+    op2 = worlds.org_params_for(dict(L=L), st)
+    eng2 = FitnessEngine(pw, op2, num_agents=A)
+    dna = synth.random_walk_population(sw.xy, sw.row_ptr, sw.col, st, 2, 1990, L, seed=13).astype(np.int32)
+    dna[1, 5, 100:] = -1                                         # ragged
+    dna[1, 9, :] = -1                                            # an empty row
+    r = eng2.evaluate(dna, detail=True, pixel_counts=False)
+    assert not r.flags.cpu().numpy()[:, 3].any()
+    ow2 = World(sw.img, sw.xy, sw.row_ptr, sw.col, sw.edge_poly, sw.edge_theta, sw.edge_dist,
+                sw.map_params, op2, name="synth-32x2047")
+    for k in range(2):
+        det = fo.calc_obj(ow2, dna[k].astype(int), detail=True)
+        assert det['obj'][0] == r.obj.cpu().numpy()[k, 0]
+        assert det['obj'][1] == r.obj.cpu().numpy()[k, 1]
+        assert np.array_equal(det['lc_mat'].astype(np.int32), r.lc_mat.cpu().numpy()[k])
+        assert det['n_components'] == r.flags.cpu().numpy()[k, 2]
+    with pytest.raises(Exception):                               # one gene more is refused, not truncated
+        FitnessEngine(pw, worlds.org_params_for(dict(L=2048), st), num_agents=A)
+
+
 def test_int16_genes_equal_int32(synth_setup):
     """gcp_eval16 / gcp_eval_host16 (half-width chromosomes) give the int32 results bit for bit."""
     import torch
