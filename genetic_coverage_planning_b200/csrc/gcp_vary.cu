@@ -508,40 +508,78 @@ k_crossover(const int32_t* __restrict__ parents, const int32_t* __restrict__ str
 // chains per warp, nothing replicated across lanes, no thread walks twice.
 constexpr int MW_THREADS = 64;
 
-// which = 0: organisms whose mutation coin came up (:159-161); 1: muterpolate coin (:163-165)
-__global__ void k_mutation_list(uint32_t P, VaryParams vp, uint64_t seed, uint32_t gen, uint32_t salt,
-                                int which, uint32_t* __restrict__ counter, uint32_t* __restrict__ list)
+// first -1 of a row that is a valid prefix followed by -1 padding, by bisection
+__device__ __forceinline__ int row_len(const int32_t* r, int L)
+{
+    int lo = 0, hi = L;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (r[mid] == -1) hi = mid; else lo = mid + 1; }
+    return lo;
+}
+
+// the cut and the tail length of a mutating row (:252-258), from the row's own Philox stream
+__device__ __forceinline__ bool mutation_cut(const int32_t* r, const VaryParams& vp, Philox& rng, int* len_out,
+                                             int* idx_out, int* tail_out)
+{
+    const int L = vp.L;
+    const int len = row_len(r, L);
+    *len_out = len;
+    if (len < 3) return false;
+    const int idx = 1 + rng.randint(len - 2);                          // randint(1, len-1)
+    int len_tail = len - idx;
+    if (len + 1 < L) len_tail += rng.randint(L - len);                 // :256-258
+    *idx_out = idx; *tail_out = len_tail;
+    return true;
+}
+
+constexpr int MW_CLASSES = 4;       // walking rows are bucketed by tail length: a warp's 32 walks end together
+
+// which = 0: rows of the organisms whose mutation coin came up (:159-161), bucketed by walk length
+// into MW_CLASSES lists (list + c * n_rows, counter[c]); 1: muterpolate coin (:163-165), one list.
+__global__ void k_mutation_list(const int32_t* __restrict__ dna, uint32_t P, VaryParams vp, uint64_t seed,
+                                uint32_t gen, uint32_t salt, int which, uint32_t* __restrict__ counter,
+                                uint32_t* __restrict__ list)
 {
     const uint32_t org = blockIdx.x * blockDim.x + threadIdx.x;
     if (org >= P) return;
     Philox org_rng(seed, gen, stream_id(STREAM_ORG, salt), org + vp.org_off);
     const float u0 = org_rng.uniform(), u1 = org_rng.uniform();
-    if (which == 0 ? (u0 < vp.mut_prob) : (u1 < vp.muterp_prob)) {
-        const uint32_t base = atomicAdd(counter, (uint32_t)vp.A);
-        for (int a = 0; a < vp.A; ++a) list[base + a] = org * vp.A + a;
+    if (which == 1) {
+        if (u1 < vp.muterp_prob) {
+            const uint32_t base = atomicAdd(counter, (uint32_t)vp.A);
+            for (int a = 0; a < vp.A; ++a) list[base + a] = org * vp.A + a;
+        }
+        return;
+    }
+    if (!(u0 < vp.mut_prob)) return;
+    const uint32_t n_rows = P * (uint32_t)vp.A;
+    for (int a = 0; a < vp.A; ++a) {
+        const uint32_t gid = org * vp.A + a;
+        Philox rng(seed, gen, stream_id(STREAM_MUT, salt), gid + vp.org_off * vp.A);
+        int len, idx, tail;
+        if (!mutation_cut(dna + (size_t)gid * vp.L, vp, rng, &len, &idx, &tail)) continue;
+        const int c = min(MW_CLASSES - 1, (tail * MW_CLASSES) / vp.L);
+        list[(size_t)c * n_rows + atomicAdd(&counter[c], 1u)] = gid;
     }
 }
 
 __global__ void __launch_bounds__(MW_THREADS)
-k_mutation_walks(int32_t* __restrict__ dna, GcpTables t, VaryParams vp, uint64_t seed, uint32_t gen,
-                 uint32_t salt, const uint32_t* __restrict__ counter, const uint32_t* __restrict__ list)
+k_mutation_walks(int32_t* __restrict__ dna, uint32_t n_rows, GcpTables t, VaryParams vp, uint64_t seed,
+                 uint32_t gen, uint32_t salt, const uint32_t* __restrict__ counter,
+                 const uint32_t* __restrict__ list)
 {
-    const uint32_t j = blockIdx.x * MW_THREADS + threadIdx.x;
-    if (j >= *counter) return;
-    const int L = vp.L;
-    const uint32_t gid = list[j];
-    int32_t* r = dna + (size_t)gid * L;
-    int len;
-    {   // rows are a valid prefix followed by -1 padding: first -1 by bisection
-        int lo = 0, hi = L;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (r[mid] == -1) hi = mid; else lo = mid + 1; }
-        len = lo;
+    uint32_t j = blockIdx.x * MW_THREADS + threadIdx.x;
+    int c = 0;
+    for (; c < MW_CLASSES; ++c) {                                     // longest walks first would also do
+        const uint32_t nc = counter[c];
+        if (j < nc) break;
+        j -= nc;
     }
-    if (len < 3) return;
+    if (c == MW_CLASSES) return;
+    const uint32_t gid = list[(size_t)c * n_rows + j];
+    int32_t* r = dna + (size_t)gid * vp.L;
     Philox rng(seed, gen, stream_id(STREAM_MUT, salt), gid + vp.org_off * vp.A);
-    const int idx = 1 + rng.randint(len - 2);                          // randint(1, len-1)
-    int len_tail = len - idx;
-    if (len + 1 < L) len_tail += rng.randint(L - len);                 // :256-258
+    int len, idx, len_tail;
+    if (!mutation_cut(r, vp, rng, &len, &idx, &len_tail)) return;
     const int last = t_walk(t, vp, r, idx, len_tail, 0, rng);
     for (int x = last + 1; x < len; ++x) r[x] = -1;                    // addTelomere
 }
@@ -774,7 +812,7 @@ int launch_mutate(gcp_ctx* c, int32_t* dna, uint32_t P, uint64_t seed, uint32_t 
     const VaryParams vp = make_vp(c);
     const uint32_t n_rows = P * (uint32_t)vp.A;
     if (vp.mut_prob > 0.f || vp.muterp_prob > 0.f) {
-        const size_t need = 512 + (size_t)n_rows * 4;
+        const size_t need = 512 + (size_t)n_rows * 4 * MW_CLASSES;
         if (c->vary_scratch_bytes < need) {
             if (c->vary_scratch) cudaFree(c->vary_scratch);
             c->vary_scratch = nullptr; c->vary_scratch_bytes = 0;
@@ -786,14 +824,14 @@ int launch_mutate(gcp_ctx* c, int32_t* dna, uint32_t P, uint64_t seed, uint32_t 
     uint32_t* list = counter + 128;
     const uint32_t row_grid = (n_rows + MW_THREADS - 1) / MW_THREADS;
     if (vp.mut_prob > 0.f) {                       // mutation (:159-161): tail regrowth walks
-        GCP_CUDA(c, cudaMemsetAsync(counter, 0, 4, st));
-        k_mutation_list<<<(P + 255) / 256, 256, 0, st>>>(P, vp, seed, gen, salt, 0, counter, list);
-        k_mutation_walks<<<row_grid, MW_THREADS, 0, st>>>(dna, c->t, vp, seed, gen, salt, counter, list);
+        GCP_CUDA(c, cudaMemsetAsync(counter, 0, 4 * MW_CLASSES, st));
+        k_mutation_list<<<(P + 255) / 256, 256, 0, st>>>(dna, P, vp, seed, gen, salt, 0, counter, list);
+        k_mutation_walks<<<row_grid, MW_THREADS, 0, st>>>(dna, n_rows, c->t, vp, seed, gen, salt, counter, list);
         c->launches += 2;
     }
     if (vp.muterp_prob > 0.f && vp.num_muterp > 0) {   // muterpolate (:163-165)
         GCP_CUDA(c, cudaMemsetAsync(counter + 64, 0, 4, st));
-        k_mutation_list<<<(P + 255) / 256, 256, 0, st>>>(P, vp, seed, gen, salt, 1, counter + 64, list);
+        k_mutation_list<<<(P + 255) / 256, 256, 0, st>>>(dna, P, vp, seed, gen, salt, 1, counter + 64, list);
         k_muterpolate_rows<<<row_grid, MW_THREADS, 0, st>>>(dna, c->t, vp, seed, gen, salt, counter + 64, list);
         c->launches += 2;
     }
