@@ -391,8 +391,10 @@ __global__ void k_lv_search(const double* __restrict__ cum, uint32_t M, double r
 
 // ------------------------------------------------------------------ crossover (+ fused mutation)
 // One warp per (pair k, agent a): parents strong[k] ("self") and strong[k + P/2] ("mate")
-// -> children 2k, 2k+1.  Rows live in shared memory: pm | pd | c1 | c2.
+// -> children 2k, 2k+1.  Rows live in shared memory: pm | pd | c1 | c2 | match-index heads.
 constexpr int VARY_WARPS = 4;
+constexpr int XO_BUCKETS = 256;
+__device__ __forceinline__ int xo_bucket(int gene) { return (int)(((uint32_t)gene * 2654435761u) >> 24); }
 
 __device__ __forceinline__ size_t vary_row_stride(int L) { return (size_t)((L + 31) & ~31); }
 
@@ -409,10 +411,11 @@ k_crossover(const int32_t* __restrict__ parents, const int32_t* __restrict__ str
     const uint32_t k = gid / vp.A, a = gid % vp.A;
     const int L = vp.L;
     const size_t RS = vary_row_stride(L);
-    int32_t* pm = s_rows + (size_t)warp * (4 * RS);
+    int32_t* pm = s_rows + (size_t)warp * (4 * RS + XO_BUCKETS);
     int32_t* pd = pm + RS;
     int32_t* c1 = pd + RS;
     int32_t* c2 = c1 + RS;
+    int32_t* s_head = c2 + RS;                                         // [XO_BUCKETS] chain heads of the match index
     const int32_t* gm = parents + ((size_t)strong[k] * vp.A + a) * L;
     const int32_t* gd = parents + ((size_t)strong[k + half] * vp.A + a) * L;
     for (int x = lane; x < L; x += 32) { pm[x] = gm[x]; pd[x] = gd[x]; }
@@ -424,17 +427,24 @@ k_crossover(const int32_t* __restrict__ parents, const int32_t* __restrict__ str
     if (want) {
         // matchWaypt :311-333: i, j >= 1, equal waypoint that is a crossover candidate,
         // |i - j| < time_thresh; candidates enumerated row-major like np.where.
-        // cnt[i] -> c1 (scratch until the children are built)
+        // The mate's positions j >= 1 are indexed by waypoint in 256 hash buckets (heads in
+        // s_head, chains in c2), so counting the matches of self[i] walks one short chain
+        // instead of scanning the whole time window.  cnt[i] -> c1 (scratch until the children
+        // are built).
+        for (int x = lane; x < XO_BUCKETS; x += 32) s_head[x] = 0;
+        __syncwarp();
+        for (int j = 1 + lane; j < ld; j += 32)
+            c2[j] = atomicExch(&s_head[xo_bucket(pd[j])], j);          // 0 terminates: j >= 1
+        __syncwarp();
         int total = 0;
         for (int i0 = 1; i0 < lm; i0 += 32) {
             const int i = i0 + lane;
             int cnt = 0;
             if (i < lm) {
                 const int w = pm[i];
-                if (__ldg(t.xover + w)) {
-                    const int j0 = max(1, i - vp.time_thresh + 1), j1 = min(ld - 1, i + vp.time_thresh - 1);
-                    for (int j = j0; j <= j1; ++j) cnt += (pd[j] == w);
-                }
+                if (__ldg(t.xover + w))
+                    for (int p = s_head[xo_bucket(w)]; p; p = c2[p])
+                        cnt += (pd[p] == w && abs(i - p) < vp.time_thresh);
                 c1[i] = cnt;
             }
             total += cnt;
@@ -458,11 +468,16 @@ k_crossover(const int32_t* __restrict__ parents, const int32_t* __restrict__ str
                     const int src = __ffs(m) - 1;
                     int jj = -1;
                     if (lane == src) {
-                        int rem = pick - (inc - cnt);
+                        const int rem = pick - (inc - cnt);                // rem-th match in ascending j
                         const int w = pm[i];
-                        const int j0 = max(1, i - vp.time_thresh + 1), j1 = min(ld - 1, i + vp.time_thresh - 1);
-                        for (int j = j0; j <= j1; ++j)
-                            if (pd[j] == w) { if (rem == 0) { jj = j; break; } --rem; }
+                        const int b = xo_bucket(w);
+                        for (int p = s_head[b]; p && jj < 0; p = c2[p]) {
+                            if (!(pd[p] == w && abs(i - p) < vp.time_thresh)) continue;
+                            int below = 0;
+                            for (int q = s_head[b]; q; q = c2[q])
+                                below += (q < p && pd[q] == w && abs(i - q) < vp.time_thresh);
+                            if (below == rem) jj = p;
+                        }
                     }
                     sel_i = i0 + src;
                     sel_j = __shfl_sync(FULL, jj, src);
@@ -847,7 +862,7 @@ int launch_crossover(gcp_ctx* c, const int32_t* parents, const int32_t* strong, 
 {
     if (P < 2) return 0;
     if (P & 1) return gcp_fail(c, -1, "population size must be even (pather_driver.py:107)");
-    size_t smem; int r = vary_smem(c, 4, 0, &smem); if (r) return r;
+    size_t smem; int r = vary_smem(c, 4, XO_BUCKETS, &smem); if (r) return r;
     GCP_CUDA(c, cudaFuncSetAttribute(k_crossover, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     StageTimer tm(c, 6, st);
     const uint32_t n = (P / 2) * c->p.num_agents;
