@@ -69,6 +69,62 @@ __device__ __forceinline__ void coverage_quarters(const uint32_t* info, int AL, 
                         lo = inf & 0x03FFFFFFu;
                         n = inf >> 26;
                     }
+                    if (R == 1) {
+                        // Flattened: the warp's 32 steps hold `total` items; lane j of round j0 takes
+                        // item j0 + j (its step is found by bisection over the lanes' prefix sums), so
+                        // every lane is busy whatever the spread of items per step.
+                        uint32_t incl = n;
+                        #pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            uint32_t v = __shfl_up_sync(FULL, incl, o);
+                            if (lane >= o) incl += v;
+                        }
+                        const uint32_t total = __shfl_sync(FULL, incl, 31);
+                        if (total == 0) continue;
+                        uint32_t base = 0;
+                        if (lane == 0) base = atomicAdd(&s_npairs, total);
+                        base = __shfl_sync(FULL, base, 0);
+                        if (base + total > (uint32_t)MAXP) {
+                            if (lane == 0) s_overflow = 1;
+                            continue;
+                        }
+                        const uint32_t excl = incl - n;
+                        for (uint32_t j0 = 0; j0 < total; j0 += 32) {
+                            const uint32_t j = j0 + lane;
+                            int a = 0, b = 31;                        // smallest lane with incl > j
+                            #pragma unroll
+                            for (int it = 0; it < 5; ++it) {
+                                const int mid = (a + b) >> 1;
+                                const uint32_t v = __shfl_sync(FULL, incl, mid);
+                                if (v > j) b = mid; else a = mid + 1;
+                            }
+                            a = min(a, 31);
+                            const uint32_t ex = __shfl_sync(FULL, excl, a), dlo = __shfl_sync(FULL, lo, a);
+                            if (j < total) {
+                                const uint2 dsc = __ldg(t.m_q_desc + dlo + (j - ex));
+                                const uint32_t blk = dsc.x >> 2, q = dsc.x & 3u;
+                                const uint32_t key = blk + 1;
+                                uint32_t h = hash_block(blk) >> (32 - logT);
+                                int probes = 0;
+                                for (;;) {
+                                    const uint32_t cur = ((volatile uint32_t*)s_keys)[h];
+                                    if (cur == key) break;
+                                    if (cur == 0) {
+                                        const uint32_t old = atomicCAS(&s_keys[h], 0u, key);
+                                        if (old == 0 || old == key) break;
+                                    }
+                                    h = (h + 1) & (T - 1);
+                                    if (++probes >= T) { s_overflow = 1; break; }
+                                }
+                                if (probes < T) {
+                                    const uint32_t rank = atomicAdd(&s_cq[4 * h + q], 1u);
+                                    s_pay[base + j] = dsc.y;
+                                    s_sr[base + j] = (h << 18) | (q << 16) | rank;
+                                }
+                            }
+                        }
+                        continue;
+                    }
                     uint2 d[4];                 // {block<<2 | q, uint4 index}; lists are 16-B aligned: two pair loads
                     {
                         const uint4* dp = reinterpret_cast<const uint4*>(t.m_q_desc + lo);
