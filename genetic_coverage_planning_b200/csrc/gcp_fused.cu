@@ -222,8 +222,9 @@ __device__ __forceinline__ void coverage_quarters(const uint32_t* info, int AL, 
                 pos[k] = KF_NIL;
                 if (i < npairs) {
                     const uint32_t sr = s_sr[i];
-                    pos[k] = (s_cq[sr >> 16] & 0xFFFFu) + (sr & 0xFFFFu);
-                    ent[k] = s_pay[i];
+                    const uint32_t cb = s_cq[sr >> 16], rank = sr & 0xFFFFu;
+                    pos[k] = (cb & 0xFFFFu) + rank;
+                    ent[k] = s_pay[i] | ((rank + 1u == (cb >> 16)) ? 0x80000000u : 0u);   // last of its list
                 }
             }
             __syncthreads();
@@ -231,11 +232,57 @@ __device__ __forceinline__ void coverage_quarters(const uint32_t* info, int AL, 
             for (int k = 0; k < KF_PPT; ++k)
                 if (pos[k] != KF_NIL) s_pay[pos[k]] = ent[k];
             __syncthreads();
-            // ---- B2: owner warps, groups of 32 slots handed out dynamically ----
+            // ---- B2 (gray maps): owner warps, groups of 32 slots handed out dynamically ----
             // per-lane tile base kept in registers: the opaque asm stops ptxas from re-deriving
             // it (S2R tid + LDC of the table pointer) in front of every load
             const uint4* tile_l = t.m_tile + l7;
             asm volatile("" : "+l"(tile_l));
+            if (!HAS_GRAY) {
+                // ---- B2 (flat): the sorted array is cut into KF_NW * 4 contiguous ranges snapped to
+                //      list boundaries; every 8-lane group streams its own range (lane = one uint4 =
+                //      2 rows of the quarter), ORs into registers and popcounts at each list end.
+                //      All groups stay busy whatever the spread of list lengths.
+                constexpr uint32_t NG = KF_NW * 4;
+                const uint32_t gid = (uint32_t)warp * 4u + myq;
+                const uint32_t gbit = 0xFFu << (myq * 8);
+                uint32_t bnd[2];
+                #pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const uint32_t w = gid + e;
+                    uint32_t c = (uint32_t)(((uint64_t)npairs * w) / NG);
+                    bool done = (w == 0) || (w >= NG);
+                    if (w >= NG) c = npairs;
+                    while (__any_sync(FULL, !done)) {               // first position >= c that starts a list
+                        const uint32_t pp = c + l7;
+                        const bool is_start = (pp >= npairs) || (pp == 0) || (s_pay[pp - 1] >> 31);
+                        const uint32_t m = __ballot_sync(FULL, is_start) & gbit;
+                        if (!done) {
+                            if (m) { c += (uint32_t)(__ffs(m) - 1) - myq * 8u; done = true; }
+                            else c += 8;
+                        }
+                    }
+                    bnd[e] = min(c, npairs);
+                }
+                const uint32_t len = bnd[1] - bnd[0];
+                const uint32_t steps = __reduce_max_sync(FULL, len);
+                const uint32_t* pb = s_pay + bnd[0];
+                uint4 acc = make_uint4(0, 0, 0, 0);
+                for (uint32_t k = 0; k < steps; k += 4) {
+                    uint32_t e[4];
+                    uint4 v[4];
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        e[j] = (k + j < len) ? pb[k + j] : 0u;
+                        v[j] = make_uint4(0, 0, 0, 0);
+                        if (k + j < len) v[j] = __ldg(tile_l + (e[j] & 0x7FFFFFFFu));
+                    }
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc.x |= v[j].x; acc.y |= v[j].y; acc.z |= v[j].z; acc.w |= v[j].w;
+                        if (e[j] >> 31) { n_cov += popc128(acc); acc = make_uint4(0, 0, 0, 0); }
+                    }
+                }
+            } else
             for (;;) {
                 uint32_t g = 0;
                 if (lane == 0) g = atomicAdd(&s_group, 1u);
@@ -251,7 +298,8 @@ __device__ __forceinline__ void coverage_quarters(const uint32_t* info, int AL, 
                     uint4 acc = make_uint4(0, 0, 0, 0);
                     for (uint32_t k = 0; k < maxc; k += 4) {
                         // reading past cnt only fetches a neighbour's entry (s_pay is padded)
-                        const uint32_t i0 = pb[k], i1 = pb[k + 1], i2 = pb[k + 2], i3 = pb[k + 3];
+                        const uint32_t i0 = pb[k] & 0x7FFFFFFFu, i1 = pb[k + 1] & 0x7FFFFFFFu, i2 = pb[k + 2] & 0x7FFFFFFFu,
+                                       i3 = pb[k + 3] & 0x7FFFFFFFu;
                         uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0, v3 = v0;
                         if (k < cnt) v0 = __ldg(tile_l + i0);
                         if (k + 1 < cnt) v1 = __ldg(tile_l + i1);
