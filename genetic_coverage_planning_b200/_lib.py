@@ -34,6 +34,13 @@ class GcpMapConsts(C.Structure):
                 ("map_size", C.c_int64), ("num_occluded", C.c_double)]
 
 
+class GcpFrustumParams(C.Structure):
+    _fields_ = [("num_rays", C.c_int32), ("window", C.c_int32), ("scale", C.c_double),
+                ("max_view", C.c_double), ("max_view_px", C.c_double), ("half_view", C.c_double),
+                ("near_last", C.c_double * 2), ("near_first", C.c_double * 2),
+                ("eps_angle", C.c_double), ("eps_round", C.c_double)]
+
+
 class GcpEvalOut(C.Structure):
     _fields_ = [("obj", C.c_void_p), ("neg_cov", C.c_void_p), ("dist", C.c_void_p),
                 ("turn", C.c_void_p), ("cov", C.c_void_p), ("lc_mat", C.c_void_p),
@@ -78,6 +85,8 @@ SIGNATURES = {
     "gcp_launch_count": (C.c_uint64, [_vp]),
     "gcp_set_timing": (C.c_int, [_vp, C.c_int]),
     "gcp_stage_ms": (C.c_float, [_vp, C.c_int]),
+    "gcp_compute_frustums": (C.c_int, [C.c_int, _vp, _u32, _u32, _vp, _vp, _vp, _u32, _u32, _vp,
+                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

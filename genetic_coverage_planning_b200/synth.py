@@ -142,10 +142,11 @@ def _rot2d(theta):
     return np.array([[np.cos(theta), -np.sin(theta)], [np.sin(theta), np.cos(theta)]])
 
 
-def compute_frustums(img, xy, row_ptr, col, map_params, progress=False):
+def compute_frustums(img, xy, row_ptr, col, map_params, progress=False, only_nodes=None):
     """Windowed restatement of Mappy.computeFrustums (mappy.py:274-328) in CSR form.
     img: float64 map as the reference holds it (g/255).  Returns (poly int32 [E,R+2,2],
-    theta [E], dist [E])."""
+    theta [E], dist [E]).  only_nodes: fill only the out-edges of these source waypoints
+    (frustums.py recomputes the edges its device kernel flags as ambiguous this way)."""
     scale = map_params['scale']
     num_rays = int(map_params['num_rays'])
     min_view = map_params['min_view']
@@ -161,7 +162,7 @@ def compute_frustums(img, xy, row_ptr, col, map_params, progress=False):
     H, W = img.shape
     R = int(np.ceil(max_view / scale)) + 1
     nz = img != 0
-    it = range(N)
+    it = range(N) if only_nodes is None else [int(v) for v in only_nodes]
     if progress:
         from tqdm import tqdm
         it = tqdm(it, desc="frustums")
@@ -278,7 +279,9 @@ class SynthWorld(object):
 
 
 def make_world(size=4096, seed=0, map_params=None, path_params=None, stride=None,
-               progress=False):
+               progress=False, frustums="host"):
+    """frustums: "host" = the windowed numpy restatement below, "device" = the CUDA kernel
+    (frustums.compute_frustums_device; bit-identical, tests/test_gpu_frustums.py)."""
     mp = dict(DEFAULT_MAP_PARAMS if map_params is None else map_params)
     pp = dict(DEFAULT_PATH_PARAMS if path_params is None else path_params)
     w = SynthWorld()
@@ -286,8 +289,13 @@ def make_world(size=4096, seed=0, map_params=None, path_params=None, stride=None
     w.img = u8.astype(np.float64)          # binary: g in {0,255} -> g/255 in {0,1}
     w.xy = place_waypoints(u8, mp, stride)
     w.row_ptr, w.col = build_graph(u8, w.xy, mp, pp)
-    w.edge_poly, w.edge_theta, w.edge_dist = compute_frustums(w.img, w.xy, w.row_ptr, w.col, mp,
-                                                              progress)
+    if frustums == "device":
+        from . import frustums as _fr
+        w.edge_poly, w.edge_theta, w.edge_dist, w.frustum_info = _fr.compute_frustums_device(
+            w.img, w.xy, w.row_ptr, w.col, mp, return_info=True)
+    else:
+        w.edge_poly, w.edge_theta, w.edge_dist = compute_frustums(w.img, w.xy, w.row_ptr, w.col, mp,
+                                                                  progress)
     w.map_params, w.path_params = mp, pp
     w.N, w.E = len(w.xy), len(w.col)
     return w

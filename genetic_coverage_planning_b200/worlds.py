@@ -42,19 +42,23 @@ def build_synth_world(size, seed=0, use_cache=True, verbose=False):
     h = hashlib.sha1()
     for mod in (synth, packing):
         h.update(open(mod.__file__.replace(".pyc", ".py"), "rb").read())
-    path = os.path.join(cache_dir(), "world_%d_%d_%s.pkl" % (size, seed, h.hexdigest()[:10]))
+    import torch
+    mode = "device" if torch.cuda.is_available() else "host"     # footprint polygons: CUDA kernel when there is a GPU
+    path = os.path.join(cache_dir(), "world_%d_%d_%s_%s.pkl" % (size, seed, h.hexdigest()[:10], mode))
     if use_cache and os.path.exists(path):
         with open(path, "rb") as f:
             return pickle.load(f)
     t0 = time.time()
-    w = synth.make_world(size, seed)
+    w = synth.make_world(size, seed, frustums=mode)
     t1 = time.time()
     pw = packing.pack_world(w.img, w.xy, w.row_ptr, w.col, w.edge_poly, w.edge_theta,
                             w.edge_dist, w.map_params)
     if verbose:
         import sys
-        print("[worlds] size %d: N=%d E=%d world %.1fs pack %.1fs" %
-              (size, w.N, w.E, t1 - t0, time.time() - t1), file=sys.stderr, flush=True)
+        print("[worlds] size %d: N=%d E=%d world %.1fs (%s frustums%s) pack %.1fs" %
+              (size, w.N, w.E, t1 - t0, mode,
+               ", kernel %.1f ms, %d ambiguous" % (w.frustum_info["kernel_ms"], w.frustum_info["ambiguous_edges"])
+               if mode == "device" else "", time.time() - t1), file=sys.stderr, flush=True)
     if use_cache:
         tmp = path + ".%d.tmp" % os.getpid()
         with open(tmp, "wb") as f:

@@ -234,6 +234,41 @@ int gcp_set_timing(gcp_ctx* ctx, int enabled);
  * Synchronises on the stage's end event. Returns milliseconds, <0 if not recorded. */
 float gcp_stage_ms(gcp_ctx* ctx, int stage);
 
+/* ---- setup path: footprint polygons ------------------------------------
+ * Replaces Mappy.computeFrustums (mappy.py:274-328): the (num_rays + 2)-point footprint polygon
+ * of every directed edge, from the obstacle pixels within max_view of the source waypoint.
+ * Needs no context (it runs before any table exists); errors are read with gcp_last_error(NULL).
+ * All pointers are HOST pointers; the call is synchronous.
+ *   occ[H][W]            != 0 where Mappy._img != 0 (mappy.py:278)
+ *   xy[N][2]             waypoint (row, col) = Mappy._all_waypoints
+ *   row_ptr[N+1], col[E] CSR of the traversability graph (graph[from, to] == 1)
+ *   ray_angles[R]        np.arange(R) * (view_angle / R) - view_angle / 2          (:279-280)
+ *   ray_sin/ray_cos[R]   np.sin / np.cos of ray_angles                             (:314)
+ *   edge_theta[E]        np.arctan2(d_col, d_row) of the edge                      (:286)
+ *   edge_cos/edge_sin[E] np.cos / np.sin of edge_theta (got.getRot2D, gori_tools.py:184-186)
+ *   poly[E][R+2][2]      out: np.around(Rot.dot(pts)).astype(int32).T              (:320)
+ *   ambiguous[E]         out: 1 where a floating-point decision fell within eps of a boundary
+ *                        (bearing vs ray boundary / field of view, coordinate vs x.5): the
+ *                        caller recomputes those edges with the reference's own expressions
+ *   kernel_ms            out (optional): device time of the kernel                          */
+typedef struct gcp_frustum_params {
+    int32_t num_rays;         /* R <= 62 */
+    int32_t window;           /* half-size in px of the obstacle window: ceil(max_view / scale) + 1 */
+    double  scale;            /* m per px */
+    double  max_view;         /* m */
+    double  max_view_px;      /* max_view / scale */
+    double  half_view;        /* view_angle / 2 (< pi) */
+    double  near_last[2];     /* {sin(ray_angles[R-1]) * min_view, cos(ray_angles[R-1]) * min_view}  (:315-316) */
+    double  near_first[2];    /* {sin(ray_angles[0]) * min_view, cos(ray_angles[0]) * min_view}      (:317-318) */
+    double  eps_angle;        /* e.g. 1e-11 rad */
+    double  eps_round;        /* e.g. 1e-9 px */
+} gcp_frustum_params;
+int gcp_compute_frustums(int device, const uint8_t* occ, uint32_t H, uint32_t W, const int32_t* xy,
+                         const uint32_t* row_ptr, const uint32_t* col, uint32_t N, uint32_t E,
+                         const gcp_frustum_params* fp, const double* ray_angles, const double* ray_sin,
+                         const double* ray_cos, const double* edge_theta, const double* edge_cos,
+                         const double* edge_sin, int32_t* poly, uint8_t* ambiguous, float* kernel_ms);
+
 #ifdef __cplusplus
 }
 #endif
