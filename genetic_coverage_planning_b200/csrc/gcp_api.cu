@@ -561,6 +561,9 @@ int gcp_set_option(gcp_ctx* c, const char* name, int64_t value)
     }
     else if (!strcmp(name, "cov_table")) c->cov_table = (int)value;
     else if (!strcmp(name, "cov_maxpairs")) c->cov_maxpairs = (int)value;
+    else if (!strcmp(name, "lc_min_parts")) c->lc_min_parts = (int)value;
+    else if (!strcmp(name, "cov_threads")) c->cov_threads = (int)value;
+    else if (!strcmp(name, "cov_dedup")) c->cov_dedup = (int)value;
     else return gcp_fail(c, -1, "gcp_set_option: unknown option '%s'", name);
     return 0;
 }

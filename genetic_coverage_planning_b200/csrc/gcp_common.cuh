@@ -70,6 +70,9 @@ struct gcp_ctx {
     cudaStream_t hstream[2] = {};
     // coverage kernel tuning (0 = auto)
     int cov_table = 0, cov_maxpairs = 0;
+    int cov_dedup = 1;       // 1: revisited edges are dropped before the coverage union (phase B0)
+    int cov_threads = 0;     // tuning: CTA size of k_cov_quarters (256 / 512 / 1024; 0 = auto)
+    int lc_min_parts = 0;    // tuning: at least this many hash partitions in k_loop_closures_part
     int force_general = 0;   // testing: never take the pre-masked fast path
     int cov_detail = 1;      // 1: all six counters; 0: only what the objectives need
     int fused_eval = 1;      // 1: objectives-only fast path runs as ONE kernel (gcp_fused.cu)
@@ -97,7 +100,7 @@ struct StageTimer {
 int launch_path_costs(gcp_ctx*, const int32_t* dna, uint32_t P, uint32_t* edge_ids,
                       uint32_t* step_info, double* dist, double* turn, uint8_t* flags,
                       cudaStream_t, int quarter_info = 0);
-int launch_coverage_quarters(gcp_ctx*, const uint32_t* step_qinfo, uint32_t P, uint32_t* cov,
+int launch_coverage_quarters(gcp_ctx*, uint32_t* step_qinfo /* duplicates are zeroed in place */, uint32_t P, uint32_t* cov,
                              uint8_t* flags, cudaStream_t);
 int launch_coverage_masked(gcp_ctx*, const uint32_t* step_info, uint32_t P, uint32_t* cov,
                            uint8_t* flags, cudaStream_t);

@@ -23,6 +23,7 @@ struct FusedShape {
     int T, MAXP, T3;
     int gene16;          // chromosome stored as int16 in global memory
     uint32_t R0;
+    uint32_t DS;         // slots of the step-dedup hash set (power of two, 0 = skip)
     uint32_t off_info, off_x, off_cst, off_lc, off_cost;   // byte offsets into dynamic smem (off_cst relative to off_x)
 };
 
@@ -33,8 +34,8 @@ struct FusedShape {
 //   (per-thread partial sums; the caller reduces them).  s_x: T*20 + MAXP*8 + 32 bytes.
 // ============================================================================
 template <int KF_THREADS, bool HAS_GRAY>
-__device__ __forceinline__ void coverage_quarters(const uint32_t* info, int AL, const GcpTables& t,
-                                                  int T, int MAXP, uint32_t R0, unsigned char* s_x,
+__device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const GcpTables& t,
+                                                  int T, int MAXP, uint32_t R0, uint32_t DS, unsigned char* s_x,
                                                   uint32_t& n_cov, uint32_t& n_wg, bool& failed)
 {
     constexpr int KF_NW = KF_THREADS / 32;
@@ -47,6 +48,28 @@ __device__ __forceinline__ void coverage_quarters(const uint32_t* info, int AL, 
     uint32_t* s_sr   = s_pay + MAXP;                           // [MAXP] slot<<18 | q<<16 | rank
     const int logT = 31 - __clz(T);
     const uint32_t myq = lane >> 3, l7 = lane & 7;
+
+    // ---- B0: a walk revisits edges (18 % of the steps at 150-step walks, half of them at 512);
+    //      the union does not care, so only the first step of every distinct item list survives.
+    //      Hash set of the info words over the first DS words of s_x (DS = 0: table too small, skip).
+    if (DS) {
+        uint32_t* s_set = reinterpret_cast<uint32_t*>(s_x);
+        const int sh_ds = __clz(DS) + 1;                       // 32 - log2(DS)
+        for (int i = tid; i < (int)DS; i += KF_THREADS) s_set[i] = 0u;
+        __syncthreads();
+        for (int s = tid; s < AL; s += KF_THREADS) {
+            const uint32_t inf = info[s];
+            if (!inf) continue;
+            uint32_t h = (inf * 0x9E3779B1u) >> sh_ds;
+            for (;;) {
+                const uint32_t cur = atomicCAS(&s_set[h], 0u, inf);
+                if (cur == 0u) break;
+                if (cur == inf) { info[s] = 0u; break; }
+                h = (h + 1) & (DS - 1);
+            }
+        }
+        __syncthreads();
+    }
 
     uint32_t R = R0;
     failed = false;
@@ -125,44 +148,47 @@ __device__ __forceinline__ void coverage_quarters(const uint32_t* info, int AL, 
                         }
                         continue;
                     }
-                    uint2 d[4];                 // {block<<2 | q, uint4 index}; lists are 16-B aligned: two pair loads
-                    {
-                        const uint4* dp = reinterpret_cast<const uint4*>(t.m_q_desc + lo);
-                        uint4 p0 = make_uint4(0, 0, 0, 0), p1 = p0;
-                        if (n > 0) p0 = __ldg(dp);
-                        if (n > 2) p1 = __ldg(dp + 1);
-                        d[0] = make_uint2(p0.x, p0.y); d[1] = make_uint2(p0.z, p0.w);
-                        d[2] = make_uint2(p1.x, p1.y); d[3] = make_uint2(p1.z, p1.w);
-                    }
-                    uint32_t mine = n;
-                    if (R > 1) {
-                        mine = 0;
-                        for (uint32_t k = 0; k < n; ++k)
-                            mine += ((part_block(__ldg(t.m_q_desc + lo + k).x >> 2) & (R - 1)) == r);
-                    }
-                    uint32_t incl = mine;
+                    // R > 1 (long genomes): same flattening; every round keeps the items of partition r
+                    // and compacts them with a ballot (one shared atomic per round of 32 items)
+                    uint32_t incl = n;
                     #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
                         uint32_t v = __shfl_up_sync(FULL, incl, o);
                         if (lane >= o) incl += v;
                     }
                     const uint32_t total = __shfl_sync(FULL, incl, 31);
-                    if (total == 0) continue;
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&s_npairs, total);
-                    base = __shfl_sync(FULL, base, 0);
-                    if (base + total > (uint32_t)MAXP) {
-                        if (lane == 0) s_overflow = 1;
-                        continue;
-                    }
-                    uint32_t idx = base + incl - mine;
-                    uint32_t last_blk = KF_NIL, h = 0;
-                    auto put = [&](const uint2 dsc) {
-                        const uint32_t blk = dsc.x >> 2, q = dsc.x & 3u;
-                        if (R > 1 && (part_block(blk) & (R - 1)) != r) return;
-                        if (blk != last_blk) {          // quarters of one sub-tile share the slot
+                    const uint32_t excl = incl - n;
+                    for (uint32_t j0 = 0; j0 < total; j0 += 32) {
+                        const uint32_t j = j0 + lane;
+                        int a = 0, b = 31;
+                        #pragma unroll
+                        for (int it = 0; it < 5; ++it) {
+                            const int mid = (a + b) >> 1;
+                            const uint32_t v = __shfl_sync(FULL, incl, mid);
+                            if (v > j) b = mid; else a = mid + 1;
+                        }
+                        a = min(a, 31);
+                        const uint32_t ex = __shfl_sync(FULL, excl, a), dlo = __shfl_sync(FULL, lo, a);
+                        uint2 dsc = make_uint2(0, 0);
+                        bool mine = false;
+                        if (j < total) {
+                            dsc = __ldg(t.m_q_desc + dlo + (j - ex));
+                            mine = (part_block(dsc.x >> 2) & (R - 1)) == r;
+                        }
+                        const uint32_t bal = __ballot_sync(FULL, mine);
+                        if (!bal) continue;
+                        uint32_t base = 0;
+                        if (lane == 0) base = atomicAdd(&s_npairs, (uint32_t)__popc(bal));
+                        base = __shfl_sync(FULL, base, 0);
+                        if (base + (uint32_t)__popc(bal) > (uint32_t)MAXP) {
+                            if (lane == 0) s_overflow = 1;
+                            break;
+                        }
+                        if (mine) {
+                            const uint32_t idx = base + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+                            const uint32_t blk = dsc.x >> 2, q = dsc.x & 3u;
                             const uint32_t key = blk + 1;
-                            h = hash_block(blk) >> (32 - logT);
+                            uint32_t h = hash_block(blk) >> (32 - logT);
                             int probes = 0;
                             for (;;) {
                                 const uint32_t cur = ((volatile uint32_t*)s_keys)[h];
@@ -172,19 +198,14 @@ __device__ __forceinline__ void coverage_quarters(const uint32_t* info, int AL, 
                                     if (old == 0 || old == key) break;
                                 }
                                 h = (h + 1) & (T - 1);
-                                if (++probes >= T) { s_overflow = 1; return; }
+                                if (++probes >= T) { s_overflow = 1; break; }
                             }
-                            last_blk = blk;
+                            // a failed probe still fills its entry: the pass is discarded anyway
+                            const uint32_t rank = (probes < T) ? atomicAdd(&s_cq[4 * h + q], 1u) : 0u;
+                            s_pay[idx] = dsc.y;
+                            s_sr[idx] = (h << 18) | (q << 16) | rank;
                         }
-                        const uint32_t rank = atomicAdd(&s_cq[4 * h + q], 1u);
-                        s_pay[idx] = dsc.y;
-                        s_sr[idx] = (h << 18) | (q << 16) | rank;
-                        ++idx;
-                    };
-                    #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (k < (int)n) put(d[k]);
-                    for (uint32_t k = 4; k < n; ++k) put(__ldg(t.m_q_desc + lo + k));
+                    }
                 }
             }
             __syncthreads();
@@ -351,6 +372,7 @@ struct StaticShape {
     static constexpr int MAXP = (maxp0 + 7) & ~7;
     static constexpr int T = SAL / 3 <= 256 ? 256 : SAL / 3 <= 512 ? 512 : SAL / 3 <= 1024 ? 1024 : SAL / 3 <= 2048 ? 2048 : SAL / 3 <= 4096 ? 4096 : 8192;
     static constexpr int T3 = (SAL * 3) / 2 + 64;
+    static constexpr uint32_t DS = (uint32_t)T * 4;        // dedup hash set: 16 KiB-aligned part of the T * 20 bytes in front of s_cst
     static constexpr uint32_t R0 = (size_t)MAXP >= (size_t)SAL * 2 ? 1u : 0u;      // 0: not representable -> runtime shape
     static constexpr uint32_t off_cst = (uint32_t)T * 20;
     static constexpr uint32_t cov_b = (uint32_t)T * 20 + (uint32_t)MAXP * 8 + 32;
@@ -425,6 +447,10 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
         if (tid == 0) { s_bad = 0; s_total = 0; s_totalw = 0; }
         for (int i = tid; i < A * A; i += KF_THREADS) s_lc[i] = 0;
     }
+    // step-dedup hash set (see coverage_quarters B0): lives in front of s_cst during phase A1
+    const uint32_t DS = ST ? SS::DS : sh.DS;
+    uint32_t* s_set = reinterpret_cast<uint32_t*>(s_x);
+    for (int i = tid; i < (int)DS; i += KF_THREADS) s_set[i] = 0u;
     __syncthreads();
     // first -1 per row (step rule mappy.py:343-345) and number of valid genes (:390)
     for (int a = warp; a < A; a += KF_NW) {
@@ -485,6 +511,15 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
                     if (!found && !sentinel) bad |= 1;
                     info = __ldg(t.m_q_info + e);
                     cst = __ldg(t.edge_cost + e);
+                    if (DS && info) {                        // a revisited edge adds nothing to the union
+                        uint32_t h = (info * 0x9E3779B1u) >> (__clz(DS) + 1);
+                        for (;;) {
+                            const uint32_t cur = atomicCAS(&s_set[h], 0u, info);
+                            if (cur == 0u) break;
+                            if (cur == info) { info = 0u; break; }
+                            h = (h + 1) & (DS - 1);
+                        }
+                    }
                 }
             }
             s_cst[s + a] = cst;                                   // row stride L + 1: see phase A2
@@ -527,7 +562,7 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     uint32_t n_cov, n_wg;
     bool failed;
     coverage_quarters<KF_THREADS, HAS_GRAY>(s_info, AL, t, ST ? SS::T : sh.T, ST ? SS::MAXP : sh.MAXP,
-                                            ST ? 1u : sh.R0, s_x, n_cov, n_wg, failed);
+                                            ST ? 1u : sh.R0, 0u, s_x, n_cov, n_wg, failed);
     {
         uint32_t v = n_cov, vw = n_wg;
         #pragma unroll
@@ -653,9 +688,9 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
 // cov[P][8] = {n_mask0, 0, wg_mask, 0, n_mask0, 0, 0, 0}.
 // ============================================================================
 template <int KF_THREADS, bool HAS_GRAY>
-__global__ void __launch_bounds__(KF_THREADS, KF_THREADS == 256 ? 5 : 1)
-k_cov_quarters(const uint32_t* __restrict__ step_qinfo, uint32_t P, GcpTables t, int AL, int T, int MAXP,
-               uint32_t R0, uint32_t* __restrict__ cov, uint8_t* __restrict__ flags)
+__global__ void __launch_bounds__(KF_THREADS, KF_THREADS == 256 ? 5 : KF_THREADS == 512 ? 2 : 1)
+k_cov_quarters(uint32_t* step_qinfo, uint32_t P, GcpTables t, int AL, int T, int MAXP,
+               uint32_t R0, uint32_t DS, uint32_t* __restrict__ cov, uint8_t* __restrict__ flags)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint32_t s_total, s_totalw;
@@ -665,7 +700,7 @@ k_cov_quarters(const uint32_t* __restrict__ step_qinfo, uint32_t P, GcpTables t,
     if (tid == 0) { s_total = 0; s_totalw = 0; }
     uint32_t n_cov, n_wg;
     bool failed;
-    coverage_quarters<KF_THREADS, HAS_GRAY>(step_qinfo + (size_t)org * AL, AL, t, T, MAXP, R0, smem,
+    coverage_quarters<KF_THREADS, HAS_GRAY>(step_qinfo + (size_t)org * AL, AL, t, T, MAXP, R0, DS, smem,
                                             n_cov, n_wg, failed);
     uint32_t v = n_cov, vw = n_wg;
     #pragma unroll
@@ -680,13 +715,14 @@ k_cov_quarters(const uint32_t* __restrict__ step_qinfo, uint32_t P, GcpTables t,
     if (tid == 0 && failed && flags) flags[(size_t)org * 4 + 3] |= 2;
 }
 
-int launch_coverage_quarters(gcp_ctx* ctx, const uint32_t* step_qinfo, uint32_t P, uint32_t* cov,
+int launch_coverage_quarters(gcp_ctx* ctx, uint32_t* step_qinfo, uint32_t P, uint32_t* cov,
                              uint8_t* flags, cudaStream_t st)
 {
     if (P == 0) return 0;
     if (!ctx->have_masked || !ctx->t.m_q_info) return gcp_fail(ctx, -1, "quarter-item tables not uploaded");
     const int AL = ctx->p.num_agents * ctx->p.max_dna_len;
-    const int threads = AL > 2048 ? 1024 : 256;
+    int threads = AL > 2048 ? 1024 : 256;
+    if (ctx->cov_threads == 256 || ctx->cov_threads == 512 || ctx->cov_threads == 1024) threads = ctx->cov_threads;
     int maxp = ctx->cov_maxpairs > 0 ? ctx->cov_maxpairs : (9 * AL) / 4;
     if (maxp < 256) maxp = 256;
     if (maxp > KF_PPT * threads) maxp = KF_PPT * threads;
@@ -698,15 +734,20 @@ int launch_coverage_quarters(gcp_ctx* ctx, const uint32_t* step_qinfo, uint32_t 
     const size_t smem = (size_t)T * 20 + (size_t)maxp * 8 + 32;
     if (smem > (size_t)ctx->max_smem_optin)
         return gcp_fail(ctx, -3, "coverage kernel needs %zu B shared memory", smem);
+    // step dedup (B0): hash set over the whole table area; skipped if it cannot stay under 80 % full
+    uint32_t DS = 1;
+    while ((size_t)DS * 2 * 4 <= (size_t)T * 20 + (size_t)maxp * 8) DS <<= 1;
+    if ((size_t)DS * 4 < (size_t)AL * 5 || ctx->cov_dedup == 0) DS = 0;
     StageTimer tm(ctx, 1, st);
     const bool gray = ctx->n_gray > 0;
 #define GCP_LAUNCH_COVQ(TH, GRAY)                                                                      \
     do {                                                                                               \
         GCP_CUDA(ctx, cudaFuncSetAttribute(k_cov_quarters<TH, GRAY>,                                   \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-        k_cov_quarters<TH, GRAY><<<P, TH, smem, st>>>(step_qinfo, P, ctx->t, AL, T, maxp, R0, cov, flags); \
+        k_cov_quarters<TH, GRAY><<<P, TH, smem, st>>>(step_qinfo, P, ctx->t, AL, T, maxp, R0, DS, cov, flags); \
     } while (0)
     if (threads == 256) { if (gray) GCP_LAUNCH_COVQ(256, true); else GCP_LAUNCH_COVQ(256, false); }
+    else if (threads == 512) { if (gray) GCP_LAUNCH_COVQ(512, true); else GCP_LAUNCH_COVQ(512, false); }
     else                { if (gray) GCP_LAUNCH_COVQ(1024, true); else GCP_LAUNCH_COVQ(1024, false); }
 #undef GCP_LAUNCH_COVQ
     ctx->launches++;
@@ -755,6 +796,7 @@ static size_t fused_shape(gcp_ctx* ctx, FusedShape& sh, int KF_THREADS)
     sh.T = T; sh.MAXP = maxp;
     sh.T3 = (sh.AL * 3) / 2 + 64;
     if (sh.T3 > 65535) return 0;
+    sh.DS = ctx->cov_dedup ? (uint32_t)T * 4 : 0u;                   // step-dedup hash set in front of s_cst
     sh.R0 = 1;
     while ((size_t)sh.R0 * maxp < (size_t)sh.AL * 2 && sh.R0 < 4096) sh.R0 <<= 1;
     sh.off_cst = (uint32_t)T * 20;                                    // over s_pay / s_sr
@@ -798,7 +840,7 @@ int launch_eval_fused(gcp_ctx* ctx, const void* dna, int gene16, uint32_t P, con
         sh.T == StaticShape<SAL>::T && sh.MAXP == StaticShape<SAL>::MAXP &&                           \
         sh.T3 == StaticShape<SAL>::T3 && sh.off_info == StaticShape<SAL>::off_info &&                 \
         sh.off_x == StaticShape<SAL>::off_x && sh.off_cst == StaticShape<SAL>::off_cst &&             \
-        sh.off_lc == StaticShape<SAL>::off_lc) {                                                       \
+        sh.off_lc == StaticShape<SAL>::off_lc && sh.DS == StaticShape<SAL>::DS) {                      \
         if (gray) GCP_LAUNCH_FUSED(256, true, SAL); else GCP_LAUNCH_FUSED(256, false, SAL);           \
         done = true;                                                                                   \
     }

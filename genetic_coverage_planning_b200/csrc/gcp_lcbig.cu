@@ -316,6 +316,7 @@ int launch_loop_closures_big(gcp_ctx* ctx, const int32_t* dna, uint32_t P, const
         auto pick = [&](bool s16, int* T3_out, size_t* smem_out) -> uint32_t {
             const size_t fixed = ((AL + 1) & ~(size_t)1) * 2 * (s16 ? 2 : 1) + (size_t)A * A * 4 + 64;
             for (uint32_t R = 1; R <= 64; R <<= 1) {
+                if ((int)R < ctx->lc_min_parts) continue;
                 const int T3 = (int)((AL * 3) / (2 * R)) + 64 + (R > 1 ? (int)(AL / (4 * R)) : 0);   // slack: uneven partitions
                 const size_t smem = (size_t)T3 * 20 + fixed;
                 if (smem <= (size_t)ctx->max_smem_optin) { *T3_out = T3; *smem_out = smem; return R; }

@@ -1,4 +1,4 @@
-import sys, torch
+import os, sys, torch
 sys.path.insert(0, "/root/repo")
 from genetic_coverage_planning_b200 import synth, worlds
 from genetic_coverage_planning_b200.engine import FitnessEngine
@@ -9,9 +9,12 @@ for name in ("C4-16", "C4-32"):
     starts = synth.spread_starts(w.xy, A, 4096)
     op = worlds.org_params_for(cfg, starts)
     eng = FitnessEngine(pw, op, num_agents=A)
+    for kv in filter(None, os.environ.get("GCP_OPTS", "").split(",")):
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
     dna = synth.random_walk_population_torch(w.xy, w.row_ptr, w.col, starts, P, cfg['walk'], L, seed=1, device=eng.device)
     for _ in range(2): eng.evaluate(dna, detail=False)
     eng.set_timing(True)
     eng.evaluate(dna, detail=False)
     torch.cuda.synchronize()
-    print(name, "P", P, {n: round(eng.stage_ms(k), 3) for k, n in enumerate(["path", "cov", "lc"])})
+    print(os.environ.get("GCP_OPTS", ""), name, "P", P, {n: round(eng.stage_ms(k), 3) for k, n in enumerate(["path", "cov", "lc"])})
