@@ -160,7 +160,8 @@ class GeneticalGorithm(object):
                           'coverage_constr_0': -population._cov_constr_0,
                           'coverage_constr_f': -population._cov_constr_f,
                           'coverage_aging': population._cov_aging,
-                          'org_params': population._org_params}
+                          # the reference keeps org_params on its organisms only (geneticalgorithm.py:25,130)
+                          'org_params': getattr(population, '_org_params', None) or first._org_params}
         L = gen_params['org_params']['max_dna_len']
         dna = np.stack([_pad_rows(list(o._dna), L) for o in population._gen_parent]).astype(np.int32)
         pop = cls(first._mappy, first._pather, gen_params, device=device, seed=seed,

@@ -170,18 +170,16 @@ def pack_world(img, xy, row_ptr, col, edge_poly, edge_theta, edge_dist, map_para
         by0 = (cy[e] - reach) // BLK
         ox, oy = bx0 * BLK, by0 * BLK
         canvas[:] = 0
-        cv2.fillPoly(canvas, [polys[e]], 1, offset=(int(cx[e] - ox), int(cy[e] - oy)))
-        # clip to the map: pixels outside [0,W)x[0,H) do not exist in draw_map
+        # the reference draws on the map itself (mappy.py:355), so cv2 clips the polygon against the
+        # map's borders - and a clipped edge is NOT the unclipped one with the outside pixels
+        # removed (cv2 restarts its line walk at the clip point).  Draw into the part of the
+        # canvas that lies inside the map: its borders coincide with the map's wherever the
+        # footprint crosses them, and are out of reach elsewhere.
         x_lo, x_hi = max(0, -ox), min(kb * BLK, W - ox)
         y_lo, y_hi = max(0, -oy), min(kb * BLK, H - oy)
-        if x_lo > 0:
-            canvas[:, :x_lo] = 0
-        if x_hi < kb * BLK:
-            canvas[:, max(x_hi, 0):] = 0
-        if y_lo > 0:
-            canvas[:y_lo, :] = 0
-        if y_hi < kb * BLK:
-            canvas[max(y_hi, 0):, :] = 0
+        if x_hi > x_lo and y_hi > y_lo:
+            cv2.fillPoly(canvas[y_lo:y_hi, x_lo:x_hi], [polys[e]], 1,
+                         offset=(int(cx[e] - ox - x_lo), int(cy[e] - oy - y_lo)))
         rows = _rows_to_u64(canvas.reshape(kb * BLK, kb, BLK))     # [kb*64, kb]
         n_sub = 0
         m_n_sub = 0

@@ -425,3 +425,28 @@ def test_evolution_matches_reference_statistics(world_small, golden_dir):
     assert abs(got[2, MEAN] - ref[n_gen, MEAN]) <= 0.03
     assert abs(got[2, COST] - ref[n_gen, COST]) <= 0.12 * ref[n_gen, COST]
     assert abs(got[2, LEN] - ref[n_gen, LEN]) <= 0.12 * ref[n_gen, LEN]
+
+
+def test_legacy_reference_pickle_migrates(golden_dir):
+    """a population evolved and pickled by the UNMODIFIED reference
+    (tests/golden/make_golden_legacy.py: cropped small map, graph from the reference's own
+    computeTraversableGraph, 3 agents, 2 generations) opens without the reference, and the GPU
+    evaluation of its parents reproduces the objectives the reference stored for them."""
+    import os
+    from genetic_coverage_planning_b200 import legacy
+    z = np.load(os.path.join(golden_dir, "legacy_population.npz"))
+    pop = legacy.load(os.path.join(golden_dir, "legacy_population.pkl.gz"), seed=1)
+    assert pop._gen_num == int(z['gen_num']) and pop._G_sz == len(z['dna'])
+    got = {np.asarray(o._dna).astype(np.int64).tobytes(): np.asarray(o._obj_val, dtype=float)
+           for o in pop._gen_parent}
+    for dna, obj in zip(z['dna'], z['obj']):
+        mine = got[np.asarray(dna).astype(np.int64).tobytes()]
+        assert mine[1] == obj[1]                               # travel cost: bit-exact
+        assert abs(mine[0] - obj[0]) <= 1e-12                  # -coverage on a gray map
+    # ranking of the migrated parents is the reference's rackNstack on the same objectives
+    want = fo.rack_n_stack(np.array([o._obj_val for o in pop._gen_parent]), pop._gen_num,
+                           dict(coverage_aging=pop._cov_aging, coverage_constr_0=-pop._cov_constr_0,
+                                coverage_constr_f=-pop._cov_constr_f))
+    assert np.array_equal(np.asarray(pop._gen_parent_fit), want)
+    hist = pop.runEvolution(2)                                 # and evolution continues
+    assert pop._gen_num == int(z['gen_num']) + 2 and len(hist) == 2 and len(hist[0]) == len(z['dna'])

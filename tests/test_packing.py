@@ -112,3 +112,52 @@ def test_pack_from_live_reference_objects(world_small):
         assert np.array_equal(getattr(a, name), getattr(b, name)), name
     assert (a.mask_size, a.gsum_mask, a.map_size, a.num_occluded) == \
            (b.mask_size, b.gsum_mask, b.map_size, b.num_occluded)
+
+
+def test_legacy_pickle_opens_without_the_reference(golden_dir):
+    """A population pickled by the unmodified reference (tests/golden/make_golden_legacy.py) opens
+    through legacy.load_population with no reference module importable, and carries the state the
+    facade needs."""
+    import os
+    from genetic_coverage_planning_b200 import legacy, packing
+    old = legacy.load_population(os.path.join(golden_dir, "legacy_population.pkl.gz"))
+    for obj, name in ((old, "geneticalgorithm.GeneticalGorithm"), (old._gen_parent[0], "geneticalgorithm.Organism"),
+                      (old._gen_parent[0]._mappy, "mappy.Mappy"), (old._gen_parent[0]._pather, "pathmaker.PathMaker")):
+        assert type(obj).__module__ == "genetic_coverage_planning_b200.legacy"      # attribute bags, not reference classes
+        assert type(obj)._legacy_class == name
+    z = np.load(os.path.join(golden_dir, "legacy_population.npz"))
+    assert old._gen_num == int(z['gen_num']) and old._G_sz == len(z['dna'])
+    assert np.array_equal(np.array([o._dna for o in old._gen_parent]), z['dna'])
+    assert np.array_equal(np.array([o._obj_val for o in old._gen_parent], dtype=float), z['obj'])
+    first = old._gen_parent[0]
+    assert np.array_equal(first._pather._graph, z['graph']) and np.array_equal(first._pather._XY, z['xy'])
+    pw = packing.pack_from_reference(first._mappy, first._pather)      # tables from the pickled state
+    assert pw.N == len(z['xy']) and pw.E == int(z['graph'].sum())
+
+
+def test_footprints_clipped_at_the_map_border_like_cv2(golden_dir):
+    """The cropped legacy world has waypoints 8 px from the map border, so most footprints are
+    clipped: the packed tiles must equal what cv2.fillPoly leaves on the map itself (the oracle
+    paints the full map like mappy.py:353-355).  A polygon drawn unclipped and cropped afterwards
+    differs along the border (cv2 restarts clipped lines) - this pins the difference."""
+    import os
+    import fitness_oracle as fo
+    from world import World
+    import helpers
+    from genetic_coverage_planning_b200 import legacy, packing
+    old = legacy.load_population(os.path.join(golden_dir, "legacy_population.pkl.gz"))
+    first = old._gen_parent[0]
+    w = World.from_reference(first._mappy, first._pather, first._org_params)
+    pw = packing.pack_from_reference(first._mappy, first._pather)
+    H, W = w.img.shape
+    for o in old._gen_parent:
+        dna = np.asarray(o._dna)
+        acc = helpers.painted_blocks(pw, helpers.edge_ids_for_dna(pw, dna))
+        mine = np.zeros((pw.nby * 64, pw.nbx * 64), dtype=bool)
+        for b, rows in acc.items():
+            by, bx = divmod(b, pw.nbx)
+            mine[by * 64:by * 64 + 64, bx * 64:bx * 64 + 64] = \
+                ((rows[:, None] >> np.arange(64, dtype='<u8')[None, :]) & 1).astype(bool)
+        assert not mine[H:].any() and not mine[:, W:].any()
+        assert np.array_equal(mine[:H, :W], fo._painted_map(w, dna))
+        assert tuple(fo.calc_obj(w, dna)) == tuple(o._obj_val)       # oracle == the reference's stored objectives
