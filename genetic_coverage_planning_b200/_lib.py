@@ -41,6 +41,11 @@ class GcpFrustumParams(C.Structure):
                 ("eps_angle", C.c_double), ("eps_round", C.c_double)]
 
 
+class GcpGraphParams(C.Structure):
+    _fields_ = [("scale", C.c_double), ("max_dist", C.c_double), ("num_dilations", C.c_int32),
+                ("cell", C.c_int32), ("sectors", C.c_double * 8), ("eps_angle", C.c_double)]
+
+
 class GcpEvalOut(C.Structure):
     _fields_ = [("obj", C.c_void_p), ("neg_cov", C.c_void_p), ("dist", C.c_void_p),
                 ("turn", C.c_void_p), ("cov", C.c_void_p), ("lc_mat", C.c_void_p),
@@ -85,6 +90,7 @@ SIGNATURES = {
     "gcp_launch_count": (C.c_uint64, [_vp]),
     "gcp_set_timing": (C.c_int, [_vp, C.c_int]),
     "gcp_stage_ms": (C.c_float, [_vp, C.c_int]),
+    "gcp_build_graph": (C.c_int, [C.c_int, _vp, _u32, _u32, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gcp_compute_frustums": (C.c_int, [C.c_int, _vp, _u32, _u32, _vp, _vp, _vp, _u32, _u32, _vp,
                                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgcp.so")
-SOURCES = ["gcp_api.cu", "gcp_eval.cu", "gcp_frustum.cu", "gcp_fused.cu", "gcp_lcbig.cu", "gcp_rank.cu", "gcp_sort.cu", "gcp_vary.cu"]
+SOURCES = ["gcp_api.cu", "gcp_eval.cu", "gcp_frustum.cu", "gcp_graph.cu", "gcp_fused.cu", "gcp_lcbig.cu", "gcp_rank.cu", "gcp_sort.cu", "gcp_vary.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false"]
 

@@ -269,6 +269,32 @@ int gcp_compute_frustums(int device, const uint8_t* occ, uint32_t H, uint32_t W,
                          const double* ray_cos, const double* edge_theta, const double* edge_cos,
                          const double* edge_sin, int32_t* poly, uint8_t* ambiguous, float* kernel_ms);
 
+
+/* ---- setup path: traversability graph -----------------------------------
+ * Replaces PathMaker.computeTraversableGraph (pathmaker.py:119-155) and the per-edge
+ * Mappy.lineCollisionCheck (mappy.py:124-159).  No context; HOST pointers; synchronous; errors
+ * through gcp_last_error(NULL).
+ *   occ[H][W]              != 0 where Mappy._img != 0
+ *   xy[N][2]               waypoint (row, col) = PathMaker._XY
+ *   cell_ptr / cell_items  waypoints bucketed into square grid cells of `cell` px, row-major cells
+ *                          ((H + cell - 1) / cell rows of (W + cell - 1) / cell), ascending waypoint
+ *                          index inside a cell; cell >= max_dist / scale
+ *   nbr[N][8]              out: per 45-degree sector the surviving neighbour, -1 if none
+ *                          (graph[i, nbr[i][s]] = 1)
+ *   ambiguous[N]           out: 1 where a bearing fell within eps_angle of a sector boundary: the
+ *                          caller recomputes those rows with the reference's own expressions   */
+typedef struct gcp_graph_params {
+    double  scale;            /* m per px (Mappy._scale) */
+    double  max_dist;         /* path_params['max_traverse_dist'], m (pathmaker.py:147) */
+    int32_t num_dilations;    /* int((hall_width / 2 / 3) / scale)  (pathmaker.py:153, mappy.py:136) */
+    int32_t cell;             /* grid cell size, px */
+    double  sectors[8];       /* (pi / 4) * [-7/2, -5/2, ..., 7/2]  (pathmaker.py:125-127) */
+    double  eps_angle;        /* e.g. 1e-11 rad */
+} gcp_graph_params;
+int gcp_build_graph(int device, const uint8_t* occ, uint32_t H, uint32_t W, const int32_t* xy, uint32_t N,
+                    const uint32_t* cell_ptr, const uint32_t* cell_items, const gcp_graph_params* gp,
+                    int32_t* nbr, uint8_t* ambiguous, float* kernel_ms);
+
 #ifdef __cplusplus
 }
 #endif

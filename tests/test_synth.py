@@ -57,3 +57,18 @@ def test_random_walks_follow_edges(synth_world):
         for a, b in zip(v[:-1], v[1:]):
             assert (int(a), int(b)) in edges or a == b
     assert np.array_equal(worlds.executed_steps(dna), np.full(16, 4 * 61))
+
+
+def test_graph_row_restatement_equals_reference(world_small, golden_dir):
+    """graphs._row_host (the exactness fallback of the device graph builder) reproduces rows of the
+    graph the unmodified reference built (tests/golden/graph_ref.npz)."""
+    import os
+    from genetic_coverage_planning_b200 import graphs
+    w = world_small
+    z = np.load(os.path.join(golden_dir, "graph_ref.npz"))
+    rp, col = z["small_row_ptr"], z["small_col"]
+    nd = int(((w.map_params['narrowest_hall'] / 2) / 3) / w.map_params['scale'])
+    obstacles = np.array(np.nonzero(graphs._dilated(w.img, nd))).T
+    for i in range(0, len(w.xy), 7):
+        got = graphs._row_host(i, w.xy, w.map_params['scale'], 4.0, obstacles)
+        assert sorted(int(v) for v in got if v >= 0) == [int(v) for v in col[rp[i]:rp[i + 1]]]
