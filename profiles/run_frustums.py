@@ -45,6 +45,29 @@ def main():
                           "host_restatement_s": t_host, "host_edges": e_hi,
                           "host_edges_per_s_1core": e_hi / t_host,
                           "bit_identical_on_host_edges": same}), flush=True)
+        # the reference's graph rule (nearest waypoint per 45-degree sector + line
+        # collision check against the dilated map) on the same map and waypoints
+        from genetic_coverage_planning_b200 import graphs
+        hall, maxd = mp['narrowest_hall'], pp['max_traverse_dist']
+        graphs.compute_traversable_graph_device(img[:256, :256], xy[:1], mp['scale'], maxd, hall)   # warm-up
+        t0 = time.time()
+        rp, cl, ginfo = graphs.compute_traversable_graph_device(img, xy, mp['scale'], maxd, hall, return_info=True)
+        t_call = time.time() - t0
+        nd = int(((hall / 2) / 3) / mp['scale'])
+        t0 = time.time()
+        obstacles = np.array(np.nonzero(graphs._dilated(img, nd))).T
+        rows = np.arange(0, N, max(1, N // 64))[:64]
+        ok = True
+        for i in rows:
+            got = graphs._row_host(int(i), xy, mp['scale'], maxd, obstacles)
+            ok = ok and sorted(int(v) for v in got if v >= 0) == [int(v) for v in cl[rp[i]:rp[i + 1]]]
+        t_host = time.time() - t0
+        print(json.dumps({"map": "%d^2 synthetic" % size, "graph": "reference rule (pathmaker.py:119-155)", "N": N,
+                          "E": int(len(cl)), "kernels_ms": ginfo["kernel_ms"], "device_call_s": t_call,
+                          "ambiguous_rows": ginfo["ambiguous_rows"], "host_rows_checked": int(len(rows)),
+                          "host_restatement_s_per_row": t_host / len(rows),
+                          "host_restatement_s_extrapolated": t_host / len(rows) * N,
+                          "rows_identical": bool(ok)}), flush=True)
 
 
 if __name__ == "__main__":
