@@ -234,6 +234,10 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     distributed = world_size > 1
+    # one process per GPU: keep the process (and the pinned staging buffers it allocates from here
+    # on) on the GPU's NUMA node, otherwise the e2e leg's H2D copies cross the socket interconnect
+    from genetic_coverage_planning_b200.distributed import bind_to_gpu_numa_node
+    numa_node = bind_to_gpu_numa_node(local)
     if distributed:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -504,7 +508,8 @@ def main():
                        "l2": "per-step input (dna, %.0f MB) exceeds the 126 MB L2; no flush; the "
                              "%.0f MB pre-masked footprint store is reused inside a launch"
                              % (P * A * L * 4 / 1e6, pw.m_n_quarters * 128 / 1e6),
-                       "parallelism": "population sharded, tables replicated, no collective"},
+                       "parallelism": "population sharded, tables replicated, no collective",
+                       "host_numa_node_rank0": numa_node},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if roofline:

@@ -10,6 +10,36 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa_node(device=0):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off (Linux sysfs), so that the
+    pinned staging buffers allocated afterwards are node-local: with one process per GPU on a
+    two-socket host, host->device copies otherwise cross the socket interconnect.  Returns the node
+    id, or None when the topology is not exposed (then nothing is changed)."""
+    import os
+    import torch
+    try:
+        p = torch.cuda.get_device_properties(device)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return node if cpus else None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except (OSError, ValueError, AttributeError):
+        return None
+
+
 def shard_range(n, rank, world):
     """Contiguous balanced shard [lo, hi) of n items for `rank` of `world`."""
     base, rem = divmod(n, world)
