@@ -269,39 +269,18 @@ class GeneticalGorithm(object):
         self._views = None
 
     # -- attributes the reference's plotting / export code reads -------------------------
-    @property
-    def _gen_parent(self):
-        """List of Organism views (gori_tools.py:23,248-250; pointselector.py:52), built on
-        first access after each change; no table copies (SURVEY F13)."""
-        if self._views is None:
-            dna = self._dna.cpu().numpy()
-            obj = self._obj.cpu().numpy()
-            sc = self._obj_sc.cpu().numpy() if self._obj_sc is not None else [None] * len(dna)
-            self._views = [Organism([None] * self._num_agents, self._mappy, self._pather,
-                                    self._org_params, _precomputed=(dna[k], obj[k], sc[k]))
-                           for k in range(len(dna))]
-        return self._views
+    _LAZY = ('_eng', '_dna', '_obj', '_fit', '_obj_sc')
 
-    @property
-    def _gen_parent_fit(self):
-        return [float(f) for f in self._fit.cpu().numpy()]
+    def __getattr__(self, name):
+        # after unpickling, the CUDA context and the device tensors are created on first use, so a
+        # pickled population opens on a machine without a GPU (plotting / export only read host copies)
+        if name in GeneticalGorithm._LAZY and '_host_state' in self.__dict__:
+            self._materialise()
+            return self.__dict__[name]
+        raise AttributeError(name)
 
-    # -- pickle (gori_tools.py:252-257): device state round-trips through numpy ----------
-    def __getstate__(self):
-        st = {k: v for k, v in self.__dict__.items() if k not in ('_eng', '_views', '_dna', '_obj',
-                                                                   '_fit', '_obj_sc')}
-        st['_dna_np'] = self._dna.cpu().numpy()
-        st['_obj_np'] = self._obj.cpu().numpy()
-        st['_fit_np'] = self._fit.cpu().numpy()
-        st['_obj_sc_np'] = self._obj_sc.cpu().numpy()
-        return st
-
-    def __setstate__(self, st):
-        st = dict(st)
-        dna, obj, fit, sc = (st.pop('_dna_np'), st.pop('_obj_np'), st.pop('_fit_np'),
-                             st.pop('_obj_sc_np'))
-        self.__dict__.update(st)
-        self._views = None
+    def _materialise(self):
+        dna, obj, fit, sc = self.__dict__.pop('_host_state')
         self._eng = _engine_for(self._mappy, self._pather, self._org_params, self._num_agents,
                                 self._device)
         dev = self._eng.device
@@ -310,7 +289,46 @@ class GeneticalGorithm(object):
         self._fit = torch.from_numpy(fit).to(dev)
         self._obj_sc = torch.from_numpy(sc).to(dev)
 
+    def _host_arrays(self):
+        if '_host_state' in self.__dict__:
+            return self.__dict__['_host_state']
+        return (self._dna.cpu().numpy(), self._obj.cpu().numpy(), self._fit.cpu().numpy(),
+                self._obj_sc.cpu().numpy() if self._obj_sc is not None else None)
+
+    # -- attributes the reference's plotting / export code reads -------------------------
+    @property
+    def _gen_parent(self):
+        """List of Organism views (gori_tools.py:23,248-250; pointselector.py:52), built on
+        first access after each change; no table copies (SURVEY F13)."""
+        if self._views is None:
+            dna, obj, _, sc = self._host_arrays()
+            if sc is None:
+                sc = [None] * len(dna)
+            self._views = [Organism([None] * self._num_agents, self._mappy, self._pather,
+                                    self._org_params, _precomputed=(dna[k], obj[k], sc[k]))
+                           for k in range(len(dna))]
+        return self._views
+
+    @property
+    def _gen_parent_fit(self):
+        return [float(f) for f in self._host_arrays()[2]]
+
+    # -- pickle (gori_tools.py:252-257): device state round-trips through numpy ----------
+    def __getstate__(self):
+        st = {k: v for k, v in self.__dict__.items() if k not in ('_eng', '_views', '_dna', '_obj',
+                                                                   '_fit', '_obj_sc', '_host_state')}
+        dna, obj, fit, sc = self._host_arrays()
+        st['_dna_np'], st['_obj_np'], st['_fit_np'], st['_obj_sc_np'] = dna, obj, fit, sc
+        return st
+
+    def __setstate__(self, st):
+        st = dict(st)
+        host = (st.pop('_dna_np'), st.pop('_obj_np'), st.pop('_fit_np'), st.pop('_obj_sc_np'))
+        self.__dict__.update(st)
+        self._views = None
+        self.__dict__['_host_state'] = host        # device side is created on first use (_materialise)
+
 
 def getObjValsList(population):
     """gori_tools.py:248-250 without materialising Organism views."""
-    return [[float(o[0]), float(o[1])] for o in population._obj.cpu().numpy()]
+    return [[float(o[0]), float(o[1])] for o in population._host_arrays()[1]]

@@ -12,25 +12,36 @@ import gzip
 import io
 import pickle
 
-_LEGACY = {("geneticalgorithm", "GeneticalGorithm"), ("geneticalgorithm", "Organism"),
-           ("mappy", "Mappy"), ("pathmaker", "PathMaker")}
-_BAGS = {}
+class _Bag(object):
+    """State of a pickled reference object (its instance __dict__), no behaviour."""
+    _legacy_class = None
 
 
-def _bag(module, name):
-    cls = _BAGS.get((module, name))
-    if cls is None:
-        cls = type(name, (object,), {"__module__": "genetic_coverage_planning_b200.legacy",
-                                     "__doc__": "state of a pickled reference %s.%s" % (module, name),
-                                     "_legacy_class": "%s.%s" % (module, name)})
-        _BAGS[(module, name)] = cls
-    return cls
+class GeneticalGorithm(_Bag):
+    _legacy_class = "geneticalgorithm.GeneticalGorithm"
+
+
+class Organism(_Bag):
+    _legacy_class = "geneticalgorithm.Organism"
+
+
+class Mappy(_Bag):
+    _legacy_class = "mappy.Mappy"
+
+
+class PathMaker(_Bag):
+    _legacy_class = "pathmaker.PathMaker"
+
+
+_LEGACY = {("geneticalgorithm", "GeneticalGorithm"): GeneticalGorithm,
+           ("geneticalgorithm", "Organism"): Organism,
+           ("mappy", "Mappy"): Mappy, ("pathmaker", "PathMaker"): PathMaker}
 
 
 class _Unpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if (module, name) in _LEGACY:
-            return _bag(module, name)
+            return _LEGACY[(module, name)]
         return super().find_class(module, name)
 
 

@@ -137,3 +137,44 @@ def build_world(config="big", num_agents=6, blend=None):
     m.setWaypoints(p.waypoint_locs)
     m.computeFrustums(p._graph)
     return m, p, (map_params, path_params, org_params, gen_params)
+
+
+class stable_argsort(object):
+    """SURVEY F9/F15 canonicalisation: np.argsort -> kind='stable' while active."""
+
+    def __enter__(self):
+        import numpy as np
+        self._np, self._orig = np, np.argsort
+
+        def _stable(a, *args, **kw):
+            kw['kind'] = 'stable'
+            return self._orig(a, *args, **kw)
+        np.argsort = _stable
+
+    def __exit__(self, *exc):
+        self._np.argsort = self._orig
+
+
+CROP = (40, 200, 20, 200)      # r0, r1, c0, c1 of data/map_scaled.png (tests/golden/make_golden_legacy.py)
+
+
+def build_cropped_world(num_agents=3):
+    """Reference Mappy / PathMaker on a crop of the small map with the shipped waypoints that fall
+    inside it (8 px margin); graph from the reference's own computeTraversableGraph."""
+    import numpy as np
+    import cv2
+    ga, mappy_m, pm_m, got = load()
+    mp, pp, op, gp = driver_params(num_agents)
+    img = cv2.imread(os.path.join(REF_DATA, "map_scaled.png"), cv2.IMREAD_GRAYSCALE) / 255
+    r0, r1, c0, c1 = CROP
+    img = np.ascontiguousarray(img[r0:r1, c0:c1])
+    xy = np.load(os.path.join(REF_DATA, "wilk_3_wpts.npy"))
+    keep = (xy[:, 0] >= r0 + 8) & (xy[:, 0] < r1 - 8) & (xy[:, 1] >= c0 + 8) & (xy[:, 1] < c1 - 8)
+    xy = xy[keep] - np.array([r0, c0])
+    m = mappy_m.Mappy(img, mp)
+    p = pm_m.PathMaker(m, pp)
+    p._XY = xy.astype(int)
+    p.computeTraversableGraph()
+    m.setWaypoints(p.waypoint_locs)
+    m.computeFrustums(p._graph)
+    return m, p, (mp, pp, op, gp)
