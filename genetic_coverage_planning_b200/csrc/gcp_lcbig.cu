@@ -9,6 +9,7 @@
 // its group and adds to the organism's A x A matrix; a last kernel applies the constraints and
 // assembles the objectives (geneticalgorithm.py:177-201).
 #include "gcp_common.cuh"
+#include <type_traits>
 #include "gcp_device.cuh"
 
 size_t radix_hist_bytes(uint32_t n);
@@ -136,54 +137,66 @@ k_lcb_finish(uint32_t P, int A, gcp_params prm, gcp_map_consts mc, const int32_t
 
 // ---------------------------------------------------------------------------------------------
 // Hash-partitioned shared-memory variant (default for long genomes): one 1024-thread CTA per
-// organism.  The compacted gene sequence goes to global scratch (it stays in L2 for the CTA's
-// lifetime); the duplicate-edge hash table of k_loop_closures is kept, but only for the keys of
-// ONE of R hash partitions at a time, so that it fits shared memory for any A*L <= 65,535.  The
-// owner agent of a position is found from the row bases instead of a per-position array.
+// organism.  The duplicate-edge hash table of k_loop_closures is kept, but only for the keys of
+// ONE of R hash partitions at a time, so that it fits shared memory for any A*L <= 65,535.
+//
+// The positions are BUCKETED by partition first: the compacted gene sequence is built in shared
+// memory (in the space the tables use later), one scan counts the keys per partition, a second
+// scan scatters {key, position} records into the organism's stretch of a global scratch array
+// (written and read back by the same CTA: it stays in L2).  Every partition then makes its three
+// passes over its own records only - linear, coalesced, key ready - instead of re-scanning all
+// positions, recomputing and filtering their keys, R times.  The owner agent of a position is
+// found from the row bases instead of a per-position array.
 // ---------------------------------------------------------------------------------------------
 constexpr int LP_THREADS = 1024;
 constexpr int LP_NW = LP_THREADS / 32;
 constexpr uint32_t LP_NIL = 0xFFFFFFFFu;
+constexpr int LP_MAX_PARTS = 64;
 
 template <typename SEQ>
-__device__ __forceinline__ unsigned long long lp_key(const SEQ* sq, int i, int n)
+__device__ __forceinline__ unsigned long long lp_key48(const SEQ* sq, int i, int n)
 {
     const unsigned long long f = (uint32_t)sq[i] & 0xFFFFFFu;
     const unsigned long long g = (uint32_t)sq[(i + 1 == n) ? 0 : i + 1] & 0xFFFFFFu;
-    return ((f << 24) | g) + 1ull;                                         // never 0
+    return (f << 24) | g;
 }
 __device__ __forceinline__ uint32_t lp_hash(unsigned long long key) { return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32); }
 
-// SEQ16: node ids fit 16 bits -> the compacted sequence lives in shared memory (u16) instead of
-// global scratch (out-of-range genes are reported by k_path_costs; here they are truncated).
+// SEQ16: node ids fit 16 bits -> the compacted sequence takes 2 bytes per gene (out-of-range genes
+// are reported by k_path_costs; here they are truncated).
 template <bool SEQ16>
 __global__ void __launch_bounds__(LP_THREADS, 1)
 k_loop_closures_part(const int32_t* __restrict__ dna, uint32_t P, int A, int L, int T3 /*slots per partition*/,
                      uint32_t R /*pow2 partitions*/, gcp_params prm, gcp_map_consts mc,
-                     int32_t* __restrict__ seq /*[P][A*L] scratch*/,
+                     unsigned long long* __restrict__ rec_all /*[P][A*L] scratch: key48 << 16 | position*/,
                      const double* __restrict__ dist, const double* __restrict__ turn,
                      const uint32_t* __restrict__ cov, int32_t* __restrict__ lc_out,
                      double* __restrict__ obj, double* __restrict__ neg_cov_out, uint8_t* __restrict__ flags)
 {
+    typedef typename std::conditional<SEQ16, uint16_t, int32_t>::type seq_t;
     extern __shared__ __align__(16) unsigned char smem[];
+    const int AL = A * L;
+    const size_t tab_b = (size_t)T3 * 20, seq_b = (size_t)AL * sizeof(seq_t);
+    const size_t x_b = ((tab_b > seq_b ? tab_b : seq_b) + 15) & ~(size_t)15;
     unsigned long long* s_hkey = reinterpret_cast<unsigned long long*>(smem);       // [T3]
     uint32_t* s_hcnt = reinterpret_cast<uint32_t*>(s_hkey + T3);                     // [T3] count | flags
     uint32_t* s_head = s_hcnt + T3;                                                  // [T3] list head
     uint32_t* s_ownm = s_head + T3;                                                  // [T3] owner mask
-    uint16_t* s_next = reinterpret_cast<uint16_t*>(s_ownm + T3);                     // [A*L]
-    int*      s_lc   = reinterpret_cast<int*>(s_next + ((A * L + 1) & ~1));          // [A*A]
-    uint16_t* s_seq16 = reinterpret_cast<uint16_t*>(s_lc + A * A);                   // [A*L] if SEQ16
+    seq_t*    s_seq  = reinterpret_cast<seq_t*>(smem);                               // [A*L] until the buckets are written
+    uint16_t* s_next = reinterpret_cast<uint16_t*>(smem + x_b);                      // [A*L]
+    int*      s_lc   = reinterpret_cast<int*>(s_next + ((AL + 1) & ~1));             // [A*A]
     __shared__ int s_len[GCP_MAX_AGENTS], s_base[GCP_MAX_AGENTS + 1];
+    __shared__ uint32_t s_pcnt[LP_MAX_PARTS], s_pbase[LP_MAX_PARTS + 1];
     __shared__ int s_fail;
 
     const uint32_t org = blockIdx.x;
     if (org >= P) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int AL = A * L;
     const int32_t* d = dna + (size_t)org * AL;
-    int32_t* sq32 = SEQ16 ? nullptr : seq + (size_t)org * AL;
+    unsigned long long* rec = rec_all + (size_t)org * AL;
 
     if (tid == 0) s_fail = 0;
+    if (tid < LP_MAX_PARTS) s_pcnt[tid] = 0;
     for (int i = tid; i < A * A; i += LP_THREADS) s_lc[i] = 0;
     for (int a = warp; a < A; a += LP_NW) {
         int cnt = 0;
@@ -208,25 +221,51 @@ k_loop_closures_part(const int32_t* __restrict__ dna, uint32_t P, int A, int L, 
             const int g = (i < L) ? d[a * L + i] : -1;
             const bool v = g != -1;
             const uint32_t bal = __ballot_sync(FULL, v);
-            if (v) {
-                const int pos = run + __popc(bal & ((1u << lane) - 1u));
-                if (SEQ16) s_seq16[pos] = (uint16_t)g; else sq32[pos] = g;
-            }
+            if (v) s_seq[run + __popc(bal & ((1u << lane) - 1u))] = (seq_t)g;
             run += __popc(bal);
         }
     }
-    __syncthreads();                                             // the CTA's own global writes are visible to it
+    __syncthreads();
+    // bucket the positions by hash partition: count, prefix, scatter (lanes of a warp that hit
+    // the same partition share one shared-memory atomic)
+    for (int i0 = warp * 32; i0 < n; i0 += LP_THREADS) {
+        const int i = i0 + lane;
+        const uint32_t p = (i < n) ? (lp_hash(lp_key48(s_seq, i, n) + 1ull) & (R - 1)) : LP_NIL;
+        const uint32_t peers = __match_any_sync(FULL, p);
+        if (i < n && lane == (int)(__ffs(peers) - 1)) atomicAdd(&s_pcnt[p], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t b = 0;
+        for (uint32_t r = 0; r < R; ++r) { s_pbase[r] = b; b += s_pcnt[r]; s_pcnt[r] = 0; }
+        s_pbase[R] = b;
+    }
+    __syncthreads();
+    for (int i0 = warp * 32; i0 < n; i0 += LP_THREADS) {
+        const int i = i0 + lane;
+        unsigned long long key = 0;
+        uint32_t p = LP_NIL;
+        if (i < n) { key = lp_key48(s_seq, i, n); p = lp_hash(key + 1ull) & (R - 1); }
+        const uint32_t peers = __match_any_sync(FULL, p);
+        uint32_t base = 0;
+        const int leader = __ffs(peers) - 1;
+        if (i < n && lane == leader) base = atomicAdd(&s_pcnt[p], (uint32_t)__popc(peers));
+        base = __shfl_sync(FULL, base, leader);
+        if (i < n)
+            rec[s_pbase[p] + base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = (key << 16) | (unsigned long long)i;
+    }
+    __syncthreads();                                             // the CTA's own global writes are visible to it; s_seq is dead
 
     const int thresh = prm.solo_sep_thresh;
     for (uint32_t r = 0; r < R; ++r) {
         for (int h = tid; h < T3; h += LP_THREADS) { s_hkey[h] = 0ull; s_hcnt[h] = 0u; s_head[h] = LP_NIL; s_ownm[h] = 0u; }
         __syncthreads();
+        const unsigned long long* rc = rec + s_pbase[r];
+        const int m = (int)(s_pbase[r + 1] - s_pbase[r]);
         // pass 1: count the keys of this partition
-        for (int i = tid; i < n; i += LP_THREADS) {
-            const unsigned long long key = SEQ16 ? lp_key(s_seq16, i, n) : lp_key(sq32, i, n);
-            const uint32_t hv = lp_hash(key);
-            if ((hv & (R - 1)) != r) continue;
-            uint32_t h = __umulhi(hv, (uint32_t)T3);
+        for (int e = tid; e < m; e += LP_THREADS) {
+            const unsigned long long key = (rc[e] >> 16) + 1ull;                   // never 0
+            uint32_t h = __umulhi(lp_hash(key), (uint32_t)T3);
             int probes = 0;
             for (;;) {
                 const unsigned long long cur = ((volatile unsigned long long*)s_hkey)[h];
@@ -243,11 +282,11 @@ k_loop_closures_part(const int32_t* __restrict__ dna, uint32_t P, int A, int L, 
         __syncthreads();
         if (s_fail) break;                                       // uniform: reported through flags[3]
         // pass 2: members of duplicate groups link themselves, record owner and split flag
-        for (int i = tid; i < n; i += LP_THREADS) {
-            const unsigned long long key = SEQ16 ? lp_key(s_seq16, i, n) : lp_key(sq32, i, n);
-            const uint32_t hv = lp_hash(key);
-            if ((hv & (R - 1)) != r) continue;
-            uint32_t h = __umulhi(hv, (uint32_t)T3);
+        for (int e = tid; e < m; e += LP_THREADS) {
+            const unsigned long long v = rc[e];
+            const unsigned long long key = (v >> 16) + 1ull;
+            const int i = (int)(v & 0xFFFFull);
+            uint32_t h = __umulhi(lp_hash(key), (uint32_t)T3);
             while (s_hkey[h] != key) h = (h + 1 == (uint32_t)T3) ? 0u : h + 1;
             if ((s_hcnt[h] & 0xFFFFu) < 2u) continue;
             int a = 0;
@@ -259,11 +298,11 @@ k_loop_closures_part(const int32_t* __restrict__ dna, uint32_t P, int A, int L, 
         }
         __syncthreads();
         // pass 3: successor gap test (ascending consecutive positions)
-        for (int i = tid; i < n; i += LP_THREADS) {
-            const unsigned long long key = SEQ16 ? lp_key(s_seq16, i, n) : lp_key(sq32, i, n);
-            const uint32_t hv = lp_hash(key);
-            if ((hv & (R - 1)) != r) continue;
-            uint32_t h = __umulhi(hv, (uint32_t)T3);
+        for (int e = tid; e < m; e += LP_THREADS) {
+            const unsigned long long v = rc[e];
+            const unsigned long long key = (v >> 16) + 1ull;
+            const int i = (int)(v & 0xFFFFull);
+            uint32_t h = __umulhi(lp_hash(key), (uint32_t)T3);
             while (s_hkey[h] != key) h = (h + 1 == (uint32_t)T3) ? 0u : h + 1;
             const uint32_t c = s_hcnt[h];
             if ((c & 0xFFFFu) < 2u || (c & (1u << 16))) continue;
@@ -313,25 +352,23 @@ int launch_loop_closures_big(gcp_ctx* ctx, const int32_t* dna, uint32_t P, const
     if (ctx->force_lc_big != 1) {
         // hash-partitioned shared-memory kernel: pick the smallest R whose tables fit; keeping the
         // sequence in shared memory (16-bit node ids) only when that does not cost a partition
-        auto pick = [&](bool s16, int* T3_out, size_t* smem_out) -> uint32_t {
-            const size_t fixed = ((AL + 1) & ~(size_t)1) * 2 * (s16 ? 2 : 1) + (size_t)A * A * 4 + 64;
-            for (uint32_t R = 1; R <= 64; R <<= 1) {
-                if ((int)R < ctx->lc_min_parts) continue;
-                const int T3 = (int)((AL * 3) / (2 * R)) + 64 + (R > 1 ? (int)(AL / (4 * R)) : 0);   // slack: uneven partitions
-                const size_t smem = (size_t)T3 * 20 + fixed;
-                if (smem <= (size_t)ctx->max_smem_optin) { *T3_out = T3; *smem_out = smem; return R; }
-            }
-            return 0;
-        };
-        int T3a = 0, T3b = 0; size_t sma = 0, smb = 0;
-        const uint32_t Ra = ctx->t.N <= 65536 ? pick(true, &T3a, &sma) : 0;
-        const uint32_t Rb = pick(false, &T3b, &smb);
-        const bool seq16 = Ra != 0 && (Rb == 0 || Ra <= Rb);
-        const uint32_t R = seq16 ? Ra : Rb;
-        const int T3 = seq16 ? T3a : T3b;
-        const size_t smem = seq16 ? sma : smb;
+        const bool seq16 = ctx->t.N <= 65536;
+        const size_t seq_b = AL * (seq16 ? 2 : 4);
+        const size_t fixed = ((AL + 1) & ~(size_t)1) * 2 + (size_t)A * A * 4 + 64;
+        uint32_t R = 0; int T3 = 0; size_t smem = 0;
+        for (uint32_t Rt = 1; Rt <= (uint32_t)LP_MAX_PARTS; Rt <<= 1) {
+            if ((int)Rt < ctx->lc_min_parts) continue;
+            const int T3t = (int)((AL * 3) / (2 * Rt)) + 64 + (Rt > 1 ? (int)(AL / (4 * Rt)) : 0);   // slack: uneven partitions
+            const size_t tab = (size_t)T3t * 20;
+            const size_t need_s = (((tab > seq_b ? tab : seq_b) + 15) & ~(size_t)15) + fixed;
+            if (need_s <= (size_t)ctx->max_smem_optin) { R = Rt; T3 = T3t; smem = need_s; break; }
+        }
         if (R != 0) {
-            const size_t need = seq16 ? 256 : al256((size_t)P * AL * 4);
+            // record scratch: 8 bytes per gene, at most 2 GiB (organisms go through in chunks)
+            uint32_t chunk = (uint32_t)(((size_t)2 << 30) / (AL * 8));
+            if (chunk < 1) chunk = 1;
+            if (chunk > P) chunk = P;
+            const size_t need = al256((size_t)chunk * AL * 8);
             if (ctx->lcb_scratch_bytes < need) {
                 if (ctx->lcb_scratch) cudaFree(ctx->lcb_scratch);
                 ctx->lcb_scratch = nullptr; ctx->lcb_scratch_bytes = 0;
@@ -339,17 +376,27 @@ int launch_loop_closures_big(gcp_ctx* ctx, const int32_t* dna, uint32_t P, const
                 ctx->lcb_scratch_bytes = need;
             }
             StageTimer tm(ctx, 2, st);
-            int32_t* seq = reinterpret_cast<int32_t*>(ctx->lcb_scratch);
-            if (seq16) {
-                GCP_CUDA(ctx, cudaFuncSetAttribute(k_loop_closures_part<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_loop_closures_part<true><<<P, LP_THREADS, smem, st>>>(dna, P, A, L, T3, R, ctx->p, ctx->mc, seq, dist,
-                                                                        turn, cov, lc_out, obj, neg_cov, flags);
-            } else {
-                GCP_CUDA(ctx, cudaFuncSetAttribute(k_loop_closures_part<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_loop_closures_part<false><<<P, LP_THREADS, smem, st>>>(dna, P, A, L, T3, R, ctx->p, ctx->mc, seq, dist,
-                                                                         turn, cov, lc_out, obj, neg_cov, flags);
+            unsigned long long* rec = reinterpret_cast<unsigned long long*>(ctx->lcb_scratch);
+            if (seq16) GCP_CUDA(ctx, cudaFuncSetAttribute(k_loop_closures_part<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else       GCP_CUDA(ctx, cudaFuncSetAttribute(k_loop_closures_part<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            for (uint32_t o0 = 0; o0 < P; o0 += chunk) {
+                const uint32_t n_org = (P - o0 < chunk) ? (P - o0) : chunk;
+                const int32_t* dna_c = dna + (size_t)o0 * AL;
+                const double* dist_c = dist + (size_t)o0 * A;
+                const double* turn_c = turn + (size_t)o0 * A;
+                const uint32_t* cov_c = cov + (size_t)o0 * 8;
+                int32_t* lc_c = lc_out ? lc_out + (size_t)o0 * A * A : nullptr;
+                double* obj_c = obj ? obj + (size_t)o0 * 2 : nullptr;
+                double* neg_c = neg_cov ? neg_cov + (size_t)o0 : nullptr;
+                uint8_t* flg_c = flags ? flags + (size_t)o0 * 4 : nullptr;
+                if (seq16)
+                    k_loop_closures_part<true><<<n_org, LP_THREADS, smem, st>>>(dna_c, n_org, A, L, T3, R, ctx->p, ctx->mc, rec,
+                                                                                dist_c, turn_c, cov_c, lc_c, obj_c, neg_c, flg_c);
+                else
+                    k_loop_closures_part<false><<<n_org, LP_THREADS, smem, st>>>(dna_c, n_org, A, L, T3, R, ctx->p, ctx->mc, rec,
+                                                                                 dist_c, turn_c, cov_c, lc_c, obj_c, neg_c, flg_c);
+                ctx->launches++;
             }
-            ctx->launches++;
             GCP_CUDA(ctx, cudaGetLastError());
             return 0;
         }
