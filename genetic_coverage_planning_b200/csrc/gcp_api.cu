@@ -64,6 +64,7 @@ void gcp_destroy(gcp_ctx* c)
     if (c->stage_dev) cudaFree(c->stage_dev);
     if (c->vary_scratch) cudaFree(c->vary_scratch);
     if (c->lcb_scratch) cudaFree(c->lcb_scratch);
+    if (c->cov_scratch) cudaFree(c->cov_scratch);
     for (int s = 0; s < 2; ++s) if (c->hstream[s]) cudaStreamDestroy(c->hstream[s]);
     for (int s = 0; s < GCP_NUM_STAGES; ++s) { cudaEventDestroy(c->ev_beg[s]); cudaEventDestroy(c->ev_end[s]); }
     delete c;
@@ -564,6 +565,7 @@ int gcp_set_option(gcp_ctx* c, const char* name, int64_t value)
     else if (!strcmp(name, "lc_min_parts")) c->lc_min_parts = (int)value;
     else if (!strcmp(name, "cov_threads")) c->cov_threads = (int)value;
     else if (!strcmp(name, "cov_dedup")) c->cov_dedup = (int)value;
+    else if (!strcmp(name, "cov_buckets")) c->cov_buckets = (int)value;
     else return gcp_fail(c, -1, "gcp_set_option: unknown option '%s'", name);
     return 0;
 }

@@ -64,12 +64,14 @@ struct gcp_ctx {
     // host-eval staging (gcp_eval_host)
     void* stage_dev = nullptr; size_t stage_bytes = 0;
     void* vary_scratch = nullptr; size_t vary_scratch_bytes = 0;   // mutation row list (gcp_vary.cu)
-    void* lcb_scratch = nullptr; size_t lcb_scratch_bytes = 0;     // sort buffers (gcp_lcbig.cu)
+    void* lcb_scratch = nullptr; size_t lcb_scratch_bytes = 0;     // sort buffers / position records (gcp_lcbig.cu)
+    void* cov_scratch = nullptr; size_t cov_scratch_bytes = 0;     // item buckets of long genomes (gcp_fused.cu)
     uint32_t vary_org_offset = 0;   // population shards: global id of local organism 0 (Philox keys)
     int force_lc_big = 0;    // testing: always take the sort-based loop-closure path
     cudaStream_t hstream[2] = {};
     // coverage kernel tuning (0 = auto)
     int cov_table = 0, cov_maxpairs = 0;
+    int cov_buckets = 1;     // 1: long genomes bucket their items by hash partition once (else: R scanning passes)
     int cov_dedup = 1;       // 1: revisited edges are dropped before the coverage union (phase B0)
     int cov_threads = 0;     // tuning: CTA size of k_cov_quarters (256 / 512 / 1024; 0 = auto)
     int lc_min_parts = 0;    // tuning: at least this many hash partitions in k_loop_closures_part

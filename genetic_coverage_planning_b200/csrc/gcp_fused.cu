@@ -33,14 +33,16 @@ struct FusedShape {
 //   n_cov: covered mask pixels with g == 0, n_wg: sum of (255 - g) over covered gray mask pixels
 //   (per-thread partial sums; the caller reduces them).  s_x: T*20 + MAXP*8 + 32 bytes.
 // ============================================================================
-template <int KF_THREADS, bool HAS_GRAY>
+template <int KF_THREADS, bool HAS_GRAY, bool BUCKETS = false>
 __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const GcpTables& t,
                                                   int T, int MAXP, uint32_t R0, uint32_t DS, unsigned char* s_x,
-                                                  uint32_t& n_cov, uint32_t& n_wg, bool& failed)
+                                                  uint32_t& n_cov, uint32_t& n_wg, bool& failed,
+                                                  uint2* rec = nullptr, uint32_t rec_cap = 0)
 {
     constexpr int KF_NW = KF_THREADS / 32;
     __shared__ uint32_t s_npairs, s_overflow, s_group;
     __shared__ uint32_t s_wsum[KF_NW];
+    __shared__ uint32_t s_pcnt[64], s_pbase[65];               // item buckets per hash partition (long genomes)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t* s_keys = reinterpret_cast<uint32_t*>(s_x);      // [T] block id + 1
     uint32_t* s_cq   = s_keys + T;                             // [T][4] count -> count<<16 | base
@@ -76,13 +78,105 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
     for (;;) {                                   // retry loop over partition count R
         n_cov = 0; n_wg = 0;
         bool overflow = false;
+        // ---- long genomes (R > 1) with a scratch array: bucket the item descriptors by hash
+        //      partition ONCE (count, prefix, scatter; lanes that hit the same partition share
+        //      one shared atomic), so that every partition pass below reads its own items
+        //      linearly instead of re-scanning and filtering all of them
+        bool bucketed = false;
+        if (BUCKETS && R > 1 && R <= 64 && rec != nullptr) {
+            auto scan_items = [&](auto&& fn) {
+                for (int s0 = warp * 32; s0 < AL; s0 += KF_NW * 32) {
+                    const int s = s0 + lane;
+                    uint32_t lo = 0, n = 0;
+                    if (s < AL) { const uint32_t inf = info[s]; lo = inf & 0x03FFFFFFu; n = inf >> 26; }
+                    uint32_t incl = n;
+                    #pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        uint32_t v = __shfl_up_sync(FULL, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                    const uint32_t total = __shfl_sync(FULL, incl, 31);
+                    const uint32_t excl = incl - n;
+                    for (uint32_t j0 = 0; j0 < total; j0 += 32) {
+                        const uint32_t j = j0 + lane;
+                        int a = 0, b = 31;
+                        #pragma unroll
+                        for (int it = 0; it < 5; ++it) {
+                            const int mid = (a + b) >> 1;
+                            const uint32_t v = __shfl_sync(FULL, incl, mid);
+                            if (v > j) b = mid; else a = mid + 1;
+                        }
+                        a = min(a, 31);
+                        const uint32_t ex = __shfl_sync(FULL, excl, a), dlo = __shfl_sync(FULL, lo, a);
+                        uint2 dsc = make_uint2(0, 0);
+                        if (j < total) dsc = __ldg(t.m_q_desc + dlo + (j - ex));
+                        fn(j < total, dsc);
+                    }
+                }
+            };
+            if (tid < 64) s_pcnt[tid] = 0;
+            __syncthreads();
+            scan_items([&](bool valid, uint2 dsc) {
+                const uint32_t p = valid ? (part_block(dsc.x >> 2) & (R - 1)) : KF_NIL;
+                const uint32_t peers = __match_any_sync(FULL, p);
+                if (valid && lane == (int)(__ffs(peers) - 1)) atomicAdd(&s_pcnt[p], (uint32_t)__popc(peers));
+            });
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t b = 0;
+                for (uint32_t r = 0; r < R; ++r) { s_pbase[r] = b; b += s_pcnt[r]; s_pcnt[r] = 0; }
+                s_pbase[R] = b;
+            }
+            __syncthreads();
+            if (s_pbase[R] <= rec_cap) {         // else: more items than the scratch holds -> scanning passes
+                scan_items([&](bool valid, uint2 dsc) {
+                    const uint32_t p = valid ? (part_block(dsc.x >> 2) & (R - 1)) : KF_NIL;
+                    const uint32_t peers = __match_any_sync(FULL, p);
+                    const int leader = __ffs(peers) - 1;
+                    uint32_t base = 0;
+                    if (valid && lane == leader) base = atomicAdd(&s_pcnt[p], (uint32_t)__popc(peers));
+                    base = __shfl_sync(FULL, base, leader);
+                    if (valid) rec[s_pbase[p] + base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = dsc;
+                });
+                bucketed = true;
+            }
+            __syncthreads();                     // the CTA's own global writes are visible to it
+        }
         for (uint32_t r = 0; r < R && !overflow; ++r) {
             for (int i = tid; i < T; i += KF_THREADS) s_keys[i] = 0;
             for (int i = tid; i < 4 * T; i += KF_THREADS) s_cq[i] = 0;
             if (tid == 0) { s_npairs = 0; s_overflow = 0; s_group = 0; }
             __syncthreads();
             // ---- B1: slot + rank for every quarter item ----
-            {
+            if (BUCKETS && bucketed) {
+                const uint2* rc = rec + s_pbase[r];
+                const uint32_t m = s_pbase[r + 1] - s_pbase[r];
+                if (m > (uint32_t)MAXP) {
+                    if (tid == 0) s_overflow = 1;
+                } else {
+                    for (uint32_t j = tid; j < m; j += KF_THREADS) {
+                        const uint2 dsc = rc[j];
+                        const uint32_t blk = dsc.x >> 2, q = dsc.x & 3u;
+                        const uint32_t key = blk + 1;
+                        uint32_t h = hash_block(blk) >> (32 - logT);
+                        int probes = 0;
+                        for (;;) {
+                            const uint32_t cur = ((volatile uint32_t*)s_keys)[h];
+                            if (cur == key) break;
+                            if (cur == 0) {
+                                const uint32_t old = atomicCAS(&s_keys[h], 0u, key);
+                                if (old == 0 || old == key) break;
+                            }
+                            h = (h + 1) & (T - 1);
+                            if (++probes >= T) { s_overflow = 1; break; }
+                        }
+                        const uint32_t rank = (probes < T) ? atomicAdd(&s_cq[4 * h + q], 1u) : 0u;
+                        s_pay[j] = dsc.y;
+                        s_sr[j] = (h << 18) | (q << 16) | rank;
+                    }
+                    if (tid == 0) s_npairs = m;
+                }
+            } else {
                 const int bw = warp, nbw = KF_NW;
                 for (int s0 = bw * 32; s0 < AL; s0 += nbw * 32) {
                     const int s = s0 + lane;
@@ -690,7 +784,8 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
 template <int KF_THREADS, bool HAS_GRAY>
 __global__ void __launch_bounds__(KF_THREADS, KF_THREADS == 256 ? 5 : KF_THREADS == 512 ? 2 : 1)
 k_cov_quarters(uint32_t* step_qinfo, uint32_t P, GcpTables t, int AL, int T, int MAXP,
-               uint32_t R0, uint32_t DS, uint32_t* __restrict__ cov, uint8_t* __restrict__ flags)
+               uint32_t R0, uint32_t DS, uint2* rec_all, uint32_t rec_cap,
+               uint32_t* __restrict__ cov, uint8_t* __restrict__ flags)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint32_t s_total, s_totalw;
@@ -700,8 +795,9 @@ k_cov_quarters(uint32_t* step_qinfo, uint32_t P, GcpTables t, int AL, int T, int
     if (tid == 0) { s_total = 0; s_totalw = 0; }
     uint32_t n_cov, n_wg;
     bool failed;
-    coverage_quarters<KF_THREADS, HAS_GRAY>(step_qinfo + (size_t)org * AL, AL, t, T, MAXP, R0, DS, smem,
-                                            n_cov, n_wg, failed);
+    coverage_quarters<KF_THREADS, HAS_GRAY, true>(step_qinfo + (size_t)org * AL, AL, t, T, MAXP, R0, DS, smem,
+                                                  n_cov, n_wg, failed,
+                                                  rec_all ? rec_all + (size_t)org * rec_cap : nullptr, rec_cap);
     uint32_t v = n_cov, vw = n_wg;
     #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(FULL, v, o); vw += __shfl_xor_sync(FULL, vw, o); }
@@ -738,19 +834,43 @@ int launch_coverage_quarters(gcp_ctx* ctx, uint32_t* step_qinfo, uint32_t P, uin
     uint32_t DS = 1;
     while ((size_t)DS * 2 * 4 <= (size_t)T * 20 + (size_t)maxp * 8) DS <<= 1;
     if ((size_t)DS * 4 < (size_t)AL * 5 || ctx->cov_dedup == 0) DS = 0;
+    // long genomes (R0 > 1): scratch for the item buckets, 3 * A*L descriptors per organism, at most
+    // 2 GiB (organisms go through in chunks); an organism with more items falls back to scanning passes
+    uint2* rec = nullptr;
+    uint32_t rec_cap = 0, chunk = P;
+    if (R0 > 1 && ctx->cov_buckets) {
+        rec_cap = 3u * (uint32_t)AL;
+        chunk = (uint32_t)(((size_t)2 << 30) / ((size_t)rec_cap * 8));
+        if (chunk < 1) chunk = 1;
+        if (chunk > P) chunk = P;
+        const size_t need = (size_t)chunk * rec_cap * 8;
+        if (ctx->cov_scratch_bytes < need) {
+            if (ctx->cov_scratch) cudaFree(ctx->cov_scratch);
+            ctx->cov_scratch = nullptr; ctx->cov_scratch_bytes = 0;
+            GCP_CUDA(ctx, cudaMalloc(&ctx->cov_scratch, need));
+            ctx->cov_scratch_bytes = need;
+        }
+        rec = reinterpret_cast<uint2*>(ctx->cov_scratch);
+    }
     StageTimer tm(ctx, 1, st);
     const bool gray = ctx->n_gray > 0;
 #define GCP_LAUNCH_COVQ(TH, GRAY)                                                                      \
     do {                                                                                               \
         GCP_CUDA(ctx, cudaFuncSetAttribute(k_cov_quarters<TH, GRAY>,                                   \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-        k_cov_quarters<TH, GRAY><<<P, TH, smem, st>>>(step_qinfo, P, ctx->t, AL, T, maxp, R0, DS, cov, flags); \
+        for (uint32_t o0 = 0; o0 < P; o0 += chunk) {                                                   \
+            const uint32_t n_org = (P - o0 < chunk) ? (P - o0) : chunk;                                \
+            k_cov_quarters<TH, GRAY><<<n_org, TH, smem, st>>>(step_qinfo + (size_t)o0 * AL, n_org, ctx->t, AL, T, \
+                                                              maxp, R0, DS, rec, rec_cap,               \
+                                                              cov + (size_t)o0 * 8,                    \
+                                                              flags ? flags + (size_t)o0 * 4 : nullptr); \
+            ctx->launches++;                                                                           \
+        }                                                                                              \
     } while (0)
     if (threads == 256) { if (gray) GCP_LAUNCH_COVQ(256, true); else GCP_LAUNCH_COVQ(256, false); }
     else if (threads == 512) { if (gray) GCP_LAUNCH_COVQ(512, true); else GCP_LAUNCH_COVQ(512, false); }
     else                { if (gray) GCP_LAUNCH_COVQ(1024, true); else GCP_LAUNCH_COVQ(1024, false); }
 #undef GCP_LAUNCH_COVQ
-    ctx->launches++;
     GCP_CUDA(ctx, cudaGetLastError());
     return 0;
 }
