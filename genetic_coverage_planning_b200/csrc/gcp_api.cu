@@ -340,8 +340,8 @@ int gcp_eval(gcp_ctx* c, const int32_t* dna, uint32_t P, const gcp_eval_out* out
     if (out->cov) cov = out->cov;
     if (out->flags) flags = out->flags;
     cudaStream_t st = (cudaStream_t)stream;
-    if ((r = launch_path_costs(c, dna, P, edge_ids, fast_staged ? step_info : nullptr, dist, turn,
-                               flags, st, fast_q ? 1 : 0))) return r;
+    if ((r = launch_path_costs(c, dna, P, fast_staged ? nullptr : edge_ids, fast_staged ? step_info : nullptr,
+                               dist, turn, flags, st, fast_q ? 1 : 0))) return r;
     if (fast_q) {
         if ((r = launch_coverage_quarters(c, step_info, P, cov, flags, st))) return r;
     } else if (fast_staged) {

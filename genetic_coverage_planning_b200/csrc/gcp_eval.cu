@@ -17,9 +17,9 @@
 //   per-agent sums are sequential fp64 adds in step order (mappy.py:351-352) so the
 //   result is bit-identical to the reference's `+=` loop.
 // ============================================================================
-constexpr int K1_THREADS = 256;
 constexpr int K1_STAGE_ELEMS = 2048;   // double2 entries (32 KB)
 
+template <int K1_THREADS>
 __global__ void __launch_bounds__(K1_THREADS)
 k_path_costs(const int32_t* __restrict__ dna, uint32_t P, GcpTables t, int A, int L,
              uint32_t* __restrict__ edge_ids, uint32_t* __restrict__ step_info,
@@ -65,16 +65,27 @@ k_path_costs(const int32_t* __restrict__ dna, uint32_t P, GcpTables t, int A, in
                 const bool sentinel = nx < 0;
                 if (nx < 0) nx += (int)t.N;                  // numpy wrap: -1 -> N-1
                 if (w < t.N && nx >= 0 && (uint32_t)nx < t.N) {
-                    const uint32_t lo = t.row_ptr[w], hi = t.row_ptr[w + 1];
+                    const uint32_t lo = __ldg(t.row_ptr + w);
                     e = t.E + w;                             // null edge unless found
                     bool found = false;
-                    for (uint32_t q = lo; q < hi; ++q)
-                        if (t.col[q] == (uint32_t)nx) { e = q; found = true; break; }
+                    if (t.adjc16) {                          // 8 x u16 out-neighbours in one 16-B load
+                        const uint4 q = __ldg(t.adjc16 + w);
+                        const uint32_t pat = (uint32_t)nx * 0x00010001u;
+                        const uint32_t m0 = __vcmpeq2(q.x, pat), m1 = __vcmpeq2(q.y, pat);
+                        const uint32_t m2 = __vcmpeq2(q.z, pat), m3 = __vcmpeq2(q.w, pat);
+                        const uint32_t hit = ((m0 & 1u) | ((m0 >> 15) & 2u)) | (((m1 & 1u) | ((m1 >> 15) & 2u)) << 2) |
+                                             (((m2 & 1u) | ((m2 >> 15) & 2u)) << 4) | (((m3 & 1u) | ((m3 >> 15) & 2u)) << 6);
+                        if (hit) { e = lo + (uint32_t)(__ffs(hit) - 1); found = true; }
+                    } else {
+                        const uint32_t hi = __ldg(t.row_ptr + w + 1);
+                        for (uint32_t q = lo; q < hi; ++q)
+                            if (__ldg(t.col + q) == (uint32_t)nx) { e = q; found = true; break; }
+                    }
                     if (!found && !sentinel) atomicOr(&s_bad, 1);
-                    c = t.edge_cost[e];
+                    c = __ldg(t.edge_cost + e);
                 }
             }
-            edge_ids[(size_t)org * AL + a * L + i] = e;
+            if (edge_ids) edge_ids[(size_t)org * AL + a * L + i] = e;
             if (step_info)
                 step_info[(size_t)org * AL + a * L + i] =
                     (e != GCP_INVALID_EDGE) ? __ldg(info_table + e) : 0u;
@@ -108,9 +119,13 @@ int launch_path_costs(gcp_ctx* ctx, const int32_t* dna, uint32_t P, uint32_t* ed
     if (step_info && !ctx->have_masked)
         return gcp_fail(ctx, -1, "step_info requested but no masked footprint store uploaded");
     StageTimer tm(ctx, 0, st);
-    k_path_costs<<<P, K1_THREADS, 0, st>>>(dna, P, ctx->t, ctx->p.num_agents, ctx->p.max_dna_len,
-                                           edge_ids, step_info,
-                                           quarter_info ? ctx->t.m_q_info : ctx->t.m_sub_info, dist, turn, flags);
+    const uint32_t* info_table = quarter_info ? ctx->t.m_q_info : ctx->t.m_sub_info;
+    if (ctx->p.num_agents * ctx->p.max_dna_len > 4096)      // long genomes: more lookups in flight per organism
+        k_path_costs<1024><<<P, 1024, 0, st>>>(dna, P, ctx->t, ctx->p.num_agents, ctx->p.max_dna_len,
+                                               edge_ids, step_info, info_table, dist, turn, flags);
+    else
+        k_path_costs<256><<<P, 256, 0, st>>>(dna, P, ctx->t, ctx->p.num_agents, ctx->p.max_dna_len,
+                                             edge_ids, step_info, info_table, dist, turn, flags);
     ctx->launches++;
     GCP_CUDA(ctx, cudaGetLastError());
     return 0;

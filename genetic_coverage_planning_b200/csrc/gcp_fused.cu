@@ -154,8 +154,15 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
                 if (m > (uint32_t)MAXP) {
                     if (tid == 0) s_overflow = 1;
                 } else {
-                    for (uint32_t j = tid; j < m; j += KF_THREADS) {
-                        const uint2 dsc = rc[j];
+                    for (uint32_t j0 = tid; j0 < m; j0 += 4 * KF_THREADS) {
+                      uint2 d4[4];                                          // four descriptor loads in flight
+                      #pragma unroll
+                      for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + u * KF_THREADS; d4[u] = (j < m) ? rc[j] : make_uint2(0, 0); }
+                      #pragma unroll
+                      for (int u = 0; u < 4; ++u) {
+                        const uint32_t j = j0 + u * KF_THREADS;
+                        if (j >= m) break;
+                        const uint2 dsc = d4[u];
                         const uint32_t blk = dsc.x >> 2, q = dsc.x & 3u;
                         const uint32_t key = blk + 1;
                         uint32_t h = hash_block(blk) >> (32 - logT);
@@ -173,6 +180,7 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
                         const uint32_t rank = (probes < T) ? atomicAdd(&s_cq[4 * h + q], 1u) : 0u;
                         s_pay[j] = dsc.y;
                         s_sr[j] = (h << 18) | (q << 16) | rank;
+                      }
                     }
                     if (tid == 0) s_npairs = m;
                 }

@@ -263,8 +263,14 @@ k_loop_closures_part(const int32_t* __restrict__ dna, uint32_t P, int A, int L, 
         const unsigned long long* rc = rec + s_pbase[r];
         const int m = (int)(s_pbase[r + 1] - s_pbase[r]);
         // pass 1: count the keys of this partition
-        for (int e = tid; e < m; e += LP_THREADS) {
-            const unsigned long long key = (rc[e] >> 16) + 1ull;                   // never 0
+        for (int e0 = tid; e0 < m; e0 += 4 * LP_THREADS) {
+          unsigned long long v4[4];                                                // four record loads in flight
+          #pragma unroll
+          for (int u = 0; u < 4; ++u) { const int e = e0 + u * LP_THREADS; v4[u] = (e < m) ? rc[e] : 0ull; }
+          #pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (e0 + u * LP_THREADS >= m) break;
+            const unsigned long long key = (v4[u] >> 16) + 1ull;                   // never 0
             uint32_t h = __umulhi(lp_hash(key), (uint32_t)T3);
             int probes = 0;
             for (;;) {
@@ -278,12 +284,19 @@ k_loop_closures_part(const int32_t* __restrict__ dna, uint32_t P, int A, int L, 
                 if (++probes >= T3) { s_fail = 1; break; }       // partition far larger than expected
             }
             if (probes < T3) atomicAdd(&s_hcnt[h], 1u);
+          }
         }
         __syncthreads();
         if (s_fail) break;                                       // uniform: reported through flags[3]
         // pass 2: members of duplicate groups link themselves, record owner and split flag
-        for (int e = tid; e < m; e += LP_THREADS) {
-            const unsigned long long v = rc[e];
+        for (int e0 = tid; e0 < m; e0 += 4 * LP_THREADS) {
+          unsigned long long v4[4];
+          #pragma unroll
+          for (int u = 0; u < 4; ++u) { const int e = e0 + u * LP_THREADS; v4[u] = (e < m) ? rc[e] : 0ull; }
+          #pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (e0 + u * LP_THREADS >= m) break;
+            const unsigned long long v = v4[u];
             const unsigned long long key = (v >> 16) + 1ull;
             const int i = (int)(v & 0xFFFFull);
             uint32_t h = __umulhi(lp_hash(key), (uint32_t)T3);
@@ -295,11 +308,18 @@ k_loop_closures_part(const int32_t* __restrict__ dna, uint32_t P, int A, int L, 
             s_next[i] = (uint16_t)atomicExch(&s_head[h], (uint32_t)i);      // NIL -> 0xFFFF
             atomicOr(&s_ownm[h], 1u << a);
             if (a >= 1 && i == s_base[a]) atomicOr(&s_hcnt[h], 1u << 16);   // touches a path split (F10)
+          }
         }
         __syncthreads();
         // pass 3: successor gap test (ascending consecutive positions)
-        for (int e = tid; e < m; e += LP_THREADS) {
-            const unsigned long long v = rc[e];
+        for (int e0 = tid; e0 < m; e0 += 4 * LP_THREADS) {
+          unsigned long long v4[4];
+          #pragma unroll
+          for (int u = 0; u < 4; ++u) { const int e = e0 + u * LP_THREADS; v4[u] = (e < m) ? rc[e] : 0ull; }
+          #pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (e0 + u * LP_THREADS >= m) break;
+            const unsigned long long v = v4[u];
             const unsigned long long key = (v >> 16) + 1ull;
             const int i = (int)(v & 0xFFFFull);
             uint32_t h = __umulhi(lp_hash(key), (uint32_t)T3);
@@ -310,6 +330,7 @@ k_loop_closures_part(const int32_t* __restrict__ dna, uint32_t P, int A, int L, 
             for (uint32_t j = s_head[h]; j != 0xFFFFu && j != LP_NIL; j = s_next[j])
                 if (j > (uint32_t)i && j < succ) succ = j;
             if (succ != 0xFFFFFFFFu && (int)(succ - (uint32_t)i) > thresh) atomicOr(&s_hcnt[h], 1u << 17);
+          }
         }
         __syncthreads();
         // pass 4: one thread per duplicate group updates lc_mat
