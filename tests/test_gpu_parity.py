@@ -97,6 +97,31 @@ def test_agent_counts_golden(golden_dir, A):
     _check_against_golden(eng, z)
 
 
+# ---- synthetic BINARY world evaluated by the unmodified reference (make_golden_synth.py): the
+#      fused kernel's binary instantiation and the staged kernels against the reference itself,
+#      -coverage bit-exact
+@pytest.fixture(scope="module")
+def world_synth_ref(golden_dir):
+    return World.load_npz(os.path.join(golden_dir, "world_synth.npz"))
+
+
+def test_eval_golden_synth_binary(world_synth_ref, golden_dir):
+    eng = _engine(world_synth_ref)
+    _check_against_golden(eng, np.load(os.path.join(golden_dir, "eval_synth.npz")), exact_cov=True)
+    _check_against_golden(eng, np.load(os.path.join(golden_dir, "edge_synth.npz")), exact_cov=True)
+
+
+def test_agent_count_golden_synth_binary(world_synth_ref, golden_dir):
+    z = np.load(os.path.join(golden_dir, "eval_synth_A3.npz"))
+    w = World.load_npz(os.path.join(golden_dir, "world_synth.npz"))
+    w.map_params['solo_sep_thresh'] = int(z['solo_sep_thresh'])
+    op = dict(w.org_params)
+    op.update(min_solo_lcs=int(z['min_solo_lcs']), min_comb_lcs=int(z['min_comb_lcs']),
+              max_dna_len=int(z['max_dna_len']), start_idx=w.org_params['start_idx'][:3])
+    eng = _engine(w, op, num_agents=3)
+    _check_against_golden(eng, z, exact_cov=True)
+
+
 def _random_dna(world, P, A, L, seed, p_nonedge=0.02):
     """Random walks on the graph with ragged lengths, a few teleports (non-edges),
     some full-length rows, some empty rows."""

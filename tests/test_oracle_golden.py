@@ -95,3 +95,32 @@ def test_sweep_maximin_equals_double_loop(golden_dir):
         for gen in (0, 50, 100):
             assert np.array_equal(fo.rack_n_stack_sweep(objs, gen, gp),
                                   fo.rack_n_stack(objs, gen, gp))
+
+
+# ---- synthetic BINARY world (the benchmark's world type), evaluated by the unmodified reference on
+#      dense tables it built itself (tests/golden/make_golden_synth.py)
+@pytest.fixture(scope="module")
+def world_synth(golden_dir):
+    return World.load_npz(os.path.join(golden_dir, "world_synth.npz"))
+
+
+def test_synth_world_is_binary(world_synth):
+    assert set(np.unique(world_synth.img)) <= {0.0, 1.0}
+
+
+def test_eval_synth(world_synth, golden_dir):
+    _check_eval(world_synth, _load(golden_dir, "eval_synth.npz"), n=12)
+
+
+def test_edge_cases_synth(world_synth, golden_dir):
+    _check_eval(world_synth, _load(golden_dir, "edge_synth.npz"))
+
+
+def test_agent_count_synth(world_synth, golden_dir):
+    z = _load(golden_dir, "eval_synth_A3.npz")
+    w = World.load_npz(os.path.join(golden_dir, "world_synth.npz"))
+    w.map_params['solo_sep_thresh'] = int(z['solo_sep_thresh'])
+    op = dict(w.org_params)
+    op.update(min_solo_lcs=int(z['min_solo_lcs']), min_comb_lcs=int(z['min_comb_lcs']),
+              max_dna_len=int(z['max_dna_len']))
+    _check_eval(w, z, op, n=8)
