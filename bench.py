@@ -403,7 +403,10 @@ def main():
                                             "+ evaluation of P children + maximin over 2P + stable "
                                             "order + survivor gather; no host round trip",
                                 "last_generation_stage_ms": last,
-                                "mean_coverage_after": float((-par_obj[:, 0]).mean().item())}
+                                # objective 0 is zeroed for organisms that miss the loop-closure
+                                # constraints (geneticalgorithm.py:197-200); agents started from six
+                                # spread corners of a 4096^2 map rarely meet, so this is ~0 here
+                                "mean_constrained_coverage_after": float((-par_obj[:, 0]).mean().item())}
         if distributed:
             from genetic_coverage_planning_b200.distributed import DistributedRanker
             ranker = DistributedRanker(eng)
