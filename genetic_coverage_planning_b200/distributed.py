@@ -36,7 +36,7 @@ def bind_to_gpu_numa_node(device=0):
             return node if cpus else None
         os.sched_setaffinity(0, cpus)
         return node
-    except (OSError, ValueError, AttributeError):
+    except Exception:                 # no sysfs topology, restricted cpuset, old torch: leave the process alone
         return None
 
 

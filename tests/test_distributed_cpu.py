@@ -84,3 +84,12 @@ def test_two_rank_ranking_matches_single():
         assert np.array_equal(glad, objs)
         assert np.array_equal(fit, want_fit)
         assert np.array_equal(order, want_order)
+
+
+def test_numa_binding_is_a_noop_without_topology():
+    """bind_to_gpu_numa_node must never raise or change affinity when there is no GPU / sysfs node."""
+    import os
+    from genetic_coverage_planning_b200.distributed import bind_to_gpu_numa_node
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa_node(0) is None
+    assert os.sched_getaffinity(0) == before
