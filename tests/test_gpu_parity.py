@@ -6,6 +6,7 @@ import os
 
 import numpy as np
 import pytest
+import torch
 
 import fitness_oracle as fo
 from world import World
@@ -162,6 +163,39 @@ def test_eval_vs_oracle_random(eng_big, world_big):
         assert det['obj'][1] == obj[k, 1]
         assert abs(det['obj'][0] - obj[k, 0]) <= COV_TOL_GRAY
         assert fo.traversable(world_big, d) == flags[k, 1], k
+
+
+@pytest.mark.parametrize("A,L", [(1, 3), (1, 33), (2, 4), (3, 64), (5, 97), (7, 150), (8, 250), (9, 40), (16, 31), (32, 20)])
+def test_shape_sweep_vs_oracle(world_synth_ref, A, L):
+    """Odd genome shapes (runtime shared-memory layouts, 1..32 agents, rows of 2..250 genes) with ragged,
+    empty, full and teleporting rows plus interior -1 holes: objectives-only kernel (fused), the staged
+    kernels, the general kernels and int16 chromosomes against the oracle, bit-exact (binary map)."""
+    w = world_synth_ref
+    op = dict(w.org_params)
+    op.update(max_dna_len=L, start_idx=list(w.org_params['start_idx'][:1]) * A, min_solo_lcs=0, min_comb_lcs=0)
+    eng = _engine(w, op, num_agents=A)
+    dna = _random_dna(w, 24, A, L, seed=100 * A + L, p_nonedge=0.05)
+    rng = np.random.RandomState(A + L)
+    for k in range(0, 24, 3):                                   # interior holes (mappy.py:343-345 vs :390)
+        a, i = int(rng.randint(A)), int(rng.randint(L))
+        dna[k, a, i] = -1
+    full = eng.evaluate(dna)                                     # general kernels, all outputs
+    fused = eng.evaluate(dna, detail=False)
+    eng.set_option("fused_eval", 0)
+    staged = eng.evaluate(dna, detail=False)
+    eng.set_option("fused_eval", 1)
+    i16 = eng.evaluate16(torch.from_numpy(dna.astype(np.int16)).to(eng.device))
+    for r in (fused, staged, i16):
+        assert torch.equal(r.obj, full.obj) and torch.equal(r.flags, full.flags)
+    obj, flags, lc = full.obj.cpu().numpy(), full.flags.cpu().numpy(), full.lc_mat.cpu().numpy()
+    ow = World(w.img, w.xy, w.row_ptr, w.col, w.edge_poly, w.edge_theta, w.edge_dist, w.map_params, op,
+               name="sweep")
+    for k in range(len(dna)):
+        det = fo.calc_obj(ow, dna[k].astype(int), detail=True)
+        assert det['obj'][0] == obj[k, 0] and det['obj'][1] == obj[k, 1], (A, L, k)
+        assert np.array_equal(det['lc_mat'].astype(np.int32), lc[k]), (A, L, k)
+        assert det['feasible'] == flags[k, 0] and det['n_components'] == flags[k, 2], (A, L, k)
+        assert fo.traversable(ow, dna[k].astype(int)) == flags[k, 1], (A, L, k)
 
 
 def test_shard_equivalence_and_host_path(eng_big, golden_dir):
