@@ -65,7 +65,7 @@ void gcp_destroy(gcp_ctx* c)
     if (c->vary_scratch) cudaFree(c->vary_scratch);
     if (c->lcb_scratch) cudaFree(c->lcb_scratch);
     if (c->cov_scratch) cudaFree(c->cov_scratch);
-    for (int s = 0; s < 2; ++s) if (c->hstream[s]) cudaStreamDestroy(c->hstream[s]);
+    for (int s = 0; s < 3; ++s) if (c->hstream[s]) cudaStreamDestroy(c->hstream[s]);
     for (int s = 0; s < GCP_NUM_STAGES; ++s) { cudaEventDestroy(c->ev_beg[s]); cudaEventDestroy(c->ev_end[s]); }
     delete c;
 }
@@ -397,7 +397,10 @@ static int eval_host_impl(gcp_ctx* c, const void* dna_host, int gene16, uint32_t
     if (P == 0) return 0;
     GCP_CUDA(c, cudaSetDevice(c->device));
     const size_t A = c->p.num_agents, L = c->p.max_dna_len;
-    // chunk so that copy-in, kernels and copy-out of neighbouring chunks overlap
+    // chunks so that copy-in, kernels and copy-out of neighbouring chunks overlap: three staging
+    // buffers on three streams; the first chunks are small so that the GPU starts computing after a
+    // quarter of a chunk's copy time instead of a whole one
+    constexpr int NBUF = 3;
     uint32_t chunk = 4096;
     if (chunk > P) chunk = P;
     const size_t gsz = gene16 ? 2 : 4;
@@ -411,19 +414,21 @@ static int eval_host_impl(gcp_ctx* c, const void* dna_host, int gene16, uint32_t
     const size_t obj_b = align256((size_t)chunk * 16);
     const size_t flg_b = align256((size_t)chunk * 4);
     const size_t per = dna_b + scr_b + obj_b + flg_b;
-    if (c->stage_bytes < 2 * per) {
+    if (c->stage_bytes < NBUF * per) {
         if (c->stage_dev) cudaFree(c->stage_dev);
         c->stage_dev = nullptr; c->stage_bytes = 0;
-        GCP_CUDA(c, cudaMalloc(&c->stage_dev, 2 * per));
-        c->stage_bytes = 2 * per;
+        GCP_CUDA(c, cudaMalloc(&c->stage_dev, NBUF * per));
+        c->stage_bytes = NBUF * per;
     }
-    for (int s = 0; s < 2; ++s)
+    for (int s = 0; s < NBUF; ++s)
         if (!c->hstream[s]) GCP_CUDA(c, cudaStreamCreateWithFlags(&c->hstream[s], cudaStreamNonBlocking));
     int k = 0;
-    for (uint32_t o0 = 0; o0 < P; o0 += chunk, ++k) {
-        const uint32_t n = (P - o0 < chunk) ? (P - o0) : chunk;
-        cudaStream_t st = c->hstream[k & 1];
-        char* base = reinterpret_cast<char*>(c->stage_dev) + (size_t)(k & 1) * per;
+    for (uint32_t o0 = 0; o0 < P; ++k) {
+        uint32_t n = (k == 0) ? chunk / 4 : (k == 1) ? chunk / 2 : chunk;      // ramp-up
+        if (n < 1) n = 1;
+        if (n > P - o0) n = P - o0;
+        cudaStream_t st = c->hstream[k % NBUF];
+        char* base = reinterpret_cast<char*>(c->stage_dev) + (size_t)(k % NBUF) * per;
         void* d_dna = base;
         void* d_scr = base + dna_b;
         double* d_obj = reinterpret_cast<double*>(base + dna_b + scr_b);
@@ -443,9 +448,9 @@ static int eval_host_impl(gcp_ctx* c, const void* dna_host, int gene16, uint32_t
         if (flags_host)
             GCP_CUDA(c, cudaMemcpyAsync(flags_host + (size_t)o0 * 4, d_flg, (size_t)n * 4,
                                         cudaMemcpyDeviceToHost, st));
+        o0 += n;
     }
-    GCP_CUDA(c, cudaStreamSynchronize(c->hstream[0]));
-    GCP_CUDA(c, cudaStreamSynchronize(c->hstream[1]));
+    for (int s = 0; s < NBUF; ++s) GCP_CUDA(c, cudaStreamSynchronize(c->hstream[s]));
     return 0;
 }
 

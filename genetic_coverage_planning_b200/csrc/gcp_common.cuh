@@ -68,7 +68,7 @@ struct gcp_ctx {
     void* cov_scratch = nullptr; size_t cov_scratch_bytes = 0;     // item buckets of long genomes (gcp_fused.cu)
     uint32_t vary_org_offset = 0;   // population shards: global id of local organism 0 (Philox keys)
     int force_lc_big = 0;    // testing: always take the sort-based loop-closure path
-    cudaStream_t hstream[2] = {};
+    cudaStream_t hstream[3] = {};
     // coverage kernel tuning (0 = auto)
     int cov_table = 0, cov_maxpairs = 0;
     int cov_buckets = 1;     // 1: long genomes bucket their items by hash partition once (else: R scanning passes)
