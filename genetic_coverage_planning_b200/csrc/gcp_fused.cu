@@ -1,15 +1,18 @@
 // Fused evaluation kernel (objectives-only fast path): Organism.calcObj for one organism per
-// CTA with the chromosome, its edge ids and its sub-tile ranges held in shared memory, so the
+// CTA with the chromosome and the quarter-item range of every step held in shared memory, so the
 // DNA is read from HBM exactly once and nothing intermediate is written back.
 //
-//   phase A  path costs        mappy.py:341-352   (k_path_costs restated on shared memory)
-//   phase B  wall coverage     mappy.py:353-364   (quarter-granular bucketing, see phase B)
-//   phase C  loop closures     mappy.py:372-437   (k_loop_closures)
+//   phase A  path costs        mappy.py:341-352   (edge lookup, per-step costs, revisited edges dropped)
+//   phase B  wall coverage     mappy.py:353-364   (coverage_quarters: counting sort of quarter items
+//                                                  by (map block, quarter), flat union + popcount)
+//   phase C  loop closures     mappy.py:372-437   (shared-memory hash of consecutive gene pairs)
 //   phase D  constraints + objectives  geneticalgorithm.py:177-201
 //
 // Preconditions (checked by the caller): pre-masked footprint store uploaded and
-// coverage_blend == 1 (wall coverage only); gray maps are handled (HAS_GRAY).  The staged kernels in gcp_eval.cu remain the general path (gray maps,
-// blend < 1, all six pixel counters) and the cross-check of this one (tests/test_gpu_parity.py).
+// coverage_blend == 1 (wall coverage only); binary and gray maps (HAS_GRAY).  The staged kernels
+// in gcp_eval.cu remain the general path (blend < 1, all six pixel counters) and the cross-check
+// of this one (tests/test_gpu_parity.py); k_cov_quarters below is phase B as a stand-alone kernel
+// for genomes that outgrow this kernel's shared memory.
 //
 #include "gcp_common.cuh"
 #include "gcp_device.cuh"
@@ -635,9 +638,10 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     // Items are QUARTERS (16 rows x 64 px = one 128-B line) of the visited edges' pre-masked
     // sub-tiles.  B1 counting-sorts them by (map block, quarter index): an open-addressing hash
     // table maps block id -> slot, one shared atomicAdd per item returns its rank inside
-    // (slot, quarter).  B2: a warp owns a block; its 8-lane group g streams the block's
-    // quarter-g list (lane = one uint4 = 2 rows), ORs into registers and popcounts once per
-    // block.  No lane idles on absent quarters, no bitmap in shared memory, no bitmap atomics.
+    // (slot, quarter).  B2: the sorted array is cut into equal ranges snapped to list starts; an
+    // 8-lane group streams its range (lane = one uint4 = 2 rows of the quarter), ORs into registers
+    // and popcounts at every list end (gray maps: a warp per block, one 8-lane group per quarter).
+    // No lane idles on absent quarters, no bitmap in shared memory, no bitmap atomics.
     // phase A2 (lanes 0..A-1 of warp 0) runs while the other warps start clearing B's tables
     if (warp == 0 && lane < A) {
         // phase A2: sequential fp64 adds in step order per agent (mappy.py:351-352),
