@@ -220,7 +220,11 @@ int gcp_gather_survivors(gcp_ctx* ctx, const int32_t* order_dev, uint32_t n_org,
  * "force_general": never take the pre-masked coverage fast path; "fused_eval": 0 = staged kernels;
  * "force_lc_big": long-genome loop closures even for short genomes (1 radix sort, 2 partitioned hash); "vary_org_offset": global id of
  * local organism 0 when a rank varies only its shard of the children (keys of the Philox streams);
- * "cov_table", "cov_maxpairs": shared-memory sizing of the coverage kernels (0 = auto). */
+ * "cov_table", "cov_maxpairs", "cov_threads": shared-memory sizing / CTA size of the coverage kernels
+ * (0 = auto); "cov_dedup": 0 = keep revisited edges in the coverage union (same result, more work);
+ * "cov_buckets": 0 = long genomes re-scan their items per hash partition instead of bucketing them
+ * once; "lc_min_parts": at least this many hash partitions in the long-genome loop-closure kernel.
+ * Unknown names return an error. */
 int gcp_set_option(gcp_ctx* ctx, const char* name, int64_t value);
 
 /* ---- introspection ---------------------------------------------------------------- */
