@@ -36,6 +36,15 @@ struct FusedShape {
 //   n_cov: covered mask pixels with g == 0, n_wg: sum of (255 - g) over covered gray mask pixels
 //   (per-thread partial sums; the caller reduces them).  s_x: T*20 + MAXP*8 + 32 bytes.
 // ============================================================================
+// base + idx * 16 in ONE wide multiply-add (the compiler otherwise splits the 36-bit product into
+// shift / funnel-shift / mask / add / add-with-carry in front of every footprint load)
+__device__ __forceinline__ const uint4* tile_at(const uint4* base, uint32_t idx)
+{
+    unsigned long long addr;
+    asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(addr) : "r"(idx), "l"(base));
+    return reinterpret_cast<const uint4*>(addr);
+}
+
 template <int KF_THREADS, bool HAS_GRAY, bool BUCKETS = false>
 __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const GcpTables& t,
                                                   int T, int MAXP, uint32_t R0, uint32_t DS, unsigned char* s_x,
@@ -400,7 +409,7 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
                     for (int j = 0; j < 4; ++j) {
                         e[j] = (k + j < len) ? pb[k + j] : 0u;
                         v[j] = make_uint4(0, 0, 0, 0);
-                        if (k + j < len) v[j] = __ldg(tile_l + (e[j] & 0x7FFFFFFFu));
+                        if (k + j < len) v[j] = __ldg(tile_at(tile_l, e[j] & 0x7FFFFFFFu));
                     }
                     #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -427,10 +436,10 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
                         const uint32_t i0 = pb[k] & 0x7FFFFFFFu, i1 = pb[k + 1] & 0x7FFFFFFFu, i2 = pb[k + 2] & 0x7FFFFFFFu,
                                        i3 = pb[k + 3] & 0x7FFFFFFFu;
                         uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0, v3 = v0;
-                        if (k < cnt) v0 = __ldg(tile_l + i0);
-                        if (k + 1 < cnt) v1 = __ldg(tile_l + i1);
-                        if (k + 2 < cnt) v2 = __ldg(tile_l + i2);
-                        if (k + 3 < cnt) v3 = __ldg(tile_l + i3);
+                        if (k < cnt) v0 = __ldg(tile_at(tile_l, i0));
+                        if (k + 1 < cnt) v1 = __ldg(tile_at(tile_l, i1));
+                        if (k + 2 < cnt) v2 = __ldg(tile_at(tile_l, i2));
+                        if (k + 3 < cnt) v3 = __ldg(tile_at(tile_l, i3));
                         acc.x |= (v0.x | v1.x) | (v2.x | v3.x);
                         acc.y |= (v0.y | v1.y) | (v2.y | v3.y);
                         acc.z |= (v0.z | v1.z) | (v2.z | v3.z);
