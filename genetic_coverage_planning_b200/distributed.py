@@ -139,7 +139,13 @@ class DistributedEvolution(object):
             eng.set_option("vary_org_offset", 0)
         kid_obj = eng.evaluate(kids, detail=False).obj
         if self.world > 1:
-            kids_all = _all_gather(kids, self.group)
+            if eng.pw.N <= 32767:
+                # waypoint ids (and the -1 padding) fit 16 bits: half the bytes on the wire for the
+                # one large exchange of a generation (2.5 GB of int32 at 8 x 65,536 organisms)
+                wire = kids.to(torch.int16).contiguous().view(torch.uint8)      # neither NCCL nor gloo moves int16
+                kids_all = _all_gather(wire, self.group).view(torch.int16).to(torch.int32)
+            else:
+                kids_all = _all_gather(kids, self.group)
             kid_obj = _all_gather(kid_obj, self.group)
         else:
             kids_all = kids
