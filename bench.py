@@ -443,8 +443,10 @@ def main():
                 "generations_per_s": 1000.0 / float(tg.item()),
                 "organisms_varied_and_evaluated_per_s": world_size * P / float(tg.item()) * 1e3,
                 "how": "children sharded by pair range, Philox keyed by global ids (bit-identical to "
-                       "one GPU), NCCL all-gather of children DNA (%d MB) + objective records, "
-                       "ranking and survivor gather replicated" % (world_size * P * A * L * 4 // 10**6)}
+                       "one GPU), NCCL all-gather of children DNA (%d MB on the wire, %d-bit genes) + "
+                       "objective records, ranking and survivor gather replicated"
+                       % (world_size * P * A * L * (2 if w.N <= 32767 else 4) // 10**6,
+                          16 if w.N <= 32767 else 32)}
             del gd, go, gf
             extras["ranking_distributed"] = {
                 "n_gladiators": world_size * P, "ms": float(tms.item()),
