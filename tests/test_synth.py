@@ -72,3 +72,17 @@ def test_graph_row_restatement_equals_reference(world_small, golden_dir):
     for i in range(0, len(w.xy), 7):
         got = graphs._row_host(i, w.xy, w.map_params['scale'], 4.0, obstacles)
         assert sorted(int(v) for v in got if v >= 0) == [int(v) for v in col[rp[i]:rp[i + 1]]]
+
+
+@pytest.mark.parametrize("which", ["small", "big", "synth"])
+def test_edge_headings_equal_reference_tables(which, world_small, world_big, golden_dir):
+    """frustums.edge_headings (the host half of gcp_compute_frustums: heading, length, cosine and
+    sine per edge from scalar numpy calls per distinct pixel offset) reproduces the reference's
+    _traverse_angles / _traverse_dists bit for bit on all three reference-made worlds."""
+    import os
+    from world import World
+    from genetic_coverage_planning_b200 import frustums
+    w = {"small": world_small, "big": world_big}.get(which) or World.load_npz(os.path.join(golden_dir, "world_synth.npz"))
+    theta, dist, co, si = frustums.edge_headings(w.xy, w.row_ptr, w.col)
+    assert np.array_equal(theta, w.edge_theta) and np.array_equal(dist, w.edge_dist)
+    assert np.array_equal(co, np.cos(w.edge_theta)) and np.array_equal(si, np.sin(w.edge_theta))
