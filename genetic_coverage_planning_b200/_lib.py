@@ -6,7 +6,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgcp.so")
 
-GCP_ABI_VERSION = 1
+GCP_ABI_VERSION = 2
+GCP_MAX_SHARDS = 16
 GCP_MAX_AGENTS = 32
 INVALID_EDGE = 0xFFFFFFFF
 
@@ -46,6 +47,10 @@ class GcpGraphParams(C.Structure):
                 ("cell", C.c_int32), ("sectors", C.c_double * 8), ("eps_angle", C.c_double)]
 
 
+class GcpShards(C.Structure):
+    _fields_ = [("world", C.c_uint32), ("per_shard", C.c_uint32), ("base", C.c_void_p * 16)]
+
+
 class GcpEvalOut(C.Structure):
     _fields_ = [("obj", C.c_void_p), ("neg_cov", C.c_void_p), ("dist", C.c_void_p),
                 ("turn", C.c_void_p), ("cov", C.c_void_p), ("lc_mat", C.c_void_p),
@@ -73,6 +78,7 @@ SIGNATURES = {
     "gcp_eval_host": (C.c_int, [_vp, _vp, _u32, _vp, _vp]),
     "gcp_eval_host16": (C.c_int, [_vp, _vp, _u32, _vp, _vp]),
     "gcp_eval16": (C.c_int, [_vp, _vp, _u32, C.POINTER(GcpEvalOut), _vp]),
+    "gcp_eval16_available": (C.c_int, [_vp]),
     "gcp_rank_scratch_bytes": (C.c_size_t, [_vp, _u32]),
     "gcp_maximin": (C.c_int, [_vp, _vp, _u32, C.c_double, _u32, _u32, _vp, _vp, _vp,
                               C.c_size_t, _vp]),
@@ -86,6 +92,16 @@ SIGNATURES = {
                                   C.c_size_t, _vp]),
     "gcp_random_walks": (C.c_int, [_vp, _vp, _u32, _vp, C.c_int32, _u64, _u32, _vp]),
     "gcp_gather_survivors": (C.c_int, [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gcp_shard_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp), _vp]),
+    "gcp_shard_free": (C.c_int, [_vp, _vp]),
+    "gcp_shard_open": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "gcp_shard_close": (C.c_int, [_vp, _vp]),
+    "gcp_crossover_shards": (C.c_int, [_vp, C.POINTER(GcpShards), C.c_int, _vp, _u32, _u32, _u32, _u64,
+                                       _u32, _vp, _vp]),
+    "gcp_mutate_genes": (C.c_int, [_vp, _vp, C.c_int, _u32, _u32, _u64, _u32, _u32, _vp]),
+    "gcp_gather_shards": (C.c_int, [_vp, _vp, _u32, _u32, _u32, C.POINTER(GcpShards),
+                                    C.POINTER(GcpShards), C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gcp_peer_barrier": (C.c_int, [_vp, C.POINTER(GcpShards), _u32, _u32, _vp, _vp]),
     "gcp_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     "gcp_launch_count": (C.c_uint64, [_vp]),
     "gcp_set_timing": (C.c_int, [_vp, C.c_int]),

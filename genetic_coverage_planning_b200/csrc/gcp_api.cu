@@ -60,11 +60,15 @@ void gcp_destroy(gcp_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    for (void* q : c->shard_peer) cudaIpcCloseMemHandle(q);
+    for (void* q : c->shard_own) cudaFree(q);
     for (int i = 0; i < c->n_owned; ++i) cudaFree(c->owned[i]);
     if (c->stage_dev) cudaFree(c->stage_dev);
     if (c->vary_scratch) cudaFree(c->vary_scratch);
-    if (c->lcb_scratch) cudaFree(c->lcb_scratch);
-    if (c->cov_scratch) cudaFree(c->cov_scratch);
+    for (int s = 0; s < 3; ++s) {
+        if (c->lcb_scratch_s[s]) cudaFree(c->lcb_scratch_s[s]);
+        if (c->cov_scratch_s[s]) cudaFree(c->cov_scratch_s[s]);
+    }
     for (int s = 0; s < 3; ++s) if (c->hstream[s]) cudaStreamDestroy(c->hstream[s]);
     for (int s = 0; s < GCP_NUM_STAGES; ++s) { cudaEventDestroy(c->ev_beg[s]); cudaEventDestroy(c->ev_end[s]); }
     delete c;
@@ -373,6 +377,14 @@ int gcp_eval16(gcp_ctx* c, const int16_t* dna, uint32_t P, const gcp_eval_out* o
     return launch_eval_fused(c, dna, 1, P, out, (cudaStream_t)stream);
 }
 
+int gcp_eval16_available(gcp_ctx* c)
+{
+    if (!c || ready(c)) return 0;
+    gcp_eval_out probe;
+    memset(&probe, 0, sizeof(probe));
+    return (c->t.N <= 32767 && fast_path(c, &probe)) ? 1 : 0;
+}
+
 static int eval_host_impl(gcp_ctx* c, const void* dna_host, int gene16, uint32_t P, double* obj_host,
                           uint8_t* flags_host);
 
@@ -439,8 +451,10 @@ static int eval_host_impl(gcp_ctx* c, const void* dna_host, int gene16, uint32_t
         memset(&out, 0, sizeof(out));
         out.obj = d_obj;
         out.flags = d_flg;
+        c->scratch_slot = k % NBUF;               // long-genome scratch of this pipeline slot
         if (gene16) r = gcp_eval16(c, reinterpret_cast<const int16_t*>(d_dna), n, &out, st);
         else r = gcp_eval(c, reinterpret_cast<const int32_t*>(d_dna), n, &out, d_scr, scr_b, st);
+        c->scratch_slot = 0;
         if (r) return r;
         if (obj_host)
             GCP_CUDA(c, cudaMemcpyAsync(obj_host + (size_t)o0 * 2, d_obj, (size_t)n * 16,
@@ -552,6 +566,104 @@ int gcp_gather_survivors(gcp_ctx* c, const int32_t* order, uint32_t P, const int
     int r = ready(c); if (r) return r;
     return launch_gather_survivors(c, order, P, par_dna, kid_dna, glad_obj, glad_fit, out_dna,
                                    out_obj, out_fit, (cudaStream_t)stream);
+}
+
+// ---- population shards: CUDA IPC plumbing + the sharded variation / truncation entry points ----
+int gcp_shard_alloc(gcp_ctx* c, size_t bytes, void** dev_ptr, uint8_t ipc_handle[64])
+{
+    if (!c || !dev_ptr || !ipc_handle) return -1;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    *dev_ptr = nullptr;
+    GCP_CUDA(c, cudaSetDevice(c->device));
+    void* p = nullptr;
+    GCP_CUDA(c, cudaMalloc(&p, bytes ? bytes : 256));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return gcp_fail(c, -2, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(ipc_handle, &h, 64);
+    c->shard_own.push_back(p);
+    *dev_ptr = p;
+    return 0;
+}
+
+static bool take(std::vector<void*>& v, void* p)
+{
+    for (size_t i = 0; i < v.size(); ++i)
+        if (v[i] == p) { v.erase(v.begin() + i); return true; }
+    return false;
+}
+
+int gcp_shard_free(gcp_ctx* c, void* p)
+{
+    if (!c) return -1;
+    if (!take(c->shard_own, p)) return gcp_fail(c, -1, "gcp_shard_free: not a shard of this context");
+    GCP_CUDA(c, cudaSetDevice(c->device));
+    GCP_CUDA(c, cudaFree(p));
+    return 0;
+}
+
+int gcp_shard_open(gcp_ctx* c, const uint8_t ipc_handle[64], void** dev_ptr)
+{
+    if (!c || !dev_ptr || !ipc_handle) return -1;
+    *dev_ptr = nullptr;
+    GCP_CUDA(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess)
+        return gcp_fail(c, -2, "cudaIpcOpenMemHandle failed: %s (peer shards need GPUs with peer access "
+                               "in one box, and a different process than the owner)", cudaGetErrorString(e));
+    c->shard_peer.push_back(p);
+    *dev_ptr = p;
+    return 0;
+}
+
+int gcp_shard_close(gcp_ctx* c, void* p)
+{
+    if (!c) return -1;
+    if (!take(c->shard_peer, p)) return gcp_fail(c, -1, "gcp_shard_close: not a peer shard of this context");
+    GCP_CUDA(c, cudaSetDevice(c->device));
+    GCP_CUDA(c, cudaIpcCloseMemHandle(p));
+    return 0;
+}
+
+int gcp_crossover_shards(gcp_ctx* c, const gcp_shards* parents, int gene_bytes, const int32_t* strong,
+                         uint32_t P, uint32_t pair_begin, uint32_t n_pairs, uint64_t seed, uint32_t gen,
+                         void* children, void* stream)
+{
+    int r = vary_ready(c); if (r) return r;
+    return launch_crossover_shards(c, parents, gene_bytes, strong, P, pair_begin, n_pairs, seed, gen,
+                                   children, (cudaStream_t)stream);
+}
+
+int gcp_mutate_genes(gcp_ctx* c, void* dna, int gene_bytes, uint32_t P, uint32_t org_offset, uint64_t seed,
+                     uint32_t gen, uint32_t salt, void* stream)
+{
+    int r = vary_ready(c); if (r) return r;
+    return launch_mutate_genes(c, dna, gene_bytes, P, org_offset, seed, gen, salt, (cudaStream_t)stream);
+}
+
+int gcp_gather_shards(gcp_ctx* c, const int32_t* order, uint32_t P, uint32_t k_begin, uint32_t n_local,
+                      const gcp_shards* parents, const gcp_shards* children, int gene_bytes,
+                      const double* glad_obj, const double* glad_fit, void* out_dna, double* out_obj,
+                      double* out_fit, void* stream)
+{
+    int r = ready(c); if (r) return r;
+    if ((out_obj == nullptr) != (out_fit == nullptr))
+        return gcp_fail(c, -1, "gcp_gather_shards: out_obj and out_fit go together");
+    return launch_gather_shards(c, order, P, k_begin, n_local, parents, children, gene_bytes, glad_obj,
+                                glad_fit, out_dna, out_obj, out_fit, (cudaStream_t)stream);
+}
+
+int gcp_peer_barrier(gcp_ctx* c, const gcp_shards* flags, uint32_t rank, uint32_t epoch,
+                     uint32_t* timed_out, void* stream)
+{
+    if (!c) return -1;
+    return launch_peer_barrier(c, flags, rank, epoch, timed_out, (cudaStream_t)stream);
 }
 
 int gcp_set_option(gcp_ctx* c, const char* name, int64_t value)

@@ -57,6 +57,8 @@ struct gcp_ctx {
     // owned device allocations
     void* owned[32] = {};
     int n_owned = 0;
+    // population shards: own allocations exported over CUDA IPC, and peers' shards opened here
+    std::vector<void*> shard_own, shard_peer;
     // timing
     int timing = 0;
     cudaEvent_t ev_beg[GCP_NUM_STAGES] = {}, ev_end[GCP_NUM_STAGES] = {};
@@ -64,8 +66,11 @@ struct gcp_ctx {
     // host-eval staging (gcp_eval_host)
     void* stage_dev = nullptr; size_t stage_bytes = 0;
     void* vary_scratch = nullptr; size_t vary_scratch_bytes = 0;   // mutation row list (gcp_vary.cu)
-    void* lcb_scratch = nullptr; size_t lcb_scratch_bytes = 0;     // sort buffers / position records (gcp_lcbig.cu)
-    void* cov_scratch = nullptr; size_t cov_scratch_bytes = 0;     // item buckets of long genomes (gcp_fused.cu)
+    // long-genome scratch, one set per pipeline slot: gcp_eval_host overlaps neighbouring chunks on
+    // three streams, and a chunk's kernels must not overwrite records another chunk still reads
+    void* lcb_scratch_s[3] = {}; size_t lcb_scratch_bytes_s[3] = {};   // sort buffers / position records (gcp_lcbig.cu)
+    void* cov_scratch_s[3] = {}; size_t cov_scratch_bytes_s[3] = {};   // item buckets of long genomes (gcp_fused.cu)
+    int scratch_slot = 0;           // slot the launchers use (0 outside gcp_eval_host)
     uint32_t vary_org_offset = 0;   // population shards: global id of local organism 0 (Philox keys)
     int force_lc_big = 0;    // testing: always take the sort-based loop-closure path
     cudaStream_t hstream[3] = {};
@@ -129,6 +134,17 @@ int launch_crossover(gcp_ctx*, const int32_t* parents, const int32_t* strong, ui
                      uint64_t seed, uint32_t gen, int32_t* children, cudaStream_t);
 int launch_mutate(gcp_ctx*, int32_t* dna, uint32_t P, uint64_t seed, uint32_t gen, uint32_t salt,
                   cudaStream_t);
+int launch_mutate_genes(gcp_ctx*, void* dna, int gene_bytes, uint32_t P, uint32_t org_offset, uint64_t seed,
+                        uint32_t gen, uint32_t salt, cudaStream_t);
+int launch_crossover_shards(gcp_ctx*, const gcp_shards* parents, int gene_bytes, const int32_t* strong,
+                            uint32_t P, uint32_t pair_begin, uint32_t n_pairs, uint64_t seed, uint32_t gen,
+                            void* children, cudaStream_t);
+int launch_gather_shards(gcp_ctx*, const int32_t* order, uint32_t P, uint32_t k_begin, uint32_t n_local,
+                         const gcp_shards* parents, const gcp_shards* children, int gene_bytes,
+                         const double* glad_obj, const double* glad_fit, void* out_dna, double* out_obj,
+                         double* out_fit, cudaStream_t);
+int launch_peer_barrier(gcp_ctx*, const gcp_shards* flags, uint32_t rank, uint32_t epoch, uint32_t* timed_out,
+                        cudaStream_t);
 int launch_random_walks(gcp_ctx*, int32_t* dna, uint32_t P, const int32_t* start_idx_dev,
                         int path_len, uint64_t seed, uint32_t batch, cudaStream_t);
 int launch_gather_survivors(gcp_ctx*, const int32_t* order, uint32_t P, const int32_t* par_dna,

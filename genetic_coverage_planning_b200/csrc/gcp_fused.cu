@@ -865,13 +865,13 @@ int launch_coverage_quarters(gcp_ctx* ctx, uint32_t* step_qinfo, uint32_t P, uin
         if (chunk < 1) chunk = 1;
         if (chunk > P) chunk = P;
         const size_t need = (size_t)chunk * rec_cap * 8;
-        if (ctx->cov_scratch_bytes < need) {
-            if (ctx->cov_scratch) cudaFree(ctx->cov_scratch);
-            ctx->cov_scratch = nullptr; ctx->cov_scratch_bytes = 0;
-            GCP_CUDA(ctx, cudaMalloc(&ctx->cov_scratch, need));
-            ctx->cov_scratch_bytes = need;
+        if (ctx->cov_scratch_bytes_s[ctx->scratch_slot] < need) {
+            if (ctx->cov_scratch_s[ctx->scratch_slot]) cudaFree(ctx->cov_scratch_s[ctx->scratch_slot]);
+            ctx->cov_scratch_s[ctx->scratch_slot] = nullptr; ctx->cov_scratch_bytes_s[ctx->scratch_slot] = 0;
+            GCP_CUDA(ctx, cudaMalloc(&ctx->cov_scratch_s[ctx->scratch_slot], need));
+            ctx->cov_scratch_bytes_s[ctx->scratch_slot] = need;
         }
-        rec = reinterpret_cast<uint2*>(ctx->cov_scratch);
+        rec = reinterpret_cast<uint2*>(ctx->cov_scratch_s[ctx->scratch_slot]);
     }
     StageTimer tm(ctx, 1, st);
     const bool gray = ctx->n_gray > 0;

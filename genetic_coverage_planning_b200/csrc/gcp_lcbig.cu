@@ -390,14 +390,14 @@ int launch_loop_closures_big(gcp_ctx* ctx, const int32_t* dna, uint32_t P, const
             if (chunk < 1) chunk = 1;
             if (chunk > P) chunk = P;
             const size_t need = al256((size_t)chunk * AL * 8);
-            if (ctx->lcb_scratch_bytes < need) {
-                if (ctx->lcb_scratch) cudaFree(ctx->lcb_scratch);
-                ctx->lcb_scratch = nullptr; ctx->lcb_scratch_bytes = 0;
-                GCP_CUDA(ctx, cudaMalloc(&ctx->lcb_scratch, need));
-                ctx->lcb_scratch_bytes = need;
+            if (ctx->lcb_scratch_bytes_s[ctx->scratch_slot] < need) {
+                if (ctx->lcb_scratch_s[ctx->scratch_slot]) cudaFree(ctx->lcb_scratch_s[ctx->scratch_slot]);
+                ctx->lcb_scratch_s[ctx->scratch_slot] = nullptr; ctx->lcb_scratch_bytes_s[ctx->scratch_slot] = 0;
+                GCP_CUDA(ctx, cudaMalloc(&ctx->lcb_scratch_s[ctx->scratch_slot], need));
+                ctx->lcb_scratch_bytes_s[ctx->scratch_slot] = need;
             }
             StageTimer tm(ctx, 2, st);
-            unsigned long long* rec = reinterpret_cast<unsigned long long*>(ctx->lcb_scratch);
+            unsigned long long* rec = reinterpret_cast<unsigned long long*>(ctx->lcb_scratch_s[ctx->scratch_slot]);
             if (seq16) GCP_CUDA(ctx, cudaFuncSetAttribute(k_loop_closures_part<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             else       GCP_CUDA(ctx, cudaFuncSetAttribute(k_loop_closures_part<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             for (uint32_t o0 = 0; o0 < P; o0 += chunk) {
@@ -431,13 +431,13 @@ int launch_loop_closures_big(gcp_ctx* ctx, const int32_t* dna, uint32_t P, const
     const size_t M = (size_t)chunk * AL;
     const size_t need = 2 * al256(M * 8) + 2 * al256(M * 4) + al256(M * 4) +
                         al256(radix_hist_bytes((uint32_t)M)) + al256((size_t)P * A * A * 4) + 256;
-    if (ctx->lcb_scratch_bytes < need) {
-        if (ctx->lcb_scratch) cudaFree(ctx->lcb_scratch);
-        ctx->lcb_scratch = nullptr; ctx->lcb_scratch_bytes = 0;
-        GCP_CUDA(ctx, cudaMalloc(&ctx->lcb_scratch, need));
-        ctx->lcb_scratch_bytes = need;
+    if (ctx->lcb_scratch_bytes_s[ctx->scratch_slot] < need) {
+        if (ctx->lcb_scratch_s[ctx->scratch_slot]) cudaFree(ctx->lcb_scratch_s[ctx->scratch_slot]);
+        ctx->lcb_scratch_s[ctx->scratch_slot] = nullptr; ctx->lcb_scratch_bytes_s[ctx->scratch_slot] = 0;
+        GCP_CUDA(ctx, cudaMalloc(&ctx->lcb_scratch_s[ctx->scratch_slot], need));
+        ctx->lcb_scratch_bytes_s[ctx->scratch_slot] = need;
     }
-    char* p = reinterpret_cast<char*>(ctx->lcb_scratch);
+    char* p = reinterpret_cast<char*>(ctx->lcb_scratch_s[ctx->scratch_slot]);
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(p);     p += al256(M * 8);
     unsigned long long* keys_tmp = reinterpret_cast<unsigned long long*>(p); p += al256(M * 8);
     uint32_t* vals = reinterpret_cast<uint32_t*>(p);                         p += al256(M * 4);

@@ -14,6 +14,7 @@
 // of the launch shape, but not equal draw-for-draw to numpy: parity for these kernels is by
 // invariants and distributions (tests/test_gpu_variation.py), as SURVEY.md section 8a states.
 #include "gcp_common.cuh"
+#include <cstring>
 
 #define FULL 0xffffffffu
 constexpr int MAX_MUT_POINTS = 64;
@@ -157,7 +158,8 @@ __device__ int w_walk(const GcpTables& t, const VaryParams& vp, int32_t* r, int 
 // per warp hide the dependent adjacency loads, and nothing is replicated across lanes.
 constexpr int PATH_MEM_MAX = 16;
 
-__device__ int t_walk(const GcpTables& t, const VaryParams& vp, int32_t* r, int pos, int n_steps,
+template <typename G>
+__device__ int t_walk(const GcpTables& t, const VaryParams& vp, G* r, int pos, int n_steps,
                       int mem_floor, Philox& rng)
 {
     const float PI = 3.14159265358979f;
@@ -168,9 +170,9 @@ __device__ int t_walk(const GcpTables& t, const VaryParams& vp, int32_t* r, int 
     #pragma unroll
     for (int k = 0; k < PATH_MEM_MAX; ++k) {
         const int idx = pos - k;
-        hist[k] = (k < mem && idx >= mem_floor) ? r[idx] : -2;
+        hist[k] = (k < mem && idx >= mem_floor) ? (int)r[idx] : -2;
     }
-    int cur = r[pos];
+    int cur = (int)r[pos];
     for (int s = 0; s < n_steps && pos + 1 < vp.L; ++s) {
         uint32_t c[8];
         float w[8];
@@ -260,7 +262,7 @@ __device__ int t_walk(const GcpTables& t, const VaryParams& vp, int32_t* r, int 
         #pragma unroll
         for (int k = PATH_MEM_MAX - 1; k > 0; --k) hist[k] = (k < mem) ? hist[k - 1] : -2;
         hist[0] = (mem > 0) ? nxt : -2;
-        r[++pos] = nxt;
+        r[++pos] = (G)nxt;
         cur = nxt;
     }
     return pos;
@@ -389,26 +391,105 @@ __global__ void k_lv_search(const double* __restrict__ cum, uint32_t M, double r
     out[m] = (int32_t)lo;
 }
 
+// ------------------------------------------------------------------ gene rows in global memory
+// Chromosomes live in global memory as int32 or, when every waypoint id fits (N <= 32767), int16
+// genes: G.  A row goes through shared memory as int32.  Rows are moved with 16-byte accesses
+// when their byte length allows it (L = 200: 400 B int16 / 800 B int32), which is what keeps the
+// reads of a PEER GPU's shard over NVLink at full request size.
+template <typename G> struct GeneVec;
+template <> struct GeneVec<int32_t> { static constexpr int N = 4; };
+template <> struct GeneVec<int16_t> { static constexpr int N = 8; };
+
+template <typename G>
+__device__ __forceinline__ void w_load_row(const G* __restrict__ g, int32_t* r, int L, int lane)
+{
+    constexpr int V = GeneVec<G>::N;
+    if ((L % V) == 0 && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
+        const int4* g4 = reinterpret_cast<const int4*>(g);
+        for (int x = lane; x < L / V; x += 32) {
+            const int4 v = g4[x];
+            if constexpr (V == 4) {
+                reinterpret_cast<int4*>(r)[x] = v;
+            } else {
+                int4 lo, hi;
+                lo.x = (int)(short)(v.x & 0xFFFF); lo.y = v.x >> 16;
+                lo.z = (int)(short)(v.y & 0xFFFF); lo.w = v.y >> 16;
+                hi.x = (int)(short)(v.z & 0xFFFF); hi.y = v.z >> 16;
+                hi.z = (int)(short)(v.w & 0xFFFF); hi.w = v.w >> 16;
+                reinterpret_cast<int4*>(r)[2 * x] = lo;
+                reinterpret_cast<int4*>(r)[2 * x + 1] = hi;
+            }
+        }
+    } else {
+        for (int x = lane; x < L; x += 32) r[x] = (int)g[x];
+    }
+}
+
+// g[x] = x < n ? r[x] : -1 for x < L (addTelomere :335-344)
+template <typename G>
+__device__ __forceinline__ void w_store_row(G* __restrict__ g, const int32_t* r, int n, int L, int lane)
+{
+    constexpr int V = GeneVec<G>::N;
+    if ((L % V) == 0 && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
+        int4* g4 = reinterpret_cast<int4*>(g);
+        for (int x = lane; x < L / V; x += 32) {
+            int e[V];
+            #pragma unroll
+            for (int k = 0; k < V; ++k) { const int i = x * V + k; e[k] = (i < n) ? r[i] : -1; }
+            int4 v;
+            if constexpr (V == 4) { v = make_int4(e[0], e[1], e[2], e[3]); }
+            else {
+                v.x = (e[0] & 0xFFFF) | (e[1] << 16); v.y = (e[2] & 0xFFFF) | (e[3] << 16);
+                v.z = (e[4] & 0xFFFF) | (e[5] << 16); v.w = (e[6] & 0xFFFF) | (e[7] << 16);
+            }
+            g4[x] = v;
+        }
+    } else {
+        for (int x = lane; x < L; x += 32) g[x] = (G)((x < n) ? r[x] : -1);
+    }
+}
+
+// Shards of one logical [P_global][A][L] gene array: organism g lives on shard g / per at
+// local index g % per.  base[] holds every shard as mapped into THIS process (own shard: plain
+// device memory, peers: cudaIpcOpenMemHandle -> NVLink peer loads).  world == 1: a plain array.
+struct ShardTab {
+    const void* base[GCP_MAX_SHARDS];
+    uint32_t world, per;
+};
+
+template <typename G>
+__device__ __forceinline__ const G* shard_org(const ShardTab& sh, uint32_t g, size_t org_genes)
+{
+    const uint32_t s = (sh.world == 1) ? 0u : g / sh.per;
+    const uint32_t loc = g - s * sh.per;
+    return reinterpret_cast<const G*>(sh.base[s]) + (size_t)loc * org_genes;
+}
+
 // ------------------------------------------------------------------ crossover (+ fused mutation)
 // One warp per (pair k, agent a): parents strong[k] ("self") and strong[k + P/2] ("mate")
 // -> children 2k, 2k+1.  Rows live in shared memory: pm | pd | c1 | c2 | match-index heads.
+// Pairs [pair_begin, pair_begin + n_pairs) of the P_global / 2 pairs are built by this launch
+// (population shards); the children go to children[2 (k - pair_begin)], +1.
 constexpr int VARY_WARPS = 4;
 constexpr int XO_BUCKETS = 256;
 __device__ __forceinline__ int xo_bucket(int gene) { return (int)(((uint32_t)gene * 2654435761u) >> 24); }
 
 __device__ __forceinline__ size_t vary_row_stride(int L) { return (size_t)((L + 31) & ~31); }
 
+template <typename G>
 __global__ void __launch_bounds__(VARY_WARPS * 32)
-k_crossover(const int32_t* __restrict__ parents, const int32_t* __restrict__ strong, uint32_t P,
-            GcpTables t, VaryParams vp, uint64_t seed, uint32_t gen,
-            int32_t* __restrict__ children)
+k_crossover(ShardTab parents, const int32_t* __restrict__ strong, uint32_t P, uint32_t pair_begin,
+            uint32_t n_pairs, GcpTables t, VaryParams vp, uint64_t seed, uint32_t gen,
+            G* __restrict__ children)
 {
     extern __shared__ int32_t s_rows[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t gid = blockIdx.x * VARY_WARPS + warp;
+    const uint32_t lid = blockIdx.x * VARY_WARPS + warp;              // local (pair, agent)
     const uint32_t half = P / 2;
-    if (gid >= half * vp.A) return;
-    const uint32_t k = gid / vp.A, a = gid % vp.A;
+    if (lid >= n_pairs * vp.A) return;
+    const uint32_t kl = lid / vp.A, a = lid % vp.A;
+    const uint32_t k = pair_begin + kl;                               // global pair
+    const uint32_t gid = k * vp.A + a;                                // global (pair, agent): Philox key
     const int L = vp.L;
     const size_t RS = vary_row_stride(L);
     int32_t* pm = s_rows + (size_t)warp * (4 * RS + XO_BUCKETS);
@@ -416,9 +497,11 @@ k_crossover(const int32_t* __restrict__ parents, const int32_t* __restrict__ str
     int32_t* c1 = pd + RS;
     int32_t* c2 = c1 + RS;
     int32_t* s_head = c2 + RS;                                         // [XO_BUCKETS] chain heads of the match index
-    const int32_t* gm = parents + ((size_t)strong[k] * vp.A + a) * L;
-    const int32_t* gd = parents + ((size_t)strong[k + half] * vp.A + a) * L;
-    for (int x = lane; x < L; x += 32) { pm[x] = gm[x]; pd[x] = gd[x]; }
+    const size_t OG = (size_t)vp.A * L;
+    const G* gm = shard_org<G>(parents, (uint32_t)strong[k], OG) + (size_t)a * L;
+    const G* gd = shard_org<G>(parents, (uint32_t)strong[k + half], OG) + (size_t)a * L;
+    w_load_row<G>(gm, pm, L, lane);
+    w_load_row<G>(gd, pd, L, lane);
     __syncwarp();
     const int lm = w_valid_len(pm, L, lane), ld = w_valid_len(pd, L, lane);
     Philox rng(seed, gen, STREAM_XOVER, gid + (vp.org_off / 2) * vp.A);   // global (pair, agent) id
@@ -505,14 +588,8 @@ k_crossover(const int32_t* __restrict__ parents, const int32_t* __restrict__ str
         for (int x = lane; x < n2; x += 32) c2[x] = pd[x];
     }
     __syncwarp();
-    {
-        int32_t* g1 = children + ((size_t)(2 * k) * vp.A + a) * L;
-        int32_t* g2 = children + ((size_t)(2 * k + 1) * vp.A + a) * L;
-        for (int x = lane; x < L; x += 32) {                            // addTelomere :335-344
-            g1[x] = (x < n1) ? c1[x] : -1;
-            g2[x] = (x < n2) ? c2[x] : -1;
-        }
-    }
+    w_store_row<G>(children + ((size_t)(2 * kl) * vp.A + a) * L, c1, n1, L, lane);       // addTelomere :335-344
+    w_store_row<G>(children + ((size_t)(2 * kl + 1) * vp.A + a) * L, c2, n2, L, lane);
 }
 
 // ------------------------------------------------------------------ mutation (:251-268)
@@ -524,19 +601,21 @@ k_crossover(const int32_t* __restrict__ parents, const int32_t* __restrict__ str
 constexpr int MW_THREADS = 64;
 
 // first -1 of a row that is a valid prefix followed by -1 padding, by bisection
-__device__ __forceinline__ int row_len(const int32_t* r, int L)
+template <typename G>
+__device__ __forceinline__ int row_len(const G* r, int L)
 {
     int lo = 0, hi = L;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (r[mid] == -1) hi = mid; else lo = mid + 1; }
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (r[mid] == (G)-1) hi = mid; else lo = mid + 1; }
     return lo;
 }
 
 // the cut and the tail length of a mutating row (:252-258), from the row's own Philox stream
-__device__ __forceinline__ bool mutation_cut(const int32_t* r, const VaryParams& vp, Philox& rng, int* len_out,
+template <typename G>
+__device__ __forceinline__ bool mutation_cut(const G* r, const VaryParams& vp, Philox& rng, int* len_out,
                                              int* idx_out, int* tail_out)
 {
     const int L = vp.L;
-    const int len = row_len(r, L);
+    const int len = row_len<G>(r, L);
     *len_out = len;
     if (len < 3) return false;
     const int idx = 1 + rng.randint(len - 2);                          // randint(1, len-1)
@@ -550,7 +629,8 @@ constexpr int MW_CLASSES = 4;       // walking rows are bucketed by tail length:
 
 // which = 0: rows of the organisms whose mutation coin came up (:159-161), bucketed by walk length
 // into MW_CLASSES lists (list + c * n_rows, counter[c]); 1: muterpolate coin (:163-165), one list.
-__global__ void k_mutation_list(const int32_t* __restrict__ dna, uint32_t P, VaryParams vp, uint64_t seed,
+template <typename G>
+__global__ void k_mutation_list(const G* __restrict__ dna, uint32_t P, VaryParams vp, uint64_t seed,
                                 uint32_t gen, uint32_t salt, int which, uint32_t* __restrict__ counter,
                                 uint32_t* __restrict__ list)
 {
@@ -571,14 +651,15 @@ __global__ void k_mutation_list(const int32_t* __restrict__ dna, uint32_t P, Var
         const uint32_t gid = org * vp.A + a;
         Philox rng(seed, gen, stream_id(STREAM_MUT, salt), gid + vp.org_off * vp.A);
         int len, idx, tail;
-        if (!mutation_cut(dna + (size_t)gid * vp.L, vp, rng, &len, &idx, &tail)) continue;
+        if (!mutation_cut<G>(dna + (size_t)gid * vp.L, vp, rng, &len, &idx, &tail)) continue;
         const int c = min(MW_CLASSES - 1, (tail * MW_CLASSES) / vp.L);
         list[(size_t)c * n_rows + atomicAdd(&counter[c], 1u)] = gid;
     }
 }
 
+template <typename G>
 __global__ void __launch_bounds__(MW_THREADS)
-k_mutation_walks(int32_t* __restrict__ dna, uint32_t n_rows, GcpTables t, VaryParams vp, uint64_t seed,
+k_mutation_walks(G* __restrict__ dna, uint32_t n_rows, GcpTables t, VaryParams vp, uint64_t seed,
                  uint32_t gen, uint32_t salt, const uint32_t* __restrict__ counter,
                  const uint32_t* __restrict__ list)
 {
@@ -591,12 +672,12 @@ k_mutation_walks(int32_t* __restrict__ dna, uint32_t n_rows, GcpTables t, VaryPa
     }
     if (c == MW_CLASSES) return;
     const uint32_t gid = list[(size_t)c * n_rows + j];
-    int32_t* r = dna + (size_t)gid * vp.L;
+    G* r = dna + (size_t)gid * vp.L;
     Philox rng(seed, gen, stream_id(STREAM_MUT, salt), gid + vp.org_off * vp.A);
     int len, idx, len_tail;
-    if (!mutation_cut(r, vp, rng, &len, &idx, &len_tail)) return;
-    const int last = t_walk(t, vp, r, idx, len_tail, 0, rng);
-    for (int x = last + 1; x < len; ++x) r[x] = -1;                    // addTelomere
+    if (!mutation_cut<G>(r, vp, rng, &len, &idx, &len_tail)) return;
+    const int last = t_walk<G>(t, vp, r, idx, len_tail, 0, rng);
+    for (int x = last + 1; x < len; ++x) r[x] = (G)-1;                 // addTelomere
 }
 
 // ------------------------------------------------------------------ muterpolate (:270-309)
@@ -619,21 +700,17 @@ __device__ __forceinline__ bool t_is_edge_csr(const GcpTables& t, int a, int b)
     return false;
 }
 
+template <typename G>
 __global__ void __launch_bounds__(MW_THREADS)
-k_muterpolate_rows(int32_t* __restrict__ dna, GcpTables t, VaryParams vp, uint64_t seed, uint32_t gen,
+k_muterpolate_rows(G* __restrict__ dna, GcpTables t, VaryParams vp, uint64_t seed, uint32_t gen,
                    uint32_t salt, const uint32_t* __restrict__ counter, const uint32_t* __restrict__ list)
 {
     const uint32_t j = blockIdx.x * MW_THREADS + threadIdx.x;
     if (j >= *counter) return;
     const int L = vp.L;
     const uint32_t gid = list[j];
-    int32_t* r = dna + (size_t)gid * L;
-    int len;
-    {
-        int lo = 0, hi = L;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (r[mid] == -1) hi = mid; else lo = mid + 1; }
-        len = lo;
-    }
+    G* r = dna + (size_t)gid * L;
+    const int len = row_len<G>(r, L);
     const int range = len - (vp.srch_dist + 3);
     if (range <= 0) return;
     Philox rng(seed, gen, stream_id(STREAM_MUTERP, salt), gid + vp.org_off * vp.A);
@@ -654,13 +731,13 @@ k_muterpolate_rows(int32_t* __restrict__ dna, GcpTables t, VaryParams vp, uint64
     bool changed = false;
     for (int q = 0; q < np_; ++q) {
         const int idx1 = pts[q];
-        const int pt1 = r[idx1];                                       // idx1 + 1 < every gap position
+        const int pt1 = (int)r[idx1];                                  // idx1 + 1 < every gap position
         uint32_t n1[8];
         if (t.adj8) t_nbrs(t, pt1, n1);
         for (int idx2 = idx1 + vp.srch_dist + 1; idx2 > idx1 + 1; --idx2) {
             if (!rng.coin(sub_thr)) continue;                          // do_it < P_muterpolate_each :285
             if (idx2 >= L - gap_len) break;                            // IndexError -> break :289
-            int pt2 = r[idx2 < gap_lo ? idx2 : idx2 + gap_len];
+            int pt2 = (int)r[idx2 < gap_lo ? idx2 : idx2 + gap_len];
             if (pt2 < 0) pt2 += (int)t.N;                              // numpy index -1
             int step = -1;
             if (t.adj8) {
@@ -695,7 +772,7 @@ k_muterpolate_rows(int32_t* __restrict__ dna, GcpTables t, VaryParams vp, uint64
                     if (t_is_edge_csr(t, pt2, c)) { if (pick == 0) { step = c; break; } --pick; }
                 }
             }
-            r[idx1 + 1] = step;                                        // :302
+            r[idx1 + 1] = (G)step;                                     // :302
             changed = true;
             const int ndel = idx2 - idx1 - 3;                          // delete idx1+2 .. idx2-2
             if (ndel > 0) {
@@ -711,17 +788,18 @@ k_muterpolate_rows(int32_t* __restrict__ dna, GcpTables t, VaryParams vp, uint64
         int w = 0;
         for (int x = 0; x < L; ++x) {
             if (x >= gap_lo && x < gap_lo + gap_len) continue;
-            const int g = r[x];
-            if (g != -1) r[w++] = g;
+            const G g = r[x];
+            if (g != (G)-1) r[w++] = g;
         }
-        for (int x = w; x < L; ++x) r[x] = -1;
+        for (int x = w; x < L; ++x) r[x] = (G)-1;
     }
 }
 
 // ------------------------------------------------------------------ pruneUTurns (:346-357)
 // One warp per (organism, agent); the row goes through shared memory and back in place.
+template <typename G>
 __global__ void __launch_bounds__(VARY_WARPS * 32)
-k_post_mutate(int32_t* __restrict__ dna, uint32_t P, GcpTables t, VaryParams vp, uint64_t seed,
+k_post_mutate(G* __restrict__ dna, uint32_t P, GcpTables t, VaryParams vp, uint64_t seed,
               uint32_t gen, uint32_t salt)
 {
     extern __shared__ int32_t s_rows[];
@@ -731,12 +809,12 @@ k_post_mutate(int32_t* __restrict__ dna, uint32_t P, GcpTables t, VaryParams vp,
     const int L = vp.L;
     const size_t RS = vary_row_stride(L);
     int32_t* r = s_rows + (size_t)warp * RS;
-    int32_t* g = dna + (size_t)gid * L;
-    for (int x = lane; x < L; x += 32) r[x] = g[x];
+    G* g = dna + (size_t)gid * L;
+    w_load_row<G>(g, r, L, lane);
     __syncwarp();
     int len = w_valid_len(r, L, lane);
     len = w_prune(r, len, lane);
-    for (int x = lane; x < L; x += 32) g[x] = (x < len) ? r[x] : -1;
+    w_store_row<G>(g, r, len, L, lane);
 }
 
 // ------------------------------------------------------------------ initial random paths
@@ -749,28 +827,66 @@ k_random_walks(int32_t* __restrict__ dna, uint32_t P, GcpTables t, VaryParams vp
     int32_t* r = dna + (size_t)gid * vp.L;
     Philox rng(seed, batch, STREAM_INIT, gid);
     r[0] = start_idx[gid % vp.A];
-    const int last = t_walk(t, vp, r, 0, path_len, 0, rng);
+    const int last = t_walk<int32_t>(t, vp, r, 0, path_len, 0, rng);
     for (int x = last + 1; x < vp.L; ++x) r[x] = -1;
 }
 
 // ------------------------------------------------------------------ arena truncation
-// new_parent[k] = gladiator[order[k]] for k < P; gladiators = parents (0..P) ++ children.
-__global__ void k_gather_survivors(const int32_t* __restrict__ order, uint32_t P, uint32_t row_ints,
-                                   const int32_t* __restrict__ par_dna, const int32_t* __restrict__ kid_dna,
+// new_parent[k] = gladiator[order[k]] for k in [k_begin, k_begin + n_local); gladiators =
+// parents (0..P) ++ children, each a sharded array (a peer's survivors come over NVLink).
+// CTAs past n_local copy the objective / fitness records of ALL P survivors (replicated, 24 B each).
+__global__ void k_gather_survivors(const int32_t* __restrict__ order, uint32_t P, uint32_t k_begin,
+                                   uint32_t n_local, uint32_t org_bytes, ShardTab par, ShardTab kid,
                                    const double* __restrict__ glad_obj, const double* __restrict__ glad_fit,
-                                   int32_t* __restrict__ out_dna, double* __restrict__ out_obj,
+                                   void* __restrict__ out_dna, double* __restrict__ out_obj,
                                    double* __restrict__ out_fit)
 {
-    const uint32_t k = blockIdx.x;
-    if (k >= P) return;
+    if (blockIdx.x >= n_local) {
+        const uint32_t k = (blockIdx.x - n_local) * blockDim.x + threadIdx.x;
+        if (k < P) {
+            const uint32_t src = (uint32_t)order[k];
+            reinterpret_cast<double2*>(out_obj)[k] = reinterpret_cast<const double2*>(glad_obj)[src];
+            out_fit[k] = glad_fit[src];
+        }
+        return;
+    }
+    const uint32_t k = k_begin + blockIdx.x;
     const uint32_t src = (uint32_t)order[k];
-    const int32_t* s = (src < P) ? par_dna + (size_t)src * row_ints : kid_dna + (size_t)(src - P) * row_ints;
-    int32_t* d = out_dna + (size_t)k * row_ints;
-    for (uint32_t x = threadIdx.x; x < row_ints; x += blockDim.x) d[x] = s[x];
-    if (threadIdx.x == 0) {
-        out_obj[2 * (size_t)k] = glad_obj[2 * (size_t)src];
-        out_obj[2 * (size_t)k + 1] = glad_obj[2 * (size_t)src + 1];
-        out_fit[k] = glad_fit[src];
+    const ShardTab& sh = (src < P) ? par : kid;
+    const uint32_t g = (src < P) ? src : src - P;
+    const uint32_t s = (sh.world == 1) ? 0u : g / sh.per;
+    const char* sp = reinterpret_cast<const char*>(sh.base[s]) + (size_t)(g - s * sh.per) * org_bytes;
+    char* d = reinterpret_cast<char*>(out_dna) + (size_t)blockIdx.x * org_bytes;
+    if ((org_bytes & 15u) == 0 && ((reinterpret_cast<uintptr_t>(sp) | reinterpret_cast<uintptr_t>(d)) & 15) == 0) {
+        const int4* s4 = reinterpret_cast<const int4*>(sp);
+        int4* d4 = reinterpret_cast<int4*>(d);
+        for (uint32_t x = threadIdx.x; x < org_bytes / 16; x += blockDim.x) d4[x] = s4[x];
+    } else {
+        for (uint32_t x = threadIdx.x; x < org_bytes; x += blockDim.x) d[x] = sp[x];
+    }
+}
+
+// ------------------------------------------------------------------ rendezvous over peer memory
+// One thread per rank: announce `epoch` in slot `rank` of rank w's flags, then wait for rank w's
+// announcement in the own flags.  release / acquire at system scope order the stores of the
+// kernels that ran before this one against the peer's loads after its barrier.
+__global__ void k_peer_barrier(ShardTab flags, uint32_t rank, uint32_t epoch, uint32_t* __restrict__ timed_out)
+{
+    const uint32_t w = threadIdx.x;
+    if (w >= flags.world) return;
+    uint32_t* theirs = reinterpret_cast<uint32_t*>(const_cast<void*>(flags.base[w])) + rank;
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(flags.base[rank]) + w;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(theirs), "r"(epoch) : "memory");
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+        if ((int32_t)(v - epoch) >= 0) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 10000000000ull) { if (timed_out) *timed_out = 1u; break; }      // 10 s: a peer died
+        __nanosleep(200);
     }
 }
 
@@ -787,6 +903,17 @@ static VaryParams make_vp(gcp_ctx* c)
     vp.inv_sigma = (float)(1.0 / c->vary.log_scale_weight);
     vp.org_off = c->vary_org_offset;
     return vp;
+}
+
+static int make_tab(gcp_ctx* c, const gcp_shards* s, ShardTab& tab)
+{
+    if (!s || s->world < 1 || s->world > GCP_MAX_SHARDS) return gcp_fail(c, -1, "shard table: world must be in [1,%d]", GCP_MAX_SHARDS);
+    if (s->world > 1 && s->per_shard == 0) return gcp_fail(c, -1, "shard table: per_shard is 0");
+    tab.world = s->world; tab.per = s->per_shard;
+    for (uint32_t w = 0; w < GCP_MAX_SHARDS; ++w) tab.base[w] = (w < s->world) ? s->base[w] : nullptr;
+    for (uint32_t w = 0; w < s->world; ++w)
+        if (!tab.base[w]) return gcp_fail(c, -1, "shard table: base[%u] is NULL", w);
+    return 0;
 }
 
 int launch_low_var_select(gcp_ctx* c, const double* fit, uint32_t M, double gamma, double r0,
@@ -817,14 +944,22 @@ static int vary_smem(gcp_ctx* c, int rows, int extra, size_t* out)
     return 0;
 }
 
-int launch_mutate(gcp_ctx* c, int32_t* dna, uint32_t P, uint64_t seed, uint32_t gen, uint32_t salt,
-                  cudaStream_t st)
+static int check_gene_bytes(gcp_ctx* c, int gene_bytes)
 {
-    if (P == 0) return 0;
+    if (gene_bytes != 2 && gene_bytes != 4) return gcp_fail(c, -1, "gene_bytes must be 2 (int16) or 4 (int32)");
+    if (gene_bytes == 2 && c->t.N > 32767) return gcp_fail(c, -1, "int16 genes need N <= 32767 waypoints (N=%u)", c->t.N);
+    return 0;
+}
+
+template <typename G>
+static int mutate_impl(gcp_ctx* c, G* dna, uint32_t P, uint32_t org_offset, uint64_t seed, uint32_t gen,
+                       uint32_t salt, cudaStream_t st)
+{
     size_t smem; int r = vary_smem(c, 1, 0, &smem); if (r) return r;
-    GCP_CUDA(c, cudaFuncSetAttribute(k_post_mutate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GCP_CUDA(c, cudaFuncSetAttribute(k_post_mutate<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     StageTimer tm(c, 7, st);
-    const VaryParams vp = make_vp(c);
+    VaryParams vp = make_vp(c);
+    vp.org_off += org_offset;
     const uint32_t n_rows = P * (uint32_t)vp.A;
     if (vp.mut_prob > 0.f || vp.muterp_prob > 0.f) {
         const size_t need = 512 + (size_t)n_rows * 4 * MW_CLASSES;
@@ -840,37 +975,79 @@ int launch_mutate(gcp_ctx* c, int32_t* dna, uint32_t P, uint64_t seed, uint32_t 
     const uint32_t row_grid = (n_rows + MW_THREADS - 1) / MW_THREADS;
     if (vp.mut_prob > 0.f) {                       // mutation (:159-161): tail regrowth walks
         GCP_CUDA(c, cudaMemsetAsync(counter, 0, 4 * MW_CLASSES, st));
-        k_mutation_list<<<(P + 255) / 256, 256, 0, st>>>(dna, P, vp, seed, gen, salt, 0, counter, list);
-        k_mutation_walks<<<row_grid, MW_THREADS, 0, st>>>(dna, n_rows, c->t, vp, seed, gen, salt, counter, list);
+        k_mutation_list<G><<<(P + 255) / 256, 256, 0, st>>>(dna, P, vp, seed, gen, salt, 0, counter, list);
+        k_mutation_walks<G><<<row_grid, MW_THREADS, 0, st>>>(dna, n_rows, c->t, vp, seed, gen, salt, counter, list);
         c->launches += 2;
     }
     if (vp.muterp_prob > 0.f && vp.num_muterp > 0) {   // muterpolate (:163-165)
         GCP_CUDA(c, cudaMemsetAsync(counter + 64, 0, 4, st));
-        k_mutation_list<<<(P + 255) / 256, 256, 0, st>>>(dna, P, vp, seed, gen, salt, 1, counter + 64, list);
-        k_muterpolate_rows<<<row_grid, MW_THREADS, 0, st>>>(dna, c->t, vp, seed, gen, salt, counter + 64, list);
+        k_mutation_list<G><<<(P + 255) / 256, 256, 0, st>>>(dna, P, vp, seed, gen, salt, 1, counter + 64, list);
+        k_muterpolate_rows<G><<<row_grid, MW_THREADS, 0, st>>>(dna, c->t, vp, seed, gen, salt, counter + 64, list);
         c->launches += 2;
     }
-    k_post_mutate<<<(n_rows + VARY_WARPS - 1) / VARY_WARPS, VARY_WARPS * 32, smem, st>>>(dna, P, c->t, vp,
-                                                                                         seed, gen, salt);
+    k_post_mutate<G><<<(n_rows + VARY_WARPS - 1) / VARY_WARPS, VARY_WARPS * 32, smem, st>>>(dna, P, c->t, vp,
+                                                                                            seed, gen, salt);
     c->launches++;
     GCP_CUDA(c, cudaGetLastError());
     return 0;
+}
+
+int launch_mutate_genes(gcp_ctx* c, void* dna, int gene_bytes, uint32_t P, uint32_t org_offset, uint64_t seed,
+                        uint32_t gen, uint32_t salt, cudaStream_t st)
+{
+    if (P == 0) return 0;
+    int r = check_gene_bytes(c, gene_bytes); if (r) return r;
+    if (gene_bytes == 2) return mutate_impl<int16_t>(c, reinterpret_cast<int16_t*>(dna), P, org_offset, seed, gen, salt, st);
+    return mutate_impl<int32_t>(c, reinterpret_cast<int32_t*>(dna), P, org_offset, seed, gen, salt, st);
+}
+
+int launch_mutate(gcp_ctx* c, int32_t* dna, uint32_t P, uint64_t seed, uint32_t gen, uint32_t salt,
+                  cudaStream_t st)
+{
+    return launch_mutate_genes(c, dna, 4, P, 0, seed, gen, salt, st);
+}
+
+template <typename G>
+static int crossover_impl(gcp_ctx* c, const ShardTab& tab, const int32_t* strong, uint32_t P, uint32_t pair_begin,
+                          uint32_t n_pairs, uint64_t seed, uint32_t gen, G* children, cudaStream_t st)
+{
+    size_t smem; int r = vary_smem(c, 4, XO_BUCKETS, &smem); if (r) return r;
+    GCP_CUDA(c, cudaFuncSetAttribute(k_crossover<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    StageTimer tm(c, 6, st);
+    const uint32_t n = n_pairs * c->p.num_agents;
+    k_crossover<G><<<(n + VARY_WARPS - 1) / VARY_WARPS, VARY_WARPS * 32, smem, st>>>(
+        tab, strong, P, pair_begin, n_pairs, c->t, make_vp(c), seed, gen, children);
+    c->launches++;
+    GCP_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+int launch_crossover_shards(gcp_ctx* c, const gcp_shards* parents, int gene_bytes, const int32_t* strong, uint32_t P,
+                            uint32_t pair_begin, uint32_t n_pairs, uint64_t seed, uint32_t gen, void* children,
+                            cudaStream_t st)
+{
+    if (n_pairs == 0) return 0;
+    if (P & 1) return gcp_fail(c, -1, "population size must be even (pather_driver.py:107)");
+    if ((uint64_t)pair_begin + n_pairs > P / 2) return gcp_fail(c, -1, "pair range exceeds P / 2");
+    int r = check_gene_bytes(c, gene_bytes); if (r) return r;
+    ShardTab tab;
+    if ((r = make_tab(c, parents, tab))) return r;
+    if (gene_bytes == 2) return crossover_impl<int16_t>(c, tab, strong, P, pair_begin, n_pairs, seed, gen,
+                                                        reinterpret_cast<int16_t*>(children), st);
+    return crossover_impl<int32_t>(c, tab, strong, P, pair_begin, n_pairs, seed, gen,
+                                   reinterpret_cast<int32_t*>(children), st);
 }
 
 int launch_crossover(gcp_ctx* c, const int32_t* parents, const int32_t* strong, uint32_t P,
                      uint64_t seed, uint32_t gen, int32_t* children, cudaStream_t st)
 {
     if (P < 2) return 0;
-    if (P & 1) return gcp_fail(c, -1, "population size must be even (pather_driver.py:107)");
-    size_t smem; int r = vary_smem(c, 4, XO_BUCKETS, &smem); if (r) return r;
-    GCP_CUDA(c, cudaFuncSetAttribute(k_crossover, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    StageTimer tm(c, 6, st);
-    const uint32_t n = (P / 2) * c->p.num_agents;
-    k_crossover<<<(n + VARY_WARPS - 1) / VARY_WARPS, VARY_WARPS * 32, smem, st>>>(
-        parents, strong, P, c->t, make_vp(c), seed, gen, children);
-    c->launches++;
-    GCP_CUDA(c, cudaGetLastError());
-    return 0;
+    gcp_shards one;
+    memset(&one, 0, sizeof(one));
+    one.world = 1; one.per_shard = P; one.base[0] = parents;
+    // `strong` holds P entries even when only the pairs of one population shard are built here
+    // (vary_org_offset keys the Philox streams by global ids)
+    return launch_crossover_shards(c, &one, 4, strong, P, 0, P / 2, seed, gen, children, st);
 }
 
 int launch_random_walks(gcp_ctx* c, int32_t* dna, uint32_t P, const int32_t* start_idx_dev,
@@ -885,15 +1062,45 @@ int launch_random_walks(gcp_ctx* c, int32_t* dna, uint32_t P, const int32_t* sta
     return 0;
 }
 
+int launch_gather_shards(gcp_ctx* c, const int32_t* order, uint32_t P, uint32_t k_begin, uint32_t n_local,
+                         const gcp_shards* parents, const gcp_shards* children, int gene_bytes,
+                         const double* glad_obj, const double* glad_fit, void* out_dna, double* out_obj,
+                         double* out_fit, cudaStream_t st)
+{
+    if (P == 0) return 0;
+    if ((uint64_t)k_begin + n_local > P) return gcp_fail(c, -1, "survivor range exceeds the population");
+    int r = check_gene_bytes(c, gene_bytes); if (r) return r;
+    ShardTab pt, kt;
+    if ((r = make_tab(c, parents, pt)) || (r = make_tab(c, children, kt))) return r;
+    const uint32_t org_bytes = (uint32_t)(c->p.num_agents * c->p.max_dna_len * gene_bytes);
+    const uint32_t rec_blocks = (out_obj && out_fit) ? (P + 127) / 128 : 0;
+    k_gather_survivors<<<n_local + rec_blocks, 128, 0, st>>>(order, P, k_begin, n_local, org_bytes, pt, kt,
+                                                             glad_obj, glad_fit, out_dna, out_obj, out_fit);
+    c->launches++;
+    GCP_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+int launch_peer_barrier(gcp_ctx* c, const gcp_shards* flags, uint32_t rank, uint32_t epoch, uint32_t* timed_out,
+                        cudaStream_t st)
+{
+    ShardTab tab;
+    int r = make_tab(c, flags, tab); if (r) return r;
+    if (rank >= tab.world) return gcp_fail(c, -1, "peer barrier: rank %u of %u", rank, tab.world);
+    if (tab.world == 1) return 0;
+    k_peer_barrier<<<1, 32, 0, st>>>(tab, rank, epoch, timed_out);
+    c->launches++;
+    GCP_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
 int launch_gather_survivors(gcp_ctx* c, const int32_t* order, uint32_t P, const int32_t* par_dna,
                             const int32_t* kid_dna, const double* glad_obj, const double* glad_fit,
                             int32_t* out_dna, double* out_obj, double* out_fit, cudaStream_t st)
 {
-    if (P == 0) return 0;
-    const uint32_t row = (uint32_t)(c->p.num_agents * c->p.max_dna_len);
-    k_gather_survivors<<<P, 128, 0, st>>>(order, P, row, par_dna, kid_dna, glad_obj, glad_fit,
-                                          out_dna, out_obj, out_fit);
-    c->launches++;
-    GCP_CUDA(c, cudaGetLastError());
-    return 0;
+    gcp_shards par, kid;
+    memset(&par, 0, sizeof(par)); memset(&kid, 0, sizeof(kid));
+    par.world = kid.world = 1; par.per_shard = kid.per_shard = P;
+    par.base[0] = par_dna; kid.base[0] = kid_dna;
+    return launch_gather_shards(c, order, P, 0, P, &par, &kid, 4, glad_obj, glad_fit, out_dna, out_obj, out_fit, st);
 }

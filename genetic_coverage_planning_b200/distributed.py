@@ -2,9 +2,16 @@
 
 Organisms are independent in evaluation, so each rank evaluates its own contiguous shard
 with replicated tables and NO collective.  Ranking is global: the per-organism objective
-records (16 B each) are all-gathered over NCCL/NVLink, every rank computes the maximin rows
-of its own shard against all columns, the fits are all-gathered, and every rank derives
-the identical stable order locally.
+records (16 B each) are all-gathered over NCCL/NVLink and every rank derives the identical
+maximin fitness and stable order locally.
+
+Whole generations (`ShardedEvolution`, geneticalgorithm.py:55-84): ONE population of P organisms,
+rank r holds parents [r P/W, (r+1) P/W) and builds, mutates and evaluates the children of the same
+range.  Per generation the ranks exchange exactly one NCCL all-gather of the children's objective
+records (16 B / organism) - chromosomes are never all-gathered: a crossover parent or a survivor
+that lives on another GPU is read by the kernel that needs it straight from the owner's memory
+over NVLink (shards are mapped into every rank with CUDA IPC, `gcp_shard_open`).  The same class
+with W = 1 is the single-GPU generation loop, so there is one code path.
 """
 import torch
 import torch.distributed as dist
@@ -96,60 +103,169 @@ def _all_gather(t, group=None):
     return buf.to(t.device)
 
 
-class DistributedEvolution(object):
-    """One generation of geneticalgorithm.py:55-76 with the CHILDREN sharded over the ranks.
+class ShardedEvolution(object):
+    """One population of `pop_size` organisms sharded over the ranks of `group` (or one GPU).
 
-    Parents (DNA, objectives, fitness) are replicated.  Every rank resamples the same parents
-    (lowVarSample, tiny), builds and evaluates only its own contiguous range of child pairs, then
-    the children's DNA and objective records are all-gathered (NCCL over NVLink) and every rank
-    derives the identical maximin fitness, stable order and survivors.  Philox streams are keyed
-    by GLOBAL organism ids (`vary_org_offset`), so the result is bit-identical to the single-GPU
-    generation with the same seed, for any number of ranks."""
+    State per rank: parents shard (double-buffered) and children shard, each [P/W, A, L] genes
+    (int16 when the waypoint ids fit and the fused evaluation kernel is in use, else int32), in
+    memory the peers can map; objective records [P, 2] and fitness [P] of the parents replicated.
 
-    def __init__(self, engine, gen_params, group=None):
+    One generation (`step`) on rank r - the reference lines are geneticalgorithm.py:59-84:
+      1. lowVarSample over the replicated fitness (tiny, identical on every rank)         :61
+      2. crossover of pairs [r P/2W, (r+1) P/2W): parents read through the shard table     :64-68
+         (peer loads over NVLink), children written to the local children shard
+      3. constructor variation + evaluation of the local children                          :156-171
+      4. NCCL all-gather of the children's objective records (16 B / organism)             :72
+      5. maximin over the 2P gladiators + stable order, replicated                         :86-123
+      6. truncation: survivors [r P/W, (r+1) P/W) are fetched from wherever they live       :83-84
+         (own or a peer's parents / children shard) into the second parents buffer
+      7. rendezvous of the ranks on the device (`gcp_peer_barrier`, flags in peer memory)
+    Philox streams are keyed by GLOBAL organism ids: the result is bit-identical for any W."""
+
+    def __init__(self, engine, gen_params, pop_size, group=None, gene_dtype=None, barrier="peer"):
         self.eng = engine
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank_id = dist.get_rank(group) if dist.is_initialized() else 0
+        on = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if on else 1
+        self.rank_id = dist.get_rank(group) if on else 0
+        self.P = int(pop_size)
+        if self.P % (2 * self.world):
+            raise ValueError("population %d must be a multiple of 2 x %d ranks" % (self.P, self.world))
+        if self.world > 16:
+            raise ValueError("at most 16 shards (one box)")
+        self.per = self.P // self.world
         self.gamma = gen_params['gamma']
         self.c0 = -gen_params['coverage_constr_0']
         self.cf = -gen_params['coverage_constr_f']
         self.aging = gen_params['coverage_aging']
+        if gene_dtype is None:
+            gene_dtype = torch.int16 if engine.gene16_available() else torch.int32
+        self.gene_dtype = gene_dtype
+        self.gb = 2 if gene_dtype == torch.int16 else 4
+        A, L, dev = engine.A, engine.L, engine.device
+        self.shape = (self.per, A, L)
+        nbytes = self.per * A * L * self.gb
+        if self.world == 1:
+            bufs = [torch.empty(self.shape, dtype=gene_dtype, device=dev) for _ in range(3)]
+            self._par = bufs[:2]
+            self._kid = bufs[2]
+            self._par_tab = [engine.shard_table([b.data_ptr()], self.per) for b in self._par]
+            self._kid_tab = engine.shard_table([self._kid.data_ptr()], self.per)
+            self._flag_tab = None
+        else:
+            own = [engine.shard_alloc(nbytes) for _ in range(3)] + [engine.shard_alloc(256)]
+            self._own = own
+            own[3].tensor.zero_()
+            torch.cuda.synchronize(dev)
+            mine = torch.tensor(list(b"".join(b.handle for b in own)), dtype=torch.uint8)
+            handles = _all_gather(mine.to(dev).view(1, -1), group).cpu().numpy()      # [W, 4 * 64]
+            ptrs = [[], [], [], []]
+            for w in range(self.world):
+                for k in range(4):
+                    ptrs[k].append(own[k].ptr if w == self.rank_id else
+                                   engine.shard_open(bytes(handles[w, 64 * k:64 * k + 64])))
+            self._par = [own[0].view(gene_dtype, self.shape), own[1].view(gene_dtype, self.shape)]
+            self._kid = own[2].view(gene_dtype, self.shape)
+            self._par_tab = [engine.shard_table(ptrs[0], self.per), engine.shard_table(ptrs[1], self.per)]
+            self._kid_tab = engine.shard_table(ptrs[2], self.per)
+            self._flag_tab = engine.shard_table(ptrs[3], 0)
+        self._cur = 0
+        # gladiator records: [0, P) parents, [P, 2P) children; double-buffered so that the
+        # truncation writes the next generation's parent records while it reads this one's
+        self._glad = [torch.zeros((2 * self.P, 2), dtype=torch.float64, device=dev) for _ in range(2)]
+        self._fit = [torch.zeros(self.P, dtype=torch.float64, device=dev) for _ in range(2)]
+        self._kid_obj = torch.empty((self.per, 2), dtype=torch.float64, device=dev)
+        self._kid_flags = torch.zeros((self.per, 4), dtype=torch.uint8, device=dev)
+        self._timed_out = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._epoch = 0
+        # two processes that share one GPU (single-GPU test boxes) time-slice it: a spinning
+        # barrier kernel would only burn the peer's slice, so they meet through the collective
+        self.barrier_mode = barrier if self.world > 1 else "none"
+        if self.world > 1 and dist.get_backend(group) != "nccl":
+            self.barrier_mode = "collective"
+        self._sync_buf = torch.zeros(1, device=dev)
+        self._sync()
+
+    # ---- state -------------------------------------------------------------------------
+    @property
+    def parents(self):
+        """this rank's parents shard [P/W, A, L] (gene dtype)."""
+        return self._par[self._cur]
+
+    @property
+    def obj(self):
+        return self._glad[self._cur][:self.P]
+
+    @property
+    def fit(self):
+        return self._fit[self._cur]
 
     def constraint(self, gen):
         alpha = min(1, gen / self.aging)                       # geneticalgorithm.py:98-100
         return (1 - alpha) * self.c0 + alpha * self.cf
 
-    def step(self, par_dna, par_obj, par_fit, seed, gen):
-        """-> (new parents dna [P,A,L], obj [P,2], fit [P]) replicated on all ranks."""
-        eng, P = self.eng, par_dna.shape[0]
-        half = P // 2
-        if half % self.world:
-            raise ValueError("pairs (%d) must divide evenly over %d ranks" % (half, self.world))
-        m = half // self.world
-        k0 = self.rank_id * m
-        r0 = float(eng.lib.gcp_low_var_r0(int(seed), int(gen), P))
-        strong = eng.low_var_select(par_fit, self.gamma, r0)
-        local = torch.cat([strong[k0:k0 + m], strong[half + k0:half + k0 + m]]).contiguous()
-        eng.set_option("vary_org_offset", 2 * k0)
-        try:
-            kids = eng.crossover(par_dna, local, seed, gen)    # [2m, A, L]: children 2k0 .. 2(k0+m)-1
-            eng.mutate(kids, seed, gen, salt=0)
-        finally:
-            eng.set_option("vary_org_offset", 0)
-        kid_obj = eng.evaluate(kids, detail=False).obj
+    def load(self, dna, gen=0):
+        """Install parents.  dna: [P, A, L] (every rank passes the same full population) or this
+        rank's [P/W, A, L] shard; any integer dtype.  Evaluates and ranks them."""
+        eng = self.eng
+        dna = torch.as_tensor(dna, device=eng.device)
+        if dna.shape[0] == self.P and self.world > 1:
+            dna = dna[self.rank_id * self.per:(self.rank_id + 1) * self.per]
+        if tuple(dna.shape) != self.shape:
+            raise ValueError("parents must be [%d or %d, %d, %d]" % ((self.P,) + self.shape))
+        self._par[self._cur].copy_(dna.to(self.gene_dtype))
+        obj = eng.evaluate_genes(self._par[self._cur]).obj
+        self._glad[self._cur][:self.P].copy_(_all_gather(obj, self.group) if self.world > 1 else obj)
+        self._fit[self._cur].copy_(eng.maximin(self.obj, self.constraint(gen)))
+        self._sync()
+
+    def gather_parents(self):
+        """Full population [P, A, L] int32 on every rank (host views, pickling - not the hot loop)."""
+        p = self.parents
         if self.world > 1:
-            if eng.pw.N <= 32767:
-                # waypoint ids (and the -1 padding) fit 16 bits: half the bytes on the wire for the
-                # one large exchange of a generation (2.5 GB of int32 at 8 x 65,536 organisms)
-                wire = kids.to(torch.int16).contiguous().view(torch.uint8)      # neither NCCL nor gloo moves int16
-                kids_all = _all_gather(wire, self.group).view(torch.int16).to(torch.int32)
-            else:
-                kids_all = _all_gather(kids, self.group)
-            kid_obj = _all_gather(kid_obj, self.group)
+            p = _all_gather(p.contiguous().view(torch.uint8).view(self.per, -1), self.group)
+            p = p.view(self.gene_dtype).view(self.P, self.shape[1], self.shape[2])
+        return p.to(torch.int32)
+
+    def _sync(self):
+        """Rendezvous: peers may touch this rank's shards only between two of these."""
+        if self.world == 1:
+            return
+        if self.barrier_mode == "peer":
+            self._epoch += 1
+            self.eng.peer_barrier(self._flag_tab, self.rank_id, self._epoch, self._timed_out)
+        elif dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(self._sync_buf, group=self.group)          # stream-ordered
         else:
-            kids_all = kids
-        glad_obj = torch.cat([par_obj, kid_obj])
-        fit = eng.maximin(glad_obj, self.constraint(gen))
+            torch.cuda.current_stream(self.eng.device).synchronize()
+            dist.barrier(group=self.group)
+
+    def check(self):
+        """Raises if a device rendezvous gave up waiting for a peer (host sync; call off the hot loop)."""
+        if int(self._timed_out.item()):
+            raise RuntimeError("gcp_peer_barrier timed out: a rank of the sharded population is gone")
+
+    # ---- one generation ------------------------------------------------------------------
+    def step(self, seed, gen):
+        eng, P, per, r = self.eng, self.P, self.per, self.rank_id
+        cur, nxt = self._cur, self._cur ^ 1
+        glad, glad_next = self._glad[cur], self._glad[nxt]
+        r0 = float(eng.lib.gcp_low_var_r0(int(seed), int(gen), P))
+        strong = eng.low_var_select(self._fit[cur], self.gamma, r0)
+        eng.crossover_shards(self._par_tab[cur], self.gb, strong, P, r * (per // 2), per // 2,
+                             seed, gen, self._kid)
+        eng.mutate_genes(self._kid, r * per, seed, gen, salt=0)
+        if self.world > 1:
+            eng.evaluate_genes(self._kid, self._kid_obj, self._kid_flags)
+            if dist.get_backend(self.group) == "nccl":
+                dist.all_gather_into_tensor(glad[P:], self._kid_obj, group=self.group)
+            else:
+                glad[P:].copy_(_all_gather(self._kid_obj, self.group))
+        else:
+            eng.evaluate_genes(self._kid, glad[P:], self._kid_flags)
+        fit = eng.maximin(glad, self.constraint(gen))
         order, _ = eng.arena_order(fit)
-        return eng.gather_survivors(order, par_dna, kids_all, glad_obj, fit)
+        eng.gather_shards(order, P, r * per, per, self._par_tab[cur], self._kid_tab, self.gb,
+                          glad, fit, self._par[nxt], glad_next, self._fit[nxt])
+        self._cur = nxt
+        self._sync()

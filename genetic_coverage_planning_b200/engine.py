@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import GcpEvalOut, GcpMapConsts, GcpParams, GcpVaryParams
+from ._lib import GcpEvalOut, GcpMapConsts, GcpParams, GcpShards, GcpVaryParams
 
 
 class GcpError(RuntimeError):
@@ -40,6 +40,30 @@ class EvalResult(object):
 
     def error(self):
         return self.flags[:, 3]
+
+
+class _RawCuda(object):
+    """Lets torch view device memory that libgcp.so allocated (gcp_shard_alloc)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1",
+                                         "data": (int(ptr), False), "version": 2}
+
+
+class ShardBuffer(object):
+    """Device memory owned by the engine's context that the other ranks of the box can map
+    (CUDA IPC).  `handle`: the 64-byte IPC handle to send to the peers; `tensor`: uint8 view."""
+
+    def __init__(self, engine, nbytes):
+        ptr = C.c_void_p()
+        h = (C.c_uint8 * 64)()
+        engine._check(engine.lib.gcp_shard_alloc(engine.ctx, int(nbytes), C.byref(ptr), h))
+        self.ptr, self.nbytes, self.handle = int(ptr.value), int(nbytes), bytes(h)
+        self.engine = engine
+        self.tensor = torch.as_tensor(_RawCuda(self.ptr, max(int(nbytes), 1)), device=engine.device)
+
+    def view(self, dtype, shape):
+        return self.tensor.view(dtype).view(*shape)
 
 
 class FitnessEngine(object):
@@ -168,6 +192,20 @@ class FitnessEngine(object):
                                       C.c_void_p(scratch.data_ptr()), scratch.numel(),
                                       self._stream()))
         return res
+
+    def raise_on_error(self, result=None, flags=None):
+        """The kernels report a gene outside [-1, N) (bit 0) or a coverage pass that ran out of
+        hash partitions (bit 1; its coverage is forced to 0) in flags[:, 3].  Raises GcpError if
+        any organism carries one.  Synchronises with the device: call it off the hot loop."""
+        f = result.flags if result is not None else flags
+        if f is None:
+            return
+        e = f[:, 3]
+        if bool((e != 0).any().item()):
+            k = int(torch.nonzero(e)[0].item())
+            raise GcpError("evaluation error flags set for %d organism(s), first at %d: %s"
+                           % (int((e != 0).sum().item()), k,
+                              "gene out of range" if int(e[k].item()) & 1 else "coverage pass overflow"))
 
     def evaluate_host(self, dna_host, obj_host=None, flags_host=None):
         """End-to-end call with HOST buffers (the reference-facing shape of the path):
@@ -365,6 +403,80 @@ class FitnessEngine(object):
             C.c_void_p(glad_fit.data_ptr()), C.c_void_p(out_dna.data_ptr()),
             C.c_void_p(out_obj.data_ptr()), C.c_void_p(out_fit.data_ptr()), self._stream()))
         return out_dna, out_obj, out_fit
+
+    # ---- population shards (multi-GPU generations) ---------------------------
+    def gene16_available(self):
+        """int16 chromosomes end to end (N <= 32767 and the fused objectives path)."""
+        return bool(self.lib.gcp_eval16_available(self.ctx))
+
+    def shard_alloc(self, nbytes):
+        return ShardBuffer(self, nbytes)
+
+    def shard_open(self, handle):
+        """Map a peer's ShardBuffer from its 64-byte IPC handle -> device pointer (int)."""
+        h = (C.c_uint8 * 64).from_buffer_copy(bytes(handle))
+        ptr = C.c_void_p()
+        self._check(self.lib.gcp_shard_open(self.ctx, h, C.byref(ptr)))
+        return int(ptr.value)
+
+    @staticmethod
+    def shard_table(ptrs, per_shard):
+        t = GcpShards()
+        t.world, t.per_shard = len(ptrs), int(per_shard)
+        for w, p in enumerate(ptrs):
+            t.base[w] = int(p)
+        return t
+
+    def evaluate_genes(self, dna, out_obj=None, out_flags=None):
+        """Objectives of a device chromosome tensor [P,A,L], int16 (fused path) or int32."""
+        if dna.dtype == torch.int32:
+            r = self.evaluate(dna, detail=False)
+            if out_obj is not None:
+                out_obj.copy_(r.obj)
+                r.obj = out_obj
+            return r
+        assert dna.is_cuda and dna.dtype == torch.int16 and dna.is_contiguous()
+        P = dna.shape[0]
+        res = EvalResult()
+        res.obj = out_obj if out_obj is not None else torch.empty((P, 2), dtype=torch.float64, device=self.device)
+        res.flags = out_flags if out_flags is not None else torch.zeros((P, 4), dtype=torch.uint8, device=self.device)
+        res.neg_cov = res.dist = res.turn = res.cov = res.lc_mat = None
+        out = GcpEvalOut()
+        out.obj = res.obj.data_ptr()
+        out.flags = res.flags.data_ptr()
+        self._check(self.lib.gcp_eval16(self.ctx, C.c_void_p(dna.data_ptr()), P, C.byref(out),
+                                        self._stream()))
+        return res
+
+    def crossover_shards(self, parents_tab, gene_bytes, strong, n_org_global, pair_begin, n_pairs,
+                         seed, gen, children):
+        """children: device gene tensor [2 * n_pairs, A, L] (written)."""
+        self._check(self.lib.gcp_crossover_shards(
+            self.ctx, C.byref(parents_tab), int(gene_bytes), C.c_void_p(strong.data_ptr()),
+            int(n_org_global), int(pair_begin), int(n_pairs), int(seed), int(gen),
+            C.c_void_p(children.data_ptr()), self._stream()))
+        return children
+
+    def mutate_genes(self, dna, org_offset, seed, gen, salt=0):
+        assert dna.is_cuda and dna.is_contiguous() and dna.dtype in (torch.int16, torch.int32)
+        self._check(self.lib.gcp_mutate_genes(
+            self.ctx, C.c_void_p(dna.data_ptr()), dna.element_size(), dna.shape[0], int(org_offset),
+            int(seed), int(gen), int(salt), self._stream()))
+        return dna
+
+    def gather_shards(self, order, n_org_global, k_begin, n_local, parents_tab, children_tab,
+                      gene_bytes, glad_obj, glad_fit, out_dna, out_obj, out_fit):
+        self._check(self.lib.gcp_gather_shards(
+            self.ctx, C.c_void_p(order.data_ptr()), int(n_org_global), int(k_begin), int(n_local),
+            C.byref(parents_tab), C.byref(children_tab), int(gene_bytes),
+            C.c_void_p(glad_obj.data_ptr()), C.c_void_p(glad_fit.data_ptr()),
+            C.c_void_p(out_dna.data_ptr()),
+            C.c_void_p(out_obj.data_ptr()) if out_obj is not None else None,
+            C.c_void_p(out_fit.data_ptr()) if out_fit is not None else None, self._stream()))
+
+    def peer_barrier(self, flags_tab, rank, epoch, timed_out):
+        self._check(self.lib.gcp_peer_barrier(self.ctx, C.byref(flags_tab), int(rank), int(epoch),
+                                              C.c_void_p(timed_out.data_ptr()), self._stream()))
 
     # ------------------------------------------------------------------
     def set_option(self, name, value):

@@ -27,23 +27,29 @@ from . import packing
 from .engine import FitnessEngine
 
 _ENGINES = {}
+_MAX_ENGINES = 4        # each holds the packed tables of one world on the GPU
 
 
 def _engine_for(mappy, pather, org_params, num_agents, device=0):
-    """One engine (packed tables + CUDA context) per (mappy, pather, A, L, device)."""
+    """One engine (packed tables + CUDA context) per (mappy, pather, A, L, device).  The scalar
+    parameters (constraints, variation probabilities, coverage blend, ...) are refreshed on every
+    call, so two populations on the same world with different parameters do not share them."""
     key = (id(mappy), id(pather), int(num_agents), int(org_params['max_dna_len']), int(device))
     ent = _ENGINES.get(key)
+    path_params = {'path_memory': getattr(pather, '_path_memory', 10),
+                   'log_scale_weight': getattr(pather, '_log_scale_weight', 0.7)}
     if ent is None or ent[1] is not mappy or ent[2] is not pather:
         pw = packing.pack_from_reference(mappy, pather)
         eng = FitnessEngine(pw, org_params, num_agents=num_agents, device=device)
-        path_params = {'path_memory': getattr(pather, '_path_memory', 10),
-                       'log_scale_weight': getattr(pather, '_log_scale_weight', 0.7)}
-        eng.set_vary_params(org_params, path_params)
         ent = (eng, mappy, pather)
+        while len(_ENGINES) >= _MAX_ENGINES:              # oldest first; its tables are freed with it
+            _ENGINES.pop(next(iter(_ENGINES)))
         _ENGINES[key] = ent
-    else:
-        ent[0].set_params(org_params)
-    return ent[0]
+    eng = ent[0]
+    eng.set_params(org_params, solo_sep_thresh=getattr(mappy, '_solo_sep_thresh', None),
+                   blend=getattr(mappy, '_coverage_blend', None))
+    eng.set_vary_params(org_params, path_params)
+    return eng
 
 
 def _pad_rows(dna_list, L):
@@ -100,6 +106,7 @@ class Organism(object):
         """geneticalgorithm.py:177-201 on the GPU."""
         eng = _engine_for(self._mappy, self._pather, self._org_params, self._num_agents)
         r = eng.evaluate(self._dna[None].astype(np.int32), detail=False)
+        eng.raise_on_error(r)
         o = r.obj[0].cpu().numpy()
         return [float(o[0]), float(o[1])]
 
@@ -118,7 +125,9 @@ class Organism(object):
 
 
 class GeneticalGorithm(object):
-    """geneticalgorithm.py:15-123."""
+    """geneticalgorithm.py:15-123.  The population lives on the GPU(s): under torch.distributed
+    (one process per GPU) it is ONE population sharded over the ranks (distributed.ShardedEvolution);
+    every rank must construct it with the same arguments - the seed is taken from rank 0."""
 
     def __init__(self, mappy, pather, gen_params, device=0, seed=None, initial_dna=None, gen_num=0):
         self._G_sz = gen_params['gen_size']
@@ -132,18 +141,30 @@ class GeneticalGorithm(object):
         self._mappy, self._pather = mappy, pather
         self._device = device
         self._seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
+        self._seed = _same_on_all_ranks(self._seed, device)
         self._gen_num = int(gen_num)
         self._views = None
+        self._dna_cache = None
         if self._G_sz % 2:
             raise ValueError("gen_size must be even (pather_driver.py:107)")
         self._eng = _engine_for(mappy, pather, self._org_params, self._num_agents, device)
+        self._evo = self._new_evo()
         if initial_dna is not None:
-            self._dna = self._eng.to_device_dna(initial_dna).clone()
-            self._obj = self._eng.evaluate(self._dna, detail=False).obj
+            dna = self._eng.to_device_dna(initial_dna)
         else:
-            self.firstGeneration(mappy, pather, self._org_params)
-        self._fit, self._obj_sc = self._eng.maximin(self._obj, self._coverage_constr(),
-                                                    return_scaled=True)
+            dna = self.firstGeneration(mappy, pather, self._org_params)
+        self._evo.load(dna, self._gen_num)
+        self._obj_sc = self._scaled()
+
+    def _new_evo(self):
+        from .distributed import ShardedEvolution
+        return ShardedEvolution(self._eng, {'gamma': self._gamma,
+                                            'coverage_constr_0': -self._cov_constr_0,
+                                            'coverage_constr_f': -self._cov_constr_f,
+                                            'coverage_aging': self._cov_aging}, self._G_sz)
+
+    def _scaled(self):
+        return self._eng.maximin(self._evo.obj, self._coverage_constr(), return_scaled=True)[1]
 
     @classmethod
     def from_population(cls, population, gen_params=None, device=0, seed=None):
@@ -171,73 +192,48 @@ class GeneticalGorithm(object):
     # -- reference: geneticalgorithm.py:37-53 ------------------------------------------
     def firstGeneration(self, mappy, pather, org_params, max_batches=10000):
         """Random paths + constructor variation + evaluation in batches, keeping the
-        candidates that meet the initial coverage constraint (:50), in generation order."""
+        candidates that meet the initial coverage constraint (:50), in generation order.
+        Returns the [P, A, L] int32 chromosomes (identical on every rank: same seed)."""
         eng, P = self._eng, self._G_sz
         start = org_params['start_idx']
-        got_dna, got_obj, n = [], [], 0
+        got_dna, n = [], 0
         batch_sz = int(min(max(2 * P, 256), 1 << 16))
         for b in range(max_batches):
             dna = eng.random_walks(batch_sz, start, self._starting_path_len, self._seed, batch=b)
             eng.mutate(dna, self._seed, 0xFFFF0000 + b, salt=3)
-            obj = eng.evaluate(dna, detail=False).obj
-            ok = obj[:, 0] <= self._cov_constr_0
+            r = eng.evaluate(dna, detail=False)
+            eng.raise_on_error(r)
+            ok = r.obj[:, 0] <= self._cov_constr_0
             k = int(ok.sum().item())
             if k:
                 got_dna.append(dna[ok])
-                got_obj.append(obj[ok])
                 n += k
             if n >= P:
                 break
         if n < P:
             raise RuntimeError("firstGeneration: only %d of %d organisms met coverage >= %g"
                                % (n, P, -self._cov_constr_0))
-        self._dna = torch.cat(got_dna)[:P].contiguous()
-        self._obj = torch.cat(got_obj)[:P].contiguous()
+        return torch.cat(got_dna)[:P].contiguous()
 
     def _coverage_constr(self):
         alpha = min(1, (self._gen_num / self._cov_aging))                    # :98
         return (1 - alpha) * self._cov_constr_0 + alpha * self._cov_constr_f  # :99-100
 
     # -- reference: geneticalgorithm.py:55-76 ------------------------------------------
-    def _sharded(self):
-        """Under torch.distributed (one process per GPU, same seed on every rank) the children
-        of each generation are split over the ranks; the population stays replicated and the
-        result is bit-identical to a single-GPU run (distributed.DistributedEvolution)."""
-        import torch.distributed as dist
-        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
-            return None
-        if (self._G_sz // 2) % dist.get_world_size():
-            return None
-        from .distributed import DistributedEvolution
-        return DistributedEvolution(self._eng, {'gamma': self._gamma,
-                                                'coverage_constr_0': -self._cov_constr_0,
-                                                'coverage_constr_f': -self._cov_constr_f,
-                                                'coverage_aging': self._cov_aging})
-
     def runEvolution(self, num_generations):
-        eng, P = self._eng, self._G_sz
+        evo = self._evo
         hist_dev = []
-        sharded = self._sharded()
         for _ in range(num_generations):
-            if sharded is not None:
-                self._dna, self._obj, self._fit = sharded.step(self._dna, self._obj, self._fit,
-                                                               self._seed, self._gen_num)
-                _, sc = eng.maximin(self._obj, self._coverage_constr(), return_scaled=True)
-                self._obj_sc = sc
-            else:
-                kids = eng.select_vary(self._dna, self._fit, self._gamma, self._seed, self._gen_num)
-                kid_obj = eng.evaluate(kids, detail=False).obj
-                glad_obj = torch.cat([self._obj, kid_obj])                    # arena :72
-                fit, sc = eng.maximin(glad_obj, self._coverage_constr(), return_scaled=True)
-                order, _ = eng.arena_order(fit)
-                self._dna, self._obj, self._fit = eng.gather_survivors(order, self._dna, kids,
-                                                                       glad_obj, fit)
-                self._obj_sc = sc[order[:P].long()]
+            evo.step(self._seed, self._gen_num)          # select -> crossover -> variation -> evaluate -> arena
             self._gen_num += 1
-            hist_dev.append(self._obj)
+            hist_dev.append(evo.obj.clone())
         self._views = None
+        self._dna_cache = None
         if not hist_dev:
             return []
+        self._obj_sc = self._scaled()
+        evo.check()
+        self._eng.raise_on_error(flags=evo._kid_flags)    # chromosome / coverage-pass errors of the last children
         flat = torch.stack(hist_dev).cpu().numpy()                            # one D2H at the end
         return [[[float(o[0]), float(o[1])] for o in gen] for gen in flat]
 
@@ -259,17 +255,13 @@ class GeneticalGorithm(object):
         order, _ = self._eng.arena_order(torch.tensor(fits, dtype=torch.float64))
         order = order.cpu().numpy()[:self._G_sz]
         keep = [gladiators[i] for i in order]
-        self._dna = self._eng.to_device_dna(np.stack([g._dna for g in keep]).astype(np.int32))
-        self._obj = torch.tensor([[float(g._obj_val[0]), float(g._obj_val[1])] for g in keep],
-                                 dtype=torch.float64, device=self._eng.device)
-        self._fit = torch.tensor([fits[i] for i in order], dtype=torch.float64,
-                                 device=self._eng.device)
-        self._obj_sc = torch.tensor([g._obj_val_sc for g in keep], dtype=torch.float64,
-                                    device=self._eng.device)
+        self._evo.load(np.stack([g._dna for g in keep]).astype(np.int32), self._gen_num)
+        self._obj_sc = self._scaled()
         self._views = None
+        self._dna_cache = None
 
-    # -- attributes the reference's plotting / export code reads -------------------------
-    _LAZY = ('_eng', '_dna', '_obj', '_fit', '_obj_sc')
+    # -- device state ------------------------------------------------------------------------
+    _LAZY = ('_eng', '_evo', '_obj_sc')
 
     def __getattr__(self, name):
         # after unpickling, the CUDA context and the device tensors are created on first use, so a
@@ -283,11 +275,24 @@ class GeneticalGorithm(object):
         dna, obj, fit, sc = self.__dict__.pop('_host_state')
         self._eng = _engine_for(self._mappy, self._pather, self._org_params, self._num_agents,
                                 self._device)
-        dev = self._eng.device
-        self._dna = torch.from_numpy(dna).to(dev)
-        self._obj = torch.from_numpy(obj).to(dev)
-        self._fit = torch.from_numpy(fit).to(dev)
-        self._obj_sc = torch.from_numpy(sc).to(dev)
+        self._evo = self._new_evo()
+        self._evo.load(dna, self._gen_num)
+        self._obj_sc = self._scaled()
+
+    @property
+    def _dna(self):
+        """[P, A, L] int32 device tensor of all parents (gathered from the shards on first use)."""
+        if self.__dict__.get('_dna_cache') is None:
+            self._dna_cache = self._evo.gather_parents()
+        return self._dna_cache
+
+    @property
+    def _obj(self):
+        return self._evo.obj
+
+    @property
+    def _fit(self):
+        return self._evo.fit
 
     def _host_arrays(self):
         if '_host_state' in self.__dict__:
@@ -315,8 +320,8 @@ class GeneticalGorithm(object):
 
     # -- pickle (gori_tools.py:252-257): device state round-trips through numpy ----------
     def __getstate__(self):
-        st = {k: v for k, v in self.__dict__.items() if k not in ('_eng', '_views', '_dna', '_obj',
-                                                                   '_fit', '_obj_sc', '_host_state')}
+        st = {k: v for k, v in self.__dict__.items() if k not in ('_eng', '_evo', '_views', '_dna_cache',
+                                                                   '_obj_sc', '_host_state')}
         dna, obj, fit, sc = self._host_arrays()
         st['_dna_np'], st['_obj_np'], st['_fit_np'], st['_obj_sc_np'] = dna, obj, fit, sc
         return st
@@ -326,7 +331,19 @@ class GeneticalGorithm(object):
         host = (st.pop('_dna_np'), st.pop('_obj_np'), st.pop('_fit_np'), st.pop('_obj_sc_np'))
         self.__dict__.update(st)
         self._views = None
+        self._dna_cache = None
         self.__dict__['_host_state'] = host        # device side is created on first use (_materialise)
+
+
+def _same_on_all_ranks(seed, device):
+    """Under torch.distributed every rank must draw the same population: rank 0's seed wins."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return seed
+    dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor([seed], dtype=torch.int64, device=dev)
+    dist.broadcast(t, src=0)
+    return int(t.item())
 
 
 def getObjValsList(population):

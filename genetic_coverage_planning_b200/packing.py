@@ -22,6 +22,8 @@ Block layout (device): block b = by*nbx + bx covers x in [64bx,64bx+64), y in
 rows 2l,2l+1 (one 16-byte word).  A *quarter* is 16 rows = 128 B = one cache line.
 A sub-tile stores only its non-empty quarters; `payload = (offset128 << 4) | qmask`.
 """
+import os
+
 import numpy as np
 
 BLK = 64
@@ -80,8 +82,9 @@ class PackedWorld(object):
 
 
 def pack_world(img, xy, row_ptr, col, edge_poly, edge_theta, edge_dist, map_params,
-               progress=False):
-    import cv2
+               progress=False, workers=None):
+    """workers: processes for the footprint rasterisation (None = all host cores for big worlds,
+    1 for small ones); the result does not depend on it."""
     pw = PackedWorld()
     img = np.ascontiguousarray(img, dtype=np.float64)
     H, W = img.shape
@@ -149,19 +152,82 @@ def pack_world(img, xy, row_ptr, col, edge_poly, edge_theta, edge_dist, map_para
     polys = np.concatenate([edge_poly, np.zeros((N, nv, 2), dtype=np.int32)]) if E else \
         np.zeros((N, nv, 2), dtype=np.int32)
     node = np.concatenate([src, np.arange(N, dtype=np.int64)])
-    cx = pw.xy[node, 1].astype(np.int64)                # center = (int(loc[1]), int(loc[0]))
-    cy = pw.xy[node, 0].astype(np.int64)
+    job = dict(polys=polys, cx=pw.xy[node, 1].astype(np.int64),      # center = (int(loc[1]), int(loc[0]))
+               cy=pw.xy[node, 0].astype(np.int64), reach=reach, H=H, W=W, nbx=nbx,
+               blk_mask_all=blk_mask_all)                            # host only: pre-masked footprint store
+    EN = E + N
+    if workers is None:
+        workers = min(os.cpu_count() or 1, 32) if EN >= 20000 else 1
+    if workers > 1:
+        # every edge is rasterised independently: fan the edge range out over forked processes
+        # (the tables are inherited, not pickled) and stitch the per-range stores together
+        import multiprocessing as mp
+        global _JOB
+        _JOB = job
+        bounds = np.linspace(0, EN, workers * 4 + 1).astype(np.int64)
+        ranges = [(int(bounds[k]), int(bounds[k + 1])) for k in range(len(bounds) - 1) if bounds[k + 1] > bounds[k]]
+        try:
+            with mp.get_context("fork").Pool(workers) as pool:
+                parts = pool.map(_rasterise_range, ranges)
+        finally:
+            _JOB = None
+    else:
+        parts = [_rasterise_edges(job, 0, EN, progress)]
+    sub_cnt = np.concatenate([p_['sub_cnt'] for p_ in parts])
+    m_sub_cnt = np.concatenate([p_['m_sub_cnt'] for p_ in parts])
+    off128 = m_off128 = 0
+    pay, m_pay = [], []
+    for p_ in parts:                                     # payload = (offset128 << 4) | qmask: rebase the offsets
+        pay.append(p_['sub_payload'] + (np.uint64(off128) << np.uint64(4)))
+        m_pay.append(p_['m_sub_payload'] + (np.uint64(m_off128) << np.uint64(4)))
+        off128 += p_['n_q']
+        m_off128 += p_['m_n_q']
+    if off128 >= (1 << 28):
+        raise ValueError("footprint store exceeds 2^28 quarters (32 GiB)")
+    sub_ptr = np.zeros(EN + 1, dtype=np.int64)
+    np.cumsum(sub_cnt, out=sub_ptr[1:])
+    m_sub_ptr = np.zeros(EN + 1, dtype=np.int64)
+    np.cumsum(m_sub_cnt, out=m_sub_ptr[1:])
+    pw.sub_ptr = sub_ptr.astype(np.uint32)
+    pw.sub_block = np.concatenate([p_['sub_block'] for p_ in parts]).astype(np.uint32)
+    pw.sub_payload = np.concatenate(pay).astype(np.uint32)
+    pw.tile_data = np.concatenate([p_['tile'] for p_ in parts]).astype('<u8')
+    pw.n_quarters = off128
+    pw.edge_pixels = np.concatenate([p_['n_pix'] for p_ in parts])
+    pw.max_sub_per_edge = int(sub_cnt.max()) if EN else 0
+    if m_off128 >= (1 << 27):
+        raise ValueError("masked footprint store exceeds 2^27 quarters")
+    pw.m_sub_ptr = m_sub_ptr.astype(np.uint32)
+    pw.m_sub_block = np.concatenate([p_['m_sub_block'] for p_ in parts]).astype(np.uint32)
+    pw.m_sub_payload = np.concatenate(m_pay).astype(np.uint32)
+    pw.m_tile_data = np.concatenate([p_['m_tile'] for p_ in parts]).astype('<u8')
+    pw.m_n_quarters = m_off128
+    return pw
+
+
+_JOB = None
+
+
+def _rasterise_range(r):
+    return _rasterise_edges(_JOB, r[0], r[1], False)
+
+
+def _rasterise_edges(job, e0, e1, progress=False):
+    """Footprint sub-tiles of edges [e0, e1) (ids >= E are the null edges): both stores, with
+    quarter offsets relative to this range."""
+    import cv2
+    polys, cx, cy, reach = job['polys'], job['cx'], job['cy'], job['reach']
+    H, W, nbx, blk_mask_all = job['H'], job['W'], job['nbx'], job['blk_mask_all']
     kb = (2 * reach) // BLK + 2                         # canvas blocks per side
     canvas = np.zeros((kb * BLK, kb * BLK), dtype=np.uint8)
-    sub_ptr = np.zeros(E + N + 1, dtype=np.int64)
+    n = e1 - e0
+    sub_cnt = np.zeros(n, dtype=np.int64)
+    m_sub_cnt = np.zeros(n, dtype=np.int64)
+    n_pix = np.zeros(n, dtype=np.int32)
     sub_block, sub_payload, chunks = [], [], []
-    off128 = 0
-    # second store: footprint AND buffer_mask (wall-coverage fast path; union and AND commute)
-    m_sub_ptr = np.zeros(E + N + 1, dtype=np.int64)
     m_sub_block, m_sub_payload, m_chunks = [], [], []
-    m_off128 = 0
-    n_pix = np.zeros(E + N, dtype=np.int32)
-    it = range(E + N)
+    off128 = m_off128 = 0
+    it = range(e0, e1)
     if progress:
         from tqdm import tqdm
         it = tqdm(it, desc="rasterising footprints")
@@ -204,26 +270,16 @@ def pack_world(img, xy, row_ptr, col, edge_poly, edge_theta, edge_dist, map_para
                     m_chunks.append(mblk.reshape(4, 16)[mq].reshape(-1).copy())
                     m_off128 += int(mq.sum())
                     m_n_sub += 1
-        n_pix[e] = int(canvas.sum())
-        sub_ptr[e + 1] = sub_ptr[e] + n_sub
-        m_sub_ptr[e + 1] = m_sub_ptr[e] + m_n_sub
-    if off128 >= (1 << 28):
-        raise ValueError("footprint store exceeds 2^28 quarters (32 GiB)")
-    pw.sub_ptr = sub_ptr.astype(np.uint32)
-    pw.sub_block = np.array(sub_block, dtype=np.uint32)
-    pw.sub_payload = np.array(sub_payload, dtype=np.uint32)
-    pw.tile_data = (np.concatenate(chunks) if chunks else np.zeros(0, dtype='<u8')).astype('<u8')
-    pw.n_quarters = off128
-    pw.edge_pixels = n_pix
-    pw.max_sub_per_edge = int(np.diff(sub_ptr).max()) if E + N else 0
-    if m_off128 >= (1 << 27):
-        raise ValueError("masked footprint store exceeds 2^27 quarters")
-    pw.m_sub_ptr = m_sub_ptr.astype(np.uint32)
-    pw.m_sub_block = np.array(m_sub_block, dtype=np.uint32)
-    pw.m_sub_payload = np.array(m_sub_payload, dtype=np.uint32)
-    pw.m_tile_data = (np.concatenate(m_chunks) if m_chunks else np.zeros(0, dtype='<u8')).astype('<u8')
-    pw.m_n_quarters = m_off128
-    return pw
+        n_pix[e - e0] = int(canvas.sum())
+        sub_cnt[e - e0] = n_sub
+        m_sub_cnt[e - e0] = m_n_sub
+    z64 = np.zeros(0, dtype='<u8')
+    return dict(sub_cnt=sub_cnt, m_sub_cnt=m_sub_cnt, n_pix=n_pix, n_q=off128, m_n_q=m_off128,
+                sub_block=np.array(sub_block, dtype=np.int64), sub_payload=np.array(sub_payload, dtype=np.uint64),
+                tile=np.concatenate(chunks) if chunks else z64,
+                m_sub_block=np.array(m_sub_block, dtype=np.int64),
+                m_sub_payload=np.array(m_sub_payload, dtype=np.uint64),
+                m_tile=np.concatenate(m_chunks) if m_chunks else z64)
 
 
 def pack_from_reference(mappy, pather, progress=False):

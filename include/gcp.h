@@ -29,9 +29,10 @@
 extern "C" {
 #endif
 
-#define GCP_ABI_VERSION 1
+#define GCP_ABI_VERSION 2
 #define GCP_MAX_AGENTS 32
 #define GCP_INVALID_EDGE 0xFFFFFFFFu
+#define GCP_MAX_SHARDS 16
 
 typedef struct gcp_ctx gcp_ctx;
 
@@ -139,6 +140,8 @@ int    gcp_eval(gcp_ctx* ctx, const int32_t* dna_dev, uint32_t n_org,
  * (pre-masked footprints uploaded, coverage_blend == 1, out->cov == NULL). */
 int    gcp_eval16(gcp_ctx* ctx, const int16_t* dna_dev, uint32_t n_org, const gcp_eval_out* out,
                   void* stream);
+/* 1 if gcp_eval16 can run with the tables / parameters uploaded so far, else 0. */
+int    gcp_eval16_available(gcp_ctx* ctx);
 /* Individual stages (same buffers; used by tests / profiling). edge_ids: dev u32 [P][A][L];
  * step_info (optional, needs the masked store): dev u32 [P][A][L], per step the masked
  * sub-tile range of its edge (first | count<<28), 0 where no step is executed. */
@@ -214,6 +217,59 @@ int gcp_gather_survivors(gcp_ctx* ctx, const int32_t* order_dev, uint32_t n_org,
                          const int32_t* parents_dna_dev, const int32_t* children_dna_dev,
                          const double* glad_obj_dev, const double* glad_fit_dev,
                          int32_t* out_dna_dev, double* out_obj_dev, double* out_fit_dev, void* stream);
+
+/* ---- population shards over the GPUs of one box ------------------------------
+ * The reference keeps ONE population (geneticalgorithm.py:28-32,55-84).  Here rank r of `world`
+ * holds parents [r*per, (r+1)*per) and builds / evaluates children of the same range; objective
+ * and fitness records (24 B / organism) are replicated; chromosomes never leave the GPU that
+ * produced them except when another rank needs them as a crossover parent or as a survivor of
+ * its own range - and then the kernel reads them from the owner's memory over NVLink (peer
+ * memory mapped with CUDA IPC).  There is no chromosome all-gather.
+ *
+ * gcp_shards describes one logical [world * per_shard][A][L] gene array: base[w] is shard w as
+ * mapped into THIS process (own shard: the pointer gcp_shard_alloc returned, peers: gcp_shard_open).
+ * world == 1 is a plain array.  Genes are int16 (gene_bytes 2, needs N <= 32767 waypoints) or
+ * int32 (gene_bytes 4), -1 padded. */
+typedef struct gcp_shards {
+    uint32_t    world;                 /* number of shards, <= GCP_MAX_SHARDS */
+    uint32_t    per_shard;             /* organisms per shard */
+    const void* base[GCP_MAX_SHARDS];  /* dev */
+} gcp_shards;
+/* device memory that other processes of the box can map: cudaMalloc + cudaIpcGetMemHandle.
+ * ipc_handle: host, 64 bytes (cudaIpcMemHandle_t), to be sent to the peers by the caller
+ * (e.g. torch.distributed all-gather).  Freed by gcp_shard_free or gcp_destroy. */
+int gcp_shard_alloc(gcp_ctx* ctx, size_t bytes, void** dev_ptr, uint8_t ipc_handle[64]);
+int gcp_shard_free(gcp_ctx* ctx, void* dev_ptr);
+/* map a peer's shard (same or another GPU of the box; peer access is enabled on demand). */
+int gcp_shard_open(gcp_ctx* ctx, const uint8_t ipc_handle[64], void** dev_ptr);
+int gcp_shard_close(gcp_ctx* ctx, void* dev_ptr);
+/* Organism.crossover for pairs [pair_begin, pair_begin + n_pairs) of the n_org_global / 2 pairs
+ * (geneticalgorithm.py:64-68): pair k = (strong[k], strong[k + n_org_global / 2]), parents read
+ * through the shard table, children 2 (k - pair_begin), +1 written to children_dev
+ * [2 * n_pairs][A][L].  Philox streams are keyed by the GLOBAL pair id: any sharding gives the
+ * children a single GPU would build.  strong_idx_dev: dev int32 [n_org_global]. */
+int gcp_crossover_shards(gcp_ctx* ctx, const gcp_shards* parents, int gene_bytes,
+                         const int32_t* strong_idx_dev, uint32_t n_org_global, uint32_t pair_begin,
+                         uint32_t n_pairs, uint64_t seed, uint32_t generation, void* children_dev,
+                         void* stream);
+/* gcp_mutate on int16 or int32 genes; org_offset = global id of local organism 0 (Philox keys). */
+int gcp_mutate_genes(gcp_ctx* ctx, void* dna_dev, int gene_bytes, uint32_t n_org, uint32_t org_offset,
+                     uint64_t seed, uint32_t generation, uint32_t salt, void* stream);
+/* arena truncation (geneticalgorithm.py:83-84) for survivors [k_begin, k_begin + n_local): out_dna
+ * [n_local][A][L] = gladiator[order[k]], gladiators = parents ++ children, both sharded (a peer's
+ * organism is read over NVLink).  out_obj [n_org_global][2] / out_fit [n_org_global] (optional, both
+ * or neither) receive the records of ALL survivors. */
+int gcp_gather_shards(gcp_ctx* ctx, const int32_t* order_dev, uint32_t n_org_global, uint32_t k_begin,
+                      uint32_t n_local, const gcp_shards* parents, const gcp_shards* children,
+                      int gene_bytes, const double* glad_obj_dev, const double* glad_fit_dev,
+                      void* out_dna_dev, double* out_obj_dev, double* out_fit_dev, void* stream);
+/* Rendezvous of the ranks on the device, without a host round trip or a collective library: every
+ * rank owns `world` u32 flags in shard memory; the kernel stores `epoch` into slot `rank` of every
+ * peer's flags (system-scope release) and waits until all of its own slots hold >= epoch.  Work
+ * enqueued after it on this stream sees everything the peers wrote before their barrier.  A peer
+ * that does not arrive within ~2 s makes the kernel give up and set *timed_out_dev (dev u32). */
+int gcp_peer_barrier(gcp_ctx* ctx, const gcp_shards* flags, uint32_t rank, uint32_t epoch,
+                     uint32_t* timed_out_dev, void* stream);
 
 /* ---- tuning / testing knobs (defaults are right for production) ---------------------
  * "rank_algo": 0 auto, 1 O(N^2) dominance-matrix tiles, 2 sort-based O(N log N) (both exact);
