@@ -168,7 +168,7 @@ class ShardedEvolution(object):
             self._kid = own[2].view(gene_dtype, self.shape)
             self._par_tab = [engine.shard_table(ptrs[0], self.per), engine.shard_table(ptrs[1], self.per)]
             self._kid_tab = engine.shard_table(ptrs[2], self.per)
-            self._flag_tab = engine.shard_table(ptrs[3], 0)
+            self._flag_tab = engine.shard_table(ptrs[3], 1)
         self._cur = 0
         # gladiator records: [0, P) parents, [P, 2P) children; double-buffered so that the
         # truncation writes the next generation's parent records while it reads this one's
