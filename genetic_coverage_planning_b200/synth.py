@@ -224,6 +224,19 @@ def spread_starts(xy, n, size):
     return out
 
 
+def clustered_starts(xy, row_ptr, n, size):
+    """n start waypoints next to each other near the map centre (the reference's own C1 set-up
+    starts several agents from one waypoint, pather_driver.py:125-134): agents that start
+    together share edges, so inter-agent loop closures - and feasible organisms - occur.
+    Waypoints with at least 3 out-edges are preferred (walks need room to diverge)."""
+    c = np.array([size / 2.0, size / 2.0])
+    d2 = ((np.asarray(xy, dtype=np.float64) - c) ** 2).sum(1)
+    deg = np.diff(np.asarray(row_ptr, dtype=np.int64))
+    order = np.argsort(d2 + np.where(deg >= 3, 0.0, 1e18), kind='stable')
+    k = max(1, (n + 1) // 2)                     # two agents per start waypoint
+    return [int(order[a // 2 % k]) for a in range(n)]
+
+
 def random_walk_population(xy, row_ptr, col, starts, n_org, walk_len, max_dna_len, seed=1,
                            path_memory=10, log_scale_weight=0.7, chunk=65536):
     """[n_org, A, max_dna_len] int32, -1 padded.  Each row is a heading-biased walk of

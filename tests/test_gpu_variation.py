@@ -63,8 +63,17 @@ def test_low_var_select_golden(world_big, golden_dir):
     fit = rs.randn(5000) * 0.3
     got = eng.low_var_select(torch.from_numpy(fit), 0.5, 0.5 / 5000).cpu().numpy()
     want = fo.low_var_sample_indices(fit, 0.5, 0.5 / 5000)
-    assert (got != want).mean() < 0.002 and np.abs(got - want).max() <= 1
-    assert (np.diff(got) >= 0).all()
+    assert np.array_equal(got, want)
+    # the BASELINE population, random and heavily tied fitness: measured mismatch rate
+    # of the parallel cumulate against the reference's sequential `c += w[i]` is 0
+    # (profiles/probe_r02a.jsonl); demand equality
+    for kind in ("randn", "ties"):
+        rs = np.random.RandomState(65536)
+        fit = rs.randn(65536) * 0.3
+        if kind == "ties":
+            fit[rs.rand(65536) < 0.7] = 0.25
+        got = eng.low_var_select(torch.from_numpy(fit), 0.5, 0.37 / 65536).cpu().numpy()
+        assert np.array_equal(got, fo.low_var_sample_indices(fit, 0.5, 0.37 / 65536)), kind
 
 
 def _parents(world, eng, P, walk=150, seed=3):
@@ -450,3 +459,141 @@ def test_legacy_reference_pickle_migrates(golden_dir):
     assert np.array_equal(np.asarray(pop._gen_parent_fit), want)
     hist = pop.runEvolution(2)                                 # and evolution continues
     assert pop._gen_num == int(z['gen_num']) + 2 and len(hist) == 2 and len(hist[0]) == len(z['dna'])
+
+
+# ---------------------------------------------------------------------------------------------
+# Distributions of the Philox kernels against samples drawn from the UNMODIFIED reference
+# (tests/golden/make_golden_variation_dist.py -> variation_dist.npz, config C1).  Two-sample
+# chi-square on statistics that are functions of the output rows only; rare categories pooled.
+# The seeds are fixed, so the tests are deterministic; the acceptance level (p > 1e-3 per
+# statistic) is what an unbiased operator passes with wide margin and a biased one does not.
+# ---------------------------------------------------------------------------------------------
+def _chi2_p(a, b, min_count=10):
+    """p-value of H0 'samples a and b (integer categories) come from one distribution'."""
+    from scipy.stats import chi2
+    a, b = np.asarray(a).ravel(), np.asarray(b).ravel()
+    cats = np.union1d(a, b)
+    ca = np.array([(a == c).sum() for c in cats], dtype=np.float64)
+    cb = np.array([(b == c).sum() for c in cats], dtype=np.float64)
+    rare = (ca + cb) < min_count
+    if rare.any():
+        ca = np.append(ca[~rare], ca[rare].sum())
+        cb = np.append(cb[~rare], cb[rare].sum())
+    keep = (ca + cb) > 0
+    ca, cb = ca[keep], cb[keep]
+    if len(ca) < 2:
+        return 1.0
+    na, nb = ca.sum(), cb.sum()
+    stat = ((np.sqrt(nb / na) * ca - np.sqrt(na / nb) * cb) ** 2 / (ca + cb)).sum()
+    return float(chi2.sf(stat, len(ca) - 1))
+
+
+def _dist_helpers():
+    import importlib.util
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden_variation_dist.py")
+    spec = importlib.util.spec_from_file_location("mk_dist", p)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.fixture(scope="module")
+def dist_gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "variation_dist.npz"))
+
+
+P_MIN = 1e-3
+
+
+def test_walk_distribution_matches_reference(world_small, dist_gold):
+    """makeMeAPath (pathmaker.py:188-213): node reached after 1 / 3 / 10 steps and the number of
+    distinct waypoints of a 150-step walk, per start waypoint."""
+    h = _dist_helpers()
+    w = world_small
+    op = w.org_params
+    eng = _engine(w, op)
+    ref = dist_gold["walks"].astype(np.int64)                         # [n, A, 151]
+    got = eng.random_walks(4000, op['start_idx'], 150, seed=2024).cpu().numpy()[:, :, :151]
+    assert (got[:, :, 150] >= 0).all()
+    starts = np.array(op['start_idx'])
+    for s in np.unique(starts):
+        agents = np.nonzero(starts == s)[0]
+        r = ref[:, agents].reshape(-1, 151)
+        g = got[:, agents].reshape(-1, 151)
+        for step in (1, 3, 10):
+            p = _chi2_p(r[:, step], g[:, step])
+            assert p > P_MIN, ("node after %d steps from %d" % (step, s), p)
+        p = _chi2_p(h.n_distinct(r) // 4, h.n_distinct(g) // 4)
+        assert p > P_MIN, ("distinct nodes from %d" % s, p)
+
+
+def _replicate(rows, n):
+    return np.repeat(np.asarray(rows, dtype=np.int32)[None], n, axis=0).copy()
+
+
+def test_mutation_distribution_matches_reference(world_small, dist_gold):
+    """Organism.mutation (geneticalgorithm.py:251-268) + pruneUTurns on one fixed organism:
+    cut point (through the common prefix with the input) and new length, per agent."""
+    import torch
+    h = _dist_helpers()
+    w = world_small
+    base = dist_gold["base"].astype(np.int32)
+    eng = _engine(w, _op(w, mutation_prob=1.0, muterpolate_prob=0.0))
+    dna = torch.from_numpy(_replicate(base, 6000)).cuda()
+    eng.mutate(dna, seed=31, gen=3)
+    got = dna.cpu().numpy()
+    ref = dist_gold["mutation"].astype(np.int32)
+    for a in range(base.shape[0]):
+        p = _chi2_p(h.common_prefix(ref[:, a], base[a]) // 4, h.common_prefix(got[:, a], base[a]) // 4)
+        assert p > P_MIN, ("mutation prefix, agent %d" % a, p)
+        p = _chi2_p(h.valid_len(ref[:, a]) // 5, h.valid_len(got[:, a]) // 5)
+        assert p > P_MIN, ("mutation length, agent %d" % a, p)
+
+
+def test_muterpolate_distribution_matches_reference(world_small, dist_gold):
+    """Organism.muterpolate (geneticalgorithm.py:270-309) on one fixed organism: how much is cut
+    out and where the first change sits, per agent."""
+    import torch
+    h = _dist_helpers()
+    w = world_small
+    base = dist_gold["base"].astype(np.int32)
+    eng = _engine(w, _op(w, mutation_prob=0.0, muterpolate_prob=1.0))
+    dna = torch.from_numpy(_replicate(base, 6000)).cuda()
+    eng.mutate(dna, seed=32, gen=5)
+    got = dna.cpu().numpy()
+    ref = dist_gold["muterpolate"].astype(np.int32)
+    for a in range(base.shape[0]):
+        p = _chi2_p(h.valid_len(ref[:, a]) // 2, h.valid_len(got[:, a]) // 2)
+        assert p > P_MIN, ("muterpolate length, agent %d" % a, p)
+        p = _chi2_p(h.common_prefix(ref[:, a], base[a]) // 4, h.common_prefix(got[:, a], base[a]) // 4)
+        assert p > P_MIN, ("muterpolate first change, agent %d" % a, p)
+
+
+def test_crossover_distribution_matches_reference(world_small, dist_gold):
+    """Organism.crossover / matchWaypt (geneticalgorithm.py:211-249,311-333) of one fixed pair:
+    the cut pair (i, j) through child 1's common prefix with the mother and its length, per agent;
+    crossover happens with the reference's probability."""
+    import torch
+    h = _dist_helpers()
+    w = world_small
+    base, mate = dist_gold["base"].astype(np.int32), dist_gold["mate"].astype(np.int32)
+    eng = _engine(w, _op(w, mutation_prob=0.0, muterpolate_prob=0.0))
+    K = 8000
+    parents = torch.from_numpy(np.stack([base, mate])).cuda()
+    strong = torch.cat([torch.zeros(K, dtype=torch.int32), torch.ones(K, dtype=torch.int32)]).cuda()
+    kids = eng.crossover(parents, strong, seed=33, gen=7)
+    eng.mutate(kids, seed=33, gen=7)                                  # constructor of the children: prune only
+    kids = kids.cpu().numpy()
+    got0, got1 = kids[0::2], kids[1::2]
+    ref = dist_gold["crossover"].astype(np.int32)                     # [n, 2, A, L]
+    for a in range(base.shape[0]):
+        same_ref = (ref[:, 0, a] == base[a]).all(-1)
+        same_got = (got0[:, a] == base[a]).all(-1)
+        p = _chi2_p(same_ref, same_got, min_count=1)
+        assert p > P_MIN, ("crossover frequency, agent %d" % a, p, same_ref.mean(), same_got.mean())
+        p = _chi2_p(h.common_prefix(ref[:, 0, a], base[a]) // 3, h.common_prefix(got0[:, a], base[a]) // 3)
+        assert p > P_MIN, ("cut index i, agent %d" % a, p)
+        p = _chi2_p(h.valid_len(ref[:, 0, a]) // 3, h.valid_len(got0[:, a]) // 3)
+        assert p > P_MIN, ("child 1 length, agent %d" % a, p)
+        p = _chi2_p(h.common_prefix(ref[:, 1, a], mate[a]) // 3, h.common_prefix(got1[:, a], mate[a]) // 3)
+        assert p > P_MIN, ("cut index j, agent %d" % a, p)
