@@ -542,6 +542,12 @@ def main():
         gp = worlds.GEN_PARAMS_6
         cstarts = synth.clustered_starts(w.xy, w.row_ptr, A, cfg['size'])
         opc = worlds.org_params_for(cfg, cstarts)
+        # the loop-closure minima of the reference's 6-agent column (2 solo per agent, 5 combined;
+        # pather_driver.py:150-158) are tuned to its 391 x 261 building and are met by ~0.1 % of the
+        # organisms on this map - with or without evolution (profiles/probe_r02b.jsonl).  The generation
+        # legs therefore keep the connectivity constraint and one combined closure, which ~96 % of the
+        # clustered walks and ~100 % of their descendants meet: ranking and selection see real objectives
+        opc.update(min_solo_lcs=0, min_comb_lcs=1)
 
         def generation_leg(P_gen, n_gen=5, n_pre=40):
             per = P_gen // world_size
@@ -577,6 +583,9 @@ def main():
                    "generations_timed": n_gen, "gene_bits": 8 * evo.gb,
                    "rank0_stage_ms_one_generation": {k: v for k, v in last.items() if v >= 0},
                    "generations_before_timing": n_pre,
+                   "constraints": {"min_solo_lcs": opc['min_solo_lcs'], "min_comb_lcs": opc['min_comb_lcs'],
+                                   "start_waypoints": [int(x) for x in cstarts]},
+                   "mean_valid_genes_per_row_after": float((evo.parents != -1).double().sum(-1).mean().item()),
                    "feasible_fraction_random_walks": feas_walks,
                    "feasible_fraction_at_timing_start": feas0,
                    "feasible_fraction_after": float((evo.obj[:, 0] != 0).double().mean().item()),

@@ -115,3 +115,68 @@ def test_full_size_ranking_properties(c3):
             m = np.minimum(sc[i, 0] - sc[:, 0], sc[i, 1] - sc[:, 1])
             m[i] = -np.inf
             assert m.max() == float(fit_sweep[i])
+
+
+_ORACLE_WORLD = None
+
+
+def _oracle_eval(dnas):
+    return [fo.calc_obj(_ORACLE_WORLD, d.astype(int), detail=True) for d in dnas]
+
+
+def _oracle_many(ow, dnas):
+    """the oracle over all host cores (forked workers inherit the world)"""
+    import multiprocessing as mp
+    import os
+    global _ORACLE_WORLD
+    _ORACLE_WORLD = ow
+    ow.safety_img
+    ow.edge_id(0, 0)
+    n = max(1, min(os.cpu_count() or 1, 32))
+    chunks = [c for c in np.array_split(np.asarray(dnas), n) if len(c)]
+    with mp.get_context("fork").Pool(len(chunks)) as pool:
+        out = pool.map(_oracle_eval, chunks)
+    return [d for part in out for d in part]
+
+
+def test_random_organisms_of_the_headline_population_against_oracle(c3):
+    """384 organisms drawn at random from the 65,536 of the benchmark population, plus 128 taken
+    from a population after 30 generations on the device (clustered starts and the loop-closure
+    constraints of the bench's generation leg: feasible organisms, shorter and mutated paths):
+    objectives, loop-closure matrices, components and feasibility bit-exact against the oracle
+    (binary map: -coverage exact)."""
+    import torch
+    from genetic_coverage_planning_b200 import synth, worlds
+    from genetic_coverage_planning_b200.distributed import ShardedEvolution
+    w, pw, op, eng, dna = c3
+    rs = np.random.RandomState(12)
+    idx = np.sort(rs.choice(P, 384, replace=False))
+    sample = dna[torch.from_numpy(idx).to(dna.device)].contiguous()
+    op2 = dict(op, min_solo_lcs=0, min_comb_lcs=1)
+    n_feasible = 0
+    try:
+        eng.set_params(op2)
+        eng.set_vary_params(op2, w.path_params)
+        cst = synth.clustered_starts(w.xy, w.row_ptr, A, 4096)
+        sub = synth.random_walk_population_torch(w.xy, w.row_ptr, w.col, cst, 4096, 150, L, seed=9,
+                                                 device=eng.device)
+        evo = ShardedEvolution(eng, worlds.GEN_PARAMS_6, 4096)
+        evo.load(sub, 0)
+        for g in range(30):
+            evo.step(5, g)
+        evolved = evo.gather_parents()[:128].contiguous()
+        for pop, params in ((evolved, op2), (sample, op)):
+            eng.set_params(params)
+            ow = World(w.img, w.xy, w.row_ptr, w.col, w.edge_poly, w.edge_theta, w.edge_dist,
+                       w.map_params, params, name="c3")
+            r = eng.evaluate(pop, detail=True, pixel_counts=False)
+            obj, lc, flags = r.obj.cpu().numpy(), r.lc_mat.cpu().numpy(), r.flags.cpu().numpy()
+            want = _oracle_many(ow, pop.cpu().numpy())
+            for k, det in enumerate(want):
+                assert det['obj'][0] == obj[k, 0] and det['obj'][1] == obj[k, 1], k
+                assert np.array_equal(det['lc_mat'].astype(np.int32), lc[k]), k
+                assert det['feasible'] == flags[k, 0] and det['n_components'] == flags[k, 2], k
+                n_feasible += det['feasible']
+    finally:
+        eng.set_params(op)
+    assert n_feasible >= 64, "the evolved part must exercise the feasible branch (%d)" % n_feasible

@@ -34,13 +34,13 @@ def _check_against_golden(eng, z, exact_cov=False):
     """Both evaluation paths against the reference's vectors: the staged general kernels (all
     pixel counters) and the objectives-only path (the fused kernel when coverage_blend == 1)."""
     dna = z['dna'].astype(np.int32)
-    _check_result(eng.evaluate(dna, detail=True, pixel_counts=False), z, exact_cov, counters=False)
-    _check_result(eng.evaluate(dna), z, exact_cov, counters=True)
+    _check_result(eng.evaluate(dna, detail=True, pixel_counts=False), z, exact_cov, False, eng.org_params)
+    _check_result(eng.evaluate(dna), z, exact_cov, True, eng.org_params)
     obj_only = eng.evaluate(dna, detail=False)
     assert np.max(np.abs(obj_only.obj.cpu().numpy() - z['obj'])) <= (0 if exact_cov else COV_TOL_GRAY)
 
 
-def _check_result(r, z, exact_cov, counters):
+def _check_result(r, z, exact_cov, counters, op):
     dist, turn = r.dist.cpu().numpy(), r.turn.cpu().numpy()
     assert np.array_equal(dist, z['dist']), "per-agent travel distance not bit-exact"
     assert np.array_equal(turn, z['turn']), "per-agent turning cost not bit-exact"
@@ -61,13 +61,32 @@ def _check_result(r, z, exact_cov, counters):
     else:
         assert np.max(np.abs(neg - z['neg_cov'])) <= COV_TOL_GRAY
         assert np.max(np.abs(obj[:, 0] - z['obj'][:, 0])) <= COV_TOL_GRAY
-    # feasibility: the reference zeroes coverage exactly when infeasible
-    infeasible_ref = (z['obj'][:, 0] == 0) & (z['neg_cov'] != 0)
-    assert np.array_equal(flags[:, 0] == 0, infeasible_ref | ((flags[:, 0] == 0) & (z['neg_cov'] == 0)))
+    # feasibility (geneticalgorithm.py:197-200) re-derived for EVERY organism from the reference's own
+    # loop-closure matrix and component count, and - where the reference's output shows it (its
+    # coverage is zeroed exactly when infeasible) - from its objectives
+    lc_ref = z['lc'].astype(np.int64)
+    solo = np.diagonal(lc_ref, axis1=1, axis2=2)
+    combo = lc_ref.sum(axis=(1, 2)) - solo.sum(axis=1)
+    feasible_ref = ~((solo < op['min_solo_lcs']).any(axis=1) | (combo < op['min_comb_lcs']) | (z['ncomp'] > 1))
+    assert np.array_equal(flags[:, 0] == 1, feasible_ref)
+    shown = z['neg_cov'] != 0
+    assert np.array_equal(feasible_ref[shown], z['obj'][shown, 0] != 0)
+    if 'feasible' in z:
+        assert np.array_equal(flags[:, 0], z['feasible'])
 
 
 def test_eval_golden_big(eng_big, golden_dir):
     _check_against_golden(eng_big, np.load(os.path.join(golden_dir, "eval_big.npz")))
+
+
+def test_eval_golden_evolved_feasible(eng_big, world_small, golden_dir):
+    """Populations evolved by the unmodified reference (make_golden_feasible.py): mostly FEASIBLE
+    organisms, i.e. the branch that keeps the coverage objective, on both reference maps."""
+    zb = np.load(os.path.join(golden_dir, "eval_big_evolved.npz"))
+    zs = np.load(os.path.join(golden_dir, "eval_small_evolved.npz"))
+    assert zb['feasible'].mean() > 0.5 and zs['feasible'].mean() > 0.5
+    _check_against_golden(eng_big, zb)
+    _check_against_golden(_engine(world_small), zs)
 
 
 def test_edge_cases_golden(eng_big, golden_dir):

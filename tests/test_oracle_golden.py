@@ -124,3 +124,14 @@ def test_agent_count_synth(world_synth, golden_dir):
     op.update(min_solo_lcs=int(z['min_solo_lcs']), min_comb_lcs=int(z['min_comb_lcs']),
               max_dna_len=int(z['max_dna_len']))
     _check_eval(w, z, op, n=8)
+
+
+def test_eval_evolved_feasible(world_big, world_small, golden_dir):
+    """reference-evolved, mostly feasible populations (tests/golden/make_golden_feasible.py)"""
+    zb, zs = _load(golden_dir, "eval_big_evolved.npz"), _load(golden_dir, "eval_small_evolved.npz")
+    assert zb['feasible'].sum() >= 12 and zs['feasible'].sum() >= 15
+    _check_eval(world_big, zb, n=12)
+    _check_eval(world_small, zs, n=12)
+    for w, z in ((world_big, zb), (world_small, zs)):
+        for k in range(12):
+            assert fo.calc_obj(w, z['dna'][k].astype(int), detail=True)['feasible'] == z['feasible'][k]
