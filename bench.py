@@ -47,6 +47,10 @@ def parse_args():
     ap.add_argument("--scaling", default=os.environ.get("GCP_BENCH_SCALING", "strong"),
                     choices=["strong", "weak"])
     ap.add_argument("--pop", type=int, default=0, help="override the population of the config")
+    ap.add_argument("--starts", default=os.environ.get("GCP_BENCH_STARTS", "spread"), choices=["spread", "diverse"],
+                    help="spread: the config's fixed start waypoints (SURVEY 8d); diverse: every organism "
+                         "starts from its own random waypoints, so a launch touches the WHOLE footprint "
+                         "store (HBM-bound stress when the store outgrows the L2, config C5)")
     ap.add_argument("--cpu-sample", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / per-kernel / ranking / generation legs")
@@ -401,7 +405,10 @@ def main():
         with its own seed, so the global population does not depend on the number of ranks)."""
         parts = []
         for c in range(lo // CHUNK, (hi + CHUNK - 1) // CHUNK):
-            d = synth.random_walk_population_torch(w.xy, w.row_ptr, w.col, start_nodes, CHUNK,
+            st = start_nodes
+            if st is None:                                   # diverse: per-organism random starts
+                st = np.random.RandomState(seed_base + c).randint(0, w.N, size=(CHUNK, A))
+            d = synth.random_walk_population_torch(w.xy, w.row_ptr, w.col, st, CHUNK,
                                                    cfg['walk'], L, seed=seed_base + c, device=dev)
             parts.append(d[max(lo, c * CHUNK) - c * CHUNK:min(hi, (c + 1) * CHUNK) - c * CHUNK])
         return torch.cat(parts).contiguous()
@@ -412,7 +419,8 @@ def main():
     dna_bytes = P * A * L * 4
     n_rot = 1 if dna_bytes > 1.2 * L2_BYTES else int(math.ceil(2.5 * L2_BYTES / dna_bytes))
     lo = rank * P
-    dnas = [population_slice(lo, lo + P, starts, 1000 + 100000 * k) for k in range(n_rot)]
+    dnas = [population_slice(lo, lo + P, starts if args.starts == "spread" else None, 1000 + 100000 * k)
+            for k in range(n_rot)]
     dna = dnas[0]
     torch.cuda.synchronize()
     if rank == 0:
@@ -634,7 +642,12 @@ def main():
                                           "(valid for N <= 32767 waypoints); the narrowing is NOT timed"}
         # ---------------- CPU baselines (rank 0, N=1 only) --------------------------------
         if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
-            sample = dna[:args.cpu_sample].cpu().numpy()
+            # bounded sample: ~20 s of single-thread work (one organism takes 0.13 s at 4096^2 and
+            # seconds at 16384^2, where the reference copies and reduces a 2 GB map per organism)
+            t0 = time.time()
+            cpu_port_rate(w, op, dna[:1].cpu().numpy(), 1)
+            n_cpu = int(min(args.cpu_sample, max(4, 20.0 / max(time.time() - t0, 1e-3))))
+            sample = dna[:n_cpu].cpu().numpy()
             rate, secs = cpu_port_rate(w, op, sample, 1)
             cpu_baseline = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
                             "sample": "first %d organisms of the same population, "
@@ -673,7 +686,8 @@ def main():
             "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u64 bitsets + f64 costs", "data": "synthetic",
-            "config": {"workload": workload_string(args.config, cfg, w.N, w.E, args.scaling, world_size),
+            "config": {"workload": workload_string(args.config, cfg, w.N, w.E, args.scaling, world_size) +
+                       ("" if args.starts == "spread" else "; DIVERSE starts (every organism from its own random waypoints)"),
                        "organisms_per_gpu": P, "global_population": P_global,
                        "mean_executed_steps_per_organism": S_mean,
                        "l2": ("per-step input (dna, %.0f MB) exceeds the 126 MB L2; no flush" % (dna_bytes / 1e6))

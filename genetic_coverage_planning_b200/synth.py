@@ -319,10 +319,13 @@ def random_walk_population_torch(xy, row_ptr, col, starts, n_org, walk_len, max_
                                  chunk=1 << 20):
     """Same walk rule as random_walk_population, on torch tensors (benchmark SETUP only:
     it seeds synthetic populations on the GPU box in seconds instead of minutes).
+    starts: A start waypoints shared by all organisms, or an [n_org, A] array of per-organism
+    starts ("diverse" populations that touch the whole footprint store).
     Returns an int32 torch tensor [n_org, A, max_dna_len] on `device`."""
     import torch
     N = len(xy)
-    A = len(starts)
+    starts = np.asarray(starts, dtype=np.int64)
+    A = starts.shape[-1]
     deg = np.diff(row_ptr)
     D = int(deg.max())
     nbr = -np.ones((N, D), dtype=np.int64)
@@ -339,7 +342,11 @@ def random_walk_population_torch(xy, row_ptr, col, starts, n_org, walk_len, max_
     n_steps = min(walk_len, max_dna_len - 1)
     total = n_org * A
     dna = torch.full((total, max_dna_len), -1, dtype=torch.int32, device=dev)
-    start_all = torch.tensor(list(starts), dtype=torch.int64, device=dev).repeat(n_org)
+    if starts.ndim == 2:
+        assert starts.shape[0] == n_org
+        start_all = torch.from_numpy(starts.reshape(-1)).to(dev)
+    else:
+        start_all = torch.from_numpy(starts).to(dev).repeat(n_org)
     two_pi = 2 * np.pi
     for s in range(0, total, chunk):
         e = min(total, s + chunk)

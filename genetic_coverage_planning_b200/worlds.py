@@ -19,14 +19,15 @@ GEN_PARAMS_6 = {'gamma': 0.5, 'coverage_constr_0': 0.3, 'coverage_constr_f': 0.9
                 'coverage_aging': 80}
 
 CONFIGS = {
-    # name: (map size, agents, max_dna_len, walk steps, population)
+    # name: map size, agents, max_dna_len, walk steps, population (the WHOLE population: bench.py
+    # shards it over the ranks under --scaling strong)
     "C3": dict(size=4096, agents=6, L=200, walk=150, pop=65536),
     "C3-small": dict(size=1024, agents=6, L=200, walk=150, pop=2048),
     "C4-2": dict(size=4096, agents=2, L=640, walk=512, pop=16384),
     "C4-6": dict(size=4096, agents=6, L=640, walk=512, pop=16384),
     "C4-16": dict(size=4096, agents=16, L=640, walk=512, pop=16384),
     "C4-32": dict(size=4096, agents=32, L=640, walk=512, pop=16384),
-    "C5": dict(size=16384, agents=6, L=200, walk=150, pop=32768),
+    "C5": dict(size=16384, agents=6, L=200, walk=150, pop=262144),
 }
 
 

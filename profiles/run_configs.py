@@ -92,7 +92,7 @@ def run_synth(name, n_check):
     t0 = time.time()
     w, pw = worlds.build_synth_world(cfg['size'], seed=0, verbose=True)
     t_build = time.time() - t0
-    A, L, P = cfg['agents'], cfg['L'], cfg['pop']
+    A, L, P = cfg['agents'], cfg['L'], min(cfg['pop'], 32768 if name == 'C5' else cfg['pop'])
     starts = synth.spread_starts(w.xy, A, cfg['size'])
     op = worlds.org_params_for(cfg, starts)
     eng = FitnessEngine(pw, op, num_agents=A)
