@@ -695,8 +695,11 @@ def main():
                        ("per-step input is %.0f MB < L2: the timed steps rotate over %d distinct populations "
                         "(%.0f MB in total) so that every step reads its chromosomes from HBM; no flush"
                         % (dna_bytes / 1e6, n_rot, n_rot * dna_bytes / 1e6)),
-                       "l2_tables": "the %.0f MB pre-masked footprint store is reused inside a launch and "
-                                    "stays L2-resident by design" % (pw.m_n_quarters * 128 / 1e6),
+                       "l2_tables": ("the %.0f MB pre-masked footprint store is reused inside a launch and stays "
+                                     "L2-resident by design" if pw.m_n_quarters * 128 < 0.8 * L2_BYTES else
+                                     "the %.0f MB pre-masked footprint store does not fit the 126 MB L2: footprint "
+                                     "gathers that leave the neighbourhood of the start waypoints come from HBM")
+                       % (pw.m_n_quarters * 128 / 1e6),
                        "parallelism": "population sharded over the ranks, tables replicated, no collective "
                                       "in the evaluation step",
                        "host_numa_node_rank0": numa_node},

@@ -224,6 +224,7 @@ int gcp_upload_masked_footprints(gcp_ctx* c, const uint32_t* sub_ptr, const uint
             if ((r = upload(c, &c->t.m_q_desc, qdesc.data(), qdesc.size()))) return r;
         }
     }
+    c->m_n_quarters = n_quarters;
     c->have_masked = true;
     return 0;
 }
@@ -683,6 +684,7 @@ int gcp_set_option(gcp_ctx* c, const char* name, int64_t value)
     else if (!strcmp(name, "cov_threads")) c->cov_threads = (int)value;
     else if (!strcmp(name, "cov_dedup")) c->cov_dedup = (int)value;
     else if (!strcmp(name, "cov_buckets")) c->cov_buckets = (int)value;
+    else if (!strcmp(name, "cov_prefetch")) c->cov_prefetch = (int)value;
     else return gcp_fail(c, -1, "gcp_set_option: unknown option '%s'", name);
     return 0;
 }

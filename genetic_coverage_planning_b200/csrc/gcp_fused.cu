@@ -25,6 +25,7 @@ struct FusedShape {
     uint32_t inv_L;      // ceil(2^32 / L): s / L == __umulhi(s, inv_L) for s < 2^16
     int T, MAXP, T3;
     int gene16;          // chromosome stored as int16 in global memory
+    int prefetch;        // footprint store outgrows the L2: B1 prefetches every quarter line into the L2
     uint32_t R0;
     uint32_t DS;         // slots of the step-dedup hash set (power of two, 0 = skip)
     uint32_t off_info, off_x, off_cst, off_lc, off_cost;   // byte offsets into dynamic smem (off_cst relative to off_x)
@@ -49,7 +50,7 @@ template <int KF_THREADS, bool HAS_GRAY, bool BUCKETS = false>
 __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const GcpTables& t,
                                                   int T, int MAXP, uint32_t R0, uint32_t DS, unsigned char* s_x,
                                                   uint32_t& n_cov, uint32_t& n_wg, bool& failed,
-                                                  uint2* rec = nullptr, uint32_t rec_cap = 0)
+                                                  uint2* rec = nullptr, uint32_t rec_cap = 0, bool prefetch = false)
 {
     constexpr int KF_NW = KF_THREADS / 32;
     __shared__ uint32_t s_npairs, s_overflow, s_group;
@@ -239,6 +240,9 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
                             const uint32_t ex = __shfl_sync(FULL, excl, a), dlo = __shfl_sync(FULL, lo, a);
                             if (j < total) {
                                 const uint2 dsc = __ldg(t.m_q_desc + dlo + (j - ex));
+                                // store larger than the L2 (config C5, diverse populations): start the
+                                // DRAM fetch of this quarter's line now, B2 finds it in the L2
+                                if (prefetch) asm volatile("prefetch.global.L2 [%0];" :: "l"(tile_at(t.m_tile, dsc.y)));
                                 const uint32_t blk = dsc.x >> 2, q = dsc.x & 3u;
                                 const uint32_t key = blk + 1;
                                 uint32_t h = hash_block(blk) >> (32 - logT);
@@ -677,7 +681,8 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     uint32_t n_cov, n_wg;
     bool failed;
     coverage_quarters<KF_THREADS, HAS_GRAY>(s_info, AL, t, ST ? SS::T : sh.T, ST ? SS::MAXP : sh.MAXP,
-                                            ST ? 1u : sh.R0, 0u, s_x, n_cov, n_wg, failed);
+                                            ST ? 1u : sh.R0, 0u, s_x, n_cov, n_wg, failed, nullptr, 0,
+                                            sh.prefetch != 0);
     {
         uint32_t v = n_cov, vw = n_wg;
         #pragma unroll
@@ -964,6 +969,9 @@ int launch_eval_fused(gcp_ctx* ctx, const void* dna, int gene16, uint32_t P, con
     sh.gene16 = gene16;
     if (threads == 0)
         return gcp_fail(ctx, -3, "fused eval kernel needs %zu B shared memory (A*L too large)", smem);
+    // a footprint store that outgrows the L2 is prefetched line by line while the items are sorted
+    sh.prefetch = ctx->cov_prefetch >= 0 ? ctx->cov_prefetch
+                                         : ((size_t)ctx->m_n_quarters * 128 > ((size_t)96 << 20) ? 1 : 0);
     StageTimer tm(ctx, 1, st);
 #define GCP_LAUNCH_FUSED(TH, GRAY, SAL)                                                                \
     do {                                                                                               \

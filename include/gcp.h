@@ -279,7 +279,9 @@ int gcp_peer_barrier(gcp_ctx* ctx, const gcp_shards* flags, uint32_t rank, uint3
  * "cov_table", "cov_maxpairs", "cov_threads": shared-memory sizing / CTA size of the coverage kernels
  * (0 = auto); "cov_dedup": 0 = keep revisited edges in the coverage union (same result, more work);
  * "cov_buckets": 0 = long genomes re-scan their items per hash partition instead of bucketing them
- * once; "lc_min_parts": at least this many hash partitions in the long-genome loop-closure kernel.
+ * once; "lc_min_parts": at least this many hash partitions in the long-genome loop-closure kernel;
+ * "cov_prefetch": -1 auto / 0 / 1, L2 prefetch of the footprint lines while the fused kernel sorts its
+ * items (helps when the footprint store is larger than the L2).
  * Unknown names return an error. */
 int gcp_set_option(gcp_ctx* ctx, const char* name, int64_t value);
 
