@@ -496,7 +496,7 @@ def main():
         staged = {"path_costs": ms_k1, "coverage_masked": ms_k2m,
                   "coverage_general_all_counters": ms_k2g, "loop_closures": ms_k3,
                   "general_path_whole_evaluation": ms_general}
-        tr = known_traffic(args.config)
+        tr = known_traffic(args.config + ("" if args.starts == "spread" else "-" + args.starts))
         tr = tr if isinstance(tr, dict) else {"dram_bytes": tr}
         # per launch of the profiled shape (65,536 organisms): scale to this launch's organisms
         scale = P / float(tr.get("organisms", 65536) or 65536)

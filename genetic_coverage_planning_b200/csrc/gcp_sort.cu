@@ -44,11 +44,16 @@ __global__ void k_rs_make_keys(const double* __restrict__ src, uint32_t stride, 
 
 // Warp w of a CTA owns keys [tile0 + w*256, +256) in 8 rounds of 32 consecutive keys, so
 // (CTA, warp, round, lane) order == input order: ranks assigned in that order are stable.
+// With `done` (a zeroed u32 ticket counter) the LAST CTA to finish also turns the histogram into
+// the exclusive offsets k_rs_scatter reads (what k_rs_scan_bins + k_rs_scan_totals do as two more
+// launches): for small populations a pass is then two launches instead of four, and the ranking of a
+// small population is launch-latency bound.
 __global__ void __launch_bounds__(RS_THREADS)
 k_rs_hist(const unsigned long long* __restrict__ keys, uint32_t n, int shift,
-          uint32_t* __restrict__ hist /*[256][nblk]*/, uint32_t nblk)
+          uint32_t* __restrict__ hist /*[256][nblk]*/, uint32_t nblk, uint32_t* __restrict__ done)
 {
     __shared__ uint32_t s_h[RS_BINS];
+    __shared__ uint32_t s_last;
     const int tid = threadIdx.x;
     s_h[tid] = 0;
     __syncthreads();
@@ -60,6 +65,34 @@ k_rs_hist(const unsigned long long* __restrict__ keys, uint32_t n, int shift,
     }
     __syncthreads();
     hist[(size_t)tid * nblk + blockIdx.x] = s_h[tid];
+    if (!done) return;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(done, 1u) == nblk - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // thread = bin: exclusive scan of its row over the tiles, then of the row totals over the bins
+    uint32_t* row = hist + (size_t)tid * nblk;
+    uint32_t run = 0;
+    for (uint32_t b0 = 0; b0 < nblk; b0 += 16) {           // 16 independent loads in flight per thread
+        uint32_t v[16];
+        #pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = (b0 + k < nblk) ? __ldcg(row + b0 + k) : 0u;
+        #pragma unroll
+        for (int k = 0; k < 16; ++k) { if (b0 + k < nblk) row[b0 + k] = run; run += v[k]; }
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+    uint32_t inc = run;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += x; }
+    __shared__ uint32_t s_w[RS_BINS / 32];
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    uint32_t off = 0;
+    for (int w = 0; w < warp; ++w) off += s_w[w];
+    hist[(size_t)RS_BINS * nblk + tid] = off + inc - run;
+    if (tid == 0) *done = 0u;                               // ready for the next pass
 }
 
 // Exclusive scan of hist in (bin, block) order in two steps: one CTA per bin scans its row
@@ -195,7 +228,10 @@ k_rs_scatter(const unsigned long long* __restrict__ keys, const uint32_t* __rest
 static inline uint32_t rs_blocks(uint32_t n) { return (n + RS_TILE - 1) / RS_TILE; }
 
 // hist scratch: (256 * nblk + 256) u32
-size_t radix_hist_bytes(uint32_t n) { return ((size_t)rs_blocks(n) * RS_BINS + RS_BINS) * 4; }
+size_t radix_hist_bytes(uint32_t n) { return ((size_t)rs_blocks(n) * RS_BINS + RS_BINS) * 4 + 256; }
+// the single last CTA scans 256 rows of nblk counts: a win up to 16 tiles (32,768 keys: 0.39 -> 0.30 ms
+// for maximin + order at 16,384 gladiators), a loss from 64 tiles on, where the two scan kernels stay
+constexpr uint32_t RS_FUSED_SCAN_MAX_TILES = 16;
 
 // Stable LSD radix sort of (keys, vals) on the low n_bits of the keys, ping-pong through the
 // tmp buffers; *out_keys / *out_vals say where the sorted data ends up.
@@ -208,13 +244,21 @@ int radix_sort_pairs_bits(gcp_ctx* ctx, unsigned long long* keys, uint32_t* vals
     unsigned long long* kin = keys; unsigned long long* kout = keys_tmp;
     uint32_t* vin = vals; uint32_t* vout = vals_tmp;
     const int passes = (n_bits + 7) / 8;
+    const bool fused_scan = nblk <= RS_FUSED_SCAN_MAX_TILES;
+    uint32_t* done = hist + (size_t)RS_BINS * nblk + RS_BINS;          // ticket counter behind the table
+    if (fused_scan) GCP_CUDA(ctx, cudaMemsetAsync(done, 0, 4, st));
     for (int pass = 0; pass < passes; ++pass) {
         const int shift = pass * 8;
-        k_rs_hist<<<nblk, RS_THREADS, 0, st>>>(kin, n, shift, hist, nblk);
-        k_rs_scan_bins<<<RS_BINS, 1024, 0, st>>>(hist, nblk);
-        k_rs_scan_totals<<<1, RS_BINS, 0, st>>>(hist + (size_t)RS_BINS * nblk);
+        if (fused_scan) {
+            k_rs_hist<<<nblk, RS_THREADS, 0, st>>>(kin, n, shift, hist, nblk, done);
+            ctx->launches += 2;
+        } else {
+            k_rs_hist<<<nblk, RS_THREADS, 0, st>>>(kin, n, shift, hist, nblk, nullptr);
+            k_rs_scan_bins<<<RS_BINS, 1024, 0, st>>>(hist, nblk);
+            k_rs_scan_totals<<<1, RS_BINS, 0, st>>>(hist + (size_t)RS_BINS * nblk);
+            ctx->launches += 4;
+        }
         k_rs_scatter<<<nblk, RS_THREADS, 0, st>>>(kin, vin, n, shift, hist, nblk, kout, vout);
-        ctx->launches += 4;
         unsigned long long* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;
     }

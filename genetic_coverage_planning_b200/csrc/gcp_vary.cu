@@ -158,17 +158,18 @@ __device__ int w_walk(const GcpTables& t, const VaryParams& vp, int32_t* r, int 
 // per warp hide the dependent adjacency loads, and nothing is replicated across lanes.
 constexpr int PATH_MEM_MAX = 16;
 
-template <typename G>
+// MEMT: compile-time capacity of the no-return memory (10 = the driver's path_memory, else 16)
+template <typename G, int MEMT = PATH_MEM_MAX>
 __device__ int t_walk(const GcpTables& t, const VaryParams& vp, G* r, int pos, int n_steps,
                       int mem_floor, Philox& rng)
 {
     const float PI = 3.14159265358979f;
     const float heading = rng.uniform() * 2.0f * PI - PI;            // :190, never updated
     const float k2 = -0.5f * vp.inv_sigma * vp.inv_sigma;
-    const int mem = min(vp.path_memory, PATH_MEM_MAX);
-    int hist[PATH_MEM_MAX];
+    const int mem = min(vp.path_memory, MEMT);
+    int hist[MEMT];
     #pragma unroll
-    for (int k = 0; k < PATH_MEM_MAX; ++k) {
+    for (int k = 0; k < MEMT; ++k) {
         const int idx = pos - k;
         hist[k] = (k < mem && idx >= mem_floor) ? (int)r[idx] : -2;
     }
@@ -204,7 +205,7 @@ __device__ int t_walk(const GcpTables& t, const VaryParams& vp, G* r, int pos, i
                     w[e] = valid ? __expf(k2 * ang * ang) : 0.f;
                     bool seen = !valid;
                     #pragma unroll
-                    for (int k = 0; k < PATH_MEM_MAX; ++k) seen |= (hist[k] == (int)c[e]);
+                    for (int k = 0; k < MEMT; ++k) seen |= (hist[k] == (int)c[e]);
                     seen_mask |= (seen ? 1u : 0u) << e;
                     tot_all += w[e];
                     if (!seen) tot_fresh += w[e];
@@ -233,7 +234,7 @@ __device__ int t_walk(const GcpTables& t, const VaryParams& vp, G* r, int pos, i
                     const int cc = (int)__ldg(t.col + lo + e);
                     bool seen = false;
                     #pragma unroll
-                    for (int k = 0; k < PATH_MEM_MAX; ++k) seen |= (hist[k] == cc);
+                    for (int k = 0; k < MEMT; ++k) seen |= (hist[k] == cc);
                     tot_all += ww;
                     if (!seen) tot_fresh += ww;
                 }
@@ -247,7 +248,7 @@ __device__ int t_walk(const GcpTables& t, const VaryParams& vp, G* r, int pos, i
                     bool seen = false;
                     if (use_fresh) {
                         #pragma unroll
-                        for (int k = 0; k < PATH_MEM_MAX; ++k) seen |= (hist[k] == cc);
+                        for (int k = 0; k < MEMT; ++k) seen |= (hist[k] == cc);
                     }
                     if (seen) continue;
                     float ang = (float)__ldg(t.edge_theta + lo + e) - heading;
@@ -260,7 +261,7 @@ __device__ int t_walk(const GcpTables& t, const VaryParams& vp, G* r, int pos, i
             }
         }
         #pragma unroll
-        for (int k = PATH_MEM_MAX - 1; k > 0; --k) hist[k] = (k < mem) ? hist[k - 1] : -2;
+        for (int k = MEMT - 1; k > 0; --k) hist[k] = (k < mem) ? hist[k - 1] : -2;
         hist[0] = (mem > 0) ? nxt : -2;
         r[++pos] = (G)nxt;
         cur = nxt;
@@ -625,14 +626,20 @@ __device__ __forceinline__ bool mutation_cut(const G* r, const VaryParams& vp, P
     return true;
 }
 
-constexpr int MW_CLASSES = 4;       // walking rows are bucketed by tail length: a warp's 32 walks end together
+// The rows that walk are counting-sorted by tail length (longest first), so that the 32 walks of a
+// warp end together: with rows in arbitrary order half of a warp's lanes sit idle behind its
+// longest walk.  k_mutation_list emits {row, class} pairs and a histogram of the classes,
+// k_mutation_bases scans it, k_mutation_place scatters the rows into the sorted list.
+constexpr int MW_BINS = 256;
+__device__ __forceinline__ int mw_class(int tail, int L) { return min(MW_BINS - 1, (tail * MW_BINS) / (L + 1)); }
 
-// which = 0: rows of the organisms whose mutation coin came up (:159-161), bucketed by walk length
-// into MW_CLASSES lists (list + c * n_rows, counter[c]); 1: muterpolate coin (:163-165), one list.
+// counter layout (u32): [0] number of listed rows, [1 .. 1+MW_BINS) histogram -> cursors,
+// [1+MW_BINS .. 1+2*MW_BINS) class bases.  which = 0: mutation coin (:159-161), pairs = {row, class};
+// which = 1: muterpolate coin (:163-165), list = rows, counter[0] = their number.
 template <typename G>
 __global__ void k_mutation_list(const G* __restrict__ dna, uint32_t P, VaryParams vp, uint64_t seed,
                                 uint32_t gen, uint32_t salt, int which, uint32_t* __restrict__ counter,
-                                uint32_t* __restrict__ list)
+                                uint32_t* __restrict__ list, uint2* __restrict__ pairs)
 {
     const uint32_t org = blockIdx.x * blockDim.x + threadIdx.x;
     if (org >= P) return;
@@ -646,37 +653,59 @@ __global__ void k_mutation_list(const G* __restrict__ dna, uint32_t P, VaryParam
         return;
     }
     if (!(u0 < vp.mut_prob)) return;
-    const uint32_t n_rows = P * (uint32_t)vp.A;
     for (int a = 0; a < vp.A; ++a) {
         const uint32_t gid = org * vp.A + a;
         Philox rng(seed, gen, stream_id(STREAM_MUT, salt), gid + vp.org_off * vp.A);
         int len, idx, tail;
         if (!mutation_cut<G>(dna + (size_t)gid * vp.L, vp, rng, &len, &idx, &tail)) continue;
-        const int c = min(MW_CLASSES - 1, (tail * MW_CLASSES) / vp.L);
-        list[(size_t)c * n_rows + atomicAdd(&counter[c], 1u)] = gid;
+        const int c = mw_class(tail, vp.L);
+        pairs[atomicAdd(counter, 1u)] = make_uint2(gid, (uint32_t)c);
+        atomicAdd(&counter[1 + c], 1u);
     }
 }
 
-template <typename G>
+// one CTA of MW_BINS threads: bases of the classes in DESCENDING tail length; cursors restart at 0
+__global__ void __launch_bounds__(MW_BINS)
+k_mutation_bases(uint32_t* __restrict__ counter)
+{
+    __shared__ uint32_t s_w[MW_BINS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = MW_BINS - 1 - tid;                                   // thread 0 = longest class
+    const uint32_t v = counter[1 + c];
+    uint32_t inc = v;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += x; }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    uint32_t off = 0;
+    for (int w = 0; w < warp; ++w) off += s_w[w];
+    counter[1 + MW_BINS + c] = off + inc - v;
+    counter[1 + c] = 0;
+}
+
+__global__ void k_mutation_place(uint32_t* __restrict__ counter, const uint2* __restrict__ pairs,
+                                 uint32_t* __restrict__ list)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= counter[0]) return;
+    const uint2 pr = pairs[j];
+    list[counter[1 + MW_BINS + pr.y] + atomicAdd(&counter[1 + pr.y], 1u)] = pr.x;
+}
+
+template <typename G, int MEMT>
 __global__ void __launch_bounds__(MW_THREADS)
-k_mutation_walks(G* __restrict__ dna, uint32_t n_rows, GcpTables t, VaryParams vp, uint64_t seed,
+k_mutation_walks(G* __restrict__ dna, GcpTables t, VaryParams vp, uint64_t seed,
                  uint32_t gen, uint32_t salt, const uint32_t* __restrict__ counter,
                  const uint32_t* __restrict__ list)
 {
-    uint32_t j = blockIdx.x * MW_THREADS + threadIdx.x;
-    int c = 0;
-    for (; c < MW_CLASSES; ++c) {                                     // longest walks first would also do
-        const uint32_t nc = counter[c];
-        if (j < nc) break;
-        j -= nc;
-    }
-    if (c == MW_CLASSES) return;
-    const uint32_t gid = list[(size_t)c * n_rows + j];
+    const uint32_t j = blockIdx.x * MW_THREADS + threadIdx.x;
+    if (j >= counter[0]) return;
+    const uint32_t gid = list[j];
     G* r = dna + (size_t)gid * vp.L;
     Philox rng(seed, gen, stream_id(STREAM_MUT, salt), gid + vp.org_off * vp.A);
     int len, idx, len_tail;
     if (!mutation_cut<G>(r, vp, rng, &len, &idx, &len_tail)) return;
-    const int last = t_walk<G>(t, vp, r, idx, len_tail, 0, rng);
+    const int last = t_walk<G, MEMT>(t, vp, r, idx, len_tail, 0, rng);
     for (int x = last + 1; x < len; ++x) r[x] = (G)-1;                 // addTelomere
 }
 
@@ -827,7 +856,7 @@ k_random_walks(int32_t* __restrict__ dna, uint32_t P, GcpTables t, VaryParams vp
     int32_t* r = dna + (size_t)gid * vp.L;
     Philox rng(seed, batch, STREAM_INIT, gid);
     r[0] = start_idx[gid % vp.A];
-    const int last = t_walk<int32_t>(t, vp, r, 0, path_len, 0, rng);
+    const int last = t_walk<int32_t, PATH_MEM_MAX>(t, vp, r, 0, path_len, 0, rng);
     for (int x = last + 1; x < vp.L; ++x) r[x] = -1;
 }
 
@@ -962,7 +991,7 @@ static int mutate_impl(gcp_ctx* c, G* dna, uint32_t P, uint32_t org_offset, uint
     vp.org_off += org_offset;
     const uint32_t n_rows = P * (uint32_t)vp.A;
     if (vp.mut_prob > 0.f || vp.muterp_prob > 0.f) {
-        const size_t need = 512 + (size_t)n_rows * 4 * MW_CLASSES;
+        const size_t need = 4096 + (size_t)n_rows * 12;           // counters | sorted list | {row, class} pairs
         if (c->vary_scratch_bytes < need) {
             if (c->vary_scratch) cudaFree(c->vary_scratch);
             c->vary_scratch = nullptr; c->vary_scratch_bytes = 0;
@@ -970,19 +999,25 @@ static int mutate_impl(gcp_ctx* c, G* dna, uint32_t P, uint32_t org_offset, uint
             c->vary_scratch_bytes = need;
         }
     }
-    uint32_t* counter = reinterpret_cast<uint32_t*>(c->vary_scratch);
-    uint32_t* list = counter + 128;
+    uint32_t* counter = reinterpret_cast<uint32_t*>(c->vary_scratch);      // [1 + 2 * MW_BINS] + muterpolate counter at [768]
+    uint2* pairs = reinterpret_cast<uint2*>(counter + 1024);
+    uint32_t* list = reinterpret_cast<uint32_t*>(pairs + n_rows);
     const uint32_t row_grid = (n_rows + MW_THREADS - 1) / MW_THREADS;
     if (vp.mut_prob > 0.f) {                       // mutation (:159-161): tail regrowth walks
-        GCP_CUDA(c, cudaMemsetAsync(counter, 0, 4 * MW_CLASSES, st));
-        k_mutation_list<G><<<(P + 255) / 256, 256, 0, st>>>(dna, P, vp, seed, gen, salt, 0, counter, list);
-        k_mutation_walks<G><<<row_grid, MW_THREADS, 0, st>>>(dna, n_rows, c->t, vp, seed, gen, salt, counter, list);
-        c->launches += 2;
+        GCP_CUDA(c, cudaMemsetAsync(counter, 0, 4 * (1 + MW_BINS), st));
+        k_mutation_list<G><<<(P + 255) / 256, 256, 0, st>>>(dna, P, vp, seed, gen, salt, 0, counter, list, pairs);
+        k_mutation_bases<<<1, MW_BINS, 0, st>>>(counter);
+        k_mutation_place<<<(n_rows + 255) / 256, 256, 0, st>>>(counter, pairs, list);
+        if (vp.path_memory <= 10)
+            k_mutation_walks<G, 10><<<row_grid, MW_THREADS, 0, st>>>(dna, c->t, vp, seed, gen, salt, counter, list);
+        else
+            k_mutation_walks<G, PATH_MEM_MAX><<<row_grid, MW_THREADS, 0, st>>>(dna, c->t, vp, seed, gen, salt, counter, list);
+        c->launches += 4;
     }
     if (vp.muterp_prob > 0.f && vp.num_muterp > 0) {   // muterpolate (:163-165)
-        GCP_CUDA(c, cudaMemsetAsync(counter + 64, 0, 4, st));
-        k_mutation_list<G><<<(P + 255) / 256, 256, 0, st>>>(dna, P, vp, seed, gen, salt, 1, counter + 64, list);
-        k_muterpolate_rows<G><<<row_grid, MW_THREADS, 0, st>>>(dna, c->t, vp, seed, gen, salt, counter + 64, list);
+        GCP_CUDA(c, cudaMemsetAsync(counter + 768, 0, 4, st));
+        k_mutation_list<G><<<(P + 255) / 256, 256, 0, st>>>(dna, P, vp, seed, gen, salt, 1, counter + 768, list, pairs);
+        k_muterpolate_rows<G><<<row_grid, MW_THREADS, 0, st>>>(dna, c->t, vp, seed, gen, salt, counter + 768, list);
         c->launches += 2;
     }
     k_post_mutate<G><<<(n_rows + VARY_WARPS - 1) / VARY_WARPS, VARY_WARPS * 32, smem, st>>>(dna, P, c->t, vp,
