@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgcp.so")
+# GCP_LIB=debug loads the bounds-checked build (build.py: libgcp_debug.so) - tests only
+LIB_PATH = os.path.join(HERE, "libgcp_debug.so" if os.environ.get("GCP_LIB") == "debug" else "libgcp.so")
 
 GCP_ABI_VERSION = 2
 GCP_MAX_SHARDS = 16

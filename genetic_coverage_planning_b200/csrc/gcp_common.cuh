@@ -8,6 +8,16 @@
 
 #define GCP_NUM_STAGES 8
 
+// Debug build (libgcp_debug.so, -DGCP_BOUNDS_CHECK): every index the kernels form into shared
+// memory or scratch is checked before use; a violation traps the kernel with file:line (device
+// assert -> cudaErrorAssert on the host).  Compiled out of the release library.
+#ifdef GCP_BOUNDS_CHECK
+#include <cassert>
+#define GCP_DASSERT(cond) assert(cond)
+#else
+#define GCP_DASSERT(cond) ((void)0)
+#endif
+
 // Device-side view of the static lookup tables (uploaded once, read-only afterwards).
 struct GcpTables {
     // graph (pathmaker.py:157-173)

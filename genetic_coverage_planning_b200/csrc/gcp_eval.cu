@@ -263,6 +263,7 @@ k_coverage(const uint32_t* __restrict__ edge_ids, uint32_t P, GcpTables t, int A
                     }
                     if (probes >= T) break;
                     const uint32_t rank = atomicAdd(&s_cnt[h], 1u);
+                    GCP_DASSERT(h < (uint32_t)T && rank < 0x10000u);
                     s_pay[idx] = dsc.y;
                     s_sr[idx] = (h << 16) | rank;
                     ++idx;
@@ -544,6 +545,7 @@ k_coverage_masked(const uint32_t* __restrict__ step_info, uint32_t P,
                     }
                     if (probes >= T) break;
                     const uint32_t rank = atomicAdd(&s_cnt[h], 1u);
+                    GCP_DASSERT(h < (uint32_t)T && rank < 0x10000u);
                     s_pay[idx] = dsc.y;
                     s_sr[idx] = (h << 16) | rank;
                     ++idx;

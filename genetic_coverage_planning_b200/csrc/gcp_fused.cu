@@ -149,6 +149,7 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
                     uint32_t base = 0;
                     if (valid && lane == leader) base = atomicAdd(&s_pcnt[p], (uint32_t)__popc(peers));
                     base = __shfl_sync(FULL, base, leader);
+                    GCP_DASSERT(!valid || s_pbase[p] + base + (uint32_t)__popc(peers & ((1u << lane) - 1u)) < rec_cap);
                     if (valid) rec[s_pbase[p] + base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = dsc;
                 });
                 bucketed = true;
@@ -191,6 +192,7 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
                             if (++probes >= T) { s_overflow = 1; break; }
                         }
                         const uint32_t rank = (probes < T) ? atomicAdd(&s_cq[4 * h + q], 1u) : 0u;
+                        GCP_DASSERT(j < (uint32_t)MAXP && h < (uint32_t)T);
                         s_pay[j] = dsc.y;
                         s_sr[j] = (h << 18) | (q << 16) | rank;
                       }
@@ -258,7 +260,9 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
                                     if (++probes >= T) { s_overflow = 1; break; }
                                 }
                                 if (probes < T) {
+                                    GCP_DASSERT(h < (uint32_t)T && base + j < (uint32_t)MAXP);
                                     const uint32_t rank = atomicAdd(&s_cq[4 * h + q], 1u);
+                                    GCP_DASSERT(rank < 0x10000u);
                                     s_pay[base + j] = dsc.y;
                                     s_sr[base + j] = (h << 18) | (q << 16) | rank;
                                 }
@@ -320,6 +324,7 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
                             }
                             // a failed probe still fills its entry: the pass is discarded anyway
                             const uint32_t rank = (probes < T) ? atomicAdd(&s_cq[4 * h + q], 1u) : 0u;
+                            GCP_DASSERT(idx < (uint32_t)MAXP && h < (uint32_t)T);
                             s_pay[idx] = dsc.y;
                             s_sr[idx] = (h << 18) | (q << 16) | rank;
                         }
@@ -363,6 +368,7 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
                     const uint32_t sr = s_sr[i];
                     const uint32_t cb = s_cq[sr >> 16], rank = sr & 0xFFFFu;
                     pos[k] = (cb & 0xFFFFu) + rank;
+                    GCP_DASSERT((sr >> 16) < 4u * (uint32_t)T && pos[k] < npairs);
                     ent[k] = s_pay[i] | ((rank + 1u == (cb >> 16)) ? 0x80000000u : 0u);   // last of its list
                 }
             }
@@ -402,6 +408,7 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
                     }
                     bnd[e] = min(c, npairs);
                 }
+                GCP_DASSERT(bnd[0] <= bnd[1] && bnd[1] <= npairs);
                 const uint32_t len = bnd[1] - bnd[0];
                 const uint32_t steps = __reduce_max_sync(FULL, len);
                 const uint32_t* pb = s_pay + bnd[0];
@@ -413,6 +420,7 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
                     for (int j = 0; j < 4; ++j) {
                         e[j] = (k + j < len) ? pb[k + j] : 0u;
                         v[j] = make_uint4(0, 0, 0, 0);
+                        GCP_DASSERT(!(k + j < len) || (e[j] & 0x7FFFFFFFu) + l7 < 0x7FFFFFFFu);
                         if (k + j < len) v[j] = __ldg(tile_at(tile_l, e[j] & 0x7FFFFFFFu));
                     }
                     #pragma unroll
@@ -640,6 +648,7 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
                     }
                 }
             }
+            GCP_DASSERT(a < A && s + a < AL + GCP_MAX_AGENTS && (e == GCP_INVALID_EDGE || e < t.E + t.N));
             s_cst[s + a] = cst;                                   // row stride L + 1: see phase A2
             s_info[s] = info;
         }
@@ -718,6 +727,7 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
             const uint32_t bal = __ballot_sync(FULL, v);
             if (v) {
                 const int pos = run + __popc(bal & ((1u << lane) - 1u));
+                GCP_DASSERT(pos >= 0 && pos < AL);
                 s_seq[pos] = g;
                 s_own[pos] = (uint8_t)(a | ((a >= 1 && pos == s_base[a]) ? 0x80 : 0));
             }
@@ -740,6 +750,7 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
             }
             h = (h + 1 == (uint32_t)T3) ? 0u : h + 1;    // T3 > n: always terminates
         }
+        GCP_DASSERT(h < (uint32_t)T3 && i < AL);
         atomicAdd(&s_hcnt[h], 1u);
         s_slot[i] = (uint16_t)h;
     }
@@ -779,6 +790,7 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
         if (__popc(owners) == 1) {
             if (c & (1u << 17)) { const int a = __ffs(owners) - 1; atomicAdd(&s_lc[a * A + a], 1); }
         } else {
+            GCP_DASSERT(owners < (A >= 32 ? 0xFFFFFFFFu : (1u << A)) || A >= 32);
             for (uint32_t mx = owners; mx; mx &= mx - 1) {
                 const int x = __ffs(mx) - 1;
                 for (uint32_t my = mx & (mx - 1); my; my &= my - 1)

@@ -251,6 +251,7 @@ k_loop_closures_part(const int32_t* __restrict__ dna, uint32_t P, int A, int L, 
         const int leader = __ffs(peers) - 1;
         if (i < n && lane == leader) base = atomicAdd(&s_pcnt[p], (uint32_t)__popc(peers));
         base = __shfl_sync(FULL, base, leader);
+        GCP_DASSERT(i >= n || s_pbase[p] + base + (uint32_t)__popc(peers & ((1u << lane) - 1u)) < (uint32_t)n);
         if (i < n)
             rec[s_pbase[p] + base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = (key << 16) | (unsigned long long)i;
     }

@@ -146,6 +146,7 @@ __device__ int w_walk(const GcpTables& t, const VaryParams& vp, int32_t* r, int 
             nxt = (int)__shfl_sync(FULL, c, src);
         }
         ++pos;
+        GCP_DASSERT(pos < vp.L && nxt >= 0 && (uint32_t)nxt < t.N);
         if (lane == 0) r[pos] = nxt;
         __syncwarp();
         cur = nxt;
@@ -263,6 +264,7 @@ __device__ int t_walk(const GcpTables& t, const VaryParams& vp, G* r, int pos, i
         #pragma unroll
         for (int k = MEMT - 1; k > 0; --k) hist[k] = (k < mem) ? hist[k - 1] : -2;
         hist[0] = (mem > 0) ? nxt : -2;
+        GCP_DASSERT(pos + 1 < vp.L && nxt >= 0 && (uint32_t)nxt < t.N);
         r[++pos] = (G)nxt;
         cur = nxt;
     }
@@ -463,6 +465,7 @@ __device__ __forceinline__ const G* shard_org(const ShardTab& sh, uint32_t g, si
 {
     const uint32_t s = (sh.world == 1) ? 0u : g / sh.per;
     const uint32_t loc = g - s * sh.per;
+    GCP_DASSERT(s < sh.world && loc < sh.per);
     return reinterpret_cast<const G*>(sh.base[s]) + (size_t)loc * org_genes;
 }
 
@@ -572,6 +575,7 @@ k_crossover(ShardTab parents, const int32_t* __restrict__ strong, uint32_t P, ui
         }
         __syncwarp();
     }
+    GCP_DASSERT(sel_i < 0 || (sel_i >= 1 && sel_i < lm && sel_j >= 1 && sel_j < ld && pm[sel_i] == pd[sel_j]));
     int n1, n2;
     if (sel_i >= 0) {
         // dna1 = self[0:i] + mate[j:], dna2 = mate[0:j] + self[i:]  (:225-229), cut at L
@@ -659,6 +663,7 @@ __global__ void k_mutation_list(const G* __restrict__ dna, uint32_t P, VaryParam
         int len, idx, tail;
         if (!mutation_cut<G>(dna + (size_t)gid * vp.L, vp, rng, &len, &idx, &tail)) continue;
         const int c = mw_class(tail, vp.L);
+        GCP_DASSERT(c >= 0 && c < MW_BINS && tail >= 1 && idx >= 1 && idx < len);
         pairs[atomicAdd(counter, 1u)] = make_uint2(gid, (uint32_t)c);
         atomicAdd(&counter[1 + c], 1u);
     }
@@ -689,7 +694,9 @@ __global__ void k_mutation_place(uint32_t* __restrict__ counter, const uint2* __
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= counter[0]) return;
     const uint2 pr = pairs[j];
-    list[counter[1 + MW_BINS + pr.y] + atomicAdd(&counter[1 + pr.y], 1u)] = pr.x;
+    const uint32_t at = counter[1 + MW_BINS + pr.y] + atomicAdd(&counter[1 + pr.y], 1u);
+    GCP_DASSERT(pr.y < (uint32_t)MW_BINS && at < counter[0]);
+    list[at] = pr.x;
 }
 
 template <typename G, int MEMT>
@@ -801,11 +808,13 @@ k_muterpolate_rows(G* __restrict__ dna, GcpTables t, VaryParams vp, uint64_t see
                     if (t_is_edge_csr(t, pt2, c)) { if (pick == 0) { step = c; break; } --pick; }
                 }
             }
+            GCP_DASSERT(idx1 + 1 < gap_lo && step >= 0 && (uint32_t)step < t.N);
             r[idx1 + 1] = (G)step;                                     // :302
             changed = true;
             const int ndel = idx2 - idx1 - 3;                          // delete idx1+2 .. idx2-2
             if (ndel > 0) {
                 const int new_lo = idx1 + 2;                           // <= gap_lo always
+                GCP_DASSERT(new_lo <= gap_lo && gap_lo - 1 + gap_len < L);
                 for (int x = gap_lo - 1; x >= new_lo; --x) r[x + gap_len] = r[x];   // move the gap left
                 gap_lo = new_lo;
                 gap_len += ndel;
@@ -881,6 +890,7 @@ __global__ void k_gather_survivors(const int32_t* __restrict__ order, uint32_t P
     }
     const uint32_t k = k_begin + blockIdx.x;
     const uint32_t src = (uint32_t)order[k];
+    GCP_DASSERT(src < 2u * P);
     const ShardTab& sh = (src < P) ? par : kid;
     const uint32_t g = (src < P) ? src : src - P;
     const uint32_t s = (sh.world == 1) ? 0u : g / sh.per;

@@ -122,10 +122,13 @@ class ShardedEvolution(object):
       7. rendezvous of the ranks on the device (`gcp_peer_barrier`, flags in peer memory)
     Philox streams are keyed by GLOBAL organism ids: the result is bit-identical for any W."""
 
-    def __init__(self, engine, gen_params, pop_size, group=None, gene_dtype=None, barrier="peer"):
+    def __init__(self, engine, gen_params, pop_size, group=None, gene_dtype=None, barrier="peer",
+                 shard=True):
+        """shard=False: keep the whole population on this GPU even under torch.distributed (every
+        rank then evolves the same population redundantly; same results)."""
         self.eng = engine
         self.group = group
-        on = dist.is_available() and dist.is_initialized()
+        on = shard and dist.is_available() and dist.is_initialized()
         self.world = dist.get_world_size(group) if on else 1
         self.rank_id = dist.get_rank(group) if on else 0
         self.P = int(pop_size)

@@ -157,11 +157,16 @@ class GeneticalGorithm(object):
         self._obj_sc = self._scaled()
 
     def _new_evo(self):
+        import torch.distributed as dist
         from .distributed import ShardedEvolution
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        # a population that does not split into whole pairs per rank stays replicated: every rank
+        # evolves all of it (same seed, same result) instead of failing
         return ShardedEvolution(self._eng, {'gamma': self._gamma,
                                             'coverage_constr_0': -self._cov_constr_0,
                                             'coverage_constr_f': -self._cov_constr_f,
-                                            'coverage_aging': self._cov_aging}, self._G_sz)
+                                            'coverage_aging': self._cov_aging}, self._G_sz,
+                                shard=(self._G_sz % (2 * world) == 0))
 
     def _scaled(self):
         return self._eng.maximin(self._evo.obj, self._coverage_constr(), return_scaled=True)[1]
