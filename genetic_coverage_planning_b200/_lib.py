@@ -4,8 +4,10 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-# GCP_LIB=debug loads the bounds-checked build (build.py: libgcp_debug.so) - tests only
-LIB_PATH = os.path.join(HERE, "libgcp_debug.so" if os.environ.get("GCP_LIB") == "debug" else "libgcp.so")
+# GCP_LIB=debug loads the bounds-checked build (build.py: libgcp_debug.so) - tests only;
+# GCP_LIB=<tag> any other in-tree libgcp_<tag>.so (A/B runs of an experimental build)
+_tag = os.environ.get("GCP_LIB", "")
+LIB_PATH = os.path.join(HERE, "libgcp_%s.so" % _tag if _tag and _tag != "release" else "libgcp.so")
 
 GCP_ABI_VERSION = 2
 GCP_MAX_SHARDS = 16

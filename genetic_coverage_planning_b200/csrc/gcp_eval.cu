@@ -277,7 +277,7 @@ k_coverage(const uint32_t* __restrict__ edge_ids, uint32_t P, GcpTables t, int A
             {
                 const int per = T / THREADS;
                 uint32_t loc = 0;
-                for (int k = 0; k < per; ++k) loc += s_cnt[tid * per + k];
+                for (int k = 0; k < per; ++k) loc += s_cnt[k * THREADS + tid];
                 uint32_t inc = loc;
                 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -290,9 +290,9 @@ k_coverage(const uint32_t* __restrict__ edge_ids, uint32_t P, GcpTables t, int A
                 for (int w2 = 0; w2 < warp; ++w2) woff += s_wsum[w2];
                 uint32_t run = woff + inc - loc;
                 for (int k = 0; k < per; ++k) {
-                    const uint32_t c = s_cnt[tid * per + k];
+                    const uint32_t c = s_cnt[k * THREADS + tid];
                     // keep the count in the high half: cnt[slot] = count<<16 | base
-                    s_cnt[tid * per + k] = (c << 16) | run;
+                    s_cnt[k * THREADS + tid] = (c << 16) | run;
                     run += c;
                 }
             }
@@ -559,7 +559,7 @@ k_coverage_masked(const uint32_t* __restrict__ step_info, uint32_t P,
             {
                 const int per = T / THREADS;
                 uint32_t loc = 0;
-                for (int k = 0; k < per; ++k) loc += s_cnt[tid * per + k];
+                for (int k = 0; k < per; ++k) loc += s_cnt[k * THREADS + tid];
                 uint32_t inc = loc;
                 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -572,8 +572,8 @@ k_coverage_masked(const uint32_t* __restrict__ step_info, uint32_t P,
                 for (int w2 = 0; w2 < warp; ++w2) woff += s_wsum[w2];
                 uint32_t run = woff + inc - loc;
                 for (int k = 0; k < per; ++k) {
-                    const uint32_t c = s_cnt[tid * per + k];
-                    s_cnt[tid * per + k] = (c << 16) | run;
+                    const uint32_t c = s_cnt[k * THREADS + tid];
+                    s_cnt[k * THREADS + tid] = (c << 16) | run;
                     run += c;
                 }
             }

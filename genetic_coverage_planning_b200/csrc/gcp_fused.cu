@@ -336,10 +336,13 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
             if (overflow) { __syncthreads(); break; }
             const uint32_t npairs = s_npairs;
             // ---- exclusive scan of the (slot, quarter) counts ----
+            //      (thread t owns counters t, t + THREADS, ...: consecutive lanes hit consecutive banks; the
+            //      order in which the lists end up in the sorted array is irrelevant, only that every
+            //      (slot, quarter) gets its own contiguous range)
             {
                 const int per = 4 * T / KF_THREADS;
                 uint32_t loc = 0;
-                for (int k = 0; k < per; ++k) loc += s_cq[tid * per + k];
+                for (int k = 0; k < per; ++k) loc += s_cq[k * KF_THREADS + tid];
                 uint32_t inc = loc;
                 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -352,8 +355,8 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
                 for (int w2 = 0; w2 < warp; ++w2) woff += s_wsum[w2];
                 uint32_t run = woff + inc - loc;
                 for (int k = 0; k < per; ++k) {
-                    const uint32_t c = s_cq[tid * per + k];
-                    s_cq[tid * per + k] = (c << 16) | run;
+                    const uint32_t c = s_cq[k * KF_THREADS + tid];
+                    s_cq[k * KF_THREADS + tid] = (c << 16) | run;
                     run += c;
                 }
             }
