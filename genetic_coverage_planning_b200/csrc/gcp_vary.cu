@@ -736,12 +736,20 @@ __device__ __forceinline__ bool t_is_edge_csr(const GcpTables& t, int a, int b)
     return false;
 }
 
+// `spread` (a power of two <= 32): only every spread-th thread takes a row.  The rows of a warp follow
+// different control paths (coins, break / continue), which SIMT serialises: a warp's time is the SUM
+// of its rows' instruction streams.  With few rows to process the machine has warps to spare, and one
+// row per warp finishes 32 x sooner than 32 rows in one warp; the host picks `spread` so that the rows
+// still fill the SMs.
 template <typename G>
 __global__ void __launch_bounds__(MW_THREADS)
 k_muterpolate_rows(G* __restrict__ dna, GcpTables t, VaryParams vp, uint64_t seed, uint32_t gen,
-                   uint32_t salt, const uint32_t* __restrict__ counter, const uint32_t* __restrict__ list)
+                   uint32_t salt, const uint32_t* __restrict__ counter, const uint32_t* __restrict__ list,
+                   uint32_t spread)
 {
-    const uint32_t j = blockIdx.x * MW_THREADS + threadIdx.x;
+    const uint32_t g = blockIdx.x * MW_THREADS + threadIdx.x;
+    if (g & (spread - 1u)) return;
+    const uint32_t j = g / spread;
     if (j >= *counter) return;
     const int L = vp.L;
     const uint32_t gid = list[j];
@@ -1027,7 +1035,12 @@ static int mutate_impl(gcp_ctx* c, G* dna, uint32_t P, uint32_t org_offset, uint
     if (vp.muterp_prob > 0.f && vp.num_muterp > 0) {   // muterpolate (:163-165)
         GCP_CUDA(c, cudaMemsetAsync(counter + 768, 0, 4, st));
         k_mutation_list<G><<<(P + 255) / 256, 256, 0, st>>>(dna, P, vp, seed, gen, salt, 1, counter + 768, list, pairs);
-        k_muterpolate_rows<G><<<row_grid, MW_THREADS, 0, st>>>(dna, c->t, vp, seed, gen, salt, counter + 768, list);
+        // expected rows = organisms x coin probability x agents; warps available = SMs x 48
+        const double rows_est = (double)P * vp.muterp_prob * vp.A + 64.0;
+        uint32_t spread = 32;
+        while (spread > 1 && rows_est * spread > (double)c->num_sms * 48.0 * 32.0) spread >>= 1;
+        const uint32_t mgrid = (uint32_t)(((uint64_t)n_rows * spread + MW_THREADS - 1) / MW_THREADS);
+        k_muterpolate_rows<G><<<mgrid, MW_THREADS, 0, st>>>(dna, c->t, vp, seed, gen, salt, counter + 768, list, spread);
         c->launches += 2;
     }
     k_post_mutate<G><<<(n_rows + VARY_WARPS - 1) / VARY_WARPS, VARY_WARPS * 32, smem, st>>>(dna, P, c->t, vp,

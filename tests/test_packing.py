@@ -161,3 +161,21 @@ def test_footprints_clipped_at_the_map_border_like_cv2(golden_dir):
         assert not mine[H:].any() and not mine[:, W:].any()
         assert np.array_equal(mine[:H, :W], fo._painted_map(w, dna))
         assert tuple(fo.calc_obj(w, dna)) == tuple(o._obj_val)       # oracle == the reference's stored objectives
+
+
+def test_parallel_packing_is_identical():
+    """pack_world(workers=N) rasterises edge ranges in forked processes and stitches the stores:
+    every array must equal the single-process result."""
+    from genetic_coverage_planning_b200 import packing, synth
+    w = synth.make_world(640, seed=4)
+    a = packing.pack_world(w.img, w.xy, w.row_ptr, w.col, w.edge_poly, w.edge_theta, w.edge_dist,
+                           w.map_params, workers=1)
+    b = packing.pack_world(w.img, w.xy, w.row_ptr, w.col, w.edge_poly, w.edge_theta, w.edge_dist,
+                           w.map_params, workers=3)
+    assert set(a.__dict__) == set(b.__dict__)
+    for k, v in a.__dict__.items():
+        u = b.__dict__[k]
+        if isinstance(v, np.ndarray):
+            assert v.dtype == u.dtype and np.array_equal(v, u), k
+        else:
+            assert v == u, k
