@@ -425,6 +425,30 @@ def test_many_agents_long_rows(synth_setup):
         assert np.array_equal(det['lc_mat'].astype(np.int32), r.lc_mat.cpu().numpy()[k])
 
 
+def test_host_pipeline_long_genomes_equals_device_call(synth_setup):
+    """gcp_eval_host overlaps neighbouring chunks on three streams; the long-genome kernels keep
+    bucket records in per-context scratch, one stretch per pipeline slot.  16 agents x 640 genes over
+    enough organisms for the slots to wrap (chunks of 1,024 / 2,048 / 4,096 / 4,096 ...): the host call
+    must return what one device-resident call returns."""
+    import torch
+    from genetic_coverage_planning_b200 import synth, worlds
+    from genetic_coverage_planning_b200.engine import FitnessEngine
+    sw, pw, ow, op, eng, starts = synth_setup
+    A, L = 16, 640
+    st = synth.spread_starts(sw.xy, A, 1024)
+    eng2 = FitnessEngine(pw, worlds.org_params_for(dict(L=L), st), num_agents=A)
+    base = synth.random_walk_population(sw.xy, sw.row_ptr, sw.col, st, 48, 520, L, seed=21).astype(np.int32)
+    base[::5, 3, 200:] = -1                                       # ragged rows, different work per organism
+    pick = np.random.default_rng(3).integers(0, len(base), 12000)
+    dna = np.ascontiguousarray(base[pick])
+    want = eng2.evaluate(dna)
+    obj_h, flags_h = eng2.evaluate_host(torch.from_numpy(dna).pin_memory())
+    assert np.array_equal(obj_h.numpy(), want.obj.cpu().numpy())
+    assert np.array_equal(flags_h.numpy(), want.flags.cpu().numpy())
+    one = eng2.evaluate(base)                                     # and each copy equals its original
+    assert np.array_equal(want.obj.cpu().numpy(), one.obj.cpu().numpy()[pick])
+
+
 def test_maximum_genome(synth_setup):
     """The largest chromosome the ABI accepts (32 agents x 2,047 genes = 65,504 <= 65,535):
     staged kernels, many hash partitions, bit-exact against the oracle."""
