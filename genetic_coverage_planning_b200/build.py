@@ -79,5 +79,32 @@ def build(force=False, verbose=False, debug=False):
     return lib
 
 
+def build_variant(tag, defines, sources=("gcp_fused.cu",)):
+    """libgcp_<tag>.so = the release objects with `sources` recompiled under extra -D switches
+    (A/B runs of kernel experiments: GCP_LIB=<tag> python profiles/exp_fused.py ...)."""
+    build()
+    objs = []
+    for s in SOURCES:
+        obj = os.path.join(OBJDIR, "%s.rel.o" % s[:-3])
+        if s in sources:
+            obj = os.path.join(OBJDIR, "%s.%s.o" % (s[:-3], tag))
+            src, rc, out = _compile(os.path.join(CSRC, s), obj, ["-DNDEBUG"] + ["-D" + d for d in defines], False)
+            if rc != 0:
+                sys.stderr.write(out)
+                raise RuntimeError("nvcc failed on %s" % src)
+        objs.append(obj)
+    lib = os.path.join(HERE, "libgcp_%s.so" % tag)
+    r = subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib] + objs,
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed linking %s" % lib)
+    return lib
+
+
 if __name__ == "__main__":
+    if "--variant" in sys.argv:          # --variant tag KF_X_A=0 KF_X_B=1 ...
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv))

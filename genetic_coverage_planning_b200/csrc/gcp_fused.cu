@@ -16,7 +16,11 @@
 //
 #include "gcp_common.cuh"
 #include "gcp_device.cuh"
+#include <type_traits>
 
+#ifndef KF_A1_U
+#define KF_A1_U 1        // steps per thread whose table loads are issued together in phase A1
+#endif
 constexpr int KF_PPT = 12;               // items (quarters) staged per thread: MAXP <= 12 * threads
 constexpr uint32_t KF_NIL = 0xFFFFFFFFu;
 
@@ -27,6 +31,7 @@ struct FusedShape {
     int gene16;          // chromosome stored as int16 in global memory
     int prefetch;        // footprint store outgrows the L2: B1 prefetches every quarter line into the L2
     uint32_t R0;
+    int c_overlap;       // loop-closure tables (32-bit keys) fit in front of the sorted quarter array
     uint32_t DS;         // slots of the step-dedup hash set (power of two, 0 = skip)
     uint32_t off_info, off_x, off_cst, off_lc, off_cost;   // byte offsets into dynamic smem (off_cst relative to off_x)
 };
@@ -50,7 +55,8 @@ template <int KF_THREADS, bool HAS_GRAY, bool BUCKETS = false>
 __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const GcpTables& t,
                                                   int T, int MAXP, uint32_t R0, uint32_t DS, unsigned char* s_x,
                                                   uint32_t& n_cov, uint32_t& n_wg, bool& failed,
-                                                  uint2* rec = nullptr, uint32_t rec_cap = 0, bool prefetch = false)
+                                                  uint2* rec = nullptr, uint32_t rec_cap = 0, bool prefetch = false,
+                                                  bool tail_barrier = true)
 {
     constexpr int KF_NW = KF_THREADS / 32;
     __shared__ uint32_t s_npairs, s_overflow, s_group;
@@ -59,8 +65,10 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t* s_keys = reinterpret_cast<uint32_t*>(s_x);      // [T] block id + 1
     uint32_t* s_cq   = s_keys + T;                             // [T][4] count -> count<<16 | base
-    uint32_t* s_pay  = s_cq + 4 * T;                           // [MAXP] uint4 index of the quarter, then sorted
-    uint32_t* s_sr   = s_pay + MAXP;                           // [MAXP] slot<<18 | q<<16 | rank
+    uint32_t* s_sr   = s_cq + 4 * T;                           // [MAXP] slot<<18 | q<<16 | rank
+    uint32_t* s_pay  = s_sr + MAXP;                            // [MAXP] uint4 index of the quarter, then sorted
+    // (s_pay last: B2 reads nothing else, so the caller may start reusing everything in front of it
+    //  as soon as it has passed the barrier in front of B2 - `tail_barrier` false)
     const int logT = 31 - __clz(T);
     const uint32_t myq = lane >> 3, l7 = lane & 7;
 
@@ -76,12 +84,7 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
             const uint32_t inf = info[s];
             if (!inf) continue;
             uint32_t h = (inf * 0x9E3779B1u) >> sh_ds;
-            for (;;) {
-                const uint32_t cur = atomicCAS(&s_set[h], 0u, inf);
-                if (cur == 0u) break;
-                if (cur == inf) { info[s] = 0u; break; }
-                h = (h + 1) & (DS - 1);
-            }
+            if (atomicExch(&s_set[h], inf) == inf) info[s] = 0u;      // see k_eval_fused phase A1
         }
         __syncthreads();
     }
@@ -416,7 +419,25 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
                 const uint32_t steps = __reduce_max_sync(FULL, len);
                 const uint32_t* pb = s_pay + bnd[0];
                 uint4 acc = make_uint4(0, 0, 0, 0);
-                for (uint32_t k = 0; k < steps; k += 4) {
+                uint32_t k = 0;
+                // the ranges of a warp's four groups are equal up to the snapping: no guards up to the
+                // shortest one
+                const uint32_t steps_min = __reduce_min_sync(FULL, len) & ~3u;
+                for (; k < steps_min; k += 4) {
+                    uint32_t e[4];
+                    uint4 v[4];
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        e[j] = pb[k + j];
+                        v[j] = __ldg(tile_at(tile_l, e[j] & 0x7FFFFFFFu));
+                    }
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc.x |= v[j].x; acc.y |= v[j].y; acc.z |= v[j].z; acc.w |= v[j].w;
+                        if (e[j] >> 31) { n_cov += popc128(acc); acc = make_uint4(0, 0, 0, 0); }
+                    }
+                }
+                for (; k < steps; k += 4) {
                     uint32_t e[4];
                     uint4 v[4];
                     #pragma unroll
@@ -482,7 +503,8 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
                     }
                 }
             }
-            __syncthreads();
+            // binary maps, one partition: B2 only reads the sorted array and registers
+            if (HAS_GRAY || tail_barrier || R > 1) __syncthreads();
         }
         if (!overflow) break;
         R <<= 1;
@@ -507,6 +529,10 @@ struct StaticShape {
     static constexpr uint32_t cov_b = (uint32_t)T * 20 + (uint32_t)MAXP * 8 + 32;
     static constexpr uint32_t a_b = off_cst + (uint32_t)SAL * 16 + GCP_MAX_AGENTS * 16;
     static constexpr uint32_t lc_b = c_al16((uint32_t)T3 * 12 + (uint32_t)SAL) + (uint32_t)SAL * 4;
+    static constexpr uint32_t lc_b32 = c_al16((uint32_t)T3 * 8 + (uint32_t)SAL) + (uint32_t)SAL * 4;   // 32-bit keys
+    // loop-closure tables (32-bit keys) fit in front of the sorted quarter array: phase C starts
+    // while other warps are still in B2
+    static constexpr bool c_overlap = lc_b32 <= (uint32_t)T * 20 + (uint32_t)MAXP * 4;
     static constexpr uint32_t x_b = cov_b > lc_b ? (cov_b > a_b ? cov_b : a_b) : (lc_b > a_b ? lc_b : a_b);
     static constexpr uint32_t off_info = c_al16((uint32_t)SAL * 4);
     static constexpr uint32_t off_x = off_info + c_al16((uint32_t)SAL * 4);
@@ -516,7 +542,7 @@ struct StaticShape {
 // KF_THREADS = 256 (5 CTAs / SM) for reference-sized genomes, 1024 (one CTA / SM) for long ones.
 // HAS_GRAY: the map has pixels with 0 < g < 255: covered gray mask pixels weigh 255 - g.
 // SAL > 0: A*L == SAL and the shared-memory layout is StaticShape<SAL> (must equal fused_shape()).
-template <int KF_THREADS, bool HAS_GRAY, int SAL>
+template <int KF_THREADS, bool HAS_GRAY, int SAL, bool KEY32>
 __global__ void __launch_bounds__(KF_THREADS, KF_THREADS == 256 ? 5 : 1)
 k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape sh,
              gcp_params prm, gcp_map_consts mc,
@@ -536,7 +562,7 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     double*   s_cost = reinterpret_cast<double*>(smem + sh.off_cost);         // dist[A], turn[A]
     __shared__ int s_first_neg[GCP_MAX_AGENTS], s_len[GCP_MAX_AGENTS], s_base[GCP_MAX_AGENTS + 1];
     __shared__ int s_bad;
-    __shared__ uint32_t s_total, s_totalw;
+    __shared__ uint32_t s_total, s_totalw, s_ngroups;
     __shared__ uint32_t s_cov[4];
 
     const uint32_t org = blockIdx.x;
@@ -596,7 +622,79 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     __syncthreads();
 
     // ------------------------------------------------------------------ phase A1: edge lookup
-    {
+    if (t.adjc16) {
+        // U steps per thread at a time: all adjacency loads first, then all cost / item-range loads
+        // (two dependent L2 round trips per batch instead of two per step)
+        constexpr int U = KF_A1_U;
+        int bad = 0;
+        for (int s0 = tid; s0 < AL; s0 += U * KF_THREADS) {
+            int a_[U];
+            uint32_t e_[U], w_[U], nx_[U];
+            uint4 q_[U];
+            bool act_[U], sent_[U];
+            #pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int s = s0 + u * KF_THREADS;
+                act_[u] = false; sent_[u] = false; a_[u] = 0; e_[u] = GCP_INVALID_EDGE; w_[u] = 0; nx_[u] = 0;
+                q_[u] = make_uint4(0, 0, 0, 0);
+                if (s < AL) {
+                    const int a = (int)__umulhi((uint32_t)s, sh.inv_L);
+                    const int i = s - a * L;
+                    const int g = s_dna[s];
+                    a_[u] = a;
+                    if (g < -1 || (g >= 0 && (uint32_t)g >= t.N)) bad |= 2;
+                    if (i < min(s_first_neg[a], L - 1)) {
+                        int nx = s_dna[s + 1];
+                        sent_[u] = nx < 0;
+                        if (nx < 0) nx += (int)t.N;              // numpy wrap: -1 -> N-1
+                        if ((uint32_t)g < t.N && nx >= 0 && (uint32_t)nx < t.N) {
+                            act_[u] = true; w_[u] = (uint32_t)g; nx_[u] = (uint32_t)nx;
+                            e_[u] = __ldg(t.row_ptr + g);
+                            q_[u] = __ldg(t.adjc16 + g);         // 8 x u16 columns in one 16-B load
+                        }
+                    }
+                }
+            }
+            uint32_t info_[U];
+            double2 cst_[U];
+            #pragma unroll
+            for (int u = 0; u < U; ++u) {
+                info_[u] = 0; cst_[u] = make_double2(0.0, 0.0);
+                if (act_[u]) {
+                    const uint4 q = q_[u];
+                    const uint32_t pat = nx_[u] * 0x00010001u;
+                    const uint32_t m0 = __vcmpeq2(q.x, pat), m1 = __vcmpeq2(q.y, pat);
+                    const uint32_t m2 = __vcmpeq2(q.z, pat), m3 = __vcmpeq2(q.w, pat);
+                    // one bit per 16-bit lane, in slot order
+                    const uint32_t hit = ((m0 & 1u) | ((m0 >> 15) & 2u)) | (((m1 & 1u) | ((m1 >> 15) & 2u)) << 2) |
+                                         (((m2 & 1u) | ((m2 >> 15) & 2u)) << 4) | (((m3 & 1u) | ((m3 >> 15) & 2u)) << 6);
+                    if (hit) e_[u] += (uint32_t)(__ffs(hit) - 1);
+                    else { e_[u] = t.E + w_[u]; if (!sent_[u]) bad |= 1; }   // null edge (F4)
+                    info_[u] = __ldg(t.m_q_info + e_[u]);
+                    cst_[u] = __ldg(t.edge_cost + e_[u]);
+                }
+            }
+            #pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int s = s0 + u * KF_THREADS;
+                if (s < AL) {
+                    uint32_t info = info_[u];
+                    if (DS && info) {                            // a revisited edge adds nothing to the union
+                        // one exchange, no probing: a step that finds its own item list in the slot is a
+                        // revisit of the step that put it there.  Dropping is an optimisation only (the
+                        // union is idempotent), so a slot shared with another edge may keep a duplicate;
+                        // the first arrival of every list always survives.
+                        const uint32_t h = (info * 0x9E3779B1u) >> (__clz(DS) + 1);
+                        if (atomicExch(&s_set[h], info) == info) info = 0u;
+                    }
+                    GCP_DASSERT(a_[u] < A && s + a_[u] < AL + GCP_MAX_AGENTS && (e_[u] == GCP_INVALID_EDGE || e_[u] < t.E + t.N));
+                    s_cst[s + a_[u]] = cst_[u];                   // row stride L + 1: see phase A2
+                    s_info[s] = info;
+                }
+            }
+        }
+        if (bad) atomicOr(&s_bad, bad);
+    } else {
         int bad = 0;
         for (int s = tid; s < AL; s += KF_THREADS) {
             const int a = (int)__umulhi((uint32_t)s, sh.inv_L);
@@ -615,16 +713,7 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
                     const uint32_t lo = __ldg(t.row_ptr + w);
                     e = t.E + w;                             // null edge unless found (F4)
                     bool found = false;
-                    if (t.adjc16) {                          // 8 x u16 columns in one 16-B load
-                        const uint4 q = __ldg(t.adjc16 + w);
-                        const uint32_t pat = (uint32_t)nx * 0x00010001u;
-                        const uint32_t m0 = __vcmpeq2(q.x, pat), m1 = __vcmpeq2(q.y, pat);
-                        const uint32_t m2 = __vcmpeq2(q.z, pat), m3 = __vcmpeq2(q.w, pat);
-                        // one bit per 16-bit lane, in slot order
-                        const uint32_t hit = ((m0 & 1u) | ((m0 >> 15) & 2u)) | (((m1 & 1u) | ((m1 >> 15) & 2u)) << 2) |
-                                             (((m2 & 1u) | ((m2 >> 15) & 2u)) << 4) | (((m3 & 1u) | ((m3 >> 15) & 2u)) << 6);
-                        if (hit) { e = lo + (uint32_t)(__ffs(hit) - 1); found = true; }
-                    } else if (t.adj8) {
+                    if (t.adj8) {
                         const uint4* rec = reinterpret_cast<const uint4*>(t.adj8 + (size_t)w * 8);
                         #pragma unroll
                         for (int h = 0; h < 4; ++h) {
@@ -640,14 +729,9 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
                     if (!found && !sentinel) bad |= 1;
                     info = __ldg(t.m_q_info + e);
                     cst = __ldg(t.edge_cost + e);
-                    if (DS && info) {                        // a revisited edge adds nothing to the union
-                        uint32_t h = (info * 0x9E3779B1u) >> (__clz(DS) + 1);
-                        for (;;) {
-                            const uint32_t cur = atomicCAS(&s_set[h], 0u, info);
-                            if (cur == 0u) break;
-                            if (cur == info) { info = 0u; break; }
-                            h = (h + 1) & (DS - 1);
-                        }
+                    if (DS && info) {                        // revisited edge: see above
+                        const uint32_t h = (info * 0x9E3779B1u) >> (__clz(DS) + 1);
+                        if (atomicExch(&s_set[h], info) == info) info = 0u;
                     }
                 }
             }
@@ -692,9 +776,12 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     }
     uint32_t n_cov, n_wg;
     bool failed;
+    // 32-bit loop-closure keys and binary map: phase C's tables lie in front of the sorted quarter
+    // array, so no barrier separates B2 from C (warps that finish their B2 range early go on)
+    const bool c_overlap = KEY32 && !HAS_GRAY && (ST ? SS::c_overlap : (sh.c_overlap != 0));
     coverage_quarters<KF_THREADS, HAS_GRAY>(s_info, AL, t, ST ? SS::T : sh.T, ST ? SS::MAXP : sh.MAXP,
                                             ST ? 1u : sh.R0, 0u, s_x, n_cov, n_wg, failed, nullptr, 0,
-                                            sh.prefetch != 0);
+                                            sh.prefetch != 0, !c_overlap);
     {
         uint32_t v = n_cov, vw = n_wg;
         #pragma unroll
@@ -702,21 +789,31 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
         if (lane == 0 && v) atomicAdd(&s_total, v);
         if (HAS_GRAY && lane == 0 && vw) atomicAdd(&s_totalw, vw);
     }
-    __syncthreads();      // B's tables are dead from here
+    if (!c_overlap) __syncthreads();      // B's tables are dead from here
 
     // ------------------------------------------------------------------ phase C: loop closures
+    // Consecutive gene pairs of the compacted sequence are hashed (key -> slot, members counted); the
+    // second arrival of a key opens a GROUP (duplicates are the minority: ~80 groups for ~900 pairs),
+    // whose record {slot << 16 | list head, owner mask} lives where the chromosome was (dead after
+    // the compaction).  Members chain themselves with one exchange, test their successor gap, and
+    // one thread per group updates lc_mat - no pass over the hash slots after the clear.
+    //   s_hcnt[h]: members (15 bits) | touches a row split << 15 (F10) | solo gap found << 16 | group id + 1 << 17
+    using HK = typename std::conditional<KEY32, uint32_t, unsigned long long>::type;
     const int T3 = ST ? SS::T3 : sh.T3;
-    unsigned long long* s_hkey = reinterpret_cast<unsigned long long*>(s_x);      // [T3]
+    HK*       s_hkey = reinterpret_cast<HK*>(s_x);                                 // [T3]
     uint32_t* s_hcnt = reinterpret_cast<uint32_t*>(s_hkey + T3);                   // [T3]
     uint8_t*  s_own  = reinterpret_cast<uint8_t*>(s_hcnt + T3);                    // [AL]
-    int32_t*  s_seq  = reinterpret_cast<int32_t*>(s_x + (((size_t)T3 * 12 + AL + 15) & ~(size_t)15)); // [AL]
+    int32_t*  s_seq  = reinterpret_cast<int32_t*>(s_x + (((size_t)T3 * (sizeof(HK) + 4) + AL + 15) & ~(size_t)15)); // [AL]
     uint16_t* s_slot = reinterpret_cast<uint16_t*>(s_info);                        // [AL]
     uint16_t* s_next = s_slot + AL;                                                // [AL]
-    for (int i = tid; i < T3; i += KF_THREADS) { s_hkey[i] = 0ull; s_hcnt[i] = 0u; }
+    uint32_t* g_head = reinterpret_cast<uint32_t*>(s_dna);                         // [AL/2] slot << 16 | newest member
+    uint32_t* g_own  = g_head + (AL >> 1);                                         // [AL/2] owner mask
+    for (int i = tid; i < T3; i += KF_THREADS) { s_hkey[i] = (HK)0; s_hcnt[i] = 0u; }
     if (tid == 0) {
         int b = 0;
         for (int a = 0; a < A; ++a) { s_base[a] = b; b += s_len[a]; }
         s_base[A] = b;
+        s_ngroups = 0;
     }
     __syncthreads();
     const int n = s_base[A];
@@ -737,39 +834,49 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
             run += __popc(bal);
         }
     }
-    __syncthreads();
-    // pass 1: hash every key, count group sizes
+    __syncthreads();                       // the chromosome is dead from here: group records take its place
+    for (int i = tid; i < (AL >> 1); i += KF_THREADS) { g_head[i] = KF_NIL; g_own[i] = 0u; }
+    // pass 1: hash every key, count the members, open a group at the second arrival
     for (int i = tid; i < n; i += KF_THREADS) {
-        const unsigned long long f = (uint32_t)s_seq[i] & 0xFFFFFFu;
-        const unsigned long long g = (uint32_t)s_seq[(i + 1 == n) ? 0 : i + 1] & 0xFFFFFFu;
-        const unsigned long long key = ((f << 24) | g) + 1ull;              // never 0
-        uint32_t h = __umulhi((uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32), (uint32_t)T3);
+        const uint32_t f = (uint32_t)s_seq[i], g = (uint32_t)s_seq[(i + 1 == n) ? 0 : i + 1];
+        HK key;
+        uint32_t h;
+        if (KEY32) {
+            key = (HK)((((f & 0xFFFFu) << 16) | (g & 0xFFFFu)) + 1u);      // ids < N <= 65,535: never 0
+            h = __umulhi((uint32_t)key * 0x9E3779B1u, (uint32_t)T3);
+        } else {
+            key = (HK)(((unsigned long long)(f & 0xFFFFFFu) << 24 | (g & 0xFFFFFFu)) + 1ull);
+            h = __umulhi((uint32_t)(((unsigned long long)key * 0x9E3779B97F4A7C15ull) >> 32), (uint32_t)T3);
+        }
         for (;;) {
-            const unsigned long long cur = ((volatile unsigned long long*)s_hkey)[h];
+            const HK cur = ((volatile HK*)s_hkey)[h];
             if (cur == key) break;
-            if (cur == 0ull) {
-                const unsigned long long old = atomicCAS(&s_hkey[h], 0ull, key);
-                if (old == 0ull || old == key) break;
+            if (cur == (HK)0) {
+                const HK old = atomicCAS(&s_hkey[h], (HK)0, key);
+                if (old == (HK)0 || old == key) break;
             }
             h = (h + 1 == (uint32_t)T3) ? 0u : h + 1;    // T3 > n: always terminates
         }
         GCP_DASSERT(h < (uint32_t)T3 && i < AL);
-        atomicAdd(&s_hcnt[h], 1u);
+        if ((atomicAdd(&s_hcnt[h], 1u) & 0x7FFFu) == 1u) {
+            const uint32_t gid = atomicAdd(&s_ngroups, 1u);
+            GCP_DASSERT(gid < (uint32_t)(AL >> 1));
+            atomicAdd(&s_hcnt[h], (gid + 1u) << 17);
+        }
         s_slot[i] = (uint16_t)h;
     }
     __syncthreads();
-    // pass 2: slots with a duplicate group become {head = NIL, owners = 0}
-    for (int h = tid; h < T3; h += KF_THREADS)
-        if (s_hcnt[h] >= 2u) s_hkey[h] = (unsigned long long)KF_NIL;        // lo = head, hi = owners
-    __syncthreads();
-    uint32_t* s_w = reinterpret_cast<uint32_t*>(s_hkey);                    // [2*h] head, [2*h+1] owners
+    // pass 2: members of duplicate groups chain themselves and leave their owner bit
     for (int i = tid; i < n; i += KF_THREADS) {
         const uint32_t h = s_slot[i];
-        if ((s_hcnt[h] & 0xFFFFu) < 2u) continue;
+        const uint32_t c = s_hcnt[h];
+        if ((c & 0x7FFFu) < 2u) continue;
+        const uint32_t gid = (c >> 17) - 1u;
         const uint8_t o = s_own[i];
-        s_next[i] = (uint16_t)atomicExch(&s_w[2 * h], (uint32_t)i);         // NIL -> 0xFFFF
-        atomicOr(&s_w[2 * h + 1], 1u << (o & 31));
-        if (o & 0x80) atomicOr(&s_hcnt[h], 1u << 16);                       // group touches a split (F10)
+        GCP_DASSERT(gid < (uint32_t)(AL >> 1));
+        s_next[i] = (uint16_t)atomicExch(&g_head[gid], (h << 16) | (uint32_t)i);       // NIL -> 0xFFFF
+        atomicOr(&g_own[gid], 1u << (o & 31));
+        if (o & 0x80) atomicOr(&s_hcnt[h], 1u << 15);                       // group touches a split (F10)
     }
     __syncthreads();
     // pass 3: successor gap test (ascending consecutive positions)
@@ -777,21 +884,21 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     for (int i = tid; i < n; i += KF_THREADS) {
         const uint32_t h = s_slot[i];
         const uint32_t c = s_hcnt[h];
-        if ((c & 0xFFFFu) < 2u || (c & (1u << 16))) continue;
+        if ((c & 0x7FFFu) < 2u || (c & (1u << 15))) continue;
         uint32_t succ = 0xFFFFFFFFu;
-        for (uint32_t j = s_w[2 * h]; j != 0xFFFFu && j != KF_NIL; j = s_next[j])
+        for (uint32_t j = g_head[(c >> 17) - 1u] & 0xFFFFu; j != 0xFFFFu; j = s_next[j])
             if (j > (uint32_t)i && j < succ) succ = j;
         if (succ != 0xFFFFFFFFu && (int)(succ - (uint32_t)i) > thresh)
-            atomicOr(&s_hcnt[h], 1u << 17);
+            atomicOr(&s_hcnt[h], 1u << 16);
     }
     __syncthreads();
     // pass 4: one thread per duplicate group updates lc_mat
-    for (int h = tid; h < T3; h += KF_THREADS) {
-        const uint32_t c = s_hcnt[h];
-        if ((c & 0xFFFFu) < 2u || (c & (1u << 16))) continue;
-        const uint32_t owners = s_w[2 * h + 1];
+    for (int gid = tid; gid < (int)s_ngroups; gid += KF_THREADS) {
+        const uint32_t c = s_hcnt[g_head[gid] >> 16];
+        if (c & (1u << 15)) continue;
+        const uint32_t owners = g_own[gid];
         if (__popc(owners) == 1) {
-            if (c & (1u << 17)) { const int a = __ffs(owners) - 1; atomicAdd(&s_lc[a * A + a], 1); }
+            if (c & (1u << 16)) { const int a = __ffs(owners) - 1; atomicAdd(&s_lc[a * A + a], 1); }
         } else {
             GCP_DASSERT(owners < (A >= 32 ? 0xFFFFFFFFu : (1u << A)) || A >= 32);
             for (uint32_t mx = owners; mx; mx &= mx - 1) {
@@ -956,7 +1063,7 @@ static size_t fused_shape(gcp_ctx* ctx, FusedShape& sh, int KF_THREADS)
     if (T > 8192) T = 8192;
     sh.T = T; sh.MAXP = maxp;
     sh.T3 = (sh.AL * 3) / 2 + 64;
-    if (sh.T3 > 65535) return 0;
+    if (sh.T3 > 65535 || sh.AL > 32767) return 0;                  // 16-bit slots, 15-bit member counts
     sh.DS = ctx->cov_dedup ? (uint32_t)T * 4 : 0u;                   // step-dedup hash set in front of s_cst
     sh.R0 = 1;
     while ((size_t)sh.R0 * maxp < (size_t)sh.AL * 2 && sh.R0 < 4096) sh.R0 <<= 1;
@@ -964,6 +1071,8 @@ static size_t fused_shape(gcp_ctx* ctx, FusedShape& sh, int KF_THREADS)
     const uint32_t cov_b = (uint32_t)T * 20 + (uint32_t)maxp * 8 + 32;  // + pad for B2's read-ahead
     const uint32_t a_b = sh.off_cst + (uint32_t)sh.AL * 16 + GCP_MAX_AGENTS * 16;    // + one pad entry per row
     const uint32_t lc_b = al16((uint32_t)sh.T3 * 12 + (uint32_t)sh.AL) + (uint32_t)sh.AL * 4;
+    const uint32_t lc_b32 = al16((uint32_t)sh.T3 * 8 + (uint32_t)sh.AL) + (uint32_t)sh.AL * 4;
+    sh.c_overlap = (sh.R0 == 1 && lc_b32 <= (uint32_t)T * 20 + (uint32_t)maxp * 4) ? 1 : 0;
     uint32_t x_b = cov_b > lc_b ? cov_b : lc_b;
     if (a_b > x_b) x_b = a_b;
     sh.off_info = al16((uint32_t)sh.AL * 4);
@@ -988,14 +1097,18 @@ int launch_eval_fused(gcp_ctx* ctx, const void* dna, int gene16, uint32_t P, con
     sh.prefetch = ctx->cov_prefetch >= 0 ? ctx->cov_prefetch
                                          : ((size_t)ctx->m_n_quarters * 128 > ((size_t)96 << 20) ? 1 : 0);
     StageTimer tm(ctx, 1, st);
-#define GCP_LAUNCH_FUSED(TH, GRAY, SAL)                                                                \
+#define GCP_LAUNCH_FUSED_K(TH, GRAY, SAL, K32)                                                         \
     do {                                                                                               \
-        GCP_CUDA(ctx, cudaFuncSetAttribute(k_eval_fused<TH, GRAY, SAL>,                                \
+        GCP_CUDA(ctx, cudaFuncSetAttribute(k_eval_fused<TH, GRAY, SAL, K32>,                           \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-        k_eval_fused<TH, GRAY, SAL><<<P, TH, smem, st>>>(dna, P, ctx->t, sh, ctx->p, ctx->mc, out->obj, \
+        k_eval_fused<TH, GRAY, SAL, K32><<<P, TH, smem, st>>>(dna, P, ctx->t, sh, ctx->p, ctx->mc, out->obj, \
                                                          out->neg_cov, out->dist, out->turn,           \
                                                          out->lc_mat, out->flags);                     \
     } while (0)
+    // node ids below 65,536: the loop-closure hash takes 32-bit keys (half the table, 32-bit CAS)
+    const bool key32 = ctx->t.N <= 65535u;
+#define GCP_LAUNCH_FUSED(TH, GRAY, SAL)                                                                \
+    do { if (key32) GCP_LAUNCH_FUSED_K(TH, GRAY, SAL, true); else GCP_LAUNCH_FUSED_K(TH, GRAY, SAL, false); } while (0)
     const bool gray = ctx->n_gray > 0;
     // the genome shapes of the reference's driver (pather_driver.py:122-158: max_dna_len 250 / 200 /
     // 150 / 125 / 125 / 200 for 1..6 agents) get the compile-time layout
@@ -1021,6 +1134,7 @@ int launch_eval_fused(gcp_ctx* ctx, const void* dna, int gene16, uint32_t P, con
         else                { if (gray) GCP_LAUNCH_FUSED(1024, true, 0); else GCP_LAUNCH_FUSED(1024, false, 0); }
     }
 #undef GCP_LAUNCH_FUSED
+#undef GCP_LAUNCH_FUSED_K
     ctx->launches++;
     GCP_CUDA(ctx, cudaGetLastError());
     return 0;

@@ -2,6 +2,7 @@
 """A/B of k_eval_fused variants on one GPU (options of gcp_set_option), results checked equal:
   python profiles/exp_fused.py C3|C5 [spread|diverse] [P] opt=a,b opt2=c,d ...
 every combination of the listed option values is timed (CUDA events, 20 launches after 5)."""
+import hashlib
 import itertools
 import json
 import os
@@ -54,7 +55,9 @@ def main():
             same = bool(torch.equal(ref, r.obj)) and not bool(r.flags[:, 3].any())
             print(json.dumps({"config": name, "starts": starts_mode, "P": P, "genes": label,
                               "options": dict(zip([k for k, _ in opts], combo)),
-                              "ms": a.elapsed_time(b) / 20, "same_results": same}), flush=True)
+                              "ms": a.elapsed_time(b) / 20, "same_results": same,
+                              "lib": os.environ.get("GCP_LIB", "release"),
+                              "obj_sha1": hashlib.sha1(r.obj.cpu().numpy().tobytes()).hexdigest()[:12]}), flush=True)
 
 
 if __name__ == "__main__":
