@@ -5,8 +5,13 @@
 //   phase A  path costs        mappy.py:341-352   (edge lookup, per-step costs, revisited edges dropped)
 //   phase B  wall coverage     mappy.py:353-364   (coverage_quarters: counting sort of quarter items
 //                                                  by (map block, quarter), flat union + popcount)
-//   phase C  loop closures     mappy.py:372-437   (shared-memory hash of consecutive gene pairs)
+//   phase C  loop closures     mappy.py:372-437   (shared-memory hash of consecutive gene pairs, one
+//                                                  record per duplicate group)
 //   phase D  constraints + objectives  geneticalgorithm.py:177-201
+//
+// Worlds with at most 65,534 waypoints run the COMPACT variant: 16-bit genes and sequence in
+// shared memory, 32-bit pair keys, 40 registers -> six resident CTAs per SM instead of five, and
+// phase C starts without a barrier while other warps still stream their B2 ranges.
 //
 // Preconditions (checked by the caller): pre-masked footprint store uploaded and
 // coverage_blend == 1 (wall coverage only); binary and gray maps (HAS_GRAY).  The staged kernels
@@ -73,8 +78,10 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
     const uint32_t myq = lane >> 3, l7 = lane & 7;
 
     // ---- B0: a walk revisits edges (18 % of the steps at 150-step walks, half of them at 512);
-    //      the union does not care, so only the first step of every distinct item list survives.
-    //      Hash set of the info words over the first DS words of s_x (DS = 0: table too small, skip).
+    //      the union does not care, so revisits are dropped: one exchange per step into a table of the
+    //      info words over the first DS words of s_x - a step that finds its own item list in its slot
+    //      is a revisit (DS = 0: table too small, skip).  No probing: a slot shared with another edge may
+    //      let a duplicate through, which costs time, never correctness.
     if (DS) {
         uint32_t* s_set = reinterpret_cast<uint32_t*>(s_x);
         const int sh_ds = __clz(DS) + 1;                       // 32 - log2(DS)
@@ -516,10 +523,14 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
 // shared-memory layout known at compile time the offsets fold into the LDS / STS / ATOMS
 // immediates instead of being rebuilt from kernel parameters in front of every access.
 constexpr uint32_t c_al16(uint32_t x) { return (x + 15u) & ~15u; }
-template <int SAL>
+// COMPACT (waypoint ids fit 16 bits, N <= 65,534): the chromosome and the compacted sequence are
+// held as u16, loop-closure keys take 32 bits and the item store is sized 49/24 instead of 9/4 items
+// per gene - together 37.4 KB instead of 41.7 KB for 6 x 200 genes, i.e. SIX resident CTAs per SM.
+template <int SAL, bool COMPACT>
 struct StaticShape {
     static constexpr int AL = SAL;
-    static constexpr int maxp0 = (9 * SAL) / 4 < 256 ? 256 : ((9 * SAL) / 4 > KF_PPT * 256 ? KF_PPT * 256 : (9 * SAL) / 4);
+    static constexpr int maxp_raw = COMPACT ? (49 * SAL) / 24 : (9 * SAL) / 4;
+    static constexpr int maxp0 = maxp_raw < 256 ? 256 : (maxp_raw > KF_PPT * 256 ? KF_PPT * 256 : maxp_raw);
     static constexpr int MAXP = (maxp0 + 7) & ~7;
     static constexpr int T = SAL / 3 <= 256 ? 256 : SAL / 3 <= 512 ? 512 : SAL / 3 <= 1024 ? 1024 : SAL / 3 <= 2048 ? 2048 : SAL / 3 <= 4096 ? 4096 : 8192;
     static constexpr int T3 = (SAL * 3) / 2 + 64;
@@ -528,22 +539,23 @@ struct StaticShape {
     static constexpr uint32_t off_cst = (uint32_t)T * 20;
     static constexpr uint32_t cov_b = (uint32_t)T * 20 + (uint32_t)MAXP * 8 + 32;
     static constexpr uint32_t a_b = off_cst + (uint32_t)SAL * 16 + GCP_MAX_AGENTS * 16;
-    static constexpr uint32_t lc_b = c_al16((uint32_t)T3 * 12 + (uint32_t)SAL) + (uint32_t)SAL * 4;
-    static constexpr uint32_t lc_b32 = c_al16((uint32_t)T3 * 8 + (uint32_t)SAL) + (uint32_t)SAL * 4;   // 32-bit keys
-    // loop-closure tables (32-bit keys) fit in front of the sorted quarter array: phase C starts
-    // while other warps are still in B2
-    static constexpr bool c_overlap = lc_b32 <= (uint32_t)T * 20 + (uint32_t)MAXP * 4;
+    // loop closures: keys (4 / 8 B) + counters (4 B) per slot, gene per position (COMPACT: 2 B + 2 B of the owner masks)
+    static constexpr uint32_t lc_b = c_al16((uint32_t)T3 * (COMPACT ? 8 : 12)) + (uint32_t)SAL * 4;
+    // the loop-closure tables fit in front of the sorted quarter array: phase C starts while other
+    // warps are still in B2
+    static constexpr bool c_overlap = COMPACT && lc_b <= (uint32_t)T * 20 + (uint32_t)MAXP * 4;
     static constexpr uint32_t x_b = cov_b > lc_b ? (cov_b > a_b ? cov_b : a_b) : (lc_b > a_b ? lc_b : a_b);
-    static constexpr uint32_t off_info = c_al16((uint32_t)SAL * 4);
+    static constexpr uint32_t off_info = c_al16((uint32_t)SAL * (COMPACT ? 2 : 4));
     static constexpr uint32_t off_x = off_info + c_al16((uint32_t)SAL * 4);
     static constexpr uint32_t off_lc = off_x + c_al16(x_b);
 };
 
-// KF_THREADS = 256 (5 CTAs / SM) for reference-sized genomes, 1024 (one CTA / SM) for long ones.
+// KF_THREADS = 256 (5 or 6 CTAs / SM) for reference-sized genomes, 1024 (one CTA / SM) for long ones.
 // HAS_GRAY: the map has pixels with 0 < g < 255: covered gray mask pixels weigh 255 - g.
 // SAL > 0: A*L == SAL and the shared-memory layout is StaticShape<SAL> (must equal fused_shape()).
-template <int KF_THREADS, bool HAS_GRAY, int SAL, bool KEY32>
-__global__ void __launch_bounds__(KF_THREADS, KF_THREADS == 256 ? 5 : 1)
+// COMPACT: N <= 65,534 waypoints - see StaticShape.
+template <int KF_THREADS, bool HAS_GRAY, int SAL, bool COMPACT>
+__global__ void __launch_bounds__(KF_THREADS, KF_THREADS == 256 ? ((COMPACT && !HAS_GRAY) ? 6 : 5) : 1)
 k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape sh,
              gcp_params prm, gcp_map_consts mc,
              double* __restrict__ obj, double* __restrict__ neg_cov_out,
@@ -551,10 +563,12 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
              int32_t* __restrict__ lc_out, uint8_t* __restrict__ flags)
 {
     constexpr int KF_NW = KF_THREADS / 32;
+    constexpr bool KEY32 = COMPACT;
+    using G = typename std::conditional<COMPACT, uint16_t, int32_t>::type;       // gene in shared memory
     extern __shared__ __align__(16) unsigned char smem[];
-    int32_t*  s_dna  = reinterpret_cast<int32_t*>(smem);                      // [AL]
+    G*        s_dna  = reinterpret_cast<G*>(smem);                            // [AL] (COMPACT: 0xFFFF = -1, 0xFFFE = out of range)
     constexpr bool ST = SAL > 0;
-    using SS = StaticShape<ST ? SAL : 1200>;
+    using SS = StaticShape<ST ? SAL : 1200, COMPACT>;
     uint32_t* s_info = reinterpret_cast<uint32_t*>(smem + (ST ? SS::off_info : sh.off_info)); // [AL] quarter-item range per step (C: slot/next)
     unsigned char* s_x = smem + (ST ? SS::off_x : sh.off_x);                  // B / C tables
     double2*  s_cst  = reinterpret_cast<double2*>(s_x + (ST ? SS::off_cst : sh.off_cst)); // [AL] {dist, turn} per step (A only; aliases s_pay/s_sr)
@@ -569,50 +583,86 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     if (org >= P) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int A = sh.A, L = sh.L, AL = ST ? SAL : sh.AL;
+    // gene i of the chromosome as the reference's integer (-1 = padding)
+    auto gene = [&](int i) -> int {
+        if (COMPACT) { const int v = (int)s_dna[i]; return v == 0xFFFF ? -1 : v; }
+        return (int)s_dna[i];
+    };
 
     // ------------------------------------------------------------------ load the chromosome
-    if (sh.gene16) {                       // int16 chromosome (N < 32768): half the bytes to move
-        const int16_t* d = reinterpret_cast<const int16_t*>(dna_v) + (size_t)org * AL;
-        if ((AL & 7) == 0) {
-            const int4* d8 = reinterpret_cast<const int4*>(d);
-            for (int i = tid; i < (AL >> 3); i += KF_THREADS) {
-                const int4 v = __ldg(d8 + i);
-                int4 lo, hi;
-                lo.x = (int)(short)(v.x & 0xFFFF); lo.y = v.x >> 16;
-                lo.z = (int)(short)(v.y & 0xFFFF); lo.w = v.y >> 16;
-                hi.x = (int)(short)(v.z & 0xFFFF); hi.y = v.z >> 16;
-                hi.z = (int)(short)(v.w & 0xFFFF); hi.w = v.w >> 16;
-                reinterpret_cast<int4*>(s_dna)[2 * i] = lo;
-                reinterpret_cast<int4*>(s_dna)[2 * i + 1] = hi;
+    if (tid == 0) { s_bad = 0; s_total = 0; s_totalw = 0; }
+    for (int i = tid; i < A * A; i += KF_THREADS) s_lc[i] = 0;
+    int bad_gene = 0;                      // a gene outside [-1, N): error bit 0 of flags[:, 3]
+    if (COMPACT) {
+        // u16 in shared memory: -1 -> 0xFFFF, anything else outside [0, N) -> 0xFFFE (>= N: never a
+        // waypoint, never a step; the organism's error flag is raised)
+        auto pack = [&](int g) -> uint32_t {
+            if (g == -1) return 0xFFFFu;
+            if ((uint32_t)g >= t.N) { bad_gene = 2; return 0xFFFEu; }
+            return (uint32_t)g;
+        };
+        uint16_t* s16 = reinterpret_cast<uint16_t*>(smem);
+        if (sh.gene16) {                   // int16 chromosome in global memory
+            const int16_t* d = reinterpret_cast<const int16_t*>(dna_v) + (size_t)org * AL;
+            if ((AL & 7) == 0) {
+                const int4* d8 = reinterpret_cast<const int4*>(d);
+                for (int i = tid; i < (AL >> 3); i += KF_THREADS) {
+                    const int4 v = __ldg(d8 + i);
+                    uint4 o;
+                    o.x = pack((int)(short)(v.x & 0xFFFF)) | (pack(v.x >> 16) << 16);
+                    o.y = pack((int)(short)(v.y & 0xFFFF)) | (pack(v.y >> 16) << 16);
+                    o.z = pack((int)(short)(v.z & 0xFFFF)) | (pack(v.z >> 16) << 16);
+                    o.w = pack((int)(short)(v.w & 0xFFFF)) | (pack(v.w >> 16) << 16);
+                    reinterpret_cast<uint4*>(s16)[i] = o;
+                }
+            } else {
+                for (int i = tid; i < AL; i += KF_THREADS) s16[i] = (uint16_t)pack((int)__ldg(d + i));
             }
         } else {
-            for (int i = tid; i < AL; i += KF_THREADS) s_dna[i] = (int)__ldg(d + i);
+            const int32_t* d = reinterpret_cast<const int32_t*>(dna_v) + (size_t)org * AL;
+            if ((AL & 3) == 0) {
+                const int4* d4 = reinterpret_cast<const int4*>(d);
+                for (int i = tid; i < (AL >> 2); i += KF_THREADS) {
+                    const int4 v = __ldg(d4 + i);
+                    reinterpret_cast<uint2*>(s16)[i] = make_uint2(pack(v.x) | (pack(v.y) << 16), pack(v.z) | (pack(v.w) << 16));
+                }
+            } else {
+                for (int i = tid; i < AL; i += KF_THREADS) s16[i] = (uint16_t)pack(__ldg(d + i));
+            }
         }
-        if (tid == 0) { s_bad = 0; s_total = 0; s_totalw = 0; }
-        for (int i = tid; i < A * A; i += KF_THREADS) s_lc[i] = 0;
     } else {
-        const int32_t* d = reinterpret_cast<const int32_t*>(dna_v) + (size_t)org * AL;
-        if ((AL & 3) == 0) {
-            const int4* d4 = reinterpret_cast<const int4*>(d);
-            int4* s4 = reinterpret_cast<int4*>(s_dna);
-            for (int i = tid; i < (AL >> 2); i += KF_THREADS) s4[i] = __ldg(d4 + i);
+        int32_t* s32 = reinterpret_cast<int32_t*>(smem);
+        auto check = [&](int g) { if (g < -1 || (g >= 0 && (uint32_t)g >= t.N)) bad_gene = 2; };
+        if (sh.gene16) {
+            const int16_t* d = reinterpret_cast<const int16_t*>(dna_v) + (size_t)org * AL;
+            for (int i = tid; i < AL; i += KF_THREADS) { const int g = (int)__ldg(d + i); check(g); s32[i] = g; }
         } else {
-            for (int i = tid; i < AL; i += KF_THREADS) s_dna[i] = __ldg(d + i);
+            const int32_t* d = reinterpret_cast<const int32_t*>(dna_v) + (size_t)org * AL;
+            if ((AL & 3) == 0) {
+                const int4* d4 = reinterpret_cast<const int4*>(d);
+                int4* s4 = reinterpret_cast<int4*>(s32);
+                for (int i = tid; i < (AL >> 2); i += KF_THREADS) {
+                    const int4 v = __ldg(d4 + i);
+                    check(v.x); check(v.y); check(v.z); check(v.w);
+                    s4[i] = v;
+                }
+            } else {
+                for (int i = tid; i < AL; i += KF_THREADS) { const int g = __ldg(d + i); check(g); s32[i] = g; }
+            }
         }
-        if (tid == 0) { s_bad = 0; s_total = 0; s_totalw = 0; }
-        for (int i = tid; i < A * A; i += KF_THREADS) s_lc[i] = 0;
     }
     // step-dedup hash set (see coverage_quarters B0): lives in front of s_cst during phase A1
     const uint32_t DS = ST ? SS::DS : sh.DS;
     uint32_t* s_set = reinterpret_cast<uint32_t*>(s_x);
     for (int i = tid; i < (int)DS; i += KF_THREADS) s_set[i] = 0u;
     __syncthreads();
+    if (bad_gene) atomicOr(&s_bad, bad_gene);
     // first -1 per row (step rule mappy.py:343-345) and number of valid genes (:390)
     for (int a = warp; a < A; a += KF_NW) {
         int first = L, cnt = 0;
         for (int i0 = 0; i0 < L; i0 += 32) {
             const int i = i0 + lane;
-            const int g = (i < L) ? s_dna[a * L + i] : 0;
+            const int g = (i < L) ? gene(a * L + i) : 0;
             const uint32_t neg = __ballot_sync(FULL, (i < L) && g < 0);
             if (neg && first == L) first = i0 + __ffs(neg) - 1;
             cnt += __popc(__ballot_sync(FULL, (i < L) && g != -1));
@@ -640,11 +690,10 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
                 if (s < AL) {
                     const int a = (int)__umulhi((uint32_t)s, sh.inv_L);
                     const int i = s - a * L;
-                    const int g = s_dna[s];
+                    const int g = gene(s);
                     a_[u] = a;
-                    if (g < -1 || (g >= 0 && (uint32_t)g >= t.N)) bad |= 2;
                     if (i < min(s_first_neg[a], L - 1)) {
-                        int nx = s_dna[s + 1];
+                        int nx = gene(s + 1);
                         sent_[u] = nx < 0;
                         if (nx < 0) nx += (int)t.N;              // numpy wrap: -1 -> N-1
                         if ((uint32_t)g < t.N && nx >= 0 && (uint32_t)nx < t.N) {
@@ -699,14 +748,13 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
         for (int s = tid; s < AL; s += KF_THREADS) {
             const int a = (int)__umulhi((uint32_t)s, sh.inv_L);
             const int i = s - a * L;
-            const int g = s_dna[s];
-            if (g < -1 || (g >= 0 && (uint32_t)g >= t.N)) bad |= 2;
+            const int g = gene(s);
             uint32_t e = GCP_INVALID_EDGE, info = 0;
             double2 cst = make_double2(0.0, 0.0);
             const int nsteps = min(s_first_neg[a], L - 1);
             if (i < nsteps) {
                 const uint32_t w = (uint32_t)g;
-                int nx = s_dna[s + 1];
+                int nx = gene(s + 1);
                 const bool sentinel = nx < 0;
                 if (nx < 0) nx += (int)t.N;                  // numpy wrap: -1 -> N-1
                 if (w < t.N && nx >= 0 && (uint32_t)nx < t.N) {
@@ -778,7 +826,7 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     bool failed;
     // 32-bit loop-closure keys and binary map: phase C's tables lie in front of the sorted quarter
     // array, so no barrier separates B2 from C (warps that finish their B2 range early go on)
-    const bool c_overlap = KEY32 && !HAS_GRAY && (ST ? SS::c_overlap : (sh.c_overlap != 0));
+    const bool c_overlap = COMPACT && !HAS_GRAY && (ST ? SS::c_overlap : (sh.c_overlap != 0));
     coverage_quarters<KF_THREADS, HAS_GRAY>(s_info, AL, t, ST ? SS::T : sh.T, ST ? SS::MAXP : sh.MAXP,
                                             ST ? 1u : sh.R0, 0u, s_x, n_cov, n_wg, failed, nullptr, 0,
                                             sh.prefetch != 0, !c_overlap);
@@ -802,12 +850,13 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     const int T3 = ST ? SS::T3 : sh.T3;
     HK*       s_hkey = reinterpret_cast<HK*>(s_x);                                 // [T3]
     uint32_t* s_hcnt = reinterpret_cast<uint32_t*>(s_hkey + T3);                   // [T3]
-    uint8_t*  s_own  = reinterpret_cast<uint8_t*>(s_hcnt + T3);                    // [AL]
-    int32_t*  s_seq  = reinterpret_cast<int32_t*>(s_x + (((size_t)T3 * (sizeof(HK) + 4) + AL + 15) & ~(size_t)15)); // [AL]
+    G*        s_seq  = reinterpret_cast<G*>(s_x + (((size_t)T3 * (sizeof(HK) + 4) + 15) & ~(size_t)15)); // [AL]
     uint16_t* s_slot = reinterpret_cast<uint16_t*>(s_info);                        // [AL]
     uint16_t* s_next = s_slot + AL;                                                // [AL]
     uint32_t* g_head = reinterpret_cast<uint32_t*>(s_dna);                         // [AL/2] slot << 16 | newest member
-    uint32_t* g_own  = g_head + (AL >> 1);                                         // [AL/2] owner mask
+    // [AL/2] owner mask: behind the heads where the chromosome took 4 bytes per gene, else behind s_seq
+    uint32_t* g_own  = COMPACT ? reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(s_seq) + (((size_t)AL * 2 + 3) & ~(size_t)3))
+                               : g_head + (AL >> 1);
     for (int i = tid; i < T3; i += KF_THREADS) { s_hkey[i] = (HK)0; s_hcnt[i] = 0u; }
     if (tid == 0) {
         int b = 0;
@@ -817,30 +866,26 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     }
     __syncthreads();
     const int n = s_base[A];
-    // compaction: seq[pos] = gene, own[pos] = agent | first-of-row(a>=1) << 7
+    // compaction: seq[pos] = gene (the owner of a position follows from s_base when it is needed)
     for (int a = warp; a < A; a += KF_NW) {
         int run = s_base[a];
         for (int i0 = 0; i0 < L; i0 += 32) {
             const int i = i0 + lane;
-            const int g = (i < L) ? s_dna[a * L + i] : -1;
+            const int g = (i < L) ? gene(a * L + i) : -1;
             const bool v = g != -1;
             const uint32_t bal = __ballot_sync(FULL, v);
             if (v) {
                 const int pos = run + __popc(bal & ((1u << lane) - 1u));
                 GCP_DASSERT(pos >= 0 && pos < AL);
-                s_seq[pos] = g;
-                s_own[pos] = (uint8_t)(a | ((a >= 1 && pos == s_base[a]) ? 0x80 : 0));
+                s_seq[pos] = (G)g;
             }
             run += __popc(bal);
         }
     }
     __syncthreads();                       // the chromosome is dead from here: group records take its place
     for (int i = tid; i < (AL >> 1); i += KF_THREADS) { g_head[i] = KF_NIL; g_own[i] = 0u; }
-    // pass 1: hash every key, count the members, open a group at the second arrival
-    for (int i = tid; i < n; i += KF_THREADS) {
+    auto lc_key = [&](int i, HK& key, uint32_t& h) {
         const uint32_t f = (uint32_t)s_seq[i], g = (uint32_t)s_seq[(i + 1 == n) ? 0 : i + 1];
-        HK key;
-        uint32_t h;
         if (KEY32) {
             key = (HK)((((f & 0xFFFFu) << 16) | (g & 0xFFFFu)) + 1u);      // ids < N <= 65,535: never 0
             h = __umulhi((uint32_t)key * 0x9E3779B1u, (uint32_t)T3);
@@ -848,6 +893,12 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
             key = (HK)(((unsigned long long)(f & 0xFFFFFFu) << 24 | (g & 0xFFFFFFu)) + 1ull);
             h = __umulhi((uint32_t)(((unsigned long long)key * 0x9E3779B97F4A7C15ull) >> 32), (uint32_t)T3);
         }
+    };
+    // pass 1: hash every key, count the members, open a group at the second arrival
+    for (int i = tid; i < n; i += KF_THREADS) {
+        HK key;
+        uint32_t h;
+        lc_key(i, key, h);
         for (;;) {
             const HK cur = ((volatile HK*)s_hkey)[h];
             if (cur == key) break;
@@ -872,11 +923,12 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
         const uint32_t c = s_hcnt[h];
         if ((c & 0x7FFFu) < 2u) continue;
         const uint32_t gid = (c >> 17) - 1u;
-        const uint8_t o = s_own[i];
+        int a = 0;                                                           // row that holds position i
+        while (a + 1 < A && i >= s_base[a + 1]) ++a;
         GCP_DASSERT(gid < (uint32_t)(AL >> 1));
         s_next[i] = (uint16_t)atomicExch(&g_head[gid], (h << 16) | (uint32_t)i);       // NIL -> 0xFFFF
-        atomicOr(&g_own[gid], 1u << (o & 31));
-        if (o & 0x80) atomicOr(&s_hcnt[h], 1u << 15);                       // group touches a split (F10)
+        atomicOr(&g_own[gid], 1u << a);
+        if (a >= 1 && i == s_base[a]) atomicOr(&s_hcnt[h], 1u << 15);       // first gene of a row: group touches a split (F10)
     }
     __syncthreads();
     // pass 3: successor gap test (ascending consecutive positions)
@@ -1049,12 +1101,16 @@ static int fused_threads(gcp_ctx* ctx, FusedShape& sh, size_t* smem)
     return 0;
 }
 
+static bool fused_compact(gcp_ctx* ctx) { return ctx->t.N <= 65534u; }
+
 static size_t fused_shape(gcp_ctx* ctx, FusedShape& sh, int KF_THREADS)
 {
+    const bool compact = fused_compact(ctx);      // u16 genes in shared memory, 32-bit loop-closure keys
     sh.A = ctx->p.num_agents; sh.L = ctx->p.max_dna_len; sh.AL = sh.A * sh.L;
     sh.inv_L = (uint32_t)((0x100000000ull + (uint64_t)sh.L - 1) / (uint64_t)sh.L);
-    // expected ~1.4 masked sub-tiles x ~1.6 quarters per executed step
-    int maxp = ctx->cov_maxpairs > 0 ? ctx->cov_maxpairs : (9 * sh.AL) / 4;
+    // expected ~1.4 masked sub-tiles x ~1.6 quarters per executed step (C3: 1,940 +- 80 items for 6 x 150
+    // steps before the revisited edges are dropped); an organism with more is redone in 2, 4, ... partitions
+    int maxp = ctx->cov_maxpairs > 0 ? ctx->cov_maxpairs : (compact ? (49 * sh.AL) / 24 : (9 * sh.AL) / 4);
     if (maxp < 256) maxp = 256;
     if (maxp > KF_PPT * KF_THREADS) maxp = KF_PPT * KF_THREADS;
     maxp = (maxp + 7) & ~7;
@@ -1067,19 +1123,26 @@ static size_t fused_shape(gcp_ctx* ctx, FusedShape& sh, int KF_THREADS)
     sh.DS = ctx->cov_dedup ? (uint32_t)T * 4 : 0u;                   // step-dedup hash set in front of s_cst
     sh.R0 = 1;
     while ((size_t)sh.R0 * maxp < (size_t)sh.AL * 2 && sh.R0 < 4096) sh.R0 <<= 1;
-    sh.off_cst = (uint32_t)T * 20;                                    // over s_pay / s_sr
+    sh.off_cst = (uint32_t)T * 20;                                    // over s_sr / s_pay
     const uint32_t cov_b = (uint32_t)T * 20 + (uint32_t)maxp * 8 + 32;  // + pad for B2's read-ahead
     const uint32_t a_b = sh.off_cst + (uint32_t)sh.AL * 16 + GCP_MAX_AGENTS * 16;    // + one pad entry per row
-    const uint32_t lc_b = al16((uint32_t)sh.T3 * 12 + (uint32_t)sh.AL) + (uint32_t)sh.AL * 4;
-    const uint32_t lc_b32 = al16((uint32_t)sh.T3 * 8 + (uint32_t)sh.AL) + (uint32_t)sh.AL * 4;
-    sh.c_overlap = (sh.R0 == 1 && lc_b32 <= (uint32_t)T * 20 + (uint32_t)maxp * 4) ? 1 : 0;
+    const uint32_t lc_b = al16((uint32_t)sh.T3 * (compact ? 8 : 12)) + (uint32_t)sh.AL * 4;    // keys + counters, genes (+ owner masks)
+    sh.c_overlap = (compact && sh.R0 == 1 && lc_b <= (uint32_t)T * 20 + (uint32_t)maxp * 4) ? 1 : 0;
     uint32_t x_b = cov_b > lc_b ? cov_b : lc_b;
     if (a_b > x_b) x_b = a_b;
-    sh.off_info = al16((uint32_t)sh.AL * 4);
+    sh.off_info = al16((uint32_t)sh.AL * (compact ? 2 : 4));
     sh.off_x = sh.off_info + al16((uint32_t)sh.AL * 4);
     sh.off_lc = sh.off_x + al16(x_b);
     sh.off_cost = sh.off_lc + al16((uint32_t)sh.A * sh.A * 4);
     return sh.off_cost + (size_t)sh.A * 16;
+}
+
+template <class SS>
+static bool shape_is(const FusedShape& sh)
+{
+    return SS::R0 == 1 && sh.R0 == 1 && sh.T == SS::T && sh.MAXP == SS::MAXP && sh.T3 == SS::T3 &&
+           sh.off_info == SS::off_info && sh.off_x == SS::off_x && sh.off_cst == SS::off_cst &&
+           sh.off_lc == SS::off_lc && sh.DS == SS::DS && (sh.c_overlap != 0) == SS::c_overlap;
 }
 
 int launch_eval_fused(gcp_ctx* ctx, const void* dna, int gene16, uint32_t P, const gcp_eval_out* out,
@@ -1105,19 +1168,16 @@ int launch_eval_fused(gcp_ctx* ctx, const void* dna, int gene16, uint32_t P, con
                                                          out->neg_cov, out->dist, out->turn,           \
                                                          out->lc_mat, out->flags);                     \
     } while (0)
-    // node ids below 65,536: the loop-closure hash takes 32-bit keys (half the table, 32-bit CAS)
-    const bool key32 = ctx->t.N <= 65535u;
+    // waypoint ids fit 16 bits: compact shared-memory layout (StaticShape), six CTAs per SM
+    const bool key32 = fused_compact(ctx);
 #define GCP_LAUNCH_FUSED(TH, GRAY, SAL)                                                                \
     do { if (key32) GCP_LAUNCH_FUSED_K(TH, GRAY, SAL, true); else GCP_LAUNCH_FUSED_K(TH, GRAY, SAL, false); } while (0)
     const bool gray = ctx->n_gray > 0;
     // the genome shapes of the reference's driver (pather_driver.py:122-158: max_dna_len 250 / 200 /
     // 150 / 125 / 125 / 200 for 1..6 agents) get the compile-time layout
 #define GCP_TRY_STATIC(SAL)                                                                            \
-    if (!done && threads == 256 && sh.AL == SAL && StaticShape<SAL>::R0 == 1 && sh.R0 == 1 &&         \
-        sh.T == StaticShape<SAL>::T && sh.MAXP == StaticShape<SAL>::MAXP &&                           \
-        sh.T3 == StaticShape<SAL>::T3 && sh.off_info == StaticShape<SAL>::off_info &&                 \
-        sh.off_x == StaticShape<SAL>::off_x && sh.off_cst == StaticShape<SAL>::off_cst &&             \
-        sh.off_lc == StaticShape<SAL>::off_lc && sh.DS == StaticShape<SAL>::DS) {                      \
+    if (!done && threads == 256 && sh.AL == SAL &&                                                     \
+        (key32 ? shape_is<StaticShape<SAL, true>>(sh) : shape_is<StaticShape<SAL, false>>(sh))) {      \
         if (gray) GCP_LAUNCH_FUSED(256, true, SAL); else GCP_LAUNCH_FUSED(256, false, SAL);           \
         done = true;                                                                                   \
     }

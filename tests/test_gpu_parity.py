@@ -495,6 +495,35 @@ def test_int16_genes_equal_int32(synth_setup):
     assert np.array_equal(obj_h.numpy(), want.obj.cpu().numpy())
 
 
+def test_out_of_range_genes_raise_the_error_flag(synth_setup):
+    """A gene outside [-1, N) is reported in flags[:, 3] bit 0 by every evaluation path (fused int32 /
+    int16 chromosomes, staged kernels) and raise_on_error() turns it into an exception; clean
+    organisms of the same launch are untouched."""
+    import torch
+    from genetic_coverage_planning_b200 import synth
+    from genetic_coverage_planning_b200.engine import GcpError
+    sw, pw, ow, op, eng, starts = synth_setup
+    dna = synth.random_walk_population(sw.xy, sw.row_ptr, sw.col, starts, 6, 150, 200, seed=31).astype(np.int32)
+    clean = eng.evaluate(dna, detail=False)
+    bad = dna.copy()
+    bad[1, 2, 40] = sw.N + 5
+    bad[3, 0, 7] = -7
+    bad[4, 5, 199] = 32000                     # last gene of the chromosome (N < 32,000 here)
+    assert sw.N < 32000
+    want_err = np.array([0, 1, 0, 1, 1, 0])
+    runs = {"fused32": eng.evaluate(bad, detail=False),
+            "fused16": eng.evaluate16(torch.from_numpy(bad.astype(np.int16)).to(eng.device)),
+            "staged": eng.evaluate(bad)}
+    for name, r in runs.items():
+        f = r.flags.cpu().numpy()
+        assert np.array_equal(f[:, 3] & 1, want_err), name
+        ok = want_err == 0
+        assert np.array_equal(r.obj.cpu().numpy()[ok], clean.obj.cpu().numpy()[ok]), name
+        with pytest.raises(GcpError):
+            eng.raise_on_error(r)
+    eng.raise_on_error(clean)
+
+
 def test_binary_world_blend(synth_setup):
     """blend < 1 needs the internal-coverage counter: general kernel, still bit-exact."""
     sw, pw, ow, op, eng, starts = synth_setup
