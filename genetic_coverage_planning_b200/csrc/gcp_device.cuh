@@ -32,6 +32,65 @@ __device__ __forceinline__ double np_sum_order(const double* a, int n)
 }
 
 
+// -coverage (mappy.py:358-364, from the integer pixel counts c[0..3]) and travel cost
+// (geneticalgorithm.py:196: np.sum over the per-agent sums, times flight_time_scale).
+__device__ __forceinline__ void objective_values(int A, const gcp_params& prm, const gcp_map_consts& mc,
+                                                 const uint32_t* c, const double* dist, const double* turn,
+                                                 double& neg_cov, double& travel)
+{
+    const long long w_mask = 255ll * c[0] + c[2];
+    const long long w_all = 255ll * c[1] + c[3];
+    const double wall = __ddiv_rn(__ddiv_rn((double)(mc.gsum_mask + w_mask), 255.0),
+                                  (double)mc.mask_size);
+    const double sum_draw = __dadd_rn(mc.num_occluded, __ddiv_rn((double)w_all, 255.0));
+    const double internal = __ddiv_rn(__dsub_rn(sum_draw, mc.num_occluded),
+                                      __dsub_rn((double)mc.map_size, mc.num_occluded));
+    const double coverage = __dadd_rn(__dmul_rn(prm.coverage_blend, wall),
+                                      __dmul_rn(prm.one_minus_blend, internal));
+    neg_cov = -coverage;
+    const double td = np_sum_order(dist, A);
+    const double tc = np_sum_order(turn, A);
+    travel = __dmul_rn(__dadd_rn(td, tc), prm.flight_time_scale);
+}
+
+// The constraint half of geneticalgorithm.py:183-201 by ONE WARP (all 32 lanes must call): lane a owns
+// row a of the loop-closure matrix.  Returns feasibility, ncomp = connected components of the graph
+// lc[a][b] + lc[b][a] >= 1 (== A - #(eig(L) > 1e-6)).  Every lane gets the same result.
+__device__ __forceinline__ bool constraints_warp(const int* s_lc, int A, const gcp_params& prm, int& ncomp)
+{
+    const int lane = threadIdx.x & 31;
+    uint32_t m = 0;
+    int rowsum = 0;
+    bool sb = false;
+    if (lane < A) {
+        for (int b = 0; b < A; ++b) {
+            const int v = s_lc[lane * A + b];
+            if (b == lane) { sb = v < prm.min_solo_lcs; continue; }
+            rowsum += v;                                             // entries <= 32,767 groups: no overflow
+            if (v + s_lc[b * A + lane] >= 1) m |= 1u << b;
+        }
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rowsum += __shfl_xor_sync(FULL, rowsum, o);
+    const bool solo_bad = __any_sync(FULL, sb);
+    // breadth-first search over the adjacency masks, identical (hence convergent) in every lane;
+    // the mask of agent x is fetched from lane x
+    ncomp = 0;
+    uint32_t seen = 0;
+    for (int a = 0; a < A; ++a) {
+        if ((seen >> a) & 1u) continue;
+        ++ncomp;
+        uint32_t fr = 1u << a;
+        while (fr) {
+            seen |= fr;
+            uint32_t nf = 0;
+            for (uint32_t f = fr; f; f &= f - 1) nf |= __shfl_sync(FULL, m, __ffs(f) - 1);
+            fr = nf & ~seen;
+        }
+    }
+    return !(solo_bad || rowsum < prm.min_comb_lcs || ncomp > 1);
+}
+
 // Constraints + objectives of one organism (geneticalgorithm.py:177-201) from its loop-closure
 // matrix (shared memory, A x A), integer coverage counters cov[0..3] and per-agent cost sums.
 __device__ __forceinline__ void finish_objectives(const int* s_lc, int A, const gcp_params& prm,
@@ -69,20 +128,8 @@ __device__ __forceinline__ void finish_objectives(const int* s_lc, int A, const 
     }
     const bool feasible = !(solo_bad || combo < (long long)prm.min_comb_lcs || ncomp > 1);
 
-    // coverage (mappy.py:358-364) from the integer pixel counts
-    const long long w_mask = 255ll * c[0] + c[2];
-    const long long w_all = 255ll * c[1] + c[3];
-    const double wall = __ddiv_rn(__ddiv_rn((double)(mc.gsum_mask + w_mask), 255.0),
-                                  (double)mc.mask_size);
-    const double sum_draw = __dadd_rn(mc.num_occluded, __ddiv_rn((double)w_all, 255.0));
-    const double internal = __ddiv_rn(__dsub_rn(sum_draw, mc.num_occluded),
-                                      __dsub_rn((double)mc.map_size, mc.num_occluded));
-    const double coverage = __dadd_rn(__dmul_rn(prm.coverage_blend, wall),
-                                      __dmul_rn(prm.one_minus_blend, internal));
-    const double neg_cov = -coverage;
-    const double td = np_sum_order(dist, A);
-    const double tc = np_sum_order(turn, A);
-    const double travel = __dmul_rn(__dadd_rn(td, tc), prm.flight_time_scale);
+    double neg_cov, travel;
+    objective_values(A, prm, mc, c, dist, turn, neg_cov, travel);
     if (neg_cov_out) neg_cov_out[org] = neg_cov;
     if (obj) {
         obj[(size_t)org * 2 + 0] = feasible ? neg_cov : 0.0;

@@ -578,6 +578,7 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     __shared__ int s_bad;
     __shared__ uint32_t s_total, s_totalw, s_ngroups;
     __shared__ uint32_t s_cov[4];
+    __shared__ double s_objv[2];
 
     const uint32_t org = blockIdx.x;
     if (org >= P) return;
@@ -590,43 +591,69 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     };
 
     // ------------------------------------------------------------------ load the chromosome
-    if (tid == 0) { s_bad = 0; s_total = 0; s_totalw = 0; }
-    for (int i = tid; i < A * A; i += KF_THREADS) s_lc[i] = 0;
+    // The first vectors are requested before the table clears so that their HBM latency runs
+    // while the CTA zeroes its tables; they are consumed afterwards.
+    const uint32_t DS = ST ? SS::DS : sh.DS;
+    uint32_t* s_set = reinterpret_cast<uint32_t*>(s_x);       // step-dedup table (phase A1), in front of s_cst
+    auto clear_tables = [&]() {
+        if (tid == 0) { s_bad = 0; s_total = 0; s_totalw = 0; }
+        for (int i = tid; i < A * A; i += KF_THREADS) s_lc[i] = 0;
+        if ((DS & 3u) == 0) {
+            for (int i = tid; i < (int)(DS >> 2); i += KF_THREADS) reinterpret_cast<uint4*>(s_set)[i] = make_uint4(0, 0, 0, 0);
+        } else {
+            for (int i = tid; i < (int)DS; i += KF_THREADS) s_set[i] = 0u;
+        }
+    };
     int bad_gene = 0;                      // a gene outside [-1, N): error bit 0 of flags[:, 3]
     if (COMPACT) {
         // u16 in shared memory: -1 -> 0xFFFF, anything else outside [0, N) -> 0xFFFE (>= N: never a
         // waypoint, never a step; the organism's error flag is raised)
         auto pack = [&](int g) -> uint32_t {
-            if (g == -1) return 0xFFFFu;
-            if ((uint32_t)g >= t.N) { bad_gene = 2; return 0xFFFEu; }
-            return (uint32_t)g;
+            const uint32_t u = (uint32_t)g;
+            const bool in = u < t.N, pad = g == -1;
+            bad_gene |= (in || pad) ? 0 : 2;
+            return in ? u : (pad ? 0xFFFFu : 0xFFFEu);
         };
         uint16_t* s16 = reinterpret_cast<uint16_t*>(smem);
         if (sh.gene16) {                   // int16 chromosome in global memory
             const int16_t* d = reinterpret_cast<const int16_t*>(dna_v) + (size_t)org * AL;
             if ((AL & 7) == 0) {
                 const int4* d8 = reinterpret_cast<const int4*>(d);
-                for (int i = tid; i < (AL >> 3); i += KF_THREADS) {
-                    const int4 v = __ldg(d8 + i);
+                auto put = [&](int i, const int4& v) {
                     uint4 o;
                     o.x = pack((int)(short)(v.x & 0xFFFF)) | (pack(v.x >> 16) << 16);
                     o.y = pack((int)(short)(v.y & 0xFFFF)) | (pack(v.y >> 16) << 16);
                     o.z = pack((int)(short)(v.z & 0xFFFF)) | (pack(v.z >> 16) << 16);
                     o.w = pack((int)(short)(v.w & 0xFFFF)) | (pack(v.w >> 16) << 16);
                     reinterpret_cast<uint4*>(s16)[i] = o;
-                }
+                };
+                const int nv = AL >> 3;
+                int4 v0 = make_int4(0, 0, 0, 0);
+                if (tid < nv) v0 = __ldg(d8 + tid);
+                clear_tables();
+                if (tid < nv) put(tid, v0);
+                for (int i = tid + KF_THREADS; i < nv; i += KF_THREADS) put(i, __ldg(d8 + i));
             } else {
+                clear_tables();
                 for (int i = tid; i < AL; i += KF_THREADS) s16[i] = (uint16_t)pack((int)__ldg(d + i));
             }
         } else {
             const int32_t* d = reinterpret_cast<const int32_t*>(dna_v) + (size_t)org * AL;
             if ((AL & 3) == 0) {
                 const int4* d4 = reinterpret_cast<const int4*>(d);
-                for (int i = tid; i < (AL >> 2); i += KF_THREADS) {
-                    const int4 v = __ldg(d4 + i);
+                auto put = [&](int i, const int4& v) {
                     reinterpret_cast<uint2*>(s16)[i] = make_uint2(pack(v.x) | (pack(v.y) << 16), pack(v.z) | (pack(v.w) << 16));
-                }
+                };
+                const int nv = AL >> 2;
+                int4 v0 = make_int4(0, 0, 0, 0), v1 = v0;
+                if (tid < nv) v0 = __ldg(d4 + tid);
+                if (tid + KF_THREADS < nv) v1 = __ldg(d4 + tid + KF_THREADS);
+                clear_tables();
+                if (tid < nv) put(tid, v0);
+                if (tid + KF_THREADS < nv) put(tid + KF_THREADS, v1);
+                for (int i = tid + 2 * KF_THREADS; i < nv; i += KF_THREADS) put(i, __ldg(d4 + i));
             } else {
+                clear_tables();
                 for (int i = tid; i < AL; i += KF_THREADS) s16[i] = (uint16_t)pack(__ldg(d + i));
             }
         }
@@ -635,26 +662,33 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
         auto check = [&](int g) { if (g < -1 || (g >= 0 && (uint32_t)g >= t.N)) bad_gene = 2; };
         if (sh.gene16) {
             const int16_t* d = reinterpret_cast<const int16_t*>(dna_v) + (size_t)org * AL;
+            clear_tables();
             for (int i = tid; i < AL; i += KF_THREADS) { const int g = (int)__ldg(d + i); check(g); s32[i] = g; }
         } else {
             const int32_t* d = reinterpret_cast<const int32_t*>(dna_v) + (size_t)org * AL;
             if ((AL & 3) == 0) {
                 const int4* d4 = reinterpret_cast<const int4*>(d);
                 int4* s4 = reinterpret_cast<int4*>(s32);
-                for (int i = tid; i < (AL >> 2); i += KF_THREADS) {
+                const int nv = AL >> 2;
+                int4 v0 = make_int4(-1, -1, -1, -1), v1 = v0;
+                if (tid < nv) v0 = __ldg(d4 + tid);
+                if (tid + KF_THREADS < nv) v1 = __ldg(d4 + tid + KF_THREADS);
+                clear_tables();
+                check(v0.x); check(v0.y); check(v0.z); check(v0.w);
+                check(v1.x); check(v1.y); check(v1.z); check(v1.w);
+                if (tid < nv) s4[tid] = v0;
+                if (tid + KF_THREADS < nv) s4[tid + KF_THREADS] = v1;
+                for (int i = tid + 2 * KF_THREADS; i < nv; i += KF_THREADS) {
                     const int4 v = __ldg(d4 + i);
                     check(v.x); check(v.y); check(v.z); check(v.w);
                     s4[i] = v;
                 }
             } else {
+                clear_tables();
                 for (int i = tid; i < AL; i += KF_THREADS) { const int g = __ldg(d + i); check(g); s32[i] = g; }
             }
         }
     }
-    // step-dedup hash set (see coverage_quarters B0): lives in front of s_cst during phase A1
-    const uint32_t DS = ST ? SS::DS : sh.DS;
-    uint32_t* s_set = reinterpret_cast<uint32_t*>(s_x);
-    for (int i = tid; i < (int)DS; i += KF_THREADS) s_set[i] = 0u;
     __syncthreads();
     if (bad_gene) atomicOr(&s_bad, bad_gene);
     // first -1 per row (step rule mappy.py:343-345) and number of valid genes (:390)
@@ -931,6 +965,14 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
         if (a >= 1 && i == s_base[a]) atomicOr(&s_hcnt[h], 1u << 15);       // first gene of a row: group touches a split (F10)
     }
     __syncthreads();
+    // phase D, first half: -coverage and travel cost need nothing from phase C - one thread of the last
+    // warp (no groups to update in pass 4) computes them here instead of at the tail of the CTA
+    if (tid == KF_THREADS - 32) {
+        s_cov[0] = failed ? 0u : s_total; s_cov[1] = 0; s_cov[2] = failed ? 0u : s_totalw; s_cov[3] = 0;
+        double nc, tr;
+        objective_values(A, prm, mc, s_cov, s_cost, s_cost + A, nc, tr);
+        s_objv[0] = nc; s_objv[1] = tr;
+    }
     // pass 3: successor gap test (ascending consecutive positions)
     const int thresh = prm.solo_sep_thresh;
     for (int i = tid; i < n; i += KF_THREADS) {
@@ -964,13 +1006,23 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     if (lc_out)
         for (int i = tid; i < A * A; i += KF_THREADS) lc_out[(size_t)org * A * A + i] = s_lc[i];
 
-    // ------------------------------------------------------------------ phase D: objectives
-    if (tid == 0) {
-        s_cov[0] = failed ? 0u : s_total; s_cov[1] = 0; s_cov[2] = failed ? 0u : s_totalw; s_cov[3] = 0;
-        finish_objectives(s_lc, A, prm, mc, s_cov, s_cost, s_cost + A, org, obj, neg_cov_out, flags);
-        if (flags) {
-            flags[(size_t)org * 4 + 1] = (s_bad & 1) ? 0 : 1;                       // traversable
-            flags[(size_t)org * 4 + 3] = (uint8_t)(((s_bad & 2) ? 1 : 0) | (failed ? 2 : 0));
+    // ------------------------------------------------------------------ phase D: constraints (warp 0)
+    if (warp == 0) {
+        int ncomp;
+        const bool feasible = constraints_warp(s_lc, A, prm, ncomp);
+        if (lane == 0) {
+            const double neg_cov = s_objv[0];
+            if (neg_cov_out) neg_cov_out[org] = neg_cov;
+            if (obj) {
+                obj[(size_t)org * 2 + 0] = feasible ? neg_cov : 0.0;
+                obj[(size_t)org * 2 + 1] = s_objv[1];
+            }
+            if (flags) {
+                flags[(size_t)org * 4 + 0] = feasible ? 1 : 0;
+                flags[(size_t)org * 4 + 1] = (s_bad & 1) ? 0 : 1;                       // traversable
+                flags[(size_t)org * 4 + 2] = (uint8_t)ncomp;
+                flags[(size_t)org * 4 + 3] = (uint8_t)(((s_bad & 2) ? 1 : 0) | (failed ? 2 : 0));
+            }
         }
     }
 }
