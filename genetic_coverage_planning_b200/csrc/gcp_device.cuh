@@ -93,6 +93,9 @@ __device__ __forceinline__ bool constraints_warp(const int* s_lc, int A, const g
 
 // Constraints + objectives of one organism (geneticalgorithm.py:177-201) from its loop-closure
 // matrix (shared memory, A x A), integer coverage counters cov[0..3] and per-agent cost sums.
+// Called by ALL 32 lanes of one warp: the A x A scan runs one row per lane (a single thread would
+// keep the whole CTA - and, at one CTA per SM, the whole SM - waiting for A*A dependent iterations),
+// lane 1 works out the objective values meanwhile, lane 0 writes the results.
 __device__ __forceinline__ void finish_objectives(const int* s_lc, int A, const gcp_params& prm,
                                                   const gcp_map_consts& mc, const uint32_t* c,
                                                   const double* dist, const double* turn,
@@ -100,36 +103,14 @@ __device__ __forceinline__ void finish_objectives(const int* s_lc, int A, const 
                                                   double* __restrict__ neg_cov_out,
                                                   uint8_t* __restrict__ flags)
 {
-    bool solo_bad = false;
-    long long combo = 0;
-    uint32_t adj[GCP_MAX_AGENTS];
-    for (int a = 0; a < A; ++a) {
-        if (s_lc[a * A + a] < prm.min_solo_lcs) solo_bad = true;
-        uint32_t m = 0;
-        for (int b = 0; b < A; ++b) {
-            if (b == a) continue;
-            combo += s_lc[a * A + b];
-            if (s_lc[a * A + b] + s_lc[b * A + a] >= 1) m |= 1u << b;
-        }
-        adj[a] = m;
-    }
-    int ncomp = 0;
-    uint32_t seen = 0;
-    for (int a = 0; a < A; ++a) {
-        if ((seen >> a) & 1u) continue;
-        ++ncomp;
-        uint32_t fr = 1u << a;
-        while (fr) {
-            seen |= fr;
-            uint32_t nf = 0;
-            for (uint32_t m = fr; m; m &= m - 1) nf |= adj[__ffs(m) - 1];
-            fr = nf & ~seen;
-        }
-    }
-    const bool feasible = !(solo_bad || combo < (long long)prm.min_comb_lcs || ncomp > 1);
-
-    double neg_cov, travel;
-    objective_values(A, prm, mc, c, dist, turn, neg_cov, travel);
+    const int lane = threadIdx.x & 31;
+    double neg_cov = 0.0, travel = 0.0;
+    if (lane == 1) objective_values(A, prm, mc, c, dist, turn, neg_cov, travel);
+    int ncomp;
+    const bool feasible = constraints_warp(s_lc, A, prm, ncomp);
+    neg_cov = __shfl_sync(FULL, neg_cov, 1);
+    travel = __shfl_sync(FULL, travel, 1);
+    if (lane != 0) return;
     if (neg_cov_out) neg_cov_out[org] = neg_cov;
     if (obj) {
         obj[(size_t)org * 2 + 0] = feasible ? neg_cov : 0.0;

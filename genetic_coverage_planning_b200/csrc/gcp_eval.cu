@@ -852,8 +852,8 @@ k_loop_closures(const int32_t* __restrict__ dna, uint32_t P, int A, int L, int T
     if (lc_out)
         for (int i = tid; i < A * A; i += K3_THREADS) lc_out[(size_t)org * A * A + i] = s_lc[i];
 
-    // ---- constraints + objectives (geneticalgorithm.py:177-201), one thread ----
-    if (tid == 0)
+    // ---- constraints + objectives (geneticalgorithm.py:177-201), one warp cooperatively ----
+    if (tid < 32)
         finish_objectives(s_lc, A, prm, mc, cov + (size_t)org * 8, dist + (size_t)org * A,
                           turn + (size_t)org * A, org, obj, neg_cov_out, flags);
 }

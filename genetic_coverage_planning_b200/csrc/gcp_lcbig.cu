@@ -130,8 +130,7 @@ k_lcb_finish(uint32_t P, int A, gcp_params prm, gcp_map_consts mc, const int32_t
     if (org >= P) return;
     for (int i = threadIdx.x; i < A * A; i += 32) s_lc[i] = lc[(size_t)org * A * A + i];
     __syncwarp();
-    if (threadIdx.x == 0)
-        finish_objectives(s_lc, A, prm, mc, cov + (size_t)org * 8, dist + (size_t)org * A,
+    finish_objectives(s_lc, A, prm, mc, cov + (size_t)org * 8, dist + (size_t)org * A,
                           turn + (size_t)org * A, org, obj, neg_cov_out, flags);
 }
 
@@ -353,10 +352,10 @@ k_loop_closures_part(const int32_t* __restrict__ dna, uint32_t P, int A, int L, 
     }
     if (lc_out)
         for (int i = tid; i < A * A; i += LP_THREADS) lc_out[(size_t)org * A * A + i] = s_lc[i];
-    if (tid == 0) {
+    if (tid < 32) {                       // one warp, cooperatively
         finish_objectives(s_lc, A, prm, mc, cov + (size_t)org * 8, dist + (size_t)org * A,
                           turn + (size_t)org * A, org, obj, neg_cov_out, flags);
-        if (s_fail && flags) flags[(size_t)org * 4 + 3] |= 4;
+        if (tid == 0 && s_fail && flags) flags[(size_t)org * 4 + 3] |= 4;
     }
 }
 
