@@ -32,6 +32,19 @@ __device__ __forceinline__ double np_sum_order(const double* a, int n)
 }
 
 
+// Row (agent) that holds position i of the compacted gene sequence: the smallest a with
+// s_base[a + 1] > i (s_base = exclusive prefix sums of the row lengths, s_base[A] = n > i; rows of
+// length 0 share their base with the next row and are skipped).  Bisection: A <= 32 -> 5 probes.
+__device__ __forceinline__ int owner_row(const int* s_base, int A, int i)
+{
+    int lo = 0, hi = A - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s_base[mid + 1] > i) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
 // -coverage (mappy.py:358-364, from the integer pixel counts c[0..3]) and travel cost
 // (geneticalgorithm.py:196: np.sum over the per-agent sums, times flight_time_scale).
 __device__ __forceinline__ void objective_values(int A, const gcp_params& prm, const gcp_map_consts& mc,

@@ -957,8 +957,7 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
         const uint32_t c = s_hcnt[h];
         if ((c & 0x7FFFu) < 2u) continue;
         const uint32_t gid = (c >> 17) - 1u;
-        int a = 0;                                                           // row that holds position i
-        while (a + 1 < A && i >= s_base[a + 1]) ++a;
+        const int a = owner_row(s_base, A, i);
         GCP_DASSERT(gid < (uint32_t)(AL >> 1));
         s_next[i] = (uint16_t)atomicExch(&g_head[gid], (h << 16) | (uint32_t)i);       // NIL -> 0xFFFF
         atomicOr(&g_own[gid], 1u << a);

@@ -302,9 +302,7 @@ k_loop_closures_part(const int32_t* __restrict__ dna, uint32_t P, int A, int L, 
             uint32_t h = __umulhi(lp_hash(key), (uint32_t)T3);
             while (s_hkey[h] != key) h = (h + 1 == (uint32_t)T3) ? 0u : h + 1;
             if ((s_hcnt[h] & 0xFFFFu) < 2u) continue;
-            int a = 0;
-            while (a + 1 < A && i >= s_base[a + 1]) ++a;          // owner row of position i
-            while (s_len[a] == 0) ++a;                            // (rows of length 0 share a base)
+            const int a = owner_row(s_base, A, i);
             s_next[i] = (uint16_t)atomicExch(&s_head[h], (uint32_t)i);      // NIL -> 0xFFFF
             atomicOr(&s_ownm[h], 1u << a);
             if (a >= 1 && i == s_base[a]) atomicOr(&s_hcnt[h], 1u << 16);   // touches a path split (F10)
