@@ -508,6 +508,8 @@ def main():
             "bound": "issue/lsu" if fast else "hbm",
             "bound_source": "ncu --set full (profiles/): issue slots and the LSU data pipe are the busiest "
                             "units, DRAM ~1 % of peak; the byte model below is SURVEY 8d's HBM model",
+            "ncu_unit_utilisation": {k: tr[k] for k in ("issue_active_pct", "l1tex_throughput_pct", "warps_active_pct",
+                                                        "warp_instructions_per_organism") if k in tr} or None,
             "model_bound": "hbm",
             "kernel": ("k_eval_fused (path-cost gather + footprint bitset union/popcount + loop closures + "
                        "objectives, one CTA per organism; the only kernel of the timed step)") if fast else
