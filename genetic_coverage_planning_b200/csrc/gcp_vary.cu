@@ -741,22 +741,16 @@ __device__ __forceinline__ bool t_is_edge_csr(const GcpTables& t, int a, int b)
 // of its rows' instruction streams.  With few rows to process the machine has warps to spare, and one
 // row per warp finishes 32 x sooner than 32 rows in one warp; the host picks `spread` so that the rows
 // still fill the SMs.
+// One row: `r` points at the row (shared-memory copy or global memory), gid = organism * A + agent.
+// Returns whether the row was changed.
 template <typename G>
-__global__ void __launch_bounds__(MW_THREADS)
-k_muterpolate_rows(G* __restrict__ dna, GcpTables t, VaryParams vp, uint64_t seed, uint32_t gen,
-                   uint32_t salt, const uint32_t* __restrict__ counter, const uint32_t* __restrict__ list,
-                   uint32_t spread)
+__device__ __forceinline__ bool muterpolate_row(G* r, uint32_t gid, const GcpTables& t, const VaryParams& vp,
+                                                uint64_t seed, uint32_t gen, uint32_t salt)
 {
-    const uint32_t g = blockIdx.x * MW_THREADS + threadIdx.x;
-    if (g & (spread - 1u)) return;
-    const uint32_t j = g / spread;
-    if (j >= *counter) return;
     const int L = vp.L;
-    const uint32_t gid = list[j];
-    G* r = dna + (size_t)gid * L;
     const int len = row_len<G>(r, L);
     const int range = len - (vp.srch_dist + 3);
-    if (range <= 0) return;
+    if (range <= 0) return false;
     Philox rng(seed, gen, stream_id(STREAM_MUTERP, salt), gid + vp.org_off * vp.A);
     int pts[MAX_MUT_POINTS];
     const int np_ = min(vp.num_muterp, MAX_MUT_POINTS);
@@ -838,6 +832,52 @@ k_muterpolate_rows(G* __restrict__ dna, GcpTables t, VaryParams vp, uint64_t see
             if (g != (G)-1) r[w++] = g;
         }
         for (int x = w; x < L; ++x) r[x] = (G)-1;
+    }
+    return changed;
+}
+
+// STAGE: the rows of a warp are copied to shared memory with coalesced loads first, edited there by
+// their owner lanes, and the changed ones copied back.  The edit is a serial chain of single-element
+// reads and writes per row; in global memory every one of them is an L1 / L2 round trip (long
+// scoreboard: 52 % of the stall samples, profiles/ncu r02w), in shared memory 29 cycles.
+template <typename G, bool STAGE>
+__global__ void __launch_bounds__(MW_THREADS)
+k_muterpolate_rows(G* __restrict__ dna, GcpTables t, VaryParams vp, uint64_t seed, uint32_t gen,
+                   uint32_t salt, const uint32_t* __restrict__ counter, const uint32_t* __restrict__ list,
+                   uint32_t spread, uint32_t stride)
+{
+    extern __shared__ __align__(16) unsigned char mp_smem[];
+    const uint32_t g = blockIdx.x * MW_THREADS + threadIdx.x;
+    const uint32_t j = g / spread;
+    const bool mine = (g & (spread - 1u)) == 0 && j < *counter;
+    const int L = vp.L;
+    const uint32_t gid = mine ? list[j] : 0u;
+    if (!STAGE) {
+        if (mine) muterpolate_row<G>(dna + (size_t)gid * L, gid, t, vp, seed, gen, salt);
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    // slot of a lane's row: rows of the block back to back, `stride` bytes apart (odd number of words:
+    // lanes that touch the same index of their rows hit different banks)
+    G* slot = reinterpret_cast<G*>(mp_smem + (size_t)(threadIdx.x / spread) * stride);
+    const uint32_t have = __ballot_sync(0xffffffffu, mine);
+    for (uint32_t m = have; m; m &= m - 1) {                           // copy in, one row at a time, all lanes
+        const int src = __ffs(m) - 1;
+        const uint32_t sg = __shfl_sync(0xffffffffu, gid, src);
+        G* dst = reinterpret_cast<G*>(mp_smem + (size_t)((threadIdx.x - lane + src) / spread) * stride);
+        const G* from = dna + (size_t)sg * L;
+        for (int x = lane; x < L; x += 32) dst[x] = from[x];
+    }
+    __syncwarp();
+    bool changed = false;
+    if (mine) changed = muterpolate_row<G>(slot, gid, t, vp, seed, gen, salt);
+    __syncwarp();
+    for (uint32_t m = __ballot_sync(0xffffffffu, changed); m; m &= m - 1) {     // copy the changed rows back
+        const int src = __ffs(m) - 1;
+        const uint32_t sg = __shfl_sync(0xffffffffu, gid, src);
+        const G* from = reinterpret_cast<const G*>(mp_smem + (size_t)((threadIdx.x - lane + src) / spread) * stride);
+        G* dst = dna + (size_t)sg * L;
+        for (int x = lane; x < L; x += 32) dst[x] = from[x];
     }
 }
 
@@ -1040,7 +1080,15 @@ static int mutate_impl(gcp_ctx* c, G* dna, uint32_t P, uint32_t org_offset, uint
         uint32_t spread = 32;
         while (spread > 1 && rows_est * spread > (double)c->num_sms * 48.0 * 32.0) spread >>= 1;
         const uint32_t mgrid = (uint32_t)(((uint64_t)n_rows * spread + MW_THREADS - 1) / MW_THREADS);
-        k_muterpolate_rows<G><<<mgrid, MW_THREADS, 0, st>>>(dna, c->t, vp, seed, gen, salt, counter + 768, list, spread);
+        // rows staged in shared memory while they fit (stride: row bytes rounded up to an odd number of words)
+        const uint32_t stride = ((((uint32_t)vp.L * (uint32_t)sizeof(G) + 3u) / 4u) | 1u) * 4u;
+        const size_t mp_smem = (size_t)(MW_THREADS / spread) * stride;
+        if (mp_smem <= 96u * 1024u) {
+            GCP_CUDA(c, cudaFuncSetAttribute(k_muterpolate_rows<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mp_smem));
+            k_muterpolate_rows<G, true><<<mgrid, MW_THREADS, mp_smem, st>>>(dna, c->t, vp, seed, gen, salt, counter + 768, list, spread, stride);
+        } else {
+            k_muterpolate_rows<G, false><<<mgrid, MW_THREADS, 0, st>>>(dna, c->t, vp, seed, gen, salt, counter + 768, list, spread, stride);
+        }
         c->launches += 2;
     }
     k_post_mutate<G><<<(n_rows + VARY_WARPS - 1) / VARY_WARPS, VARY_WARPS * 32, smem, st>>>(dna, P, c->t, vp,
