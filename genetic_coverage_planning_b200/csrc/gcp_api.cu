@@ -671,6 +671,7 @@ int gcp_set_option(gcp_ctx* c, const char* name, int64_t value)
 {
     if (!c || !name) return -1;
     if (!strcmp(name, "rank_algo")) c->rank_algo = (int)value;
+    else if (!strcmp(name, "sort_onesweep")) c->sort_onesweep = (int)value;
     else if (!strcmp(name, "force_general")) c->force_general = (int)value;
     else if (!strcmp(name, "fused_eval")) c->fused_eval = (int)value;
     else if (!strcmp(name, "force_lc_big")) c->force_lc_big = (int)value;

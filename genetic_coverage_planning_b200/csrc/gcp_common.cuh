@@ -96,6 +96,7 @@ struct gcp_ctx {
     int cov_prefetch = -1;   // -1 auto (store > 96 MiB), 0 / 1: L2 prefetch of the footprint lines in phase B1
     uint64_t m_n_quarters = 0;
     int rank_algo = 0;       // 0 auto, 1 O(N^2) dominance tiles, 2 sort-based (gcp_rank.cu)
+    int sort_onesweep = 1;   // 1: radix sorts of <= 2^20 pairs run one launch per pass (decoupled look-back)
 };
 
 int gcp_fail(gcp_ctx* ctx, int code, const char* fmt, ...);

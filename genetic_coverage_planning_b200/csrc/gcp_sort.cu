@@ -225,10 +225,155 @@ k_rs_scatter(const unsigned long long* __restrict__ keys, const uint32_t* __rest
     }
 }
 
+// ---------------------------------------------------------------------------------
+// One launch per pass ("onesweep"): the digit histograms of ALL passes come from one upfront kernel
+// (the multiset of keys does not change between passes), and k_os_scatter finds the number of keys
+// with its digit in the tiles in front of it by DECOUPLED LOOK-BACK: every tile publishes
+// {count | flag} per digit - first its own count (AGG), then the inclusive prefix (PRE) - and walks
+// back over its predecessors until it meets a prefix.  Tiles are numbered by an atomic ticket, so a
+// tile only ever waits for tiles that started before it.  A sort of 131,072 pairs is 1 + 8 launches
+// instead of 32; the ranking of a population is bound by launch latency, not by bandwidth.
+// ---------------------------------------------------------------------------------
+constexpr uint32_t OS_AGG = 1u << 30, OS_PRE = 1u << 31, OS_VAL = (1u << 30) - 1u;
+constexpr uint32_t RS_ONESWEEP_MAX_KEYS = 1u << 20;        // status words: passes * tiles * 256 * 4 B (4 MiB here)
+constexpr int OS_MAX_PASSES = 8;
+
+// ghist [OS_MAX_PASSES][256] zeroed by the caller -> exclusive digit bases per pass; `done` zeroed ticket
+__global__ void __launch_bounds__(RS_THREADS)
+k_os_hist(const unsigned long long* __restrict__ keys, uint32_t n, int passes,
+          uint32_t* __restrict__ ghist, uint32_t* __restrict__ done, uint32_t nblk)
+{
+    __shared__ uint32_t s_h[OS_MAX_PASSES][RS_BINS];
+    __shared__ uint32_t s_last;
+    const int tid = threadIdx.x;
+    for (int p = 0; p < passes; ++p) s_h[p][tid] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * RS_TILE;
+    #pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const uint32_t i = base + r * RS_THREADS + tid;
+        if (i < n) {
+            const unsigned long long k = keys[i];
+            for (int p = 0; p < passes; ++p) atomicAdd(&s_h[p][(uint32_t)(k >> (8 * p)) & 255u], 1u);
+        }
+    }
+    __syncthreads();
+    for (int p = 0; p < passes; ++p) { const uint32_t c = s_h[p][tid]; if (c) atomicAdd(&ghist[p * RS_BINS + tid], c); }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(done, 1u) == nblk - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // last CTA: counts -> exclusive bases, one pass after the other (thread = digit)
+    const int lane = tid & 31, warp = tid >> 5;
+    __shared__ uint32_t s_w[RS_BINS / 32];
+    for (int p = 0; p < passes; ++p) {
+        const uint32_t v = __ldcg(ghist + p * RS_BINS + tid);
+        uint32_t inc = v;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += x; }
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        uint32_t off = 0;
+        for (int w = 0; w < warp; ++w) off += s_w[w];
+        ghist[p * RS_BINS + tid] = off + inc - v;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+k_os_scatter(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals,
+             uint32_t n, int shift, const uint32_t* __restrict__ gbase /*[256] of this pass*/,
+             uint32_t* status /*[nblk][256] of this pass, zeroed*/, uint32_t* ticket /*zeroed*/,
+             unsigned long long* __restrict__ keys_out, uint32_t* __restrict__ vals_out)
+{
+    __shared__ uint32_t s_cnt[RS_NW][RS_BINS];          // per-warp digit counts -> bases
+    __shared__ uint32_t s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < RS_NW * RS_BINS; i += RS_THREADS) (&s_cnt[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t wbase = tile * RS_TILE + warp * (RS_ITEMS * 32);
+    unsigned long long k[RS_ITEMS];
+    uint32_t v[RS_ITEMS];
+    const uint32_t lt = (1u << lane) - 1u;
+    #pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const uint32_t i = wbase + r * 32 + lane;
+        const bool ok = i < n;
+        k[r] = ok ? keys[i] : ~0ull;
+        v[r] = ok ? vals[i] : 0u;
+        const uint32_t d = (uint32_t)(k[r] >> shift) & 255u;
+        const uint32_t act = __ballot_sync(FULL, ok);
+        if (ok) {
+            const uint32_t peers = __match_any_sync(act, d);
+            if ((peers & lt) == 0) s_cnt[warp][d] += __popc(peers);   // leader, warp-private row
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // digit `tid`: tile total, look-back over the tiles in front, then the per-warp bases
+        uint32_t total = 0;
+        #pragma unroll
+        for (int w = 0; w < RS_NW; ++w) total += s_cnt[w][tid];
+        volatile uint32_t* st = status;
+        uint32_t excl = 0;
+        if (tile == 0) {
+            st[tid] = total | OS_PRE;
+        } else {
+            st[(size_t)tile * RS_BINS + tid] = total | OS_AGG;
+            for (uint32_t t = tile; t-- > 0;) {
+                uint32_t w, spins = 0;
+                while (((w = st[(size_t)t * RS_BINS + tid]) & (OS_AGG | OS_PRE)) == 0)
+                    if (++spins > (1u << 28)) __trap();                // a predecessor never published: fail loudly, never hang
+                excl += w & OS_VAL;
+                if (w & OS_PRE) break;
+            }
+            st[(size_t)tile * RS_BINS + tid] = (excl + total) | OS_PRE;
+        }
+        uint32_t run = gbase[tid] + excl;
+        #pragma unroll
+        for (int w = 0; w < RS_NW; ++w) {
+            const uint32_t c = s_cnt[w][tid];
+            s_cnt[w][tid] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    #pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const uint32_t i = wbase + r * 32 + lane;
+        const bool ok = i < n;
+        const uint32_t d = (uint32_t)(k[r] >> shift) & 255u;
+        const uint32_t act = __ballot_sync(FULL, ok);
+        uint32_t peers = 0;
+        if (ok) {
+            peers = __match_any_sync(act, d);
+            const uint32_t pos = s_cnt[warp][d] + __popc(peers & lt);
+            keys_out[pos] = k[r];
+            vals_out[pos] = v[r];
+        }
+        __syncwarp();
+        if (ok && (peers & lt) == 0) s_cnt[warp][d] += __popc(peers);
+        __syncwarp();
+    }
+}
+
 static inline uint32_t rs_blocks(uint32_t n) { return (n + RS_TILE - 1) / RS_TILE; }
 
 // hist scratch: (256 * nblk + 256) u32
-size_t radix_hist_bytes(uint32_t n) { return ((size_t)rs_blocks(n) * RS_BINS + RS_BINS) * 4 + 256; }
+static inline size_t onesweep_words(uint32_t n)
+{   // [digit bases: 8 x 256][tickets: 16][status: 8 passes x tiles x 256]
+    return (size_t)OS_MAX_PASSES * RS_BINS + 16 + (size_t)OS_MAX_PASSES * rs_blocks(n) * RS_BINS;
+}
+size_t radix_hist_bytes(uint32_t n)
+{
+    const size_t staged = ((size_t)rs_blocks(n) * RS_BINS + RS_BINS) * 4 + 256;
+    const size_t one = n <= RS_ONESWEEP_MAX_KEYS ? onesweep_words(n) * 4 + 256 : 0;
+    return one > staged ? one : staged;
+}
 // the single last CTA scans 256 rows of nblk counts: a win up to 16 tiles (32,768 keys: 0.39 -> 0.30 ms
 // for maximin + order at 16,384 gladiators), a loss from 64 tiles on, where the two scan kernels stay
 constexpr uint32_t RS_FUSED_SCAN_MAX_TILES = 16;
@@ -244,6 +389,25 @@ int radix_sort_pairs_bits(gcp_ctx* ctx, unsigned long long* keys, uint32_t* vals
     unsigned long long* kin = keys; unsigned long long* kout = keys_tmp;
     uint32_t* vin = vals; uint32_t* vout = vals_tmp;
     const int passes = (n_bits + 7) / 8;
+    if (ctx->sort_onesweep && n <= RS_ONESWEEP_MAX_KEYS && passes <= OS_MAX_PASSES && n > 0) {
+        uint32_t* gbase = hist;
+        uint32_t* tickets = hist + OS_MAX_PASSES * RS_BINS;               // [0] histogram kernel, [1 + pass] scatter
+        uint32_t* status = tickets + 16;
+        GCP_CUDA(ctx, cudaMemsetAsync(hist, 0, (OS_MAX_PASSES * RS_BINS + 16 + (size_t)passes * nblk * RS_BINS) * 4, st));
+        k_os_hist<<<nblk, RS_THREADS, 0, st>>>(kin, n, passes, gbase, tickets, nblk);
+        for (int pass = 0; pass < passes; ++pass) {
+            k_os_scatter<<<nblk, RS_THREADS, 0, st>>>(kin, vin, n, pass * 8, gbase + pass * RS_BINS,
+                                                      status + (size_t)pass * nblk * RS_BINS, tickets + 1 + pass,
+                                                      kout, vout);
+            unsigned long long* tk = kin; kin = kout; kout = tk;
+            uint32_t* tv = vin; vin = vout; vout = tv;
+        }
+        ctx->launches += 2 + passes;
+        GCP_CUDA(ctx, cudaGetLastError());
+        if (out_keys) *out_keys = kin;
+        if (out_vals) *out_vals = vin;
+        return 0;
+    }
     const bool fused_scan = nblk <= RS_FUSED_SCAN_MAX_TILES;
     uint32_t* done = hist + (size_t)RS_BINS * nblk + RS_BINS;          // ticket counter behind the table
     if (fused_scan) GCP_CUDA(ctx, cudaMemsetAsync(done, 0, 4, st));

@@ -273,6 +273,8 @@ int gcp_peer_barrier(gcp_ctx* ctx, const gcp_shards* flags, uint32_t rank, uint3
 
 /* ---- tuning / testing knobs (defaults are right for production) ---------------------
  * "rank_algo": 0 auto, 1 O(N^2) dominance-matrix tiles, 2 sort-based O(N log N) (both exact);
+ * "sort_onesweep": 1 (default) radix sorts of <= 2^20 pairs take one launch per pass (decoupled
+ * look-back), 0 = histogram / scan / scatter launches per pass (same order, the cross-check);
  * "force_general": never take the pre-masked coverage fast path; "fused_eval": 0 = staged kernels;
  * "force_lc_big": long-genome loop closures even for short genomes (1 radix sort, 2 partitioned hash); "vary_org_offset": global id of
  * local organism 0 when a rank varies only its shard of the children (keys of the Philox streams);

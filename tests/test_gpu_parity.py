@@ -303,6 +303,26 @@ def test_radix_order_is_stable_on_adversarial_keys(eng_big):
         assert np.array_equal(nondom.cpu().numpy() == 1, fit < 0)
 
 
+@pytest.mark.parametrize("n", [1, 2, 2048, 2049, 70001, 302000, 700001, 1300000])
+def test_radix_sort_one_launch_per_pass_equals_staged_passes(eng_big, n):
+    """The default radix sort (<= 2^20 pairs: one launch per pass, tile offsets by decoupled look-back
+    with ticketed tiles) and the histogram / scan / scatter variant give the stable (fit, index) order:
+    one tile, a partial tile, more tiles than SMs can hold at once, and a size beyond the one-launch
+    limit; heavy ties (the order inside a tie group is what stability is about)."""
+    import torch
+    rs = np.random.RandomState(n % 1000)
+    fit = np.where(rs.rand(n) < 0.4, rs.randint(-4, 4, n) * 0.125, rs.randn(n))
+    want = np.argsort(fit, kind='stable')
+    for one in (1, 0):
+        eng_big.set_option("sort_onesweep", one)
+        try:
+            order, nondom = eng_big.arena_order(torch.from_numpy(fit))
+        finally:
+            eng_big.set_option("sort_onesweep", 1)
+        assert np.array_equal(order.cpu().numpy(), want), one
+        assert np.array_equal(nondom.cpu().numpy() == 1, fit < 0)
+
+
 # ---------------------------------------------------------------------------------------
 # binary synthetic world: -coverage must be BIT-exact, and the objectives-only fast path
 # (pre-masked footprint store) must agree with the general kernel and the oracle.
