@@ -18,8 +18,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgcp.so")
 LIB_DEBUG = os.path.join(HERE, "libgcp_debug.so")
 OBJDIR = os.path.join(HERE, "_build")
-SOURCES = ["gcp_api.cu", "gcp_eval.cu", "gcp_frustum.cu", "gcp_graph.cu", "gcp_fused.cu", "gcp_lcbig.cu",
-           "gcp_rank.cu", "gcp_sort.cu", "gcp_vary.cu"]
+SOURCES = ["gcp_api.cu", "gcp_eval.cu", "gcp_frustum.cu", "gcp_graph.cu", "gcp_fused.cu", "gcp_host.cu",
+           "gcp_lcbig.cu", "gcp_rank.cu", "gcp_sort.cu", "gcp_vary.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

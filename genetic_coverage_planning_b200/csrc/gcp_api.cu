@@ -64,6 +64,7 @@ void gcp_destroy(gcp_ctx* c)
     for (void* q : c->shard_own) cudaFree(q);
     for (int i = 0; i < c->n_owned; ++i) cudaFree(c->owned[i]);
     if (c->stage_dev) cudaFree(c->stage_dev);
+    gcp_host_free(c);
     if (c->vary_scratch) cudaFree(c->vary_scratch);
     for (int s = 0; s < 3; ++s) {
         if (c->lcb_scratch_s[s]) cudaFree(c->lcb_scratch_s[s]);
@@ -422,6 +423,9 @@ static int eval_host_impl(gcp_ctx* c, const void* dna_host, int gene16, uint32_t
     const bool fused = fast_path(c, &probe);
     if (gene16 && !fused)
         return gcp_fail(c, -1, "gcp_eval_host16: only the fused objectives path takes int16 genes");
+    // int32 genes of a world whose ids fit int16: host threads narrow them on the way (gcp_host.cu)
+    if (!gene16 && fused && c->host_narrow && c->t.N <= 32767u)
+        return eval_host_narrowed(c, reinterpret_cast<const int32_t*>(dna_host), P, obj_host, flags_host);
     const size_t dna_b = align256((size_t)chunk * A * L * gsz);
     const size_t scr_b = fused ? 256 : align256(gcp_eval_scratch_bytes(c, chunk));
     const size_t obj_b = align256((size_t)chunk * 16);
@@ -672,6 +676,8 @@ int gcp_set_option(gcp_ctx* c, const char* name, int64_t value)
     if (!c || !name) return -1;
     if (!strcmp(name, "rank_algo")) c->rank_algo = (int)value;
     else if (!strcmp(name, "sort_onesweep")) c->sort_onesweep = (int)value;
+    else if (!strcmp(name, "host_narrow")) c->host_narrow = (int)value;
+    else if (!strcmp(name, "host_threads")) { if (value < 0 || value > 64) return gcp_fail(c, -1, "host_threads must be in [0,64]"); c->host_threads = (int)value; }
     else if (!strcmp(name, "force_general")) c->force_general = (int)value;
     else if (!strcmp(name, "fused_eval")) c->fused_eval = (int)value;
     else if (!strcmp(name, "force_lc_big")) c->force_lc_big = (int)value;

@@ -273,6 +273,9 @@ int gcp_peer_barrier(gcp_ctx* ctx, const gcp_shards* flags, uint32_t rank, uint3
 
 /* ---- tuning / testing knobs (defaults are right for production) ---------------------
  * "rank_algo": 0 auto, 1 O(N^2) dominance-matrix tiles, 2 sort-based O(N log N) (both exact);
+ * "host_narrow": 1 (default) gcp_eval_host narrows int32 genes to int16 with host threads on the way to
+ * the GPU when the waypoint ids fit (N <= 32767) - half the PCIe bytes, same results; "host_threads":
+ * worker threads of that conversion (0 = auto: cores / LOCAL_WORLD_SIZE - 1, at most 12);
  * "sort_onesweep": 1 (default) radix sorts of <= 2^20 pairs take one launch per pass (decoupled
  * look-back), 0 = histogram / scan / scatter launches per pass (same order, the cross-check);
  * "force_general": never take the pre-masked coverage fast path; "fused_eval": 0 = staged kernels;

@@ -544,6 +544,40 @@ def test_out_of_range_genes_raise_the_error_flag(synth_setup):
     eng.raise_on_error(clean)
 
 
+def test_host_call_narrows_int32_genes_on_the_way(synth_setup):
+    """gcp_eval_host on a world whose ids fit int16: worker threads narrow the int32 chromosomes
+    (saturating) into a pinned int16 copy while finished chunks go to the GPU.  Same objectives and
+    flags as the device-resident call and as the plain int32 transfer, for 1 / 3 / auto threads, ragged
+    population sizes, and genes far outside int16 (they must stay flagged, not wrap into valid ids)."""
+    import torch
+    from genetic_coverage_planning_b200 import synth
+    sw, pw, ow, op, eng, starts = synth_setup
+    base = synth.random_walk_population(sw.xy, sw.row_ptr, sw.col, starts, 40, 150, 200, seed=41).astype(np.int32)
+    for P in (1, 37, 5000, 9731):
+        dna = np.ascontiguousarray(base[np.random.default_rng(P).integers(0, len(base), P)])
+        if P >= 37:
+            dna[5, 1, 10] = 70000                   # 70000 & 0xFFFF = 4464 would be a valid waypoint
+            dna[9, 0, 3] = -65537 + 2               # low half = 1
+            dna[11, 2, 0] = -2
+        want = eng.evaluate(dna, detail=False)
+        wo, wf = want.obj.cpu().numpy(), want.flags.cpu().numpy()
+        if P >= 37:
+            assert wf[5, 3] & 1 and wf[9, 3] & 1 and wf[11, 3] & 1 and not wf[6, 3]
+        pinned = torch.from_numpy(dna).pin_memory()
+        for narrow, threads in ((1, 1), (1, 3), (1, 0), (0, 0)):
+            eng.set_option("host_narrow", narrow)
+            eng.set_option("host_threads", threads)
+            try:
+                obj_h, flags_h = eng.evaluate_host(pinned)
+            finally:
+                eng.set_option("host_narrow", 1)
+                eng.set_option("host_threads", 0)
+            ok = wf[:, 3] == 0                       # objectives of flagged organisms are unspecified
+            assert np.array_equal(flags_h.numpy()[:, 3] & 1, wf[:, 3] & 1), (P, narrow, threads)
+            assert np.array_equal(flags_h.numpy()[ok], wf[ok]), (P, narrow, threads)
+            assert np.array_equal(obj_h.numpy()[ok], wo[ok]), (P, narrow, threads)
+
+
 def test_binary_world_blend(synth_setup):
     """blend < 1 needs the internal-coverage counter: general kernel, still bit-exact."""
     sw, pw, ow, op, eng, starts = synth_setup
