@@ -90,6 +90,56 @@ static int upload(gcp_ctx* c, const T** dst, const void* src, size_t count)
     return 0;
 }
 
+// Flat per-edge lists of QUARTER items {block << 2 | q, index} for the fused kernels (index: quarter
+// number << idx_shift; 3 = uint4 units).  false if an edge has more than 63 items or the lists
+// outgrow 26 bits.
+static bool build_quarter_lists(const uint32_t* sub_ptr, const uint32_t* sub_block, const uint32_t* sub_payload,
+                                size_t EN, uint64_t n_sub, int idx_shift, std::vector<uint32_t>& qinfo,
+                                std::vector<uint2>& qdesc)
+{
+    qinfo.assign(EN, 0u);
+    qdesc.clear();
+    qdesc.reserve((size_t)n_sub * 2);
+    for (size_t e = 0; e < EN; ++e) {
+        if (qdesc.size() & 1) qdesc.push_back(make_uint2(0u, 0u));   // lists start 16-B aligned: items are read in pairs
+        const size_t first = qdesc.size();
+        for (uint32_t k = sub_ptr[e]; k < sub_ptr[e + 1]; ++k) {
+            uint32_t off = sub_payload[k] >> 4;
+            for (uint32_t q = 0; q < 4; ++q)
+                if ((sub_payload[k] >> q) & 1u) qdesc.push_back(make_uint2((sub_block[k] << 2) | q, (off++) << idx_shift));
+        }
+        const size_t n = qdesc.size() - first;
+        if (n > 63 || first >= (1u << 26)) return false;
+        qinfo[e] = (uint32_t)first | ((uint32_t)n << 26);
+    }
+    qdesc.push_back(make_uint2(0u, 0u));                             // pair reads may touch one item past a list
+    qdesc.push_back(make_uint2(0u, 0u));
+    qdesc.push_back(make_uint2(0u, 0u));
+    return true;
+}
+
+// General fused kernel: footprint quarters, (g == 0) plane and mask & (g == 0) plane in ONE allocation
+// (the map planes are 32 x uint4 = four 128-B quarters per block, like the tiles), so that the kernel's
+// sorted stream addresses all three with one 30-bit quarter index.  Replaces the tile allocation.
+static int build_general_store(gcp_ctx* c)
+{
+    c->t.g_free_q = 0; c->t.g_mask_q = 0;
+    if (!c->have_edges || !c->have_map || !c->t.q_info) return 0;
+    const size_t nq = c->n_quarters, nb = c->t.n_blocks;
+    if (nq == 0 || nq + 8 * nb >= (1ull << 30)) return 0;            // the staged kernels remain
+    char* p = nullptr;
+    GCP_CUDA(c, cudaMalloc(&p, (nq + 8 * nb) * 128));
+    GCP_CUDA(c, cudaMemcpy(p, c->t.tile, nq * 128, cudaMemcpyDeviceToDevice));
+    GCP_CUDA(c, cudaMemcpy(p + nq * 128, c->t.blk_free0, nb * 512, cudaMemcpyDeviceToDevice));
+    GCP_CUDA(c, cudaMemcpy(p + (nq + 4 * nb) * 128, c->t.blk_mask0, nb * 512, cudaMemcpyDeviceToDevice));
+    for (int i = 0; i < c->n_owned; ++i)
+        if (c->owned[i] == (void*)c->t.tile) { cudaFree(c->owned[i]); c->owned[i] = p; }
+    c->t.tile = reinterpret_cast<const uint4*>(p);
+    c->t.g_free_q = (uint32_t)nq;
+    c->t.g_mask_q = (uint32_t)(nq + 4 * nb);
+    return 0;
+}
+
 extern "C" {
 
 int gcp_upload_graph(gcp_ctx* c, uint32_t N, uint32_t E, const uint32_t* row_ptr,
@@ -170,9 +220,18 @@ int gcp_upload_edges(gcp_ctx* c, const double* edge_cost, const double* edge_the
         if ((r = upload(c, &c->t.sub_desc, desc.data(), n_sub))) return r;
     }
     if ((r = upload(c, &c->t.tile, tile_data, (size_t)n_quarters * 8))) return r;   // uint4
+    {   // quarter items of the unmasked store: the general fused kernel (blend < 1, pixel counters)
+        std::vector<uint32_t> qinfo;
+        std::vector<uint2> qdesc;
+        c->t.q_info = nullptr; c->t.q_desc = nullptr;
+        if (build_quarter_lists(sub_ptr, sub_block, sub_payload, EN, n_sub, 0, qinfo, qdesc)) {
+            if ((r = upload(c, &c->t.q_info, qinfo.data(), EN))) return r;
+            if ((r = upload(c, &c->t.q_desc, qdesc.data(), qdesc.size()))) return r;
+        }
+    }
     c->n_sub = n_sub; c->n_quarters = n_quarters;
     c->have_edges = true;
-    return 0;
+    return build_general_store(c);
 }
 
 int gcp_upload_masked_footprints(gcp_ctx* c, const uint32_t* sub_ptr, const uint32_t* sub_block,
@@ -200,28 +259,11 @@ int gcp_upload_masked_footprints(gcp_ctx* c, const uint32_t* sub_ptr, const uint
     if ((r = upload(c, &c->t.m_sub_desc, desc.data(), n_sub))) return r;
     if ((r = upload(c, &c->t.m_tile, tile_data, (size_t)n_quarters * 8))) return r;
     {   // flat per-edge lists of QUARTER items for the fused kernel: {block<<2 | q, uint4 index}
-        std::vector<uint32_t> qinfo(EN);
+        std::vector<uint32_t> qinfo;
         std::vector<uint2> qdesc;
-        qdesc.reserve((size_t)n_sub * 2);
-        bool ok = true;
-        for (size_t e = 0; e < EN && ok; ++e) {
-            if (qdesc.size() & 1) qdesc.push_back(make_uint2(0u, 0u));   // lists start 16-B aligned: items are read in pairs
-            const size_t first = qdesc.size();
-            for (uint32_t k = sub_ptr[e]; k < sub_ptr[e + 1]; ++k) {
-                uint32_t off = sub_payload[k] >> 4;
-                for (uint32_t q = 0; q < 4; ++q)
-                    if ((sub_payload[k] >> q) & 1u) qdesc.push_back(make_uint2((sub_block[k] << 2) | q, (off++) << 3));
-            }
-            const size_t n = qdesc.size() - first;
-            if (n > 63 || first >= (1u << 26)) ok = false;
-            qinfo[e] = (uint32_t)first | ((uint32_t)n << 26);
-        }
         c->t.m_q_info = nullptr; c->t.m_q_desc = nullptr;
-        if (ok) {
+        if (build_quarter_lists(sub_ptr, sub_block, sub_payload, EN, n_sub, 3, qinfo, qdesc)) {
             if ((r = upload(c, &c->t.m_q_info, qinfo.data(), EN))) return r;
-            qdesc.push_back(make_uint2(0u, 0u));                             // pair reads may touch one item past a list
-            qdesc.push_back(make_uint2(0u, 0u));
-            qdesc.push_back(make_uint2(0u, 0u));
             if ((r = upload(c, &c->t.m_q_desc, qdesc.data(), qdesc.size()))) return r;
         }
     }
@@ -244,12 +286,25 @@ int gcp_upload_map(gcp_ctx* c, const gcp_map_consts* mc, const uint64_t* blk_mas
     if ((r = upload(c, &c->t.blk_mask0, blk_mask0, nb * 32))) return r;    // uint4
     if ((r = upload(c, &c->t.blk_free0, blk_free0, nb * 32))) return r;
     if ((r = upload(c, &c->t.gray_ptr, gray_ptr, nb + 1))) return r;
-    if ((r = upload(c, &c->t.gray_ent, gray_ent, n_gray))) return r;
+    {   // a block's gray entries ordered by quarter (stable), plus the CSR over (block, quarter): the flat
+        // union of the general fused kernel applies the gray weights at the end of every quarter list
+        std::vector<uint32_t> ent(gray_ent, gray_ent + n_gray), qptr(nb * 4 + 1, 0u);
+        for (size_t b = 0; b < nb; ++b) {
+            uint32_t cnt[4] = {0, 0, 0, 0};
+            for (uint32_t g = gray_ptr[b]; g < gray_ptr[b + 1]; ++g) cnt[((gray_ent[g] & 4095u) >> 6) >> 4]++;
+            uint32_t at[4], run = gray_ptr[b];
+            for (int q = 0; q < 4; ++q) { qptr[b * 4 + q] = run; at[q] = run; run += cnt[q]; }
+            for (uint32_t g = gray_ptr[b]; g < gray_ptr[b + 1]; ++g) ent[at[((gray_ent[g] & 4095u) >> 6) >> 4]++] = gray_ent[g];
+        }
+        qptr[nb * 4] = (uint32_t)n_gray;
+        if ((r = upload(c, &c->t.gray_qptr, qptr.data(), qptr.size()))) return r;
+        if ((r = upload(c, &c->t.gray_ent, ent.data(), n_gray))) return r;
+    }
     c->t.n_blocks = (uint32_t)nb;
     c->mc = *mc;
     c->n_gray = n_gray;
     c->have_map = true;
-    return 0;
+    return build_general_store(c);
 }
 
 int gcp_set_params(gcp_ctx* c, const gcp_params* p)
@@ -330,6 +385,9 @@ int gcp_eval(gcp_ctx* c, const int32_t* dna, uint32_t P, const gcp_eval_out* out
     const bool fast_staged = fast && (fast_q || c->n_gray == 0);
     if (fast && c->fused_eval && c->t.m_q_info && eval_fused_fits(c))   // one kernel, no scratch (gcp_fused.cu)
         return launch_eval_fused(c, dna, 0, P, out, (cudaStream_t)stream);
+    // any coverage_blend / all six pixel counters: the same kernel over the unmasked store
+    if (c->fused_eval && eval_fused_fits(c, true))
+        return launch_eval_fused(c, dna, 0, P, out, (cudaStream_t)stream, true);
     if (scratch_bytes < gcp_eval_scratch_bytes(c, P) || !scratch)
         return gcp_fail(c, -1, "gcp_eval: scratch too small (%zu < %zu)", scratch_bytes,
                         gcp_eval_scratch_bytes(c, P));

@@ -34,6 +34,11 @@ struct GcpTables {
     const uint32_t* sub_info;  // [E+N] first sub-tile (28 bits) | count << 28
     const uint2*    sub_desc;  // [S] {block id, (offset128<<4)|qmask}
     const uint4*    tile;      // quarters: 8 x uint4 = 16 rows of 64 px
+    const uint32_t* q_info;    // [E+N] first quarter item (26 bits) | count << 26 over the UNMASKED store (general fused kernel)
+    const uint2*    q_desc;    // {block id << 2 | quarter index, index of the 128-B quarter in tile}
+    // general fused kernel: the (g == 0) and mask & (g == 0) planes are appended to the tile allocation, so
+    // that ONE 30-bit quarter index addresses footprint quarters and plane quarters alike (0 = not built)
+    uint32_t g_free_q, g_mask_q;
     // second store: footprints pre-ANDed with buffer_mask (optional)
     const uint32_t* m_sub_info;
     const uint2*    m_sub_desc;
@@ -45,6 +50,7 @@ struct GcpTables {
     const uint4*    blk_mask0; // buffer_mask & (g==0)
     const uint4*    blk_free0; // (g==0)
     const uint32_t* gray_ptr;  // [n_blocks+1]
+    const uint32_t* gray_qptr; // [4*n_blocks+1] the same entries per (block, quarter): a block's entries are ordered by quarter
     const uint32_t* gray_ent;  // pos(12) | (255-g)<<12 | in_mask<<20
 };
 
@@ -136,8 +142,8 @@ int launch_loop_closures(gcp_ctx*, const int32_t* dna, uint32_t P, const double*
                          const double* turn, const uint32_t* cov, int32_t* lc, double* obj,
                          double* neg_cov, uint8_t* flags, cudaStream_t);
 int launch_eval_fused(gcp_ctx*, const void* dna, int gene16, uint32_t P, const gcp_eval_out* out,
-                      cudaStream_t);
-bool eval_fused_fits(gcp_ctx*);
+                      cudaStream_t, bool general = false);
+bool eval_fused_fits(gcp_ctx*, bool general = false);
 int eval_host_narrowed(gcp_ctx*, const int32_t* dna_host, uint32_t P, double* obj_host, uint8_t* flags_host);
 void gcp_host_free(gcp_ctx*);
 int launch_loop_closures_big(gcp_ctx*, const int32_t* dna, uint32_t P, const double* dist,

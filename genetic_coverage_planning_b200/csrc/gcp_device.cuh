@@ -12,6 +12,15 @@ __device__ __forceinline__ int popc128(uint4 a)
     return __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w);
 }
 
+__device__ __forceinline__ uint4 and128(uint4 a, uint4 b)
+{
+    return make_uint4(a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w);
+}
+__device__ __forceinline__ void or128(uint4& a, uint4 b)
+{
+    a.x |= b.x; a.y |= b.y; a.z |= b.z; a.w |= b.w;
+}
+
 __device__ __forceinline__ double np_sum_order(const double* a, int n)
 {
     // numpy pairwise_sum for n < 128 (verified against np.sum, tests/test_oracle_golden)

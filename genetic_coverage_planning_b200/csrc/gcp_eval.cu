@@ -160,14 +160,7 @@ __device__ __forceinline__ uint4 ld_quarter(const uint4* __restrict__ tile, uint
     return v;
 }
 
-__device__ __forceinline__ uint4 and128(uint4 a, uint4 b)
-{
-    return make_uint4(a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w);
-}
-__device__ __forceinline__ void or128(uint4& a, uint4 b)
-{
-    a.x |= b.x; a.y |= b.y; a.z |= b.z; a.w |= b.w;
-}
+
 
 // NEED_FREE: also count against the (g==0) plane (internal coverage, blend < 1 or detail)
 // NEED_ALL : also count every painted pixel (detail output n_cov_all)

@@ -56,14 +56,39 @@ __device__ __forceinline__ const uint4* tile_at(const uint4* base, uint32_t idx)
     return reinterpret_cast<const uint4*>(addr);
 }
 
-template <int KF_THREADS, bool HAS_GRAY, bool BUCKETS = false>
+// base + idx * 128: a whole quarter (8 x uint4) per index
+__device__ __forceinline__ const uint4* quarter_at(const uint4* base, uint32_t idx)
+{
+    unsigned long long addr;
+    asm("mad.wide.u32 %0, %1, 128, %2;" : "=l"(addr) : "r"(idx), "l"(base));
+    return reinterpret_cast<const uint4*>(addr);
+}
+
+// Per-thread partial pixel counts of one organism (the caller reduces them over the CTA).
+//   objectives-only (pre-masked store): n_cov = covered mask pixels with g == 0, n_wg = sum of (255 - g)
+//   over covered gray mask pixels.
+//   GENERAL (unmasked store): n_cov = n_mask0 and n_wg = wg_mask as above, n_free0 = covered pixels with
+//   g == 0, wg_all = sum of (255 - g) over all covered gray pixels, n_gmask = covered gray mask pixels,
+//   n_all = every covered pixel (occluded ones included) - the six counters of k_coverage (gcp_eval.cu).
+struct CovCounts { uint32_t n_cov, n_wg, n_free0, wg_all, n_gmask, n_all; };
+
+// GENERAL: the items come from the UNMASKED store (GcpTables::q_info / q_desc / tile) and the sorted
+// array carries, behind every (block, quarter) list, two MARKER entries {tag, block << 2 | quarter}: the
+// first makes the group AND the finished union with the (g == 0) plane of that quarter, the second with
+// the mask & (g == 0) plane - loaded like any other 128-B line of the stream, four loads in flight.
+// Gray pixels are weighed at the second marker from the per-quarter gray lists.
+template <int KF_THREADS, bool HAS_GRAY, bool BUCKETS = false, bool GENERAL = false>
 __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const GcpTables& t,
                                                   int T, int MAXP, uint32_t R0, uint32_t DS, unsigned char* s_x,
-                                                  uint32_t& n_cov, uint32_t& n_wg, bool& failed,
+                                                  CovCounts& cc, bool& failed,
                                                   uint2* rec = nullptr, uint32_t rec_cap = 0, bool prefetch = false,
                                                   bool tail_barrier = true)
 {
     constexpr int KF_NW = KF_THREADS / 32;
+    constexpr uint32_t NM = GENERAL ? 2u : 0u;                 // marker entries behind every list
+    const uint2* const q_desc = GENERAL ? t.q_desc : t.m_q_desc;
+    const uint4* const q_tile = GENERAL ? t.tile : t.m_tile;
+    uint32_t n_cov = 0, n_wg = 0, n_free0 = 0, wg_all = 0, n_gmask = 0, n_all = 0;
     __shared__ uint32_t s_npairs, s_overflow, s_group;
     __shared__ uint32_t s_wsum[KF_NW];
     __shared__ uint32_t s_pcnt[64], s_pbase[65];               // item buckets per hash partition (long genomes)
@@ -99,7 +124,7 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
     uint32_t R = R0;
     failed = false;
     for (;;) {                                   // retry loop over partition count R
-        n_cov = 0; n_wg = 0;
+        n_cov = 0; n_wg = 0; n_free0 = 0; wg_all = 0; n_gmask = 0; n_all = 0;
         bool overflow = false;
         // ---- long genomes (R > 1) with a scratch array: bucket the item descriptors by hash
         //      partition ONCE (count, prefix, scatter; lanes that hit the same partition share
@@ -132,7 +157,7 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
                         a = min(a, 31);
                         const uint32_t ex = __shfl_sync(FULL, excl, a), dlo = __shfl_sync(FULL, lo, a);
                         uint2 dsc = make_uint2(0, 0);
-                        if (j < total) dsc = __ldg(t.m_q_desc + dlo + (j - ex));
+                        if (j < total) dsc = __ldg(q_desc + dlo + (j - ex));
                         fn(j < total, dsc);
                     }
                 }
@@ -251,10 +276,10 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
                             a = min(a, 31);
                             const uint32_t ex = __shfl_sync(FULL, excl, a), dlo = __shfl_sync(FULL, lo, a);
                             if (j < total) {
-                                const uint2 dsc = __ldg(t.m_q_desc + dlo + (j - ex));
+                                const uint2 dsc = __ldg(q_desc + dlo + (j - ex));
                                 // store larger than the L2 (config C5, diverse populations): start the
                                 // DRAM fetch of this quarter's line now, B2 finds it in the L2
-                                if (prefetch) asm volatile("prefetch.global.L2 [%0];" :: "l"(tile_at(t.m_tile, dsc.y)));
+                                if (prefetch) asm volatile("prefetch.global.L2 [%0];" :: "l"(GENERAL ? quarter_at(q_tile, dsc.y) : tile_at(q_tile, dsc.y)));
                                 const uint32_t blk = dsc.x >> 2, q = dsc.x & 3u;
                                 const uint32_t key = blk + 1;
                                 uint32_t h = hash_block(blk) >> (32 - logT);
@@ -304,7 +329,7 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
                         uint2 dsc = make_uint2(0, 0);
                         bool mine = false;
                         if (j < total) {
-                            dsc = __ldg(t.m_q_desc + dlo + (j - ex));
+                            dsc = __ldg(q_desc + dlo + (j - ex));
                             mine = (part_block(dsc.x >> 2) & (R - 1)) == r;
                         }
                         const uint32_t bal = __ballot_sync(FULL, mine);
@@ -345,6 +370,7 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
             overflow = (s_overflow != 0);
             if (overflow) { __syncthreads(); break; }
             const uint32_t npairs = s_npairs;
+            uint32_t n_sorted = npairs;            // entries of the sorted array (GENERAL: items + markers)
             // ---- exclusive scan of the (slot, quarter) counts ----
             //      (thread t owns counters t, t + THREADS, ...: consecutive lanes hit consecutive banks; the
             //      order in which the lists end up in the sorted array is irrelevant, only that every
@@ -352,7 +378,7 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
             {
                 const int per = 4 * T / KF_THREADS;
                 uint32_t loc = 0;
-                for (int k = 0; k < per; ++k) loc += s_cq[k * KF_THREADS + tid];
+                for (int k = 0; k < per; ++k) { const uint32_t c = s_cq[k * KF_THREADS + tid]; loc += c + (c ? NM : 0u); }
                 uint32_t inc = loc;
                 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -361,13 +387,18 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
                 }
                 if (lane == 31) s_wsum[warp] = inc;
                 __syncthreads();
-                uint32_t woff = 0;
-                for (int w2 = 0; w2 < warp; ++w2) woff += s_wsum[w2];
+                uint32_t woff = 0, wall = 0;
+                for (int w2 = 0; w2 < KF_NW; ++w2) { if (w2 == warp) woff = wall; wall += s_wsum[w2]; }
+                if (GENERAL) {
+                    // the markers share the sorted array with the items: more entries than it holds -> more partitions
+                    if (wall > (uint32_t)MAXP) { overflow = true; __syncthreads(); break; }
+                    n_sorted = wall;
+                }
                 uint32_t run = woff + inc - loc;
                 for (int k = 0; k < per; ++k) {
                     const uint32_t c = s_cq[k * KF_THREADS + tid];
                     s_cq[k * KF_THREADS + tid] = (c << 16) | run;
-                    run += c;
+                    run += c + (c ? NM : 0u);
                 }
             }
             __syncthreads();
@@ -381,21 +412,132 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
                     const uint32_t sr = s_sr[i];
                     const uint32_t cb = s_cq[sr >> 16], rank = sr & 0xFFFFu;
                     pos[k] = (cb & 0xFFFFu) + rank;
-                    GCP_DASSERT((sr >> 16) < 4u * (uint32_t)T && pos[k] < npairs);
-                    ent[k] = s_pay[i] | ((rank + 1u == (cb >> 16)) ? 0x80000000u : 0u);   // last of its list
+                    GCP_DASSERT((sr >> 16) < 4u * (uint32_t)T && pos[k] + ((rank + 1u == (cb >> 16)) ? NM : 0u) < n_sorted);
+                    if (GENERAL) {
+                        ent[k] = s_pay[i];
+                        if (rank + 1u == (cb >> 16)) pos[k] |= 0x80000000u;                  // last of its list: the markers follow
+                    } else {
+                        ent[k] = s_pay[i] | ((rank + 1u == (cb >> 16)) ? 0x80000000u : 0u);   // last of its list
+                    }
                 }
             }
             __syncthreads();
             #pragma unroll
             for (int k = 0; k < KF_PPT; ++k)
-                if (pos[k] != KF_NIL) s_pay[pos[k]] = ent[k];
+                if (pos[k] != KF_NIL) {
+                    if (GENERAL) {
+                        const uint32_t p = pos[k] & 0x7FFFFFFFu;
+                        s_pay[p] = ent[k];
+                        if (pos[k] >> 31) {
+                            const uint32_t sr = s_sr[tid + k * KF_THREADS];
+                            const uint32_t bq = ((s_keys[sr >> 18] - 1u) << 2) | ((sr >> 16) & 3u);
+                            s_pay[p + 1] = 0x80000000u | (t.g_free_q + bq);   // AND with the (g == 0) plane
+                            s_pay[p + 2] = 0xC0000000u | (t.g_mask_q + bq);   // AND with mask & (g == 0), gray weights, list ends
+                        }
+                    } else {
+                        s_pay[pos[k]] = ent[k];
+                    }
+                }
             __syncthreads();
             // ---- B2 (gray maps): owner warps, groups of 32 slots handed out dynamically ----
             // per-lane tile base kept in registers: the opaque asm stops ptxas from re-deriving
             // it (S2R tid + LDC of the table pointer) in front of every load
-            const uint4* tile_l = t.m_tile + l7;
+            const uint4* tile_l = q_tile + l7;
             asm volatile("" : "+l"(tile_l));
-            if (!HAS_GRAY) {
+            if (GENERAL) {
+                // ---- B2 (flat, general): as below, over items + markers.  An entry is a quarter of the
+                //      unmasked store (OR into the registers) or a marker {tag, block << 2 | quarter}, whose
+                //      128-B line is the (g == 0) plane (tag 10) or the mask & (g == 0) plane (tag 11, list end)
+                //      of that quarter of the map: the group ANDs its finished union with it and counts.
+                constexpr uint32_t NG = KF_NW * 4;
+                const uint32_t gid = (uint32_t)warp * 4u + myq;
+                const uint32_t gbit = 0xFFu << (myq * 8);
+                uint32_t bnd[2];
+                #pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const uint32_t w = gid + e;
+                    uint32_t c = (uint32_t)(((uint64_t)n_sorted * w) / NG);
+                    bool done = (w == 0) || (w >= NG);
+                    if (w >= NG) c = n_sorted;
+                    while (__any_sync(FULL, !done)) {               // first position >= c that starts a list
+                        const uint32_t pp = c + l7;
+                        const bool is_start = (pp >= n_sorted) || (pp == 0) || ((s_pay[pp - 1] >> 30) == 3u);
+                        const uint32_t m = __ballot_sync(FULL, is_start) & gbit;
+                        if (!done) {
+                            if (m) { c += (uint32_t)(__ffs(m) - 1) - myq * 8u; done = true; }
+                            else c += 8;
+                        }
+                    }
+                    bnd[e] = min(c, n_sorted);
+                }
+                GCP_DASSERT(bnd[0] <= bnd[1] && bnd[1] <= n_sorted);
+                const uint32_t len = bnd[1] - bnd[0];
+                const uint32_t steps = __reduce_max_sync(FULL, len);
+                const uint32_t* pb = s_pay + bnd[0];
+                uint4 acc = make_uint4(0, 0, 0, 0);
+                // entry: footprint quarter (OR) or marker - its line is the plane quarter to AND the finished
+                // union with; the second marker ends the list
+                auto take = [&](uint32_t e, const uint4& v) {
+                    if (!(e >> 31)) {
+                        acc.x |= v.x; acc.y |= v.y; acc.z |= v.z; acc.w |= v.w;
+                    } else {
+                        const uint32_t c = (uint32_t)popc128(and128(acc, v));
+                        if (!(e & 0x40000000u)) {
+                            n_free0 += c;
+                        } else {
+                            n_cov += c;
+                            n_all += popc128(acc);
+                            if (HAS_GRAY) {
+                                // gray pixels of this quarter (CSR list {pos, 255 - g, in_mask}): lane i of the
+                                // group takes entry i and fetches the row word that holds its pixel by shuffle
+                                const uint32_t bq = (e & 0x3FFFFFFFu) - t.g_mask_q;
+                                const uint32_t ga = __ldg(t.gray_qptr + bq), gb = __ldg(t.gray_qptr + bq + 1);
+                                for (uint32_t g0 = ga; g0 < gb; g0 += 8) {
+                                    const uint32_t gi = g0 + l7;
+                                    const uint32_t ent = (gi < gb) ? __ldg(t.gray_ent + gi) : 0u;
+                                    const uint32_t pos = ent & 4095u, row = (pos >> 6) & 15u, col = pos & 63u;
+                                    const int src = (int)((myq << 3) | (row >> 1));
+                                    const uint32_t wx = __shfl_sync(gbit, acc.x, src), wy = __shfl_sync(gbit, acc.y, src);
+                                    const uint32_t wz = __shfl_sync(gbit, acc.z, src), ww = __shfl_sync(gbit, acc.w, src);
+                                    const uint32_t word = (row & 1u) ? ((col & 32u) ? ww : wz) : ((col & 32u) ? wy : wx);
+                                    if (gi < gb && ((word >> (col & 31u)) & 1u)) {
+                                        const uint32_t w = (ent >> 12) & 255u;
+                                        wg_all += w;
+                                        if ((ent >> 20) & 1u) { n_wg += w; n_gmask += 1u; }
+                                    }
+                                }
+                            }
+                            acc = make_uint4(0, 0, 0, 0);
+                        }
+                    }
+                };
+                uint32_t k = 0;
+                // the ranges of a warp's four groups are equal up to the snapping: no guards up to the shortest one
+                const uint32_t steps_min = __reduce_min_sync(FULL, len) & ~3u;
+                for (; k < steps_min; k += 4) {
+                    uint32_t e[4];
+                    uint4 v[4];
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        e[j] = pb[k + j];
+                        v[j] = __ldg(quarter_at(tile_l, e[j] & 0x3FFFFFFFu));
+                    }
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) take(e[j], v[j]);
+                }
+                for (; k < steps; k += 4) {
+                    uint32_t e[4];
+                    uint4 v[4];
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        e[j] = (k + j < len) ? pb[k + j] : 0u;
+                        v[j] = make_uint4(0, 0, 0, 0);
+                        if (k + j < len) v[j] = __ldg(quarter_at(tile_l, e[j] & 0x3FFFFFFFu));
+                    }
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) take(e[j], v[j]);
+                }
+            } else if (!HAS_GRAY) {
                 // ---- B2 (flat): the sorted array is cut into KF_NW * 4 contiguous ranges snapped to
                 //      list boundaries; every 8-lane group streams its own range (lane = one uint4 =
                 //      2 rows of the quarter), ORs into registers and popcounts at each list end.
@@ -511,12 +653,13 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
                 }
             }
             // binary maps, one partition: B2 only reads the sorted array and registers
-            if (HAS_GRAY || tail_barrier || R > 1) __syncthreads();
+            if ((HAS_GRAY && !GENERAL) || tail_barrier || R > 1) __syncthreads();
         }
         if (!overflow) break;
         R <<= 1;
         if (R > 4096) { failed = true; break; }
     }
+    cc.n_cov = n_cov; cc.n_wg = n_wg; cc.n_free0 = n_free0; cc.wg_all = wg_all; cc.n_gmask = n_gmask; cc.n_all = n_all;
 }
 
 // Compile-time copy of fused_shape() for A*L == SAL with 256 threads and default tuning: with the
@@ -526,16 +669,17 @@ constexpr uint32_t c_al16(uint32_t x) { return (x + 15u) & ~15u; }
 // COMPACT (waypoint ids fit 16 bits, N <= 65,534): the chromosome and the compacted sequence are
 // held as u16, loop-closure keys take 32 bits and the item store is sized 49/24 instead of 9/4 items
 // per gene - together 37.4 KB instead of 41.7 KB for 6 x 200 genes, i.e. SIX resident CTAs per SM.
-template <int SAL, bool COMPACT>
+template <int SAL, bool COMPACT, bool GEN = false>
 struct StaticShape {
     static constexpr int AL = SAL;
-    static constexpr int maxp_raw = COMPACT ? (49 * SAL) / 24 : (9 * SAL) / 4;
-    static constexpr int maxp0 = maxp_raw < 256 ? 256 : (maxp_raw > KF_PPT * 256 ? KF_PPT * 256 : maxp_raw);
+    static constexpr int TH = GEN ? 512 : 256;           // CTA size this layout is for
+    static constexpr int maxp_raw = GEN ? (41 * SAL) / 8 : COMPACT ? (49 * SAL) / 24 : (9 * SAL) / 4;
+    static constexpr int maxp0 = maxp_raw < 256 ? 256 : (maxp_raw > KF_PPT * TH ? KF_PPT * TH : maxp_raw);
     static constexpr int MAXP = (maxp0 + 7) & ~7;
-    static constexpr int T = SAL / 3 <= 256 ? 256 : SAL / 3 <= 512 ? 512 : SAL / 3 <= 1024 ? 1024 : SAL / 3 <= 2048 ? 2048 : SAL / 3 <= 4096 ? 4096 : 8192;
+    static constexpr int T = SAL / 3 <= TH ? TH : SAL / 3 <= 512 ? 512 : SAL / 3 <= 1024 ? 1024 : SAL / 3 <= 2048 ? 2048 : SAL / 3 <= 4096 ? 4096 : 8192;
     static constexpr int T3 = (SAL * 3) / 2 + 64;
     static constexpr uint32_t DS = (uint32_t)T * 4;        // dedup hash set: 16 KiB-aligned part of the T * 20 bytes in front of s_cst
-    static constexpr uint32_t R0 = (size_t)MAXP >= (size_t)SAL * 2 ? 1u : 0u;      // 0: not representable -> runtime shape
+    static constexpr uint32_t R0 = (size_t)MAXP >= (size_t)SAL * (GEN ? 5 : 2) ? 1u : 0u;      // 0: not representable -> runtime shape
     static constexpr uint32_t off_cst = (uint32_t)T * 20;
     static constexpr uint32_t cov_b = (uint32_t)T * 20 + (uint32_t)MAXP * 8 + 32;
     static constexpr uint32_t a_b = off_cst + (uint32_t)SAL * 16 + GCP_MAX_AGENTS * 16;
@@ -554,13 +698,16 @@ struct StaticShape {
 // HAS_GRAY: the map has pixels with 0 < g < 255: covered gray mask pixels weigh 255 - g.
 // SAL > 0: A*L == SAL and the shared-memory layout is StaticShape<SAL> (must equal fused_shape()).
 // COMPACT: N <= 65,534 waypoints - see StaticShape.
-template <int KF_THREADS, bool HAS_GRAY, int SAL, bool COMPACT>
-__global__ void __launch_bounds__(KF_THREADS, KF_THREADS == 256 ? ((COMPACT && !HAS_GRAY) ? 6 : 5) : 1)
+// GENERAL: any coverage_blend and / or the six pixel counters (cov_out) - the union runs over the
+// UNMASKED footprint store with marker entries for the map planes (see coverage_quarters); 512 threads,
+// three CTAs per SM (the unmasked store carries 2.6 x the items of the pre-masked one).
+template <int KF_THREADS, bool HAS_GRAY, int SAL, bool COMPACT, bool GENERAL = false>
+__global__ void __launch_bounds__(KF_THREADS, KF_THREADS == 256 ? ((COMPACT && !HAS_GRAY) ? 6 : 5) : KF_THREADS == 512 ? 3 : 1)
 k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape sh,
              gcp_params prm, gcp_map_consts mc,
              double* __restrict__ obj, double* __restrict__ neg_cov_out,
              double* __restrict__ dist_out, double* __restrict__ turn_out,
-             int32_t* __restrict__ lc_out, uint8_t* __restrict__ flags)
+             int32_t* __restrict__ lc_out, uint8_t* __restrict__ flags, uint32_t* __restrict__ cov_out = nullptr)
 {
     constexpr int KF_NW = KF_THREADS / 32;
     constexpr bool KEY32 = COMPACT;
@@ -568,7 +715,7 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     extern __shared__ __align__(16) unsigned char smem[];
     G*        s_dna  = reinterpret_cast<G*>(smem);                            // [AL] (COMPACT: 0xFFFF = -1, 0xFFFE = out of range)
     constexpr bool ST = SAL > 0;
-    using SS = StaticShape<ST ? SAL : 1200, COMPACT>;
+    using SS = StaticShape<ST ? SAL : 1200, COMPACT, GENERAL>;
     uint32_t* s_info = reinterpret_cast<uint32_t*>(smem + (ST ? SS::off_info : sh.off_info)); // [AL] quarter-item range per step (C: slot/next)
     unsigned char* s_x = smem + (ST ? SS::off_x : sh.off_x);                  // B / C tables
     double2*  s_cst  = reinterpret_cast<double2*>(s_x + (ST ? SS::off_cst : sh.off_cst)); // [AL] {dist, turn} per step (A only; aliases s_pay/s_sr)
@@ -577,6 +724,7 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     __shared__ int s_first_neg[GCP_MAX_AGENTS], s_len[GCP_MAX_AGENTS], s_base[GCP_MAX_AGENTS + 1];
     __shared__ int s_bad;
     __shared__ uint32_t s_total, s_totalw, s_ngroups;
+    __shared__ uint32_t s_gen[4];          // GENERAL: n_free0, wg_all, n_gmask, n_all
     __shared__ uint32_t s_cov[4];
     __shared__ double s_objv[2];
 
@@ -597,6 +745,7 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     uint32_t* s_set = reinterpret_cast<uint32_t*>(s_x);       // step-dedup table (phase A1), in front of s_cst
     auto clear_tables = [&]() {
         if (tid == 0) { s_bad = 0; s_total = 0; s_totalw = 0; }
+        if (GENERAL && tid < 4) s_gen[tid] = 0;
         for (int i = tid; i < A * A; i += KF_THREADS) s_lc[i] = 0;
         if ((DS & 3u) == 0) {
             for (int i = tid; i < (int)(DS >> 2); i += KF_THREADS) reinterpret_cast<uint4*>(s_set)[i] = make_uint4(0, 0, 0, 0);
@@ -753,7 +902,7 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
                                          (((m2 & 1u) | ((m2 >> 15) & 2u)) << 4) | (((m3 & 1u) | ((m3 >> 15) & 2u)) << 6);
                     if (hit) e_[u] += (uint32_t)(__ffs(hit) - 1);
                     else { e_[u] = t.E + w_[u]; if (!sent_[u]) bad |= 1; }   // null edge (F4)
-                    info_[u] = __ldg(t.m_q_info + e_[u]);
+                    info_[u] = __ldg((GENERAL ? t.q_info : t.m_q_info) + e_[u]);
                     cst_[u] = __ldg(t.edge_cost + e_[u]);
                 }
             }
@@ -809,7 +958,7 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
                             if (__ldg(t.col + q) == (uint32_t)nx) { e = q; found = true; break; }
                     }
                     if (!found && !sentinel) bad |= 1;
-                    info = __ldg(t.m_q_info + e);
+                    info = __ldg((GENERAL ? t.q_info : t.m_q_info) + e);
                     cst = __ldg(t.edge_cost + e);
                     if (DS && info) {                        // revisited edge: see above
                         const uint32_t h = (info * 0x9E3779B1u) >> (__clz(DS) + 1);
@@ -856,20 +1005,32 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
         if (dist_out) dist_out[(size_t)org * A + lane] = acc_d;
         if (turn_out) turn_out[(size_t)org * A + lane] = acc_t;
     }
-    uint32_t n_cov, n_wg;
+    CovCounts cc;
     bool failed;
-    // 32-bit loop-closure keys and binary map: phase C's tables lie in front of the sorted quarter
-    // array, so no barrier separates B2 from C (warps that finish their B2 range early go on)
-    const bool c_overlap = COMPACT && !HAS_GRAY && (ST ? SS::c_overlap : (sh.c_overlap != 0));
-    coverage_quarters<KF_THREADS, HAS_GRAY>(s_info, AL, t, ST ? SS::T : sh.T, ST ? SS::MAXP : sh.MAXP,
-                                            ST ? 1u : sh.R0, 0u, s_x, n_cov, n_wg, failed, nullptr, 0,
+    // 32-bit loop-closure keys and a flat B2 (binary map, or the general kernel): phase C's tables lie in
+    // front of the sorted quarter array, so no barrier separates B2 from C (warps that finish their B2
+    // range early go on)
+    const bool c_overlap = COMPACT && (!HAS_GRAY || GENERAL) && (ST ? SS::c_overlap : (sh.c_overlap != 0));
+    coverage_quarters<KF_THREADS, HAS_GRAY, false, GENERAL>(s_info, AL, t, ST ? SS::T : sh.T, ST ? SS::MAXP : sh.MAXP,
+                                            ST ? 1u : sh.R0, 0u, s_x, cc, failed, nullptr, 0,
                                             sh.prefetch != 0, !c_overlap);
     {
-        uint32_t v = n_cov, vw = n_wg;
+        uint32_t v = cc.n_cov, vw = cc.n_wg;
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(FULL, v, o); vw += __shfl_xor_sync(FULL, vw, o); }
         if (lane == 0 && v) atomicAdd(&s_total, v);
         if (HAS_GRAY && lane == 0 && vw) atomicAdd(&s_totalw, vw);
+        if (GENERAL) {
+            uint32_t g4[4] = {cc.n_free0, cc.wg_all, cc.n_gmask, cc.n_all};
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!HAS_GRAY && (k == 1 || k == 2)) continue;
+                uint32_t x = g4[k];
+                #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+                if (lane == 0 && x) atomicAdd(&s_gen[k], x);
+            }
+        }
     }
     if (!c_overlap) __syncthreads();      // B's tables are dead from here
 
@@ -967,7 +1128,8 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     // phase D, first half: -coverage and travel cost need nothing from phase C - one thread of the last
     // warp (no groups to update in pass 4) computes them here instead of at the tail of the CTA
     if (tid == KF_THREADS - 32) {
-        s_cov[0] = failed ? 0u : s_total; s_cov[1] = 0; s_cov[2] = failed ? 0u : s_totalw; s_cov[3] = 0;
+        s_cov[0] = failed ? 0u : s_total; s_cov[1] = (GENERAL && !failed) ? s_gen[0] : 0u;
+        s_cov[2] = failed ? 0u : s_totalw; s_cov[3] = (GENERAL && !failed) ? s_gen[1] : 0u;
         double nc, tr;
         objective_values(A, prm, mc, s_cov, s_cost, s_cost + A, nc, tr);
         s_objv[0] = nc; s_objv[1] = tr;
@@ -1005,6 +1167,19 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     if (lc_out)
         for (int i = tid; i < A * A; i += KF_THREADS) lc_out[(size_t)org * A * A + i] = s_lc[i];
 
+    // the six pixel counters of the general path, as k_coverage writes them (gcp_eval.cu)
+    if (GENERAL && cov_out && tid < 8) {
+        uint32_t v = 0;
+        if (!failed) {
+            if (tid == 0) v = s_total;
+            else if (tid == 1) v = s_gen[0];
+            else if (tid == 2) v = s_totalw;
+            else if (tid == 3) v = s_gen[1];
+            else if (tid == 4) v = s_total + s_gen[2];
+            else if (tid == 5) v = s_gen[3];
+        }
+        cov_out[(size_t)org * 8 + tid] = v;
+    }
     // ------------------------------------------------------------------ phase D: constraints (warp 0)
     if (warp == 0) {
         int ncomp;
@@ -1044,12 +1219,12 @@ k_cov_quarters(uint32_t* step_qinfo, uint32_t P, GcpTables t, int AL, int T, int
     if (org >= P) return;
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) { s_total = 0; s_totalw = 0; }
-    uint32_t n_cov, n_wg;
+    CovCounts cc;
     bool failed;
     coverage_quarters<KF_THREADS, HAS_GRAY, true>(step_qinfo + (size_t)org * AL, AL, t, T, MAXP, R0, DS, smem,
-                                                  n_cov, n_wg, failed,
+                                                  cc, failed,
                                                   rec_all ? rec_all + (size_t)org * rec_cap : nullptr, rec_cap);
-    uint32_t v = n_cov, vw = n_wg;
+    uint32_t v = cc.n_cov, vw = cc.n_wg;
     #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(FULL, v, o); vw += __shfl_xor_sync(FULL, vw, o); }
     if (lane == 0 && v) atomicAdd(&s_total, v);
@@ -1128,33 +1303,42 @@ int launch_coverage_quarters(gcp_ctx* ctx, uint32_t* step_qinfo, uint32_t P, uin
 
 static inline uint32_t al16(uint32_t x) { return (x + 15u) & ~15u; }
 
-static size_t fused_shape(gcp_ctx* ctx, FusedShape& sh, int threads);
-static int fused_threads(gcp_ctx* ctx, FusedShape& sh, size_t* smem);
+static size_t fused_shape(gcp_ctx* ctx, FusedShape& sh, int threads, bool general);
+static int fused_threads(gcp_ctx* ctx, FusedShape& sh, size_t* smem, bool general);
 
 // does the fused kernel's shared-memory footprint fit this (A, L)?
-bool eval_fused_fits(gcp_ctx* ctx)
+bool eval_fused_fits(gcp_ctx* ctx, bool general)
 {
     FusedShape sh;
     size_t smem;
-    return fused_threads(ctx, sh, &smem) != 0;
+    if (general && (!ctx->t.q_info || !ctx->t.gray_qptr || !ctx->t.g_mask_q)) return false;
+    return fused_threads(ctx, sh, &smem, general) != 0;
 }
 
 // 256 threads when at least 3 CTAs fit an SM, else 1024 threads (one CTA per SM, 4x the item
 // store, so long genomes are not split into hash partitions); 0 if neither fits.
-static int fused_threads(gcp_ctx* ctx, FusedShape& sh, size_t* smem)
+// General kernel: 512 threads when 3 CTAs fit, else 1024.
+static int fused_threads(gcp_ctx* ctx, FusedShape& sh, size_t* smem, bool general)
 {
-    *smem = fused_shape(ctx, sh, 256);
+    if (general) {
+        *smem = fused_shape(ctx, sh, 512, true);
+        if (*smem != 0 && *smem * 3 + 3 * 1024 <= (size_t)ctx->max_smem_optin) return 512;
+        *smem = fused_shape(ctx, sh, 1024, true);
+        if (*smem != 0 && *smem <= (size_t)ctx->max_smem_optin) return 1024;
+        return 0;
+    }
+    *smem = fused_shape(ctx, sh, 256, false);
     if (*smem != 0 && *smem * 3 + 3 * 1024 <= (size_t)ctx->max_smem_optin) return 256;
-    *smem = fused_shape(ctx, sh, 1024);
+    *smem = fused_shape(ctx, sh, 1024, false);
     if (*smem != 0 && *smem <= (size_t)ctx->max_smem_optin) return 1024;
-    *smem = fused_shape(ctx, sh, 256);
+    *smem = fused_shape(ctx, sh, 256, false);
     if (*smem != 0 && *smem <= (size_t)ctx->max_smem_optin) return 256;
     return 0;
 }
 
 static bool fused_compact(gcp_ctx* ctx) { return ctx->t.N <= 65534u; }
 
-static size_t fused_shape(gcp_ctx* ctx, FusedShape& sh, int KF_THREADS)
+static size_t fused_shape(gcp_ctx* ctx, FusedShape& sh, int KF_THREADS, bool general)
 {
     const bool compact = fused_compact(ctx);      // u16 genes in shared memory, 32-bit loop-closure keys
     sh.A = ctx->p.num_agents; sh.L = ctx->p.max_dna_len; sh.AL = sh.A * sh.L;
@@ -1162,6 +1346,9 @@ static size_t fused_shape(gcp_ctx* ctx, FusedShape& sh, int KF_THREADS)
     // expected ~1.4 masked sub-tiles x ~1.6 quarters per executed step (C3: 1,940 +- 80 items for 6 x 150
     // steps before the revisited edges are dropped); an organism with more is redone in 2, 4, ... partitions
     int maxp = ctx->cov_maxpairs > 0 ? ctx->cov_maxpairs : (compact ? (49 * sh.AL) / 24 : (9 * sh.AL) / 4);
+    // general kernel: the unmasked store carries ~4.9 quarters per edge (C3: ~3,700 items per organism
+    // after the dedup of 6 x 150 steps) plus two markers per (block, quarter) list (~1,100)
+    if (general && ctx->cov_maxpairs <= 0) maxp = (41 * sh.AL) / 8;
     if (maxp < 256) maxp = 256;
     if (maxp > KF_PPT * KF_THREADS) maxp = KF_PPT * KF_THREADS;
     maxp = (maxp + 7) & ~7;
@@ -1173,7 +1360,7 @@ static size_t fused_shape(gcp_ctx* ctx, FusedShape& sh, int KF_THREADS)
     if (sh.T3 > 65535 || sh.AL > 32767) return 0;                  // 16-bit slots, 15-bit member counts
     sh.DS = ctx->cov_dedup ? (uint32_t)T * 4 : 0u;                   // step-dedup hash set in front of s_cst
     sh.R0 = 1;
-    while ((size_t)sh.R0 * maxp < (size_t)sh.AL * 2 && sh.R0 < 4096) sh.R0 <<= 1;
+    while ((size_t)sh.R0 * maxp < (size_t)sh.AL * (general ? 5 : 2) && sh.R0 < 4096) sh.R0 <<= 1;
     sh.off_cst = (uint32_t)T * 20;                                    // over s_sr / s_pay
     const uint32_t cov_b = (uint32_t)T * 20 + (uint32_t)maxp * 8 + 32;  // + pad for B2's read-ahead
     const uint32_t a_b = sh.off_cst + (uint32_t)sh.AL * 16 + GCP_MAX_AGENTS * 16;    // + one pad entry per row
@@ -1197,20 +1384,50 @@ static bool shape_is(const FusedShape& sh)
 }
 
 int launch_eval_fused(gcp_ctx* ctx, const void* dna, int gene16, uint32_t P, const gcp_eval_out* out,
-                      cudaStream_t st)
+                      cudaStream_t st, bool general)
 {
     if (P == 0) return 0;
-    if (!ctx->have_masked) return gcp_fail(ctx, -1, "masked footprint store not uploaded");
+    if (!general && !ctx->have_masked) return gcp_fail(ctx, -1, "masked footprint store not uploaded");
+    if (general && (!ctx->t.q_info || !ctx->t.gray_qptr || !ctx->t.g_mask_q)) return gcp_fail(ctx, -1, "quarter-item tables of the unmasked store not uploaded");
     FusedShape sh;
     size_t smem;
-    const int threads = fused_threads(ctx, sh, &smem);
+    const int threads = fused_threads(ctx, sh, &smem, general);
     sh.gene16 = gene16;
     if (threads == 0)
         return gcp_fail(ctx, -3, "fused eval kernel needs %zu B shared memory (A*L too large)", smem);
     // a footprint store that outgrows the L2 is prefetched line by line while the items are sorted
     sh.prefetch = ctx->cov_prefetch >= 0 ? ctx->cov_prefetch
-                                         : ((size_t)ctx->m_n_quarters * 128 > ((size_t)96 << 20) ? 1 : 0);
+                                         : ((size_t)(general ? ctx->n_quarters : ctx->m_n_quarters) * 128 > ((size_t)96 << 20) ? 1 : 0);
     StageTimer tm(ctx, 1, st);
+    if (general) {
+        // any coverage_blend, all six pixel counters: one kernel over the unmasked store
+#define GCP_LAUNCH_GENERAL(TH, GRAY, SAL, K32)                                                         \
+    do {                                                                                               \
+        GCP_CUDA(ctx, cudaFuncSetAttribute(k_eval_fused<TH, GRAY, SAL, K32, true>,                     \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        k_eval_fused<TH, GRAY, SAL, K32, true><<<P, TH, smem, st>>>(dna, P, ctx->t, sh, ctx->p, ctx->mc, out->obj, \
+                                                         out->neg_cov, out->dist, out->turn,           \
+                                                         out->lc_mat, out->flags, out->cov);           \
+    } while (0)
+        const bool k32 = fused_compact(ctx), g = ctx->n_gray > 0;
+        // 6 x 200 genes (the reference's six-agent shape): compile-time shared-memory layout
+        const bool st1200 = threads == 512 && sh.AL == 1200 &&
+                            (k32 ? shape_is<StaticShape<1200, true, true>>(sh) : shape_is<StaticShape<1200, false, true>>(sh));
+        if (st1200) {
+            if (g) { if (k32) GCP_LAUNCH_GENERAL(512, true, 1200, true); else GCP_LAUNCH_GENERAL(512, true, 1200, false); }
+            else   { if (k32) GCP_LAUNCH_GENERAL(512, false, 1200, true); else GCP_LAUNCH_GENERAL(512, false, 1200, false); }
+        } else if (threads == 512) {
+            if (g) { if (k32) GCP_LAUNCH_GENERAL(512, true, 0, true); else GCP_LAUNCH_GENERAL(512, true, 0, false); }
+            else   { if (k32) GCP_LAUNCH_GENERAL(512, false, 0, true); else GCP_LAUNCH_GENERAL(512, false, 0, false); }
+        } else {
+            if (g) { if (k32) GCP_LAUNCH_GENERAL(1024, true, 0, true); else GCP_LAUNCH_GENERAL(1024, true, 0, false); }
+            else   { if (k32) GCP_LAUNCH_GENERAL(1024, false, 0, true); else GCP_LAUNCH_GENERAL(1024, false, 0, false); }
+        }
+#undef GCP_LAUNCH_GENERAL
+        ctx->launches++;
+        GCP_CUDA(ctx, cudaGetLastError());
+        return 0;
+    }
 #define GCP_LAUNCH_FUSED_K(TH, GRAY, SAL, K32)                                                         \
     do {                                                                                               \
         GCP_CUDA(ctx, cudaFuncSetAttribute(k_eval_fused<TH, GRAY, SAL, K32>,                           \

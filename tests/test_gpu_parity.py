@@ -35,7 +35,16 @@ def _check_against_golden(eng, z, exact_cov=False):
     pixel counters) and the objectives-only path (the fused kernel when coverage_blend == 1)."""
     dna = z['dna'].astype(np.int32)
     _check_result(eng.evaluate(dna, detail=True, pixel_counts=False), z, exact_cov, False, eng.org_params)
-    _check_result(eng.evaluate(dna), z, exact_cov, True, eng.org_params)
+    general = eng.evaluate(dna)                      # fused kernel over the unmasked store, all pixel counters
+    _check_result(general, z, exact_cov, True, eng.org_params)
+    eng.set_option("fused_eval", 0)                  # the staged general kernels (k_coverage)
+    try:
+        staged = eng.evaluate(dna)
+    finally:
+        eng.set_option("fused_eval", 1)
+    _check_result(staged, z, exact_cov, True, eng.org_params)
+    for name in ("obj", "neg_cov", "dist", "turn", "lc_mat", "flags", "cov"):
+        assert torch.equal(getattr(general, name), getattr(staged, name)), name
     obj_only = eng.evaluate(dna, detail=False)
     assert np.max(np.abs(obj_only.obj.cpu().numpy() - z['obj'])) <= (0 if exact_cov else COV_TOL_GRAY)
 
@@ -384,13 +393,20 @@ def test_fused_kernel_equals_staged_kernels(synth_setup):
         staged = eng.evaluate(dna, detail=True, pixel_counts=False)
     finally:
         eng.set_option("fused_eval", 1)
-    general = eng.evaluate(dna, detail=True, pixel_counts=True)
+    general = eng.evaluate(dna, detail=True, pixel_counts=True)          # fused kernel, unmasked store
+    eng.set_option("fused_eval", 0)
+    try:
+        general_staged = eng.evaluate(dna, detail=True, pixel_counts=True)
+    finally:
+        eng.set_option("fused_eval", 1)
     ok = np.ones(len(dna), dtype=bool)
     ok[[7, 9]] = False
     for name in ("obj", "neg_cov", "dist", "turn", "lc_mat", "flags"):
-        a, b, c = (getattr(r, name).cpu().numpy() for r in (fused, staged, general))
+        a, b, c, d = (getattr(r, name).cpu().numpy() for r in (fused, staged, general, general_staged))
         assert np.array_equal(a[ok], b[ok]), name
         assert np.array_equal(a[ok], c[ok]), name
+        assert np.array_equal(a[ok], d[ok]), name
+    assert np.array_equal(general.cov.cpu().numpy()[ok], general_staged.cov.cpu().numpy()[ok])
     assert fused.flags.cpu().numpy()[7, 3] & 1 and fused.flags.cpu().numpy()[9, 3] & 1
     for k in (0, 1, 300, 301, 400):
         o = fo.calc_obj(ow, dna[k].astype(int))
