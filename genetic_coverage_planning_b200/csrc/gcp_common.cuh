@@ -105,7 +105,7 @@ struct gcp_ctx {
     int force_general = 0;   // testing: never take the pre-masked fast path
     int cov_detail = 1;      // 1: all six counters; 0: only what the objectives need
     int fused_eval = 1;      // 1: objectives-only fast path runs as ONE kernel (gcp_fused.cu)
-    int cov_prefetch = -1;   // -1 auto (store > 96 MiB), 0 / 1: L2 prefetch of the footprint lines in phase B1
+    int cov_prefetch = -1;   // -1 auto (store > 96 MiB: 2), bit 0: L2 prefetch of the footprint lines in phase B1, bit 1: look-ahead in B2
     uint64_t m_n_quarters = 0;
     int rank_algo = 0;       // 0 auto, 1 O(N^2) dominance tiles, 2 sort-based (gcp_rank.cu)
     int sort_onesweep = 1;   // 1: radix sorts of <= 2^20 pairs run one launch per pass (decoupled look-back)

@@ -34,7 +34,8 @@ struct FusedShape {
     uint32_t inv_L;      // ceil(2^32 / L): s / L == __umulhi(s, inv_L) for s < 2^16
     int T, MAXP, T3;
     int gene16;          // chromosome stored as int16 in global memory
-    int prefetch;        // footprint store outgrows the L2: B1 prefetches every quarter line into the L2
+    int prefetch;        // footprint store outgrows the L2: bit 0 = B1 requests every quarter line into the L2 while it
+                         // sorts the items, bit 1 = B2 requests the lines KF_PF_DIST entries ahead of its stream (PF kernels)
     uint32_t R0;
     int c_overlap;       // loop-closure tables (32-bit keys) fit in front of the sorted quarter array
     uint32_t DS;         // slots of the step-dedup hash set (power of two, 0 = skip)
@@ -77,11 +78,16 @@ struct CovCounts { uint32_t n_cov, n_wg, n_free0, wg_all, n_gmask, n_all; };
 // first makes the group AND the finished union with the (g == 0) plane of that quarter, the second with
 // the mask & (g == 0) plane - loaded like any other 128-B line of the stream, four loads in flight.
 // Gray pixels are weighed at the second marker from the per-quarter gray lists.
-template <int KF_THREADS, bool HAS_GRAY, bool BUCKETS = false, bool GENERAL = false>
+#ifndef KF_PF_DIST_N
+#define KF_PF_DIST_N 16
+#endif
+constexpr uint32_t KF_PF_DIST = KF_PF_DIST_N;      // B2 look-ahead of the L2 prefetch, in entries of a group's range (multiple of 8)
+
+template <int KF_THREADS, bool HAS_GRAY, bool BUCKETS = false, bool GENERAL = false, bool PF = false>
 __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const GcpTables& t,
                                                   int T, int MAXP, uint32_t R0, uint32_t DS, unsigned char* s_x,
                                                   CovCounts& cc, bool& failed,
-                                                  uint2* rec = nullptr, uint32_t rec_cap = 0, bool prefetch = false,
+                                                  uint2* rec = nullptr, uint32_t rec_cap = 0, int prefetch = 0,
                                                   bool tail_barrier = true)
 {
     constexpr int KF_NW = KF_THREADS / 32;
@@ -279,7 +285,7 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
                                 const uint2 dsc = __ldg(q_desc + dlo + (j - ex));
                                 // store larger than the L2 (config C5, diverse populations): start the
                                 // DRAM fetch of this quarter's line now, B2 finds it in the L2
-                                if (prefetch) asm volatile("prefetch.global.L2 [%0];" :: "l"(GENERAL ? quarter_at(q_tile, dsc.y) : tile_at(q_tile, dsc.y)));
+                                if (prefetch & 1) asm volatile("prefetch.global.L2 [%0];" :: "l"(GENERAL ? quarter_at(q_tile, dsc.y) : tile_at(q_tile, dsc.y)));
                                 const uint32_t blk = dsc.x >> 2, q = dsc.x & 3u;
                                 const uint32_t key = blk + 1;
                                 uint32_t h = hash_block(blk) >> (32 - logT);
@@ -572,9 +578,22 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
                 // the ranges of a warp's four groups are equal up to the snapping: no guards up to the
                 // shortest one
                 const uint32_t steps_min = __reduce_min_sync(FULL, len) & ~3u;
+                if (PF) {
+                    // store larger than the L2: the group requests the lines of its next KF_PF_DIST entries
+                    // now and keeps that distance in the loop (lane j < 4 takes entry k + KF_PF_DIST + j), so a
+                    // line is on its way from DRAM ~4 iterations before its load and the lines in flight over
+                    // the whole chip stay far below the L2's capacity
+                    #pragma unroll
+                    for (uint32_t u = 0; u < KF_PF_DIST; u += 8)
+                        if (u + l7 < len) asm volatile("prefetch.global.L2 [%0];" :: "l"(tile_at(q_tile, pb[u + l7] & 0x7FFFFFFFu)));
+                }
                 for (; k < steps_min; k += 4) {
                     uint32_t e[4];
                     uint4 v[4];
+                    if (PF) {
+                        const uint32_t kk = k + KF_PF_DIST + l7;
+                        if (l7 < 4 && kk < len) asm volatile("prefetch.global.L2 [%0];" :: "l"(tile_at(q_tile, pb[kk] & 0x7FFFFFFFu)));
+                    }
                     #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         e[j] = pb[k + j];
@@ -701,7 +720,7 @@ struct StaticShape {
 // GENERAL: any coverage_blend and / or the six pixel counters (cov_out) - the union runs over the
 // UNMASKED footprint store with marker entries for the map planes (see coverage_quarters); 512 threads,
 // three CTAs per SM (the unmasked store carries 2.6 x the items of the pre-masked one).
-template <int KF_THREADS, bool HAS_GRAY, int SAL, bool COMPACT, bool GENERAL = false>
+template <int KF_THREADS, bool HAS_GRAY, int SAL, bool COMPACT, bool GENERAL = false, bool PF = false>
 __global__ void __launch_bounds__(KF_THREADS, KF_THREADS == 256 ? ((COMPACT && !HAS_GRAY) ? 6 : 5) : KF_THREADS == 512 ? 3 : 1)
 k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape sh,
              gcp_params prm, gcp_map_consts mc,
@@ -1011,9 +1030,9 @@ k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape
     // front of the sorted quarter array, so no barrier separates B2 from C (warps that finish their B2
     // range early go on)
     const bool c_overlap = COMPACT && (!HAS_GRAY || GENERAL) && (ST ? SS::c_overlap : (sh.c_overlap != 0));
-    coverage_quarters<KF_THREADS, HAS_GRAY, false, GENERAL>(s_info, AL, t, ST ? SS::T : sh.T, ST ? SS::MAXP : sh.MAXP,
+    coverage_quarters<KF_THREADS, HAS_GRAY, false, GENERAL, PF>(s_info, AL, t, ST ? SS::T : sh.T, ST ? SS::MAXP : sh.MAXP,
                                             ST ? 1u : sh.R0, 0u, s_x, cc, failed, nullptr, 0,
-                                            sh.prefetch != 0, !c_overlap);
+                                            sh.prefetch, !c_overlap);
     {
         uint32_t v = cc.n_cov, vw = cc.n_wg;
         #pragma unroll
@@ -1395,9 +1414,11 @@ int launch_eval_fused(gcp_ctx* ctx, const void* dna, int gene16, uint32_t P, con
     sh.gene16 = gene16;
     if (threads == 0)
         return gcp_fail(ctx, -3, "fused eval kernel needs %zu B shared memory (A*L too large)", smem);
-    // a footprint store that outgrows the L2 is prefetched line by line while the items are sorted
+    // a footprint store that outgrows the L2: B2 requests its lines KF_PF_DIST entries ahead of its stream
+    // (C5, organisms spread over the whole map: 6.05 -> 5.53 ms per 65,536; requesting every line while B1
+    // sorts - bit 0 - gains nothing: 740 resident CTAs x 200 KB of lines is more than the L2 holds)
     sh.prefetch = ctx->cov_prefetch >= 0 ? ctx->cov_prefetch
-                                         : ((size_t)(general ? ctx->n_quarters : ctx->m_n_quarters) * 128 > ((size_t)96 << 20) ? 1 : 0);
+                                         : ((size_t)(general ? ctx->n_quarters : ctx->m_n_quarters) * 128 > ((size_t)96 << 20) ? 2 : 0);
     StageTimer tm(ctx, 1, st);
     if (general) {
         // any coverage_blend, all six pixel counters: one kernel over the unmasked store
@@ -1450,6 +1471,21 @@ int launch_eval_fused(gcp_ctx* ctx, const void* dna, int gene16, uint32_t P, con
         done = true;                                                                                   \
     }
     bool done = false;
+    // footprint store beyond the L2 (config C5): the variant whose B2 prefetches ahead of its own stream
+    if ((sh.prefetch & 2) && !gray && threads == 256 && sh.AL == 1200 &&
+        (key32 ? shape_is<StaticShape<1200, true>>(sh) : shape_is<StaticShape<1200, false>>(sh))) {
+#define GCP_LAUNCH_PF(K32)                                                                             \
+    do {                                                                                               \
+        GCP_CUDA(ctx, cudaFuncSetAttribute(k_eval_fused<256, false, 1200, K32, false, true>,           \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        k_eval_fused<256, false, 1200, K32, false, true><<<P, 256, smem, st>>>(dna, P, ctx->t, sh, ctx->p, ctx->mc, \
+                                                         out->obj, out->neg_cov, out->dist, out->turn, \
+                                                         out->lc_mat, out->flags);                     \
+    } while (0)
+        if (key32) GCP_LAUNCH_PF(true); else GCP_LAUNCH_PF(false);
+#undef GCP_LAUNCH_PF
+        done = true;
+    }
     GCP_TRY_STATIC(1200)
     GCP_TRY_STATIC(625)
     GCP_TRY_STATIC(500)

@@ -285,8 +285,9 @@ int gcp_peer_barrier(gcp_ctx* ctx, const gcp_shards* flags, uint32_t rank, uint3
  * (0 = auto); "cov_dedup": 0 = keep revisited edges in the coverage union (same result, more work);
  * "cov_buckets": 0 = long genomes re-scan their items per hash partition instead of bucketing them
  * once; "lc_min_parts": at least this many hash partitions in the long-genome loop-closure kernel;
- * "cov_prefetch": -1 auto / 0 / 1, L2 prefetch of the footprint lines while the fused kernel sorts its
- * items (helps when the footprint store is larger than the L2).
+ * "cov_prefetch": -1 auto (2 when the footprint store is larger than the L2, else 0) / bit 0: L2 prefetch
+ * of the footprint lines while the fused kernel sorts its items / bit 1: the union stream requests its
+ * lines 16 entries ahead (the one that helps on config C5).
  * Unknown names return an error. */
 int gcp_set_option(gcp_ctx* ctx, const char* name, int64_t value);
 
