@@ -153,21 +153,32 @@ int eval_host_narrowed(gcp_ctx* c, const int32_t* dna_host, uint32_t P, double* 
     }
     beg.push_back(P);
     const size_t nchunks = beg.size() - 1;
+    // work units: granules of GRAN genes handed out IN ORDER from one atomic counter, so the chunks are
+    // finished front to back by whichever threads are free - a worker that loses its core for a while
+    // holds back one granule, not its share of every chunk
+    constexpr size_t GRAN = 32768;
+    std::vector<size_t> gbeg(nchunks + 1, 0);
+    for (size_t k = 0; k < nchunks; ++k)
+        gbeg[k + 1] = gbeg[k] + (((size_t)(beg[k + 1] - beg[k]) * AL + GRAN - 1) / GRAN);
+    const size_t ngran = gbeg[nchunks];
     std::vector<std::atomic<int>> done(nchunks);
     for (auto& d : done) d.store(0, std::memory_order_relaxed);
-    const int T = pool->T;
-    pool->start([&, T](int tid, int) {
-        for (size_t k = 0; k < nchunks; ++k) {
+    std::atomic<size_t> next{0};
+    pool->start([&](int, int) {
+        size_t k = 0;
+        for (;;) {
+            const size_t i = next.fetch_add(1, std::memory_order_relaxed);
+            if (i >= ngran) break;
+            while (i >= gbeg[k + 1]) ++k;                                   // i only grows
             const size_t g0 = (size_t)beg[k] * AL, g1 = (size_t)beg[k + 1] * AL;
-            const size_t span = ((g1 - g0) / T + 15) & ~(size_t)15;        // 16-gene granules keep the stores aligned
-            const size_t a = g0 + (size_t)tid * span, b = a + span;
-            if (a < g1) narrow_i32_i16(dna_host + a, stage + a, (b < g1 ? b : g1) - a);
+            const size_t a = g0 + (i - gbeg[k]) * GRAN, b = a + GRAN;
+            narrow_i32_i16(dna_host + a, stage + a, (b < g1 ? b : g1) - a);
             done[k].fetch_add(1, std::memory_order_release);
         }
     });
     int rc = 0;
     for (size_t k = 0; k < nchunks && rc == 0; ++k) {
-        while (done[k].load(std::memory_order_acquire) < T) _mm_pause();
+        while (done[k].load(std::memory_order_acquire) < (int)(gbeg[k + 1] - gbeg[k])) _mm_pause();
         const uint32_t o0 = beg[k], n = beg[k + 1] - beg[k];
         cudaStream_t st = c->hstream[k % NBUF];
         char* base = reinterpret_cast<char*>(c->hstage_dev[k % NBUF]);

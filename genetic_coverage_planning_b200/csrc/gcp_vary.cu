@@ -817,7 +817,14 @@ __device__ __forceinline__ bool muterpolate_row(G* r, uint32_t gid, const GcpTab
             if (ndel > 0) {
                 const int new_lo = idx1 + 2;                           // <= gap_lo always
                 GCP_DASSERT(new_lo <= gap_lo && gap_lo - 1 + gap_len < L);
-                for (int x = gap_lo - 1; x >= new_lo; --x) r[x + gap_len] = r[x];   // move the gap left
+                // move the gap left: four independent reads, then their writes (a move to the right walked
+                // from the right end: a block that is read before it is written can never be clobbered)
+                int x = gap_lo - 1;
+                for (; x - 3 >= new_lo; x -= 4) {
+                    const G m0 = r[x], m1 = r[x - 1], m2 = r[x - 2], m3 = r[x - 3];
+                    r[x + gap_len] = m0; r[x - 1 + gap_len] = m1; r[x - 2 + gap_len] = m2; r[x - 3 + gap_len] = m3;
+                }
+                for (; x >= new_lo; --x) r[x + gap_len] = r[x];
                 gap_lo = new_lo;
                 gap_len += ndel;
             }
@@ -825,13 +832,26 @@ __device__ __forceinline__ bool muterpolate_row(G* r, uint32_t gid, const GcpTab
         }
     }
     if (changed) {                                                     // close the gap, strip -1 (:307)
-        int w = 0;
-        for (int x = 0; x < L; ++x) {
-            if (x >= gap_lo && x < gap_lo + gap_len) continue;
+        // below the gap nothing moved unless a -1 hole sits there (w == x: nothing to write); above it the
+        // survivors slide left - four reads at a time, their writes land at or below what has been read
+        int w = 0, x = 0;
+        for (; x < gap_lo; ++x) {
+            const G g = r[x];
+            if (g != (G)-1) { if (w != x) r[w] = g; ++w; }
+        }
+        x = gap_lo + gap_len;
+        for (; x + 3 < L; x += 4) {
+            const G g0 = r[x], g1 = r[x + 1], g2 = r[x + 2], g3 = r[x + 3];
+            if (g0 != (G)-1) r[w++] = g0;
+            if (g1 != (G)-1) r[w++] = g1;
+            if (g2 != (G)-1) r[w++] = g2;
+            if (g3 != (G)-1) r[w++] = g3;
+        }
+        for (; x < L; ++x) {
             const G g = r[x];
             if (g != (G)-1) r[w++] = g;
         }
-        for (int x = w; x < L; ++x) r[x] = (G)-1;
+        for (x = w; x < L; ++x) r[x] = (G)-1;
     }
     return changed;
 }
