@@ -1336,12 +1336,12 @@ bool eval_fused_fits(gcp_ctx* ctx, bool general)
 
 // 256 threads when at least 3 CTAs fit an SM, else 1024 threads (one CTA per SM, 4x the item
 // store, so long genomes are not split into hash partitions); 0 if neither fits.
-// General kernel: 512 threads when 3 CTAs fit, else 1024.
+// General kernel: 512 threads when at least 2 CTAs fit, else 1024.
 static int fused_threads(gcp_ctx* ctx, FusedShape& sh, size_t* smem, bool general)
 {
     if (general) {
         *smem = fused_shape(ctx, sh, 512, true);
-        if (*smem != 0 && *smem * 3 + 3 * 1024 <= (size_t)ctx->max_smem_optin) return 512;
+        if (*smem != 0 && *smem * 2 + 2 * 1024 <= (size_t)ctx->max_smem_optin) return 512;
         *smem = fused_shape(ctx, sh, 1024, true);
         if (*smem != 0 && *smem <= (size_t)ctx->max_smem_optin) return 1024;
         return 0;

@@ -127,10 +127,13 @@ int gcp_set_params(gcp_ctx* ctx, const gcp_params* p);
  * dna: dev int32 [P][A][L], -1 padded (Organism._dna, geneticalgorithm.py:335-344).
  *
  * Dispatch: with the pre-masked footprints uploaded, coverage_blend == 1 and out->cov == NULL the
- * whole evaluation is ONE kernel (k_eval_fused: binary and gray maps, genomes up to ~7,000 genes;
- * scratch may then be NULL).  Otherwise the staged kernels run (all six pixel counters, blend < 1,
- * longer genomes; loop closures switch to a radix-sort formulation when A*L outgrows shared
- * memory) and scratch_dev must hold gcp_eval_scratch_bytes(n_org) bytes.  Results are identical. */
+ * whole evaluation is ONE kernel (k_eval_fused: binary and gray maps, genomes up to ~7,000 genes).
+ * Any other request - coverage_blend < 1 (mappy.py:364), the six pixel counters of out->cov - runs the
+ * GENERAL variant of the same kernel over the unmasked footprints (genomes up to ~6,000 genes).
+ * Longer genomes, and every request under gcp_set_option("fused_eval", 0), run the staged kernels
+ * (loop closures switch to a hash-partitioned / radix-sort formulation when A*L outgrows shared
+ * memory).  scratch_dev must hold gcp_eval_scratch_bytes(n_org) bytes whenever the staged kernels
+ * may run (the fused kernels do not touch it).  Results are identical on every route. */
 size_t gcp_eval_scratch_bytes(gcp_ctx* ctx, uint32_t n_org);
 int    gcp_eval(gcp_ctx* ctx, const int32_t* dna_dev, uint32_t n_org,
                 const gcp_eval_out* out, void* scratch_dev, size_t scratch_bytes,
