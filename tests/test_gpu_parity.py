@@ -634,3 +634,54 @@ def test_long_genomes_partition_fallback(synth_setup):
         assert det['obj'][0] == full.obj.cpu().numpy()[k, 0]
         assert det['obj'][1] == full.obj.cpu().numpy()[k, 1]
         assert np.array_equal(det['lc_mat'].astype(np.int32), full.lc_mat.cpu().numpy()[k])
+
+
+@pytest.mark.parametrize("A,L,walk", [(3, 640, 600), (6, 640, 600), (6, 200, 150), (2, 97, 90)])
+def test_general_fused_kernel_partitions_and_cta_sizes(synth_setup, A, L, walk):
+    """The general fused kernel (all six pixel counters, blend 0.3) beyond its compile-time shape: 512
+    threads with two hash partitions (3 x 640 genes), 1,024 threads with two partitions (6 x 640), the
+    static 6 x 200 layout and a small runtime shape - every output equal to the staged general kernels,
+    objectives equal to the oracle."""
+    from genetic_coverage_planning_b200 import synth, worlds
+    from genetic_coverage_planning_b200.engine import FitnessEngine
+    sw, pw, ow, op, eng, starts = synth_setup
+    st = synth.spread_starts(sw.xy, A, 1024)
+    op2 = worlds.org_params_for(dict(L=L), st)
+    op2.update(min_solo_lcs=0, min_comb_lcs=1)
+    eng2 = FitnessEngine(pw, op2, num_agents=A)
+    eng2.set_params(op2, blend=0.3)
+    dna = synth.random_walk_population(sw.xy, sw.row_ptr, sw.col, st, 40, walk, L, seed=31 + A).astype(np.int32)
+    fused = eng2.evaluate(dna)
+    eng2.set_option("fused_eval", 0)
+    try:
+        staged = eng2.evaluate(dna)
+    finally:
+        eng2.set_option("fused_eval", 1)
+    assert not fused.flags.cpu().numpy()[:, 3].any()
+    for name in ("obj", "neg_cov", "dist", "turn", "lc_mat", "flags", "cov"):
+        assert torch.equal(getattr(fused, name), getattr(staged, name)), name
+    mp = dict(sw.map_params)
+    mp['coverage_blend'] = 0.3
+    ow2 = World(sw.img, sw.xy, sw.row_ptr, sw.col, sw.edge_poly, sw.edge_theta, sw.edge_dist, mp, op2,
+                name="synth-general")
+    obj = fused.obj.cpu().numpy()
+    for k in range(2):
+        o = fo.calc_obj(ow2, dna[k].astype(int))
+        assert o[0] == obj[k, 0] and o[1] == obj[k, 1]
+
+
+def test_prefetch_variants_of_the_fused_kernel(synth_setup):
+    """cov_prefetch selects how the fused kernel requests footprint lines ahead of use when the store
+    outgrows the L2 (bit 1: look-ahead inside the union stream, its own kernel variant): same bits."""
+    from genetic_coverage_planning_b200 import synth
+    sw, pw, ow, op, eng, starts = synth_setup
+    dna = synth.random_walk_population(sw.xy, sw.row_ptr, sw.col, starts, 300, 150, 200, seed=77).astype(np.int32)
+    want = eng.evaluate(dna, detail=True, pixel_counts=False)
+    try:
+        for pf in (1, 2, 3, 0):
+            eng.set_option("cov_prefetch", pf)
+            got = eng.evaluate(dna, detail=True, pixel_counts=False)
+            for name in ("obj", "neg_cov", "dist", "turn", "lc_mat", "flags"):
+                assert torch.equal(getattr(got, name), getattr(want, name)), (pf, name)
+    finally:
+        eng.set_option("cov_prefetch", -1)
