@@ -630,17 +630,19 @@ def main():
             return dt
         use16 = fast and w.N <= 32767
         dna_h32 = dna.cpu().pin_memory()
+        # the library narrows int32 genes to int16 on the host where that pays (one rank per host, >= 6 worker threads)
+        narrowed = bool(use16 and eng.lib.gcp_host_narrow_active(eng.ctx))
         dt32 = e2e_leg(dna_h32)                      # the call as a user makes it (library defaults)
         dt16 = e2e_leg(dna.to(torch.int16).cpu().pin_memory()) if use16 else None
-        dt32_wire = None
-        if use16:                                    # the same call with the host-side narrowing switched off
-            eng.set_option("host_narrow", 0)
-            dt32_wire = e2e_leg(dna_h32)
-            eng.set_option("host_narrow", 1)
+        dt32_other = None
+        if use16:                                    # the same call with the host-side narrowing forced the other way
+            eng.set_option("host_narrow", 0 if narrowed else 1)
+            dt32_other = e2e_leg(dna_h32)
+            eng.set_option("host_narrow", -1)
         del dna_h32
         host_cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
         e2e = {"value": P_global / dt32, "unit": UNIT,
-               "h2d_bytes_per_step": int(P * A * L * (2 if use16 else 4)), "d2h_bytes_per_step": int(P * 20),
+               "h2d_bytes_per_step": int(P * A * L * (2 if narrowed else 4)), "d2h_bytes_per_step": int(P * 20),
                "host_bytes_read_per_step": int(P * A * L * 4),
                "ms_per_step": dt32 * 1e3,
                "api": "FitnessEngine.evaluate_host -> gcp_eval_host (pinned host int32 chromosomes in, "
@@ -648,11 +650,20 @@ def main():
                       "its own shard of the population" +
                       ("; the waypoint ids fit int16, so worker threads of the library narrow the int32 genes "
                        "on the way (inside the timed call): half the PCIe bytes; %d host cores for %d rank(s)"
-                       % (host_cores, world_size) if use16 else "")}
-        if dt32_wire is not None:
-            e2e["int32_on_the_wire"] = {"value": P_global / dt32_wire, "ms_per_step": dt32_wire * 1e3,
-                                        "h2d_bytes_per_step": int(P * A * L * 4),
-                                        "note": "gcp_set_option(host_narrow, 0): the int32 genes cross PCIe as they are"}
+                       % (host_cores, world_size) if narrowed else
+                       ("; int32 genes on the wire: with %d ranks on this host (%d cores) the library does not "
+                        "narrow them on the host (the GPUs' DMA engines together read host memory faster than "
+                        "the cores convert it)" % (world_size, host_cores) if use16 else ""))}
+        if dt32_other is not None:
+            if narrowed:
+                e2e["int32_on_the_wire"] = {"value": P_global / dt32_other, "ms_per_step": dt32_other * 1e3,
+                                            "h2d_bytes_per_step": int(P * A * L * 4),
+                                            "note": "gcp_set_option(host_narrow, 0): the int32 genes cross PCIe as they are"}
+            else:
+                e2e["narrowed_on_host"] = {"value": P_global / dt32_other, "ms_per_step": dt32_other * 1e3,
+                                           "h2d_bytes_per_step": int(P * A * L * 2),
+                                           "note": "gcp_set_option(host_narrow, 1): worker threads narrow the genes to int16 "
+                                                   "inside the call (what a single rank per host does by default)"}
         if dt16 is not None:
             e2e["int16_genes"] = {"value": P_global / dt16, "ms_per_step": dt16 * 1e3,
                                   "h2d_bytes_per_step": int(P * A * L * 2),

@@ -82,6 +82,7 @@ SIGNATURES = {
     "gcp_eval_host16": (C.c_int, [_vp, _vp, _u32, _vp, _vp]),
     "gcp_eval16": (C.c_int, [_vp, _vp, _u32, C.POINTER(GcpEvalOut), _vp]),
     "gcp_eval16_available": (C.c_int, [_vp]),
+    "gcp_host_narrow_active": (C.c_int, [_vp]),
     "gcp_rank_scratch_bytes": (C.c_size_t, [_vp, _u32]),
     "gcp_maximin": (C.c_int, [_vp, _vp, _u32, C.c_double, _u32, _u32, _vp, _vp, _vp,
                               C.c_size_t, _vp]),

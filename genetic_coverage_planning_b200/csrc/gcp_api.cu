@@ -448,6 +448,20 @@ int gcp_eval16_available(gcp_ctx* c)
 static int eval_host_impl(gcp_ctx* c, const void* dna_host, int gene16, uint32_t P, double* obj_host,
                           uint8_t* flags_host);
 
+static bool narrow_on_host(gcp_ctx* c)
+{
+    return c->t.N <= 32767u &&
+           (c->host_narrow > 0 || (c->host_narrow < 0 && (c->host_threads > 0 || host_narrow_auto())));
+}
+
+int gcp_host_narrow_active(gcp_ctx* c)
+{
+    if (!c || ready(c)) return 0;
+    gcp_eval_out probe;
+    memset(&probe, 0, sizeof(probe));
+    return (fast_path(c, &probe) && narrow_on_host(c)) ? 1 : 0;
+}
+
 int gcp_eval_host(gcp_ctx* c, const int32_t* dna_host, uint32_t P, double* obj_host,
                   uint8_t* flags_host)
 {
@@ -482,7 +496,7 @@ static int eval_host_impl(gcp_ctx* c, const void* dna_host, int gene16, uint32_t
     if (gene16 && !fused)
         return gcp_fail(c, -1, "gcp_eval_host16: only the fused objectives path takes int16 genes");
     // int32 genes of a world whose ids fit int16: host threads narrow them on the way (gcp_host.cu)
-    if (!gene16 && fused && c->host_narrow && c->t.N <= 32767u)
+    if (!gene16 && fused && narrow_on_host(c))
         return eval_host_narrowed(c, reinterpret_cast<const int32_t*>(dna_host), P, obj_host, flags_host);
     const size_t dna_b = align256((size_t)chunk * A * L * gsz);
     const size_t scr_b = fused ? 256 : align256(gcp_eval_scratch_bytes(c, chunk));

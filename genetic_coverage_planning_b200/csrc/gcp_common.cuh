@@ -85,7 +85,8 @@ struct gcp_ctx {
     void* host_pool = nullptr;
     void* host_stage16 = nullptr; size_t host_stage16_bytes = 0;
     void* hstage_dev[3] = {}; size_t hstage_dev_bytes = 0;
-    int host_narrow = 1;     // 1: gcp_eval_host narrows int32 genes to int16 on the host when N <= 32767 (fused path)
+    int host_narrow = -1;    // gcp_eval_host narrows int32 genes to int16 on the host when N <= 32767 (fused path): 1 always, 0 never,
+                             // -1 auto = one rank on this host and >= 6 worker threads (gcp_host.cu: host_narrow_auto)
     int host_threads = 0;    // worker threads of the narrowing (0 = auto: cores / LOCAL_WORLD_SIZE - 1, at most 12)
     void* vary_scratch = nullptr; size_t vary_scratch_bytes = 0;   // mutation row list (gcp_vary.cu)
     // long-genome scratch, one set per pipeline slot: gcp_eval_host overlaps neighbouring chunks on
@@ -146,6 +147,7 @@ int launch_eval_fused(gcp_ctx*, const void* dna, int gene16, uint32_t P, const g
 bool eval_fused_fits(gcp_ctx*, bool general = false);
 int eval_host_narrowed(gcp_ctx*, const int32_t* dna_host, uint32_t P, double* obj_host, uint8_t* flags_host);
 void gcp_host_free(gcp_ctx*);
+bool host_narrow_auto();
 int launch_loop_closures_big(gcp_ctx*, const int32_t* dna, uint32_t P, const double* dist,
                              const double* turn, const uint32_t* cov, int32_t* lc, double* obj,
                              double* neg_cov, uint8_t* flags, cudaStream_t);

@@ -145,6 +145,9 @@ int    gcp_eval16(gcp_ctx* ctx, const int16_t* dna_dev, uint32_t n_org, const gc
                   void* stream);
 /* 1 if gcp_eval16 can run with the tables / parameters uploaded so far, else 0. */
 int    gcp_eval16_available(gcp_ctx* ctx);
+/* 1 if gcp_eval_host would narrow its int32 genes to int16 on the host with the current tables,
+ * parameters and options (see "host_narrow" below), else 0. */
+int    gcp_host_narrow_active(gcp_ctx* ctx);
 /* Individual stages (same buffers; used by tests / profiling). edge_ids: dev u32 [P][A][L];
  * step_info (optional, needs the masked store): dev u32 [P][A][L], per step the masked
  * sub-tile range of its edge (first | count<<28), 0 where no step is executed. */
@@ -276,9 +279,11 @@ int gcp_peer_barrier(gcp_ctx* ctx, const gcp_shards* flags, uint32_t rank, uint3
 
 /* ---- tuning / testing knobs (defaults are right for production) ---------------------
  * "rank_algo": 0 auto, 1 O(N^2) dominance-matrix tiles, 2 sort-based O(N log N) (both exact);
- * "host_narrow": 1 (default) gcp_eval_host narrows int32 genes to int16 with host threads on the way to
- * the GPU when the waypoint ids fit (N <= 32767) - half the PCIe bytes, same results; "host_threads":
- * worker threads of that conversion (0 = auto: cores / LOCAL_WORLD_SIZE - 1, at most 12);
+ * "host_narrow": gcp_eval_host narrows int32 genes to int16 with host threads on the way to the GPU
+ * when the waypoint ids fit (N <= 32767) - half the PCIe bytes, same results: 1 always, 0 never, -1
+ * (default) when it pays, i.e. one rank on this host (LOCAL_WORLD_SIZE) and at least six worker
+ * threads (gcp_host_narrow_active tells); "host_threads": worker threads of that conversion
+ * (0 = auto: cores / LOCAL_WORLD_SIZE - 1, at most 12);
  * "sort_onesweep": 1 (default) radix sorts of <= 2^20 pairs take one launch per pass (decoupled
  * look-back), 0 = histogram / scan / scatter launches per pass (same order, the cross-check);
  * "force_general": never take the pre-masked coverage fast path; "fused_eval": 0 = staged kernels;

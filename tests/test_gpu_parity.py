@@ -586,7 +586,7 @@ def test_host_call_narrows_int32_genes_on_the_way(synth_setup):
             try:
                 obj_h, flags_h = eng.evaluate_host(pinned)
             finally:
-                eng.set_option("host_narrow", 1)
+                eng.set_option("host_narrow", -1)
                 eng.set_option("host_threads", 0)
             ok = wf[:, 3] == 0                       # objectives of flagged organisms are unspecified
             assert np.array_equal(flags_h.numpy()[:, 3] & 1, wf[:, 3] & 1), (P, narrow, threads)
