@@ -101,8 +101,10 @@ struct gcp_ctx {
     int cov_table = 0, cov_maxpairs = 0;
     int cov_buckets = 1;     // 1: long genomes bucket their items by hash partition once (else: R scanning passes)
     int cov_dedup = 1;       // 1: revisited edges are dropped before the coverage union (phase B0)
+    int cov_split = 1;       // 1: long genomes run their hash partitions as work items of small CTAs (k_cov_bucket / k_cov_part)
     int cov_threads = 0;     // tuning: CTA size of k_cov_quarters (256 / 512 / 1024; 0 = auto)
     int lc_min_parts = 0;    // tuning: at least this many hash partitions in k_loop_closures_part
+    int lc_split = 1;        // 1: long genomes run their loop-closure partitions as work items of small CTAs (k_lc_bucket / k_lc_part)
     int force_general = 0;   // testing: never take the pre-masked fast path
     int cov_detail = 1;      // 1: all six counters; 0: only what the objectives need
     int fused_eval = 1;      // 1: objectives-only fast path runs as ONE kernel (gcp_fused.cu)

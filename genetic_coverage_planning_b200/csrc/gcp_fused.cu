@@ -88,8 +88,11 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
                                                   int T, int MAXP, uint32_t R0, uint32_t DS, unsigned char* s_x,
                                                   CovCounts& cc, bool& failed,
                                                   uint2* rec = nullptr, uint32_t rec_cap = 0, int prefetch = 0,
-                                                  bool tail_barrier = true)
+                                                  bool tail_barrier = true, uint32_t pre_m = 0xFFFFFFFFu)
 {
+    // pre_m (BUCKETS only): `rec` already holds the pre_m item descriptors of ONE hash partition of the
+    // organism (k_cov_bucket wrote them): a single pass over them, no dedup, no retry - an overflow of the
+    // item store or of the block table is reported through `failed` and the caller redoes the organism.
     constexpr int KF_NW = KF_THREADS / 32;
     constexpr uint32_t NM = GENERAL ? 2u : 0u;                 // marker entries behind every list
     const uint2* const q_desc = GENERAL ? t.q_desc : t.m_q_desc;
@@ -137,7 +140,12 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
         //      one shared atomic), so that every partition pass below reads its own items
         //      linearly instead of re-scanning and filtering all of them
         bool bucketed = false;
-        if (BUCKETS && R > 1 && R <= 64 && rec != nullptr) {
+        if (BUCKETS && pre_m != 0xFFFFFFFFu) {
+            if (tid == 0) { s_pbase[0] = 0; s_pbase[1] = pre_m; }
+            bucketed = true;
+            __syncthreads();
+        }
+        if (BUCKETS && pre_m == 0xFFFFFFFFu && R > 1 && R <= 64 && rec != nullptr) {
             auto scan_items = [&](auto&& fn) {
                 for (int s0 = warp * 32; s0 < AL; s0 += KF_NW * 32) {
                     const int s = s0 + lane;
@@ -675,6 +683,7 @@ __device__ __forceinline__ void coverage_quarters(uint32_t* info, int AL, const 
             if ((HAS_GRAY && !GENERAL) || tail_barrier || R > 1) __syncthreads();
         }
         if (!overflow) break;
+        if (BUCKETS && pre_m != 0xFFFFFFFFu) { failed = true; break; }
         R <<= 1;
         if (R > 4096) { failed = true; break; }
     }
@@ -1230,13 +1239,20 @@ template <int KF_THREADS, bool HAS_GRAY>
 __global__ void __launch_bounds__(KF_THREADS, KF_THREADS == 256 ? 5 : KF_THREADS == 512 ? 2 : 1)
 k_cov_quarters(uint32_t* step_qinfo, uint32_t P, GcpTables t, int AL, int T, int MAXP,
                uint32_t R0, uint32_t DS, uint2* rec_all, uint32_t rec_cap,
-               uint32_t* __restrict__ cov, uint8_t* __restrict__ flags)
+               uint32_t* __restrict__ cov, uint8_t* __restrict__ flags,
+               const uint8_t* __restrict__ fix = nullptr, const uint32_t* __restrict__ acc = nullptr)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint32_t s_total, s_totalw;
     const uint32_t org = blockIdx.x;
     if (org >= P) return;
     const int tid = threadIdx.x, lane = tid & 31;
+    // split path (k_cov_bucket -> k_cov_part): the partition CTAs have summed this organism's counts
+    // unless one of them overflowed (fix[org]) - then it is redone here, in one CTA, exactly
+    if (fix && !fix[org]) {
+        if (tid < 8) cov[(size_t)org * 8 + tid] = (tid == 0 || tid == 4) ? acc[(size_t)org * 2] : (tid == 2 ? acc[(size_t)org * 2 + 1] : 0u);
+        return;
+    }
     if (tid == 0) { s_total = 0; s_totalw = 0; }
     CovCounts cc;
     bool failed;
@@ -1254,6 +1270,173 @@ k_cov_quarters(uint32_t* step_qinfo, uint32_t P, GcpTables t, int AL, int T, int
         cov[(size_t)org * 8 + tid] = (tid == 0 || tid == 4) ? n : (tid == 2 ? w : 0u);
     }
     if (tid == 0 && failed && flags) flags[(size_t)org * 4 + 3] |= 2;
+}
+
+
+// ============================================================================
+// Long genomes, split form.  The monolithic k_cov_quarters keeps one 1,024-thread CTA per organism (one
+// per SM) busy with R sequential hash partitions, each a chain of short barrier-separated phases: issue
+// slots ~50 % busy.  Here the partitions of ALL organisms become independent work items for small CTAs
+// (256 threads, six per SM - the regime of the fused kernel's phase B):
+//   k_cov_bucket  one CTA per organism: revisited steps dropped, items counted, K = 2^k partitions chosen
+//                 for ~cap items each, item descriptors scattered by partition into the organism's stretch of
+//                 the scratch array (partition r owns the r-th K-th of it); {K, items per partition} to hdr, K work
+//                 items {organism, partition} to the list
+//   k_cov_part    persistent CTAs take work items off the list: one coverage_quarters pass over the
+//                 bucket (counting sort by (block, quarter), flat union, popcount), counts added to acc[org]
+//   k_cov_quarters(fix, acc)  writes cov[] from acc; an organism whose bucket overflowed is redone monolithically
+// ============================================================================
+constexpr int CB_THREADS = 1024;
+constexpr uint32_t CB_MAXK = 64;
+constexpr uint32_t CB_HDR = CB_MAXK + 2;         // words per organism: K, items of partition 0 .. K-1
+
+__global__ void __launch_bounds__(CB_THREADS, 1)
+k_cov_bucket(uint32_t* step_qinfo, uint32_t P, GcpTables t, int AL, uint32_t DS, uint32_t cap,
+             uint2* __restrict__ rec_all, uint32_t rec_cap, uint32_t* __restrict__ hdr_all,
+             uint32_t* __restrict__ work /* [0] = items listed, [1] = ticket, [2..] = organism << 6 | partition */,
+             uint8_t* __restrict__ fix)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int NW = CB_THREADS / 32;
+    __shared__ uint32_t s_pcnt[CB_MAXK], s_wsum[NW], s_K, s_wbase;
+    const uint32_t org = blockIdx.x;
+    if (org >= P) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t* info = step_qinfo + (size_t)org * AL;
+    uint2* rec = rec_all + (size_t)org * rec_cap;
+    uint32_t* hdr = hdr_all + (size_t)org * CB_HDR;
+    // revisited edges add nothing to the union (see coverage_quarters B0)
+    if (DS) {
+        uint32_t* s_set = reinterpret_cast<uint32_t*>(smem);
+        const int sh_ds = __clz(DS) + 1;
+        for (int i = tid; i < (int)DS; i += CB_THREADS) s_set[i] = 0u;
+        __syncthreads();
+        for (int s = tid; s < AL; s += CB_THREADS) {
+            const uint32_t inf = info[s];
+            if (!inf) continue;
+            const uint32_t h = (inf * 0x9E3779B1u) >> sh_ds;
+            if (atomicExch(&s_set[h], inf) == inf) info[s] = 0u;
+        }
+    }
+    if (tid < (int)CB_MAXK) s_pcnt[tid] = 0;
+    __syncthreads();
+    // items of the organism -> number of partitions
+    uint32_t mine = 0;
+    for (int s = tid; s < AL; s += CB_THREADS) mine += info[s] >> 26;
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(FULL, mine, o);
+    if (lane == 0) s_wsum[warp] = mine;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t total = 0;
+        for (int w2 = 0; w2 < NW; ++w2) total += s_wsum[w2];
+        uint32_t K = 1;
+        while ((uint64_t)K * cap < total && K < CB_MAXK) K <<= 1;
+        if (total > rec_cap) K = 0;                       // more items than the scratch holds: monolithic pass
+        s_K = K;
+    }
+    __syncthreads();
+    const uint32_t K = s_K;
+    if (K == 0) {
+        if (tid == 0) { hdr[0] = 0; fix[org] = 1; }
+        return;
+    }
+    auto scan_items = [&](auto&& fn) {
+        for (int s0 = warp * 32; s0 < AL; s0 += NW * 32) {
+            const int s = s0 + lane;
+            uint32_t lo = 0, n = 0;
+            if (s < AL) { const uint32_t inf = info[s]; lo = inf & 0x03FFFFFFu; n = inf >> 26; }
+            uint32_t incl = n;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const uint32_t total = __shfl_sync(FULL, incl, 31);
+            const uint32_t excl = incl - n;
+            for (uint32_t j0 = 0; j0 < total; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                int a = 0, b = 31;
+                #pragma unroll
+                for (int it = 0; it < 5; ++it) {
+                    const int mid = (a + b) >> 1;
+                    const uint32_t v = __shfl_sync(FULL, incl, mid);
+                    if (v > j) b = mid; else a = mid + 1;
+                }
+                a = min(a, 31);
+                const uint32_t ex = __shfl_sync(FULL, excl, a), dlo = __shfl_sync(FULL, lo, a);
+                uint2 dsc = make_uint2(0, 0);
+                if (j < total) dsc = __ldg(t.m_q_desc + dlo + (j - ex));
+                fn(j < total, dsc);
+            }
+        }
+    };
+    // ONE pass: partition r owns the stretch [r * region, (r + 1) * region) of the organism's scratch, an item
+    // takes the next free place of its partition (lanes of a warp that hit the same partition share one
+    // shared-memory atomic).  A partition that outgrows its stretch could not be sorted by a partition CTA
+    // either (region >= its item store whenever K >= 2): the organism is redone monolithically.
+    const uint32_t region = rec_cap / K;
+    scan_items([&](bool valid, uint2 dsc) {
+        const uint32_t p = valid ? (part_block(dsc.x >> 2) & (K - 1)) : KF_NIL;
+        const uint32_t peers = __match_any_sync(FULL, p);
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (valid && lane == leader) base = atomicAdd(&s_pcnt[p], (uint32_t)__popc(peers));
+        base = __shfl_sync(FULL, base, leader);
+        const uint32_t at = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        if (valid && at < region) rec[(size_t)p * region + at] = dsc;
+    });
+    __syncthreads();
+    if (tid == 0) {
+        bool over = false;
+        hdr[0] = K;
+        for (uint32_t r = 0; r < K; ++r) { hdr[1 + r] = s_pcnt[r]; over |= s_pcnt[r] > region; }
+        if (over) { hdr[0] = 0; fix[org] = 1; }
+        else s_wbase = atomicAdd(&work[0], K);
+        s_K = over ? 0u : K;
+    }
+    __syncthreads();
+    if (s_K && tid < (int)K) work[2 + s_wbase + tid] = (org << 6) | (uint32_t)tid;
+}
+
+template <bool HAS_GRAY>
+__global__ void __launch_bounds__(256, 6)
+k_cov_part(GcpTables t, int T, int MAXP, uint2* __restrict__ rec_all, uint32_t rec_cap,
+           const uint32_t* __restrict__ hdr_all, uint32_t* __restrict__ work, uint32_t* __restrict__ acc,
+           uint8_t* __restrict__ fix)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint32_t s_w, s_total, s_totalw;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t n_work = work[0];
+    for (;;) {
+        __syncthreads();                                  // the previous item's readers are done
+        if (tid == 0) { s_w = atomicAdd(&work[1], 1u); s_total = 0; s_totalw = 0; }
+        __syncthreads();
+        const uint32_t w = s_w;
+        if (w >= n_work) break;
+        const uint32_t item = work[2 + w], org = item >> 6, r = item & 63u;
+        const uint32_t* hdr = hdr_all + (size_t)org * CB_HDR;
+        const uint32_t b0 = r * (rec_cap / hdr[0]), m = hdr[1 + r];
+        if (m == 0) continue;
+        CovCounts cc;
+        bool failed;
+        coverage_quarters<256, HAS_GRAY, true>(nullptr, 0, t, T, MAXP, 1u, 0u, smem, cc, failed,
+                                               rec_all + (size_t)org * rec_cap + b0, 0u, 0, true, m);
+        uint32_t v = cc.n_cov, vw = cc.n_wg;
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(FULL, v, o); vw += __shfl_xor_sync(FULL, vw, o); }
+        if (lane == 0 && v) atomicAdd(&s_total, v);
+        if (HAS_GRAY && lane == 0 && vw) atomicAdd(&s_totalw, vw);
+        __syncthreads();
+        if (tid == 0) {
+            if (failed) fix[org] = 1;
+            else {
+                if (s_total) atomicAdd(&acc[(size_t)org * 2], s_total);
+                if (HAS_GRAY && s_totalw) atomicAdd(&acc[(size_t)org * 2 + 1], s_totalw);
+            }
+        }
+    }
 }
 
 int launch_coverage_quarters(gcp_ctx* ctx, uint32_t* step_qinfo, uint32_t P, uint32_t* cov,
@@ -1283,12 +1466,22 @@ int launch_coverage_quarters(gcp_ctx* ctx, uint32_t* step_qinfo, uint32_t P, uin
     // 2 GiB (organisms go through in chunks); an organism with more items falls back to scanning passes
     uint2* rec = nullptr;
     uint32_t rec_cap = 0, chunk = P;
+    // split form (k_cov_bucket -> k_cov_part -> k_cov_quarters as the writer / fallback): partitions of all
+    // organisms as work items for 256-thread CTAs
+    const bool split = R0 > 1 && ctx->cov_buckets && ctx->cov_split && threads == 1024;
+    size_t off_hdr = 0, off_work = 0, off_acc = 0;
     if (R0 > 1 && ctx->cov_buckets) {
         rec_cap = 3u * (uint32_t)AL;
         chunk = (uint32_t)(((size_t)2 << 30) / ((size_t)rec_cap * 8));
         if (chunk < 1) chunk = 1;
         if (chunk > P) chunk = P;
-        const size_t need = (size_t)chunk * rec_cap * 8;
+        size_t need = (size_t)chunk * rec_cap * 8;
+        if (split) {
+            off_hdr = (need + 255) & ~(size_t)255;
+            off_work = (off_hdr + (size_t)chunk * CB_HDR * 4 + 255) & ~(size_t)255;
+            off_acc = (off_work + (2 + (size_t)chunk * CB_MAXK) * 4 + 255) & ~(size_t)255;
+            need = off_acc + (size_t)chunk * 8 + chunk;          // acc[chunk][2] u32, fix[chunk] u8
+        }
         if (ctx->cov_scratch_bytes_s[ctx->scratch_slot] < need) {
             if (ctx->cov_scratch_s[ctx->scratch_slot]) cudaFree(ctx->cov_scratch_s[ctx->scratch_slot]);
             ctx->cov_scratch_s[ctx->scratch_slot] = nullptr; ctx->cov_scratch_bytes_s[ctx->scratch_slot] = 0;
@@ -1299,6 +1492,48 @@ int launch_coverage_quarters(gcp_ctx* ctx, uint32_t* step_qinfo, uint32_t P, uin
     }
     StageTimer tm(ctx, 1, st);
     const bool gray = ctx->n_gray > 0;
+    if (split) {
+        char* base = reinterpret_cast<char*>(ctx->cov_scratch_s[ctx->scratch_slot]);
+        uint32_t* hdr = reinterpret_cast<uint32_t*>(base + off_hdr);
+        uint32_t* work = reinterpret_cast<uint32_t*>(base + off_work);
+        uint32_t* acc = reinterpret_cast<uint32_t*>(base + off_acc);
+        uint8_t* fix = reinterpret_cast<uint8_t*>(base + off_acc + (size_t)chunk * 8);
+        constexpr uint32_t CAP = 1536;                     // items aimed at per partition
+        constexpr int TP = 512, MAXPP = 3072;              // block slots / item store of a partition CTA
+        const size_t smem_p = (size_t)TP * 20 + (size_t)MAXPP * 8 + 32;
+        // dedup table of the bucket kernel: the CTA's whole shared memory is free for it
+        uint32_t DSb = 1024;
+        while (DSb < 32768u && (size_t)DSb * 2 < (size_t)AL * 3) DSb <<= 1;
+        if (ctx->cov_dedup == 0) DSb = 0;
+        GCP_CUDA(ctx, cudaFuncSetAttribute(k_cov_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DSb * 4 + 16)));
+        if (gray) {
+            GCP_CUDA(ctx, cudaFuncSetAttribute(k_cov_part<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+            GCP_CUDA(ctx, cudaFuncSetAttribute(k_cov_quarters<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        } else {
+            GCP_CUDA(ctx, cudaFuncSetAttribute(k_cov_part<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+            GCP_CUDA(ctx, cudaFuncSetAttribute(k_cov_quarters<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        const int grid_p = ctx->num_sms * 6;
+        for (uint32_t o0 = 0; o0 < P; o0 += chunk) {
+            const uint32_t n_org = (P - o0 < chunk) ? (P - o0) : chunk;
+            uint32_t* qi = step_qinfo + (size_t)o0 * AL;
+            GCP_CUDA(ctx, cudaMemsetAsync(work, 0, 8, st));
+            GCP_CUDA(ctx, cudaMemsetAsync(acc, 0, (size_t)chunk * 8 + chunk, st));
+            k_cov_bucket<<<n_org, CB_THREADS, DSb * 4 + 16, st>>>(qi, n_org, ctx->t, AL, DSb, CAP, rec, rec_cap, hdr, work, fix);
+            if (gray) {
+                k_cov_part<true><<<grid_p, 256, smem_p, st>>>(ctx->t, TP, MAXPP, rec, rec_cap, hdr, work, acc, fix);
+                k_cov_quarters<1024, true><<<n_org, 1024, smem, st>>>(qi, n_org, ctx->t, AL, T, maxp, R0, DS, rec, rec_cap,
+                                                                      cov + (size_t)o0 * 8, flags ? flags + (size_t)o0 * 4 : nullptr, fix, acc);
+            } else {
+                k_cov_part<false><<<grid_p, 256, smem_p, st>>>(ctx->t, TP, MAXPP, rec, rec_cap, hdr, work, acc, fix);
+                k_cov_quarters<1024, false><<<n_org, 1024, smem, st>>>(qi, n_org, ctx->t, AL, T, maxp, R0, DS, rec, rec_cap,
+                                                                       cov + (size_t)o0 * 8, flags ? flags + (size_t)o0 * 4 : nullptr, fix, acc);
+            }
+            ctx->launches += 3;
+        }
+        GCP_CUDA(ctx, cudaGetLastError());
+        return 0;
+    }
 #define GCP_LAUNCH_COVQ(TH, GRAY)                                                                      \
     do {                                                                                               \
         GCP_CUDA(ctx, cudaFuncSetAttribute(k_cov_quarters<TH, GRAY>,                                   \

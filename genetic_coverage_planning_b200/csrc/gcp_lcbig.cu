@@ -123,11 +123,12 @@ __global__ void __launch_bounds__(32)
 k_lcb_finish(uint32_t P, int A, gcp_params prm, gcp_map_consts mc, const int32_t* __restrict__ lc,
              const double* __restrict__ dist, const double* __restrict__ turn,
              const uint32_t* __restrict__ cov, double* __restrict__ obj,
-             double* __restrict__ neg_cov_out, uint8_t* __restrict__ flags)
+             double* __restrict__ neg_cov_out, uint8_t* __restrict__ flags, const uint8_t* __restrict__ fix = nullptr)
 {
     __shared__ int s_lc[GCP_MAX_AGENTS * GCP_MAX_AGENTS];
     const uint32_t org = blockIdx.x;
     if (org >= P) return;
+    if (fix && fix[org]) return;              // redone (and finished) by the monolithic kernel
     for (int i = threadIdx.x; i < A * A; i += 32) s_lc[i] = lc[(size_t)org * A * A + i];
     __syncwarp();
     finish_objectives(s_lc, A, prm, mc, cov + (size_t)org * 8, dist + (size_t)org * A,
@@ -170,9 +171,11 @@ k_loop_closures_part(const int32_t* __restrict__ dna, uint32_t P, int A, int L, 
                      unsigned long long* __restrict__ rec_all /*[P][A*L] scratch: key48 << 16 | position*/,
                      const double* __restrict__ dist, const double* __restrict__ turn,
                      const uint32_t* __restrict__ cov, int32_t* __restrict__ lc_out,
-                     double* __restrict__ obj, double* __restrict__ neg_cov_out, uint8_t* __restrict__ flags)
+                     double* __restrict__ obj, double* __restrict__ neg_cov_out, uint8_t* __restrict__ flags,
+                     const uint8_t* __restrict__ fix = nullptr)
 {
     typedef typename std::conditional<SEQ16, uint16_t, int32_t>::type seq_t;
+    if (fix && !fix[blockIdx.x]) return;      // split form: only organisms whose bucket overflowed come here
     extern __shared__ __align__(16) unsigned char smem[];
     const int AL = A * L;
     const size_t tab_b = (size_t)T3 * 20, seq_b = (size_t)AL * sizeof(seq_t);
@@ -357,6 +360,204 @@ k_loop_closures_part(const int32_t* __restrict__ dna, uint32_t P, int A, int L, 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Split form of the hash-partitioned kernel: the K partitions of ALL organisms become independent work
+// items for small CTAs (256 threads, several per SM) instead of K sequential passes inside one
+// 1,024-thread CTA per organism (one per SM, issue slots ~50 % busy between its barriers).
+//   k_lc_bucket  one CTA per organism: compaction, {key, position} records scattered by key partition -
+//                partition r owns the r-th K-th of the organism's scratch stretch; {K, n, row bases, records
+//                per partition} to hdr, K work items to the list (an overflowing partition: fix[org])
+//   k_lc_part    persistent CTAs take work items: the four passes of the monolithic kernel over ONE bucket,
+//                chains by record index, lc_mat contributions added to the organism's matrix in global memory
+//   k_lcb_finish constraints + objectives; k_loop_closures_part(fix) redoes flagged organisms
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t LS_MAXK = 64;
+constexpr int LS_THREADS = 256;
+constexpr uint32_t LS_HDR = 2 + GCP_MAX_AGENTS + 1 + LS_MAXK;      // K, n, base[A + 1], records per partition
+
+template <bool SEQ16>
+__global__ void __launch_bounds__(LP_THREADS, 1)
+k_lc_bucket(const int32_t* __restrict__ dna, uint32_t P, int A, int L, uint32_t K, uint32_t region,
+            unsigned long long* __restrict__ rec_all, uint32_t* __restrict__ hdr_all,
+            uint32_t* __restrict__ work /* [0] = items listed, [1] = ticket, [2..] = organism << 6 | partition */,
+            uint8_t* __restrict__ fix)
+{
+    typedef typename std::conditional<SEQ16, uint16_t, int32_t>::type seq_t;
+    extern __shared__ __align__(16) unsigned char smem[];
+    seq_t* s_seq = reinterpret_cast<seq_t*>(smem);                                   // [A*L]
+    __shared__ int s_len[GCP_MAX_AGENTS], s_base[GCP_MAX_AGENTS + 1];
+    __shared__ uint32_t s_pcnt[LS_MAXK], s_wbase, s_ok;
+    const uint32_t org = blockIdx.x;
+    if (org >= P) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int AL = A * L;
+    const int32_t* d = dna + (size_t)org * AL;
+    unsigned long long* rec = rec_all + (size_t)org * K * region;
+    uint32_t* hdr = hdr_all + (size_t)org * LS_HDR;
+    if (tid < (int)LS_MAXK) s_pcnt[tid] = 0;
+    for (int a = warp; a < A; a += LP_NW) {
+        int cnt = 0;
+        for (int i0 = 0; i0 < L; i0 += 32) {
+            const int i = i0 + lane;
+            cnt += __popc(__ballot_sync(FULL, (i < L) && (d[a * L + i] != -1)));
+        }
+        if (lane == 0) s_len[a] = cnt;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int b = 0;
+        for (int a = 0; a < A; ++a) { s_base[a] = b; b += s_len[a]; }
+        s_base[A] = b;
+    }
+    __syncthreads();
+    const int n = s_base[A];
+    for (int a = warp; a < A; a += LP_NW) {                      // compaction (row-major, mappy.py:390)
+        int run = s_base[a];
+        for (int i0 = 0; i0 < L; i0 += 32) {
+            const int i = i0 + lane;
+            const int g = (i < L) ? d[a * L + i] : -1;
+            const bool v = g != -1;
+            const uint32_t bal = __ballot_sync(FULL, v);
+            if (v) s_seq[run + __popc(bal & ((1u << lane) - 1u))] = (seq_t)g;
+            run += __popc(bal);
+        }
+    }
+    __syncthreads();
+    for (int i0 = warp * 32; i0 < n; i0 += LP_THREADS) {
+        const int i = i0 + lane;
+        unsigned long long key = 0;
+        uint32_t p = LP_NIL;
+        if (i < n) { key = lp_key48(s_seq, i, n); p = lp_hash(key + 1ull) & (K - 1); }
+        const uint32_t peers = __match_any_sync(FULL, p);
+        uint32_t base = 0;
+        const int leader = __ffs(peers) - 1;
+        if (i < n && lane == leader) base = atomicAdd(&s_pcnt[p], (uint32_t)__popc(peers));
+        base = __shfl_sync(FULL, base, leader);
+        const uint32_t at = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        if (i < n && at < region) rec[(size_t)p * region + at] = (key << 16) | (unsigned long long)i;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        bool over = false;
+        for (uint32_t r = 0; r < K; ++r) over |= s_pcnt[r] > region;
+        hdr[0] = K; hdr[1] = (uint32_t)n;
+        s_ok = over ? 0u : 1u;
+        if (over) fix[org] = 1;
+        else if (n > 0) s_wbase = atomicAdd(&work[0], K);
+    }
+    __syncthreads();
+    if (tid <= A) hdr[2 + tid] = (uint32_t)s_base[tid];
+    if (tid < (int)K) hdr[2 + GCP_MAX_AGENTS + 1 + tid] = s_pcnt[tid];
+    if (s_ok && n > 0 && tid < (int)K) work[2 + s_wbase + tid] = (org << 6) | (uint32_t)tid;
+}
+
+__global__ void __launch_bounds__(LS_THREADS, 4)
+k_lc_part(int A, int T3, uint32_t region, int thresh, const unsigned long long* __restrict__ rec_all,
+          const uint32_t* __restrict__ hdr_all, uint32_t* __restrict__ work, int32_t* __restrict__ lc_acc /*[P][A][A]*/)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned long long* s_hkey = reinterpret_cast<unsigned long long*>(smem);        // [T3]
+    uint32_t* s_hcnt = reinterpret_cast<uint32_t*>(s_hkey + T3);                      // [T3] members | split << 16 | gap << 17
+    uint32_t* s_head = s_hcnt + T3;                                                   // [T3] newest member (record index)
+    uint32_t* s_ownm = s_head + T3;                                                   // [T3] owner mask
+    int*      s_lc   = reinterpret_cast<int*>(s_ownm + T3);                           // [A*A]
+    uint16_t* s_pos  = reinterpret_cast<uint16_t*>(s_lc + A * A);                     // [region] position of record e
+    uint16_t* s_nxt  = s_pos + region;                                                // [region] next member of e's group
+    uint16_t* s_slot = s_nxt + region;                                                // [region] hash slot of e's key
+    __shared__ int s_base[GCP_MAX_AGENTS + 1];
+    __shared__ uint32_t s_w;
+    const int tid = threadIdx.x;
+    const uint32_t n_work = work[0];
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_w = atomicAdd(&work[1], 1u);
+        __syncthreads();
+        const uint32_t w = s_w;
+        if (w >= n_work) break;
+        const uint32_t item = work[2 + w], org = item >> 6, r = item & 63u;
+        const uint32_t* hdr = hdr_all + (size_t)org * LS_HDR;
+        const uint32_t K = hdr[0];
+        const int m = (int)hdr[2 + GCP_MAX_AGENTS + 1 + r];
+        if (m == 0) continue;
+        const unsigned long long* rc = rec_all + ((size_t)org * K + r) * region;
+        for (int h = tid; h < T3; h += LS_THREADS) { s_hkey[h] = 0ull; s_hcnt[h] = 0u; s_head[h] = LP_NIL; s_ownm[h] = 0u; }
+        for (int i = tid; i < A * A; i += LS_THREADS) s_lc[i] = 0;
+        if (tid <= A) s_base[tid] = (int)hdr[2 + tid];
+        __syncthreads();
+        // pass 1: count the keys of this partition
+        for (int e0 = tid; e0 < m; e0 += 4 * LS_THREADS) {
+            unsigned long long v4[4];                                                // four record loads in flight
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) { const int e = e0 + u * LS_THREADS; v4[u] = (e < m) ? rc[e] : 0ull; }
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * LS_THREADS;
+                if (e >= m) break;
+                const unsigned long long key = (v4[u] >> 16) + 1ull;                 // never 0
+                uint32_t h = __umulhi(lp_hash(key), (uint32_t)T3);
+                for (;;) {                                                           // T3 > region >= m: always terminates
+                    const unsigned long long cur = ((volatile unsigned long long*)s_hkey)[h];
+                    if (cur == key) break;
+                    if (cur == 0ull) {
+                        const unsigned long long old = atomicCAS(&s_hkey[h], 0ull, key);
+                        if (old == 0ull || old == key) break;
+                    }
+                    h = (h + 1 == (uint32_t)T3) ? 0u : h + 1;
+                }
+                atomicAdd(&s_hcnt[h], 1u);
+                GCP_DASSERT(e < (int)region && h < (uint32_t)T3);
+                s_pos[e] = (uint16_t)(v4[u] & 0xFFFFull);
+                s_slot[e] = (uint16_t)h;
+            }
+        }
+        __syncthreads();
+        // pass 2: members of duplicate groups link themselves, record owner and split flag
+        for (int e = tid; e < m; e += LS_THREADS) {
+            const uint32_t h = s_slot[e];
+            if ((s_hcnt[h] & 0xFFFFu) < 2u) continue;
+            const int i = (int)s_pos[e];
+            const int a = owner_row(s_base, A, i);
+            s_nxt[e] = (uint16_t)atomicExch(&s_head[h], (uint32_t)e);               // NIL -> 0xFFFF
+            atomicOr(&s_ownm[h], 1u << a);
+            if (a >= 1 && i == s_base[a]) atomicOr(&s_hcnt[h], 1u << 16);            // touches a path split (F10)
+        }
+        __syncthreads();
+        // pass 3: successor gap test (ascending consecutive positions)
+        for (int e = tid; e < m; e += LS_THREADS) {
+            const uint32_t h = s_slot[e];
+            const uint32_t c = s_hcnt[h];
+            if ((c & 0xFFFFu) < 2u || (c & (1u << 16))) continue;
+            const uint32_t i = s_pos[e];
+            uint32_t succ = 0xFFFFFFFFu;
+            for (uint32_t j = s_head[h] & 0xFFFFu; j != 0xFFFFu; j = s_nxt[j]) {
+                const uint32_t pj = s_pos[j];
+                if (pj > i && pj < succ) succ = pj;
+            }
+            if (succ != 0xFFFFFFFFu && (int)(succ - i) > thresh) atomicOr(&s_hcnt[h], 1u << 17);
+        }
+        __syncthreads();
+        // pass 4: one thread per duplicate group updates lc_mat
+        for (int h = tid; h < T3; h += LS_THREADS) {
+            const uint32_t c = s_hcnt[h];
+            if ((c & 0xFFFFu) < 2u || (c & (1u << 16))) continue;
+            const uint32_t owners = s_ownm[h];
+            if (__popc(owners) == 1) {
+                if (c & (1u << 17)) { const int a = __ffs(owners) - 1; atomicAdd(&s_lc[a * A + a], 1); }
+            } else {
+                for (uint32_t mx = owners; mx; mx &= mx - 1) {
+                    const int x = __ffs(mx) - 1;
+                    for (uint32_t my = mx & (mx - 1); my; my &= my - 1)
+                        atomicAdd(&s_lc[x * A + (__ffs(my) - 1)], 1);
+                }
+            }
+        }
+        __syncthreads();
+        int32_t* out = lc_acc + (size_t)org * A * A;
+        for (int i = tid; i < A * A; i += LS_THREADS) { const int v = s_lc[i]; if (v) atomicAdd(&out[i], v); }
+    }
+}
+
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static int bits_for(uint32_t x) { int b = 1; while (b < 32 && (1u << b) <= x) ++b; return b; }
@@ -381,6 +582,78 @@ int launch_loop_closures_big(gcp_ctx* ctx, const int32_t* dna, uint32_t P, const
             const size_t tab = (size_t)T3t * 20;
             const size_t need_s = (((tab > seq_b ? tab : seq_b) + 15) & ~(size_t)15) + fixed;
             if (need_s <= (size_t)ctx->max_smem_optin) { R = Rt; T3 = T3t; smem = need_s; break; }
+        }
+        if (R > 1 && ctx->lc_split) {
+            // split form: partitions as work items of 256-thread CTAs (see k_lc_bucket)
+            uint32_t K = 2;
+            while (K < LS_MAXK && (size_t)K * 640 < AL) K <<= 1;
+            uint32_t region = (uint32_t)((2 * AL + K - 1) / K);
+            region = (region + 7u) & ~7u;
+            const int T3p = (int)(region * 3 / 2) + 64;
+            const size_t smem_p = (size_t)T3p * 20 + (size_t)A * A * 4 + (size_t)region * 6 + 16;
+            const size_t smem_b = seq_b + 16;
+            if (region < 65000u && smem_p * 2 <= (size_t)ctx->max_smem_optin && smem_b <= (size_t)ctx->max_smem_optin) {
+                uint32_t chunk = (uint32_t)(((size_t)2 << 30) / ((size_t)K * region * 8));
+                if (chunk < 1) chunk = 1;
+                if (chunk > P) chunk = P;
+                const size_t off_hdr = al256((size_t)chunk * K * region * 8);
+                const size_t off_work = off_hdr + al256((size_t)chunk * LS_HDR * 4);
+                const size_t off_fix = off_work + al256((2 + (size_t)chunk * K) * 4);
+                const size_t off_lc = off_fix + al256(chunk);
+                const size_t need = off_lc + (lc_out ? 0 : al256((size_t)chunk * A * A * 4));
+                if (ctx->lcb_scratch_bytes_s[ctx->scratch_slot] < need) {
+                    if (ctx->lcb_scratch_s[ctx->scratch_slot]) cudaFree(ctx->lcb_scratch_s[ctx->scratch_slot]);
+                    ctx->lcb_scratch_s[ctx->scratch_slot] = nullptr; ctx->lcb_scratch_bytes_s[ctx->scratch_slot] = 0;
+                    GCP_CUDA(ctx, cudaMalloc(&ctx->lcb_scratch_s[ctx->scratch_slot], need));
+                    ctx->lcb_scratch_bytes_s[ctx->scratch_slot] = need;
+                }
+                char* base = reinterpret_cast<char*>(ctx->lcb_scratch_s[ctx->scratch_slot]);
+                unsigned long long* rec = reinterpret_cast<unsigned long long*>(base);
+                uint32_t* hdr = reinterpret_cast<uint32_t*>(base + off_hdr);
+                uint32_t* work = reinterpret_cast<uint32_t*>(base + off_work);
+                uint8_t* fix = reinterpret_cast<uint8_t*>(base + off_fix);
+                StageTimer tm(ctx, 2, st);
+                if (seq16) {
+                    GCP_CUDA(ctx, cudaFuncSetAttribute(k_lc_bucket<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+                    GCP_CUDA(ctx, cudaFuncSetAttribute(k_loop_closures_part<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                } else {
+                    GCP_CUDA(ctx, cudaFuncSetAttribute(k_lc_bucket<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+                    GCP_CUDA(ctx, cudaFuncSetAttribute(k_loop_closures_part<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                }
+                GCP_CUDA(ctx, cudaFuncSetAttribute(k_lc_part, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+                int per_sm = (int)((size_t)ctx->max_smem_optin / (smem_p + 1024));
+                if (per_sm > 4) per_sm = 4;
+                if (per_sm < 1) per_sm = 1;
+                for (uint32_t o0 = 0; o0 < P; o0 += chunk) {
+                    const uint32_t n_org = (P - o0 < chunk) ? (P - o0) : chunk;
+                    const int32_t* dna_c = dna + (size_t)o0 * AL;
+                    int32_t* lc_c = lc_out ? lc_out + (size_t)o0 * A * A : reinterpret_cast<int32_t*>(base + off_lc);
+                    double* obj_c = obj ? obj + (size_t)o0 * 2 : nullptr;
+                    double* neg_c = neg_cov ? neg_cov + (size_t)o0 : nullptr;
+                    uint8_t* flg_c = flags ? flags + (size_t)o0 * 4 : nullptr;
+                    GCP_CUDA(ctx, cudaMemsetAsync(work, 0, 8, st));
+                    GCP_CUDA(ctx, cudaMemsetAsync(fix, 0, n_org, st));
+                    GCP_CUDA(ctx, cudaMemsetAsync(lc_c, 0, (size_t)n_org * A * A * 4, st));
+                    if (seq16) k_lc_bucket<true><<<n_org, LP_THREADS, smem_b, st>>>(dna_c, n_org, A, L, K, region, rec, hdr, work, fix);
+                    else       k_lc_bucket<false><<<n_org, LP_THREADS, smem_b, st>>>(dna_c, n_org, A, L, K, region, rec, hdr, work, fix);
+                    k_lc_part<<<ctx->num_sms * per_sm, LS_THREADS, smem_p, st>>>(A, T3p, region, ctx->p.solo_sep_thresh, rec, hdr, work, lc_c);
+                    k_lcb_finish<<<n_org, 32, 0, st>>>(n_org, A, ctx->p, ctx->mc, lc_c, dist + (size_t)o0 * A, turn + (size_t)o0 * A,
+                                                       cov + (size_t)o0 * 8, obj_c, neg_c, flg_c, fix);
+                    // organisms whose bucket overflowed (fix): the monolithic kernel redoes and finishes them.  Its record
+                    // scratch is the split form's stretch of the organism (2 * A*L records >= the A*L it needs).
+                    if (seq16)
+                        k_loop_closures_part<true><<<n_org, LP_THREADS, smem, st>>>(dna_c, n_org, A, L, T3, R, ctx->p, ctx->mc, rec,
+                                                                                    dist + (size_t)o0 * A, turn + (size_t)o0 * A, cov + (size_t)o0 * 8,
+                                                                                    lc_out ? lc_c : nullptr, obj_c, neg_c, flg_c, fix);
+                    else
+                        k_loop_closures_part<false><<<n_org, LP_THREADS, smem, st>>>(dna_c, n_org, A, L, T3, R, ctx->p, ctx->mc, rec,
+                                                                                     dist + (size_t)o0 * A, turn + (size_t)o0 * A, cov + (size_t)o0 * 8,
+                                                                                     lc_out ? lc_c : nullptr, obj_c, neg_c, flg_c, fix);
+                    ctx->launches += 4;
+                }
+                GCP_CUDA(ctx, cudaGetLastError());
+                return 0;
+            }
         }
         if (R != 0) {
             // record scratch: 8 bytes per gene, at most 2 GiB (organisms go through in chunks)
