@@ -17,7 +17,9 @@
 //   per-agent sums are sequential fp64 adds in step order (mappy.py:351-352) so the
 //   result is bit-identical to the reference's `+=` loop.
 // ============================================================================
-constexpr int K1_STAGE_ELEMS = 2048;   // double2 entries (32 KB)
+// double2 entries per staging buffer, two buffers in dynamic shared memory: 2 x 32 KB for the 1,024-thread
+// kernel of long genomes, 2 x 16 KB for the 256-thread one
+template <int K1_THREADS> struct K1Stage { static constexpr int ELEMS = K1_THREADS >= 1024 ? 2048 : 1024; };
 
 template <int K1_THREADS>
 __global__ void __launch_bounds__(K1_THREADS)
@@ -28,7 +30,9 @@ k_path_costs(const int32_t* __restrict__ dna, uint32_t P, GcpTables t, int A, in
 {
     __shared__ int s_first_neg[GCP_MAX_AGENTS];
     __shared__ int s_bad;       // bit0: non-traversable step, bit1: gene out of range
-    __shared__ double2 s_stage[K1_STAGE_ELEMS];
+    extern __shared__ __align__(16) unsigned char k1_smem[];
+    constexpr int K1_STAGE_ELEMS = K1Stage<K1_THREADS>::ELEMS;
+    double2* s_stage_all = reinterpret_cast<double2*>(k1_smem);        // [2][K1_STAGE_ELEMS]
 
     const uint32_t org = blockIdx.x;
     if (org >= P) return;
@@ -52,8 +56,14 @@ k_path_costs(const int32_t* __restrict__ dna, uint32_t P, GcpTables t, int A, in
 
     const int CL = min(L, K1_STAGE_ELEMS / A);     // columns staged per pass
     double acc_d = 0.0, acc_t = 0.0;               // lane a of warp 0 owns agent a
-    for (int c0 = 0; c0 < L; c0 += CL) {
+    // Two staging buffers: the A lanes that add up pass c (sequentially, in step order) do so while the other
+    // warps are already gathering pass c + 1 into the other buffer - one barrier per pass; buffer c & 1 is
+    // written again in pass c + 2, behind the barrier of pass c + 1, which the summing lanes only reach when
+    // their sums of pass c are done.
+    int pass = 0;
+    for (int c0 = 0; c0 < L; c0 += CL, ++pass) {
         const int cl = min(CL, L - c0);
+        double2* s_stage = s_stage_all + (pass & 1) * K1_STAGE_ELEMS;
         for (int k = tid; k < A * cl; k += K1_THREADS) {
             const int a = k / cl, ii = k - a * cl, i = c0 + ii;
             const int nsteps = min(s_first_neg[a], L - 1);
@@ -93,13 +103,19 @@ k_path_costs(const int32_t* __restrict__ dna, uint32_t P, GcpTables t, int A, in
         }
         __syncthreads();
         if (tid < A) {
-            for (int ii = 0; ii < cl; ++ii) {
+            int ii = 0;
+            for (; ii + 4 <= cl; ii += 4) {                   // four loads in flight, adds in step order
+                const double2 c0_ = s_stage[ii * A + tid], c1_ = s_stage[(ii + 1) * A + tid];
+                const double2 c2_ = s_stage[(ii + 2) * A + tid], c3_ = s_stage[(ii + 3) * A + tid];
+                acc_d = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(acc_d, c0_.x), c1_.x), c2_.x), c3_.x);
+                acc_t = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(acc_t, c0_.y), c1_.y), c2_.y), c3_.y);
+            }
+            for (; ii < cl; ++ii) {
                 const double2 c = s_stage[ii * A + tid];
                 acc_d = __dadd_rn(acc_d, c.x);
                 acc_t = __dadd_rn(acc_t, c.y);
             }
         }
-        __syncthreads();
     }
     if (tid < A) {
         dist[(size_t)org * A + tid] = acc_d;
@@ -120,12 +136,17 @@ int launch_path_costs(gcp_ctx* ctx, const int32_t* dna, uint32_t P, uint32_t* ed
         return gcp_fail(ctx, -1, "step_info requested but no masked footprint store uploaded");
     StageTimer tm(ctx, 0, st);
     const uint32_t* info_table = quarter_info ? ctx->t.m_q_info : ctx->t.m_sub_info;
-    if (ctx->p.num_agents * ctx->p.max_dna_len > 4096)      // long genomes: more lookups in flight per organism
-        k_path_costs<1024><<<P, 1024, 0, st>>>(dna, P, ctx->t, ctx->p.num_agents, ctx->p.max_dna_len,
-                                               edge_ids, step_info, info_table, dist, turn, flags);
-    else
-        k_path_costs<256><<<P, 256, 0, st>>>(dna, P, ctx->t, ctx->p.num_agents, ctx->p.max_dna_len,
-                                             edge_ids, step_info, info_table, dist, turn, flags);
+    if (ctx->p.num_agents * ctx->p.max_dna_len > 4096) {    // long genomes: more lookups in flight per organism
+        const size_t smem = (size_t)2 * K1Stage<1024>::ELEMS * sizeof(double2);
+        GCP_CUDA(ctx, cudaFuncSetAttribute(k_path_costs<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_path_costs<1024><<<P, 1024, smem, st>>>(dna, P, ctx->t, ctx->p.num_agents, ctx->p.max_dna_len,
+                                                  edge_ids, step_info, info_table, dist, turn, flags);
+    } else {
+        const size_t smem = (size_t)2 * K1Stage<256>::ELEMS * sizeof(double2);
+        GCP_CUDA(ctx, cudaFuncSetAttribute(k_path_costs<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_path_costs<256><<<P, 256, smem, st>>>(dna, P, ctx->t, ctx->p.num_agents, ctx->p.max_dna_len,
+                                                edge_ids, step_info, info_table, dist, turn, flags);
+    }
     ctx->launches++;
     GCP_CUDA(ctx, cudaGetLastError());
     return 0;

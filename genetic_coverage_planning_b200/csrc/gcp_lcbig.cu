@@ -380,7 +380,7 @@ template <bool SEQ16>
 __global__ void __launch_bounds__(LP_THREADS, 1)
 k_lc_bucket(const int32_t* __restrict__ dna, uint32_t P, int A, int L, uint32_t K, uint32_t region,
             unsigned long long* __restrict__ rec_all, uint32_t* __restrict__ hdr_all,
-            uint32_t* __restrict__ work /* [0] = items listed, [1] = ticket, [2..] = organism << 6 | partition */,
+            uint32_t* __restrict__ work /* [0] = items listed, [4 + 4 i ..] = item i: {organism, partition, records, K} */,
             uint8_t* __restrict__ fix)
 {
     typedef typename std::conditional<SEQ16, uint16_t, int32_t>::type seq_t;
@@ -449,38 +449,43 @@ k_lc_bucket(const int32_t* __restrict__ dna, uint32_t P, int A, int L, uint32_t 
     __syncthreads();
     if (tid <= A) hdr[2 + tid] = (uint32_t)s_base[tid];
     if (tid < (int)K) hdr[2 + GCP_MAX_AGENTS + 1 + tid] = s_pcnt[tid];
-    if (s_ok && n > 0 && tid < (int)K) work[2 + s_wbase + tid] = (org << 6) | (uint32_t)tid;
+    if (s_ok && n > 0 && tid < (int)K)
+        reinterpret_cast<uint4*>(work + 4)[s_wbase + tid] = make_uint4(org, (uint32_t)tid, s_pcnt[tid], K);
 }
 
-__global__ void __launch_bounds__(LS_THREADS, 4)
-k_lc_part(int A, int T3, uint32_t region, int thresh, const unsigned long long* __restrict__ rec_all,
+__global__ void __launch_bounds__(LS_THREADS, 5)
+k_lc_part(int A, int T3max, uint32_t region, int thresh, const unsigned long long* __restrict__ rec_all,
           const uint32_t* __restrict__ hdr_all, uint32_t* __restrict__ work, int32_t* __restrict__ lc_acc /*[P][A][A]*/)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    unsigned long long* s_hkey = reinterpret_cast<unsigned long long*>(smem);        // [T3]
-    uint32_t* s_hcnt = reinterpret_cast<uint32_t*>(s_hkey + T3);                      // [T3] members | split << 16 | gap << 17
-    uint32_t* s_head = s_hcnt + T3;                                                   // [T3] newest member (record index)
-    uint32_t* s_ownm = s_head + T3;                                                   // [T3] owner mask
-    int*      s_lc   = reinterpret_cast<int*>(s_ownm + T3);                           // [A*A]
+    unsigned long long* s_hkey = reinterpret_cast<unsigned long long*>(smem);        // [T3max]
+    uint32_t* s_hcnt = reinterpret_cast<uint32_t*>(s_hkey + T3max);                   // [T3max] members | split << 16 | gap << 17
+    uint32_t* s_head = s_hcnt + T3max;                                                // [T3max] newest member (record index)
+    uint32_t* s_ownm = s_head + T3max;                                                // [T3max] owner mask
+    int*      s_lc   = reinterpret_cast<int*>(s_ownm + T3max);                        // [A*A]
     uint16_t* s_pos  = reinterpret_cast<uint16_t*>(s_lc + A * A);                     // [region] position of record e
     uint16_t* s_nxt  = s_pos + region;                                                // [region] next member of e's group
     uint16_t* s_slot = s_nxt + region;                                                // [region] hash slot of e's key
     __shared__ int s_base[GCP_MAX_AGENTS + 1];
-    __shared__ uint32_t s_w;
     const int tid = threadIdx.x;
     const uint32_t n_work = work[0];
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_w = atomicAdd(&work[1], 1u);
-        __syncthreads();
-        const uint32_t w = s_w;
-        if (w >= n_work) break;
-        const uint32_t item = work[2 + w], org = item >> 6, r = item & 63u;
-        const uint32_t* hdr = hdr_all + (size_t)org * LS_HDR;
-        const uint32_t K = hdr[0];
-        const int m = (int)hdr[2 + GCP_MAX_AGENTS + 1 + r];
+    const uint4* items = reinterpret_cast<const uint4*>(work + 4);
+    // items are dealt out statically (CTA b takes b, b + grid, ...) and the next item's descriptor is loaded
+    // while the current one is processed: no ticket, one dependent L2 round trip (the records) per item
+    uint32_t w = blockIdx.x;
+    uint4 cur = (w < n_work) ? items[w] : make_uint4(0, 0, 0, 0);
+    for (; w < n_work; w += gridDim.x) {
+        const uint4 nxt = (w + gridDim.x < n_work) ? items[w + gridDim.x] : make_uint4(0, 0, 0, 0);
+        const uint32_t org = cur.x, r = cur.y, K = cur.w;
+        const int m = (int)cur.z;
+        cur = nxt;
         if (m == 0) continue;
+        const uint32_t* hdr = hdr_all + (size_t)org * LS_HDR;
+        __syncthreads();                                  // the previous item's readers are done
         const unsigned long long* rc = rec_all + ((size_t)org * K + r) * region;
+        // the arrays are laid out for the largest bucket (T3max slots); this bucket uses 1.5 slots per record,
+        // so clearing and the slot scan of pass 4 cost what the bucket holds, not what it may hold
+        const int T3 = min(T3max, max(64, m + (m >> 1) + 8));
         for (int h = tid; h < T3; h += LS_THREADS) { s_hkey[h] = 0ull; s_hcnt[h] = 0u; s_head[h] = LP_NIL; s_ownm[h] = 0u; }
         for (int i = tid; i < A * A; i += LS_THREADS) s_lc[i] = 0;
         if (tid <= A) s_base[tid] = (int)hdr[2 + tid];
@@ -587,7 +592,7 @@ int launch_loop_closures_big(gcp_ctx* ctx, const int32_t* dna, uint32_t P, const
             // split form: partitions as work items of 256-thread CTAs (see k_lc_bucket)
             uint32_t K = 2;
             while (K < LS_MAXK && (size_t)K * 640 < AL) K <<= 1;
-            uint32_t region = (uint32_t)((2 * AL + K - 1) / K);
+            uint32_t region = (uint32_t)((3 * AL / 2 + K - 1) / K);   // 1.5 x the mean bucket (sigma of a bucket: ~5 % of it)
             region = (region + 7u) & ~7u;
             const int T3p = (int)(region * 3 / 2) + 64;
             const size_t smem_p = (size_t)T3p * 20 + (size_t)A * A * 4 + (size_t)region * 6 + 16;
@@ -598,7 +603,7 @@ int launch_loop_closures_big(gcp_ctx* ctx, const int32_t* dna, uint32_t P, const
                 if (chunk > P) chunk = P;
                 const size_t off_hdr = al256((size_t)chunk * K * region * 8);
                 const size_t off_work = off_hdr + al256((size_t)chunk * LS_HDR * 4);
-                const size_t off_fix = off_work + al256((2 + (size_t)chunk * K) * 4);
+                const size_t off_fix = off_work + al256((4 + (size_t)chunk * K * 4) * 4);
                 const size_t off_lc = off_fix + al256(chunk);
                 const size_t need = off_lc + (lc_out ? 0 : al256((size_t)chunk * A * A * 4));
                 if (ctx->lcb_scratch_bytes_s[ctx->scratch_slot] < need) {
@@ -622,7 +627,7 @@ int launch_loop_closures_big(gcp_ctx* ctx, const int32_t* dna, uint32_t P, const
                 }
                 GCP_CUDA(ctx, cudaFuncSetAttribute(k_lc_part, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
                 int per_sm = (int)((size_t)ctx->max_smem_optin / (smem_p + 1024));
-                if (per_sm > 4) per_sm = 4;
+                if (per_sm > 5) per_sm = 5;
                 if (per_sm < 1) per_sm = 1;
                 for (uint32_t o0 = 0; o0 < P; o0 += chunk) {
                     const uint32_t n_org = (P - o0 < chunk) ? (P - o0) : chunk;
@@ -631,7 +636,7 @@ int launch_loop_closures_big(gcp_ctx* ctx, const int32_t* dna, uint32_t P, const
                     double* obj_c = obj ? obj + (size_t)o0 * 2 : nullptr;
                     double* neg_c = neg_cov ? neg_cov + (size_t)o0 : nullptr;
                     uint8_t* flg_c = flags ? flags + (size_t)o0 * 4 : nullptr;
-                    GCP_CUDA(ctx, cudaMemsetAsync(work, 0, 8, st));
+                    GCP_CUDA(ctx, cudaMemsetAsync(work, 0, 16, st));
                     GCP_CUDA(ctx, cudaMemsetAsync(fix, 0, n_org, st));
                     GCP_CUDA(ctx, cudaMemsetAsync(lc_c, 0, (size_t)n_org * A * A * 4, st));
                     if (seq16) k_lc_bucket<true><<<n_org, LP_THREADS, smem_b, st>>>(dna_c, n_org, A, L, K, region, rec, hdr, work, fix);
