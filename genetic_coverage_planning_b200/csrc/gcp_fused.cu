@@ -13,11 +13,13 @@
 // shared memory, 32-bit pair keys, 40 registers -> six resident CTAs per SM instead of five, and
 // phase C starts without a barrier while other warps still stream their B2 ranges.
 //
-// Preconditions (checked by the caller): pre-masked footprint store uploaded and
-// coverage_blend == 1 (wall coverage only); binary and gray maps (HAS_GRAY).  The staged kernels
-// in gcp_eval.cu remain the general path (blend < 1, all six pixel counters) and the cross-check
-// of this one (tests/test_gpu_parity.py); k_cov_quarters below is phase B as a stand-alone kernel
-// for genomes that outgrow this kernel's shared memory.
+// Objectives-only variant: pre-masked footprint store uploaded and coverage_blend == 1 (wall coverage
+// only); binary and gray maps (HAS_GRAY).  GENERAL variant: any coverage_blend and the six pixel
+// counters, over the unmasked store with marker entries for the map planes (see coverage_quarters).
+// The staged kernels in gcp_eval.cu are the cross-check of both (tests/test_gpu_parity.py).  Genomes
+// that outgrow this kernel's shared memory run phase B stand-alone: k_cov_quarters (one CTA per
+// organism, partitions one after the other) or, by default, k_cov_bucket + k_cov_part (the partitions
+// of all organisms as work items of small CTAs).
 //
 #include "gcp_common.cuh"
 #include "gcp_device.cuh"
@@ -1404,8 +1406,7 @@ k_cov_bucket(uint32_t* step_qinfo, uint32_t P, GcpTables t, int AL, uint32_t DS,
 template <bool HAS_GRAY>
 __global__ void __launch_bounds__(256, 6)
 k_cov_part(GcpTables t, int T, int MAXP, uint2* __restrict__ rec_all, uint32_t rec_cap,
-           const uint32_t* __restrict__ hdr_all, uint32_t* __restrict__ work, uint32_t* __restrict__ acc,
-           uint8_t* __restrict__ fix)
+           uint32_t* __restrict__ work, uint32_t* __restrict__ acc, uint8_t* __restrict__ fix)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint32_t s_total, s_totalw;
@@ -1431,7 +1432,6 @@ k_cov_part(GcpTables t, int T, int MAXP, uint2* __restrict__ rec_all, uint32_t r
         bool failed;
         coverage_quarters<256, HAS_GRAY, true>(nullptr, 0, t, T, MAXP, 1u, 0u, smem, cc, failed,
                                                rec_all + (size_t)org * rec_cap + b0, 0u, 0, true, m);
-        (void)hdr_all;
         uint32_t v = cc.n_cov, vw = cc.n_wg;
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(FULL, v, o); vw += __shfl_xor_sync(FULL, vw, o); }
@@ -1530,11 +1530,11 @@ int launch_coverage_quarters(gcp_ctx* ctx, uint32_t* step_qinfo, uint32_t P, uin
             GCP_CUDA(ctx, cudaMemsetAsync(acc, 0, (size_t)chunk * 8 + chunk, st));
             k_cov_bucket<<<n_org, CB_THREADS, DSb * 4 + 16, st>>>(qi, n_org, ctx->t, AL, DSb, CAP, rec, rec_cap, hdr, work, fix);
             if (gray) {
-                k_cov_part<true><<<grid_p, 256, smem_p, st>>>(ctx->t, TP, MAXPP, rec, rec_cap, hdr, work, acc, fix);
+                k_cov_part<true><<<grid_p, 256, smem_p, st>>>(ctx->t, TP, MAXPP, rec, rec_cap, work, acc, fix);
                 k_cov_quarters<1024, true><<<n_org, 1024, smem, st>>>(qi, n_org, ctx->t, AL, T, maxp, R0, DS, rec, rec_cap,
                                                                       cov + (size_t)o0 * 8, flags ? flags + (size_t)o0 * 4 : nullptr, fix, acc);
             } else {
-                k_cov_part<false><<<grid_p, 256, smem_p, st>>>(ctx->t, TP, MAXPP, rec, rec_cap, hdr, work, acc, fix);
+                k_cov_part<false><<<grid_p, 256, smem_p, st>>>(ctx->t, TP, MAXPP, rec, rec_cap, work, acc, fix);
                 k_cov_quarters<1024, false><<<n_org, 1024, smem, st>>>(qi, n_org, ctx->t, AL, T, maxp, R0, DS, rec, rec_cap,
                                                                        cov + (size_t)o0 * 8, flags ? flags + (size_t)o0 * 4 : nullptr, fix, acc);
             }
