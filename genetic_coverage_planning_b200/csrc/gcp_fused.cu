@@ -80,6 +80,9 @@ struct CovCounts { uint32_t n_cov, n_wg, n_free0, wg_all, n_gmask, n_all; };
 // first makes the group AND the finished union with the (g == 0) plane of that quarter, the second with
 // the mask & (g == 0) plane - loaded like any other 128-B line of the stream, four loads in flight.
 // Gray pixels are weighed at the second marker from the per-quarter gray lists.
+#ifndef KF_GEN_MINB
+#define KF_GEN_MINB 3     // resident CTAs per SM the general kernel (512 threads) is compiled for
+#endif
 #ifndef KF_PF_DIST_N
 #define KF_PF_DIST_N 16
 #endif
@@ -732,7 +735,7 @@ struct StaticShape {
 // UNMASKED footprint store with marker entries for the map planes (see coverage_quarters); 512 threads,
 // three CTAs per SM (the unmasked store carries 2.6 x the items of the pre-masked one).
 template <int KF_THREADS, bool HAS_GRAY, int SAL, bool COMPACT, bool GENERAL = false, bool PF = false>
-__global__ void __launch_bounds__(KF_THREADS, KF_THREADS == 256 ? ((COMPACT && !HAS_GRAY) ? 6 : 5) : KF_THREADS == 512 ? 3 : 1)
+__global__ void __launch_bounds__(KF_THREADS, KF_THREADS == 256 ? ((COMPACT && !HAS_GRAY) ? 6 : 5) : KF_THREADS == 512 ? KF_GEN_MINB : 1)
 k_eval_fused(const void* __restrict__ dna_v, uint32_t P, GcpTables t, FusedShape sh,
              gcp_params prm, gcp_map_consts mc,
              double* __restrict__ obj, double* __restrict__ neg_cov_out,
