@@ -102,6 +102,8 @@ struct gcp_ctx {
     int cov_buckets = 1;     // 1: long genomes bucket their items by hash partition once (else: R scanning passes)
     int cov_dedup = 1;       // 1: revisited edges are dropped before the coverage union (phase B0)
     int cov_split = 1;       // 1: long genomes run their hash partitions as work items of small CTAs (k_cov_bucket / k_cov_part)
+    int cov_split_cap = 0;   // testing: items aimed at per partition (0 = 1,536); a huge value overflows every partition CTA -> fallback path
+    int lc_split_slack = 0;  // testing: stretch of a loop-closure bucket in % of the mean bucket (0 = 150); < 100 overflows -> fallback path
     int cov_threads = 0;     // tuning: CTA size of k_cov_quarters (256 / 512 / 1024; 0 = auto)
     int lc_min_parts = 0;    // tuning: at least this many hash partitions in k_loop_closures_part
     int lc_split = 1;        // 1: long genomes run their loop-closure partitions as work items of small CTAs (k_lc_bucket / k_lc_part)

@@ -1510,7 +1510,7 @@ int launch_coverage_quarters(gcp_ctx* ctx, uint32_t* step_qinfo, uint32_t P, uin
         uint32_t* work = reinterpret_cast<uint32_t*>(base + off_work);
         uint32_t* acc = reinterpret_cast<uint32_t*>(base + off_acc);
         uint8_t* fix = reinterpret_cast<uint8_t*>(base + off_acc + (size_t)chunk * 8);
-        constexpr uint32_t CAP = 1536;                     // items aimed at per partition
+        const uint32_t CAP = ctx->cov_split_cap > 0 ? (uint32_t)ctx->cov_split_cap : 1536u;   // items aimed at per partition
         constexpr int TP = 512, MAXPP = 3072;              // block slots / item store of a partition CTA
         const size_t smem_p = (size_t)TP * 20 + (size_t)MAXPP * 8 + 32;
         // dedup table of the bucket kernel: the CTA's whole shared memory is free for it

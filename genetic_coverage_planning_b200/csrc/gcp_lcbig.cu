@@ -592,16 +592,19 @@ int launch_loop_closures_big(gcp_ctx* ctx, const int32_t* dna, uint32_t P, const
             // split form: partitions as work items of 256-thread CTAs (see k_lc_bucket)
             uint32_t K = 2;
             while (K < LS_MAXK && (size_t)K * 640 < AL) K <<= 1;
-            uint32_t region = (uint32_t)((3 * AL / 2 + K - 1) / K);   // 1.5 x the mean bucket (sigma of a bucket: ~5 % of it)
+            const size_t slack = ctx->lc_split_slack > 0 ? (size_t)ctx->lc_split_slack : 150;
+            uint32_t region = (uint32_t)((AL * slack / 100 + K - 1) / K);   // 1.5 x the mean bucket (sigma of a bucket: ~5 % of it)
             region = (region + 7u) & ~7u;
             const int T3p = (int)(region * 3 / 2) + 64;
             const size_t smem_p = (size_t)T3p * 20 + (size_t)A * A * 4 + (size_t)region * 6 + 16;
             const size_t smem_b = seq_b + 16;
             if (region < 65000u && smem_p * 2 <= (size_t)ctx->max_smem_optin && smem_b <= (size_t)ctx->max_smem_optin) {
-                uint32_t chunk = (uint32_t)(((size_t)2 << 30) / ((size_t)K * region * 8));
+                // records per organism: K stretches of the split form, and at least the A*L the monolithic fallback indexes
+                const size_t rec_per = (size_t)K * region > AL ? (size_t)K * region : AL;
+                uint32_t chunk = (uint32_t)(((size_t)2 << 30) / (rec_per * 8));
                 if (chunk < 1) chunk = 1;
                 if (chunk > P) chunk = P;
-                const size_t off_hdr = al256((size_t)chunk * K * region * 8);
+                const size_t off_hdr = al256((size_t)chunk * rec_per * 8);
                 const size_t off_work = off_hdr + al256((size_t)chunk * LS_HDR * 4);
                 const size_t off_fix = off_work + al256((4 + (size_t)chunk * K * 4) * 4);
                 const size_t off_lc = off_fix + al256(chunk);

@@ -685,3 +685,52 @@ def test_prefetch_variants_of_the_fused_kernel(synth_setup):
                 assert torch.equal(getattr(got, name), getattr(want, name)), (pf, name)
     finally:
         eng.set_option("cov_prefetch", -1)
+
+
+def test_long_genome_split_kernels_edge_cases_and_fallback(synth_setup):
+    """16 agents x 640 genes (beyond the fused kernel): the split form (bucket + partition kernels, the
+    default), the monolithic kernels, the radix-sort loop closures and the split form with its overflow
+    fallback forced must agree bit for bit - on walks, an all-empty organism, empty agent rows, interior
+    -1 holes, a full row, teleporting rows and an out-of-range gene; two organisms against the oracle."""
+    from genetic_coverage_planning_b200 import synth, worlds
+    from genetic_coverage_planning_b200.engine import FitnessEngine
+    sw, pw, ow, op, eng, starts = synth_setup
+    A, L = 16, 640
+    st = synth.spread_starts(sw.xy, A, 1024)
+    op2 = worlds.org_params_for(dict(L=L), st)
+    op2.update(min_solo_lcs=0, min_comb_lcs=1)
+    eng2 = FitnessEngine(pw, op2, num_agents=A)
+    dna = synth.random_walk_population(sw.xy, sw.row_ptr, sw.col, st, 24, 600, L, seed=41).astype(np.int32)
+    rng = np.random.RandomState(5)
+    dna[1] = -1                                           # nothing at all
+    dna[2, 3] = -1; dna[2, 9] = -1                        # empty agent rows
+    for a in range(A):                                    # interior holes: the step rule stops, the sequence goes on
+        dna[3, a, rng.randint(5, 500)] = -1
+    dna[4, 0] = rng.randint(0, sw.N, size=L)              # a full row of teleports (non-edges)
+    dna[5, :, 100:] = -1                                  # short rows
+    dna[6, 7, 20] = sw.N + 5                              # out of range: error flag
+    ref = eng2.evaluate(dna, detail=True, pixel_counts=False)
+    assert ref.flags.cpu().numpy()[6, 3] & 1
+    ok = np.ones(len(dna), dtype=bool)
+    ok[6] = False
+    runs = {}
+    for name, opts in (("monolithic", dict(cov_split=0, lc_split=0)), ("radix", dict(force_lc_big=1)),
+                       ("fallback", dict(cov_split_cap=1 << 30, lc_split_slack=60))):
+        for k, v in opts.items():
+            eng2.set_option(k, v)
+        try:
+            runs[name] = eng2.evaluate(dna, detail=True, pixel_counts=False)
+        finally:
+            for k in opts:
+                eng2.set_option(k, 1 if k in ("cov_split", "lc_split") else 0)
+    for name, r in runs.items():
+        for f in ("obj", "neg_cov", "dist", "turn", "lc_mat", "flags"):
+            a, b = getattr(ref, f).cpu().numpy(), getattr(r, f).cpu().numpy()
+            assert np.array_equal(a[ok], b[ok]), (name, f)
+    ow2 = World(sw.img, sw.xy, sw.row_ptr, sw.col, sw.edge_poly, sw.edge_theta, sw.edge_dist,
+                sw.map_params, op2, name="synth-16x640-edge")
+    obj, lc = ref.obj.cpu().numpy(), ref.lc_mat.cpu().numpy()
+    for k in (2, 3):
+        det = fo.calc_obj(ow2, dna[k].astype(int), detail=True)
+        assert det['obj'][0] == obj[k, 0] and det['obj'][1] == obj[k, 1], k
+        assert np.array_equal(det['lc_mat'].astype(np.int32), lc[k]), k
