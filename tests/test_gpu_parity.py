@@ -734,3 +734,32 @@ def test_long_genome_split_kernels_edge_cases_and_fallback(synth_setup):
         det = fo.calc_obj(ow2, dna[k].astype(int), detail=True)
         assert det['obj'][0] == obj[k, 0] and det['obj'][1] == obj[k, 1], k
         assert np.array_equal(det['lc_mat'].astype(np.int32), lc[k]), k
+
+
+def test_long_genome_split_kernels_on_a_gray_map(world_big):
+    """The reference's big (gray) map with 12 agents x 640 genes: the partition kernels apply the gray
+    pixel weights per bucket; split form == monolithic kernels bit for bit, objectives == oracle (1e-12)."""
+    from genetic_coverage_planning_b200 import synth
+    w = world_big
+    A, L = 12, 640
+    op = dict(w.org_params)
+    op.update(max_dna_len=L, start_idx=(list(w.org_params['start_idx']) * 2)[:A], min_solo_lcs=0, min_comb_lcs=1)
+    eng = _engine(w, op, num_agents=A)
+    dna = synth.random_walk_population(w.xy, w.row_ptr, w.col, op['start_idx'], 12, 600, L, seed=3).astype(np.int32)
+    split = eng.evaluate(dna, detail=True, pixel_counts=False)
+    eng.set_option("cov_split", 0)
+    eng.set_option("lc_split", 0)
+    try:
+        mono = eng.evaluate(dna, detail=True, pixel_counts=False)
+    finally:
+        eng.set_option("cov_split", 1)
+        eng.set_option("lc_split", 1)
+    assert not split.flags.cpu().numpy()[:, 3].any()
+    for f in ("obj", "neg_cov", "dist", "turn", "lc_mat", "flags"):
+        assert torch.equal(getattr(split, f), getattr(mono, f)), f
+    ow = World(w.img, w.xy, w.row_ptr, w.col, w.edge_poly, w.edge_theta, w.edge_dist, w.map_params, op,
+               name="big-12x640")
+    obj = split.obj.cpu().numpy()
+    for k in range(2):
+        o = fo.calc_obj(ow, dna[k].astype(int))
+        assert abs(o[0] - obj[k, 0]) <= COV_TOL_GRAY and o[1] == obj[k, 1]
