@@ -453,12 +453,15 @@ k_lc_bucket(const int32_t* __restrict__ dna, uint32_t P, int A, int L, uint32_t 
         reinterpret_cast<uint4*>(work + 4)[s_wbase + tid] = make_uint4(org, (uint32_t)tid, s_pcnt[tid], K);
 }
 
-__global__ void __launch_bounds__(LS_THREADS, 5)
+// KEY32: waypoint ids fit 16 bits - the table key is (from << 16 | to) + 1 in 32 bits (16 B per slot, 32-bit CAS)
+template <bool KEY32>
+__global__ void __launch_bounds__(LS_THREADS, KEY32 ? 6 : 5)
 k_lc_part(int A, int T3max, uint32_t region, int thresh, const unsigned long long* __restrict__ rec_all,
           const uint32_t* __restrict__ hdr_all, uint32_t* __restrict__ work, int32_t* __restrict__ lc_acc /*[P][A][A]*/)
 {
+    using HK = typename std::conditional<KEY32, uint32_t, unsigned long long>::type;
     extern __shared__ __align__(16) unsigned char smem[];
-    unsigned long long* s_hkey = reinterpret_cast<unsigned long long*>(smem);        // [T3max]
+    HK* s_hkey = reinterpret_cast<HK*>(smem);                                         // [T3max]
     uint32_t* s_hcnt = reinterpret_cast<uint32_t*>(s_hkey + T3max);                   // [T3max] members | split << 16 | gap << 17
     uint32_t* s_head = s_hcnt + T3max;                                                // [T3max] newest member (record index)
     uint32_t* s_ownm = s_head + T3max;                                                // [T3max] owner mask
@@ -486,7 +489,7 @@ k_lc_part(int A, int T3max, uint32_t region, int thresh, const unsigned long lon
         // the arrays are laid out for the largest bucket (T3max slots); this bucket uses 1.5 slots per record,
         // so clearing and the slot scan of pass 4 cost what the bucket holds, not what it may hold
         const int T3 = min(T3max, max(64, m + (m >> 1) + 8));
-        for (int h = tid; h < T3; h += LS_THREADS) { s_hkey[h] = 0ull; s_hcnt[h] = 0u; s_head[h] = LP_NIL; s_ownm[h] = 0u; }
+        for (int h = tid; h < T3; h += LS_THREADS) { s_hkey[h] = (HK)0; s_hcnt[h] = 0u; s_head[h] = LP_NIL; s_ownm[h] = 0u; }
         for (int i = tid; i < A * A; i += LS_THREADS) s_lc[i] = 0;
         if (tid <= A) s_base[tid] = (int)hdr[2 + tid];
         __syncthreads();
@@ -499,14 +502,22 @@ k_lc_part(int A, int T3max, uint32_t region, int thresh, const unsigned long lon
             for (int u = 0; u < 4; ++u) {
                 const int e = e0 + u * LS_THREADS;
                 if (e >= m) break;
-                const unsigned long long key = (v4[u] >> 16) + 1ull;                 // never 0
-                uint32_t h = __umulhi(lp_hash(key), (uint32_t)T3);
+                const unsigned long long k48 = v4[u] >> 16;
+                HK key;                                                              // never 0
+                uint32_t h;
+                if (KEY32) {
+                    key = (HK)(((uint32_t)(k48 >> 24) << 16 | (uint32_t)(k48 & 0xFFFFull)) + 1u);
+                    h = __umulhi((uint32_t)key * 0x9E3779B1u, (uint32_t)T3);
+                } else {
+                    key = (HK)(k48 + 1ull);
+                    h = __umulhi(lp_hash(k48 + 1ull), (uint32_t)T3);
+                }
                 for (;;) {                                                           // T3 > region >= m: always terminates
-                    const unsigned long long cur = ((volatile unsigned long long*)s_hkey)[h];
+                    const HK cur = ((volatile HK*)s_hkey)[h];
                     if (cur == key) break;
-                    if (cur == 0ull) {
-                        const unsigned long long old = atomicCAS(&s_hkey[h], 0ull, key);
-                        if (old == 0ull || old == key) break;
+                    if (cur == (HK)0) {
+                        const HK old = atomicCAS(&s_hkey[h], (HK)0, key);
+                        if (old == (HK)0 || old == key) break;
                     }
                     h = (h + 1 == (uint32_t)T3) ? 0u : h + 1;
                 }
@@ -596,7 +607,8 @@ int launch_loop_closures_big(gcp_ctx* ctx, const int32_t* dna, uint32_t P, const
             uint32_t region = (uint32_t)((AL * slack / 100 + K - 1) / K);   // 1.5 x the mean bucket (sigma of a bucket: ~5 % of it)
             region = (region + 7u) & ~7u;
             const int T3p = (int)(region * 3 / 2) + 64;
-            const size_t smem_p = (size_t)T3p * 20 + (size_t)A * A * 4 + (size_t)region * 6 + 16;
+            const bool key32 = ctx->t.N <= 65534u;
+            const size_t smem_p = (size_t)T3p * (key32 ? 16 : 20) + (size_t)A * A * 4 + (size_t)region * 6 + 16;
             const size_t smem_b = seq_b + 16;
             if (region < 65000u && smem_p * 2 <= (size_t)ctx->max_smem_optin && smem_b <= (size_t)ctx->max_smem_optin) {
                 // records per organism: K stretches of the split form, and at least the A*L the monolithic fallback indexes
@@ -628,9 +640,10 @@ int launch_loop_closures_big(gcp_ctx* ctx, const int32_t* dna, uint32_t P, const
                     GCP_CUDA(ctx, cudaFuncSetAttribute(k_lc_bucket<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
                     GCP_CUDA(ctx, cudaFuncSetAttribute(k_loop_closures_part<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 }
-                GCP_CUDA(ctx, cudaFuncSetAttribute(k_lc_part, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+                if (key32) GCP_CUDA(ctx, cudaFuncSetAttribute(k_lc_part<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+                else       GCP_CUDA(ctx, cudaFuncSetAttribute(k_lc_part<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
                 int per_sm = (int)((size_t)ctx->max_smem_optin / (smem_p + 1024));
-                if (per_sm > 5) per_sm = 5;
+                if (per_sm > (key32 ? 6 : 5)) per_sm = key32 ? 6 : 5;
                 if (per_sm < 1) per_sm = 1;
                 for (uint32_t o0 = 0; o0 < P; o0 += chunk) {
                     const uint32_t n_org = (P - o0 < chunk) ? (P - o0) : chunk;
@@ -644,7 +657,8 @@ int launch_loop_closures_big(gcp_ctx* ctx, const int32_t* dna, uint32_t P, const
                     GCP_CUDA(ctx, cudaMemsetAsync(lc_c, 0, (size_t)n_org * A * A * 4, st));
                     if (seq16) k_lc_bucket<true><<<n_org, LP_THREADS, smem_b, st>>>(dna_c, n_org, A, L, K, region, rec, hdr, work, fix);
                     else       k_lc_bucket<false><<<n_org, LP_THREADS, smem_b, st>>>(dna_c, n_org, A, L, K, region, rec, hdr, work, fix);
-                    k_lc_part<<<ctx->num_sms * per_sm, LS_THREADS, smem_p, st>>>(A, T3p, region, ctx->p.solo_sep_thresh, rec, hdr, work, lc_c);
+                    if (key32) k_lc_part<true><<<ctx->num_sms * per_sm, LS_THREADS, smem_p, st>>>(A, T3p, region, ctx->p.solo_sep_thresh, rec, hdr, work, lc_c);
+                    else       k_lc_part<false><<<ctx->num_sms * per_sm, LS_THREADS, smem_p, st>>>(A, T3p, region, ctx->p.solo_sep_thresh, rec, hdr, work, lc_c);
                     k_lcb_finish<<<n_org, 32, 0, st>>>(n_org, A, ctx->p, ctx->mc, lc_c, dist + (size_t)o0 * A, turn + (size_t)o0 * A,
                                                        cov + (size_t)o0 * 8, obj_c, neg_c, flg_c, fix);
                     // organisms whose bucket overflowed (fix): the monolithic kernel redoes and finishes them.  Its record
