@@ -1296,7 +1296,7 @@ constexpr uint32_t CB_MAXK = 64;
 constexpr uint32_t CB_HDR = CB_MAXK + 2;         // words per organism: K, items of partition 0 .. K-1
 
 __global__ void __launch_bounds__(CB_THREADS, 1)
-k_cov_bucket(uint32_t* step_qinfo, uint32_t P, GcpTables t, int AL, uint32_t DS, uint32_t cap,
+k_cov_bucket(uint32_t* step_qinfo, uint32_t P, GcpTables t, int AL, uint32_t DS, uint32_t cap, uint32_t K_fixed,
              uint2* __restrict__ rec_all, uint32_t rec_cap, uint32_t* __restrict__ hdr_all,
              uint32_t* __restrict__ work /* [0] = items listed, [1] = ticket, [4 + 4 i ..] = item i: {organism, first record, records, 0} */,
              uint8_t* __restrict__ fix)
@@ -1310,48 +1310,61 @@ k_cov_bucket(uint32_t* step_qinfo, uint32_t P, GcpTables t, int AL, uint32_t DS,
     uint32_t* info = step_qinfo + (size_t)org * AL;
     uint2* rec = rec_all + (size_t)org * rec_cap;
     uint32_t* hdr = hdr_all + (size_t)org * CB_HDR;
-    // revisited edges add nothing to the union (see coverage_quarters B0); the surviving steps' items are
-    // counted in the same pass
-    uint32_t mine = 0;
+    // revisited edges add nothing to the union (see coverage_quarters B0).  K_fixed != 0 (the launcher's choice
+    // from the genome length): the exchange filter runs inside the ONE scatter pass below.  K_fixed == 0: a
+    // first pass filters and counts the surviving items, K is chosen per organism for <= cap items each.
+    uint32_t* s_set = reinterpret_cast<uint32_t*>(smem);
+    const int sh_ds = DS ? __clz(DS) + 1 : 0;
     if (tid < (int)CB_MAXK) s_pcnt[tid] = 0;
-    if (DS) {
-        uint32_t* s_set = reinterpret_cast<uint32_t*>(smem);
-        const int sh_ds = __clz(DS) + 1;
+    if (DS)
         for (int i = tid; i < (int)(DS >> 2); i += CB_THREADS) reinterpret_cast<uint4*>(s_set)[i] = make_uint4(0, 0, 0, 0);
-        __syncthreads();
-        for (int s = tid; s < AL; s += CB_THREADS) {
-            const uint32_t inf = info[s];
-            if (!inf) continue;
-            const uint32_t h = (inf * 0x9E3779B1u) >> sh_ds;
-            if (atomicExch(&s_set[h], inf) == inf) info[s] = 0u;
-            else mine += inf >> 26;
+    __syncthreads();
+    const bool inline_dedup = K_fixed != 0 && DS != 0;
+    uint32_t K = K_fixed;
+    if (K_fixed == 0) {
+        uint32_t mine = 0;
+        if (DS) {
+            for (int s = tid; s < AL; s += CB_THREADS) {
+                const uint32_t inf = info[s];
+                if (!inf) continue;
+                const uint32_t h = (inf * 0x9E3779B1u) >> sh_ds;
+                if (atomicExch(&s_set[h], inf) == inf) info[s] = 0u;
+                else mine += inf >> 26;
+            }
+        } else {
+            for (int s = tid; s < AL; s += CB_THREADS) mine += info[s] >> 26;
         }
-    } else {
-        for (int s = tid; s < AL; s += CB_THREADS) mine += info[s] >> 26;
-    }
-    #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(FULL, mine, o);
-    if (lane == 0) s_wsum[warp] = mine;
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t total = 0;
-        for (int w2 = 0; w2 < NW; ++w2) total += s_wsum[w2];
-        uint32_t K = 1;
-        while ((uint64_t)K * cap < total && K < CB_MAXK) K <<= 1;
-        if (total > rec_cap) K = 0;                       // more items than the scratch holds: monolithic pass
-        s_K = K;
-    }
-    __syncthreads();
-    const uint32_t K = s_K;
-    if (K == 0) {
-        if (tid == 0) { hdr[0] = 0; fix[org] = 1; }
-        return;
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(FULL, mine, o);
+        if (lane == 0) s_wsum[warp] = mine;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t total = 0;
+            for (int w2 = 0; w2 < NW; ++w2) total += s_wsum[w2];
+            uint32_t Kc = 1;
+            while ((uint64_t)Kc * cap < total && Kc < CB_MAXK) Kc <<= 1;
+            if (total > rec_cap) Kc = 0;                  // more items than the scratch holds: monolithic pass
+            s_K = Kc;
+        }
+        __syncthreads();
+        K = s_K;
+        if (K == 0) {
+            if (tid == 0) { hdr[0] = 0; fix[org] = 1; }
+            return;
+        }
     }
     auto scan_items = [&](auto&& fn) {
         for (int s0 = warp * 32; s0 < AL; s0 += NW * 32) {
             const int s = s0 + lane;
             uint32_t lo = 0, n = 0;
-            if (s < AL) { const uint32_t inf = info[s]; lo = inf & 0x03FFFFFFu; n = inf >> 26; }
+            if (s < AL) {
+                uint32_t inf = info[s];
+                if (inline_dedup && inf) {                // a revisit finds its own item list in its slot
+                    const uint32_t h = (inf * 0x9E3779B1u) >> sh_ds;
+                    if (atomicExch(&s_set[h], inf) == inf) inf = 0u;
+                }
+                lo = inf & 0x03FFFFFFu; n = inf >> 26;
+            }
             uint32_t incl = n;
             #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -1511,6 +1524,11 @@ int launch_coverage_quarters(gcp_ctx* ctx, uint32_t* step_qinfo, uint32_t P, uin
         uint32_t* acc = reinterpret_cast<uint32_t*>(base + off_acc);
         uint8_t* fix = reinterpret_cast<uint8_t*>(base + off_acc + (size_t)chunk * 8);
         const uint32_t CAP = ctx->cov_split_cap > 0 ? (uint32_t)ctx->cov_split_cap : 1536u;   // items aimed at per partition
+        // partitions per organism, fixed from the genome length (~0.75 items per gene survive the dedup on the
+        // benchmark walks): the bucket kernel then filters and scatters in ONE pass.  cov_split_cap (testing) -> 0:
+        // the kernel counts first and chooses K per organism.
+        uint32_t KFIX = 0;
+        if (ctx->cov_split_cap <= 0) { KFIX = 1; while (KFIX < CB_MAXK && (size_t)KFIX * CAP * 10 < (size_t)AL * 9) KFIX <<= 1; }
         constexpr int TP = 512, MAXPP = 3072;              // block slots / item store of a partition CTA
         const size_t smem_p = (size_t)TP * 20 + (size_t)MAXPP * 8 + 32;
         // dedup table of the bucket kernel: the CTA's whole shared memory is free for it
@@ -1531,7 +1549,7 @@ int launch_coverage_quarters(gcp_ctx* ctx, uint32_t* step_qinfo, uint32_t P, uin
             uint32_t* qi = step_qinfo + (size_t)o0 * AL;
             GCP_CUDA(ctx, cudaMemsetAsync(work, 0, 16, st));
             GCP_CUDA(ctx, cudaMemsetAsync(acc, 0, (size_t)chunk * 8 + chunk, st));
-            k_cov_bucket<<<n_org, CB_THREADS, DSb * 4 + 16, st>>>(qi, n_org, ctx->t, AL, DSb, CAP, rec, rec_cap, hdr, work, fix);
+            k_cov_bucket<<<n_org, CB_THREADS, DSb * 4 + 16, st>>>(qi, n_org, ctx->t, AL, DSb, CAP, KFIX, rec, rec_cap, hdr, work, fix);
             if (gray) {
                 k_cov_part<true><<<grid_p, 256, smem_p, st>>>(ctx->t, TP, MAXPP, rec, rec_cap, work, acc, fix);
                 k_cov_quarters<1024, true><<<n_org, 1024, smem, st>>>(qi, n_org, ctx->t, AL, T, maxp, R0, DS, rec, rec_cap,
