@@ -767,6 +767,8 @@ int gcp_set_option(gcp_ctx* c, const char* name, int64_t value)
     else if (!strcmp(name, "cov_split")) c->cov_split = (int)value;
     else if (!strcmp(name, "lc_split")) c->lc_split = (int)value;
     else if (!strcmp(name, "cov_split_cap")) c->cov_split_cap = (int)value;
+    else if (!strcmp(name, "cov_split_k")) c->cov_split_k = (int)value;
+    else if (!strcmp(name, "lc_split_keys")) c->lc_split_keys = (int)value;
     else if (!strcmp(name, "lc_split_slack")) c->lc_split_slack = (int)value;
     else return gcp_fail(c, -1, "gcp_set_option: unknown option '%s'", name);
     return 0;

@@ -102,7 +102,9 @@ struct gcp_ctx {
     int cov_buckets = 1;     // 1: long genomes bucket their items by hash partition once (else: R scanning passes)
     int cov_dedup = 1;       // 1: revisited edges are dropped before the coverage union (phase B0)
     int cov_split = 1;       // 1: long genomes run their hash partitions as work items of small CTAs (k_cov_bucket / k_cov_part)
-    int cov_split_cap = 0;   // testing: items aimed at per partition (0 = 1,536); a huge value overflows every partition CTA -> fallback path
+    int cov_split_cap = 0;   // tuning / testing: items aimed at per partition (0 = 2,600); a huge value overflows every partition CTA -> fallback path
+    int lc_split_keys = 0;   // tuning: genes aimed at per loop-closure partition (0 = 640)
+    int cov_split_k = 0;     // tuning: partitions per organism fixed (power of two) instead of chosen per organism
     int lc_split_slack = 0;  // testing: stretch of a loop-closure bucket in % of the mean bucket (0 = 150); < 100 overflows -> fallback path
     int cov_threads = 0;     // tuning: CTA size of k_cov_quarters (256 / 512 / 1024; 0 = auto)
     int lc_min_parts = 0;    // tuning: at least this many hash partitions in k_loop_closures_part

@@ -1523,12 +1523,15 @@ int launch_coverage_quarters(gcp_ctx* ctx, uint32_t* step_qinfo, uint32_t P, uin
         uint32_t* work = reinterpret_cast<uint32_t*>(base + off_work);
         uint32_t* acc = reinterpret_cast<uint32_t*>(base + off_acc);
         uint8_t* fix = reinterpret_cast<uint8_t*>(base + off_acc + (size_t)chunk * 8);
-        const uint32_t CAP = ctx->cov_split_cap > 0 ? (uint32_t)ctx->cov_split_cap : 1536u;   // items aimed at per partition
-        // partitions per organism, fixed from the genome length (~0.75 items per gene survive the dedup on the
-        // benchmark walks): the bucket kernel then filters and scatters in ONE pass.  cov_split_cap (testing) -> 0:
-        // the kernel counts first and chooses K per organism.
+        // items aimed at per partition: few large work items beat many small ones (C4-32, coverage per 4,096
+        // organisms: 2.91 / 2.32 / 2.15 ms at <= 1,024 / 2,048 / 2,600 items, i.e. K = 32 / 16 / 8); 2,600 + the
+        // ~10 % imbalance of the block hash stays inside the partition CTA's store of 3,072
+        const uint32_t CAP = ctx->cov_split_cap > 0 ? (uint32_t)ctx->cov_split_cap : 2600u;
+        // cov_split_k (tuning): K fixed for all organisms - the bucket kernel then filters and scatters in ONE
+        // pass (-2 %), but an organism with more items than expected overflows into the monolithic fallback.
+        // Default 0: the kernel counts the surviving items first and chooses K per organism.
         uint32_t KFIX = 0;
-        if (ctx->cov_split_cap <= 0) { KFIX = 1; while (KFIX < CB_MAXK && (size_t)KFIX * CAP * 10 < (size_t)AL * 9) KFIX <<= 1; }
+        if (ctx->cov_split_k > 0) { KFIX = 1; while (KFIX < CB_MAXK && KFIX < (uint32_t)ctx->cov_split_k) KFIX <<= 1; }
         constexpr int TP = 512, MAXPP = 3072;              // block slots / item store of a partition CTA
         const size_t smem_p = (size_t)TP * 20 + (size_t)MAXPP * 8 + 32;
         // dedup table of the bucket kernel: the CTA's whole shared memory is free for it

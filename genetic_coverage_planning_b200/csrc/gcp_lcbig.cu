@@ -601,8 +601,9 @@ int launch_loop_closures_big(gcp_ctx* ctx, const int32_t* dna, uint32_t P, const
         }
         if (R > 1 && ctx->lc_split) {
             // split form: partitions as work items of 256-thread CTAs (see k_lc_bucket)
+            const size_t keys_per = ctx->lc_split_keys > 0 ? (size_t)ctx->lc_split_keys : 640;   // genes aimed at per partition
             uint32_t K = 2;
-            while (K < LS_MAXK && (size_t)K * 640 < AL) K <<= 1;
+            while (K < LS_MAXK && (size_t)K * keys_per < AL) K <<= 1;
             const size_t slack = ctx->lc_split_slack > 0 ? (size_t)ctx->lc_split_slack : 150;
             uint32_t region = (uint32_t)((AL * slack / 100 + K - 1) / K);   // 1.5 x the mean bucket (sigma of a bucket: ~5 % of it)
             region = (region + 7u) & ~7u;
