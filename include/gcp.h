@@ -295,8 +295,8 @@ int gcp_peer_barrier(gcp_ctx* ctx, const gcp_shards* flags, uint32_t rank, uint3
  * once; "cov_split": 0 = the hash partitions of a long genome run one after the other in the organism's
  * CTA instead of as work items of small CTAs ("lc_split": the same switch for the loop closures;
  * "cov_split_cap" (items aimed at per partition, 0 = 2,600) / "cov_split_k" (partitions per organism fixed
- * instead of chosen per organism) / "lc_split_slack": tuning and testing - e.g. force the overflow
- * fallback of the split kernels); "lc_min_parts": at least this many hash partitions in the long-genome loop-closure kernel;
+ * instead of chosen per organism) / "lc_split_keys" (genes aimed at per loop-closure partition, 0 = 640) /
+ * "lc_split_slack": tuning and testing - e.g. force the overflow fallback of the split kernels); "lc_min_parts": at least this many hash partitions in the long-genome loop-closure kernel;
  * "cov_prefetch": -1 auto (2 when the footprint store is larger than the L2, else 0) / bit 0: L2 prefetch
  * of the footprint lines while the fused kernel sorts its items / bit 1: the union stream requests its
  * lines 16 entries ahead (the one that helps on config C5).
