@@ -55,3 +55,14 @@ def test_product_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, fn)).read()
                 assert "fitness_oracle" not in txt and "ref_shim" not in txt, fn
+
+
+def test_option_names_documented_and_implemented():
+    """Every knob gcp_set_option accepts is described in include/gcp.h, and every knob the header
+    describes is accepted (the header is the only documentation a C caller has)."""
+    api = open(os.path.join(ROOT, "genetic_coverage_planning_b200", "csrc", "gcp_api.cu")).read()
+    implemented = set(re.findall(r'strcmp\(name, "([a-z_0-9]+)"\)', api))
+    hdr = open(os.path.join(ROOT, "include", "gcp.h")).read()
+    i = hdr.index("tuning / testing knobs")
+    documented = set(re.findall(r'"([a-z_0-9]+)"', hdr[i:hdr.index("int gcp_set_option", i)]))
+    assert implemented and implemented == documented, (sorted(implemented - documented), sorted(documented - implemented))
